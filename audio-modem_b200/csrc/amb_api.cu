@@ -1,0 +1,656 @@
+// C-ABI of the B200-native OFDM receive path (include/audio_modem_b200.h).
+// Host side: owns the CUDA stream, device scratch and the streaming arenas; every entry point is a fixed
+// sequence of kernel launches from amb_kernels.cuh.  There is no CPU compute path in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "amb_kernels.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct PendingCopy { void* host; const void* dev; size_t bytes; };
+
+}  // namespace
+
+struct amb_modem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    AmbTables tables;
+    AmbTables* d_tables = nullptr;
+    AmbEmaTables* d_ema = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // scratch
+    DevBuf in_a, in_b, in_c, in_lens, out_a, out_b, out_c, out_res, out_bytes;
+    DevBuf jobs, idx, xf, psum, pmin, pmax, norm, metric, tile_max, amb, cidx, cbest;
+    std::vector<PendingCopy> pending;
+    // streaming
+    bool open = false;
+    int n_streams = 0;
+    int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
+    int rec_cap = 0;
+    DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            m->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return e__ == cudaErrorMemoryAllocation ? AMB_E_NOMEM : AMB_E_CUDA;                     \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH_OK()                                                                                \
+    do {                                                                                           \
+        m->launches++;                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) { m->err = std::string("kernel launch: ") + cudaGetErrorString(e__); return AMB_E_CUDA; } \
+    } while (0)
+
+namespace {
+
+int fail(amb_modem* m, int code, const char* msg) { m->err = msg; return code; }
+
+// device view of a caller input: copies host memory into `buf`, passes device pointers through
+template <class T>
+int in_ptr(amb_modem* m, const T* src, size_t count, int mem, DevBuf& buf, const T** out) {
+    if (!src) { *out = nullptr; return AMB_OK; }
+    if (mem == AMB_MEM_DEVICE) { *out = src; return AMB_OK; }
+    CK(buf.ensure(count * sizeof(T)));
+    CK(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, m->stream));
+    *out = buf.as<T>();
+    return AMB_OK;
+}
+
+// device view of a caller output: device pointers pass through; host pointers get a staging buffer whose
+// content is copied back by flush()
+template <class T>
+int out_ptr(amb_modem* m, T* dst, size_t count, int mem, DevBuf& buf, T** out) {
+    if (!dst) { *out = nullptr; return AMB_OK; }
+    if (mem == AMB_MEM_DEVICE) { *out = dst; return AMB_OK; }
+    CK(buf.ensure(count * sizeof(T)));
+    *out = buf.as<T>();
+    m->pending.push_back({dst, buf.p, count * sizeof(T)});
+    return AMB_OK;
+}
+
+int flush(amb_modem* m) {
+    for (auto& c : m->pending) CK(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, m->stream));
+    m->pending.clear();
+    CK(cudaStreamSynchronize(m->stream));
+    return AMB_OK;
+}
+
+int check_common(amb_modem* m, int n, int64_t stride, int mem) {
+    if (!m) return AMB_E_INVALID;
+    m->pending.clear();
+    if (n < 0 || stride < 0 || (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE)) return fail(m, AMB_E_INVALID, "bad argument");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    return AMB_OK;
+}
+
+inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+// demod + parse over m->jobs (n_jobs), results/bytes already device pointers
+int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_frame_result* d_res, uint8_t* d_bytes, int64_t bytes_stride) {
+    if (n_jobs == 0) return AMB_OK;
+    const AmbTables& T = m->tables;
+    const int64_t idx_stride = (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data;
+    CK(m->idx.ensure((size_t)n_jobs * idx_stride));
+    if (frame_max) { k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs); LAUNCH_OK(); }
+    AmbDemodOut o;
+    std::memset(&o, 0, sizeof(o));
+    o.idx = m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
+    const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
+    k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o);
+    LAUNCH_OK();
+    k_parse<<<blocks_for(n_jobs, 4), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
+                                                          d_res, d_bytes, bytes_stride);
+    LAUNCH_OK();
+    return AMB_OK;
+}
+
+int64_t max_len_of(const int64_t* lens_host, int n, int64_t stride) {
+    if (!lens_host) return stride;
+    int64_t mx = 0;
+    for (int i = 0; i < n; i++) mx = lens_host[i] > mx ? lens_host[i] : mx;
+    return mx;
+}
+
+// preprocess statistics -> m->xf (AmbXform per row)
+int run_stats(amb_modem* m, const float* d_x, int64_t stride, const int64_t* d_lens, int n, int64_t max_len) {
+    const int parts = (int)((max_len + AMB_STAT_PART - 1) / AMB_STAT_PART) > 0 ? (int)((max_len + AMB_STAT_PART - 1) / AMB_STAT_PART) : 1;
+    CK(m->psum.ensure((size_t)n * parts * 8)); CK(m->pmin.ensure((size_t)n * parts * 4)); CK(m->pmax.ensure((size_t)n * parts * 4));
+    CK(m->xf.ensure((size_t)n * sizeof(AmbXform)));
+    k_stats_partial<<<n * parts, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>());
+    LAUNCH_OK();
+    k_stats_final<<<blocks_for(n, 128), 128, 0, m->stream>>>(d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>(), n, m->xf.as<AmbXform>());
+    LAUNCH_OK();
+    return AMB_OK;
+}
+
+int run_apply(amb_modem* m, const float* d_x, int64_t stride, const int64_t* d_lens, int n, int64_t max_len, float* d_out) {
+    int per = (int)((max_len + 256 * 8 - 1) / (256 * 8));
+    if (per < 1) per = 1;
+    if (per > 4096) per = 4096;
+    k_apply_xform<<<n * per, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, per, m->xf.as<AmbXform>(), d_out);
+    LAUNCH_OK();
+    return AMB_OK;
+}
+
+// Schmidl-Cox detector over rows -> m->cidx / m->cbest (device)
+int run_detect(amb_modem* m, const float* d_y, int64_t stride, const int64_t* d_lens, int n, int64_t max_len) {
+    const int tiles = (int)((max_len + AMB_TILE - 1) / AMB_TILE) > 0 ? (int)((max_len + AMB_TILE - 1) / AMB_TILE) : 1;
+    CK(m->metric.ensure((size_t)n * (size_t)stride * 8)); CK(m->tile_max.ensure((size_t)n * tiles * 8));
+    CK(m->amb.ensure((size_t)n * 4)); CK(m->cidx.ensure((size_t)n * 8)); CK(m->cbest.ensure((size_t)n * 8));
+    k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->metric.as<double>(), tiles, m->tile_max.as<double>());
+    LAUNCH_OK();
+    k_argmax<<<n, 256, 0, m->stream>>>(m->metric.as<double>(), stride, d_lens, stride, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
+                                      m->cbest.as<double>(), m->amb.as<int>());
+    LAUNCH_OK();
+    k_replay<<<blocks_for(n, 64), 64, 0, m->stream>>>(d_y, stride, d_lens, stride, n, 0.01, m->amb.as<int>(), m->cidx.as<int64_t>(), m->cbest.as<double>());
+    LAUNCH_OK();
+    return AMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amb_version(void) { return AMB_VERSION; }
+
+const char* amb_status_string(int status) {
+    switch (status) {
+        case AMB_ST_OK: return "";
+        case AMB_ST_PREAMBLE_NOT_DETECTED: return "Preamble not detected";
+        case AMB_ST_PREAMBLE_LOW_CORRELATION: return "Preamble not detected (low correlation)";
+        case AMB_ST_SIGNAL_TOO_SHORT_FOR_CE: return "Signal too short for CE";
+        case AMB_ST_NO_DATA_AFTER_CE: return "No data after CE";
+        case AMB_ST_DECODED_TOO_SHORT: return "Decoded data too short";
+        case AMB_ST_DECODED_TOO_SHORT_FOR_HEADER: return "Decoded data too short for header";
+        case AMB_ST_INVALID_DATA_LENGTH: return "Invalid data length: {arg}";
+        case AMB_ST_FRAME_TOO_SHORT_FOR_CE: return "Frame too short for CE";
+        case AMB_ST_UNKNOWN_FRAME_TYPE: return "Unknown frame type: 0x{arg:x}";
+        case AMB_ST_META_TOO_SHORT: return "Metadata frame too short";
+        case AMB_ST_META_TRUNCATED: return "Metadata frame truncated";
+        case AMB_ST_CHUNK_TOO_SHORT: return "Data chunk frame too short";
+        case AMB_ST_CHUNK_TRUNCATED: return "Data chunk truncated";
+        case AMB_ST_RING_OVERWRITTEN: return "(ring buffer overwritten)";
+    }
+    return "?";
+}
+
+int amb_create(amb_modem** out, int device, int config, int constellation, int repetition) {
+    if (!out) return AMB_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return AMB_E_NODEVICE;
+    if (device < 0 || device >= count) return AMB_E_INVALID;
+    if (constellation < 0 || constellation > 2) return AMB_E_INVALID;
+    amb_modem* m = new amb_modem();
+    m->device = device;
+    if (amb_tables_build(&m->tables, config, constellation, repetition) != 0) { delete m; return AMB_E_INVALID; }
+    auto bail = [&](int code) { amb_destroy(m); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(AMB_E_CUDA);
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(AMB_E_CUDA);
+    if (cudaMalloc(&m->d_tables, sizeof(AmbTables)) != cudaSuccess) return bail(AMB_E_NOMEM);
+    if (cudaMalloc(&m->d_ema, sizeof(AmbEmaTables)) != cudaSuccess) return bail(AMB_E_NOMEM);
+    AmbEmaTables e;
+    const long double a = (long double)m->tables.dc_alpha;
+    for (int k = 0; k < AMB_CHUNK; k++) e.w_in[k] = (double)((long double)m->tables.dc_beta * powl(a, (long double)(AMB_CHUNK - 1 - k)));
+    for (int j = 0; j <= AMB_EMA_TERMS; j++) e.w_chunk[j] = (double)powl(a, (long double)(AMB_CHUNK * j));
+    e.a16 = (double)powl(a, 16.0L); e.alpha = m->tables.dc_alpha; e.beta = m->tables.dc_beta;
+    if (cudaMemcpy(m->d_tables, &m->tables, sizeof(AmbTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
+    if (cudaMemcpy(m->d_ema, &e, sizeof(e), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
+    cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
+    cudaFuncSetAttribute(k_scan_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
+    cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
+    *out = m;
+    return AMB_OK;
+}
+
+void amb_destroy(amb_modem* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx,
+                     &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->raw, &m->cleaned,
+                     &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
+                     &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp};
+    for (DevBuf* b : all) b->release();
+    if (m->d_tables) cudaFree(m->d_tables);
+    if (m->d_ema) cudaFree(m->d_ema);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+const char* amb_last_error(const amb_modem* m) { return m ? m->err.c_str() : "null handle"; }
+int amb_synchronize(amb_modem* m) { if (!m) return AMB_E_INVALID; CK(cudaStreamSynchronize(m->stream)); return AMB_OK; }
+void* amb_cuda_stream(amb_modem* m) { return m ? (void*)m->stream : nullptr; }
+int64_t amb_kernel_launches(const amb_modem* m) { return m ? m->launches : 0; }
+
+int64_t amb_estimate_frame_samples(int config, int constellation, int64_t payload_bytes, int repetition) {
+    return amb_tables_estimate_frame_samples(config, constellation, payload_bytes, repetition);
+}
+
+int amb_config_info(int config, int32_t* out8, int32_t* pilots) {
+    AmbTables t;
+    if (amb_tables_build(&t, config, AMB_MOD_QPSK, 1) != 0) return AMB_E_INVALID;
+    out8[0] = AMB_FFT; out8[1] = t.cp_len; out8[2] = t.sym_len; out8[3] = 44100; out8[4] = t.sub_start; out8[5] = t.sub_end;
+    out8[6] = t.n_pilots; out8[7] = t.n_data;
+    if (pilots) for (int i = 0; i < t.n_pilots; i++) pilots[i] = t.pilots[i];
+    return AMB_OK;
+}
+
+int amb_preamble_symbol1(int config, float* out) {
+    AmbTables t;
+    if (amb_tables_build(&t, config, AMB_MOD_QPSK, 1) != 0) return AMB_E_INVALID;
+    std::memcpy(out, t.pre1, (size_t)t.sym_len * 4);
+    return AMB_OK;
+}
+
+int amb_channel_est_symbol(int config, float* out, double* known_re) { amb_tables_ce_symbol(config, out, known_re); return AMB_OK; }
+
+// ---------------------------------------------------------------------------------------------- batched ops
+int amb_crc32(amb_modem* m, const uint8_t* data, int64_t stride, const int64_t* lens, int n, uint32_t* out, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    const uint8_t* d_data; const int64_t* d_lens; uint32_t* d_out;
+    if ((rc = in_ptr(m, data, (size_t)n * stride, mem, m->in_a, &d_data))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    if ((rc = out_ptr(m, out, (size_t)n, mem, m->out_a, &d_out))) return rc;
+    k_crc32<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out);
+    LAUNCH_OK();
+    return flush(m);
+}
+
+int amb_preprocess_signal(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, float* out, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0 || stride == 0) return AMB_OK;
+    const float* d_x; const int64_t* d_lens; float* d_out;
+    if ((rc = in_ptr(m, x, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    if ((rc = out_ptr(m, out, (size_t)n * stride, mem, m->out_a, &d_out))) return rc;
+    const int64_t max_len = mem == AMB_MEM_HOST ? max_len_of(lens, n, stride) : stride;
+    if ((rc = run_stats(m, d_x, stride, d_lens, n, max_len))) return rc;
+    if ((rc = run_apply(m, d_x, stride, d_lens, n, max_len, d_out))) return rc;
+    return flush(m);
+}
+
+int amb_detect_preamble(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, int64_t* idx_out,
+                        double* metric_out, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    const float* d_x; const int64_t* d_lens;
+    if ((rc = in_ptr(m, x, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    const int64_t max_len = mem == AMB_MEM_HOST ? max_len_of(lens, n, stride) : stride;
+    if ((rc = run_detect(m, d_x, stride, d_lens, n, max_len))) return rc;
+    if (mem == AMB_MEM_HOST) {
+        if (idx_out) m->pending.push_back({idx_out, m->cidx.p, (size_t)n * 8});
+        if (metric_out) m->pending.push_back({metric_out, m->cbest.p, (size_t)n * 8});
+    } else {
+        if (idx_out) CK(cudaMemcpyAsync(idx_out, m->cidx.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, m->stream));
+        if (metric_out) CK(cudaMemcpyAsync(metric_out, m->cbest.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    return flush(m);
+}
+
+int amb_detect_preamble_xcorr(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, int64_t* idx_out,
+                              double* metric_out, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    const float* d_x; const int64_t* d_lens; int64_t* d_idx; double* d_best;
+    if ((rc = in_ptr(m, x, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    CK(m->cidx.ensure((size_t)n * 8)); CK(m->cbest.ensure((size_t)n * 8));
+    d_idx = m->cidx.as<int64_t>(); d_best = m->cbest.as<double>();
+    const int64_t plen = m->tables.sym_len;
+    const int64_t step = plen / 10 > 1 ? plen / 10 : 1;
+    const int64_t max_pos = stride >= plen ? (stride - plen) / step + 1 : 1;
+    CK(m->metric.ensure((size_t)n * max_pos * 8));
+    const int per = blocks_for(max_pos, 128);
+    k_xcorr_coarse<<<n * per, 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, step, per, m->metric.as<double>(), max_pos);
+    LAUNCH_OK();
+    k_xcorr_pick<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, step, m->metric.as<double>(), max_pos, d_idx, d_best);
+    LAUNCH_OK();
+    if (mem == AMB_MEM_HOST) {
+        if (idx_out) m->pending.push_back({idx_out, d_idx, (size_t)n * 8});
+        if (metric_out) m->pending.push_back({metric_out, d_best, (size_t)n * 8});
+    } else {
+        if (idx_out) CK(cudaMemcpyAsync(idx_out, d_idx, (size_t)n * 8, cudaMemcpyDeviceToDevice, m->stream));
+        if (metric_out) CK(cudaMemcpyAsync(metric_out, d_best, (size_t)n * 8, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    return flush(m);
+}
+
+int amb_estimate_channel(amb_modem* m, const float* ce, int n, const double* known_re, const double* known_im, double* ch_re,
+                         double* ch_im, int mem) {
+    int rc = check_common(m, n, m ? m->tables.sym_len : 0, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    const int64_t stride = m->tables.sym_len;
+    const float* d_ce; const double *d_kr, *d_ki; double *d_hr, *d_hi;
+    if ((rc = in_ptr(m, ce, (size_t)n * stride, mem, m->in_a, &d_ce))) return rc;
+    if ((rc = in_ptr(m, known_re, (size_t)AMB_FFT, mem, m->in_b, &d_kr))) return rc;
+    if ((rc = in_ptr(m, known_im, (size_t)AMB_FFT, mem, m->in_c, &d_ki))) return rc;
+    if ((rc = out_ptr(m, ch_re, (size_t)n * AMB_FFT, mem, m->out_a, &d_hr))) return rc;
+    if ((rc = out_ptr(m, ch_im, (size_t)n * AMB_FFT, mem, m->out_b, &d_hi))) return rc;
+    if (!d_hr || !d_hi) return fail(m, AMB_E_INVALID, "ch_re/ch_im required");
+    CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
+    k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_ce, stride, nullptr, stride, n, 1, m->jobs.as<AmbJob>());
+    LAUNCH_OK();
+    AmbDemodOut o;
+    std::memset(&o, 0, sizeof(o));
+    o.h_out_re = d_hr; o.h_out_im = d_hi; o.known_re = d_kr; o.known_im = d_ki;
+    k_demod<<<dim3(n, 1), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o);
+    LAUNCH_OK();
+    return flush(m);
+}
+
+int amb_demodulate(amb_modem* m, const float* signal, int64_t stride, const int64_t* lens, int n, const double* ch_re,
+                   const double* ch_im, uint8_t* bits, int64_t bits_stride, int64_t* nbits_out, double* eq_out, int64_t eq_stride,
+                   int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    if (!ch_re || !ch_im) return fail(m, AMB_E_INVALID, "ch_re/ch_im required");
+    const AmbTables& T = m->tables;
+    const float* d_x; const int64_t* d_lens; const double *d_hr, *d_hi; uint8_t* d_bits; double* d_eq;
+    if ((rc = in_ptr(m, signal, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    if ((rc = in_ptr(m, ch_re, (size_t)n * AMB_FFT, mem, m->in_b, &d_hr))) return rc;
+    if ((rc = in_ptr(m, ch_im, (size_t)n * AMB_FFT, mem, m->in_c, &d_hi))) return rc;
+    const int max_nsym = (int)(stride / T.sym_len);
+    if (bits && bits_stride < (int64_t)max_nsym * T.n_data * T.bps) return fail(m, AMB_E_INVALID, "bits_stride too small");
+    if (eq_out && eq_stride < (int64_t)max_nsym * T.n_data) return fail(m, AMB_E_INVALID, "eq_stride too small");
+    if ((rc = out_ptr(m, bits, (size_t)n * bits_stride, mem, m->out_a, &d_bits))) return rc;
+    if ((rc = out_ptr(m, eq_out, (size_t)n * eq_stride * 2, mem, m->out_b, &d_eq))) return rc;
+    CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
+    k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, 0, m->jobs.as<AmbJob>());
+    LAUNCH_OK();
+    if (max_nsym > 0) {
+        AmbDemodOut o;
+        std::memset(&o, 0, sizeof(o));
+        o.bits = d_bits; o.bits_stride = bits_stride; o.eq = d_eq; o.eq_stride = eq_stride; o.h_re = d_hr; o.h_im = d_hi;
+        const int groups = (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP;
+        k_demod<<<dim3(n, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o);
+        LAUNCH_OK();
+    }
+    if (nbits_out) {
+        if (mem != AMB_MEM_HOST) return fail(m, AMB_E_INVALID, "nbits_out is a host-side convenience (pass NULL with device memory)");
+        for (int i = 0; i < n; i++) nbits_out[i] = ((lens ? lens[i] : stride) / T.sym_len) * T.n_data * T.bps;
+    }
+    return flush(m);
+}
+
+int amb_decode_chunk_frames(amb_modem* m, const float* frames, int64_t stride, const int64_t* lens, int n,
+                            amb_frame_result* results, uint8_t* bytes_out, int64_t bytes_stride, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    if (!results || !bytes_out || bytes_stride <= 0) return fail(m, AMB_E_INVALID, "results/bytes_out required");
+    const AmbTables& T = m->tables;
+    const float* d_x; const int64_t* d_lens; amb_frame_result* d_res; uint8_t* d_bytes;
+    if ((rc = in_ptr(m, frames, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    if ((rc = out_ptr(m, results, (size_t)n, mem, m->out_res, &d_res))) return rc;
+    if ((rc = out_ptr(m, bytes_out, (size_t)n * bytes_stride, mem, m->out_bytes, &d_bytes))) return rc;
+    CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
+    k_jobs_chunk<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, m->jobs.as<AmbJob>());
+    LAUNCH_OK();
+    const int max_nsym = (int)(stride / T.sym_len) - 3;
+    if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
+    return flush(m);
+}
+
+int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n,
+                                amb_frame_result* results, uint8_t* bytes_out, int64_t bytes_stride, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    if (!results || !bytes_out || bytes_stride <= 0) return fail(m, AMB_E_INVALID, "results/bytes_out required");
+    const AmbTables& T = m->tables;
+    const float* d_x; const int64_t* d_lens; amb_frame_result* d_res; uint8_t* d_bytes;
+    if ((rc = in_ptr(m, x, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    if ((rc = out_ptr(m, results, (size_t)n, mem, m->out_res, &d_res))) return rc;
+    if ((rc = out_ptr(m, bytes_out, (size_t)n * bytes_stride, mem, m->out_bytes, &d_bytes))) return rc;
+    const int64_t max_len = mem == AMB_MEM_HOST ? max_len_of(lens, n, stride) : stride;
+    CK(m->norm.ensure((size_t)n * stride * 4));
+    if ((rc = run_stats(m, d_x, stride, d_lens, n, max_len))) return rc;
+    if ((rc = run_apply(m, d_x, stride, d_lens, n, max_len, m->norm.as<float>()))) return rc;
+    if ((rc = run_detect(m, m->norm.as<float>(), stride, d_lens, n, max_len))) return rc;
+    CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
+    k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
+                                                             m->cbest.as<double>(), m->jobs.as<AmbJob>());
+    LAUNCH_OK();
+    const int max_nsym = (int)(max_len / T.sym_len);
+    if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
+    return flush(m);
+}
+
+// ---------------------------------------------------------------------------------------------- streaming
+int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push) {
+    if (!m) return AMB_E_INVALID;
+    if (n_streams <= 0 || block_len <= 0 || max_push <= 0) return fail(m, AMB_E_INVALID, "bad stream geometry");
+    if (block_len != AMB_TILE) return fail(m, AMB_E_INVALID, "block_len must be 4096 (the reference's ScriptProcessor block, app.js:1107)");
+    if (max_push % block_len) return fail(m, AMB_E_INVALID, "max_push must be a multiple of block_len");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    if (m->open) amb_stream_close(m);
+    const AmbTables& T = m->tables;
+    m->n_streams = n_streams; m->block_len = block_len; m->max_push = max_push;
+    // RingBuffer capacity, app.js:712-715
+    m->ring_cap = amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 4096 + 16, T.rep) * 3 + 8192;
+    // history kept in the arena: the ring, one more block (reads happen while a call's samples are being added),
+    // the refine radius and a tile of slack, rounded to whole tiles
+    int64_t h = m->ring_cap + block_len + T.fine_radius + T.sym_len + 2 * AMB_TILE;
+    m->hist = (h + AMB_TILE - 1) / AMB_TILE * AMB_TILE;
+    m->stride = m->hist + max_push;
+    m->base_g = -m->hist;
+    m->written = 0;
+    m->sum_stride = m->stride / 256;
+    const int64_t min_frame = amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 280, T.rep) < amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 11, T.rep)
+                                  ? amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 280, T.rep)
+                                  : amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 11, T.rep);
+    m->rec_cap = (int)(max_push / min_frame) + 3;
+    const size_t ns = (size_t)n_streams;
+    CK(m->raw.ensure(ns * m->stride * 4)); CK(m->cleaned.ensure(ns * m->stride * 4));
+    CK(m->sums.ensure(ns * m->sum_stride * AMB_SUM_W * 4));
+    CK(m->agg.ensure(ns * (size_t)(max_push / AMB_CHUNK) * 8)); CK(m->dc_next.ensure(ns * 8));
+    CK(m->states.ensure(ns * sizeof(AmbStreamState))); CK(m->recs.ensure(ns * m->rec_cap * sizeof(AmbFrameRec)));
+    CK(m->nrec.ensure(ns * 4)); CK(m->job_off.ensure(ns * 4)); CK(m->total.ensure(16)); CK(m->redo.ensure(ns * 4)); CK(m->n_redo.ensure(16));
+    CK(cudaMemsetAsync(m->raw.p, 0, ns * m->stride * 4, m->stream));
+    CK(cudaMemsetAsync(m->cleaned.p, 0, ns * m->stride * 4, m->stream));
+    CK(cudaMemsetAsync(m->sums.p, 0, ns * m->sum_stride * AMB_SUM_W * 4, m->stream));
+    CK(cudaMemsetAsync(m->dc_next.p, 0, ns * 8, m->stream));
+    std::vector<AmbStreamState> init(ns);
+    std::memset(init.data(), 0, ns * sizeof(AmbStreamState));
+    for (auto& s : init) { s.pre_pos = -1; s.frame_end = -1; }
+    CK(cudaMemcpyAsync(m->states.p, init.data(), ns * sizeof(AmbStreamState), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->open = true;
+    return AMB_OK;
+}
+
+int amb_stream_close(amb_modem* m) {
+    if (!m) return AMB_E_INVALID;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
+                     &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp};
+    for (DevBuf* b : all) b->release();
+    m->open = false;
+    return AMB_OK;
+}
+
+int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride) {
+    if (!m || !m->open) return m ? fail(m, AMB_E_STATE, "stream not open") : AMB_E_INVALID;
+    if (dev_ptr) *dev_ptr = m->raw.as<float>() + (m->written - m->base_g);
+    if (stride) *stride = m->stride;
+    return AMB_OK;
+}
+
+static int stream_compact(amb_modem* m) {
+    // keep `hist` samples of history: move [written - hist, written) to the arena front (raw, cleaned, summaries).
+    // Source and destination rows overlap when the push was shorter than the history, so go through a scratch copy.
+    const int64_t off = m->written - m->base_g;        // arena index of the next sample
+    if (off == m->hist) return AMB_OK;
+    const int64_t shift = off - m->hist;               // multiple of 4096
+    const size_t row = (size_t)m->hist * 4;
+    CK(m->ctmp.ensure((size_t)m->n_streams * row));
+    float* bases[2] = {m->raw.as<float>(), m->cleaned.as<float>()};
+    for (float* b : bases) {
+        CK(cudaMemcpy2DAsync(m->ctmp.p, row, b + shift, (size_t)m->stride * 4, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+        CK(cudaMemcpy2DAsync(b, (size_t)m->stride * 4, m->ctmp.p, row, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    const size_t srow = (size_t)(m->hist / 256) * AMB_SUM_W * 4;
+    CK(cudaMemcpy2DAsync(m->ctmp.p, srow, m->sums.as<float>() + (shift / 256) * AMB_SUM_W, (size_t)m->sum_stride * AMB_SUM_W * 4, srow, m->n_streams,
+                         cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpy2DAsync(m->sums.p, (size_t)m->sum_stride * AMB_SUM_W * 4, m->ctmp.p, srow, srow, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    m->base_g += shift;
+    return AMB_OK;
+}
+
+int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
+    if (!m) return AMB_E_INVALID;
+    m->pending.clear();
+    if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
+    if (n_new <= 0 || n_new > m->max_push || n_new % m->block_len) return fail(m, AMB_E_INVALID, "n_new must be a positive multiple of block_len, at most max_push");
+    if (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE && mem != AMB_MEM_INPLACE) return fail(m, AMB_E_INVALID, "bad mem");
+    if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
+    if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    const AmbTables& T = m->tables;
+    const int ns = m->n_streams;
+    const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
+    if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
+    float* raw = m->raw.as<float>();
+    if (mem != AMB_MEM_INPLACE) {
+        if (!x) return fail(m, AMB_E_INVALID, "x required");
+        CK(cudaMemcpy2DAsync(raw + off0, (size_t)m->stride * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
+                             mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
+    }
+    // 1. DC removal
+    const int64_t n_chunks = n_new / AMB_CHUNK;
+    const int per = blocks_for(n_chunks, 4);
+    k_ema_agg<<<ns * per, 128, 0, m->stream>>>(raw, m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>());
+    LAUNCH_OK();
+    k_ema_apply<<<ns * per, 128, 0, m->stream>>>(raw, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
+                                                 m->states.as<AmbStreamState>(), m->dc_next.as<double>());
+    LAUNCH_OK();
+    // 2. window-sum summaries of the new window-end samples
+    const int tiles = (int)(n_new / AMB_TILE);
+    k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride);
+    LAUNCH_OK();
+    // 3. walk / decode / apply, repeated for streams whose collection window changed
+    AmbStreamGeom g;
+    g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
+    g.sum_lo = m->base_g > 0 ? m->base_g : 0; g.block_len = m->block_len; g.ring_cap = m->ring_cap;
+    g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
+    int n_out = 0;
+    int n_todo = ns;
+    const int* todo = nullptr;
+    int rc = AMB_OK;
+    amb_frame_result* dst_res = results;
+    uint8_t* dst_bytes = bytes_out;
+    if (results_mem == AMB_MEM_HOST) {
+        if (results) { CK(m->g_res.ensure((size_t)(max_results > 0 ? max_results : 1) * sizeof(amb_frame_result))); dst_res = m->g_res.as<amb_frame_result>(); }
+        if (bytes_out) { CK(m->g_bytes.ensure((size_t)(max_results > 0 ? max_results : 1) * bytes_stride)); dst_bytes = m->g_bytes.as<uint8_t>(); }
+    }
+    CK(m->jobs.ensure((size_t)ns * m->rec_cap * sizeof(AmbJob)));
+    CK(m->s_sel.ensure((size_t)ns * 4));
+    for (int pass = 0; pass < 64 && n_todo > 0; pass++) {
+        CK(cudaMemsetAsync(m->nrec.p, 0, (size_t)ns * 4, m->stream));
+        CK(cudaMemsetAsync(m->n_redo.p, 0, 4, m->stream));
+        CK(cudaMemsetAsync(m->total.p, 0, 16, m->stream));
+        k_walk<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+                                                             m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>());
+        LAUNCH_OK();
+        k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>());
+        LAUNCH_OK();
+        k_jobs_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
+                                                                  m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1);
+        LAUNCH_OK();
+        int tot[2] = {0, 0};   // frames, max data symbols
+        CK(cudaMemcpyAsync(tot, m->total.p, 8, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        const int total = tot[0];
+        if (total == 0) break;
+        CK(m->s_res.ensure((size_t)total * sizeof(amb_frame_result)));
+        CK(m->s_bytes.ensure((size_t)total * bytes_stride));
+        CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
+        CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
+        if ((rc = run_demod_parse(m, total, tot[1], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
+        k_post_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+                                                                  m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
+                                                                  m->redo.as<int>(), m->n_redo.as<int>());
+        LAUNCH_OK();
+        k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2);
+        LAUNCH_OK();
+        k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
+                                               bytes_stride, n_out, max_results, dst_res, dst_bytes);
+        LAUNCH_OK();
+        int kept = 0, n_redo = 0;
+        CK(cudaMemcpyAsync(&kept, m->total.as<int>() + 2, 4, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(&n_redo, m->n_redo.p, 4, cudaMemcpyDeviceToHost, m->stream));
+        if (n_redo > ns) n_redo = ns;
+        CK(cudaStreamSynchronize(m->stream));
+        n_out += kept;
+        n_todo = n_redo;
+        if (n_todo > 0) {
+            // the redo list is rewritten by the next k_post_stream while k_walk may still read it: copy it aside
+            CK(cudaMemcpyAsync(m->s_sel.p, m->redo.p, (size_t)n_todo * 4, cudaMemcpyDeviceToDevice, m->stream));
+            todo = m->s_sel.as<int>();
+        }
+    }
+    const bool overflow = n_out > max_results;
+    if (results_mem == AMB_MEM_HOST) {
+        const int n_copy = n_out < max_results ? n_out : max_results;
+        if (n_copy > 0 && results) CK(cudaMemcpyAsync(results, m->g_res.p, (size_t)n_copy * sizeof(amb_frame_result), cudaMemcpyDeviceToHost, m->stream));
+        if (n_copy > 0 && bytes_out) CK(cudaMemcpyAsync(bytes_out, m->g_bytes.p, (size_t)n_copy * bytes_stride, cudaMemcpyDeviceToHost, m->stream));
+    }
+    m->written += n_new;
+    *n_results = n_out;
+    if ((rc = stream_compact(m))) return rc;
+    CK(cudaStreamSynchronize(m->stream));
+    return overflow ? AMB_E_OVERFLOW : AMB_OK;
+}
+
+int amb_stream_counters(amb_modem* m, int stream, int64_t* out8) {
+    if (!m || !out8) return AMB_E_INVALID;
+    if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
+    if (stream >= m->n_streams) return fail(m, AMB_E_INVALID, "bad stream index");
+    std::vector<AmbStreamState> st((size_t)m->n_streams);
+    CK(cudaMemcpyAsync(st.data(), m->states.p, st.size() * sizeof(AmbStreamState), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < 8; i++) out8[i] = 0;
+    for (int s = 0; s < m->n_streams; s++) {
+        if (stream >= 0 && s != stream) continue;
+        out8[0] += st[s].frames_decoded; out8[1] += st[s].frame_errors; out8[2] += st[s].false_pos; out8[3] += st[s].received;
+        out8[4] += st[s].crc_errors; out8[5] += st[s].dups; out8[6] += st[s].meta_received; out8[7] += st[s].written;
+    }
+    return AMB_OK;
+}
+
+}  // extern "C"

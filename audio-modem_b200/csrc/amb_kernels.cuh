@@ -1,0 +1,788 @@
+// CUDA kernels of the OFDM receive path (sm_100a).  See DESIGN.md for the data layout and the
+// bytes-per-sample budget of each kernel.  None of this is a dense contraction: no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "amb_walker.cuh"
+
+#define AMB_TILE 4096        // samples per scan tile (= the reference's audio block, app.js:1107)
+#define AMB_CHUNK 512        // EMA carry granularity
+#define AMB_EMA_TERMS 80     // alpha^(512*80) ~ 1.6e-18: older chunks cannot change a float64 EMA
+#define AMB_SYM_GROUP 64     // data symbols per demod CTA
+#define AMB_HALO 512
+// 1-D grids: blockIdx.x = outer * per + inner (gridDim.y would cap streams at 65535)
+#define AMB_SPLIT_BID(per, outer, inner) \
+    const int outer = (int)(blockIdx.x / (unsigned)(per)); \
+    const int inner = (int)(blockIdx.x % (unsigned)(per));
+
+// ------------------------------------------------------------------------------------------------
+// warp reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_minf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_maxd(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ================================================================================================
+// EMA DC removal (app.js:750-755):  m <- alpha*m + beta*x,  cleaned = f32(x - m)
+// The recurrence is linear, so the state entering 512-sample chunk c of a push is
+//   m_c = alpha^(512 c) m_0 + sum_{i<c} alpha^(512 (c-1-i)) B_i,   B_i = sum_k beta alpha^(511-k) x_{512 i + k}
+// and terms older than 80 chunks are below float64 resolution.  k_ema_agg computes B_i (one warp per
+// chunk); k_ema_apply rebuilds m_c from at most 80 aggregates, then each lane runs 16 samples and the
+// lane carries are chained in lane order.  Regrouped float64 sums differ from the sequential recurrence
+// by ~1e-16 relative: the float32 rounding of x - m flips for about one sample in 1e9.
+// ================================================================================================
+struct AmbEmaTables {
+    double w_in[AMB_CHUNK];            // beta * alpha^(511-k)
+    double w_chunk[AMB_EMA_TERMS + 1]; // alpha^(512 j)
+    double a16;                        // alpha^16
+    double alpha, beta;
+};
+
+__global__ void k_ema_agg(const float* __restrict__ x, int64_t stride, int64_t off0, int64_t n_chunks, int per,
+                          const AmbEmaTables* __restrict__ E, double* __restrict__ agg) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AMB_SPLIT_BID(per, s, cb)
+    const int64_t c = (int64_t)cb * (blockDim.x >> 5) + warp;
+    if (c >= n_chunks) return;
+    const float* p = x + (int64_t)s * stride + off0 + c * AMB_CHUNK;
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < AMB_CHUNK / 32; t++) {
+        const int k = t * 32 + lane;
+        acc = fma(E->w_in[k], (double)p[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) agg[(int64_t)s * n_chunks + c] = acc;
+}
+
+__global__ void k_ema_apply(const float* __restrict__ x, float* __restrict__ cleaned, int64_t stride, int64_t off0,
+                            int64_t n_chunks, int per, const AmbEmaTables* __restrict__ E, const double* __restrict__ agg,
+                            const AmbStreamState* __restrict__ states, double* __restrict__ dc_next) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AMB_SPLIT_BID(per, s, cb)
+    const int64_t c = (int64_t)cb * (blockDim.x >> 5) + warp;
+    if (c >= n_chunks) return;
+    const double alpha = E->alpha, beta = E->beta, a16 = E->a16;
+    double part = 0.0;
+    for (int j = lane; j < AMB_EMA_TERMS && j < c; j += 32)
+        part = fma(E->w_chunk[j], agg[(int64_t)s * n_chunks + (c - 1 - j)], part);
+    double m = warp_sum(part);
+    if (c <= AMB_EMA_TERMS) m = fma(E->w_chunk[c], states[s].dc_mean, m);
+    const int64_t at = (int64_t)s * stride + off0 + c * AMB_CHUNK + lane * 16;
+    float xv[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = reinterpret_cast<const float4*>(x + at)[q];
+        xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+    }
+    double bl = 0.0;   // lane-local response from a zero state
+#pragma unroll
+    for (int t = 0; t < 16; t++) bl = fma(alpha, bl, beta * (double)xv[t]);
+    double carry = m, my_in = m;
+    for (int u = 0; u < 32; u++) {
+        const double bu = __shfl_sync(0xffffffffu, bl, u);
+        if (lane == u) my_in = carry;
+        carry = fma(a16, carry, bu);
+    }
+    double mm = my_in;
+    float out[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        mm = fma(alpha, mm, beta * (double)xv[t]);
+        out[t] = (float)((double)xv[t] - mm);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        reinterpret_cast<float4*>(cleaned + at)[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    if (c == n_chunks - 1 && lane == 31) dc_next[s] = mm;
+}
+
+// ================================================================================================
+// Window-sum prefix machinery shared by the streaming summary scan and the batch metric kernel.
+// A CTA of 256 threads owns 4096 consecutive window-END samples q (tile), i.e. the windows
+// d = q - 511, and needs samples [t0 - 512, t0 + 4096).  c[] holds them (index 0 = sample t0 - 512);
+// ST/SQ are float64 exclusive prefix sums of c[i]*c[i+256] and c[i]^2.  Window at local index
+// dl = d - (t0 - 512):  P = ST[dl+256]-ST[dl], Ra = SQ[dl+256]-SQ[dl], Rb = SQ[dl+512]-SQ[dl+256].
+// ================================================================================================
+#define AMB_SPAN (AMB_TILE + AMB_HALO)            // 4608 samples
+#define AMB_PER_THREAD (AMB_SPAN / 256)           // 18
+#define AMB_SCAN_SMEM (AMB_SPAN * 4 + (AMB_SPAN + 1) * 8 * 2 + 256 * 8 * 2 + 64)
+
+__device__ __forceinline__ void block_prefix(const float* c, double* ST, double* SQ, double* tot_t, double* tot_q) {
+    const int tid = threadIdx.x;
+    const int i0 = tid * AMB_PER_THREAD;
+    double st = 0.0, sq = 0.0;
+#pragma unroll
+    for (int t = 0; t < AMB_PER_THREAD; t++) {
+        const int i = i0 + t;
+        const double v = (double)c[i];
+        const double w = (i + AMB_HALF < AMB_SPAN) ? (double)c[i + AMB_HALF] : 0.0;
+        ST[i] = st; SQ[i] = sq;
+        st = fma(v, w, st); sq = fma(v, v, sq);
+    }
+    tot_t[tid] = st; tot_q[tid] = sq;
+    __syncthreads();
+    // inclusive Hillis-Steele scan of the 256 thread totals
+    for (int o = 1; o < 256; o <<= 1) {
+        double a = 0.0, b = 0.0;
+        if (tid >= o) { a = tot_t[tid - o]; b = tot_q[tid - o]; }
+        __syncthreads();
+        if (tid >= o) { tot_t[tid] += a; tot_q[tid] += b; }
+        __syncthreads();
+    }
+    const double ot = tid ? tot_t[tid - 1] : 0.0, oq = tid ? tot_q[tid - 1] : 0.0;
+#pragma unroll
+    for (int t = 0; t < AMB_PER_THREAD; t++) { ST[i0 + t] += ot; SQ[i0 + t] += oq; }
+    if (tid == 255) { ST[AMB_SPAN] = tot_t[255]; SQ[AMB_SPAN] = tot_q[255]; }
+    __syncthreads();
+}
+
+// Streaming summary scan.  cleaned: arena [n_streams][stride]; tile t of the push covers window-end samples
+// [off0 + 4096 t, +4096) in arena coordinates; g0 = global sample index of arena index off0.
+// sums: [n_streams][sum_stride][5]; summary tile index of arena sample a is a >> 8.
+__global__ void __launch_bounds__(256) k_scan_sums(const float* __restrict__ cleaned, int64_t stride, int64_t off0, int64_t g0, int per,
+                                                    float* __restrict__ sums, int64_t sum_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* c = reinterpret_cast<float*>(smem_raw);
+    double* ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
+    double* SQ = ST + (AMB_SPAN + 1);
+    double* tot_t = SQ + (AMB_SPAN + 1);
+    double* tot_q = tot_t + 256;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    AMB_SPLIT_BID(per, s, tile)
+    const int64_t a0 = off0 + (int64_t)tile * AMB_TILE;         // arena index of the tile's first window-end sample
+    const float* src = cleaned + (int64_t)s * stride;
+    for (int i = tid; i < AMB_SPAN; i += 256) {
+        const int64_t a = a0 - AMB_HALO + i;
+        c[i] = a >= 0 ? src[a] : 0.0f;
+    }
+    __syncthreads();
+    block_prefix(c, ST, SQ, tot_t, tot_q);
+    __shared__ float red[8][5];
+    for (int jj = 0; jj < AMB_TILE / 256; jj++) {
+        const int dl = jj * 256 + 1 + tid;                             // window start, local index
+        const int64_t d_global = g0 + (int64_t)tile * AMB_TILE - AMB_HALO + dl;
+        float ap = 0.f, mnA = 3.0e38f, mxA = 0.f, mnB = 3.0e38f, mxB = 0.f;
+        if (d_global >= 0) {
+            const double P = ST[dl + 256] - ST[dl], A = SQ[dl + 256] - SQ[dl], B = SQ[dl + 512] - SQ[dl + 256];
+            ap = (float)fabs(P); mnA = mxA = (float)A; mnB = mxB = (float)B;
+        }
+        ap = warp_maxf(ap); mnA = warp_minf(mnA); mxA = warp_maxf(mxA); mnB = warp_minf(mnB); mxB = warp_maxf(mxB);
+        if (lane == 0) { red[warp][0] = ap; red[warp][1] = mnA; red[warp][2] = mxA; red[warp][3] = mnB; red[warp][4] = mxB; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; w++) {
+                ap = fmaxf(ap, red[w][0]); mnA = fminf(mnA, red[w][1]); mxA = fmaxf(mxA, red[w][2]);
+                mnB = fminf(mnB, red[w][3]); mxB = fmaxf(mxB, red[w][4]);
+            }
+            float* o = sums + ((int64_t)s * sum_stride + ((a0 >> 8) + jj)) * AMB_SUM_W;
+            o[0] = ap; o[1] = mnA; o[2] = mxA; o[3] = mnB; o[4] = mxB;
+        }
+        __syncthreads();
+    }
+}
+
+// ================================================================================================
+// Walker launch: one warp per stream.
+// ================================================================================================
+struct AmbStreamGeom {
+    int64_t stride;        // floats per stream in the arenas
+    int64_t base_g;        // global sample index of arena index 0
+    int64_t avail_hi;      // global index one past the last written sample
+    int64_t sum_stride;    // summary tiles per stream
+    int64_t sum_lo;        // summaries valid for q >= sum_lo (global)
+    int64_t block_len, ring_cap;
+    int64_t k_end;         // calls [state.next_call, k_end) are processed
+    int rec_cap;           // frame records per stream
+};
+
+__global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                                              const float* __restrict__ sums, AmbStreamState* __restrict__ states,
+                                              const double* __restrict__ dc_next, const int* __restrict__ todo /*stream list or NULL*/,
+                                              int n_todo, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec) {
+    __shared__ AmbWalkScratch scratch[4];
+    const int warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + warp;
+    if (w >= n_todo) return;
+    const int s = todo ? todo[w] : w;
+    AmbStreamState st = states[s];
+    AmbWalkGeom G;
+    G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+    AmbSig sig;
+    sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
+    sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+    const int n = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, recs + (int64_t)s * g.rec_cap,
+                           g.rec_cap, &scratch[warp]);
+    if ((threadIdx.x & 31) == 0) {
+        st.dc_mean = dc_next[s];
+        st.written = g.avail_hi;
+        states[s] = st;
+        nrec[s] = n;
+    }
+}
+
+// ================================================================================================
+// Demodulation jobs.  A job is one frame: CE symbol + nsym data symbols read from a float32 span through
+// a sample transform.  k_frame_max fills the per-frame peak for SCALE jobs (app.js:918-925), k_demod runs
+// the float64-faithful symbol pipeline (one warp per symbol, 8 warps per CTA), k_parse votes, packs,
+// parses and checks the CRC (one warp per frame).
+// ================================================================================================
+struct AmbJob {
+    const float* p;          // span pointer (arena row / caller row)
+    int64_t base, lo, hi;    // AmbSig geometry
+    int64_t pos;             // global position of preamble-1 (frame start)
+    int64_t len;             // frame length in samples (SCALE: normalisation span)
+    int64_t ce_pos;          // CE symbol start
+    int64_t data_pos;        // first data symbol
+    int32_t nsym;            // data symbols to demodulate
+    int32_t status;          // preset status (non-zero: skip demod)
+    int32_t stream;
+    int32_t mode;            // 0: decodeChunkFrame tail, 1: decodeReceivedSignal tail
+    AmbXform xf;
+    double coarse, fine;
+    int64_t result_pos;      // preamble_idx to report (-1: none)
+};
+
+__global__ void k_frame_max(AmbJob* __restrict__ jobs, int n_jobs) {
+    const int j = blockIdx.x;
+    if (j >= n_jobs) return;
+    AmbJob& J = jobs[j];
+    if (J.xf.kind != AMB_XF_SCALE || J.status != 0) return;
+    float mx = 0.f;
+    for (int64_t i = threadIdx.x; i < J.len; i += blockDim.x) {
+        const int64_t g = J.pos + i;
+        const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
+        mx = fmaxf(mx, fabsf(v));
+    }
+    __shared__ float red[32];
+    mx = warp_maxf(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmaxf(mx, red[w]);
+        J.xf.mx = mx;
+    }
+}
+
+struct AmbDemodOut {
+    uint8_t* idx;        // [n_jobs][idx_stride] constellation index per data subcarrier
+    int64_t idx_stride;
+    uint8_t* bits;       // optional [n_jobs][bits_stride] one byte per bit
+    int64_t bits_stride;
+    double* eq;          // optional [n_jobs][eq_stride][2]
+    int64_t eq_stride;
+    const double* h_re;  // optional externally supplied channel [n_jobs][512] (amb_demodulate)
+    const double* h_im;
+    double* h_out_re;    // optional channel output [n_jobs][512] (amb_estimate_channel)
+    double* h_out_im;
+    const double* known_re;  // optional override of the CE known symbol [512]
+    const double* known_im;
+};
+
+#define AMB_DEMOD_WARPS 8
+#define AMB_DEMOD_SMEM (AMB_DEMOD_WARPS * 2 * AMB_FFT * 8 + 2 * AMB_FFT * 8 + 2 * AMB_FFT * 8 + AMB_DEMOD_WARPS * 2 * AMB_MAX_PILOTS * 8)
+
+__global__ void __launch_bounds__(256) k_demod(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
+                                                AmbDemodOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* work = reinterpret_cast<double*>(smem_raw);                       // per warp: re[512], im[512]
+    double* tw_re = work + AMB_DEMOD_WARPS * 2 * AMB_FFT;
+    double* tw_im = tw_re + AMB_FFT;
+    double* h_re = tw_im + AMB_FFT;
+    double* h_im = h_re + AMB_FFT;
+    double* qs = h_im + AMB_FFT;
+    const int j = blockIdx.x;
+    if (j >= n_jobs) return;
+    const AmbJob J = jobs[j];
+    if (J.status != 0) return;
+    const int g0 = blockIdx.y * AMB_SYM_GROUP;
+    const bool ce_only = out.h_out_re != nullptr;
+    if (!ce_only && g0 >= J.nsym) return;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < AMB_FFT; i += blockDim.x) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+    __syncthreads();
+    AmbSig sig;
+    sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
+    double* re = work + warp * 2 * AMB_FFT;
+    double* im = re + AMB_FFT;
+    if (out.h_re) {
+        for (int i = threadIdx.x; i < AMB_FFT; i += blockDim.x) { h_re[i] = out.h_re[(int64_t)j * AMB_FFT + i]; h_im[i] = out.h_im[(int64_t)j * AMB_FFT + i]; }
+    } else if (warp == 0) {
+        amb_fft512_load(sig, J.ce_pos + T->cp_len, re, im);
+        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+        amb_channel_from_spectrum(re, im, out.known_re ? out.known_re : T->known_re, out.known_re ? out.known_im : nullptr,
+                                  T->sub_start, T->sub_end, h_re, h_im);
+    }
+    __syncthreads();
+    if (ce_only) {
+        if (blockIdx.y == 0)
+            for (int i = threadIdx.x; i < AMB_FFT; i += blockDim.x) { out.h_out_re[(int64_t)j * AMB_FFT + i] = h_re[i]; out.h_out_im[(int64_t)j * AMB_FFT + i] = h_im[i]; }
+        return;
+    }
+    const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
+    for (int sidx = g0 + warp; sidx < s_end; sidx += AMB_DEMOD_WARPS) {
+        amb_fft512_load(sig, J.data_pos + (int64_t)sidx * T->sym_len + T->cp_len, re, im);
+        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+        const int64_t e0 = (int64_t)sidx * T->n_data;
+        amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS,
+                         out.idx ? out.idx + (int64_t)j * out.idx_stride + e0 : nullptr,
+                         out.bits ? out.bits + (int64_t)j * out.bits_stride + e0 * T->bps : nullptr,
+                         out.eq ? out.eq + ((int64_t)j * out.eq_stride + e0) * 2 : nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
+                                                const uint8_t* __restrict__ idx, int64_t idx_stride, amb_frame_result* __restrict__ results,
+                                                uint8_t* __restrict__ bytes_out, int64_t bytes_stride) {
+    const int warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 4 + warp;
+    if (j >= n_jobs) return;
+    const AmbJob J = jobs[j];
+    amb_frame_result r;
+    amb_result_clear(&r);
+    r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
+    if (J.status != 0) {
+        r.status = J.status;
+        if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
+        if ((threadIdx.x & 31) == 0) results[j] = r;
+        return;
+    }
+    uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
+    const int64_t n_elems = (int64_t)J.nsym * T->n_data;
+    const int64_t nb_full = amb_num_bytes(n_elems, T->bps, T->rep);
+    amb_pack_bytes(idx + (int64_t)j * idx_stride, n_elems, T->bps, T->rep, bytes, bytes_stride);
+    if ((threadIdx.x & 31) == 0) {
+        const int64_t nb = nb_full < bytes_stride ? nb_full : bytes_stride;
+        if (J.mode == 0) amb_parse_chunk_frame(T->crc_table, bytes, nb, &r);
+        else amb_parse_received(T->crc_table, bytes, nb, &r);
+        r.n_bytes = (int32_t)nb_full;
+        // decodeReceivedSignal attaches preambleIdx to chunk-type results even when their parser failed (modem.js:611-619)
+        const bool chunk_type = nb >= 10 && (bytes[0] == AMB_FRAME_META || bytes[0] == AMB_FRAME_DATA);
+        if (J.mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = J.result_pos;
+        results[j] = r;
+    }
+}
+
+// ================================================================================================
+// Batch mode (decodeReceivedSignal / detectPreamble on whole recordings)
+// ================================================================================================
+struct AmbRec { const float* p; int64_t n; };   // one recording
+
+// pass 1 of preprocessSignal (modem.js:215-217): partial float64 sums, min and max per 64K-sample part
+#define AMB_STAT_PART 65536
+__global__ void __launch_bounds__(256) k_stats_partial(const float* __restrict__ x, int64_t stride, const int64_t* __restrict__ lens,
+                                                        int64_t n_default, int parts, double* __restrict__ psum, float* __restrict__ pmin,
+                                                        float* __restrict__ pmax) {
+    AMB_SPLIT_BID(parts, r, part)
+    const int64_t n = lens ? lens[r] : n_default;
+    const int64_t a = (int64_t)part * AMB_STAT_PART, b = min(n, a + AMB_STAT_PART);
+    const float* p = x + (int64_t)r * stride;
+    double s = 0.0;
+    float mn = 3.0e38f, mx = -3.0e38f;
+    for (int64_t i = a + threadIdx.x; i < b; i += 256) { const float v = p[i]; s += (double)v; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+    __shared__ double rs[8];
+    __shared__ float rmn[8], rmx[8];
+    s = warp_sum(s); mn = warp_minf(mn); mx = warp_maxf(mx);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rmn[threadIdx.x >> 5] = mn; rmx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { s += rs[w]; mn = fminf(mn, rmn[w]); mx = fmaxf(mx, rmx[w]); }
+        psum[(int64_t)r * parts + part] = s; pmin[(int64_t)r * parts + part] = mn; pmax[(int64_t)r * parts + part] = mx;
+    }
+}
+
+// mean = sum/N; mx = max |f32(x - mean)| = max(|f32(xmax-mean)|, |f32(xmin-mean)|) because rounding is monotone
+__global__ void k_stats_final(const int64_t* __restrict__ lens, int64_t n_default, int parts, const double* __restrict__ psum,
+                              const float* __restrict__ pmin, const float* __restrict__ pmax, int n, AmbXform* __restrict__ xf) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    const int used = (int)((len + AMB_STAT_PART - 1) / AMB_STAT_PART);
+    double s = 0.0;
+    float mn = 3.0e38f, mx = -3.0e38f;
+    for (int i = 0; i < used; i++) { s += psum[(int64_t)r * parts + i]; mn = fminf(mn, pmin[(int64_t)r * parts + i]); mx = fmaxf(mx, pmax[(int64_t)r * parts + i]); }
+    AmbXform o;
+    o.kind = AMB_XF_PRE;
+    o.mean = len > 0 ? s / (double)len : 0.0;
+    const float hi = fabsf((float)((double)mx - o.mean)), lo = fabsf((float)((double)mn - o.mean));
+    o.mx = len > 0 ? fmaxf(hi, lo) : 0.f;
+    xf[r] = o;
+}
+
+__global__ void k_apply_xform(const float* __restrict__ x, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int per,
+                              const AmbXform* __restrict__ xf, float* __restrict__ out) {
+    AMB_SPLIT_BID(per, r, blk)
+    const int64_t n = lens ? lens[r] : n_default;
+    const AmbXform f = xf[r];
+    for (int64_t i = (int64_t)blk * blockDim.x + threadIdx.x; i < n; i += (int64_t)per * blockDim.x)
+        out[(int64_t)r * stride + i] = amb_xform(f, x[(int64_t)r * stride + i]);
+}
+
+// Schmidl-Cox metric at every offset of a recording (modem.js:304-309), float64, gate = min_energy.
+// tile t covers window-end samples [4096 t, +4096), i.e. offsets d = q - 511.  metric[d] = -1 where the
+// gate fails.  Also writes the per-tile maximum.
+__global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
+                                                 int64_t n_default, double min_energy, double* __restrict__ metric, int tiles,
+                                                 double* __restrict__ tile_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* c = reinterpret_cast<float*>(smem_raw);
+    double* ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
+    double* SQ = ST + (AMB_SPAN + 1);
+    double* tot_t = SQ + (AMB_SPAN + 1);
+    double* tot_q = tot_t + 256;
+    const int tid = threadIdx.x;
+    AMB_SPLIT_BID(tiles, r, tile)
+    const int64_t n = lens ? lens[r] : n_default;
+    const int64_t q0 = (int64_t)tile * AMB_TILE;
+    const float* src = y + (int64_t)r * stride;
+    for (int i = tid; i < AMB_SPAN; i += 256) {
+        const int64_t a = q0 - AMB_HALO + i;
+        c[i] = (a >= 0 && a < n) ? src[a] : 0.0f;
+    }
+    __syncthreads();
+    block_prefix(c, ST, SQ, tot_t, tot_q);
+    double best = -1.0;
+    for (int jj = 0; jj < AMB_TILE / 256; jj++) {
+        const int dl = jj * 256 + 1 + tid;
+        const int64_t d = q0 - AMB_HALO + dl;
+        if (d >= 0 && d + 2 * AMB_HALF <= n) {
+            const double P = ST[dl + 256] - ST[dl], A = SQ[dl + 256] - SQ[dl], B = SQ[dl + 512] - SQ[dl + 256];
+            double m = -1.0;
+            if (A > min_energy && B > min_energy) m = (P * P) / (A * B);
+            metric[(int64_t)r * stride + d] = m;
+            best = fmax(best, m);
+        }
+    }
+    __shared__ double red[8];
+    best = warp_maxd(best);
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; w++) best = fmax(best, red[w]);
+        tile_max[(int64_t)r * tiles + tile] = best;
+    }
+}
+
+// argmax of the metric with the reference's first-maximum rule (modem.js:308).  The reference's sums are
+// sliding float64 accumulators, ours are prefix differences: both carry ~1e-13 relative noise, so values
+// within 1e-9 of the maximum count as tied.  A tie confined to one contiguous run of offsets is a plateau
+// (exactly equal values in the reference): the first offset wins.  A tie between separate runs cannot be
+// decided here; `ambiguous` is set and k_replay settles it with the reference's own sequential recurrence.
+__global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metric, int64_t stride, const int64_t* __restrict__ lens,
+                                                 int64_t n_default, const double* __restrict__ tile_max, int tiles,
+                                                 int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous) {
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int64_t n = lens ? lens[r] : n_default;
+    __shared__ double sbest;
+    __shared__ long long sfirst, slast, scount;
+    if (tid == 0) { sbest = -1.0; sfirst = (long long)1 << 62; slast = -1; scount = 0; }
+    __syncthreads();
+    if (n < 2 * AMB_HALF) { if (tid == 0) { idx_out[r] = -1; best_out[r] = 0.0; ambiguous[r] = 0; } return; }
+    const int used = (int)((n - 1) / AMB_TILE) + 1;
+    double b = -1.0;
+    for (int t = tid; t < used && t < tiles; t += 256) b = fmax(b, tile_max[(int64_t)r * tiles + t]);
+    __shared__ double red[8];
+    b = warp_maxd(b);
+    if ((tid & 31) == 0) red[tid >> 5] = b;
+    __syncthreads();
+    if (tid == 0) { for (int w = 1; w < 8; w++) b = fmax(b, red[w]); sbest = b; }
+    __syncthreads();
+    const double best = sbest;
+    if (!(best > 0.0)) { if (tid == 0) { idx_out[r] = -1; best_out[r] = 0.0; ambiguous[r] = 0; } return; }
+    const double thr = best * (1.0 - 1e-9);
+    const int64_t end = n - 2 * AMB_HALF;
+    long long first = (long long)1 << 62, last = -1, count = 0;
+    for (int t = 0; t < used && t < tiles; t++) {
+        if (tile_max[(int64_t)r * tiles + t] < thr) continue;
+        const int64_t d_lo = (int64_t)t * AMB_TILE - 511, d_hi = d_lo + AMB_TILE - 1;
+        for (int64_t d = d_lo + tid; d <= d_hi; d += 256) {
+            if (d < 0 || d > end) continue;
+            if (metric[(int64_t)r * stride + d] >= thr) { if (d < first) first = d; if (d > last) last = d; count++; }
+        }
+    }
+    atomicMin(&sfirst, first); atomicMax(&slast, last); atomicAdd((unsigned long long*)&scount, (unsigned long long)count);
+    __syncthreads();
+    if (tid == 0) {
+        best_out[r] = best;
+        const bool contiguous = scount == slast - sfirst + 1;
+        ambiguous[r] = contiguous ? 0 : 1;
+        idx_out[r] = best > 0.5 ? (int64_t)sfirst : -1;
+    }
+}
+
+// Sequential float64 replay of detectPreamble (modem.js:292-318) for recordings whose maximum is tied
+// between separate offsets: one thread per recording, same operation order as the reference.
+__global__ void k_replay(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int n,
+                         double min_energy, const int* __restrict__ ambiguous, int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !ambiguous[r]) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    const float* s = y + (int64_t)r * stride;
+    double p = 0, ra = 0, rb = 0;
+    for (int m = 0; m < AMB_HALF; m++) {
+        const double a = s[m], b = s[m + AMB_HALF];
+        p = amb_add(p, amb_mul(a, b)); ra = amb_add(ra, amb_mul(a, a)); rb = amb_add(rb, amb_mul(b, b));
+    }
+    double best = 0; int64_t best_idx = -1;
+    const int64_t end = len - 2 * AMB_HALF;
+    for (int64_t d = 0; d <= end; d++) {
+        if (ra > min_energy && rb > min_energy) {
+            const double m = amb_div(amb_mul(p, p), amb_mul(ra, rb));
+            if (m > best) { best = m; best_idx = d; }
+        }
+        if (d < end) {
+            const double ao = s[d], mid = s[d + AMB_HALF], bi = s[d + 2 * AMB_HALF];
+            p = amb_add(p, amb_sub(amb_mul(mid, bi), amb_mul(ao, mid)));
+            ra = amb_add(ra, amb_sub(amb_mul(mid, mid), amb_mul(ao, ao)));
+            rb = amb_add(rb, amb_sub(amb_mul(bi, bi), amb_mul(mid, mid)));
+        }
+    }
+    best_out[r] = best;
+    idx_out[r] = best > 0.5 ? best_idx : -1;
+}
+
+// Fine cross-correlation + job setup for decodeReceivedSignal (modem.js:566-603): one warp per recording.
+// y = preprocessed signal (materialised), rows [n][stride].
+__global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restrict__ T, const float* __restrict__ y, int64_t stride,
+                                                       const int64_t* __restrict__ lens, int64_t n_default, int n,
+                                                       const int64_t* __restrict__ coarse_idx, const double* __restrict__ coarse_best,
+                                                       AmbJob* __restrict__ jobs) {
+    __shared__ double scratch[4][64];
+    const int warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * 4 + warp;
+    if (r >= n) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    AmbJob J;
+    J.p = y + (int64_t)r * stride; J.base = 0; J.lo = 0; J.hi = len;
+    J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
+    J.stream = r; J.mode = 1; J.status = 0; J.nsym = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
+    J.coarse = coarse_best[r]; J.fine = 0.0; J.result_pos = -1;
+    const int64_t c = coarse_idx[r];
+    if (c < 0) J.status = AMB_ST_PREAMBLE_NOT_DETECTED;
+    else {
+        AmbSig sig; sig.p = J.p; sig.base = 0; sig.lo = 0; sig.hi = len; sig.xf = J.xf;
+        const int64_t R = T->fine_radius, plen = T->sym_len;
+        const int64_t fs = c - R > 0 ? c - R : 0, fe = (c + R < len - plen) ? c + R : len - plen;
+        int64_t pos;
+        const double best = amb_fine_xcorr(T, sig, fs, fe, c, scratch[warp], &pos);
+        J.fine = best;
+        if (best < 0.1) J.status = AMB_ST_PREAMBLE_LOW_CORRELATION;
+        else {
+            J.pos = pos; J.result_pos = pos;
+            J.ce_pos = pos + 2 * plen;
+            J.data_pos = J.ce_pos + plen;
+            if (J.ce_pos + plen > len) J.status = AMB_ST_SIGNAL_TOO_SHORT_FOR_CE;
+            else if (J.data_pos >= len) J.status = AMB_ST_NO_DATA_AFTER_CE;
+            else J.nsym = (int32_t)((len - J.data_pos) / plen);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) jobs[r] = J;
+}
+
+// detectPreambleCrossCorr, modem.js:235-283: coarse metric at every `step`-th offset (one warp per offset
+// batch), then per recording the first maximum, the +-step fine search and the 0.15 thresholds.
+__global__ void __launch_bounds__(128) k_xcorr_coarse(const AmbTables* __restrict__ T, const float* __restrict__ x, int64_t stride,
+                                                       const int64_t* __restrict__ lens, int64_t n_default, int64_t step, int per,
+                                                       double* __restrict__ metric, int64_t metric_stride) {
+    AMB_SPLIT_BID(per, r, blk)
+    const int64_t len = lens ? lens[r] : n_default;
+    const int64_t plen = T->sym_len;
+    if (len < plen) return;
+    const int64_t n_pos = (len - plen) / step + 1;
+    const int64_t i = (int64_t)blk * blockDim.x + threadIdx.x;
+    if (i >= n_pos) return;
+    const float* s = x + (int64_t)r * stride + i * step;
+    double corr = 0, se = 0;
+    for (int k = 0; k < plen; k++) { const double v = s[k]; corr = fma(v, (double)T->pre1[k], corr); se = fma(v, v, se); }
+    const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
+    metric[(int64_t)r * metric_stride + i] = denom > 0.001 ? amb_div(corr, denom) : -2.0;
+}
+
+__global__ void __launch_bounds__(128) k_xcorr_pick(const AmbTables* __restrict__ T, const float* __restrict__ x, int64_t stride,
+                                                     const int64_t* __restrict__ lens, int64_t n_default, int n, int64_t step,
+                                                     const double* __restrict__ metric, int64_t metric_stride,
+                                                     int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
+    __shared__ double scratch[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 4 + warp;
+    if (r >= n) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    const int64_t plen = T->sym_len;
+    int64_t res = -1;
+    double res_best = 0.0;
+    if (len >= plen && T->pre1_energy >= 1e-10) {
+        const int64_t end = len - plen, n_pos = end / step + 1;
+        // first maximum above 0 over the coarse grid (strict '>' from best = 0)
+        double b = 0.0; int64_t bi = -1;
+        for (int64_t i = lane; i < n_pos; i += 32) { const double m = metric[(int64_t)r * metric_stride + i]; if (m > b) { b = m; bi = i; } }
+        scratch[warp][lane] = b; scratch[warp][32 + lane] = (double)bi;
+        __syncwarp();
+        b = 0.0; bi = -1;
+        for (int l = 0; l < 32; l++) {
+            const double m = scratch[warp][l]; const int64_t p = (int64_t)scratch[warp][32 + l];
+            if (p < 0) continue;
+            if (m > b || (m == b && p < bi)) { b = m; bi = p; }
+        }
+        __syncwarp();
+        res_best = b;
+        if (bi >= 0 && !(b < 0.15)) {
+            const int64_t c = bi * step;
+            const int64_t fs = c - step > 0 ? c - step : 0, fe = c + step < end ? c + step : end;
+            AmbSig sig; sig.p = x + (int64_t)r * stride; sig.base = 0; sig.lo = 0; sig.hi = len;
+            sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+            int64_t pos;
+            const double fb = amb_fine_xcorr(T, sig, fs, fe, c, scratch[warp], &pos);
+            // fine pass restarts from best = 0 with strict '>' (modem.js:268-280)
+            double best = 0.0; int64_t best_idx = c;
+            if (fb > 0.0) { best = fb; best_idx = pos; }
+            res_best = best;
+            res = best > 0.15 ? best_idx : -1;
+        }
+    }
+    if (lane == 0) { idx_out[r] = res; best_out[r] = res_best; }
+}
+
+// crc32 of n byte rows, one thread per row (modem.js:453-457)
+__global__ void k_crc32(const AmbTables* __restrict__ T, const uint8_t* __restrict__ data, int64_t stride, const int64_t* __restrict__ lens,
+                        int64_t n_default, int n, uint32_t* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    out[r] = amb_crc32_bytes(T->crc_table, data + (int64_t)r * stride, lens ? lens[r] : n_default);
+}
+
+// Job setup for decodeChunkFrame rows (modem.js:770-789)
+__global__ void k_jobs_chunk(const AmbTables* __restrict__ T, const float* __restrict__ frames, int64_t stride,
+                             const int64_t* __restrict__ lens, int64_t n_default, int n, AmbJob* __restrict__ jobs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    AmbJob J;
+    J.p = frames + (int64_t)r * stride; J.base = 0; J.lo = 0; J.hi = len;
+    J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
+    J.stream = r; J.mode = 0; J.status = 0; J.pos = 0; J.len = len; J.coarse = 0; J.fine = 0; J.result_pos = -1;
+    J.ce_pos = 2 * (int64_t)T->sym_len; J.data_pos = 3 * (int64_t)T->sym_len; J.nsym = 0;
+    if (J.ce_pos + T->sym_len > len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
+    else if (J.data_pos >= len) J.status = AMB_ST_NO_DATA_AFTER_CE;
+    else J.nsym = (int32_t)((len - J.data_pos) / T->sym_len);
+    jobs[r] = J;
+}
+
+// Job setup for amb_demodulate / amb_estimate_channel rows
+__global__ void k_jobs_rows(const AmbTables* __restrict__ T, const float* __restrict__ rows, int64_t stride,
+                            const int64_t* __restrict__ lens, int64_t n_default, int n, int ce_only, AmbJob* __restrict__ jobs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t len = lens ? lens[r] : n_default;
+    AmbJob J;
+    J.p = rows + (int64_t)r * stride; J.base = 0; J.lo = 0; J.hi = len;
+    J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
+    J.stream = r; J.mode = 0; J.status = 0; J.pos = 0; J.len = len; J.coarse = 0; J.fine = 0; J.result_pos = -1;
+    J.ce_pos = 0; J.data_pos = 0;
+    J.nsym = ce_only ? 0 : (int32_t)(len / T->sym_len);
+    jobs[r] = J;
+}
+
+// ================================================================================================
+// Streaming: frame records -> jobs, and the in-order application of decode results to stream state
+// (app.js:937-965, :610-643 without storage).
+// ================================================================================================
+__global__ void k_jobs_stream(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                              const AmbFrameRec* __restrict__ recs, const int* __restrict__ nrec, const int* __restrict__ job_off,
+                              int n_streams, AmbJob* __restrict__ jobs, int* __restrict__ max_nsym) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const int cnt = nrec[s], o = job_off[s];
+    for (int i = 0; i < cnt; i++) {
+        const AmbFrameRec& R = recs[(int64_t)s * g.rec_cap + i];
+        AmbJob J;
+        J.p = cleaned + (int64_t)s * g.stride; J.base = g.base_g; J.lo = g.base_g > 0 ? g.base_g : 0; J.hi = g.avail_hi;
+        J.xf.kind = AMB_XF_SCALE; J.xf.mx = 0.f; J.xf.mean = 0.0;
+        J.stream = s; J.mode = 0; J.status = R.status; J.pos = R.pos; J.len = R.len; J.coarse = R.coarse; J.fine = R.fine;
+        J.result_pos = R.pos;
+        J.ce_pos = R.pos + 2 * (int64_t)T->sym_len; J.data_pos = R.pos + 3 * (int64_t)T->sym_len; J.nsym = 0;
+        if (R.status == 0) {
+            if (2 * (int64_t)T->sym_len + T->sym_len > R.len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
+            else if (3 * (int64_t)T->sym_len >= R.len) J.status = AMB_ST_NO_DATA_AFTER_CE;
+            else J.nsym = (int32_t)((R.len - 3 * (int64_t)T->sym_len) / T->sym_len);
+        }
+        jobs[o + i] = J;
+        if (J.nsym > 0) atomicMax(max_nsym, J.nsym);
+    }
+}
+
+// Copies the kept frames (results + decoded bytes) to consecutive output rows starting at out_base.
+__global__ void __launch_bounds__(128) k_gather(const int* __restrict__ keep, const int* __restrict__ keep_off, int n_jobs,
+                                                 const amb_frame_result* __restrict__ res, const uint8_t* __restrict__ bytes, int64_t bytes_stride,
+                                                 int out_base, int max_out, amb_frame_result* __restrict__ dst_res, uint8_t* __restrict__ dst_bytes) {
+    const int j = blockIdx.x;
+    if (j >= n_jobs || !keep[j]) return;
+    const int o = out_base + keep_off[j];
+    if (o >= max_out) return;
+    if (threadIdx.x == 0 && dst_res) dst_res[o] = res[j];
+    if (dst_bytes) {
+        int64_t nb = res[j].n_bytes;
+        if (nb > bytes_stride) nb = bytes_stride;
+        const uint8_t* src = bytes + (int64_t)j * bytes_stride;
+        uint8_t* dst = dst_bytes + (int64_t)o * bytes_stride;
+        for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// exclusive prefix of nrec over streams (single block), total in *total
+__global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __restrict__ off, int* __restrict__ total) {
+    __shared__ int carry;
+    __shared__ int buf[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? nrec[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int a = 0;
+            if ((int)threadIdx.x >= o) a = buf[threadIdx.x - o];
+            __syncthreads();
+            buf[threadIdx.x] += a;
+            __syncthreads();
+        }
+        if (i < n) off[i] = carry + buf[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += buf[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the
+// streams whose collection window changed for another walk.
+__global__ void k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
+                              const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
+                              AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
+                              int* __restrict__ redo_list, int* __restrict__ n_redo) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const int cnt = nrec[s], o = job_off[s];
+    if (cnt == 0) return;
+    AmbStreamState st;
+    const int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, states[s], &st, keep + o);
+    states[s] = st;
+    if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
+}

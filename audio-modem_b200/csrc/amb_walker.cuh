@@ -1,0 +1,277 @@
+// Streaming receiver state machine (app.js:749-981) as a warp-cooperative "walker".
+//
+// The reference scans every sample sequentially.  Here a bandwidth-bound scan kernel has already
+// reduced the stream to per-tile summaries of the Schmidl-Cox window sums (max|P|, min/max Ra, min/max
+// Rb over 256 consecutive windows); the walker replays the reference's state machine call by call
+// (one call = one processAudioBlock of `block_len` samples), skips tiles whose summary proves that no
+// window can pass `metric > 0.5` with the energy gate, and evaluates the remaining windows exactly in
+// float64.  All decisions (candidate, 0.7 drop, end-of-buffer commit, refine, collect, reset) follow the
+// reference line by line, including two quirks:
+//   * app.js:826 advances acScanPos at the last position of a call although no slide happened, so from
+//     the next call on the running sums describe window d-1 at its first position and afterwards carry a
+//     constant defect  T(a-1) - T(a+255)  (a = first position of that call) until the next re-init.  The
+//     walker carries that defect explicitly (Ep, Ea, Eb) and the one-sample lag flag.
+//   * the pre-metadata collection window is a fixed 280-byte guess (app.js:892-896).
+// Exact ties on a noise-free plateau: the reference's sums are unchanged by the exact-zero updates, so
+// its strict '>' keeps the first plateau sample; directly evaluated sums differ in the last ulp, so a
+// new best must exceed the old one by 1e-12 relative here.
+#pragma once
+#include "amb_device.cuh"
+
+enum { AMB_RX_IDLE = 0, AMB_RX_PREAMBLE = 1, AMB_RX_COLLECT = 2 };
+
+struct AmbStreamState {
+    int32_t state, ac_init, lag, meta_received, chunk_size, total_chunks;
+    int64_t ac_scan_pos, pre_pos, frame_end;
+    double Ep, Ea, Eb;
+    double coarse, fine;
+    int64_t next_call;
+    int64_t frames_decoded, frame_errors, false_pos, received, crc_errors, dups;
+    double dc_mean;
+    int64_t written;
+};
+
+struct AmbFrameRec {
+    int32_t stream, status;
+    int64_t pos, len;
+    double coarse, fine;
+    AmbStreamState snap;   // walker state right after the frame's reset to IDLE
+};
+
+struct AmbWalkGeom {
+    int64_t block_len;     // samples per emulated processAudioBlock call
+    int64_t ring_cap;      // RingBuffer capacity, app.js:712-715
+    int64_t sum_base;      // global sample index of summary tile 0 (multiple of 256)
+    int64_t sum_tiles;     // tiles available from sum_base
+    int64_t sum_lo;        // summaries valid for window-end samples q >= sum_lo
+};
+
+// tile summary: {max|P|, minRa, maxRa, minRb, maxRb}
+#define AMB_SUM_W 5
+
+AMB_HD bool amb_tile_hot(const float* s, double Ep, double Ea, double Eb) {
+    const double g = 0.001;
+    const double up = 1.0 + 1e-5, eps = 1e-9;
+    const double maxA = (double)s[2] * up + eps + Ea, maxB = (double)s[4] * up + eps + Eb;
+    if (!(maxA > g) || !(maxB > g)) return false;
+    double minA = (double)s[1] * (1.0 - 1e-5) - eps + Ea, minB = (double)s[3] * (1.0 - 1e-5) - eps + Eb;
+    if (minA < g) minA = g;
+    if (minB < g) minB = g;
+    const double pm = (double)s[0] * up + eps + fabs(Ep);
+    return pm * pm > 0.5 * minA * minB * (1.0 - 1e-5);
+}
+
+struct AmbWalkScratch {      // per-warp shared memory
+    double P[264], A[264], B[264], M[264];
+    double x[64];
+    int32_t hot[32];
+    int32_t gate[264];
+};
+
+AMB_HD int64_t amb_frame_samples(const AmbTables* T, int64_t payload) {   // modem.js:863-874
+    const int64_t bits = payload * 8 * T->rep, per = (int64_t)T->n_data * T->bps;
+    return (3 + (bits + per - 1) / per) * T->sym_len;
+}
+
+// metric with the carried defect; returns gate flag
+AMB_HD int amb_metric(double P, double A, double B, const AmbStreamState& st, double* m) {
+    const double a = A + st.Ea, b = B + st.Eb, p = P + st.Ep;
+    if (a > 0.001 && b > 0.001) { *m = amb_div(amb_mul(p, p), amb_mul(a, b)); return 1; }
+    *m = 0.0;
+    return 0;
+}
+
+AMB_HD void amb_commit(AmbStreamState& st, int64_t best_pos, double best, int64_t next_pos, int lag) {
+    st.pre_pos = best_pos; st.coarse = best; st.state = AMB_RX_PREAMBLE; st.ac_scan_pos = next_pos; st.lag = lag;
+}
+
+// _scanForPreamble, app.js:775-847, for the call whose totalWritten is `tw`
+AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums,
+                          AmbStreamState& st, int64_t tw, AmbWalkScratch* W) {
+    const int64_t oldest = tw - G.ring_cap;
+    if (st.ac_scan_pos < oldest + 2 * AMB_HALF) {
+        st.ac_scan_pos = oldest + 2 * AMB_HALF > 0 ? oldest + 2 * AMB_HALF : 0;
+        st.ac_init = 0;
+    }
+    const int64_t scan_end = tw - 2 * AMB_HALF;
+    if (st.ac_scan_pos > scan_end) return;
+    if (!st.ac_init) {
+        if (st.ac_scan_pos < oldest) return;
+        st.Ep = st.Ea = st.Eb = 0.0; st.lag = 0; st.ac_init = 1;
+    }
+    double best = 0.0;
+    int64_t best_pos = -1;
+    int64_t d = st.ac_scan_pos;
+
+    if (st.lag == 1) {
+        // first position of a call that continues an uninterrupted scan: sums still describe window d-1
+        amb_window_sums(sig, d - 1, 3, W->P, W->A, W->B);
+        double m;
+        if (amb_metric(W->P[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
+        if (d < scan_end) {
+            // slide with the label d: removes T(d), adds T(d+256)  ->  W(d+1) + [T(d-1) - T(d+255)]
+            const double xm1 = (double)amb_sig(sig, d - 1), x255 = (double)amb_sig(sig, d + 255), x511 = (double)amb_sig(sig, d + 511);
+            st.Ep += xm1 * x255 - x255 * x511;
+            st.Ea += xm1 * xm1 - x255 * x255;
+            st.Eb += x255 * x255 - x511 * x511;
+            st.lag = 0;
+            if (best > 0.5) {
+                double cur;
+                if (amb_metric(W->P[2], W->A[2], W->B[2], st, &cur) && cur < best * 0.7) { amb_commit(st, best_pos, best, d + 1, 0); return; }
+            }
+            d = d + 1;
+        } else {
+            // cannot happen for block_len > 1 (the next call's scan_end is at least block_len later)
+            st.ac_scan_pos = d + 1;
+            if (best > 0.5) amb_commit(st, best_pos, best, d + 1, 1);
+            return;
+        }
+    }
+
+    while (d <= scan_end) {
+        if (!(best > 0.5)) {
+            // skip tiles that cannot hold a candidate.  tile j covers window-end samples [256j, 256j+256)
+            const int64_t q = d + 511;
+            int64_t j = q >> 8;
+            const int64_t j_end = (scan_end + 511) >> 8;
+            bool found = false;
+            while (j <= j_end) {
+                AMB_WARP_FOR(t, 32) {
+                    const int64_t jj = j + t;
+                    int h = 0;
+                    if (jj <= j_end) {
+                        const int64_t rel = jj - (G.sum_base >> 8);
+                        if (rel < 0 || rel >= G.sum_tiles || (jj << 8) < G.sum_lo) h = 1;   // no summary: must evaluate
+                        else h = amb_tile_hot(sums + rel * AMB_SUM_W, st.Ep, st.Ea, st.Eb) ? 1 : 0;
+                    }
+                    W->hot[t] = h;
+                }
+                AMB_WARP_SYNC();
+                int first = -1;
+                for (int t = 0; t < 32; t++) if (W->hot[t]) { first = t; break; }
+                AMB_WARP_SYNC();
+                if (first >= 0) { j += first; found = true; break; }
+                j += 32;
+            }
+            if (!found) break;
+            const int64_t tile_first = (j << 8) - 511;
+            if (tile_first > d) d = tile_first;
+            if (d > scan_end) break;
+        }
+        // evaluate up to 256 windows exactly (to the end of the tile when idle, any 256 when tracking)
+        int64_t d_end = d + 255;
+        if (!(best > 0.5)) { const int64_t tile_last = (((d + 511) >> 8) << 8) + 255 - 511; if (tile_last < d_end) d_end = tile_last; }
+        if (d_end > scan_end) d_end = scan_end;
+        const int cnt = (int)(d_end - d + 1);
+        const int look = d_end < scan_end ? 1 : 0;
+        amb_window_sums(sig, d, cnt + look, W->P, W->A, W->B);
+        AMB_WARP_FOR(i, cnt + look) {
+            double m;
+            W->gate[i] = amb_metric(W->P[i], W->A[i], W->B[i], st, &m);
+            W->M[i] = m;
+        }
+        AMB_WARP_SYNC();
+        for (int i = 0; i < cnt; i++) {
+            const int64_t pos = d + i;
+            if (W->gate[i]) {
+                const double m = W->M[i];
+                if (m > 0.5 && m > best * (1.0 + 1e-12)) { best = m; best_pos = pos; }
+            }
+            const int nxt = pos < scan_end ? i + 1 : i;
+            if (best > 0.5 && best_pos >= 0 && W->gate[nxt] && W->M[nxt] < best * 0.7) {
+                amb_commit(st, best_pos, best, pos + 1, pos < scan_end ? 0 : 1);
+                AMB_WARP_SYNC();
+                return;
+            }
+        }
+        AMB_WARP_SYNC();
+        d = d_end + 1;
+    }
+    // end of the data available in this call (app.js:842-846)
+    st.ac_scan_pos = scan_end + 1;
+    st.lag = 1;
+    if (best > 0.5 && best_pos >= 0) amb_commit(st, best_pos, best, scan_end + 1, 1);
+}
+
+// _refineAndCollect, app.js:849-898
+AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, AmbStreamState& st, int64_t tw,
+                            AmbWalkScratch* W) {
+    const int64_t plen = T->sym_len, R = T->fine_radius;
+    if (tw < st.pre_pos + plen + R) return;
+    int64_t fs = st.pre_pos - R, fe = st.pre_pos + R;
+    if (fs < tw - G.ring_cap) fs = tw - G.ring_cap;
+    if (fe > tw - plen) fe = tw - plen;
+    int64_t pos;
+    const double best = amb_fine_xcorr(T, sig, fs, fe, st.pre_pos, W->x, &pos);
+    if (best < 0.1) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
+    st.pre_pos = pos; st.fine = best;
+    const int64_t max_payload = st.meta_received ? (int64_t)(st.chunk_size ? st.chunk_size : 4096) + 11 : 280;
+    st.frame_end = st.pre_pos + amb_frame_samples(T, max_payload);
+    st.state = AMB_RX_COLLECT;
+}
+
+// Runs calls [st.next_call, k_end) of one stream.  Emits one record per completed frame.
+// Returns the number of records written (stops early, leaving st.next_call behind k_end, if `cap` is hit).
+AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums, AmbStreamState& st,
+                    int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W) {
+    int n = 0;
+    while (st.next_call < k_end) {
+        const int64_t tw = (st.next_call + 1) * G.block_len;
+        if (st.state == AMB_RX_IDLE) amb_walk_scan(T, G, sig, sums, st, tw, W);
+        else if (st.state == AMB_RX_PREAMBLE) amb_walk_refine(T, G, sig, st, tw, W);
+        else if (tw >= st.frame_end) {
+            // _checkFrameComplete + _demodulateFrame + _resetToIdle, app.js:900-981
+            if (n >= cap) return n;
+            AmbFrameRec rec;
+            rec.stream = stream;
+            rec.status = st.pre_pos < tw - G.ring_cap ? AMB_ST_RING_OVERWRITTEN : AMB_ST_OK;
+            rec.pos = st.pre_pos; rec.len = st.frame_end - st.pre_pos; rec.coarse = st.coarse; rec.fine = st.fine;
+            st.ac_scan_pos = st.frame_end; st.ac_init = 0; st.pre_pos = -1; st.frame_end = -1; st.state = AMB_RX_IDLE;
+            st.next_call++;
+            rec.snap = st;
+            if (AMB_LEADER()) out[n] = rec;
+            n++;
+            continue;
+        }
+        st.next_call++;
+    }
+    return n;
+}
+
+// Applies the decoded frames of one stream in time order (app.js:937-965 and the storage-free part of
+// ChunkAssembler, app.js:610-643).  `cur` is the stream state after the walk (the walker never touches the
+// flags or the frame counters).  A CRC-valid metadata frame that changes the collection window (first
+// metadata, or a different chunkSize) invalidates everything the walker did after it: the state is rewound to
+// the snapshot taken after that frame, with the new flags, and 1 is returned so that the caller walks again.
+// keep[i] = 1 for frames to report.
+AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_result* res, const AmbStreamState& cur,
+                           AmbStreamState* out, int* keep) {
+    AmbStreamState st = cur;
+    int64_t fd = cur.frames_decoded, fe = cur.frame_errors, rc = cur.received, ce = cur.crc_errors;
+    int meta = cur.meta_received, chunk = cur.chunk_size, total = cur.total_chunks;
+    int rewind = -1;
+    for (int i = 0; i < cnt; i++) {
+        const amb_frame_result& r = res[i];
+        keep[i] = 1;
+        if (r.status != 0) { fe++; continue; }
+        fd++;
+        if (r.frame_type == AMB_FRAME_META) {
+            if (r.crc_valid) {
+                const bool changes = !meta || chunk != r.chunk_size;
+                meta = 1; chunk = r.chunk_size; total = r.total_chunks; rc = 0; ce = 0;
+                if (changes) { rewind = i; break; }
+            } else fe++;
+        } else if (r.frame_type == AMB_FRAME_DATA) {
+            if (meta == 1 && !(r.seq_num >= total)) { if (!r.crc_valid) ce++; else rc++; }
+        }
+    }
+    if (rewind >= 0) {
+        for (int i = rewind + 1; i < cnt; i++) keep[i] = 0;
+        st = recs[rewind].snap;
+        st.dc_mean = cur.dc_mean; st.written = cur.written;
+    }
+    st.meta_received = meta; st.chunk_size = chunk; st.total_chunks = total;
+    st.frames_decoded = fd; st.frame_errors = fe; st.received = rc; st.crc_errors = ce;
+    *out = st;
+    return rewind >= 0 ? 1 : 0;
+}

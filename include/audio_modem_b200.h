@@ -1,0 +1,186 @@
+/*
+ * audio_modem_b200.h — C-ABI of the B200-native OFDM receive path.
+ *
+ * Drop-in boundary for the receive hot path of playok/audio-modem.  The
+ * reference has no FFI: its interface is the set of browser-global functions
+ * of modem.js plus the StreamingReceiver class of app.js.  Every entry point
+ * below names the reference function (file:line under /root/reference) it
+ * replaces.  An N-API addon (node/), or the ctypes mirror in the Python
+ * package, converts between these calls and the reference's JavaScript
+ * signatures and result objects.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary;
+ *   - every call returns 0 (AMB_OK) or a negative AMB_E_* library error;
+ *     the reference's own per-frame failures ({error: "..."} objects, -1
+ *     indices) are NOT library errors: they come back in amb_frame_result
+ *     .status (AMB_ST_*) or as index -1, exactly where the reference puts them;
+ *   - `mem` says where caller buffers live: AMB_MEM_HOST (pageable or pinned
+ *     host memory; the call copies in and out) or AMB_MEM_DEVICE (device
+ *     pointers on the handle's GPU; nothing is copied through the host);
+ *   - all work of a handle runs on one CUDA stream (amb_cuda_stream); calls
+ *     on one handle must be serialised by the caller, different handles are
+ *     independent (the reference's hidden global `OFDM`, modem.js:87-98, is
+ *     replaced by the explicit per-handle config);
+ *   - there is NO CPU fallback: amb_create fails when no CUDA device exists.
+ */
+#ifndef AUDIO_MODEM_B200_H
+#define AUDIO_MODEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMB_VERSION 100
+
+/* OFDM_CONFIGS, modem.js:69-85 (setOFDMConfig, :95-98: unknown -> standard) */
+#define AMB_CFG_STANDARD 0
+#define AMB_CFG_ACOUSTIC 1
+#define AMB_CFG_NARROWBAND 2
+
+/* Constellations, modem.js:101-131 */
+#define AMB_MOD_BPSK 0
+#define AMB_MOD_QPSK 1
+#define AMB_MOD_QAM16 2
+
+#define AMB_MEM_HOST 0
+#define AMB_MEM_DEVICE 1
+#define AMB_MEM_INPLACE 2 /* streaming only: samples already written at amb_stream_input_window() */
+
+/* library errors (negative) */
+#define AMB_OK 0
+#define AMB_E_INVALID (-1)  /* bad argument */
+#define AMB_E_CUDA (-2)     /* CUDA runtime error; see amb_last_error */
+#define AMB_E_NOMEM (-3)
+#define AMB_E_STATE (-4)    /* call not valid in this state (e.g. stream not open) */
+#define AMB_E_OVERFLOW (-5) /* caller's result buffer too small; see n_results */
+#define AMB_E_NODEVICE (-6) /* no CUDA device: the library has no CPU path */
+
+/* amb_frame_result.status: 0 or one of the reference's failures */
+#define AMB_ST_OK 0
+#define AMB_ST_PREAMBLE_NOT_DETECTED 1        /* modem.js:564 */
+#define AMB_ST_PREAMBLE_LOW_CORRELATION 2     /* modem.js:588 */
+#define AMB_ST_SIGNAL_TOO_SHORT_FOR_CE 3      /* modem.js:592 */
+#define AMB_ST_NO_DATA_AFTER_CE 4             /* modem.js:600, :785 */
+#define AMB_ST_DECODED_TOO_SHORT 5            /* modem.js:607, :793 */
+#define AMB_ST_DECODED_TOO_SHORT_FOR_HEADER 6 /* modem.js:625 */
+#define AMB_ST_INVALID_DATA_LENGTH 7          /* modem.js:634 (err_arg = dataLen) */
+#define AMB_ST_FRAME_TOO_SHORT_FOR_CE 8       /* modem.js:776 */
+#define AMB_ST_UNKNOWN_FRAME_TYPE 9           /* modem.js:801 (err_arg = type byte) */
+#define AMB_ST_META_TOO_SHORT 10              /* modem.js:807 */
+#define AMB_ST_META_TRUNCATED 11              /* modem.js:813 */
+#define AMB_ST_CHUNK_TOO_SHORT 12             /* modem.js:832 */
+#define AMB_ST_CHUNK_TRUNCATED 13             /* modem.js:836 */
+#define AMB_ST_RING_OVERWRITTEN 14            /* app.js:912-916 (frameErrors++, no message) */
+
+#define AMB_FRAME_LEGACY 0
+#define AMB_FRAME_META 0xFE /* modem.js:661 */
+#define AMB_FRAME_DATA 0xFF /* modem.js:662 */
+
+/*
+ * One decoded frame.  Field meaning follows the reference's result objects:
+ * legacy {data,dataLen,fileName,crcValid,expectedCRC,actualCRC,preambleIdx}
+ * (modem.js:644-653), metadata (:822-827), data chunk (:843-848).  `n_bytes`
+ * decoded bytes (bitsToBytes output, modem.js:605/:791) are written to the
+ * caller's byte buffer; name/data are slices of it at name_off / data_off.
+ */
+typedef struct amb_frame_result {
+    int32_t status;          /* AMB_ST_* */
+    int32_t frame_type;      /* AMB_FRAME_*, or -1 when none was parsed */
+    int64_t preamble_idx;    /* refined preamble start; global stream position when streaming; -1 n/a */
+    int32_t seq_num;         /* data chunk seqNum (signed 32-bit, modem.js:834) */
+    int32_t data_len;        /* legacy / data chunk dataLen */
+    int32_t total_chunks;    /* metadata (signed, modem.js:809) */
+    int32_t total_file_size; /* metadata (signed, modem.js:810) */
+    int32_t chunk_size;      /* metadata */
+    int32_t name_len;        /* legacy / metadata */
+    int32_t name_off;
+    int32_t data_off;
+    uint32_t expected_crc;
+    uint32_t actual_crc;
+    int32_t crc_valid;
+    int32_t n_bytes;         /* length of the decoded byte array */
+    int32_t err_arg;
+    int32_t stream;          /* recording / frame / stream index inside the batch */
+    double coarse_metric;    /* Schmidl-Cox metric at the coarse index */
+    double fine_metric;      /* refined cross-correlation peak */
+} amb_frame_result;
+
+typedef struct amb_modem amb_modem;
+
+/* ---- lifecycle -------------------------------------------------------- */
+int amb_version(void);
+/* the reference's message for an AMB_ST_* status ("{arg}" placeholders filled by the caller) */
+const char* amb_status_string(int status);
+/* setOFDMConfig + the (modName, repetition) pair every decode call takes:
+ * modem.js:95, :557, :770; app.js:60-66 */
+int amb_create(amb_modem** out, int device, int config, int constellation, int repetition);
+void amb_destroy(amb_modem* m);
+const char* amb_last_error(const amb_modem* m);
+int amb_synchronize(amb_modem* m);
+void* amb_cuda_stream(amb_modem* m); /* the cudaStream_t all work is queued on */
+int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by this handle */
+
+/* ---- pure host helpers (no device work) -------------------------------- */
+/* estimateFrameSamples, modem.js:863-874 */
+int64_t amb_estimate_frame_samples(int config, int constellation, int64_t payload_bytes, int repetition);
+/* OFDM config fields: out8 = FFT_SIZE, CP_LEN, SYMBOL_LEN, SAMPLE_RATE, SUB_START, SUB_END, nPilots,
+ * numDataSubs (modem.js:69-93); pilots receives nPilots bins */
+int amb_config_info(int config, int32_t* out8, int32_t* pilots);
+/* generatePreambleSymbol1 / generateChannelEstSymbol, modem.js:158-170, :186-200 */
+int amb_preamble_symbol1(int config, float* out_symbol_len);
+int amb_channel_est_symbol(int config, float* out_symbol_len, double* known_re_512);
+
+/* ---- batched operators (one launch covers n independent inputs) --------- */
+/* Inputs are rows of a [n][stride] array; lens[i] (NULL = all `stride`) is the valid length of row i. */
+
+/* crc32, modem.js:453-457 */
+int amb_crc32(amb_modem* m, const uint8_t* data, int64_t stride, const int64_t* lens, int n, uint32_t* out, int mem);
+/* preprocessSignal, modem.js:213-232; out has the same [n][stride] shape */
+int amb_preprocess_signal(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, float* out, int mem);
+/* detectPreamble, modem.js:286-319; idx_out[i] = index or -1; metric_out (optional) = best metric */
+int amb_detect_preamble(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, int64_t* idx_out,
+                        double* metric_out, int mem);
+/* detectPreambleCrossCorr, modem.js:235-283 */
+int amb_detect_preamble_xcorr(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n,
+                              int64_t* idx_out, double* metric_out, int mem);
+/* estimateChannel, modem.js:421-440; ce = [n][SYMBOL_LEN]; known_re/known_im = [512] shared by all rows
+ * (NULL = the config's generateChannelEstSymbol values); ch_re/ch_im = [n][512] */
+int amb_estimate_channel(amb_modem* m, const float* ce, int n, const double* known_re, const double* known_im,
+                         double* ch_re, double* ch_im, int mem);
+/* demodulateOFDM, modem.js:365-418; signal rows start at the first data symbol; ch_re/ch_im = [n][512];
+ * bits = [n][bits_stride], one byte per bit like the reference's number[]; nbits_out[i] = bits produced;
+ * eq_out (optional) = [n][eq_stride][2] de-rotated (cr, ci) per data subcarrier, symbol-major */
+int amb_demodulate(amb_modem* m, const float* signal, int64_t stride, const int64_t* lens, int n, const double* ch_re,
+                   const double* ch_im, uint8_t* bits, int64_t bits_stride, int64_t* nbits_out, double* eq_out,
+                   int64_t eq_stride, int mem);
+/* decodeChunkFrame, modem.js:770-803; rows start at preamble-1 */
+int amb_decode_chunk_frames(amb_modem* m, const float* frames, int64_t stride, const int64_t* lens, int n,
+                            amb_frame_result* results, uint8_t* bytes_out, int64_t bytes_stride, int mem);
+/* decodeReceivedSignal, modem.js:557-654; one recording per row */
+int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n,
+                                amb_frame_result* results, uint8_t* bytes_out, int64_t bytes_stride, int mem);
+
+/* ---- streaming receiver: new StreamingReceiver(modName, repetition) / processAudioBlock,
+ *      app.js:706-981, for n_streams independent streams at once ------------------------- */
+/* block_len = the ScriptProcessor block size whose call cadence is emulated (app.js:1107: 4096);
+ * max_push = largest n_new a push will carry (multiple of block_len) */
+int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push);
+int amb_stream_close(amb_modem* m);
+/* where the next push's samples go on the device (stream s at dev_ptr + s*stride floats); for AMB_MEM_INPLACE */
+int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride);
+/* Feed n_new samples (multiple of block_len) to every stream: x = [n_streams][x_stride].  Frames completed by
+ * these samples come back in stream-major, time order; bytes_out row j belongs to results[j]. */
+int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem);
+/* per-stream counters (stream = -1: sum over streams): framesDecoded, frameErrors (app.js:738-739),
+ * falsePositives (app.js:879-884), receivedCount, crcErrors (app.js:604-605), duplicates, metaReceived,
+ * samplesWritten */
+int amb_stream_counters(amb_modem* m, int stream, int64_t* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

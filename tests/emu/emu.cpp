@@ -1,0 +1,167 @@
+// TEST-ONLY host emulation of the device logic.
+//
+// Compiles audio-modem_b200/csrc/amb_device.cuh and amb_walker.cuh with g++ (warp loops become sequential
+// loops) and drives them the way the CUDA kernels do, so that the kernel LOGIC (faithful FFT schedule,
+// equaliser, demap slicing, vote/pack/parse/CRC, the streaming walker and its rewind rule) can be compared
+// with the oracle on a machine without a GPU.  It is not part of the product and is never loaded by it; the
+// parallel decomposition itself (thread indexing, shared memory, scans) is only exercised by the -m gpu tests.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../audio-modem_b200/csrc/amb_walker.cuh"
+
+namespace {
+
+struct Frame { amb_frame_result res; std::vector<uint8_t> bytes; };
+
+// mirrors k_demod (+ k_frame_max) and k_parse for one job
+void decode_job(const AmbTables& T, const AmbSig& sig_in, int64_t pos, int64_t len, int64_t ce_pos, int64_t data_pos, int nsym,
+                int status, int mode, bool scale, int64_t result_pos, Frame* out) {
+    amb_frame_result& r = out->res;
+    amb_result_clear(&r);
+    if (status != 0) { r.status = status; if (status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = result_pos; return; }
+    AmbSig sig = sig_in;
+    if (scale) {
+        float mx = 0.f;
+        for (int64_t i = 0; i < len; i++) { const int64_t g = pos + i; const float v = (g >= sig.lo && g < sig.hi) ? sig.p[g - sig.base] : 0.f; mx = fmaxf(mx, fabsf(v)); }
+        sig.xf.kind = AMB_XF_SCALE; sig.xf.mx = mx;
+    }
+    std::vector<double> re(AMB_FFT), im(AMB_FFT), hre(AMB_FFT, 0.0), him(AMB_FFT, 0.0), qs(2 * AMB_MAX_PILOTS);
+    amb_fft512_load(sig, ce_pos + T.cp_len, re.data(), im.data());
+    amb_fft512_faithful(re.data(), im.data(), T.tw_re, T.tw_im, T.sub_start, T.sub_end);
+    amb_channel_from_spectrum(re.data(), im.data(), T.known_re, nullptr, T.sub_start, T.sub_end, hre.data(), him.data());
+    std::vector<uint8_t> idx((size_t)(nsym > 0 ? nsym : 1) * T.n_data);
+    for (int s = 0; s < nsym; s++) {
+        amb_fft512_load(sig, data_pos + (int64_t)s * T.sym_len + T.cp_len, re.data(), im.data());
+        amb_fft512_faithful(re.data(), im.data(), T.tw_re, T.tw_im, T.sub_start, T.sub_end);
+        amb_symbol_demap(&T, re.data(), im.data(), hre.data(), him.data(), qs.data(), idx.data() + (size_t)s * T.n_data, nullptr, nullptr);
+    }
+    const int64_t n_elems = (int64_t)nsym * T.n_data;
+    const int64_t nb = amb_num_bytes(n_elems, T.bps, T.rep);
+    out->bytes.assign((size_t)nb + 8, 0);
+    amb_pack_bytes(idx.data(), n_elems, T.bps, T.rep, out->bytes.data(), nb);
+    if (mode == 0) amb_parse_chunk_frame(T.crc_table, out->bytes.data(), nb, &r);
+    else amb_parse_received(T.crc_table, out->bytes.data(), nb, &r);
+    r.n_bytes = (int32_t)nb;
+    const bool chunk_type = nb >= 10 && (out->bytes[0] == AMB_FRAME_META || out->bytes[0] == AMB_FRAME_DATA);
+    if (mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = result_pos;
+    out->bytes.resize((size_t)nb);
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_result_size(void) { return (int)sizeof(amb_frame_result); }
+
+// decodeChunkFrame through the device logic
+int emu_decode_chunk_frame(int cfg, int mod, int rep, const float* x, int64_t n, amb_frame_result* res, uint8_t* bytes, int64_t cap) {
+    AmbTables T;
+    if (amb_tables_build(&T, cfg, mod, rep)) return -1;
+    AmbSig sig; sig.p = x; sig.base = 0; sig.lo = 0; sig.hi = n; sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0; sig.xf.mean = 0;
+    int status = 0, nsym = 0;
+    const int64_t ce = 2 * (int64_t)T.sym_len, data = 3 * (int64_t)T.sym_len;
+    if (ce + T.sym_len > n) status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
+    else if (data >= n) status = AMB_ST_NO_DATA_AFTER_CE;
+    else nsym = (int)((n - data) / T.sym_len);
+    Frame f;
+    decode_job(T, sig, 0, n, ce, data, nsym, status, 0, false, -1, &f);
+    *res = f.res;
+    if (bytes) std::memcpy(bytes, f.bytes.data(), (size_t)std::min<int64_t>(cap, (int64_t)f.bytes.size()));
+    return 0;
+}
+
+// streaming receiver through the device logic: EMA (sequential, as the reference), tile summaries computed
+// directly, then walk / decode / post until no stream needs another walk.  Pushes of `push_len` samples.
+int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t block_len, int64_t push_len,
+               amb_frame_result* res_out, int max_res, uint8_t* bytes_out, int64_t bytes_stride, int64_t* counters) {
+    AmbTables T;
+    if (amb_tables_build(&T, cfg, mod, rep)) return -1;
+    std::vector<float> cleaned((size_t)n);
+    double m = 0;
+    for (int64_t i = 0; i < n; i++) { m = T.dc_alpha * m + T.dc_beta * (double)x[i]; cleaned[i] = (float)((double)x[i] - m); }
+    const int64_t n_tiles = n / 256 + 1;
+    std::vector<float> sums((size_t)n_tiles * AMB_SUM_W, 0.f);
+    AmbSig sig; sig.p = cleaned.data(); sig.base = 0; sig.lo = 0; sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0; sig.xf.mean = 0;
+    AmbWalkGeom G;
+    G.block_len = block_len; G.ring_cap = amb_tables_estimate_frame_samples(cfg, mod, 4096 + 16, rep) * 3 + 8192;
+    G.sum_base = 0; G.sum_tiles = n_tiles; G.sum_lo = 0;
+    AmbStreamState st;
+    std::memset(&st, 0, sizeof(st));
+    st.pre_pos = -1; st.frame_end = -1;
+    AmbWalkScratch W;
+    std::vector<AmbFrameRec> recs(4096);
+    int n_out = 0;
+    int64_t tiles_done = 0;
+    for (int64_t w0 = 0; w0 < n; w0 += push_len) {
+        const int64_t w1 = std::min(n, w0 + push_len);
+        if ((w1 - w0) % block_len) break;
+        sig.hi = w1;
+        // summaries of the window-end samples that became available
+        for (int64_t j = tiles_done; (j + 1) * 256 <= w1; j++, tiles_done = j) {
+            float ap = 0, mnA = 3e38f, mxA = 0, mnB = 3e38f, mxB = 0;
+            for (int64_t q = j * 256; q < (j + 1) * 256; q++) {
+                const int64_t d = q - 511;
+                if (d < 0) continue;
+                double P = 0, A = 0, B = 0;
+                for (int t = 0; t < 256; t++) { const double a = cleaned[d + t], b = cleaned[d + t + 256]; P += a * b; A += a * a; B += b * b; }
+                ap = fmaxf(ap, (float)fabs(P)); mnA = fminf(mnA, (float)A); mxA = fmaxf(mxA, (float)A); mnB = fminf(mnB, (float)B); mxB = fmaxf(mxB, (float)B);
+            }
+            float* o = &sums[(size_t)j * AMB_SUM_W];
+            o[0] = ap; o[1] = mnA; o[2] = mxA; o[3] = mnB; o[4] = mxB;
+        }
+        const int64_t k_end = w1 / block_len;
+        for (int pass = 0; pass < 64; pass++) {
+            const int cnt = amb_walk(&T, G, sig, sums.data(), st, k_end, 0, recs.data(), (int)recs.size(), &W);
+            if (cnt == 0) break;
+            std::vector<Frame> fr((size_t)cnt);
+            std::vector<amb_frame_result> rr((size_t)cnt);
+            for (int i = 0; i < cnt; i++) {
+                const AmbFrameRec& R = recs[i];
+                int status = R.status, nsym = 0;
+                if (status == 0) {
+                    if (3 * (int64_t)T.sym_len > R.len) status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
+                    else if (3 * (int64_t)T.sym_len >= R.len) status = AMB_ST_NO_DATA_AFTER_CE;
+                    else nsym = (int)((R.len - 3 * (int64_t)T.sym_len) / T.sym_len);
+                }
+                decode_job(T, sig, R.pos, R.len, R.pos + 2 * T.sym_len, R.pos + 3 * T.sym_len, nsym, status, 0, true, R.pos, &fr[i]);
+                fr[i].res.coarse_metric = R.coarse; fr[i].res.fine_metric = R.fine;
+                rr[i] = fr[i].res;
+            }
+            std::vector<int> keep((size_t)cnt, 0);
+            AmbStreamState nst;
+            const int redo = amb_post_frames(recs.data(), cnt, rr.data(), st, &nst, keep.data());
+            st = nst;
+            for (int i = 0; i < cnt; i++) {
+                if (!keep[i]) continue;
+                if (n_out < max_res) {
+                    res_out[n_out] = rr[i];
+                    if (bytes_out) std::memcpy(bytes_out + (size_t)n_out * bytes_stride, fr[i].bytes.data(), (size_t)std::min<int64_t>(bytes_stride, (int64_t)fr[i].bytes.size()));
+                }
+                n_out++;
+            }
+            if (!redo) break;
+        }
+    }
+    if (counters) {
+        counters[0] = st.frames_decoded; counters[1] = st.frame_errors; counters[2] = st.false_pos; counters[3] = st.received;
+        counters[4] = st.crc_errors; counters[5] = st.dups; counters[6] = st.meta_received; counters[7] = st.ac_scan_pos;
+    }
+    return n_out;
+}
+
+// tables for inspection
+int emu_tables(int cfg, int mod, int rep, float* pre1, double* known_re, double* tw_re, double* tw_im, double* pts, double* scalars) {
+    AmbTables T;
+    if (amb_tables_build(&T, cfg, mod, rep)) return -1;
+    std::memcpy(pre1, T.pre1, sizeof(float) * T.sym_len);
+    std::memcpy(known_re, T.known_re, sizeof(T.known_re));
+    std::memcpy(tw_re, T.tw_re, sizeof(T.tw_re)); std::memcpy(tw_im, T.tw_im, sizeof(T.tw_im));
+    std::memcpy(pts, T.pts, sizeof(T.pts));
+    scalars[0] = T.pre1_energy; scalars[1] = T.qam_thr; scalars[2] = T.dc_beta; scalars[3] = T.n_data; scalars[4] = T.pre1_sign;
+    return 0;
+}
+
+}  // extern "C"
