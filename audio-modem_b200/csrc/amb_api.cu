@@ -541,7 +541,6 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
     if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
     if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
-    const AmbTables& T = m->tables;
     const int ns = m->n_streams;
     const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");

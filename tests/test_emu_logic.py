@@ -1,0 +1,98 @@
+"""Device LOGIC vs the oracle, on the CPU: tests/emu/emu.cpp compiles the very .cuh sources the CUDA kernels are
+built from (warp loops run sequentially) and drives them as the kernels do.  This checks the faithful FFT
+schedule, equaliser, demap slicing, vote/pack/parse/CRC, the streaming walker (tile skipping, the reference's
+block-boundary quirk, refine/collect/reset) and the metadata rewind rule; the GPU parity tests then only have to
+establish that the parallel decomposition computes the same thing."""
+import numpy as np
+import pytest
+
+from helpers import MODES, emu_decode_chunk_frame, emu_stream, make_stream, results_equal
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_decode_chunk_frame_bit_exact(O, emu, mode):
+    cfg, mod, rep, chunk = MODES[mode]
+    lead = 13230 if cfg == "standard" else 22050
+    cases = [
+        O.addAwgn(O.buildDataChunkFrame(cfg, O.randomBytes(9, chunk), 5, mod, rep), 0.01, 5)[2205:],
+        O.addAwgn(O.buildMetadataFrame(cfg, 7, 1234, chunk, "näme.bin", mod, rep), 0.3, 6)[lead:],      # hopeless SNR
+        (np.random.default_rng(1).standard_normal(20000) * 0.1).astype(np.float32),                     # garbage
+        np.zeros(5000, np.float32),                                                                      # silence: eq = 0/0 guards
+        O.buildDataChunkFrame(cfg, O.randomBytes(9, 16), 1, mod, rep)[2205:][: 3 * O.config(cfg)["SYMBOL_LEN"] + 5],
+        np.zeros(100, np.float32),
+    ]
+    for i, x in enumerate(cases):
+        r1, b1 = O.decodeChunkFrame(cfg, x, mod, rep, raw=True)
+        r2, b2 = emu_decode_chunk_frame(emu, O, cfg, mod, rep, x)
+        assert results_equal(r1, b1, r2, b2, check_metrics=False) == [], (mode, i)
+
+
+def _compare_stream(O, emu, mode, x, push=None):
+    cfg, mod, rep, _ = MODES[mode]
+    rx = O.StreamingReceiver(cfg, mod, rep)
+    want = rx.push(x, 4096, raw=True)
+    got, cnt = emu_stream(emu, O, cfg, mod, rep, x, push=push)
+    assert len(got) == len(want)
+    for (r1, b1), (r2, b2) in zip(want, got):
+        assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == []
+    c = rx.counters()
+    for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived"):
+        assert c[k] == cnt[k], k
+    return want
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_stream_matches_oracle(O, emu, mode):
+    x, _ = make_stream(O, mode, 3, 3)
+    _compare_stream(O, emu, mode, x)
+    _compare_stream(O, emu, mode, x, push=8 * 4096)
+
+
+@pytest.mark.parametrize("lead", [0, 777, 3000, 4000])
+def test_stream_block_alignment(O, emu, lead):
+    # different alignments of the frames against the 4096-sample call cadence move the end-of-buffer commits
+    x, pay = make_stream(O, "16-QAM", 5, 11, lead=lead, gaps=[0, 100, 5000, 333])
+    ev = _compare_stream(O, emu, "16-QAM", x)
+    assert sum(1 for r, _ in ev if r.crc_valid) == 6
+
+
+def test_stream_low_and_high_snr(O, emu):
+    x, _ = make_stream(O, "QPSK", 4, 12, snr_db=8.0)
+    _compare_stream(O, emu, "QPSK", x)
+    x, _ = make_stream(O, "16-QAM", 4, 13, snr_db=60.0)
+    _compare_stream(O, emu, "16-QAM", x)
+
+
+def test_stream_noise_free_plateau(O, emu):
+    # exact ties on the plateau: the first plateau sample must win (reference: sums unchanged by exact zeros)
+    x, _ = make_stream(O, "16-QAM", 3, 14, noise=False)
+    _compare_stream(O, emu, "16-QAM", x)
+
+
+def test_stream_without_metadata(O, emu):
+    # data frames only: every frame is cut by the 280-byte window and fails to parse the same way
+    x, _ = make_stream(O, "16-QAM", 3, 15, meta=False, lead=5000)
+    _compare_stream(O, emu, "16-QAM", x)
+
+
+def test_stream_long_idle_noise_drift(O, emu):
+    # 60 calls of pure noise before the frames: the reference's block-boundary defect accumulates in its sliding
+    # sums; the walker must carry the same defect (Ep, Ea, Eb)
+    rng = np.random.default_rng(5)
+    x, _ = make_stream(O, "QPSK", 2, 16)
+    noise = (rng.standard_normal(60 * 4096) * 0.03).astype(np.float32)
+    _compare_stream(O, emu, "QPSK", np.concatenate([noise, x]))
+
+
+def test_stream_second_metadata_changes_chunk_size(O, emu):
+    cfg, mod, rep, _ = MODES["QPSK"]
+    parts = [O.buildMetadataFrame(cfg, 2, 4096, 2048, "a", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(i, 2048), i, mod, rep) for i in range(2)]
+    m2 = O.buildMetadataFrame(cfg, 3, 1536, 512, "b", mod, rep)
+    parts.append(m2[13230 - 2205:])
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(10 + i, 512), i, mod, rep) for i in range(3)]
+    from helpers import pad_blocks
+
+    x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 3))
+    ev = _compare_stream(O, emu, "QPSK", x)
+    assert sum(1 for r, _ in ev if r.frame_type == 0xFE and r.crc_valid) >= 1
