@@ -482,9 +482,11 @@ __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int
 
 // argmax of the metric with the reference's first-maximum rule (modem.js:308).  The reference's sums are
 // sliding float64 accumulators, ours are prefix differences: both carry ~1e-13 relative noise, so values
-// within 1e-9 of the maximum count as tied.  A tie confined to one contiguous run of offsets is a plateau
-// (exactly equal values in the reference): the first offset wins.  A tie between separate runs cannot be
-// decided here; `ambiguous` is set and k_replay settles it with the reference's own sequential recurrence.
+// within 1e-9 of the maximum count as tied.  With noise in the signal the maximum is unique and this kernel
+// decides.  Any tie (a noise-free plateau, or separate offsets such as a junction of two identical symbols)
+// is decided in the reference by its own rounding sequence: exactly equal values on an even-bin plateau (first
+// wins), last-ulp differences on an odd-bin plateau after DC removal.  `ambiguous` is then set and k_replay
+// settles it with the reference's own sequential recurrence.
 __global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metric, int64_t stride, const int64_t* __restrict__ lens,
                                                  int64_t n_default, const double* __restrict__ tile_max, int tiles,
                                                  int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous) {
@@ -521,8 +523,7 @@ __global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metri
     __syncthreads();
     if (tid == 0) {
         best_out[r] = best;
-        const bool contiguous = scount == slast - sfirst + 1;
-        ambiguous[r] = contiguous ? 0 : 1;
+        ambiguous[r] = scount > 1 ? 1 : 0;
         idx_out[r] = best > 0.5 ? (int64_t)sfirst : -1;
     }
 }

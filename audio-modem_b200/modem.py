@@ -238,6 +238,8 @@ class Modem:
 
     def stream_push(self, x=None, n_new=None, raw=False, collect=True):
         """x: [n_streams][n_new] float32 (numpy = host, torch.cuda tensor = device, None = already written in place)."""
+        if not self._stream_open:
+            raise AmbError("stream not open")
         if x is None:
             mem, ptr, xs = MEM_INPLACE, None, 0
         elif _is_torch(x):

@@ -281,7 +281,7 @@ def demodulateOFDM(cfg, x, mod, chRe, chIm, with_eq=False):
     n = lib().orc_demodulate(_cfg(cfg), _mod(mod), _p(x, C.c_float), len(x), _p(cr, C.c_double), _p(ci, C.c_double),
                              _p(bits, C.c_uint8), _p(eq, C.c_double) if with_eq else None)
     bits = bits[:n]
-    return (bits, eq.reshape(-1, 2)) if with_eq else bits
+    return (bits, eq[: 2 * (n // bps)].reshape(-1, 2)) if with_eq else bits
 
 
 def crc32(data):
