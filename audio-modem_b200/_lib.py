@@ -37,6 +37,8 @@ EXPORTS = {
     "amb_synchronize": (C.c_int, [C.c_void_p]),
     "amb_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "amb_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "amb_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "amb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
     "amb_estimate_frame_samples": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "amb_config_info": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "amb_preamble_symbol1": (C.c_int, [C.c_int, C.c_void_p]),
@@ -56,6 +58,11 @@ EXPORTS = {
     "amb_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                   C.c_void_p, C.c_int64, C.c_int]),
     "amb_stream_counters": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "amb_chunk_frame_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
+    "amb_build_data_chunk_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int32, C.c_uint64, C.c_void_p,
+                                              C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_int]),
+    "amb_build_metadata_frame": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
+                                           C.c_uint64, C.c_int64, C.c_int]),
 }
 
 _lib = None

@@ -31,6 +31,7 @@ struct DevBuf {
 };
 
 struct PendingCopy { void* host; const void* dev; size_t bytes; };
+struct ProfSpan { const char* name; cudaEvent_t a, b; };
 
 }  // namespace
 
@@ -42,9 +43,14 @@ struct amb_modem {
     AmbEmaTables* d_ema = nullptr;
     std::string err;
     int64_t launches = 0;
+    // optional per-kernel device timing (CUDA events on the handle's stream)
+    bool prof = false;
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
     // scratch
     DevBuf in_a, in_b, in_c, in_lens, out_a, out_b, out_c, out_res, out_bytes;
-    DevBuf jobs, idx, xf, psum, pmin, pmax, norm, metric, tile_max, amb, cidx, cbest;
+    DevBuf jobs, idx, xf, psum, pmin, pmax, norm, metric, tile_max, amb, cidx, cbest, tx_pay, tx_out, tx_copy;
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
@@ -63,6 +69,14 @@ struct amb_modem {
         }                                                                                          \
     } while (0)
 
+#define LAUNCH(NAME, ...)                                                                          \
+    do {                                                                                           \
+        prof_mark(m, NAME, 0);                                                                     \
+        __VA_ARGS__;                                                                               \
+        prof_mark(m, NAME, 1);                                                                     \
+        LAUNCH_OK();                                                                               \
+    } while (0)
+
 #define LAUNCH_OK()                                                                                \
     do {                                                                                           \
         m->launches++;                                                                             \
@@ -71,6 +85,20 @@ struct amb_modem {
     } while (0)
 
 namespace {
+
+// start (which = 0) / end (which = 1) event of one kernel launch; no-op unless amb_profile(m, 1)
+void prof_mark(amb_modem* m, const char* name, int which) {
+    if (!m->prof) return;
+    if (m->prof_used == m->prof_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        m->prof_pool.push_back(e);
+    }
+    cudaEvent_t e = m->prof_pool[m->prof_used++];
+    cudaEventRecord(e, m->stream);
+    if (which == 0) m->prof_spans.push_back({name, e, nullptr});
+    else if (!m->prof_spans.empty()) m->prof_spans.back().b = e;
+}
 
 int fail(amb_modem* m, int code, const char* msg) { m->err = msg; return code; }
 
@@ -120,16 +148,14 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     const AmbTables& T = m->tables;
     const int64_t idx_stride = (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data;
     CK(m->idx.ensure((size_t)n_jobs * idx_stride));
-    if (frame_max) { k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs); LAUNCH_OK(); }
+    if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));
     o.idx = m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
     const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
-    k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o);
-    LAUNCH_OK();
-    k_parse<<<blocks_for(n_jobs, 4), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
-                                                          d_res, d_bytes, bytes_stride);
-    LAUNCH_OK();
+    LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
+    LAUNCH("k_parse", k_parse<<<blocks_for(n_jobs, 4), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
+                                                          d_res, d_bytes, bytes_stride));
     return AMB_OK;
 }
 
@@ -145,10 +171,8 @@ int run_stats(amb_modem* m, const float* d_x, int64_t stride, const int64_t* d_l
     const int parts = (int)((max_len + AMB_STAT_PART - 1) / AMB_STAT_PART) > 0 ? (int)((max_len + AMB_STAT_PART - 1) / AMB_STAT_PART) : 1;
     CK(m->psum.ensure((size_t)n * parts * 8)); CK(m->pmin.ensure((size_t)n * parts * 4)); CK(m->pmax.ensure((size_t)n * parts * 4));
     CK(m->xf.ensure((size_t)n * sizeof(AmbXform)));
-    k_stats_partial<<<n * parts, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>());
-    LAUNCH_OK();
-    k_stats_final<<<blocks_for(n, 128), 128, 0, m->stream>>>(d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>(), n, m->xf.as<AmbXform>());
-    LAUNCH_OK();
+    LAUNCH("k_stats_partial", k_stats_partial<<<n * parts, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>()));
+    LAUNCH("k_stats_final", k_stats_final<<<blocks_for(n, 128), 128, 0, m->stream>>>(d_lens, stride, parts, m->psum.as<double>(), m->pmin.as<float>(), m->pmax.as<float>(), n, m->xf.as<AmbXform>()));
     return AMB_OK;
 }
 
@@ -156,8 +180,7 @@ int run_apply(amb_modem* m, const float* d_x, int64_t stride, const int64_t* d_l
     int per = (int)((max_len + 256 * 8 - 1) / (256 * 8));
     if (per < 1) per = 1;
     if (per > 4096) per = 4096;
-    k_apply_xform<<<n * per, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, per, m->xf.as<AmbXform>(), d_out);
-    LAUNCH_OK();
+    LAUNCH("k_apply_xform", k_apply_xform<<<n * per, 256, 0, m->stream>>>(d_x, stride, d_lens, stride, per, m->xf.as<AmbXform>(), d_out));
     return AMB_OK;
 }
 
@@ -166,13 +189,10 @@ int run_detect(amb_modem* m, const float* d_y, int64_t stride, const int64_t* d_
     const int tiles = (int)((max_len + AMB_TILE - 1) / AMB_TILE) > 0 ? (int)((max_len + AMB_TILE - 1) / AMB_TILE) : 1;
     CK(m->metric.ensure((size_t)n * (size_t)stride * 8)); CK(m->tile_max.ensure((size_t)n * tiles * 8));
     CK(m->amb.ensure((size_t)n * 4)); CK(m->cidx.ensure((size_t)n * 8)); CK(m->cbest.ensure((size_t)n * 8));
-    k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->metric.as<double>(), tiles, m->tile_max.as<double>());
-    LAUNCH_OK();
-    k_argmax<<<n, 256, 0, m->stream>>>(m->metric.as<double>(), stride, d_lens, stride, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
-                                      m->cbest.as<double>(), m->amb.as<int>());
-    LAUNCH_OK();
-    k_replay<<<blocks_for(n, 64), 64, 0, m->stream>>>(d_y, stride, d_lens, stride, n, 0.01, m->amb.as<int>(), m->cidx.as<int64_t>(), m->cbest.as<double>());
-    LAUNCH_OK();
+    LAUNCH("k_metric", k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->metric.as<double>(), tiles, m->tile_max.as<double>()));
+    LAUNCH("k_argmax", k_argmax<<<n, 256, 0, m->stream>>>(m->metric.as<double>(), stride, d_lens, stride, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
+                                      m->cbest.as<double>(), m->amb.as<int>()));
+    LAUNCH("k_replay", k_replay<<<blocks_for(n, 64), 64, 0, m->stream>>>(d_y, stride, d_lens, stride, n, 0.01, m->amb.as<int>(), m->cidx.as<int64_t>(), m->cbest.as<double>()));
     return AMB_OK;
 }
 
@@ -228,6 +248,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_scan_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
+    cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
     *out = m;
     return AMB_OK;
 }
@@ -237,10 +258,11 @@ void amb_destroy(amb_modem* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx,
-                     &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->raw, &m->cleaned,
+                     &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp};
     for (DevBuf* b : all) b->release();
+    for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
     if (m->d_ema) cudaFree(m->d_ema);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -251,6 +273,41 @@ const char* amb_last_error(const amb_modem* m) { return m ? m->err.c_str() : "nu
 int amb_synchronize(amb_modem* m) { if (!m) return AMB_E_INVALID; CK(cudaStreamSynchronize(m->stream)); return AMB_OK; }
 void* amb_cuda_stream(amb_modem* m) { return m ? (void*)m->stream : nullptr; }
 int64_t amb_kernel_launches(const amb_modem* m) { return m ? m->launches : 0; }
+
+int amb_profile(amb_modem* m, int enable) {
+    if (!m) return AMB_E_INVALID;
+    CK(cudaStreamSynchronize(m->stream));
+    m->prof = enable != 0;
+    m->prof_spans.clear();
+    m->prof_used = 0;
+    return AMB_OK;
+}
+
+int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n) {
+    if (!m || !n) return AMB_E_INVALID;
+    CK(cudaStreamSynchronize(m->stream));
+    std::vector<std::string> keys;
+    std::vector<double> ms;
+    std::vector<int64_t> cnt;
+    for (auto& sp : m->prof_spans) {
+        if (!sp.b) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) != cudaSuccess) continue;
+        size_t k = 0;
+        for (; k < keys.size(); k++) if (keys[k] == sp.name) break;
+        if (k == keys.size()) { keys.push_back(sp.name); ms.push_back(0.0); cnt.push_back(0); }
+        ms[k] += t; cnt[k]++;
+    }
+    *n = (int)keys.size();
+    for (int k = 0; k < *n && k < cap; k++) {
+        if (names) { std::strncpy(names + 32 * k, keys[k].c_str(), 31); names[32 * k + 31] = 0; }
+        if (total_ms) total_ms[k] = ms[k];
+        if (launches) launches[k] = cnt[k];
+    }
+    m->prof_spans.clear();
+    m->prof_used = 0;
+    return AMB_OK;
+}
 
 int64_t amb_estimate_frame_samples(int config, int constellation, int64_t payload_bytes, int repetition) {
     return amb_tables_estimate_frame_samples(config, constellation, payload_bytes, repetition);
@@ -282,8 +339,7 @@ int amb_crc32(amb_modem* m, const uint8_t* data, int64_t stride, const int64_t* 
     if ((rc = in_ptr(m, data, (size_t)n * stride, mem, m->in_a, &d_data))) return rc;
     if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
     if ((rc = out_ptr(m, out, (size_t)n, mem, m->out_a, &d_out))) return rc;
-    k_crc32<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out);
-    LAUNCH_OK();
+    LAUNCH("k_crc32", k_crc32<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out));
     return flush(m);
 }
 
@@ -333,10 +389,8 @@ int amb_detect_preamble_xcorr(amb_modem* m, const float* x, int64_t stride, cons
     const int64_t max_pos = stride >= plen ? (stride - plen) / step + 1 : 1;
     CK(m->metric.ensure((size_t)n * max_pos * 8));
     const int per = blocks_for(max_pos, 128);
-    k_xcorr_coarse<<<n * per, 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, step, per, m->metric.as<double>(), max_pos);
-    LAUNCH_OK();
-    k_xcorr_pick<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, step, m->metric.as<double>(), max_pos, d_idx, d_best);
-    LAUNCH_OK();
+    LAUNCH("k_xcorr_coarse", k_xcorr_coarse<<<n * per, 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, step, per, m->metric.as<double>(), max_pos));
+    LAUNCH("k_xcorr_pick", k_xcorr_pick<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, step, m->metric.as<double>(), max_pos, d_idx, d_best));
     if (mem == AMB_MEM_HOST) {
         if (idx_out) m->pending.push_back({idx_out, d_idx, (size_t)n * 8});
         if (metric_out) m->pending.push_back({metric_out, d_best, (size_t)n * 8});
@@ -360,13 +414,11 @@ int amb_estimate_channel(amb_modem* m, const float* ce, int n, const double* kno
     if ((rc = out_ptr(m, ch_im, (size_t)n * AMB_FFT, mem, m->out_b, &d_hi))) return rc;
     if (!d_hr || !d_hi) return fail(m, AMB_E_INVALID, "ch_re/ch_im required");
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_ce, stride, nullptr, stride, n, 1, m->jobs.as<AmbJob>());
-    LAUNCH_OK();
+    LAUNCH("k_jobs_rows", k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_ce, stride, nullptr, stride, n, 1, m->jobs.as<AmbJob>()));
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));
     o.h_out_re = d_hr; o.h_out_im = d_hi; o.known_re = d_kr; o.known_im = d_ki;
-    k_demod<<<dim3(n, 1), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o);
-    LAUNCH_OK();
+    LAUNCH("k_demod", k_demod<<<dim3(n, 1), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o));
     return flush(m);
 }
 
@@ -388,15 +440,13 @@ int amb_demodulate(amb_modem* m, const float* signal, int64_t stride, const int6
     if ((rc = out_ptr(m, bits, (size_t)n * bits_stride, mem, m->out_a, &d_bits))) return rc;
     if ((rc = out_ptr(m, eq_out, (size_t)n * eq_stride * 2, mem, m->out_b, &d_eq))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, 0, m->jobs.as<AmbJob>());
-    LAUNCH_OK();
+    LAUNCH("k_jobs_rows", k_jobs_rows<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, 0, m->jobs.as<AmbJob>()));
     if (max_nsym > 0) {
         AmbDemodOut o;
         std::memset(&o, 0, sizeof(o));
         o.bits = d_bits; o.bits_stride = bits_stride; o.eq = d_eq; o.eq_stride = eq_stride; o.h_re = d_hr; o.h_im = d_hi;
         const int groups = (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP;
-        k_demod<<<dim3(n, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o);
-        LAUNCH_OK();
+        LAUNCH("k_demod", k_demod<<<dim3(n, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, o));
     }
     if (nbits_out) {
         if (mem != AMB_MEM_HOST) return fail(m, AMB_E_INVALID, "nbits_out is a host-side convenience (pass NULL with device memory)");
@@ -417,8 +467,7 @@ int amb_decode_chunk_frames(amb_modem* m, const float* frames, int64_t stride, c
     if ((rc = out_ptr(m, results, (size_t)n, mem, m->out_res, &d_res))) return rc;
     if ((rc = out_ptr(m, bytes_out, (size_t)n * bytes_stride, mem, m->out_bytes, &d_bytes))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    k_jobs_chunk<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, m->jobs.as<AmbJob>());
-    LAUNCH_OK();
+    LAUNCH("k_jobs_chunk", k_jobs_chunk<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(stride / T.sym_len) - 3;
     if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
     return flush(m);
@@ -441,9 +490,8 @@ int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, co
     if ((rc = run_apply(m, d_x, stride, d_lens, n, max_len, m->norm.as<float>()))) return rc;
     if ((rc = run_detect(m, m->norm.as<float>(), stride, d_lens, n, max_len))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
-                                                             m->cbest.as<double>(), m->jobs.as<AmbJob>());
-    LAUNCH_OK();
+    LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
+                                                             m->cbest.as<double>(), m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(max_len / T.sym_len);
     if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
     return flush(m);
@@ -553,15 +601,12 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     // 1. DC removal
     const int64_t n_chunks = n_new / AMB_CHUNK;
     const int per = blocks_for(n_chunks, 4);
-    k_ema_agg<<<ns * per, 128, 0, m->stream>>>(raw, m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>());
-    LAUNCH_OK();
-    k_ema_apply<<<ns * per, 128, 0, m->stream>>>(raw, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
-                                                 m->states.as<AmbStreamState>(), m->dc_next.as<double>());
-    LAUNCH_OK();
+    LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(raw, m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>()));
+    LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(raw, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
+                                                 m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
     // 2. window-sum summaries of the new window-end samples
     const int tiles = (int)(n_new / AMB_TILE);
-    k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride);
-    LAUNCH_OK();
+    LAUNCH("k_scan_sums", k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride));
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;
     g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
@@ -583,14 +628,11 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         CK(cudaMemsetAsync(m->nrec.p, 0, (size_t)ns * 4, m->stream));
         CK(cudaMemsetAsync(m->n_redo.p, 0, 4, m->stream));
         CK(cudaMemsetAsync(m->total.p, 0, 16, m->stream));
-        k_walk<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
-                                                             m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>());
-        LAUNCH_OK();
-        k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>());
-        LAUNCH_OK();
-        k_jobs_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
-                                                                  m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1);
-        LAUNCH_OK();
+        LAUNCH("k_walk", k_walk<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+                                                             m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>()));
+        LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));
+        LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
+                                                                  m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1));
         int tot[2] = {0, 0};   // frames, max data symbols
         CK(cudaMemcpyAsync(tot, m->total.p, 8, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaStreamSynchronize(m->stream));
@@ -601,15 +643,12 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
         if ((rc = run_demod_parse(m, total, tot[1], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
-        k_post_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+        LAUNCH("k_post_stream", k_post_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                   m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
-                                                                  m->redo.as<int>(), m->n_redo.as<int>());
-        LAUNCH_OK();
-        k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2);
-        LAUNCH_OK();
-        k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
-                                               bytes_stride, n_out, max_results, dst_res, dst_bytes);
-        LAUNCH_OK();
+                                                                  m->redo.as<int>(), m->n_redo.as<int>()));
+        LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
+        LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
+                                               bytes_stride, n_out, max_results, dst_res, dst_bytes));
         int kept = 0, n_redo = 0;
         CK(cudaMemcpyAsync(&kept, m->total.as<int>() + 2, 4, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaMemcpyAsync(&n_redo, m->n_redo.p, 4, cudaMemcpyDeviceToHost, m->stream));
@@ -634,6 +673,58 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     if ((rc = stream_compact(m))) return rc;
     CK(cudaStreamSynchronize(m->stream));
     return overflow ? AMB_E_OVERFLOW : AMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- transmit side
+int64_t amb_chunk_frame_samples(amb_modem* m, int64_t payload_bytes, int is_first_frame) {
+    if (!m) return -1;
+    return amb_tx_frame_samples(&m->tables, payload_bytes, is_first_frame);
+}
+
+static int tx_run(amb_modem* m, const uint8_t* d_pay, int64_t pay_stride, int pay_len, int n, int first, float* out, int64_t out_stride,
+                  double sigma, uint64_t seed, int64_t g0, int mem) {
+    const int64_t total = amb_tx_frame_samples(&m->tables, pay_len, first);
+    if (out_stride < total) return fail(m, AMB_E_INVALID, "out_stride smaller than the frame");
+    float* d_out = out;
+    if (mem == AMB_MEM_HOST) { CK(m->tx_out.ensure((size_t)n * out_stride * 4)); d_out = m->tx_out.as<float>(); CK(cudaMemsetAsync(d_out, 0, (size_t)n * out_stride * 4, m->stream)); }
+    AmbTxArgs a;
+    a.payloads = d_pay; a.payload_stride = pay_stride; a.payload_len = pay_len; a.first = first; a.out = d_out; a.out_stride = out_stride;
+    a.noise_sigma = sigma; a.noise_seed = seed; a.noise_g0 = g0;
+    LAUNCH("k_tx_frames", k_tx_frames<<<n, 256, AMB_TX_SMEM, m->stream>>>(m->d_tables, a, n));
+    if (mem == AMB_MEM_HOST) m->pending.push_back({out, d_out, (size_t)n * out_stride * 4});
+    return AMB_OK;
+}
+
+int amb_build_data_chunk_frames(amb_modem* m, const uint8_t* data, int64_t data_stride, int data_len, int n, int32_t seq0,
+                                uint64_t synth_seed, float* out, int64_t out_stride, double noise_sigma, uint64_t noise_seed,
+                                int64_t noise_g0, uint8_t* data_copy, int mem) {
+    int rc = check_common(m, n, out_stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    if (!out || data_len < 0 || data_len > 65535) return fail(m, AMB_E_INVALID, "bad argument");
+    const uint8_t* d_data; uint8_t* d_copy;
+    if ((rc = in_ptr(m, data, (size_t)n * (data ? data_stride : 0), mem, m->in_a, &d_data))) return rc;
+    if ((rc = out_ptr(m, data_copy, (size_t)n * data_len, mem, m->tx_copy, &d_copy))) return rc;
+    const int pay_len = data_len + 11;
+    CK(m->tx_pay.ensure((size_t)n * pay_len));
+    LAUNCH("k_tx_chunk_payloads", k_tx_chunk_payloads<<<blocks_for(n, 64), 64, 0, m->stream>>>(m->d_tables, d_data, data_stride, data_len, n, seq0, synth_seed,
+                                                                 m->tx_pay.as<uint8_t>(), pay_len, d_copy, data_len));
+    if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, n, 0, out, out_stride, noise_sigma, noise_seed, noise_g0, mem))) return rc;
+    return flush(m);
+}
+
+int amb_build_metadata_frame(amb_modem* m, int32_t total_chunks, int32_t total_file_size, int32_t chunk_size, const uint8_t* name,
+                             int name_len, float* out, double noise_sigma, uint64_t noise_seed, int64_t noise_g0, int mem) {
+    int rc = check_common(m, 1, 0, mem); if (rc) return rc;
+    if (!out) return fail(m, AMB_E_INVALID, "out required");
+    static const uint8_t dflt[4] = {'f', 'i', 'l', 'e'};                 // `fileName || 'file'`
+    if (!name || name_len <= 0) { name = dflt; name_len = 4; }
+    uint8_t pay[300];
+    const int pay_len = amb_metadata_payload(m->tables.crc_table, total_chunks, total_file_size, chunk_size, name, name_len, pay);
+    CK(m->tx_pay.ensure(512));
+    CK(cudaMemcpyAsync(m->tx_pay.p, pay, (size_t)pay_len, cudaMemcpyHostToDevice, m->stream));
+    const int64_t total = amb_tx_frame_samples(&m->tables, pay_len, 1);
+    if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, 1, 1, out, total, noise_sigma, noise_seed, noise_g0, mem))) return rc;
+    return flush(m);
 }
 
 int amb_stream_counters(amb_modem* m, int stream, int64_t* out8) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "amb_walker.cuh"
+#include "amb_tx.cuh"
 
 #define AMB_TILE 4096        // samples per scan tile (= the reference's audio block, app.js:1107)
 #define AMB_CHUNK 512        // EMA carry granularity
@@ -786,4 +787,76 @@ __global__ void k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap,
     const int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, states[s], &st, keep + o);
     states[s] = st;
     if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
+}
+
+// ================================================================================================
+// Transmit path: buildDataChunkFrame / buildMetadataFrame (modem.js:718-766), float64-faithful, plus the
+// synthetic-input options used by bench.py and the tests (counter-based payload bytes, AWGN).
+// ================================================================================================
+// one thread per frame: [0xFF][seq][len][data][crc]; data from `data` rows or, when NULL, amb_synth_byte
+__global__ void k_tx_chunk_payloads(const AmbTables* __restrict__ T, const uint8_t* __restrict__ data, int64_t data_stride, int data_len,
+                                    int n, int32_t seq0, uint64_t synth_seed, uint8_t* __restrict__ payloads, int64_t payload_stride,
+                                    uint8_t* __restrict__ data_copy, int64_t copy_stride) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    uint8_t* out = payloads + (int64_t)f * payload_stride;
+    const int32_t seq = seq0 + f;
+    int off = 0;
+    out[off++] = 0xFF;
+    out[off++] = (uint8_t)(seq >> 24); out[off++] = (uint8_t)(seq >> 16); out[off++] = (uint8_t)(seq >> 8); out[off++] = (uint8_t)seq;
+    out[off++] = (uint8_t)(data_len >> 8); out[off++] = (uint8_t)data_len;
+    for (int i = 0; i < data_len; i++) {
+        const uint8_t b = data ? data[(int64_t)f * data_stride + i] : amb_synth_byte(synth_seed, seq, i);
+        out[off++] = b;
+        if (data_copy) data_copy[(int64_t)f * copy_stride + i] = b;
+    }
+    const uint32_t cs = amb_crc32_bytes(T->crc_table, out, off);
+    out[off++] = (uint8_t)(cs >> 24); out[off++] = (uint8_t)(cs >> 16); out[off++] = (uint8_t)(cs >> 8); out[off++] = (uint8_t)cs;
+}
+
+struct AmbTxArgs {
+    const uint8_t* payloads; int64_t payload_stride; int payload_len;
+    int first;                 // 1: metadata-style lead-in silence (isFirstFrame)
+    float* out; int64_t out_stride;
+    double noise_sigma; uint64_t noise_seed; int64_t noise_g0;
+};
+
+#define AMB_TX_WARPS 8
+#define AMB_TX_SMEM (AMB_TX_WARPS * 2 * AMB_FFT * 8)
+
+__global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__ T, AmbTxArgs a, int n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int f = blockIdx.x;
+    if (f >= n) return;
+    const int warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const uint8_t* payload = a.payloads + (int64_t)f * a.payload_stride;
+    const int64_t nsym = amb_tx_num_symbols(T, a.payload_len);
+    const int64_t pre = amb_tx_silence_pre(T, a.first), post = amb_tx_silence_post();
+    const int64_t sym = T->sym_len, total = pre + (3 + nsym) * sym + post;
+    float* out = a.out + (int64_t)f * a.out_stride;
+    for (int64_t i = tid; i < pre; i += 256) out[i] = 0.f;
+    for (int64_t i = tid; i < post; i += 256) out[total - post + i] = 0.f;
+    for (int i = tid; i < sym; i += 256) { out[pre + i] = T->pre1[i]; out[pre + sym + i] = T->pre2[i]; out[pre + 2 * sym + i] = T->ce_sym[i]; }
+    double* re = work + warp * 2 * AMB_FFT;
+    double* im = re + AMB_FFT;
+    for (int64_t s = warp; s < nsym; s += AMB_TX_WARPS) amb_tx_symbol(T, payload, a.payload_len, s, re, im, out + pre + (3 + s) * sym);
+    __syncthreads();
+    // normalise the whole frame to peak 0.8 (modem.js:751-753)
+    float mx = 0.f;
+    for (int64_t i = tid; i < total; i += 256) mx = fmaxf(mx, fabsf(out[i]));
+    __shared__ float red[8];
+    mx = warp_maxf(mx);
+    if ((tid & 31) == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
+    const double s = mx > 0.f ? 0.8 / (double)mx : 1.0;
+    const int64_t g0 = a.noise_g0 + (int64_t)f * a.out_stride;
+    for (int64_t i = tid; i < total; i += 256) {
+        float v = out[i];
+        if (mx > 0.f) v = (float)amb_mul((double)v, s);
+        if (a.noise_sigma > 0.0) v = (float)((double)v + a.noise_sigma * amb_synth_normal(a.noise_seed, g0 + i));
+        out[i] = v;
+    }
 }

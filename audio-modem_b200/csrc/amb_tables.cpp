@@ -107,6 +107,9 @@ int amb_tables_build(AmbTables* t, int config, int constellation, int repetition
     for (int i = 0; i < c.sym; i++) e += (double)t->pre1[i] * (double)t->pre1[i];
     t->pre1_energy = e;
 
+    make_symbol(c, 43, 1, t->pre2, nullptr);
+    make_symbol(c, 44, 1, t->ce_sym, nullptr);
+
     // constellations
     if (constellation == 0) {
         const double p[4] = {1, 0, -1, 0};
@@ -137,6 +140,17 @@ int amb_tables_build(AmbTables* t, int config, int constellation, int repetition
         double wr = 1, wi = 0;
         for (int j = 0; j < half; j++) {
             t->tw_re[half + j] = wr; t->tw_im[half + j] = wi;
+            const double nr = wr * cr - wi * ci;
+            wi = wr * ci + wi * cr;
+            wr = nr;
+        }
+    }
+    for (int half = 1; half <= AMB_HALF; half <<= 1) {
+        const double angle = 1.0 * 2 * M_PI / (2 * half);
+        const double cr = std::cos(angle), ci = std::sin(angle);
+        double wr = 1, wi = 0;
+        for (int j = 0; j < half; j++) {
+            t->twi_re[half + j] = wr; t->twi_im[half + j] = wi;
             const double nr = wr * cr - wi * ci;
             wi = wr * ci + wi * cr;
             wr = nr;

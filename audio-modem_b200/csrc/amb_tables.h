@@ -31,6 +31,11 @@ struct AmbTables {
     // --- forward FFT twiddles: tw[half + j], j < half, half = 1..256; running product of modem.js:41-43 ---
     double tw_re[AMB_FFT];
     double tw_im[AMB_FFT];
+    // --- transmit side (modem.js:172-184, :186-200, :15-24): preamble-2 and CE symbols incl. CP, inverse twiddles ---
+    float pre2[AMB_MAX_SYM];
+    float ce_sym[AMB_MAX_SYM];
+    double twi_re[AMB_FFT];         // inverse-transform running product (angle +2*pi/size)
+    double twi_im[AMB_FFT];
     // --- CRC-32 table, modem.js:443-451 ---
     uint32_t crc_table[256];
     // --- EMA DC removal, app.js:734, :753 ---

@@ -125,6 +125,23 @@ class Modem:
     def kernel_launches(self):
         return int(self._L.amb_kernel_launches(self._h))
 
+    def profile(self, enable=True):
+        """bracket every kernel launch with CUDA events on the handle's stream (device time per kernel)"""
+        self._ck(self._L.amb_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since the last read"""
+        cap = 64
+        names = C.create_string_buffer(32 * cap)
+        ms = (C.c_double * cap)()
+        cnt = (C.c_int64 * cap)()
+        n = C.c_int(0)
+        self._ck(self._L.amb_profile_read(self._h, names, ms, cnt, cap, C.byref(n)))
+        out = {}
+        for k in range(min(n.value, cap)):
+            out[names.raw[32 * k:32 * k + 32].split(b"\0")[0].decode()] = (ms[k], int(cnt[k]))
+        return out
+
     def cuda_stream(self):
         return self._L.amb_cuda_stream(self._h)
 
@@ -211,6 +228,50 @@ class Modem:
     def decode_received_signals(self, recordings, raw=False):
         """decodeReceivedSignal (modem.js:557) over many recordings"""
         return self._decode(self._L.amb_decode_received_signals, recordings, raw)
+
+    # ------------------------------------------------------------------ transmit side
+    def chunk_frame_samples(self, payload_bytes, first=False):
+        """estimateFrameSamplesWithSilence (modem.js:876-884)"""
+        return int(self._L.amb_chunk_frame_samples(self._h, payload_bytes, int(first)))
+
+    def build_data_chunk_frames(self, chunks=None, seq0=0, n=None, data_len=None, synth_seed=0, noise_sigma=0.0, noise_seed=0,
+                                noise_g0=0, out=None, return_data=False):
+        """buildDataChunkFrame (modem.js:763) for many chunks.  chunks: [n][data_len] uint8 (or list of equal-length bytes),
+        or None for synthetic chunk bytes.  out: optional torch.cuda float32 tensor [n][stride] to fill on the device."""
+        if chunks is not None:
+            data = np.ascontiguousarray(np.stack([np.frombuffer(bytes(c), np.uint8) if isinstance(c, (bytes, bytearray)) else np.asarray(c, np.uint8)
+                                                  for c in chunks]))
+            n, data_len = data.shape
+        else:
+            data = None
+        flen = self.chunk_frame_samples(data_len + 11, False)
+        copy = np.zeros((n, max(data_len, 1)), np.uint8)[:, :data_len] if return_data else None
+        if copy is not None:
+            copy = np.ascontiguousarray(copy)
+        if out is None:
+            frames = np.zeros((n, flen), np.float32)
+            self._ck(self._L.amb_build_data_chunk_frames(self._h, _ptr(data), data_len if data is not None else 0, data_len, n, seq0, synth_seed,
+                                                        _ptr(frames), flen, noise_sigma, noise_seed, noise_g0, _ptr(copy), MEM_HOST))
+            return (frames, copy) if return_data else frames
+        assert _is_torch(out) and out.is_cuda and data is None and not return_data
+        self._ck(self._L.amb_build_data_chunk_frames(self._h, None, 0, data_len, n, seq0, synth_seed, _ptr(out), out.stride(0), noise_sigma,
+                                                    noise_seed, noise_g0, None, MEM_DEVICE))
+        return out
+
+    def build_metadata_frame(self, totalChunks, totalFileSize, chunkSize, fileName="file", noise_sigma=0.0, noise_seed=0, noise_g0=0, out=None):
+        """buildMetadataFrame (modem.js:758)"""
+        name = np.frombuffer((fileName or "file").encode("utf-8"), np.uint8)
+        name = np.ascontiguousarray(name[:255])
+        flen = self.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len(name) + 4, True)
+        if out is None:
+            frame = np.zeros(flen, np.float32)
+            self._ck(self._L.amb_build_metadata_frame(self._h, totalChunks, totalFileSize, chunkSize, _ptr(name), len(name), _ptr(frame),
+                                                     noise_sigma, noise_seed, noise_g0, MEM_HOST))
+            return frame
+        assert _is_torch(out) and out.is_cuda and out.numel() >= flen
+        self._ck(self._L.amb_build_metadata_frame(self._h, totalChunks, totalFileSize, chunkSize, _ptr(name), len(name), _ptr(out),
+                                                 noise_sigma, noise_seed, noise_g0, MEM_DEVICE))
+        return flen
 
     # ------------------------------------------------------------------ streaming
     def stream_open(self, n_streams=1, block_len=4096, max_push=4096 * 64, max_results=None, max_chunk=4096):
@@ -351,6 +412,16 @@ def decodeReceivedSignal(signal, modName, repetition=1):
 
 def decodeChunkFrame(frameSamples, modName, repetition=1):
     return _modem(modName, repetition).decode_chunk_frames([frameSamples])[0]
+
+
+def buildDataChunkFrame(chunkData, seqNum, modName, rep=1):
+    """modem.js:763-766"""
+    return _modem(modName, rep).build_data_chunk_frames([chunkData], seq0=seqNum)[0]
+
+
+def buildMetadataFrame(totalChunks, totalFileSize, chunkSize, fileName, modName, rep=1):
+    """modem.js:758-761"""
+    return _modem(modName, rep).build_metadata_frame(totalChunks, totalFileSize, chunkSize, fileName)
 
 
 class StreamingReceiver:

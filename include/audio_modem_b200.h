@@ -122,6 +122,11 @@ const char* amb_last_error(const amb_modem* m);
 int amb_synchronize(amb_modem* m);
 void* amb_cuda_stream(amb_modem* m); /* the cudaStream_t all work is queued on */
 int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by this handle */
+/* per-kernel device time: amb_profile(m, 1) brackets every kernel launch with CUDA events on the handle's stream;
+ * amb_profile_read returns, per kernel name (names = [cap][32] chars), the summed milliseconds and launch count since
+ * the last read, and clears them */
+int amb_profile(amb_modem* m, int enable);
+int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n);
 
 /* ---- pure host helpers (no device work) -------------------------------- */
 /* estimateFrameSamples, modem.js:863-874 */
@@ -179,6 +184,21 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
  * falsePositives (app.js:879-884), receivedCount, crcErrors (app.js:604-605), duplicates, metaReceived,
  * samplesWritten */
 int amb_stream_counters(amb_modem* m, int stream, int64_t* out8);
+
+/* ---- transmit side (the "next" row of the scope table; also synthesises bench / test input on the device) ---- */
+/* samples of one chunk frame incl. its silences: estimateFrameSamplesWithSilence, modem.js:876-884 */
+int64_t amb_chunk_frame_samples(amb_modem* m, int64_t payload_bytes, int is_first_frame);
+/* buildDataChunkFrame, modem.js:763-766 (+ buildDataChunkPayload :694-714, buildChunkOFDMFrame :718-756) for n chunks of
+ * data_len bytes with sequence numbers seq0.. ; frame i is written at out + i*out_stride, bit-identical to the reference's
+ * Float32Array.  data = [n][data_stride] chunk bytes, or NULL for synthetic bytes (SplitMix64 of synth_seed, seq, offset).
+ * noise_sigma > 0 adds white Gaussian noise (counter-based, indexed from noise_g0) after the frame normalisation.
+ * data_copy (optional, [n][data_len]) receives the chunk bytes actually sent. */
+int amb_build_data_chunk_frames(amb_modem* m, const uint8_t* data, int64_t data_stride, int data_len, int n, int32_t seq0,
+                                uint64_t synth_seed, float* out, int64_t out_stride, double noise_sigma, uint64_t noise_seed,
+                                int64_t noise_g0, uint8_t* data_copy, int mem);
+/* buildMetadataFrame, modem.js:758-761 (+ buildMetadataPayload :666-692) */
+int amb_build_metadata_frame(amb_modem* m, int32_t total_chunks, int32_t total_file_size, int32_t chunk_size, const uint8_t* name,
+                             int name_len, float* out, double noise_sigma, uint64_t noise_seed, int64_t noise_g0, int mem);
 
 #ifdef __cplusplus
 }

@@ -1215,6 +1215,32 @@ void orc_cfo(const float* x, int64_t n, double df, double fs, float* out) {
     }
 }
 
+// counter-based variants (same formulas as the device-side synthetic input helpers, amb_tx.cuh)
+static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void orc_synth_bytes(uint64_t seed, int64_t frame, uint8_t* out, int64_t n) {
+    for (int64_t j = 0; j < n; j++) {
+        const uint64_t v = mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(frame * 65536 + (j >> 3) + 1));
+        out[j] = (uint8_t)(v >> (8 * (j & 7)));
+    }
+}
+void orc_add_awgn_ctr(float* x, int64_t n, double sigma, uint64_t seed, int64_t g0) {
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t g = g0 + i;
+        const uint64_t c = (uint64_t)(g >> 1);
+        const uint64_t a = mix64(seed + 0x9E3779B97F4A7C15ull * (2 * c + 1));
+        const uint64_t b = mix64(seed + 0x9E3779B97F4A7C15ull * (2 * c + 2));
+        const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+        const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+        const double r = std::sqrt(-2.0 * std::log(u1));
+        const double ph = 6.283185307179586 * u2;
+        x[i] = (float)((double)x[i] + sigma * ((g & 1) ? r * std::sin(ph) : r * std::cos(ph)));
+    }
+}
+
 // ---- timed legs for bench.py's cpu_baseline (whole-path calls, no Python in the loop) ----
 // Runs the streaming receiver over x in block_len blocks; returns frames decoded with crc_valid.
 int64_t orc_bench_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t block_len, int64_t* payload_bytes) {

@@ -107,6 +107,8 @@ def lib():
             "orc_power": (C.c_double, [f32p, C.c_int64, C.c_int64]),
             "orc_multipath": (None, [f32p, C.c_int64, i32p, f64p, C.c_int, f32p]),
             "orc_cfo": (None, [f32p, C.c_int64, C.c_double, C.c_double, f32p]),
+            "orc_synth_bytes": (None, [C.c_uint64, C.c_int64, u8p, C.c_int64]),
+            "orc_add_awgn_ctr": (None, [f32p, C.c_int64, C.c_double, C.c_uint64, C.c_int64]),
             "orc_bench_stream": (C.c_int64, [C.c_int, C.c_int, C.c_int, f32p, C.c_int64, C.c_int64, i64p]),
         }
         for name, (res, args) in sig.items():
@@ -443,6 +445,18 @@ def cfo(x, df, fs=44100.0):
     out = np.empty_like(x)
     lib().orc_cfo(_p(x, C.c_float), len(x), float(df), float(fs), _p(out, C.c_float))
     return out
+
+
+def synthBytes(seed, frame, n):
+    out = np.zeros(n, dtype=np.uint8)
+    lib().orc_synth_bytes(seed, frame, _p(out, C.c_uint8), n)
+    return out
+
+
+def addAwgnCtr(x, sigma, seed, g0=0):
+    x = _f32(x).copy()
+    lib().orc_add_awgn_ctr(_p(x, C.c_float), len(x), float(sigma), seed, g0)
+    return x
 
 
 def benchStream(cfg, mod, rep, x, block_len=4096):

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../audio-modem_b200/csrc/amb_walker.cuh"
+#include "../../audio-modem_b200/csrc/amb_tx.cuh"
 
 namespace {
 
@@ -151,6 +152,37 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     }
     return n_out;
 }
+
+// buildDataChunkFrame / buildMetadataFrame through the device logic (mirrors k_tx_chunk_payloads + k_tx_frames)
+static int64_t tx_frame(const AmbTables& T, const uint8_t* pay, int pay_len, int first, float* out, int64_t cap) {
+    const int64_t nsym = amb_tx_num_symbols(&T, pay_len), pre = amb_tx_silence_pre(&T, first), post = amb_tx_silence_post();
+    const int64_t sym = T.sym_len, total = pre + (3 + nsym) * sym + post;
+    if (!out || cap < total) return total;
+    std::memset(out, 0, (size_t)total * 4);
+    for (int i = 0; i < sym; i++) { out[pre + i] = T.pre1[i]; out[pre + sym + i] = T.pre2[i]; out[pre + 2 * sym + i] = T.ce_sym[i]; }
+    std::vector<double> re(AMB_FFT), im(AMB_FFT);
+    for (int64_t s = 0; s < nsym; s++) amb_tx_symbol(&T, pay, pay_len, s, re.data(), im.data(), out + pre + (3 + s) * sym);
+    float mx = 0.f;
+    for (int64_t i = 0; i < total; i++) mx = fmaxf(mx, fabsf(out[i]));
+    if (mx > 0.f) { const double sc = 0.8 / (double)mx; for (int64_t i = 0; i < total; i++) out[i] = (float)((double)out[i] * sc); }
+    return total;
+}
+int64_t emu_build_data_chunk_frame(int cfg, int mod, int rep, const uint8_t* data, int len, int32_t seq, uint64_t synth_seed, float* out, int64_t cap) {
+    AmbTables T;
+    if (amb_tables_build(&T, cfg, mod, rep)) return -1;
+    std::vector<uint8_t> d((size_t)len), pay((size_t)len + 16);
+    for (int i = 0; i < len; i++) d[i] = data ? data[i] : amb_synth_byte(synth_seed, seq, i);
+    const int pl = amb_data_chunk_payload(T.crc_table, d.data(), len, seq, pay.data());
+    return tx_frame(T, pay.data(), pl, 0, out, cap);
+}
+int64_t emu_build_metadata_frame(int cfg, int mod, int rep, int32_t tc, int32_t tfs, int32_t cs, const uint8_t* name, int name_len, float* out, int64_t cap) {
+    AmbTables T;
+    if (amb_tables_build(&T, cfg, mod, rep)) return -1;
+    uint8_t pay[300];
+    const int pl = amb_metadata_payload(T.crc_table, tc, tfs, cs, name, name_len, pay);
+    return tx_frame(T, pay, pl, 1, out, cap);
+}
+double emu_synth_normal(uint64_t seed, int64_t g) { return amb_synth_normal(seed, g); }
 
 // tables for inspection
 int emu_tables(int cfg, int mod, int rep, float* pre1, double* known_re, double* tw_re, double* tw_im, double* pts, double* scalars) {

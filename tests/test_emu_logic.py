@@ -96,3 +96,44 @@ def test_stream_second_metadata_changes_chunk_size(O, emu):
     x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 3))
     ev = _compare_stream(O, emu, "QPSK", x)
     assert sum(1 for r, _ in ev if r.frame_type == 0xFE and r.crc_valid) >= 1
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tx_frames_bit_identical(O, emu, mode):
+    """Transmit-side device logic (amb_tx.cuh) against the oracle's buildDataChunkFrame / buildMetadataFrame."""
+    import ctypes as C
+
+    from helpers import P
+
+    cfg, mod, rep, chunk = MODES[mode]
+    emu.emu_build_data_chunk_frame.restype = C.c_int64
+    emu.emu_build_metadata_frame.restype = C.c_int64
+    for seq, n in ((0, chunk), (123456, 17), (-3, 1)):
+        d = O.randomBytes(40 + n, n)
+        want = O.buildDataChunkFrame(cfg, d, seq, mod, rep)
+        out = np.zeros(len(want), np.float32)
+        got_n = emu.emu_build_data_chunk_frame(O.CONFIGS[cfg], O.MODS[mod], rep, P(d, C.c_uint8), n, seq, C.c_uint64(0), P(out, C.c_float), C.c_int64(len(out)))
+        assert got_n == len(want) and np.array_equal(out, want), (mode, seq, n)
+    # synthetic chunk bytes: the device formula equals the oracle's mirror
+    d = O.synthBytes(77, 5, chunk)
+    want = O.buildDataChunkFrame(cfg, d, 5, mod, rep)
+    out = np.zeros(len(want), np.float32)
+    emu.emu_build_data_chunk_frame(O.CONFIGS[cfg], O.MODS[mod], rep, None, chunk, 5, C.c_uint64(77), P(out, C.c_float), C.c_int64(len(out)))
+    assert np.array_equal(out, want)
+    name = "ünï.bin".encode()
+    want = O.buildMetadataFrame(cfg, 9, 9 * chunk - 1, chunk, name, mod, rep)
+    out = np.zeros(len(want), np.float32)
+    nb = np.frombuffer(name, np.uint8)
+    assert emu.emu_build_metadata_frame(O.CONFIGS[cfg], O.MODS[mod], rep, 9, 9 * chunk - 1, chunk, P(nb, C.c_uint8), len(nb), P(out, C.c_float), C.c_int64(len(out))) == len(want)
+    assert np.array_equal(out, want)
+
+
+def test_counter_noise_matches_oracle_mirror(O, emu):
+    import ctypes as C
+
+    emu.emu_synth_normal.restype = C.c_double
+    x = O.addAwgnCtr(np.zeros(4096, np.float32), 1.0, 99, g0=1000)
+    z = np.array([emu.emu_synth_normal(C.c_uint64(99), C.c_int64(1000 + i)) for i in range(4096)])
+    assert np.allclose(x, z.astype(np.float32), rtol=1e-6, atol=1e-7)
+    big = O.addAwgnCtr(np.zeros(200000, np.float32), 1.0, 5)
+    assert abs(float(big.mean())) < 0.01 and abs(float(big.std()) - 1.0) < 0.01
