@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the OFDM receive hot path on B200, BASELINE.json's metric on its config C2.
+
+Workload (config.workload = "C2"): a 16-QAM chunked stream — 4 KB chunks as OFDM frames of 28,431 samples
+(buildDataChunkFrame, modem.js:763), AWGN at 25 dB relative to the frame-core power, received by the streaming
+path (EMA DC removal, Schmidl-Cox scan, refine, collect, demodulate, CRC-32; app.js:749-981).  Synthetic data:
+chunk bytes and noise come from counter-based generators, frames are built on the device by the float64-faithful
+transmit path (bit-identical to the reference's frames).  One "step" = one push of `frames_per_step` whole frames.
+
+  value : whole-job Msamples/s with the step inputs already resident in HBM (device time, CUDA events on the
+          library's stream, max over ranks).  Inputs cycle over several distinct segments, each larger than L2.
+  e2e   : the same metric through the host-buffer call (amb_stream_push with AMB_MEM_HOST from pinned memory):
+          host->device copy of the samples and device->host copy of results and decoded bytes inside the timed region.
+  roofline : the kernel with the largest share of the timed region, algorithmic bytes / its mean launch duration
+          (per-kernel CUDA events recorded by the library during the timed region) against MEASURED_PEAKS.json.
+  cpu_baseline : the oracle (C++ float64 restatement of modem.js/app.js; Node is not available) on the host cores.
+
+`--impl reference` times that CPU path alone (all host cores) on the same config, metric and unit.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG, MOD, REP, CHUNK = "standard", "QAM16", 1, 4096
+FRAME = 28431            # samples per data-chunk frame incl. silences (2205 + 44*576 + 882)
+CORE = 25344             # preamble-1 .. last data symbol
+META = 16416
+SNR_DB = 25.0
+METRIC = "rx_audio_msamples_per_s"
+UNIT = "Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=int(os.environ.get("AMB_FRAMES_PER_STEP", "4096")))
+    ap.add_argument("--segments", type=int, default=4, help="distinct resident input segments cycled through")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, extra=None):
+    d = {"workload": "C2: 16-QAM chunked stream, 4 KB chunks as 28,431-sample OFDM frames, AWGN 25 dB, streaming preamble scan + CRC-32",
+         "ofdm_config": CFG, "constellation": MOD, "repetition": REP, "chunk_bytes": CHUNK, "frames_per_step": args.frames_per_step,
+         "samples_per_step": args.frames_per_step * FRAME, "block_len": 4096, "snr_db": SNR_DB,
+         "l2_policy": "inputs larger than L2 (step input %.0f MB, %d distinct segments cycled)" % (args.frames_per_step * FRAME * 4 / 1e6, args.segments),
+         "parallelism": "streams sharded by rank, no collective on the hot path"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ CPU leg (oracle)
+def cpu_leg(steps, warmup, frames_per_thread, threads=None, budget_s=None):
+    """Times the oracle's streaming receiver on `threads` host threads, each decoding its own copy of one stream
+    segment (metadata + frames_per_thread data frames) per step.  Returns (Msamples/s, payload MB/s, cores, sample)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    threads = threads or (os.cpu_count() or 1)
+    parts = [O.buildMetadataFrame(CFG, frames_per_thread, frames_per_thread * CHUNK, CHUNK, "bench.bin", MOD, REP)]
+    for i in range(frames_per_thread):
+        parts.append(O.buildDataChunkFrame(CFG, O.synthBytes(2, i, CHUNK), i, MOD, REP))
+    x = np.concatenate(parts)
+    p = O.power(parts[1][2205:2205 + CORE])
+    x = O.addAwgnCtr(x, (p / 10 ** (SNR_DB / 10)) ** 0.5, 3)
+    n = (len(x) + 4095) // 4096 * 4096
+    x = np.concatenate([x, np.zeros(n - len(x), np.float32)])
+    ok = [0] * threads
+    pb = [0] * threads
+
+    def work(t):
+        ok[t], pb[t] = O.benchStream(CFG, MOD, REP, x)     # ctypes releases the GIL: the C++ runs in parallel
+
+    def one_step():
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        one_step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        times.append(one_step())
+        if budget_s and time.perf_counter() - t_begin > budget_s:
+            break
+    assert all(o == frames_per_thread + 1 for o in ok), ok       # every frame found with a valid CRC
+    total = sum(times)
+    samples = len(times) * threads * n
+    payload = len(times) * sum(pb)
+    sample = f"{threads} threads x (metadata + {frames_per_thread} data frames = {n} samples) per step, {len(times)} steps"
+    return samples / total / 1e6, payload / total / 1e6, threads, sample, total / len(times) * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    v, pmb, cores, sample, ms = cpu_leg(args.steps, args.warmup, frames_per_thread=64)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "payload_mb_per_s": pmb,
+            "config": config_dict(args, {"reference_note": "CPU path = C++ float64 restatement of modem.js + app.js StreamingReceiver (oracle/); "
+                                         "Node.js is not installed, so modem.js itself cannot run here"}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in out.strip().splitlines():
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def prologue_frames():
+    """data frames after the metadata frame that make the prologue a whole number of 4096-sample blocks"""
+    for k in range(1, 4097):
+        if (META + FRAME * k) % 4096 == 0:
+            return k
+    raise AssertionError
+
+
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    import audio_modem_b200 as amb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s (of fallback)")
+
+    F = args.frames_per_step
+    step_samples = F * FRAME
+    m = amb.Modem(CFG, MOD, REP, device=local_rank)
+    # noise level: 25 dB below the power of a frame core (preamble-1 .. last data symbol), measured on one clean frame
+    clean = torch.zeros((1, FRAME), dtype=torch.float32, device=dev)
+    m.build_data_chunk_frames(n=1, data_len=CHUNK, seq0=0, synth_seed=2, out=clean)
+    sigma = float((clean[0, 2205:2205 + CORE].double().pow(2).mean() / 10 ** (SNR_DB / 10)).sqrt())
+    del clean
+
+    kp = prologue_frames()
+    pro_samples = META + kp * FRAME
+    max_push = max(step_samples, pro_samples)
+    seed_payload, seed_noise = 2 + 1000 * rank, 3 + 1000 * rank
+    # resident inputs: prologue + `segments` distinct steps
+    pro = torch.zeros((1, pro_samples), dtype=torch.float32, device=dev)
+    m.build_metadata_frame(128000, 500 * 1024 * 1024, CHUNK, "bench.bin", noise_sigma=sigma, noise_seed=seed_noise, noise_g0=0, out=pro[0, :META])
+    m.build_data_chunk_frames(n=kp, data_len=CHUNK, seq0=0, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise, noise_g0=META,
+                              out=pro[0, META:].view(kp, FRAME))
+    segs = []
+    for s in range(args.segments):
+        t = torch.zeros((1, step_samples), dtype=torch.float32, device=dev)
+        m.build_data_chunk_frames(n=F, data_len=CHUNK, seq0=kp + s * F, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise,
+                                  noise_g0=pro_samples + s * step_samples, out=t[0].view(F, FRAME))
+        segs.append(t)
+    m.synchronize()
+
+    m.stream_open(1, 4096, max_push, max_results=max(F, kp) + 64)
+    got = m.stream_push(pro, collect=False)
+    c0 = m.stream_counters()
+    assert c0["metaReceived"] == 1 and got == kp + 1, (c0, got, kp)
+
+    ext = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
+    for w in range(args.warmup):
+        m.stream_push(segs[w % len(segs)], collect=False)
+    m.synchronize()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = m.kernel_launches
+    m.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    frames_found = 0
+    for k in range(args.steps):
+        frames_found += m.stream_push(segs[(args.warmup + k) % len(segs)], collect=False)
+    e1.record(ext)
+    m.synchronize()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    prof = m.profile_read()
+    m.profile(False)
+    clk = clocks.stop()
+    launches = m.kernel_launches - launches0
+    c1 = m.stream_counters()
+    decoded = c1["framesDecoded"] - c0["framesDecoded"]
+    crc_bad = c1["crcErrors"] - c0["crcErrors"]
+    # every frame must be found and parsed; at 25 dB a few frames per 10,000 fail their CRC (real bit errors: the zero-padded
+    # last symbol sets the frame peak, so the payload symbols sit ~24 dB below full scale)
+    assert frames_found == args.steps * F and decoded == args.steps * F and crc_bad <= max(2, decoded // 500) and c1["frameErrors"] == c0["frameErrors"], (frames_found, c0, c1)
+
+    # end-to-end: host buffers (pinned), H2D of the samples + D2H of results and decoded bytes inside the timed region
+    host = torch.empty((1, step_samples), dtype=torch.float32, pin_memory=True)
+    host.copy_(segs[0])
+    hx = host.numpy()
+    m.stream_push(hx, collect=False)
+    m.synchronize()
+    t0 = time.perf_counter()
+    e2e_frames = 0
+    for k in range(args.e2e_steps):
+        e2e_frames += m.stream_push(hx, collect=False)
+    m.synchronize()
+    e2e_s = time.perf_counter() - t0
+    d2h = F * (m.bytes_stride + 88)
+    m.stream_close()
+
+    # aggregate over ranks
+    total_ms = amb.shard.max_over_ranks(dev_ms, device=dev) if dist else dev_ms
+    e2e_s_max = amb.shard.max_over_ranks(e2e_s, device=dev) if dist else e2e_s
+    counters = {"frames": args.steps * F, "payloadBytes": args.steps * F * CHUNK, "samples": args.steps * step_samples,
+                "crcValidFrames": decoded - crc_bad, "launches": launches}
+    tot = amb.shard.gather_counters(counters, device=dev) if dist else counters
+    value = tot["samples"] / (total_ms / 1e3) / 1e6
+    e2e_value = world * args.e2e_steps * step_samples / e2e_s_max / 1e6
+
+    # roofline of the dominant kernel (largest share of the timed region on this rank)
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
+    algo_step = 4 * step_samples + F * (CHUNK + 64)                 # 4 B/sample once + payload + 64 B result per frame
+    per_launch = {"k_demod": F * (4 * 44 * 576 + CHUNK + 64), "k_parse": F * (4202 + CHUNK + 64), "k_frame_max": F * 4 * CORE}
+    roof = None
+    if dom:
+        name, (ms, cnt) = dom
+        b = per_launch.get(name, 4 * step_samples)
+        achieved = b / (ms / cnt / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "mean_launch_ms": ms / cnt,
+                "share_of_step": ms / dev_ms,
+                "whole_step": {"algorithmic_bytes": algo_step, "achieved": algo_step * args.steps / (dev_ms / 1e3) / 1e9,
+                               "frac": algo_step * args.steps / (dev_ms / 1e3) / 1e9 / hbm_peak},
+                "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "payload_mb_per_s": tot["payloadBytes"] / (total_ms / 1e3) / 1e6,
+            "config": config_dict(args), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * step_samples, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+            "gpu_launches": tot["launches"], "roofline": roof,
+            "check": {"frames_per_step_found": frames_found // args.steps, "crc_valid_frames": tot["crcValidFrames"], "crc_errors": crc_bad}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, pmb, cores, sample, _ = cpu_leg(steps=1000, warmup=1, frames_per_thread=64, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "payload_mb_per_s": pmb}
+    if rank == 0:
+        print(json.dumps(line))
+    m.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

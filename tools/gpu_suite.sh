@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 groups=("crc32 or preprocess or extension or api_argument" "detect_preamble" "estimate_channel" "decode_chunk_frames"
         "decode_received" "stream_matches_oracle" "stream_single_block or stream_block_alignment" "stream_edge_cases or second_metadata"
-        "many_streams or round_trip")
+        "many_streams or round_trip" "tx_frames")
 i=0
 for g in "${groups[@]}"; do
   log="gpurun_out/tests_$i.log"
