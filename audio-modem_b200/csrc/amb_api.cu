@@ -58,6 +58,9 @@ struct amb_modem {
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
+    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc;
+    int slot_cap = 0, xc_w = 0;
+    int64_t calls_stride = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -260,7 +263,8 @@ void amb_destroy(amb_modem* m) {
     DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx,
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
-                     &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp};
+                     &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -531,6 +535,18 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(cudaMemsetAsync(m->cleaned.p, 0, ns * m->stride * 4, m->stream));
     CK(cudaMemsetAsync(m->sums.p, 0, ns * m->sum_stride * AMB_SUM_W * 4, m->stream));
     CK(cudaMemsetAsync(m->dc_next.p, 0, ns * 8, m->stream));
+    // stores written by the scan kernel for the walker
+    m->calls_stride = m->stride / AMB_TILE;
+    m->xc_w = 256 + 2 * T.fine_radius;
+    const int64_t tiles_per_push = (max_push / 256) * n_streams;
+    m->slot_cap = (int)(tiles_per_push / 8 + 64 < 2000000 ? tiles_per_push / 8 + 64 : 2000000);
+    CK(m->tile_slot.ensure(ns * m->sum_stride * 4)); CK(m->tri.ensure((size_t)m->slot_cap * 256 * 3 * 8));
+    CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16));
+    CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8));
+    CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
+    CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
+    CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
+    cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     std::vector<AmbStreamState> init(ns);
     std::memset(init.data(), 0, ns * sizeof(AmbStreamState));
     for (auto& s : init) { s.pre_pos = -1; s.frame_end = -1; }
@@ -545,7 +561,8 @@ int amb_stream_close(amb_modem* m) {
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
-                     &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp};
+                     &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -575,6 +592,10 @@ static int stream_compact(amb_modem* m) {
     CK(cudaMemcpy2DAsync(m->ctmp.p, srow, m->sums.as<float>() + (shift / 256) * AMB_SUM_W, (size_t)m->sum_stride * AMB_SUM_W * 4, srow, m->n_streams,
                          cudaMemcpyDeviceToDevice, m->stream));
     CK(cudaMemcpy2DAsync(m->sums.p, (size_t)m->sum_stride * AMB_SUM_W * 4, m->ctmp.p, srow, srow, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    const size_t frow = (size_t)(m->hist / AMB_TILE) * 3 * 8;
+    CK(cudaMemcpy2DAsync(m->ctmp.p, frow, m->fpre.as<double>() + (shift / AMB_TILE) * 3, (size_t)m->calls_stride * 3 * 8, frow, m->n_streams,
+                         cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpy2DAsync(m->fpre.p, (size_t)m->calls_stride * 3 * 8, m->ctmp.p, frow, frow, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
     m->base_g += shift;
     return AMB_OK;
 }
@@ -589,6 +610,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
     if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
     if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    const AmbTables& T = m->tables;
     const int ns = m->n_streams;
     const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
@@ -606,12 +628,26 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
                                                  m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
     // 2. window-sum summaries of the new window-end samples
     const int tiles = (int)(n_new / AMB_TILE);
-    LAUNCH("k_scan_sums", k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride));
+    AmbScanStore ss;
+    ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
+    ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
+    CK(cudaMemsetAsync(m->tile_slot.p, 0xFF, (size_t)ns * m->sum_stride * 4, m->stream));      // history tiles: no slot (-1)
+    CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
+    LAUNCH("k_scan_sums", k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride, ss));
+    LAUNCH("k_defect_prefix", k_defect_prefix<<<blocks_for(ns, 4), 128, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_new / AMB_TILE, ns));
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;
     g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
     g.sum_lo = m->base_g > 0 ? m->base_g : 0; g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
+    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w;
+    g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
+    {
+        const int L = m->xc_w + T.sym_len;
+        const size_t smem = (size_t)L * 8 + (size_t)((T.sym_len + 1) & ~1) * 4 + (size_t)(L + 1) * 8 + 16;
+        LAUNCH("k_xcorr_store", k_xcorr_store<<<m->slot_cap, 128, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
+                                                                                     m->slot_count.as<int>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
+    }
     int n_out = 0;
     int n_todo = ns;
     const int* todo = nullptr;

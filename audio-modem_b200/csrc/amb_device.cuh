@@ -369,6 +369,22 @@ AMB_HD void amb_window_sums(const AmbSig& s, int64_t d0, int cnt, double* P, dou
     AMB_WARP_SYNC();
 }
 
+// Cross-correlation metric of preamble-1 at one offset d (modem.js:577-585): float64 sums in tap order, so the
+// value is bit-identical to the reference's given identical samples.  Returns false where the denominator fails
+// the 0.001 test (the reference skips such offsets).
+AMB_HD bool amb_xcorr_at(const AmbTables* T, const AmbSig& s, int64_t d, double* metric) {
+    double corr = 0, se = 0;
+    for (int i = 0; i < T->sym_len; i++) {
+        const double v = (double)amb_sig(s, d + i);
+        corr = fma(v, (double)T->pre1[i], corr);   // the product is exact, so fma == mul then add
+        se = fma(v, v, se);
+    }
+    const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
+    if (!(denom > 0.001)) { *metric = 0.0; return false; }
+    *metric = amb_div(corr, denom);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fine cross-correlation against preamble-1 over offsets [lo, hi] (modem.js:576-587, app.js:864-877):
 // float64 sequential sums in tap order (bit-identical to the reference given identical samples),
@@ -390,17 +406,8 @@ AMB_HD double amb_fine_xcorr(const AmbTables* T, const AmbSig& s, int64_t lo, in
         int64_t bpos = -1;
         for (int o = lane; o < n; o += 32) {
             const int64_t d = lo + o;
-            double corr = 0, se = 0;
-            for (int i = 0; i < plen; i++) {
-                const double v = (double)amb_sig(s, d + i);
-                corr = fma(v, (double)T->pre1[i], corr);   // the product is exact, so fma == mul then add
-                se = fma(v, v, se);
-            }
-            const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
-            if (denom > 0.001) {
-                const double m = amb_div(corr, denom);
-                if (m > best) { best = m; bpos = d; }
-            }
+            double m;
+            if (amb_xcorr_at(T, s, d, &m) && m > best) { best = m; bpos = d; }
         }
         scratch[lane] = best;
         scratch[32 + lane] = (double)bpos;

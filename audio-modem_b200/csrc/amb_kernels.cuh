@@ -158,8 +158,23 @@ __device__ __forceinline__ void block_prefix(const float* c, double* ST, double*
 // Streaming summary scan.  cleaned: arena [n_streams][stride]; tile t of the push covers window-end samples
 // [off0 + 4096 t, +4096) in arena coordinates; g0 = global sample index of arena index off0.
 // sums: [n_streams][sum_stride][5]; summary tile index of arena sample a is a >> 8.
+// Besides the summaries, tiles that may matter to the walker are written out in full: a tile with a window whose
+// metric exceeds 0.25 (energy gate relaxed by 10 %) gets a slot in the triple store (float64 P, Ra, Rb of its 256
+// windows), so the walker never recomputes them; the slot also records whether any window passes the exact
+// candidate test (metric > 0.5 with the 0.001 gate), which is what the cross-correlation screening kernel runs on.
+// The block-boundary defect terms of the call this tile completes (amb_walker.cuh) are written per call.
+struct AmbScanStore {
+    int32_t* tile_slot;      // [n_streams][sum_stride]
+    double* tri;             // [slot_cap][256][3]
+    int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate, unused
+    int* slot_count;
+    int slot_cap;
+    double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
+    int64_t calls_stride;
+};
+
 __global__ void __launch_bounds__(256) k_scan_sums(const float* __restrict__ cleaned, int64_t stride, int64_t off0, int64_t g0, int per,
-                                                    float* __restrict__ sums, int64_t sum_stride) {
+                                                    float* __restrict__ sums, int64_t sum_stride, AmbScanStore st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* c = reinterpret_cast<float*>(smem_raw);
     double* ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
@@ -177,13 +192,42 @@ __global__ void __launch_bounds__(256) k_scan_sums(const float* __restrict__ cle
     __syncthreads();
     block_prefix(c, ST, SQ, tot_t, tot_q);
     __shared__ float red[8][5];
+    __shared__ int s_slot;
+    if (tid == 0 && st.defect) {
+        // defect of the boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
+        const double xm1 = c[0], x255 = c[256], x511 = c[512];
+        double* D = st.defect + ((int64_t)s * st.calls_stride + (a0 >> 12)) * 3;
+        D[0] = xm1 * x255 - x255 * x511; D[1] = xm1 * xm1 - x255 * x255; D[2] = x255 * x255 - x511 * x511;
+    }
     for (int jj = 0; jj < AMB_TILE / 256; jj++) {
         const int dl = jj * 256 + 1 + tid;                             // window start, local index
         const int64_t d_global = g0 + (int64_t)tile * AMB_TILE - AMB_HALO + dl;
         float ap = 0.f, mnA = 3.0e38f, mxA = 0.f, mnB = 3.0e38f, mxB = 0.f;
+        double P = 0.0, A = 0.0, B = 0.0;
+        int hot = 0, cand = 0;
         if (d_global >= 0) {
-            const double P = ST[dl + 256] - ST[dl], A = SQ[dl + 256] - SQ[dl], B = SQ[dl + 512] - SQ[dl + 256];
+            P = ST[dl + 256] - ST[dl]; A = SQ[dl + 256] - SQ[dl]; B = SQ[dl + 512] - SQ[dl + 256];
             ap = (float)fabs(P); mnA = mxA = (float)A; mnB = mxB = (float)B;
+            hot = A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
+            cand = A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+        }
+        if (st.tile_slot) {
+            const int any_hot = __syncthreads_or(hot), any_cand = __syncthreads_or(cand);
+            if (tid == 0) {
+                int slot = -1;
+                if (any_hot) {
+                    slot = atomicAdd(st.slot_count, 1);
+                    if (slot >= st.slot_cap) slot = -1;
+                    else { st.slot_info[slot * 4] = s; st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + jj); st.slot_info[slot * 4 + 2] = any_cand; st.slot_info[slot * 4 + 3] = 0; }
+                }
+                s_slot = slot;
+                st.tile_slot[(int64_t)s * sum_stride + ((a0 >> 8) + jj)] = slot;
+            }
+            __syncthreads();
+            if (s_slot >= 0) {
+                double* o = st.tri + ((int64_t)s_slot * 256 + tid) * 3;
+                o[0] = P; o[1] = A; o[2] = B;
+            }
         }
         ap = warp_maxf(ap); mnA = warp_minf(mnA); mxA = warp_maxf(mxA); mnB = warp_minf(mnB); mxB = warp_maxf(mxB);
         if (lane == 0) { red[warp][0] = ap; red[warp][1] = mnA; red[warp][2] = mxA; red[warp][3] = mnB; red[warp][4] = mxB; }
@@ -212,6 +256,9 @@ struct AmbStreamGeom {
     int64_t block_len, ring_cap;
     int64_t k_end;         // calls [state.next_call, k_end) are processed
     int rec_cap;           // frame records per stream
+    // stores of the scan kernels (see AmbWalkGeom)
+    const int32_t* tile_slot; const double* tri; const float* xc; int xc_w;
+    const double* F; int64_t calls_stride;
 };
 
 __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
@@ -226,6 +273,8 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     AmbStreamState st = states[s];
     AmbWalkGeom G;
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+    G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
     sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
@@ -858,5 +907,101 @@ __global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__
         if (mx > 0.f) v = (float)amb_mul((double)v, s);
         if (a.noise_sigma > 0.0) v = (float)((double)v + a.noise_sigma * amb_synth_normal(a.noise_seed, g0 + i));
         out[i] = v;
+    }
+}
+
+// Inclusive prefix over calls of the defect terms: F[c] = F[c-1] + D[c] for the n new arena calls starting at c0
+// (one warp per stream; F[c0-1] is the carry from the previous push, 0 before the stream start).
+__global__ void __launch_bounds__(128) k_defect_prefix(const double* __restrict__ D, double* __restrict__ F, int64_t calls_stride, int64_t c0, int64_t n,
+                                                       int n_streams) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= n_streams) return;
+    const double* d = D + (int64_t)s * calls_stride * 3;
+    double* f = F + (int64_t)s * calls_stride * 3;
+    double carry[3];
+    for (int c = 0; c < 3; c++) carry[c] = c0 > 0 ? f[(c0 - 1) * 3 + c] : 0.0;
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t i = base + lane;
+        double v[3];
+        for (int c = 0; c < 3; c++) v[c] = i < n ? d[(c0 + i) * 3 + c] : 0.0;
+        for (int o = 1; o < 32; o <<= 1)
+            for (int c = 0; c < 3; c++) { const double u = __shfl_up_sync(0xffffffffu, v[c], o); if (lane >= o) v[c] += u; }
+        for (int c = 0; c < 3; c++) { v[c] += carry[c]; if (i < n) f[(c0 + i) * 3 + c] = v[c]; carry[c] = __shfl_sync(0xffffffffu, v[c], 31); }
+    }
+}
+
+// Cross-correlation screening values for every slot whose tile holds a candidate: float32 metric of preamble-1 at the
+// xc_w = 256 + 2R offsets  tile_first - R + i  (amb_fine_xcorr_store re-evaluates the near-maximal ones exactly).
+// The preamble's two body halves are equal up to the sign pre1_sign, so the body taps are folded:
+//   corr(o) = sum_{i<cp} pre1[i] s[o+i] + sum_{r<256} pre1[cp+r] (s[o+cp+r] + sign * s[o+cp+256+r]).
+// Each thread carries 4 consecutive offsets in registers (one new sample and one tap per 4 FMAs).
+#define AMB_XC_MAXW (256 + 2 * 768)
+__global__ void __launch_bounds__(128) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                                                      const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count, int slot_cap,
+                                                      float* __restrict__ xc, int xc_w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int slot = blockIdx.x;
+    const int n_slots = min(*slot_count, slot_cap);
+    if (slot >= n_slots || !slot_info[slot * 4 + 2]) return;
+    const int s = slot_info[slot * 4], tile = slot_info[slot * 4 + 1];
+    const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
+    const int L = xc_w + plen;                                         // samples needed
+    float* sg = reinterpret_cast<float*>(smem_raw);                    // [L]
+    float* u = sg + L;                                                 // [L] folded
+    float* tp = u + L;                                                 // [plen] template
+    double* SQ = reinterpret_cast<double*>(tp + ((plen + 1) & ~1));    // [L + 1] prefix of squares
+    const int tid = threadIdx.x;
+    const int64_t tile_first = g.base_g + ((int64_t)tile << 8) - 511;  // global position of the tile's first window
+    const int64_t base = tile_first - R;
+    const float* src = cleaned + (int64_t)s * g.stride;
+    const int64_t lo = g.base_g > 0 ? g.base_g : 0;
+    for (int i = tid; i < L; i += 128) {
+        const int64_t p = base + i;
+        sg[i] = (p >= lo && p < g.avail_hi) ? src[p - g.base_g] : 0.f;
+    }
+    for (int i = tid; i < plen; i += 128) tp[i] = T->pre1[i];
+    __syncthreads();
+    const float sign = (float)T->pre1_sign;
+    for (int i = tid; i < L; i += 128) u[i] = (i + 256 < L) ? sg[i] + sign * sg[i + 256] : sg[i];
+    // prefix of squares (float64): 128 threads x contiguous chunks, then a serial pass over the 128 totals
+    const int per = (L + 127) / 128;
+    __shared__ double tot[128];
+    {
+        double acc = 0.0;
+        for (int i = tid * per; i < min(L, (tid + 1) * per); i++) { SQ[i] = acc; acc += (double)sg[i] * (double)sg[i]; }
+        tot[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) { double acc = 0.0; for (int t = 0; t < 128; t++) { const double v = tot[t]; tot[t] = acc; acc += v; } SQ[L] = acc; }
+    __syncthreads();
+    { const double o = tot[tid]; for (int i = tid * per; i < min(L, (tid + 1) * per); i++) SQ[i] += o; }
+    __syncthreads();
+    const double tE = T->pre1_energy;
+    float* out = xc + (int64_t)slot * xc_w;
+    for (int o0 = tid * 4; o0 < xc_w; o0 += 128 * 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float x0 = sg[o0], x1 = sg[o0 + 1], x2 = sg[o0 + 2];
+        for (int i = 0; i < cp; i++) {                                 // cyclic-prefix taps on the raw samples
+            const float x3 = sg[o0 + i + 3], t = tp[i];
+            a0 = fmaf(t, x0, a0); a1 = fmaf(t, x1, a1); a2 = fmaf(t, x2, a2); a3 = fmaf(t, x3, a3);
+            x0 = x1; x1 = x2; x2 = x3;
+        }
+        x0 = u[o0 + cp]; x1 = u[o0 + cp + 1]; x2 = u[o0 + cp + 2];
+        for (int r = 0; r < 256; r++) {                                // folded body taps
+            const float x3 = u[o0 + cp + r + 3], t = tp[cp + r];
+            a0 = fmaf(t, x0, a0); a1 = fmaf(t, x1, a1); a2 = fmaf(t, x2, a2); a3 = fmaf(t, x3, a3);
+            x0 = x1; x1 = x2; x2 = x3;
+        }
+        const float acc[4] = {a0, a1, a2, a3};
+        for (int q = 0; q < 4 && o0 + q < xc_w; q++) {
+            const double se = SQ[o0 + q + plen] - SQ[o0 + q];
+            const double denom = sqrt(se * tE);
+            float v;
+            if (denom > 0.001 * (1.0 + 1e-4)) v = (float)((double)acc[q] / denom);
+            else if (denom < 0.001 * (1.0 - 1e-4)) v = AMB_XC_FAIL;
+            else v = AMB_XC_UNSURE;
+            out[o0 + q] = v;
+        }
     }
 }

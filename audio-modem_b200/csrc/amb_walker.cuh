@@ -44,7 +44,26 @@ struct AmbWalkGeom {
     int64_t sum_base;      // global sample index of summary tile 0 (multiple of 256)
     int64_t sum_tiles;     // tiles available from sum_base
     int64_t sum_lo;        // summaries valid for window-end samples q >= sum_lo
+    // Optional stores written by the scan kernels (NULL = evaluate inline):
+    const int32_t* tile_slot;   // per summary tile: slot in the stores, -1 = none
+    const double* tri;          // [slot][256][3]  (P, Ra, Rb) of the tile's 256 windows
+    const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
+    int xc_w;
+    const double* F;            // per call: inclusive prefix of the block-boundary defect terms (3 doubles per call)
+    int64_t F_call0, F_calls;   // F[(call - F_call0) * 3 + c] valid for 0 <= call - F_call0 < F_calls
 };
+
+// screening values in the xc store: a metric in [-1, 1]; AMB_XC_FAIL where the denominator fails its 0.001 test;
+// AMB_XC_UNSURE where float32 cannot tell
+#define AMB_XC_FAIL (-2.0f)
+#define AMB_XC_UNSURE (2.0f)
+
+AMB_HD int amb_tile_slot_of(const AmbWalkGeom& G, int64_t j) {
+    if (!G.tile_slot) return -1;
+    const int64_t rel = j - (G.sum_base >> 8);
+    if (rel < 0 || rel >= G.sum_tiles) return -1;
+    return G.tile_slot[rel];
+}
 
 // tile summary: {max|P|, minRa, maxRa, minRb, maxRb}
 #define AMB_SUM_W 5
@@ -85,6 +104,115 @@ AMB_HD void amb_commit(AmbStreamState& st, int64_t best_pos, double best, int64_
     st.pre_pos = best_pos; st.coarse = best; st.state = AMB_RX_PREAMBLE; st.ac_scan_pos = next_pos; st.lag = lag;
 }
 
+// Window sums at cnt consecutive offsets from d0: copied from the scan kernel's store where the tile has a slot,
+// evaluated directly otherwise.
+AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0, int cnt, double* P, double* A, double* B) {
+    int done = 0;
+    while (done < cnt) {
+        const int64_t d = d0 + done;
+        const int64_t j = (d + 511) >> 8;
+        const int64_t tile_first = (j << 8) - 511;
+        int seg = (int)(tile_first + 256 - d);
+        if (seg > cnt - done) seg = cnt - done;
+        const int slot = amb_tile_slot_of(G, j);
+        if (slot >= 0 && G.tri) {
+            const double* src = G.tri + ((int64_t)slot * 256 + (d - tile_first)) * 3;
+            AMB_WARP_FOR(i, seg) { P[done + i] = src[3 * i]; A[done + i] = src[3 * i + 1]; B[done + i] = src[3 * i + 2]; }
+            AMB_WARP_SYNC();
+        } else {
+            amb_window_sums(sig, d, seg, P + done, A + done, B + done);
+        }
+        done += seg;
+    }
+}
+
+// 1 if none of the 16 summary tiles of call k (window-end samples [k*B, (k+1)*B)) can hold a candidate under E
+AMB_HD int amb_call_cold(const AmbWalkGeom& G, const float* sums, int64_t k, double Ep, double Ea, double Eb) {
+    const int64_t j0 = (k * G.block_len) >> 8, n = G.block_len >> 8;
+    for (int64_t t = 0; t < n; t++) {
+        const int64_t jj = j0 + t, rel = jj - (G.sum_base >> 8);
+        if (rel < 0 || rel >= G.sum_tiles || (jj << 8) < G.sum_lo) return 0;
+        if (amb_tile_hot(sums + rel * AMB_SUM_W, Ep, Ea, Eb)) return 0;
+    }
+    return 1;
+}
+
+// Idle fast-forward.  While the scan is caught up and uninterrupted (state IDLE, sums initialised, lag 1, next
+// position = first position of the next call) nothing can happen in a call whose 16 tiles are cold under the defect
+// that will be in force there, E_k = E + F[k] - F[k_now - 1].  Returns how many whole calls from st.next_call can be
+// skipped (< k_end) and advances the state over them.
+AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums, AmbStreamState& st, int64_t k_end, AmbWalkScratch* W) {
+    if (!G.F || st.state != AMB_RX_IDLE || !st.ac_init || st.lag != 1) return 0;
+    int64_t k = st.next_call;
+    if (st.ac_scan_pos != k * G.block_len - 511) return 0;
+    if (st.ac_scan_pos < (k + 1) * G.block_len - G.ring_cap + 2 * AMB_HALF) return 0;      // ring clamp would fire
+    const int64_t f0 = k - 1 - G.F_call0;
+    if (f0 < 0) return 0;
+    const double b0 = G.F[f0 * 3], b1 = G.F[f0 * 3 + 1], b2 = G.F[f0 * 3 + 2];
+    int64_t skipped = 0;
+    while (k < k_end) {
+        AMB_WARP_FOR(t, 32) {
+            const int64_t kk = k + t, fi = kk - G.F_call0;
+            int cold = 0;
+            if (kk < k_end && fi >= 0 && fi < G.F_calls)
+                cold = amb_call_cold(G, sums, kk, st.Ep + (G.F[fi * 3] - b0), st.Ea + (G.F[fi * 3 + 1] - b1), st.Eb + (G.F[fi * 3 + 2] - b2));
+            W->hot[t] = cold ? 0 : 1;
+        }
+        AMB_WARP_SYNC();
+        int first = 32;
+        for (int t = 0; t < 32; t++) if (W->hot[t]) { first = t; break; }
+        AMB_WARP_SYNC();
+        k += first; skipped += first;
+        if (first < 32) break;
+    }
+    if (skipped > 0) {
+        const int64_t fi = k - 1 - G.F_call0;
+        st.Ep += G.F[fi * 3] - b0; st.Ea += G.F[fi * 3 + 1] - b1; st.Eb += G.F[fi * 3 + 2] - b2;
+        st.ac_scan_pos = k * G.block_len - 511;
+        st.next_call = k;
+    }
+    return skipped;
+}
+
+// Refine with the scan kernel's float32 screening values: offsets whose screening metric is within 1e-3 of the
+// maximum are re-evaluated exactly (amb_xcorr_at), so the argmax and the reported metric are the reference's.
+// Falls back to the direct evaluation when the store does not cover [lo, hi] or cannot decide.
+AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, int64_t lo, int64_t hi, int64_t p,
+                                   double* scratch, int64_t* pos_out) {
+    const int64_t j = (p + 511) >> 8;
+    const int slot = G.xc ? amb_tile_slot_of(G, j) : -1;
+    const int64_t base = (j << 8) - 511 - T->fine_radius;
+    if (slot < 0 || lo < base || hi >= base + G.xc_w || hi < lo) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    const float* v = G.xc + (int64_t)slot * G.xc_w;
+    float mx = -3.0f;
+    bool unsure = false;
+    for (int64_t d = lo; d <= hi; d++) {
+        const float x = v[d - base];
+        if (x == AMB_XC_UNSURE) unsure = true;
+        else if (x != AMB_XC_FAIL && x > mx) mx = x;
+    }
+    if (unsure) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    if (mx < -2.5f) { *pos_out = p; return -INFINITY; }                 // no offset passes the denominator test
+    int cnt = 0;
+    for (int64_t d = lo; d <= hi && cnt <= 32; d++) {
+        const float x = v[d - base];
+        if (x != AMB_XC_FAIL && x >= mx - 1e-3f) { if (cnt < 32 && AMB_LEADER()) scratch[32 + cnt] = (double)d; cnt++; }
+    }
+    AMB_WARP_SYNC();
+    if (cnt > 32) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    AMB_WARP_FOR(i, cnt) {
+        double m;
+        scratch[i] = amb_xcorr_at(T, sig, (int64_t)scratch[32 + i], &m) ? m : -INFINITY;
+    }
+    AMB_WARP_SYNC();
+    double best = -INFINITY;
+    int64_t bpos = p;
+    for (int i = 0; i < cnt; i++) if (scratch[i] > best) { best = scratch[i]; bpos = (int64_t)scratch[32 + i]; }
+    AMB_WARP_SYNC();
+    *pos_out = bpos;
+    return best;
+}
+
 // _scanForPreamble, app.js:775-847, for the call whose totalWritten is `tw`
 AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums,
                           AmbStreamState& st, int64_t tw, AmbWalkScratch* W) {
@@ -105,7 +233,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
 
     if (st.lag == 1) {
         // first position of a call that continues an uninterrupted scan: sums still describe window d-1
-        amb_window_sums(sig, d - 1, 3, W->P, W->A, W->B);
+        amb_eval_windows(G, sig, d - 1, 3, W->P, W->A, W->B);
         double m;
         if (amb_metric(W->P[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
         if (d < scan_end) {
@@ -164,7 +292,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
         if (d_end > scan_end) d_end = scan_end;
         const int cnt = (int)(d_end - d + 1);
         const int look = d_end < scan_end ? 1 : 0;
-        amb_window_sums(sig, d, cnt + look, W->P, W->A, W->B);
+        amb_eval_windows(G, sig, d, cnt + look, W->P, W->A, W->B);
         AMB_WARP_FOR(i, cnt + look) {
             double m;
             W->gate[i] = amb_metric(W->P[i], W->A[i], W->B[i], st, &m);
@@ -202,7 +330,7 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
     if (fs < tw - G.ring_cap) fs = tw - G.ring_cap;
     if (fe > tw - plen) fe = tw - plen;
     int64_t pos;
-    const double best = amb_fine_xcorr(T, sig, fs, fe, st.pre_pos, W->x, &pos);
+    const double best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos);
     if (best < 0.1) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
     st.pre_pos = pos; st.fine = best;
     const int64_t max_payload = st.meta_received ? (int64_t)(st.chunk_size ? st.chunk_size : 4096) + 11 : 280;
@@ -216,6 +344,7 @@ AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig,
                     int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W) {
     int n = 0;
     while (st.next_call < k_end) {
+        if (amb_walk_skip_cold_calls(G, sums, st, k_end, W) > 0) continue;
         const int64_t tw = (st.next_call + 1) * G.block_len;
         if (st.state == AMB_RX_IDLE) amb_walk_scan(T, G, sig, sums, st, tw, W);
         else if (st.state == AMB_RX_PREAMBLE) amb_walk_refine(T, G, sig, st, tw, W);

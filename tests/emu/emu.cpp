@@ -76,6 +76,9 @@ int emu_decode_chunk_frame(int cfg, int mod, int rep, const float* x, int64_t n,
 
 // streaming receiver through the device logic: EMA (sequential, as the reference), tile summaries computed
 // directly, then walk / decode / post until no stream needs another walk.  Pushes of `push_len` samples.
+static int g_use_stores = 1;
+void emu_use_stores(int on) { g_use_stores = on; }
+
 int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t block_len, int64_t push_len,
                amb_frame_result* res_out, int max_res, uint8_t* bytes_out, int64_t bytes_stride, int64_t* counters) {
     AmbTables T;
@@ -89,6 +92,13 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     AmbWalkGeom G;
     G.block_len = block_len; G.ring_cap = amb_tables_estimate_frame_samples(cfg, mod, 4096 + 16, rep) * 3 + 8192;
     G.sum_base = 0; G.sum_tiles = n_tiles; G.sum_lo = 0;
+    // stores as the scan kernels write them (k_scan_sums, k_defect_prefix, k_xcorr_store): slots only for the tiles of the
+    // current push, float64 triples, float32 screening correlation, per-call defect prefix
+    std::vector<int32_t> tile_slot((size_t)n_tiles, -1);
+    std::vector<double> tri, Fpre((size_t)(n / block_len + 2) * 3, 0.0);
+    std::vector<float> xc;
+    const int xc_w = 256 + 2 * T.fine_radius;
+    G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.F = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
     AmbStreamState st;
     std::memset(&st, 0, sizeof(st));
     st.pre_pos = -1; st.frame_end = -1;
@@ -100,18 +110,48 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
         const int64_t w1 = std::min(n, w0 + push_len);
         if ((w1 - w0) % block_len) break;
         sig.hi = w1;
+        if (g_use_stores) { std::fill(tile_slot.begin(), tile_slot.end(), -1); tri.clear(); xc.clear(); }
+        int n_slots = 0;
         // summaries of the window-end samples that became available
         for (int64_t j = tiles_done; (j + 1) * 256 <= w1; j++, tiles_done = j) {
             float ap = 0, mnA = 3e38f, mxA = 0, mnB = 3e38f, mxB = 0;
+            bool hot = false, cand = false;
+            std::vector<double> t3(256 * 3, 0.0);
             for (int64_t q = j * 256; q < (j + 1) * 256; q++) {
                 const int64_t d = q - 511;
                 if (d < 0) continue;
                 double P = 0, A = 0, B = 0;
                 for (int t = 0; t < 256; t++) { const double a = cleaned[d + t], b = cleaned[d + t + 256]; P += a * b; A += a * a; B += b * b; }
+                t3[(q - j * 256) * 3] = P; t3[(q - j * 256) * 3 + 1] = A; t3[(q - j * 256) * 3 + 2] = B;
+                hot |= A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
+                cand |= A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
                 ap = fmaxf(ap, (float)fabs(P)); mnA = fminf(mnA, (float)A); mxA = fmaxf(mxA, (float)A); mnB = fminf(mnB, (float)B); mxB = fmaxf(mxB, (float)B);
             }
             float* o = &sums[(size_t)j * AMB_SUM_W];
             o[0] = ap; o[1] = mnA; o[2] = mxA; o[3] = mnB; o[4] = mxB;
+            if (g_use_stores && hot) {
+                tile_slot[(size_t)j] = n_slots++;
+                tri.insert(tri.end(), t3.begin(), t3.end());
+                xc.resize((size_t)n_slots * xc_w, AMB_XC_UNSURE);
+                if (cand) {
+                    AmbSig s2 = sig; s2.hi = w1;
+                    const int64_t base = j * 256 - 511 - T.fine_radius;
+                    for (int i = 0; i < xc_w; i++) {
+                        double mm;
+                        xc[(size_t)(n_slots - 1) * xc_w + i] = amb_xcorr_at(&T, s2, base + i, &mm) ? (float)mm : AMB_XC_FAIL;
+                    }
+                }
+            }
+        }
+        if (g_use_stores) {
+            // defect prefix over the calls completed by this push (k_scan_sums thread 0 + k_defect_prefix)
+            for (int64_t k = w0 / block_len; k < w1 / block_len; k++) {
+                auto c = [&](int64_t g) { return g >= 0 ? (double)cleaned[g] : 0.0; };
+                const double xm1 = c(k * block_len - 512), x255 = c(k * block_len - 256), x511 = c(k * block_len);
+                const double D[3] = {xm1 * x255 - x255 * x511, xm1 * xm1 - x255 * x255, x255 * x255 - x511 * x511};
+                for (int q = 0; q < 3; q++) Fpre[(size_t)k * 3 + q] = (k > 0 ? Fpre[(size_t)(k - 1) * 3 + q] : 0.0) + D[q];
+            }
+            G.tile_slot = tile_slot.data(); G.tri = tri.data(); G.xc = xc.data(); G.F = Fpre.data();
         }
         const int64_t k_end = w1 / block_len;
         for (int pass = 0; pass < 64; pass++) {
