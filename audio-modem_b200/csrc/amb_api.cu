@@ -59,6 +59,9 @@ struct amb_modem {
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc;
+    DevBuf l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
+    int run_cap = 0;
+    int64_t link_iterations = 0, link_passes = 0;
     int slot_cap = 0, xc_w = 0;
     int64_t calls_stride = 0;
 };
@@ -264,7 +267,9 @@ void amb_destroy(amb_modem* m) {
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc};
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
+                     &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
+                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -547,6 +552,9 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    m->run_cap = (int)(max_push / 512) + 2;
+    CK(m->l_runs.ensure(ns * m->run_cap * sizeof(AmbRun))); CK(m->l_nruns.ensure(ns * 4)); CK(m->l_runoff.ensure(ns * 4));
+    CK(m->l_nlinks.ensure(ns * 4)); CK(m->l_active.ensure(ns * 4)); CK(m->l_nactive.ensure(16));
     std::vector<AmbStreamState> init(ns);
     std::memset(init.data(), 0, ns * sizeof(AmbStreamState));
     for (auto& s : init) { s.pre_pos = -1; s.frame_end = -1; }
@@ -562,7 +570,9 @@ int amb_stream_close(amb_modem* m) {
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc};
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
+                     &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
+                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -660,12 +670,60 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     }
     CK(m->jobs.ensure((size_t)ns * m->rec_cap * sizeof(AmbJob)));
     CK(m->s_sel.ensure((size_t)ns * 4));
-    for (int pass = 0; pass < 64 && n_todo > 0; pass++) {
+    for (int pass = 0; pass < 4096 && n_todo > 0; pass++) {
         CK(cudaMemsetAsync(m->nrec.p, 0, (size_t)ns * 4, m->stream));
         CK(cudaMemsetAsync(m->n_redo.p, 0, 4, m->stream));
         CK(cudaMemsetAsync(m->total.p, 0, 16, m->stream));
+        // streams without metadata yet: one frame per pass with the sequential walker
         LAUNCH("k_walk", k_walk<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
-                                                             m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>()));
+                                                             m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), 1));
+        // streams with metadata: link-parallel resolution (speculate, then verify; amb_walker.cuh)
+        {
+            AmbLinkBufs L;
+            std::memset(&L, 0, sizeof(L));
+            L.runs = m->l_runs.as<AmbRun>(); L.n_runs = m->l_nruns.as<int>(); L.run_off = m->l_runoff.as<int>(); L.run_cap = m->run_cap;
+            L.n_links = m->l_nlinks.as<int>(); L.active = m->l_active.as<int>(); L.n_active = m->l_nactive.as<int>();
+            CK(cudaMemsetAsync(L.n_runs, 0, (size_t)ns * 4, m->stream));
+            CK(cudaMemsetAsync(L.active, 0, (size_t)ns * 4, m->stream));
+            CK(cudaMemsetAsync(L.n_active, 0, 8, m->stream));
+            LAUNCH("k_runs_build", k_runs_build<<<n_todo, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
+                                                                               todo, n_todo, off0 / 256, (off0 + n_new) / 256, L));
+            LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
+            int total_runs = 0;
+            CK(cudaMemcpyAsync(&total_runs, L.n_active + 1, 4, cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            const size_t nr = (size_t)total_runs + 1, nl = (size_t)total_runs + ns + 1;
+            CK(m->l_recA.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_endA.ensure(nr * sizeof(AmbStreamState))); CK(m->l_hasA.ensure(nr * 4));
+            CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
+            CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
+            CK(m->l_hasB.ensure(nl * 4));
+            L.recA = m->l_recA.as<AmbFrameRec>(); L.endA = m->l_endA.as<AmbStreamState>(); L.hasA = m->l_hasA.as<int>(); L.next = m->l_next.as<int>();
+            L.vis = m->l_vis.as<unsigned char>(); L.jump_a = m->l_ja.as<int>(); L.jump_b = m->l_jb.as<int>();
+            L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
+            if (total_runs > 0) {
+                LAUNCH("k_link_walk_A", k_link_walk<<<blocks_for(total_runs, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
+                                                                                                    m->states.as<AmbStreamState>(), ns, 0, total_runs, L));
+                LAUNCH("k_chain_next", k_chain_next<<<blocks_for(total_runs, 128), 128, 0, m->stream>>>(ns, total_runs, L));
+            }
+            LAUNCH("k_link_first", k_link_first<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
+                                                                                             m->states.as<AmbStreamState>(), m->dc_next.as<double>(), todo, n_todo,
+                                                                                             m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+            int n_active = 0;
+            CK(cudaMemcpyAsync(&n_active, L.n_active, 4, cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            m->link_passes++;
+            for (int it = 0; n_active > 0 && it < (1 << 20); it++) {
+                m->link_iterations++;
+                CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
+                LAUNCH("k_chain_links", k_chain_links<<<ns, 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
+                LAUNCH("k_link_walk_B", k_link_walk<<<blocks_for(total_runs + ns, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
+                                                                                                         m->states.as<AmbStreamState>(), ns, 1, total_runs + ns, L));
+                LAUNCH("k_verify_links", k_verify_links<<<ns, 256, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi,
+                                                                                  m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+                CK(cudaMemcpyAsync(&n_active, L.n_active, 4, cudaMemcpyDeviceToHost, m->stream));
+                CK(cudaStreamSynchronize(m->stream));
+            }
+        }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));
         LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
                                                                   m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1));
@@ -681,7 +739,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         if ((rc = run_demod_parse(m, total, tot[1], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
         LAUNCH("k_post_stream", k_post_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                   m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
-                                                                  m->redo.as<int>(), m->n_redo.as<int>()));
+                                                                  m->redo.as<int>(), m->n_redo.as<int>(), g.k_end));
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
         LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
                                                bytes_stride, n_out, max_results, dst_res, dst_bytes));

@@ -264,13 +264,16 @@ struct AmbStreamGeom {
 __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                               const float* __restrict__ sums, AmbStreamState* __restrict__ states,
                                               const double* __restrict__ dc_next, const int* __restrict__ todo /*stream list or NULL*/,
-                                              int n_todo, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec) {
+                                              int n_todo, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, int pre_meta_only) {
     __shared__ AmbWalkScratch scratch[4];
     const int warp = threadIdx.x >> 5;
     const int w = blockIdx.x * 4 + warp;
     if (w >= n_todo) return;
     const int s = todo ? todo[w] : w;
     AmbStreamState st = states[s];
+    // pre_meta_only: streams that have seen a valid metadata frame are resolved link-parallel (k_link_*); the others
+    // advance one frame per pass here, because that frame may be the metadata frame that changes the collection window
+    if (pre_meta_only && st.meta_received) return;
     AmbWalkGeom G;
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
     G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
     sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
     const int n = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, recs + (int64_t)s * g.rec_cap,
-                           g.rec_cap, &scratch[warp]);
+                           g.rec_cap, &scratch[warp], pre_meta_only ? 1 : 0x7fffffff);
     if ((threadIdx.x & 31) == 0) {
         st.dc_mean = dc_next[s];
         st.written = g.avail_hi;
@@ -827,14 +830,16 @@ __global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __rest
 __global__ void k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
                               const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
                               AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
-                              int* __restrict__ redo_list, int* __restrict__ n_redo) {
+                              int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     const int cnt = nrec[s], o = job_off[s];
     if (cnt == 0) return;
     AmbStreamState st;
-    const int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, states[s], &st, keep + o);
+    int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, states[s], &st, keep + o);
     states[s] = st;
+    // a stream still waiting for its metadata frame advances one frame per pass (k_walk, pre_meta_only)
+    if (!st.meta_received && st.next_call < k_end) redo = 1;
     if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
 }
 
@@ -1003,5 +1008,279 @@ __global__ void __launch_bounds__(128) k_xcorr_store(const AmbTables* __restrict
             else v = AMB_XC_UNSURE;
             out[o0 + q] = v;
         }
+    }
+}
+
+// ================================================================================================
+// Link-parallel stream resolution (amb_walker.cuh, "speculate, then verify").  Streams that have seen a valid
+// metadata frame take this path; the others are walked one frame per pass by k_walk (their pre-metadata behaviour
+// re-scans inside frames and does not speculate well, and it ends with the first metadata frame).
+// ================================================================================================
+struct AmbLinkBufs {
+    AmbRun* runs;            // [n_streams][run_cap]
+    int* n_runs;             // [n_streams]
+    int* run_off;            // [n_streams] exclusive prefix of n_runs
+    int run_cap;
+    // phase A (per flat run index run_off[s] + r)
+    AmbFrameRec* recA; AmbStreamState* endA; int* hasA; int* next;
+    // chain / phase B (per flat link index run_off[s] + s + i; stream s owns n_runs[s] + 1 entries)
+    int* link_run;           // run index, -1 tail link, -2 unused
+    int* n_links;            // [n_streams]
+    AmbStreamState* outB; AmbFrameRec* recB; int* hasB;
+    unsigned char* vis; int* jump_a; int* jump_b;     // chain scratch, per flat run index
+    int* active;             // [n_streams] 1 = needs another iteration
+    int* n_active;
+};
+
+__device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
+    const int sl = tile_slot[idx];
+    return sl >= 0 && slot_info[sl * 4 + 2] != 0;
+}
+
+// ordered list of candidate runs of this push for every stream on the link path (one CTA per stream)
+__global__ void __launch_bounds__(256) k_runs_build(AmbStreamGeom g, const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info,
+                                                     const AmbStreamState* __restrict__ states, const int* __restrict__ todo, int n_todo,
+                                                     int64_t tile_lo, int64_t tile_hi, AmbLinkBufs L) {
+    if ((int)blockIdx.x >= n_todo) return;
+    const int s = todo ? todo[blockIdx.x] : blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int wsum[8];
+    __shared__ int base;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    if (!states[s].meta_received) { if (tid == 0) L.n_runs[s] = 0; return; }
+    const int32_t* ts = tile_slot + (int64_t)s * g.sum_stride;
+    AmbRun* runs = L.runs + (int64_t)s * L.run_cap;
+    const int PER = 16;
+    for (int64_t c0 = tile_lo; c0 < tile_hi; c0 += 256 * PER) {
+        const int64_t t0 = c0 + (int64_t)tid * PER;
+        int starts = 0;
+        bool prev = (t0 > tile_lo && t0 - 1 < tile_hi) ? tile_is_cand(ts, slot_info, t0 - 1) : false;
+        unsigned cmask = 0;
+        for (int i = 0; i < PER; i++) {
+            const int64_t t = t0 + i;
+            const bool c = t < tile_hi && tile_is_cand(ts, slot_info, t);
+            if (c) cmask |= 1u << i;
+            if (c && !prev) starts++;
+            prev = c;
+        }
+        // exclusive prefix of `starts` over the block
+        int v = starts;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; w++) woff += wsum[w];
+        int idx = base + woff + v - starts;      // index of this thread's first run start
+        // a run that continues from the previous thread's tiles has index idx - 1
+        prev = (t0 > tile_lo && t0 - 1 < tile_hi) ? tile_is_cand(ts, slot_info, t0 - 1) : false;
+        for (int i = 0; i < PER; i++) {
+            const int64_t t = t0 + i;
+            if (t >= tile_hi) break;
+            const bool c = (cmask >> i) & 1u;
+            const int64_t first = g.base_g + (t << 8) - 511;
+            if (c && !prev) { if (idx < L.run_cap) runs[idx].first_pos = first; idx++; }
+            if (c) {
+                const bool nxt = (t + 1 < tile_hi) && tile_is_cand(ts, slot_info, t + 1);
+                if (!nxt && idx - 1 < L.run_cap && idx >= 1) runs[idx - 1].last_pos = first + 255;
+            }
+            prev = c;
+        }
+        __syncthreads();
+        if (tid == 255) base = base + woff + v;
+        __syncthreads();
+    }
+    if (tid == 0) L.n_runs[s] = base < L.run_cap ? base : L.run_cap;
+}
+
+__device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n_streams, int f, int extra_per_stream) {
+    // largest s with off[s] + s*extra <= f
+    int lo = 0, hi = n_streams - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] + mid * extra_per_stream <= f) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+// One warp per link.  mode 0 (phase A): flat run index, synthetic start before the run.  mode 1 (phase B): flat link
+// index, start state = the stream's current state (link 0) or the phase-A end state of the previous chain run.
+__global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                                                    const float* __restrict__ sums, const AmbStreamState* __restrict__ states, int n_streams,
+                                                    int mode, int total, AmbLinkBufs L) {
+    __shared__ AmbWalkScratch scratch[4];
+    const int warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * 4 + warp;
+    if (f >= total) return;
+    const int s = stream_of_flat(L.run_off, n_streams, f, mode);
+    const int i = f - (L.run_off[s] + s * mode);
+    AmbStreamState st;
+    if (mode == 0) {
+        if (i >= L.n_runs[s]) return;
+    } else {
+        if (!L.active[s] || i >= L.n_links[s]) return;
+    }
+    AmbWalkGeom G;
+    G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+    G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+    if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
+    else if (i == 0) st = states[s];
+    else st = L.endA[L.run_off[s] + L.link_run[f - 1]];
+    AmbSig sig;
+    sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
+    sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+    AmbFrameRec* rec = mode == 0 ? L.recA + f : L.recB + f;
+    const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, rec, 1, &scratch[warp], 1);
+    if ((threadIdx.x & 31) == 0) {
+        if (mode == 0) { L.endA[f] = st; L.hasA[f] = has; }
+        else { L.outB[f] = st; L.hasB[f] = has; }
+    }
+}
+
+// next[r] = first run still ahead of run r's frame end (local index; n = none)
+__global__ void k_chain_next(int n_streams, int total, AmbLinkBufs L) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total) return;
+    const int s = stream_of_flat(L.run_off, n_streams, f, 0);
+    const int r = f - L.run_off[s], n = L.n_runs[s];
+    if (r >= n) return;
+    int nx = n;
+    if (L.hasA[f]) {
+        nx = amb_run_at_or_after(L.runs + (int64_t)s * L.run_cap, n, L.endA[f].ac_scan_pos);
+        if (nx <= r) nx = n;
+    }
+    L.next[f] = nx;
+}
+
+// First link of the pass: one frame from the carried state (which may be mid-frame).  One warp per stream.
+__global__ void __launch_bounds__(128) k_link_first(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                                                     const float* __restrict__ sums, AmbStreamState* __restrict__ states,
+                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo,
+                                                     AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
+    __shared__ AmbWalkScratch scratch[4];
+    const int warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + warp;
+    if (w >= n_todo) return;
+    const int s = todo ? todo[w] : w;
+    AmbStreamState st = states[s];
+    if (!st.meta_received) { if ((threadIdx.x & 31) == 0) L.active[s] = 0; return; }
+    AmbWalkGeom G;
+    G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+    G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+    AmbSig sig;
+    sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
+    sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+    const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, recs + (int64_t)s * g.rec_cap, 1,
+                             &scratch[warp], 1);
+    if ((threadIdx.x & 31) == 0) {
+        st.dc_mean = dc_next[s]; st.written = g.avail_hi;
+        states[s] = st;
+        nrec[s] = has;
+        L.active[s] = has ? 1 : 0;       // no frame: the push is exhausted for this stream
+        if (has) atomicAdd(L.n_active, 1);
+    }
+}
+
+// Speculated chain of an active stream from its current (post-reset) state: the runs reachable through next[],
+// in order, plus a tail link when the last of them is expected to emit a frame.  One CTA per stream.
+__global__ void __launch_bounds__(256) k_chain_links(int n_streams, const AmbStreamState* __restrict__ states, AmbLinkBufs L) {
+    const int s = blockIdx.x;
+    if (s >= n_streams || !L.active[s]) return;
+    const int tid = threadIdx.x;
+    const int n = L.n_runs[s], off = L.run_off[s];
+    const AmbRun* runs = L.runs + (int64_t)s * L.run_cap;
+    unsigned char* vis = L.vis + off;
+    int* ja = L.jump_a + off;
+    int* jb = L.jump_b + off;
+    int* link_run = L.link_run + off + s;
+    const AmbStreamState st = states[s];
+    int first = n;
+    if (st.state == AMB_RX_IDLE && !st.ac_init) first = amb_run_at_or_after(runs, n, st.ac_scan_pos);
+    for (int r = tid; r < n; r += 256) { vis[r] = r == first; ja[r] = L.next[off + r]; }
+    __syncthreads();
+    // pointer doubling: after round k every run within distance < 2^(k+1) of `first` is marked
+    for (int span = 1; span < n; span <<= 1) {
+        for (int r = tid; r < n; r += 256) if (vis[r] && ja[r] < n) vis[ja[r]] = 1;
+        __syncthreads();
+        for (int r = tid; r < n; r += 256) { const int j = ja[r]; jb[r] = j < n ? ja[j] : n; }
+        __syncthreads();
+        int* t = ja; ja = jb; jb = t;
+    }
+    // ordered compaction of the visited runs
+    __shared__ int wsum[8];
+    __shared__ int base;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c0 = 0; c0 < n; c0 += 256) {
+        const int r = c0 + tid;
+        const int v = r < n && vis[r];
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 8; w++) { if (w < warp) woff += wsum[w]; tot += wsum[w]; }
+        if (v) {
+            const int idx = base + woff + __popc(m & ((1u << lane) - 1));
+            link_run[idx] = r;
+        }
+        __syncthreads();
+        if (tid == 0) base += tot;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = base;
+        const bool tail = m == 0 || L.hasA[off + link_run[m - 1]];
+        if (tail) link_run[m++] = -1;
+        L.n_links[s] = m;
+    }
+}
+
+// Accepts the verified prefix of the chain (see amb_walker.cuh) and leaves the stream either finished for this push or
+// ready for another chain from the exact state where the speculation failed.  One CTA per stream.
+__global__ void __launch_bounds__(256) k_verify_links(int n_streams, int rec_cap, AmbStreamState* __restrict__ states, const double* __restrict__ dc_next,
+                                                       int64_t avail_hi, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
+    const int s = blockIdx.x;
+    if (s >= n_streams || !L.active[s]) return;
+    const int tid = threadIdx.x;
+    const int off = L.run_off[s], lo = off + s, m = L.n_links[s];
+    __shared__ int first_stop;
+    __shared__ unsigned long long fp_sum;
+    if (tid == 0) { first_stop = m - 1; fp_sum = 0ull; }
+    __syncthreads();
+    for (int i = tid; i < m; i += 256) {
+        const int run = L.link_run[lo + i];
+        bool stop = !L.hasB[lo + i];
+        if (!stop) {
+            const bool ok = run >= 0 && L.hasA[off + run] == 1 && amb_same_link_state(L.outB[lo + i], L.endA[off + run]);
+            stop = !ok;
+        }
+        if (stop) atomicMin(&first_stop, i);
+    }
+    __syncthreads();
+    const int stop = first_stop;
+    const int have = nrec[s];
+    const int64_t fp_base = states[s].false_pos;
+    for (int i = tid; i <= stop; i += 256) {
+        if (L.hasB[lo + i] && have + i < rec_cap) recs[(int64_t)s * rec_cap + have + i] = L.recB[lo + i];
+        // refine failures (app.js:879-884) are counted per link: end-state counter minus the link's start-state counter
+        const int64_t in_fp = i == 0 ? fp_base : L.endA[off + L.link_run[lo + i - 1]].false_pos;
+        const int64_t d = L.outB[lo + i].false_pos - in_fp;
+        if (d > 0) atomicAdd(&fp_sum, (unsigned long long)d);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // links before `stop` all emitted a frame
+        const int acc = L.hasB[lo + stop] ? stop + 1 : stop;
+        int total = have + acc;
+        if (total > rec_cap) total = rec_cap;
+        nrec[s] = total;
+        AmbStreamState st = L.outB[lo + stop];
+        st.dc_mean = dc_next[s]; st.written = avail_hi;
+        st.false_pos = fp_base + (int64_t)fp_sum;
+        states[s] = st;
+        const int again = L.hasB[lo + stop] && total < rec_cap ? 1 : 0;      // stopped at a frame: chain again from its exact end state
+        L.active[s] = again;
+        if (again) atomicAdd(L.n_active, 1);
     }
 }

@@ -341,7 +341,7 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
 // Runs calls [st.next_call, k_end) of one stream.  Emits one record per completed frame.
 // Returns the number of records written (stops early, leaving st.next_call behind k_end, if `cap` is hit).
 AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums, AmbStreamState& st,
-                    int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W) {
+                    int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W, int stop_after = 0x7fffffff) {
     int n = 0;
     while (st.next_call < k_end) {
         if (amb_walk_skip_cold_calls(G, sums, st, k_end, W) > 0) continue;
@@ -360,6 +360,7 @@ AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig,
             rec.snap = st;
             if (AMB_LEADER()) out[n] = rec;
             n++;
+            if (n >= stop_after) return n;
             continue;
         }
         st.next_call++;
@@ -403,4 +404,46 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
     st.frames_decoded = fd; st.frame_errors = fe; st.received = rc; st.crc_errors = ce;
     *out = st;
     return rewind >= 0 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Link-parallel resolution of one stream (speculate, then verify with the exact walker).
+//
+// After every frame the receiver re-initialises its scan at the frame end, so a stream is a chain of LINKS: a
+// link starts in a post-reset state (scan position e, next call k, flags) and ends with the next frame's reset.
+// A link's outcome is a deterministic function of its start state.  Candidate RUNS (maximal groups of consecutive
+// tiles holding a window with metric > 0.5) are where links can end, and they are known from the scan kernel.
+//   phase A: every run is walked from a synthetic start just before it (one warp each, all in parallel);
+//   chain  : next[r] = first run still ahead of run r's frame end; the runs reachable from the current state are
+//            the speculated chain;
+//   phase B: every chain link is walked again, now from its predecessor's phase-A end state, with the same exact
+//            walker; link i is exact if links < i reproduced their phase-A end states.  At the first link whose
+//            phase-B end state differs from the speculation, the chain is rebuilt from that (exact) state.
+// The helpers below are the pieces shared by the CUDA kernels and the host emulation.
+// ------------------------------------------------------------------------------------------------
+struct AmbRun { int64_t first_pos, last_pos; };      // window positions covered by the run's tiles
+
+// synthetic start of phase A: scan re-initialised one tile before the run, in the call that first sees that position
+AMB_HD AmbStreamState amb_run_start_state(const AmbStreamState& flags_from, const AmbRun& r, const AmbWalkGeom& G) {
+    AmbStreamState s = flags_from;
+    int64_t p = r.first_pos - 256;
+    if (p < 0) p = 0;
+    s.state = AMB_RX_IDLE; s.ac_init = 0; s.lag = 0; s.ac_scan_pos = p; s.pre_pos = -1; s.frame_end = -1;
+    s.Ep = s.Ea = s.Eb = 0.0;
+    s.next_call = (p + 511) / G.block_len;
+    return s;
+}
+
+// first run with windows at or after position e (runs are sorted by position); n if none
+AMB_HD int amb_run_at_or_after(const AmbRun* runs, int n, int64_t e) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (runs[mid].last_pos >= e) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// do two post-link states describe the same receiver? (everything the next link depends on)
+AMB_HD bool amb_same_link_state(const AmbStreamState& a, const AmbStreamState& b) {
+    return a.state == b.state && a.ac_init == b.ac_init && a.ac_scan_pos == b.ac_scan_pos && a.next_call == b.next_call &&
+           a.pre_pos == b.pre_pos && a.frame_end == b.frame_end && a.meta_received == b.meta_received && a.chunk_size == b.chunk_size &&
+           (a.ac_init == 0 || (a.lag == b.lag && a.Ep == b.Ep && a.Ea == b.Ea && a.Eb == b.Eb));
 }

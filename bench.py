@@ -230,6 +230,7 @@ def run_b200(args, rank, world, local_rank):
         m.stream_push(segs[w % len(segs)], collect=False)
     m.synchronize()
     torch.cuda.synchronize()
+    c0 = m.stream_counters()
     if dist:
         dist.barrier()
     clocks = ClockSampler(local_rank)

@@ -6,6 +6,7 @@
 // with the oracle on a machine without a GPU.  It is not part of the product and is never loaded by it; the
 // parallel decomposition itself (thread indexing, shared memory, scans) is only exercised by the -m gpu tests.
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -76,8 +77,82 @@ int emu_decode_chunk_frame(int cfg, int mod, int rep, const float* x, int64_t n,
 
 // streaming receiver through the device logic: EMA (sequential, as the reference), tile summaries computed
 // directly, then walk / decode / post until no stream needs another walk.  Pushes of `push_len` samples.
-static int g_use_stores = 1;
+static int g_use_stores = 1, g_use_links = 1;
+static int64_t g_link_iters = 0, g_link_walks = 0, g_link_pushes = 0;
 void emu_use_stores(int on) { g_use_stores = on; }
+void emu_use_links(int on) { g_use_links = on; }
+void emu_link_stats(int64_t* out) { out[0] = g_link_iters; out[1] = g_link_walks; out[2] = g_link_pushes; g_link_iters = g_link_walks = g_link_pushes = 0; }
+
+// Link-parallel resolution of one stream for one push (sequential stand-in for k_link_* / k_chain): returns the
+// number of frame records written, leaves the end-of-push state in st.
+static int resolve_links(const AmbTables& T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums, AmbStreamState& st, int64_t k_end,
+                         const std::vector<AmbRun>& runs, std::vector<AmbFrameRec>& out, AmbWalkScratch* W) {
+    const int n = (int)runs.size();
+    g_link_pushes++;
+    // phase A
+    std::vector<AmbFrameRec> recA((size_t)n);
+    std::vector<AmbStreamState> endA((size_t)n);
+    std::vector<int> hasA((size_t)n, 0);
+    for (int r = 0; r < n; r++) {
+        AmbStreamState s = amb_run_start_state(st, runs[r], G);
+        hasA[r] = amb_walk(&T, G, sig, sums, s, k_end, 0, &recA[r], 1, W, 1);
+        endA[r] = s; g_link_walks++;
+    }
+    int n_out = 0;
+    AmbStreamState cur = st;
+    // first link from the carried state (always exact)
+    {
+        AmbFrameRec rec;
+        const int got = amb_walk(&T, G, sig, sums, cur, k_end, 0, &rec, 1, W, 1);
+        g_link_walks++;
+        if (!got) { st = cur; return 0; }
+        out[n_out++] = rec;
+    }
+    for (int iter = 0; iter < 1 << 20; iter++) {
+        g_link_iters++;
+        // chain from cur
+        std::vector<int> chain;
+        if (cur.state == AMB_RX_IDLE && !cur.ac_init) {
+            int r = amb_run_at_or_after(runs.data(), n, cur.ac_scan_pos);
+            while (r < n) {
+                chain.push_back(r);
+                if (!hasA[r]) break;
+                const int nx = amb_run_at_or_after(runs.data(), n, endA[r].ac_scan_pos);
+                r = nx > r ? nx : n;
+            }
+        }
+        // links: run links + a tail link when the last run link is expected to emit a frame (or when there is no run)
+        const bool tail = chain.empty() || hasA[chain.back()];
+        const int m = (int)chain.size() + (tail ? 1 : 0);
+        std::vector<AmbStreamState> in((size_t)m), outB((size_t)m);
+        std::vector<AmbFrameRec> recB((size_t)m);
+        std::vector<int> hasB((size_t)m);
+        for (int i = 0; i < m; i++) in[i] = i == 0 ? cur : endA[chain[i - 1]];
+        for (int i = 0; i < m; i++) {          // phase B: independent walks (parallel on the GPU)
+            AmbStreamState s = in[i];
+            hasB[i] = amb_walk(&T, G, sig, sums, s, k_end, 0, &recB[i], 1, W, 1);
+            outB[i] = s; g_link_walks++;
+        }
+        bool redo = false;
+        for (int i = 0; i < m; i++) {
+            if (hasB[i]) out[n_out++] = recB[i];
+            if (!hasB[i]) { st = outB[i]; if (getenv("EMU_DEBUG")) fprintf(stderr, "resolve: meta %d runs %d frames %d iterations %d\n", st.meta_received, n, n_out, iter + 1); return n_out; }
+            const bool is_run = i < (int)chain.size();
+            const bool ok = is_run && hasA[chain[i]] == hasB[i] && amb_same_link_state(outB[i], endA[chain[i]]);
+            if (!ok && getenv("EMU_DEBUG")) {
+                const AmbStreamState& x = outB[i]; 
+                if (is_run) { const AmbStreamState& y = endA[chain[i]];
+                  fprintf(stderr, "mismatch link %d/%d run %d hasA %d hasB %d | B: st %d init %d scan %lld call %lld  | A: st %d init %d scan %lld call %lld | recB pos %lld recA pos %lld in.scan %lld in.call %lld runfirst %lld\n", i, m, chain[i], hasA[chain[i]], hasB[i],
+                        x.state, x.ac_init, (long long)x.ac_scan_pos, (long long)x.next_call, y.state, y.ac_init, (long long)y.ac_scan_pos, (long long)y.next_call,
+                        (long long)recB[i].pos, (long long)recA[chain[i]].pos, (long long)in[i].ac_scan_pos, (long long)in[i].next_call, (long long)runs[chain[i]].first_pos); }
+                else fprintf(stderr, "tail link emitted a frame at %lld\n", (long long)recB[i].pos);
+            }
+            if (!ok) { cur = outB[i]; redo = true; break; }
+        }
+        if (!redo) { st = outB[m - 1]; return n_out; }                       // cannot happen: the last link ends the push
+    }
+    return n_out;
+}
 
 int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t block_len, int64_t push_len,
                amb_frame_result* res_out, int max_res, uint8_t* bytes_out, int64_t bytes_stride, int64_t* counters) {
@@ -154,8 +229,24 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
             G.tile_slot = tile_slot.data(); G.tri = tri.data(); G.xc = xc.data(); G.F = Fpre.data();
         }
         const int64_t k_end = w1 / block_len;
-        for (int pass = 0; pass < 64; pass++) {
-            const int cnt = amb_walk(&T, G, sig, sums.data(), st, k_end, 0, recs.data(), (int)recs.size(), &W);
+        for (int pass = 0; pass < 4096; pass++) {
+            int cnt;
+            if (g_use_links && g_use_stores && !st.meta_received) {
+                // no metadata yet: one frame per pass with the sequential walker (k_walk, pre_meta_only)
+                cnt = amb_walk(&T, G, sig, sums.data(), st, k_end, 0, recs.data(), (int)recs.size(), &W, 1);
+            } else if (g_use_links && g_use_stores) {
+                // candidate runs of this push (k_scan_sums marks the tiles): consecutive tiles holding a candidate window
+                std::vector<AmbRun> runs;
+                for (int64_t j = 0; j < n_tiles; j++) {
+                    const int sl = tile_slot[(size_t)j];
+                    const bool c = sl >= 0 && xc[(size_t)sl * xc_w] != AMB_XC_UNSURE;     // emu marks candidate tiles by filling xc
+                    if (!c) continue;
+                    const int64_t first = j * 256 - 511, last = first + 255;
+                    if (!runs.empty() && runs.back().last_pos + 1 == first) runs.back().last_pos = last;
+                    else runs.push_back({first, last});
+                }
+                cnt = resolve_links(T, G, sig, sums.data(), st, k_end, runs, recs, &W);
+            } else cnt = amb_walk(&T, G, sig, sums.data(), st, k_end, 0, recs.data(), (int)recs.size(), &W);
             if (cnt == 0) break;
             std::vector<Frame> fr((size_t)cnt);
             std::vector<amb_frame_result> rr((size_t)cnt);
@@ -183,7 +274,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 }
                 n_out++;
             }
-            if (!redo) break;
+            if (!redo && !(g_use_links && g_use_stores && !st.meta_received && st.next_call < k_end)) break;
         }
     }
     if (counters) {
