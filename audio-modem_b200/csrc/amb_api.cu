@@ -59,7 +59,7 @@ struct amb_modem {
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc;
-    DevBuf l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
+    DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     int run_cap = 0;
     int64_t link_iterations = 0, link_passes = 0;
     int slot_cap = 0, xc_w = 0;
@@ -268,7 +268,7 @@ void amb_destroy(amb_modem* m) {
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
-                     &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
+                     &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
@@ -571,7 +571,7 @@ int amb_stream_close(amb_modem* m) {
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
-                     &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
+                     &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
     for (DevBuf* b : all) b->release();
     m->open = false;
@@ -644,7 +644,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     CK(cudaMemsetAsync(m->tile_slot.p, 0xFF, (size_t)ns * m->sum_stride * 4, m->stream));      // history tiles: no slot (-1)
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
     LAUNCH("k_scan_sums", k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride, ss));
-    LAUNCH("k_defect_prefix", k_defect_prefix<<<blocks_for(ns, 4), 128, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_new / AMB_TILE, ns));
+    LAUNCH("k_defect_prefix", k_defect_prefix<<<ns, 256, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_new / AMB_TILE, ns));
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;
     g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
@@ -686,8 +686,16 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
             CK(cudaMemsetAsync(L.n_runs, 0, (size_t)ns * 4, m->stream));
             CK(cudaMemsetAsync(L.active, 0, (size_t)ns * 4, m->stream));
             CK(cudaMemsetAsync(L.n_active, 0, 8, m->stream));
-            LAUNCH("k_runs_build", k_runs_build<<<n_todo, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
-                                                                               todo, n_todo, off0 / 256, (off0 + n_new) / 256, L));
+            {
+                const int64_t tile_lo = off0 / 256, tile_hi = (off0 + n_new) / 256;
+                const int chunks = (int)((tile_hi - tile_lo + AMB_RUN_CHUNK - 1) / AMB_RUN_CHUNK);
+                CK(m->l_chunks.ensure((size_t)ns * chunks * 4));
+                LAUNCH("k_runs_count", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
+                                                                                          todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 0, L));
+                LAUNCH("k_runs_offsets", k_runs_offsets<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->states.as<AmbStreamState>(), todo, n_todo, chunks, m->l_chunks.as<int>(), L));
+                LAUNCH("k_runs_write", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
+                                                                                          todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 1, L));
+            }
             LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
             int total_runs = 0;
             CK(cudaMemcpyAsync(&total_runs, L.n_active + 1, 4, cudaMemcpyDeviceToHost, m->stream));
@@ -725,7 +733,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
             }
         }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));
-        LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
+        LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for((int64_t)ns * m->rec_cap, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
                                                                   m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1));
         int tot[2] = {0, 0};   // frames, max data symbols
         CK(cudaMemcpyAsync(tot, m->total.p, 8, cudaMemcpyDeviceToHost, m->stream));
@@ -737,7 +745,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
         if ((rc = run_demod_parse(m, total, tot[1], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
-        LAUNCH("k_post_stream", k_post_stream<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+        LAUNCH("k_post_stream", k_post_stream<<<ns, 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                   m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
                                                                   m->redo.as<int>(), m->n_redo.as<int>(), g.k_end));
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));

@@ -760,25 +760,23 @@ __global__ void k_jobs_rows(const AmbTables* __restrict__ T, const float* __rest
 __global__ void k_jobs_stream(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                               const AmbFrameRec* __restrict__ recs, const int* __restrict__ nrec, const int* __restrict__ job_off,
                               int n_streams, AmbJob* __restrict__ jobs, int* __restrict__ max_nsym) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    const int cnt = nrec[s], o = job_off[s];
-    for (int i = 0; i < cnt; i++) {
-        const AmbFrameRec& R = recs[(int64_t)s * g.rec_cap + i];
-        AmbJob J;
-        J.p = cleaned + (int64_t)s * g.stride; J.base = g.base_g; J.lo = g.base_g > 0 ? g.base_g : 0; J.hi = g.avail_hi;
-        J.xf.kind = AMB_XF_SCALE; J.xf.mx = 0.f; J.xf.mean = 0.0;
-        J.stream = s; J.mode = 0; J.status = R.status; J.pos = R.pos; J.len = R.len; J.coarse = R.coarse; J.fine = R.fine;
-        J.result_pos = R.pos;
-        J.ce_pos = R.pos + 2 * (int64_t)T->sym_len; J.data_pos = R.pos + 3 * (int64_t)T->sym_len; J.nsym = 0;
-        if (R.status == 0) {
-            if (2 * (int64_t)T->sym_len + T->sym_len > R.len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
-            else if (3 * (int64_t)T->sym_len >= R.len) J.status = AMB_ST_NO_DATA_AFTER_CE;
-            else J.nsym = (int32_t)((R.len - 3 * (int64_t)T->sym_len) / T->sym_len);
-        }
-        jobs[o + i] = J;
-        if (J.nsym > 0) atomicMax(max_nsym, J.nsym);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (stream, record slot)
+    const int s = (int)(idx / g.rec_cap), i = (int)(idx % g.rec_cap);
+    if (s >= n_streams || i >= nrec[s]) return;
+    const AmbFrameRec& R = recs[(int64_t)s * g.rec_cap + i];
+    AmbJob J;
+    J.p = cleaned + (int64_t)s * g.stride; J.base = g.base_g; J.lo = g.base_g > 0 ? g.base_g : 0; J.hi = g.avail_hi;
+    J.xf.kind = AMB_XF_SCALE; J.xf.mx = 0.f; J.xf.mean = 0.0;
+    J.stream = s; J.mode = 0; J.status = R.status; J.pos = R.pos; J.len = R.len; J.coarse = R.coarse; J.fine = R.fine;
+    J.result_pos = R.pos;
+    J.ce_pos = R.pos + 2 * (int64_t)T->sym_len; J.data_pos = R.pos + 3 * (int64_t)T->sym_len; J.nsym = 0;
+    if (R.status == 0) {
+        if (2 * (int64_t)T->sym_len + T->sym_len > R.len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
+        else if (3 * (int64_t)T->sym_len >= R.len) J.status = AMB_ST_NO_DATA_AFTER_CE;
+        else J.nsym = (int32_t)((R.len - 3 * (int64_t)T->sym_len) / T->sym_len);
     }
+    jobs[job_off[s] + i] = J;
+    if (J.nsym > 0) atomicMax(max_nsym, J.nsym);
 }
 
 // Copies the kept frames (results + decoded bytes) to consecutive output rows starting at out_base.
@@ -825,18 +823,42 @@ __global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __rest
     if (threadIdx.x == 0) *total = carry;
 }
 
-// Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the
-// streams whose collection window changed for another walk.
-__global__ void k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
+// Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the streams whose
+// collection window changed for another walk.  One CTA per stream.  Without a CRC-valid metadata frame among them (the
+// steady state) the frames only move counters, which is a parallel count; otherwise thread 0 applies them sequentially.
+__global__ void __launch_bounds__(128) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
                               const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
                               AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
                               int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x;
     if (s >= n_streams) return;
-    const int cnt = nrec[s], o = job_off[s];
+    const int cnt = nrec[s], o = job_off[s], tid = threadIdx.x;
     if (cnt == 0) return;
+    __shared__ int n_valid_meta;
+    __shared__ unsigned long long c_fd, c_fe, c_rc, c_ce;
+    if (tid == 0) { n_valid_meta = 0; c_fd = c_fe = c_rc = c_ce = 0ull; }
+    __syncthreads();
+    const AmbStreamState cur = states[s];
+    unsigned fd = 0, fe = 0, rc = 0, ce = 0;
+    for (int i = tid; i < cnt; i += blockDim.x) {
+        const amb_frame_result& r = results[o + i];
+        keep[o + i] = 1;
+        if (r.status != 0) { fe++; continue; }
+        fd++;
+        if (r.frame_type == AMB_FRAME_META) { if (r.crc_valid) atomicAdd(&n_valid_meta, 1); else fe++; }
+        else if (r.frame_type == AMB_FRAME_DATA && cur.meta_received == 1 && !(r.seq_num >= cur.total_chunks)) { if (r.crc_valid) rc++; else ce++; }
+    }
+    atomicAdd(&c_fd, (unsigned long long)fd); atomicAdd(&c_fe, (unsigned long long)fe);
+    atomicAdd(&c_rc, (unsigned long long)rc); atomicAdd(&c_ce, (unsigned long long)ce);
+    __syncthreads();
+    if (tid != 0) return;
     AmbStreamState st;
-    int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, states[s], &st, keep + o);
+    int redo = 0;
+    if (n_valid_meta > 0) redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o);
+    else {
+        st = cur;
+        st.frames_decoded += (int64_t)c_fd; st.frame_errors += (int64_t)c_fe; st.received += (int64_t)c_rc; st.crc_errors += (int64_t)c_ce;
+    }
     states[s] = st;
     // a stream still waiting for its metadata frame advances one frame per pass (k_walk, pre_meta_only)
     if (!st.meta_received && st.next_call < k_end) redo = 1;
@@ -916,24 +938,30 @@ __global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__
 }
 
 // Inclusive prefix over calls of the defect terms: F[c] = F[c-1] + D[c] for the n new arena calls starting at c0
-// (one warp per stream; F[c0-1] is the carry from the previous push, 0 before the stream start).
-__global__ void __launch_bounds__(128) k_defect_prefix(const double* __restrict__ D, double* __restrict__ F, int64_t calls_stride, int64_t c0, int64_t n,
+// (F[c0-1] is the carry from the previous push, 0 before the stream start).  One CTA per stream: contiguous chunks per
+// thread, block scan of the chunk totals.
+__global__ void __launch_bounds__(256) k_defect_prefix(const double* __restrict__ D, double* __restrict__ F, int64_t calls_stride, int64_t c0, int64_t n,
                                                        int n_streams) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 4 + warp;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (s >= n_streams) return;
-    const double* d = D + (int64_t)s * calls_stride * 3;
-    double* f = F + (int64_t)s * calls_stride * 3;
-    double carry[3];
-    for (int c = 0; c < 3; c++) carry[c] = c0 > 0 ? f[(c0 - 1) * 3 + c] : 0.0;
-    for (int64_t base = 0; base < n; base += 32) {
-        const int64_t i = base + lane;
-        double v[3];
-        for (int c = 0; c < 3; c++) v[c] = i < n ? d[(c0 + i) * 3 + c] : 0.0;
-        for (int o = 1; o < 32; o <<= 1)
-            for (int c = 0; c < 3; c++) { const double u = __shfl_up_sync(0xffffffffu, v[c], o); if (lane >= o) v[c] += u; }
-        for (int c = 0; c < 3; c++) { v[c] += carry[c]; if (i < n) f[(c0 + i) * 3 + c] = v[c]; carry[c] = __shfl_sync(0xffffffffu, v[c], 31); }
+    const double* d = D + ((int64_t)s * calls_stride + c0) * 3;
+    double* f = F + ((int64_t)s * calls_stride + c0) * 3;
+    const int64_t per = (n + 255) / 256, lo = (int64_t)tid * per, hi = lo + per < n ? lo + per : n;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = lo; i < hi; i++) for (int c = 0; c < 3; c++) v[c] += d[i * 3 + c];
+    double inc[3] = {v[0], v[1], v[2]};
+    for (int o = 1; o < 32; o <<= 1)
+        for (int c = 0; c < 3; c++) { const double u = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += u; }
+    __shared__ double wtot[8][3];
+    if (lane == 31) for (int c = 0; c < 3; c++) wtot[warp][c] = inc[c];
+    __syncthreads();
+    double off[3];
+    for (int c = 0; c < 3; c++) {
+        off[c] = c0 > 0 ? F[((int64_t)s * calls_stride + c0 - 1) * 3 + c] : 0.0;
+        for (int w = 0; w < warp; w++) off[c] += wtot[w][c];
+        off[c] += inc[c] - v[c];
     }
+    for (int64_t i = lo; i < hi; i++) for (int c = 0; c < 3; c++) { off[c] += d[i * 3 + c]; f[i * 3 + c] = off[c]; }
 }
 
 // Cross-correlation screening values for every slot whose tile holds a candidate: float32 metric of preamble-1 at the
@@ -1037,60 +1065,76 @@ __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_sl
     return sl >= 0 && slot_info[sl * 4 + 2] != 0;
 }
 
-// ordered list of candidate runs of this push for every stream on the link path (one CTA per stream)
-__global__ void __launch_bounds__(256) k_runs_build(AmbStreamGeom g, const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info,
-                                                     const AmbStreamState* __restrict__ states, const int* __restrict__ todo, int n_todo,
-                                                     int64_t tile_lo, int64_t tile_hi, AmbLinkBufs L) {
-    if ((int)blockIdx.x >= n_todo) return;
-    const int s = todo ? todo[blockIdx.x] : blockIdx.x;
+// Ordered list of the candidate runs of this push for every stream on the link path.  A chunk is 4096 tiles (256
+// threads x 16 tiles); pass 0 counts the run starts of each chunk, k_runs_offsets turns the counts of a stream into
+// offsets, pass 1 writes first/last positions in order.
+#define AMB_RUN_CHUNK 4096
+__global__ void __launch_bounds__(256) k_runs_pass(AmbStreamGeom g, const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info,
+                                                    const AmbStreamState* __restrict__ states, const int* __restrict__ todo, int n_todo,
+                                                    int64_t tile_lo, int64_t tile_hi, int chunks, int* __restrict__ chunk_count, int pass, AmbLinkBufs L) {
+    const int w = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    if (w >= n_todo) return;
+    const int s = todo ? todo[w] : w;
+    if (!states[s].meta_received) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int wsum[8];
-    __shared__ int base;
-    if (tid == 0) base = 0;
-    __syncthreads();
-    if (!states[s].meta_received) { if (tid == 0) L.n_runs[s] = 0; return; }
     const int32_t* ts = tile_slot + (int64_t)s * g.sum_stride;
-    AmbRun* runs = L.runs + (int64_t)s * L.run_cap;
-    const int PER = 16;
-    for (int64_t c0 = tile_lo; c0 < tile_hi; c0 += 256 * PER) {
-        const int64_t t0 = c0 + (int64_t)tid * PER;
-        int starts = 0;
-        bool prev = (t0 > tile_lo && t0 - 1 < tile_hi) ? tile_is_cand(ts, slot_info, t0 - 1) : false;
-        unsigned cmask = 0;
-        for (int i = 0; i < PER; i++) {
-            const int64_t t = t0 + i;
-            const bool c = t < tile_hi && tile_is_cand(ts, slot_info, t);
-            if (c) cmask |= 1u << i;
-            if (c && !prev) starts++;
-            prev = c;
-        }
-        // exclusive prefix of `starts` over the block
-        int v = starts;
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (lane == 31) wsum[warp] = v;
-        __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < warp; w++) woff += wsum[w];
-        int idx = base + woff + v - starts;      // index of this thread's first run start
-        // a run that continues from the previous thread's tiles has index idx - 1
-        prev = (t0 > tile_lo && t0 - 1 < tile_hi) ? tile_is_cand(ts, slot_info, t0 - 1) : false;
-        for (int i = 0; i < PER; i++) {
-            const int64_t t = t0 + i;
-            if (t >= tile_hi) break;
-            const bool c = (cmask >> i) & 1u;
-            const int64_t first = g.base_g + (t << 8) - 511;
-            if (c && !prev) { if (idx < L.run_cap) runs[idx].first_pos = first; idx++; }
-            if (c) {
-                const bool nxt = (t + 1 < tile_hi) && tile_is_cand(ts, slot_info, t + 1);
-                if (!nxt && idx - 1 < L.run_cap && idx >= 1) runs[idx - 1].last_pos = first + 255;
-            }
-            prev = c;
-        }
-        __syncthreads();
-        if (tid == 255) base = base + woff + v;
-        __syncthreads();
+    const int PER = AMB_RUN_CHUNK / 256;
+    const int64_t t0 = tile_lo + (int64_t)chunk * AMB_RUN_CHUNK + (int64_t)tid * PER;
+    int starts = 0;
+    const bool prev0 = (t0 > tile_lo && t0 - 1 < tile_hi) ? tile_is_cand(ts, slot_info, t0 - 1) : false;
+    bool prev = prev0;
+    unsigned cmask = 0;
+    for (int i = 0; i < PER; i++) {
+        const int64_t t = t0 + i;
+        const bool c = t < tile_hi && tile_is_cand(ts, slot_info, t);
+        if (c) cmask |= 1u << i;
+        if (c && !prev) starts++;
+        prev = c;
     }
-    if (tid == 0) L.n_runs[s] = base < L.run_cap ? base : L.run_cap;
+    int v = starts;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int k = 0; k < 8; k++) { if (k < warp) woff += wsum[k]; tot += wsum[k]; }
+    if (pass == 0) { if (tid == 0) chunk_count[(int64_t)s * chunks + chunk] = tot; return; }
+    AmbRun* runs = L.runs + (int64_t)s * L.run_cap;
+    int idx = chunk_count[(int64_t)s * chunks + chunk] + woff + v - starts;    // after k_runs_offsets: exclusive offset of the chunk
+    prev = prev0;
+    for (int i = 0; i < PER; i++) {
+        const int64_t t = t0 + i;
+        if (t >= tile_hi) break;
+        const bool c = (cmask >> i) & 1u;
+        const int64_t first = g.base_g + (t << 8) - 511;
+        if (c && !prev) { if (idx < L.run_cap) runs[idx].first_pos = first; idx++; }
+        if (c) {
+            const bool nxt = (t + 1 < tile_hi) && tile_is_cand(ts, slot_info, t + 1);
+            if (!nxt && idx >= 1 && idx - 1 < L.run_cap) runs[idx - 1].last_pos = first + 255;
+        }
+        prev = c;
+    }
+}
+
+// per stream: exclusive prefix of its chunk counts (in place) and the run total (one warp per stream)
+__global__ void __launch_bounds__(128) k_runs_offsets(const AmbStreamState* __restrict__ states, const int* __restrict__ todo, int n_todo, int chunks,
+                                                       int* __restrict__ chunk_count, AmbLinkBufs L) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + warp;
+    if (w >= n_todo) return;
+    const int s = todo ? todo[w] : w;
+    if (!states[s].meta_received) return;
+    int* cc = chunk_count + (int64_t)s * chunks;
+    int carry = 0;
+    for (int base = 0; base < chunks; base += 32) {
+        const int i = base + lane;
+        const int c = i < chunks ? cc[i] : 0;
+        int v = c;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        if (i < chunks) cc[i] = carry + v - c;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) L.n_runs[s] = carry < L.run_cap ? carry : L.run_cap;
 }
 
 __device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n_streams, int f, int extra_per_stream) {
