@@ -252,7 +252,6 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     if (cudaMemcpy(m->d_tables, &m->tables, sizeof(AmbTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
     if (cudaMemcpy(m->d_ema, &e, sizeof(e), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
-    cudaFuncSetAttribute(k_scan_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
     *out = m;
@@ -643,7 +642,12 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
     CK(cudaMemsetAsync(m->tile_slot.p, 0xFF, (size_t)ns * m->sum_stride * 4, m->stream));      // history tiles: no slot (-1)
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
-    LAUNCH("k_scan_sums", k_scan_sums<<<ns * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(), m->sum_stride, ss));
+    {
+        const int64_t n_warps = (int64_t)ns * tiles;
+        LAUNCH("k_scan_fast", k_scan_fast<<<blocks_for(n_warps, 8), 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(),
+                                                                                        m->sum_stride, ss, n_warps));
+        LAUNCH("k_tri_store", k_tri_store<<<m->slot_cap, 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
+    }
     LAUNCH("k_defect_prefix", k_defect_prefix<<<ns, 256, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_new / AMB_TILE, ns));
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;

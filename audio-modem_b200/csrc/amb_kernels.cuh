@@ -158,90 +158,164 @@ __device__ __forceinline__ void block_prefix(const float* c, double* ST, double*
 // Streaming summary scan.  cleaned: arena [n_streams][stride]; tile t of the push covers window-end samples
 // [off0 + 4096 t, +4096) in arena coordinates; g0 = global sample index of arena index off0.
 // sums: [n_streams][sum_stride][5]; summary tile index of arena sample a is a >> 8.
-// Besides the summaries, tiles that may matter to the walker are written out in full: a tile with a window whose
-// metric exceeds 0.25 (energy gate relaxed by 10 %) gets a slot in the triple store (float64 P, Ra, Rb of its 256
-// windows), so the walker never recomputes them; the slot also records whether any window passes the exact
-// candidate test (metric > 0.5 with the 0.001 gate), which is what the cross-correlation screening kernel runs on.
-// The block-boundary defect terms of the call this tile completes (amb_walker.cuh) are written per call.
+//
+// One WARP per 4096-sample call tile, everything in registers.  The warp streams over 18 blocks of 256 samples (block
+// m = local samples 256m+1 .. 256m+256, local index 0 = arena a0-512; the +1 makes block m exactly the window starts of
+// summary tile m).  Lane l owns 8 consecutive samples of each block; per block it forms the exclusive prefix of x^2 and of
+// x[i]*x[i+256] (8 local adds + one warp shuffle scan each), and the window starting at (m, r) is then
+//   Ra = (totQ_m - preQ_m[r]) + preQ_{m+1}[r],  Rb = (totQ_{m+1} - preQ_{m+1}[r]) + preQ_{m+2}[r],  P likewise from T,
+// all from the lane's own registers.  This pass is float32 SCREENING: the summaries are widened by a bound on its
+// rounding error so that amb_tile_hot stays conservative, and tiles that might matter get a slot; k_tri_store then writes
+// the exact float64 sums of those tiles only.
 struct AmbScanStore {
     int32_t* tile_slot;      // [n_streams][sum_stride]
     double* tri;             // [slot_cap][256][3]
-    int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate, unused
+    int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate (k_tri_store), unused
     int* slot_count;
     int slot_cap;
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
 
-__global__ void __launch_bounds__(256) k_scan_sums(const float* __restrict__ cleaned, int64_t stride, int64_t off0, int64_t g0, int per,
-                                                    float* __restrict__ sums, int64_t sum_stride, AmbScanStore st) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* c = reinterpret_cast<float*>(smem_raw);
-    double* ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
-    double* SQ = ST + (AMB_SPAN + 1);
-    double* tot_t = SQ + (AMB_SPAN + 1);
-    double* tot_q = tot_t + 256;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    AMB_SPLIT_BID(per, s, tile)
-    const int64_t a0 = off0 + (int64_t)tile * AMB_TILE;         // arena index of the tile's first window-end sample
-    const float* src = cleaned + (int64_t)s * stride;
-    for (int i = tid; i < AMB_SPAN; i += 256) {
-        const int64_t a = a0 - AMB_HALO + i;
-        c[i] = a >= 0 ? src[a] : 0.0f;
+__device__ __forceinline__ void scan_load_block(const float* __restrict__ row, int64_t a_base, int64_t limit, int m, int lane, float* x) {
+    // samples local 256m + 1 + 8*lane + k, k < 8: three aligned float4 loads, elements 1..8
+    const int64_t a = a_base + 256 * m + 8 * lane;
+    float e[12];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a + 4 * q + 3 < limit) v = __ldg(reinterpret_cast<const float4*>(row + a + 4 * q));
+        else { float t[4]; for (int j = 0; j < 4; j++) t[j] = (a + 4 * q + j < limit) ? row[a + 4 * q + j] : 0.f; v = make_float4(t[0], t[1], t[2], t[3]); }
+        e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
     }
-    __syncthreads();
-    block_prefix(c, ST, SQ, tot_t, tot_q);
-    __shared__ float red[8][5];
-    __shared__ int s_slot;
-    if (tid == 0 && st.defect) {
-        // defect of the boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
-        const double xm1 = c[0], x255 = c[256], x511 = c[512];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = e[k + 1];
+}
+
+// exclusive prefix (within the 256-sample block) of v[k] over lanes and k; returns the block total
+__device__ __forceinline__ float scan_block_prefix(const float* v, int lane, float* pre) {
+    float run = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { pre[k] = run; run += v[k]; }
+    float inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    const float base = inc - run;
+#pragma unroll
+    for (int k = 0; k < 8; k++) pre[k] += base;
+    return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+__global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cleaned, int64_t stride, int64_t off0, int64_t g0, int per,
+                                                    float* __restrict__ sums, int64_t sum_stride, AmbScanStore st, int64_t n_warps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= n_warps) return;
+    const int s = (int)(w / per), tile = (int)(w % per);
+    const int64_t a0 = off0 + (int64_t)tile * AMB_TILE;
+    const float* row = cleaned + (int64_t)s * stride;
+    const int64_t a_base = a0 - AMB_HALO;                      // arena index of local sample 0
+    if (lane == 0 && st.defect) {
+        // defect of the block boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
+        const double xm1 = row[a_base], x255 = row[a_base + 256], x511 = row[a_base + 512];
         double* D = st.defect + ((int64_t)s * st.calls_stride + (a0 >> 12)) * 3;
         D[0] = xm1 * x255 - x255 * x511; D[1] = xm1 * xm1 - x255 * x255; D[2] = x255 * x255 - x511 * x511;
     }
-    for (int jj = 0; jj < AMB_TILE / 256; jj++) {
-        const int dl = jj * 256 + 1 + tid;                             // window start, local index
-        const int64_t d_global = g0 + (int64_t)tile * AMB_TILE - AMB_HALO + dl;
+    float X0[8], X1[8], X2[8], PQ0[8], PQ1[8], PQ2[8], PT0[8], PT1[8], v[8];
+    float TQ0, TQ1, TQ2, TT0, TT1;
+    scan_load_block(row, a_base, stride, 0, lane, X0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = X0[k] * X0[k];
+    TQ0 = scan_block_prefix(v, lane, PQ0);
+    scan_load_block(row, a_base, stride, 1, lane, X1);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = X1[k] * X1[k];
+    TQ1 = scan_block_prefix(v, lane, PQ1);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = X0[k] * X1[k];
+    TT0 = scan_block_prefix(v, lane, PT0);
+    for (int m = 0; m < AMB_TILE / 256; m++) {
+        scan_load_block(row, a_base, stride, m + 2, lane, X2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = X2[k] * X2[k];
+        TQ2 = scan_block_prefix(v, lane, PQ2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = X1[k] * X2[k];
+        TT1 = scan_block_prefix(v, lane, PT1);
+        // windows (m, r = 8*lane + k): local start 256m + 1 + r
+        const float err = 4e-7f * (TQ0 + TQ1 + TQ2) + 1e-12f;
         float ap = 0.f, mnA = 3.0e38f, mxA = 0.f, mnB = 3.0e38f, mxB = 0.f;
-        double P = 0.0, A = 0.0, B = 0.0;
-        int hot = 0, cand = 0;
-        if (d_global >= 0) {
-            P = ST[dl + 256] - ST[dl]; A = SQ[dl + 256] - SQ[dl]; B = SQ[dl + 512] - SQ[dl + 256];
-            ap = (float)fabs(P); mnA = mxA = (float)A; mnB = mxB = (float)B;
-            hot = A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
-            cand = A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
-        }
-        if (st.tile_slot) {
-            const int any_hot = __syncthreads_or(hot), any_cand = __syncthreads_or(cand);
-            if (tid == 0) {
-                int slot = -1;
-                if (any_hot) {
-                    slot = atomicAdd(st.slot_count, 1);
-                    if (slot >= st.slot_cap) slot = -1;
-                    else { st.slot_info[slot * 4] = s; st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + jj); st.slot_info[slot * 4 + 2] = any_cand; st.slot_info[slot * 4 + 3] = 0; }
-                }
-                s_slot = slot;
-                st.tile_slot[(int64_t)s * sum_stride + ((a0 >> 8) + jj)] = slot;
-            }
-            __syncthreads();
-            if (s_slot >= 0) {
-                double* o = st.tri + ((int64_t)s_slot * 256 + tid) * 3;
-                o[0] = P; o[1] = A; o[2] = B;
-            }
+        int hot = 0;
+        const int64_t d0 = g0 + (int64_t)tile * AMB_TILE - AMB_HALO + 256 * m + 1 + 8 * lane;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (d0 + k < 0) continue;
+            const float A = (TQ0 - PQ0[k]) + PQ1[k], B = (TQ1 - PQ1[k]) + PQ2[k], P = (TT0 - PT0[k]) + PT1[k];
+            ap = fmaxf(ap, fabsf(P)); mnA = fminf(mnA, A); mxA = fmaxf(mxA, A); mnB = fminf(mnB, B); mxB = fmaxf(mxB, B);
+            const float Pa = fabsf(P) + err;
+            hot |= (A + err > 0.0009f) && (B + err > 0.0009f) && Pa * Pa > 0.25f * fmaxf(A - err, 0.0009f) * fmaxf(B - err, 0.0009f);
         }
         ap = warp_maxf(ap); mnA = warp_minf(mnA); mxA = warp_maxf(mxA); mnB = warp_minf(mnB); mxB = warp_maxf(mxB);
-        if (lane == 0) { red[warp][0] = ap; red[warp][1] = mnA; red[warp][2] = mxA; red[warp][3] = mnB; red[warp][4] = mxB; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 8; w++) {
-                ap = fmaxf(ap, red[w][0]); mnA = fminf(mnA, red[w][1]); mxA = fmaxf(mxA, red[w][2]);
-                mnB = fminf(mnB, red[w][3]); mxB = fmaxf(mxB, red[w][4]);
+        const int any_hot = __any_sync(0xffffffffu, hot);
+        if (lane == 0) {
+            const int64_t tix = (int64_t)s * sum_stride + ((a0 >> 8) + m);
+            float* o = sums + tix * AMB_SUM_W;
+            // widened by the screening error so that the walker's cold test stays conservative
+            o[0] = ap + err; o[1] = fmaxf(mnA - err, 0.f); o[2] = mxA + err; o[3] = fmaxf(mnB - err, 0.f); o[4] = mxB + err;
+            if (st.tile_slot && any_hot) {
+                int slot = atomicAdd(st.slot_count, 1);
+                if (slot >= st.slot_cap) slot = -1;
+                else { st.slot_info[slot * 4] = s; st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + m); st.slot_info[slot * 4 + 2] = 0; st.slot_info[slot * 4 + 3] = 0; }
+                st.tile_slot[tix] = slot;
             }
-            float* o = sums + ((int64_t)s * sum_stride + ((a0 >> 8) + jj)) * AMB_SUM_W;
-            o[0] = ap; o[1] = mnA; o[2] = mxA; o[3] = mnB; o[4] = mxB;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { X0[k] = X1[k]; X1[k] = X2[k]; PQ0[k] = PQ1[k]; PQ1[k] = PQ2[k]; PT0[k] = PT1[k]; }
+        TQ0 = TQ1; TQ1 = TQ2; TT0 = TT1;
+    }
+}
+
+// Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
+// (metric > 0.5 with the 0.001 energy gate, no defect).  One CTA per slot: 768 samples, float64 prefix sums.
+__global__ void __launch_bounds__(256) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
+    const int slot = blockIdx.x;
+    if (slot >= min(*st.slot_count, st.slot_cap)) return;
+    __shared__ float c[768];
+    __shared__ double ST[513], SQ[769], tt[256], tq[256];
+    const int tid = threadIdx.x;
+    const int s = st.slot_info[slot * 4], tile = st.slot_info[slot * 4 + 1];
+    const int64_t a_first = ((int64_t)tile << 8) - 511;                 // arena index of the tile's first window
+    const float* row = cleaned + (int64_t)s * stride;
+    const int64_t a_hi = avail_hi - base_g;
+    for (int i = tid; i < 768; i += 256) { const int64_t a = a_first + i; c[i] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
+    __syncthreads();
+    double lt = 0.0, lq = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const int i = 3 * tid + k;
+        const double x = c[i];
+        SQ[i] = lq; lq = fma(x, x, lq);
+        if (i < 512) { ST[i] = lt; lt = fma(x, (double)c[i + 256], lt); }
+    }
+    tt[tid] = lt; tq[tid] = lq;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        double a = 0.0, b = 0.0;
+        if (tid >= o) { a = tt[tid - o]; b = tq[tid - o]; }
+        __syncthreads();
+        if (tid >= o) { tt[tid] += a; tq[tid] += b; }
         __syncthreads();
     }
+    const double ot = tid ? tt[tid - 1] : 0.0, oq = tid ? tq[tid - 1] : 0.0;
+    for (int k = 0; k < 3; k++) { const int i = 3 * tid + k; SQ[i] += oq; if (i < 512) ST[i] += ot; }
+    if (tid == 255) { SQ[768] = tq[255]; ST[512] = tt[255]; }
+    __syncthreads();
+    const double P = ST[tid + 256] - ST[tid], A = SQ[tid + 256] - SQ[tid], B = SQ[tid + 512] - SQ[tid + 256];
+    const bool valid = base_g + a_first + tid >= 0;
+    double* o = st.tri + ((int64_t)slot * 256 + tid) * 3;
+    o[0] = valid ? P : 0.0; o[1] = valid ? A : 0.0; o[2] = valid ? B : 0.0;
+    const int cand = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+    const int any = __syncthreads_or(cand);
+    if (tid == 0) st.slot_info[slot * 4 + 2] = any;
 }
 
 // ================================================================================================
