@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,9 @@ struct amb_modem {
     AmbTables tables;
     AmbTables* d_tables = nullptr;
     AmbEmaTables* d_ema = nullptr;
+    AmbFastTables* d_fast = nullptr;
+    unsigned long long* d_fallbacks = nullptr;
+    bool fast_demod = true;
     std::string err;
     int64_t launches = 0;
     // optional per-kernel device timing (CUDA events on the handle's stream)
@@ -154,12 +158,17 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     const AmbTables& T = m->tables;
     const int64_t idx_stride = (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data;
     CK(m->idx.ensure((size_t)n_jobs * idx_stride));
-    if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));
     o.idx = m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
     const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
-    LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
+    if (m->fast_demod) {
+        // float32 symbol pipeline with margin guard and float64-faithful fallback; computes the per-frame peak itself
+        LAUNCH("k_demod_fast", k_demod_fast<<<dim3(n_jobs, groups), 256, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+    } else {
+        if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
+        LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
+    }
     LAUNCH("k_parse", k_parse<<<blocks_for(n_jobs, 4), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
                                                           d_res, d_bytes, bytes_stride));
     return AMB_OK;
@@ -251,6 +260,18 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     e.a16 = (double)powl(a, 16.0L); e.alpha = m->tables.dc_alpha; e.beta = m->tables.dc_beta;
     if (cudaMemcpy(m->d_tables, &m->tables, sizeof(AmbTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
     if (cudaMemcpy(m->d_ema, &e, sizeof(e), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
+    {
+        AmbFastTables ft;
+        for (int k = 0; k < 256; k++) {
+            ft.tw256[k] = make_float2((float)std::cos(-2.0 * M_PI * k / 256.0), (float)std::sin(-2.0 * M_PI * k / 256.0));
+            ft.tw512[k] = make_float2((float)std::cos(-2.0 * M_PI * k / 512.0), (float)std::sin(-2.0 * M_PI * k / 512.0));
+        }
+        if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 8) != cudaSuccess) return bail(AMB_E_NOMEM);
+        if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
+        const char* e = std::getenv("AMB_FAST_DEMOD");
+        m->fast_demod = !(e && e[0] == '0');
+    }
+    cudaFuncSetAttribute(k_demod_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
@@ -273,6 +294,8 @@ void amb_destroy(amb_modem* m) {
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
     if (m->d_ema) cudaFree(m->d_ema);
+    if (m->d_fast) cudaFree(m->d_fast);
+    if (m->d_fallbacks) cudaFree(m->d_fallbacks);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -281,6 +304,20 @@ const char* amb_last_error(const amb_modem* m) { return m ? m->err.c_str() : "nu
 int amb_synchronize(amb_modem* m) { if (!m) return AMB_E_INVALID; CK(cudaStreamSynchronize(m->stream)); return AMB_OK; }
 void* amb_cuda_stream(amb_modem* m) { return m ? (void*)m->stream : nullptr; }
 int64_t amb_kernel_launches(const amb_modem* m) { return m ? m->launches : 0; }
+
+int64_t amb_debug_counter(amb_modem* m, int which) {
+    if (!m) return -1;
+    if (which == 0) return m->launches;
+    if (which == 1) {
+        unsigned long long v = 0;
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpy(&v, m->d_fallbacks, 8, cudaMemcpyDeviceToHost);
+        return (int64_t)v;
+    }
+    if (which == 2) return m->link_iterations;
+    if (which == 3) return m->link_passes;
+    return -1;
+}
 
 int amb_profile(amb_modem* m, int enable) {
     if (!m) return AMB_E_INVALID;

@@ -475,6 +475,198 @@ __global__ void __launch_bounds__(256) k_demod(const AmbTables* __restrict__ T, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast demodulation: float32 symbol pipeline with a margin guard, float64-faithful fallback per symbol.
+//
+// The channel estimate is always the float64-faithful one (one transform per frame).  From it the CTA derives the
+// float32 equaliser G = conj(H)/|H|^2 and 1/|H| per bin.  Each data symbol is then transformed in float32 (real 512-pt
+// = complex 256-pt Stockham radix-4 + split), equalised, phase-corrected and sliced.  Every sliced coordinate must be
+// at least tol away from its decision boundaries, where tol bounds the float32 pipeline's deviation from the float64
+// one:  tol_k = 1e-3 + 8e-5 * S / |H_k| * (1 + |eq_k| * pilot term),  S = sum |x_n| >= |Y_k|  (float32 transform error is
+// ~5e-7 S, so this is > 20x pessimistic).  If any subcarrier of the symbol fails the guard (or a pilot sits near the
+// 1e-6 test of modem.js:400) the whole symbol is redone by the float64-faithful routine, so the emitted indices are
+// the reference's in every case.  Clean 16-QAM frames at 25 dB never trip the guard; garbage symbols usually do.
+// ------------------------------------------------------------------------------------------------
+struct AmbFastTables { float2 tw256[256]; float2 tw512[256]; };     // exp(-2 pi i k / 256), exp(-2 pi i k / 512)
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 256-point complex forward transform, Stockham autosort radix-4, one warp, two float2[256] buffers; result in `a`
+__device__ __forceinline__ void fft256_stockham(float2* a, float2* b, const float2* __restrict__ tw256, int lane) {
+    float2* src = a;
+    float2* dst = b;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int Ns = 1 << (2 * t);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int j = lane + 32 * h;
+            const int k = j & (Ns - 1);
+            float2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
+            if (t > 0) {
+                const int step = 64 / Ns;                      // angle = -2 pi k / (4 Ns) = index k * (256 / (4 Ns))
+                v1 = cmulf(v1, tw256[k * step]); v2 = cmulf(v2, tw256[2 * k * step]); v3 = cmulf(v3, tw256[3 * k * step]);
+            }
+            const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+            const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+            const float2 t3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));       // (v1 - v3) * (-i)
+            const int j0 = ((j - k) << 2) + k;
+            dst[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+            dst[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+            dst[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+            dst[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+        }
+        __syncwarp();
+        float2* tmp = src; src = dst; dst = tmp;
+    }
+}
+
+#define AMB_FAST_WARP_BYTES (2 * AMB_FFT * 8)                       // the faithful fallback needs re[512] + im[512] doubles
+#define AMB_DEMOD_FAST_SMEM (AMB_DEMOD_WARPS * AMB_FAST_WARP_BYTES + 4 * AMB_FFT * 8 + AMB_DEMOD_WARPS * 2 * AMB_MAX_PILOTS * 8 +                              2 * 256 * 8 + AMB_FFT * 8 + AMB_FFT * 4 + 64)
+
+__global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
+                                                     int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* p = smem_raw;
+    unsigned char* work = p; p += AMB_DEMOD_WARPS * AMB_FAST_WARP_BYTES;
+    double* tw_re = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
+    double* tw_im = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
+    double* h_re = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
+    double* h_im = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
+    double* qs = reinterpret_cast<double*>(p); p += AMB_DEMOD_WARPS * 2 * AMB_MAX_PILOTS * 8;
+    float2* tw256 = reinterpret_cast<float2*>(p); p += 256 * 8;
+    float2* tw512 = reinterpret_cast<float2*>(p); p += 256 * 8;
+    float2* G = reinterpret_cast<float2*>(p); p += AMB_FFT * 8;
+    float* invH = reinterpret_cast<float*>(p); p += AMB_FFT * 4;
+    __shared__ float s_mx;
+    __shared__ float red[8];
+    const int j = blockIdx.x;
+    if (j >= n_jobs) return;
+    AmbJob J = jobs[j];
+    if (J.status != 0) return;
+    const int g0 = blockIdx.y * AMB_SYM_GROUP;
+    if (g0 >= J.nsym) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < AMB_FFT; i += 256) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+    for (int i = tid; i < 256; i += 256) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
+    // per-frame peak (app.js:918-925), fused here instead of a separate pass
+    if (J.xf.kind == AMB_XF_SCALE) {
+        float mx = 0.f;
+        for (int64_t i = tid; i < J.len; i += 256) {
+            const int64_t g = J.pos + i;
+            const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
+            mx = fmaxf(mx, fabsf(v));
+        }
+        mx = warp_maxf(mx);
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        if (tid == 0) { for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]); s_mx = mx; if (blockIdx.y == 0) jobs[j].xf.mx = mx; }
+        __syncthreads();
+        J.xf.mx = s_mx;
+    }
+    __syncthreads();
+    AmbSig sig;
+    sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
+    double* re = reinterpret_cast<double*>(work + warp * AMB_FAST_WARP_BYTES);
+    double* im = re + AMB_FFT;
+    if (warp == 0) {
+        amb_fft512_load(sig, J.ce_pos + T->cp_len, re, im);
+        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+        amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
+    }
+    __syncthreads();
+    for (int k = T->sub_start + tid; k <= T->sub_end; k += 256) {
+        const double hr = h_re[k], hi = h_im[k], hm = hr * hr + hi * hi;
+        if (hm > 1e-10) { G[k] = make_float2((float)(hr / hm), (float)(-hi / hm)); invH[k] = (float)(1.0 / sqrt(hm)); }
+        else { G[k] = make_float2(1.f, 0.f); invH[k] = -1.f; }                      // modem.js:392-394: bin left unequalised; always re-checked exactly
+    }
+    __syncthreads();
+    float2* za = reinterpret_cast<float2*>(re);
+    float2* zb = za + 256;
+    const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
+    unsigned long long my_fallbacks = 0;
+    for (int sidx = g0 + warp; sidx < s_end; sidx += AMB_DEMOD_WARPS) {
+        const int64_t p0 = J.data_pos + (int64_t)sidx * T->sym_len + T->cp_len;
+        // load: z[n] = x[2n] + i x[2n+1], with the frame transform; S = sum |x|
+        float S = 0.f;
+        bool bad = false;
+        for (int n = lane; n < 256; n += 32) {
+            float a = amb_sig(sig, p0 + 2 * n), b = amb_sig(sig, p0 + 2 * n + 1);
+            if (a != a) a = 0.f;
+            if (b != b) b = 0.f;
+            S += fabsf(a) + fabsf(b);
+            za[n] = make_float2(a, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        __syncwarp();
+        fft256_stockham(za, zb, tw256, lane);
+        // split into the real signal's spectrum on the used bins, equalise
+        const int nb = T->sub_end - T->sub_start + 1;
+        float2* E = zb;                                    // equalised bins, indexed k - sub_start (zb is free after the transform)
+        for (int kk = lane; kk < nb; kk += 32) {
+            const int k = T->sub_start + kk;
+            const float2 zk = za[k], zn = za[256 - k];
+            const float2 ze = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+            const float2 zo = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));      // (Z[k] - conj(Z[N-k])) / (2i)
+            const float2 y = make_float2(ze.x + tw512[k].x * zo.x - tw512[k].y * zo.y, ze.y + tw512[k].x * zo.y + tw512[k].y * zo.x);
+            E[kk] = cmulf(y, G[k]);
+        }
+        __syncwarp();
+        // pilot phase (modem.js:398-405)
+        float ph_sum = 0.f, ptol = 0.f;
+        int pc = 0;
+        for (int q = 0; q < T->n_pilots; q++) {
+            const int k = T->pilots[q];
+            if (k < T->sub_start || k > T->sub_end) continue;
+            const float2 e = E[k - T->sub_start];
+            const float ih = invH[k];
+            const float dk = ih < 0.f ? 1e30f : 8e-5f * S * ih;           // bound on |e - exact|
+            const float ar = fabsf(e.x);
+            if (fabsf(ar - 1e-6f) <= dk) bad = true;                       // the |eqRe| > 1e-6 test could flip
+            if (ar > 1e-6f) {
+                ph_sum += e.y / e.x; pc++;
+                ptol += dk * (1.f + fabsf(e.y) / ar) / ar;                 // d(eqIm/eqRe)
+            }
+        }
+        const float phase = pc > 0 ? ph_sum / (float)pc : 0.f;
+        const float dphase = pc > 0 ? ptol / (float)pc + 1e-6f * fabsf(phase) : 0.f;
+        uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * T->n_data;
+        const float thr = (float)T->qam_thr;
+        for (int di = lane; di < T->n_data; di += 32) {
+            const int k = T->data_k[di];
+            const float2 e = E[k - T->sub_start];
+            const float ih = invH[k];
+            const float cr = e.x + e.y * phase, ci = e.y - e.x * phase;
+            const float mag = fabsf(e.x) + fabsf(e.y);
+            const float tol = 1e-3f + (ih < 0.f ? 1e30f : 8e-5f * S * ih * (1.f + fabsf(phase))) + mag * dphase + 1e-5f * mag;
+            int idx;
+            float margin;
+            if (T->mod == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
+            else if (T->mod == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
+            else {
+                const float ar = fabsf(cr), ai = fabsf(ci);
+                const int gc = cr < 0.f ? (ar > thr ? 0 : 1) : (ar > thr ? 3 : 2);
+                const int gr = ci < 0.f ? (ai > thr ? 0 : 1) : (ai > thr ? 3 : 2);
+                idx = (((gr ^ (gr >> 1))) << 2) | (gc ^ (gc >> 1));
+                margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
+            }
+            if (!(margin > tol)) bad = true;                               // also catches NaN
+            idx_out[di] = (uint8_t)idx;
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            // float64-faithful symbol (bit-identical to the reference arithmetic)
+            __syncwarp();
+            amb_fft512_load(sig, p0, re, im);
+            amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+            amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, idx_out, nullptr, nullptr);
+            if (lane == 0) my_fallbacks++;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && my_fallbacks && fallback_count) atomicAdd(fallback_count, my_fallbacks);
+}
+
 __global__ void __launch_bounds__(128) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride, amb_frame_result* __restrict__ results,
                                                 uint8_t* __restrict__ bytes_out, int64_t bytes_stride) {

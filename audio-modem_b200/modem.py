@@ -125,6 +125,10 @@ class Modem:
     def kernel_launches(self):
         return int(self._L.amb_kernel_launches(self._h))
 
+    def debug_counter(self, which):
+        """0 launches, 1 fast-demod fallback symbols, 2 link iterations, 3 link passes"""
+        return int(self._L.amb_debug_counter(self._h, which))
+
     def profile(self, enable=True):
         """bracket every kernel launch with CUDA events on the handle's stream (device time per kernel)"""
         self._ck(self._L.amb_profile(self._h, int(enable)))

@@ -125,6 +125,9 @@ int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by t
 /* per-kernel device time: amb_profile(m, 1) brackets every kernel launch with CUDA events on the handle's stream;
  * amb_profile_read returns, per kernel name (names = [cap][32] chars), the summed milliseconds and launch count since
  * the last read, and clears them */
+/* development counters: 0 kernel launches, 1 data symbols redone by the float64-faithful fallback of the fast
+ * demodulator, 2 link-resolution iterations, 3 link-resolution passes */
+int64_t amb_debug_counter(amb_modem* m, int which);
 int amb_profile(amb_modem* m, int enable);
 int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n);
 
