@@ -169,7 +169,7 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
     }
-    LAUNCH("k_parse", k_parse<<<blocks_for(n_jobs, 4), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
+    LAUNCH("k_parse", k_parse<<<n_jobs < 65536 ? n_jobs : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
                                                           d_res, d_bytes, bytes_stride));
     return AMB_OK;
 }
@@ -319,6 +319,15 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
     return -1;
 }
 
+int amb_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return AMB_E_INVALID;
+    *out = nullptr;
+    if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return AMB_E_NOMEM; }
+    return AMB_OK;
+}
+
+int amb_host_free(void* p) { if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return AMB_E_CUDA; } return AMB_OK; }
+
 int amb_profile(amb_modem* m, int enable) {
     if (!m) return AMB_E_INVALID;
     CK(cudaStreamSynchronize(m->stream));
@@ -384,7 +393,7 @@ int amb_crc32(amb_modem* m, const uint8_t* data, int64_t stride, const int64_t* 
     if ((rc = in_ptr(m, data, (size_t)n * stride, mem, m->in_a, &d_data))) return rc;
     if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
     if ((rc = out_ptr(m, out, (size_t)n, mem, m->out_a, &d_out))) return rc;
-    LAUNCH("k_crc32", k_crc32<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out));
+    LAUNCH("k_crc32", k_crc32<<<n < 65536 ? n : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out));
     return flush(m);
 }
 

@@ -241,23 +241,39 @@ AMB_HD int64_t amb_num_bytes(int64_t n_elems, int bps, int rep) {
     return voted / 8;
 }
 
+// decoded byte j (majority vote + MSB-first packing); rep == 1 reads whole constellation indices
+AMB_HD uint8_t amb_pack_byte(const uint8_t* idx, int bps, int rep, int64_t j) {
+    if (rep == 1) {
+        if (bps == 4) return (uint8_t)((idx[2 * j] << 4) | (idx[2 * j + 1] & 15));
+        if (bps == 2) return (uint8_t)((idx[4 * j] << 6) | ((idx[4 * j + 1] & 3) << 4) | ((idx[4 * j + 2] & 3) << 2) | (idx[4 * j + 3] & 3));
+        int v = 0;
+        for (int t = 0; t < 8; t++) v = (v << 1) | (idx[8 * j + t] & 1);
+        return (uint8_t)v;
+    }
+    int v = 0;
+    if (bps == 1) {
+        // BPSK with repetition (the acoustic modes): raw bit b is idx[b]
+        for (int t = 0; t < 8; t++) {
+            const int64_t b0 = (j * 8 + t) * rep;
+            int sum = 0;
+            for (int r = 0; r < rep; r++) sum += idx[b0 + r] & 1;
+            v = (v << 1) | ((2 * sum >= rep) ? 1 : 0);
+        }
+        return (uint8_t)v;
+    }
+    for (int t = 0; t < 8; t++) {
+        const int64_t vb = j * 8 + t;
+        int sum = 0;
+        for (int r = 0; r < rep; r++) sum += amb_raw_bit(idx, bps, vb * rep + r);
+        v = (v << 1) | ((2 * sum >= rep) ? 1 : 0);
+    }
+    return (uint8_t)v;
+}
+
 AMB_HD void amb_pack_bytes(const uint8_t* idx, int64_t n_elems, int bps, int rep, uint8_t* bytes, int64_t cap) {
     int64_t nb = amb_num_bytes(n_elems, bps, rep);
     if (nb > cap) nb = cap;
-    AMB_WARP_FOR(j, nb) {
-        int v = 0;
-        for (int t = 0; t < 8; t++) {
-            const int64_t vb = (int64_t)j * 8 + t;
-            int bit;
-            if (rep > 1) {
-                int sum = 0;
-                for (int r = 0; r < rep; r++) sum += amb_raw_bit(idx, bps, vb * rep + r);
-                bit = (2 * sum >= rep) ? 1 : 0;
-            } else bit = amb_raw_bit(idx, bps, vb);
-            v = (v << 1) | bit;
-        }
-        bytes[j] = (uint8_t)v;
-    }
+    AMB_WARP_FOR(j, nb) bytes[j] = amb_pack_byte(idx, bps, rep, j);
     AMB_WARP_SYNC();
 }
 
@@ -265,6 +281,38 @@ AMB_HD uint32_t amb_crc32_bytes(const uint32_t* table, const uint8_t* data, int6
     uint32_t c = 0xFFFFFFFFu;
     for (int64_t i = 0; i < n; i++) c = table[(c ^ data[i]) & 0xFF] ^ (c >> 8);
     return c ^ 0xFFFFFFFFu;
+}
+
+// CRC-32 over a byte range split into chunks (parallel evaluation).  The reflected CRC register is a polynomial
+// over GF(2) with bit 31 = x^0; for the finalised values crc(A||B) = crc(A) * x^(8|B|) + crc(B) (mod P), so chunk
+// CRCs combine by a multiplication with a power of x.  Chunks are aligned to the END of the range (the first chunk
+// absorbs the remainder), so every right operand of the combining tree has the full length 2^level * L.
+AMB_HD uint32_t amb_gf_mul(uint32_t a, uint32_t b) {          // a * b mod P
+    uint32_t p = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & (0x80000000u >> i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+
+AMB_HD uint32_t amb_gf_xpow8(uint32_t n_bytes) {               // x^(8 n) mod P
+    uint32_t r = 0x80000000u, sq = 0x00800000u;                // 1, x^8
+    while (n_bytes) {
+        if (n_bytes & 1u) r = amb_gf_mul(r, sq);
+        sq = amb_gf_mul(sq, sq);
+        n_bytes >>= 1;
+    }
+    return r;
+}
+
+// chunk t of nt covers [lo, hi) of an n-byte range, chunk length L = ceil(n / nt), aligned to the end
+AMB_HD void amb_crc_chunk(int64_t n, int nt, int t, int64_t* lo, int64_t* hi) {
+    const int64_t L = (n + nt - 1) / nt;
+    int64_t h = n - (int64_t)(nt - 1 - t) * L, l = h - L;
+    if (h < 0) h = 0;
+    if (l < 0) l = 0;
+    *lo = l; *hi = h;
 }
 
 AMB_HD int32_t amb_be32(const uint8_t* b) {   // JS `(b0<<24)|(b1<<16)|(b2<<8)|b3` is a signed int32
@@ -278,7 +326,15 @@ AMB_HD void amb_result_clear(amb_frame_result* r) {
 }
 
 // parseMetadataResult, modem.js:805-828
-AMB_HD void amb_parse_meta(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r) {
+// The parsers take an optional `defer`: when non-NULL the CRC is left to the caller (a CTA-wide parallel CRC): *defer
+// receives the number of leading bytes the CRC covers (-1 if the parser failed before reaching it).
+AMB_HD void amb_finish_crc(const uint32_t* crc_table, const uint8_t* bytes, int64_t off, amb_frame_result* r, int64_t* defer) {
+    if (defer) { *defer = off; return; }
+    r->actual_crc = amb_crc32_bytes(crc_table, bytes, off);
+    r->crc_valid = r->expected_crc == r->actual_crc;
+}
+
+AMB_HD void amb_parse_meta(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r, int64_t* defer = nullptr) {
     r->frame_type = AMB_FRAME_META;
     if (n < 16) { r->status = AMB_ST_META_TOO_SHORT; r->frame_type = -1; return; }
     int64_t off = 1;
@@ -290,12 +346,11 @@ AMB_HD void amb_parse_meta(const uint32_t* crc_table, const uint8_t* bytes, int6
     r->name_len = name_len; r->name_off = (int32_t)off;
     off += name_len;
     r->expected_crc = (uint32_t)amb_be32(bytes + off);
-    r->actual_crc = amb_crc32_bytes(crc_table, bytes, off);
-    r->crc_valid = r->expected_crc == r->actual_crc;
+    amb_finish_crc(crc_table, bytes, off, r, defer);
 }
 
 // parseDataChunkResult, modem.js:830-849
-AMB_HD void amb_parse_chunk(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r) {
+AMB_HD void amb_parse_chunk(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r, int64_t* defer = nullptr) {
     r->frame_type = AMB_FRAME_DATA;
     if (n < 11) { r->status = AMB_ST_CHUNK_TOO_SHORT; r->frame_type = -1; return; }
     int64_t off = 1;
@@ -305,27 +360,28 @@ AMB_HD void amb_parse_chunk(const uint32_t* crc_table, const uint8_t* bytes, int
     r->data_len = data_len; r->data_off = (int32_t)off;
     off += data_len;
     r->expected_crc = (uint32_t)amb_be32(bytes + off);
-    r->actual_crc = amb_crc32_bytes(crc_table, bytes, off);
-    r->crc_valid = r->expected_crc == r->actual_crc;
+    amb_finish_crc(crc_table, bytes, off, r, defer);
 }
 
 // tail of decodeChunkFrame, modem.js:793-802
-AMB_HD void amb_parse_chunk_frame(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r) {
+AMB_HD void amb_parse_chunk_frame(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r, int64_t* defer = nullptr) {
     r->n_bytes = (int32_t)n;
+    if (defer) *defer = -1;
     if (n < 6) { r->status = AMB_ST_DECODED_TOO_SHORT; return; }
     const int ft = bytes[0];
-    if (ft == AMB_FRAME_META) amb_parse_meta(crc_table, bytes, n, r);
-    else if (ft == AMB_FRAME_DATA) amb_parse_chunk(crc_table, bytes, n, r);
+    if (ft == AMB_FRAME_META) amb_parse_meta(crc_table, bytes, n, r, defer);
+    else if (ft == AMB_FRAME_DATA) amb_parse_chunk(crc_table, bytes, n, r, defer);
     else { r->status = AMB_ST_UNKNOWN_FRAME_TYPE; r->err_arg = ft; r->frame_type = ft; }
 }
 
 // tail of decodeReceivedSignal, modem.js:607-653 (preamble_idx is filled by the caller)
-AMB_HD void amb_parse_received(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r) {
+AMB_HD void amb_parse_received(const uint32_t* crc_table, const uint8_t* bytes, int64_t n, amb_frame_result* r, int64_t* defer = nullptr) {
     r->n_bytes = (int32_t)n;
+    if (defer) *defer = -1;
     if (n < 10) { r->status = AMB_ST_DECODED_TOO_SHORT; return; }
     const int first = bytes[0];
-    if (first == AMB_FRAME_META) { amb_parse_meta(crc_table, bytes, n, r); return; }
-    if (first == AMB_FRAME_DATA) { amb_parse_chunk(crc_table, bytes, n, r); return; }
+    if (first == AMB_FRAME_META) { amb_parse_meta(crc_table, bytes, n, r, defer); return; }
+    if (first == AMB_FRAME_DATA) { amb_parse_chunk(crc_table, bytes, n, r, defer); return; }
     int64_t off = 0;
     const int name_len = bytes[off++];
     if (off + name_len + 4 + 4 > n) { r->status = AMB_ST_DECODED_TOO_SHORT_FOR_HEADER; return; }
@@ -337,8 +393,7 @@ AMB_HD void amb_parse_received(const uint32_t* crc_table, const uint8_t* bytes, 
     r->data_len = data_len; r->data_off = (int32_t)off;
     off += data_len;
     r->expected_crc = (uint32_t)amb_be32(bytes + off);
-    r->actual_crc = amb_crc32_bytes(crc_table, bytes, off);
-    r->crc_valid = r->expected_crc == r->actual_crc;
+    amb_finish_crc(crc_table, bytes, off, r, defer);
     r->frame_type = AMB_FRAME_LEGACY;
 }
 

@@ -667,35 +667,87 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
     if (lane == 0 && my_fallbacks && fallback_count) atomicAdd(fallback_count, my_fallbacks);
 }
 
-__global__ void __launch_bounds__(128) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
+// CTA-wide CRC-32 of data[0, n): every thread takes one end-aligned chunk (amb_crc_chunk), the chunk CRCs are combined
+// by a tree of GF(2) multiplications with x^(8 * chunk length * 2^level).  blockDim.x = AMB_CRC_THREADS; all threads
+// call; the result is returned to all.  tab: the 256-entry table in shared memory; sh: AMB_CRC_THREADS words.
+#define AMB_CRC_THREADS 128
+__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint8_t* data, int64_t n, uint32_t* sh) {
+    const int tid = threadIdx.x;
+    int64_t lo, hi;
+    amb_crc_chunk(n, AMB_CRC_THREADS, tid, &lo, &hi);
+    uint32_t c = 0;
+    if (hi > lo) {
+        c = 0xFFFFFFFFu;
+        for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
+        c ^= 0xFFFFFFFFu;
+    }
+    uint32_t op = amb_gf_xpow8((uint32_t)((n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS));
+    sh[tid] = c;
+    __syncthreads();
+    for (int span = 1; span < AMB_CRC_THREADS; span <<= 1) {
+        const bool act = (tid & (2 * span - 1)) == 0;
+        if (act) c = amb_gf_mul(c, op) ^ sh[tid + span];
+        op = amb_gf_mul(op, op);
+        __syncthreads();
+        if (act) sh[tid] = c;
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+// majorityVote + bitsToBytes + frame parser + crc32 (modem.js:487-495, :468-476, :793-849, :607-653): one CTA per frame.
+__global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride, amb_frame_result* __restrict__ results,
                                                 uint8_t* __restrict__ bytes_out, int64_t bytes_stride) {
-    const int warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * 4 + warp;
-    if (j >= n_jobs) return;
-    const AmbJob J = jobs[j];
-    amb_frame_result r;
-    amb_result_clear(&r);
-    r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
-    if (J.status != 0) {
-        r.status = J.status;
-        if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
-        if ((threadIdx.x & 31) == 0) results[j] = r;
-        return;
-    }
-    uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
-    const int64_t n_elems = (int64_t)J.nsym * T->n_data;
-    const int64_t nb_full = amb_num_bytes(n_elems, T->bps, T->rep);
-    amb_pack_bytes(idx + (int64_t)j * idx_stride, n_elems, T->bps, T->rep, bytes, bytes_stride);
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t sh[AMB_CRC_THREADS];
+    __shared__ amb_frame_result sr;
+    __shared__ long long s_crc_len;
+    const int tid = threadIdx.x;
+    for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
+        const AmbJob J = jobs[j];
+        if (J.status != 0) {
+            if (tid == 0) {
+                amb_frame_result r;
+                amb_result_clear(&r);
+                r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
+                r.status = J.status;
+                if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
+                results[j] = r;
+            }
+            continue;
+        }
+        for (int i = tid; i < 256; i += AMB_CRC_THREADS) tab[i] = T->crc_table[i];
+        uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
+        const uint8_t* ix = idx + (int64_t)j * idx_stride;
+        const int64_t n_elems = (int64_t)J.nsym * T->n_data;
+        const int64_t nb_full = amb_num_bytes(n_elems, T->bps, T->rep);
         const int64_t nb = nb_full < bytes_stride ? nb_full : bytes_stride;
-        if (J.mode == 0) amb_parse_chunk_frame(T->crc_table, bytes, nb, &r);
-        else amb_parse_received(T->crc_table, bytes, nb, &r);
-        r.n_bytes = (int32_t)nb_full;
-        // decodeReceivedSignal attaches preambleIdx to chunk-type results even when their parser failed (modem.js:611-619)
-        const bool chunk_type = nb >= 10 && (bytes[0] == AMB_FRAME_META || bytes[0] == AMB_FRAME_DATA);
-        if (J.mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = J.result_pos;
-        results[j] = r;
+        const int bps = T->bps, rep = T->rep;
+        for (int64_t b = tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = amb_pack_byte(ix, bps, rep, b);
+        __syncthreads();
+        if (tid == 0) {
+            amb_frame_result r;
+            amb_result_clear(&r);
+            r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
+            int64_t crc_len = -1;
+            if (J.mode == 0) amb_parse_chunk_frame(tab, bytes, nb, &r, &crc_len);
+            else amb_parse_received(tab, bytes, nb, &r, &crc_len);
+            r.n_bytes = (int32_t)nb_full;
+            // decodeReceivedSignal attaches preambleIdx to chunk-type results even when their parser failed (modem.js:611-619)
+            const bool chunk_type = nb >= 10 && (bytes[0] == AMB_FRAME_META || bytes[0] == AMB_FRAME_DATA);
+            if (J.mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = J.result_pos;
+            sr = r;
+            s_crc_len = crc_len;
+        }
+        __syncthreads();
+        const int64_t crc_len = s_crc_len;
+        if (crc_len >= 0) {
+            const uint32_t c = block_crc32(tab, bytes, crc_len, sh);
+            if (tid == 0) { sr.actual_crc = c; sr.crc_valid = sr.expected_crc == c; }
+        }
+        if (tid == 0) results[j] = sr;
+        __syncthreads();
     }
 }
 
@@ -979,12 +1031,18 @@ __global__ void __launch_bounds__(128) k_xcorr_pick(const AmbTables* __restrict_
     if (lane == 0) { idx_out[r] = res; best_out[r] = res_best; }
 }
 
-// crc32 of n byte rows, one thread per row (modem.js:453-457)
-__global__ void k_crc32(const AmbTables* __restrict__ T, const uint8_t* __restrict__ data, int64_t stride, const int64_t* __restrict__ lens,
-                        int64_t n_default, int n, uint32_t* __restrict__ out) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    out[r] = amb_crc32_bytes(T->crc_table, data + (int64_t)r * stride, lens ? lens[r] : n_default);
+// crc32 of n byte rows, one CTA per row (modem.js:453-457)
+__global__ void __launch_bounds__(AMB_CRC_THREADS) k_crc32(const AmbTables* __restrict__ T, const uint8_t* __restrict__ data, int64_t stride,
+                                                          const int64_t* __restrict__ lens, int64_t n_default, int n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t sh[AMB_CRC_THREADS];
+    for (int i = threadIdx.x; i < 256; i += AMB_CRC_THREADS) tab[i] = T->crc_table[i];
+    __syncthreads();
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const uint32_t c = block_crc32(tab, data + (int64_t)r * stride, lens ? lens[r] : n_default, sh);
+        if (threadIdx.x == 0) out[r] = c;
+        __syncthreads();
+    }
 }
 
 // Job setup for decodeChunkFrame rows (modem.js:770-789)

@@ -30,6 +30,37 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from amb_host_alloc (freed by .free() or with the object)"""
+
+    def __init__(self, shape, dtype):
+        self._L = _lib.load()
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        if self._L.amb_host_alloc(C.byref(p), n) != 0:
+            raise AmbError(f"amb_host_alloc({n}) failed")
+        self.ptr, self.nbytes = p.value, n
+        self.array = np.frombuffer((C.c_uint8 * max(n, 1)).from_address(self.ptr), dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._L.amb_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """page-locked host array (keeps its owner alive through `.base` chains: hold on to the returned PinnedArray)"""
+    return PinnedArray(shape, dtype)
+
+
 def _status_message(status, arg):
     s = _lib.load().amb_status_string(status).decode()
     return s.replace("{arg:x}", format(arg & 0xFFFFFFFF if arg < 0 else arg, "x")).replace("{arg}", str(arg))
@@ -107,6 +138,11 @@ class Modem:
 
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_stream_open", False):
+                try:
+                    self.stream_close()
+                except Exception:
+                    pass
             self._L.amb_destroy(self._h)
             self._h = None
 
@@ -287,13 +323,19 @@ class Modem:
         self.bytes_stride = self.decoded_capacity(int(self._L.amb_estimate_frame_samples(CFG[self.config], MOD[self.modName], max_chunk + 16, self.repetition)))
         min_frame = int(self._L.amb_estimate_frame_samples(CFG[self.config], MOD[self.modName], 11, self.repetition))
         self.max_results = max_results or n_streams * (max_push // min_frame + 3)
-        self._res = (FrameResult * self.max_results)()
-        self._dec = np.zeros((self.max_results, self.bytes_stride), dtype=np.uint8)
+        # results and decoded bytes land in page-locked memory (full-rate, asynchronous device->host copies)
+        self._res_pin = PinnedArray((self.max_results * C.sizeof(FrameResult),), np.uint8)
+        self._dec_pin = PinnedArray((self.max_results, self.bytes_stride), np.uint8)
+        self._res = (FrameResult * self.max_results).from_address(self._res_pin.ptr)
+        self._dec = self._dec_pin.array
 
     def stream_close(self):
         if self._stream_open:
             self._ck(self._L.amb_stream_close(self._h))
             self._stream_open = False
+            self._res = self._dec = None
+            self._res_pin.free()
+            self._dec_pin.free()
 
     def stream_input_window(self):
         p = C.c_void_p()
@@ -301,8 +343,10 @@ class Modem:
         self._ck(self._L.amb_stream_input_window(self._h, C.byref(p), C.byref(s)))
         return p.value, s.value
 
-    def stream_push(self, x=None, n_new=None, raw=False, collect=True):
-        """x: [n_streams][n_new] float32 (numpy = host, torch.cuda tensor = device, None = already written in place)."""
+    def stream_push(self, x=None, n_new=None, raw=False, collect=True, device_results=None):
+        """x: [n_streams][n_new] float32 (numpy = host, torch.cuda tensor = device, None = already written in place).
+        device_results: optional (results, bytes) torch.cuda uint8 tensors ([max_results * sizeof(amb_frame_result)] and
+        [max_results][bytes_stride]) that receive the frames on the device instead of the host buffers; returns the count."""
         if not self._stream_open:
             raise AmbError("stream not open")
         if x is None:
@@ -316,6 +360,14 @@ class Modem:
                 x = x[None, :]
             mem, ptr, xs, n_new = MEM_HOST, _ptr(x), x.shape[1], x.shape[1]
         n = C.c_int(0)
+        if device_results is not None:
+            dres, dbytes = device_results
+            assert dres.is_cuda and dbytes.is_cuda and dbytes.stride(0) == self.bytes_stride
+            cap = min(dres.numel() // C.sizeof(FrameResult), dbytes.shape[0])
+            rc = self._L.amb_stream_push(self._h, ptr, xs, n_new, mem, _ptr(dres), cap, C.byref(n), _ptr(dbytes), self.bytes_stride, MEM_DEVICE)
+            self._ck(rc, allow_overflow=True)
+            self.last_push_frames = n.value
+            return n.value
         rc = self._L.amb_stream_push(self._h, ptr, xs, n_new, mem, C.cast(self._res, C.c_void_p), self.max_results, C.byref(n),
                                      _ptr(self._dec), self.bytes_stride, MEM_HOST)
         self._ck(rc, allow_overflow=True)

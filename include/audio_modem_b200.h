@@ -131,6 +131,12 @@ int64_t amb_debug_counter(amb_modem* m, int which);
 int amb_profile(amb_modem* m, int enable);
 int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n);
 
+/* page-locked host memory for caller buffers (samples in, results and decoded bytes out): copies to and from it run
+ * at full PCIe rate and asynchronously; the N-API addon wraps it in external ArrayBuffers.  Plain malloc'd memory is
+ * accepted everywhere too (the driver then stages it). */
+int amb_host_alloc(void** out, uint64_t bytes);
+int amb_host_free(void* p);
+
 /* ---- pure host helpers (no device work) -------------------------------- */
 /* estimateFrameSamples, modem.js:863-874 */
 int64_t amb_estimate_frame_samples(int config, int constellation, int64_t payload_bytes, int repetition);

@@ -58,6 +58,24 @@ extern "C" {
 
 int emu_result_size(void) { return (int)sizeof(amb_frame_result); }
 
+// the chunked CRC-32 of block_crc32 (amb_kernels.cuh), threads run one after the other
+uint32_t emu_crc32_chunked(const uint8_t* data, int64_t n, int nt) {
+    AmbTables T;
+    amb_tables_build(&T, 0, 1, 1);
+    std::vector<uint32_t> c((size_t)nt, 0);
+    for (int t = 0; t < nt; t++) {
+        int64_t lo, hi;
+        amb_crc_chunk(n, nt, t, &lo, &hi);
+        if (hi > lo) c[t] = amb_crc32_bytes(T.crc_table, data + lo, hi - lo);
+    }
+    uint32_t op = amb_gf_xpow8((uint32_t)((n + nt - 1) / nt));
+    for (int span = 1; span < nt; span <<= 1) {
+        for (int t = 0; t + span < nt; t += 2 * span) c[t] = amb_gf_mul(c[t], op) ^ c[t + span];
+        op = amb_gf_mul(op, op);
+    }
+    return c[0];
+}
+
 // decodeChunkFrame through the device logic
 int emu_decode_chunk_frame(int cfg, int mod, int rep, const float* x, int64_t n, amb_frame_result* res, uint8_t* bytes, int64_t cap) {
     AmbTables T;

@@ -137,3 +137,19 @@ def test_counter_noise_matches_oracle_mirror(O, emu):
     assert np.allclose(x, z.astype(np.float32), rtol=1e-6, atol=1e-7)
     big = O.addAwgnCtr(np.zeros(200000, np.float32), 1.0, 5)
     assert abs(float(big.mean())) < 0.01 and abs(float(big.std()) - 1.0) < 0.01
+
+
+def test_chunked_crc32_matches_zlib(emu):
+    """the end-aligned chunking + GF(2) combining tree used by the CTA-wide CRC-32 (k_parse, k_crc32)"""
+    import ctypes as C
+    import zlib
+
+    emu.emu_crc32_chunked.restype = C.c_uint32
+    emu.emu_crc32_chunked.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+    rng = np.random.default_rng(12)
+    for n in [0, 1, 2, 3, 9, 127, 128, 129, 255, 256, 1000, 4103, 4107, 32777, 70001]:
+        d = rng.integers(0, 256, max(n, 1), dtype=np.uint8)
+        for nt in (1, 2, 32, 128):
+            assert emu.emu_crc32_chunked(d.ctypes.data, n, nt) == zlib.crc32(d[:n].tobytes()), (n, nt)
+    d = np.frombuffer(b"123456789", np.uint8).copy()
+    assert emu.emu_crc32_chunked(d.ctypes.data, 9, 128) == 0xCBF43926
