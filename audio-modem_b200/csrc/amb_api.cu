@@ -163,7 +163,9 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     o.idx = m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
     const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
     if (m->fast_demod) {
-        // float32 symbol pipeline with margin guard and float64-faithful fallback; computes the per-frame peak itself
+        // float32 symbol pipeline with margin guard and float64-faithful fallback; gathers the per-frame peak itself when one
+        // CTA covers the whole frame
+        if (frame_max && groups > 1) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod_fast", k_demod_fast<<<dim3(n_jobs, groups), 256, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }

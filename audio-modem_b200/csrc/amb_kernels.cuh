@@ -478,191 +478,317 @@ __global__ void __launch_bounds__(256) k_demod(const AmbTables* __restrict__ T, 
 // ------------------------------------------------------------------------------------------------
 // Fast demodulation: float32 symbol pipeline with a margin guard, float64-faithful fallback per symbol.
 //
-// The channel estimate is always the float64-faithful one (one transform per frame).  From it the CTA derives the
-// float32 equaliser G = conj(H)/|H|^2 and 1/|H| per bin.  Each data symbol is then transformed in float32 (real 512-pt
-// = complex 256-pt Stockham radix-4 + split), equalised, phase-corrected and sliced.  Every sliced coordinate must be
-// at least tol away from its decision boundaries, where tol bounds the float32 pipeline's deviation from the float64
-// one:  tol_k = 1e-3 + 8e-5 * S / |H_k| * (1 + |eq_k| * pilot term),  S = sum |x_n| >= |Y_k|  (float32 transform error is
-// ~5e-7 S, so this is > 20x pessimistic).  If any subcarrier of the symbol fails the guard (or a pilot sits near the
-// 1e-6 test of modem.js:400) the whole symbol is redone by the float64-faithful routine, so the emitted indices are
-// the reference's in every case.  Clean 16-QAM frames at 25 dB never trip the guard; garbage symbols usually do.
+// Phase 1 (all symbols, float32, raw samples).  One HALF-WARP per symbol, 16 complex points per lane in registers:
+// the real 512-point transform is a complex 256-point one (z[n] = x[2n] + i x[2n+1]) done as two radix-16 passes with
+// one padded shared-memory transpose in between, then the split into the real signal's spectrum on the used bins.
+// The channel comes from the CE symbol by the same float32 transform; the per-frame peak normalisation (app.js:918-925)
+// cancels in Y/H, so raw samples are used and each sample is read from HBM once (the peak itself is gathered on the
+// way, for the fallback and for the |H|^2 > 1e-10 guard of modem.js:389, which is checked at the end of the frame).
+// Every sliced coordinate must clear its decision boundaries by tol, a bound on the deviation of this pipeline
+// from the float64 one:  |dY_k| <= 8e-5 S (S = sum |x_n| of the symbol; float32 transform error is ~1e-6 S, so this
+// is > 50x pessimistic), the same for the CE symbol, propagated through the equaliser, the pilot phase
+// (modem.js:398-405) and the de-rotation.  A symbol that fails the guard (or whose pilots sit near the 1e-6 test of
+// modem.js:400) is flagged.
+// Phase 2 (flagged symbols only): the float64-faithful channel estimate and symbol routine (amb_device.cuh), so the
+// emitted indices are the reference's in every case.  Clean 16-QAM frames at 25 dB never reach phase 2; garbage does.
 // ------------------------------------------------------------------------------------------------
 struct AmbFastTables { float2 tw256[256]; float2 tw512[256]; };     // exp(-2 pi i k / 256), exp(-2 pi i k / 512)
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// 256-point complex forward transform, Stockham autosort radix-4, one warp, two float2[256] buffers; result in `a`
-__device__ __forceinline__ void fft256_stockham(float2* a, float2* b, const float2* __restrict__ tw256, int lane) {
-    float2* src = a;
-    float2* dst = b;
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int Ns = 1 << (2 * t);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int j = lane + 32 * h;
-            const int k = j & (Ns - 1);
-            float2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
-            if (t > 0) {
-                const int step = 64 / Ns;                      // angle = -2 pi k / (4 Ns) = index k * (256 / (4 Ns))
-                v1 = cmulf(v1, tw256[k * step]); v2 = cmulf(v2, tw256[2 * k * step]); v3 = cmulf(v3, tw256[3 * k * step]);
-            }
-            const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-            const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-            const float2 t3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));       // (v1 - v3) * (-i)
-            const int j0 = ((j - k) << 2) + k;
-            dst[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-            dst[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
-            dst[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
-            dst[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
-        }
-        __syncwarp();
-        float2* tmp = src; src = dst; dst = tmp;
-    }
+// forward 4-point transform, outputs in natural order
+__device__ __forceinline__ void fft4f(float2& a, float2& b, float2& c, float2& d) {
+    const float2 t0 = caddf(a, c), t1 = csubf(a, c), t2 = caddf(b, d);
+    const float2 t3 = make_float2(b.y - d.y, -(b.x - d.x));        // (b - d) * (-i)
+    a = caddf(t0, t2); b = caddf(t1, t3); c = csubf(t0, t2); d = csubf(t1, t3);
 }
 
-#define AMB_FAST_WARP_BYTES (2 * AMB_FFT * 8)                       // the faithful fallback needs re[512] + im[512] doubles
-#define AMB_DEMOD_FAST_SMEM (AMB_DEMOD_WARPS * AMB_FAST_WARP_BYTES + 4 * AMB_FFT * 8 + AMB_DEMOD_WARPS * 2 * AMB_MAX_PILOTS * 8 +                              2 * 256 * 8 + AMB_FFT * 8 + AMB_FFT * 4 + 64)
+// forward 16-point transform in registers.  Output bin k ends up in v[4 * (k & 3) + (k >> 2)]  (AMB_R16(k)).
+#define AMB_R16(k) (4 * ((k) & 3) + ((k) >> 2))
+__device__ __forceinline__ void fft16f(float2* v) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+#pragma unroll
+    for (int b = 0; b < 4; b++) fft4f(v[b], v[4 + b], v[8 + b], v[12 + b]);     // over a (n = 4a + b): v[4c + b] = t[b][c]
+    // t[b][c] *= W16^(b c),  W16^m = exp(-2 pi i m / 16)
+    v[4 * 1 + 1] = cmulf(v[4 * 1 + 1], make_float2(C1, -S1));     // m = 1
+    v[4 * 1 + 2] = cmulf(v[4 * 1 + 2], make_float2(C2, -C2));     // m = 2
+    v[4 * 1 + 3] = cmulf(v[4 * 1 + 3], make_float2(S1, -C1));     // m = 3
+    v[4 * 2 + 1] = cmulf(v[4 * 2 + 1], make_float2(C2, -C2));     // m = 2
+    v[4 * 2 + 2] = make_float2(v[4 * 2 + 2].y, -v[4 * 2 + 2].x);  // m = 4: * (-i)
+    v[4 * 2 + 3] = cmulf(v[4 * 2 + 3], make_float2(-C2, -C2));    // m = 6
+    v[4 * 3 + 1] = cmulf(v[4 * 3 + 1], make_float2(S1, -C1));     // m = 3
+    v[4 * 3 + 2] = cmulf(v[4 * 3 + 2], make_float2(-C2, -C2));    // m = 6
+    v[4 * 3 + 3] = cmulf(v[4 * 3 + 3], make_float2(-C1, S1));     // m = 9
+#pragma unroll
+    for (int c = 0; c < 4; c++) fft4f(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);   // over b: v[4c + d] = X[c + 4d]
+}
+
+#define AMB_FD_HW 16                                    // half-warps (symbols in flight) per CTA
+#define AMB_FD_TSTRIDE 17                               // padded row of the 16x16 transpose
+#define AMB_FD_HWBUF (16 * AMB_FD_TSTRIDE)              // float2 per half-warp
+#define AMB_FD_MAXBINS 224
+#define AMB_FD_ITERS (AMB_FD_MAXBINS / 16)              // 14
+#define AMB_FD_FB_WARPS 4                               // warps that run the float64-faithful fallback
+#define AMB_FD_SMEM_FAST (AMB_FD_HW * AMB_FD_HWBUF * 8 + 2 * 256 * 8 + AMB_FD_MAXBINS * (8 + 4 + 4 + 4))
+#define AMB_FD_SMEM_FB (4 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS * 8)
+#define AMB_DEMOD_FAST_SMEM ((AMB_FD_SMEM_FAST > AMB_FD_SMEM_FB ? AMB_FD_SMEM_FAST : AMB_FD_SMEM_FB) + 64)
+
+// complex 256-point spectrum of the 512 real samples starting at global position p0 (raw values, NaN -> 0), by the
+// 16 lanes of a half-warp (l = lane & 15).  On return buf[k], k < 256, holds Z[k]; *S_out = sum |x| (half-warp total);
+// returns this lane's max |x|.  `inside`: the whole symbol lies in [lo, hi).
+__device__ __forceinline__ float fd_spectrum(const AmbJob& J, int64_t p0, bool inside, int l, float2* buf, const float2* __restrict__ tw256,
+                                             float* S_out) {
+    float2 v[16];
+    float S = 0.f, mx = 0.f;
+    if (inside) {
+        const float* src = J.p + (p0 - J.base) + 2 * l;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) { v[n1].x = src[32 * n1]; v[n1].y = src[32 * n1 + 1]; }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int64_t g = p0 + 2 * (16 * n1 + l);
+            v[n1].x = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
+            v[n1].y = (g + 1 >= J.lo && g + 1 < J.hi) ? J.p[g + 1 - J.base] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        if (v[n1].x != v[n1].x) v[n1].x = 0.f;                     // `x || 0` (modem.js:377, :425)
+        if (v[n1].y != v[n1].y) v[n1].y = 0.f;
+        const float ax = fabsf(v[n1].x), ay = fabsf(v[n1].y);
+        S += ax + ay; mx = fmaxf(mx, fmaxf(ax, ay));
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    *S_out = S;
+    // pass 1: lane n2 = l transforms z[16 n1 + n2] over n1, scales by W256^(n2 k1), stores row k1
+    fft16f(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) {
+        float2 a = v[AMB_R16(k1)];
+        if (k1 > 0) a = cmulf(a, tw256[(l * k1) & 255]);
+        buf[k1 * AMB_FD_TSTRIDE + l] = a;
+    }
+    __syncwarp();
+    // pass 2: lane k1 = l transforms row k1 over n2: Z[k1 + 16 k2]
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = buf[l * AMB_FD_TSTRIDE + n2];
+    __syncwarp();
+    fft16f(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) buf[l + 16 * k2] = v[AMB_R16(k2)];
+    __syncwarp();
+    return mx;
+}
+
+// bin k of the real signal's spectrum from the packed transform (k in 1..255)
+__device__ __forceinline__ float2 fd_split(const float2* buf, const float2* __restrict__ tw512, int k) {
+    const float2 zk = buf[k], zn = buf[256 - k], w = tw512[k];
+    const float2 ze = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+    const float2 zo = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));      // (Z[k] - conj(Z[256-k])) / (2i)
+    return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
+}
 
 __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
                                                      int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* p = smem_raw;
-    unsigned char* work = p; p += AMB_DEMOD_WARPS * AMB_FAST_WARP_BYTES;
-    double* tw_re = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
-    double* tw_im = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
-    double* h_re = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
-    double* h_im = reinterpret_cast<double*>(p); p += AMB_FFT * 8;
-    double* qs = reinterpret_cast<double*>(p); p += AMB_DEMOD_WARPS * 2 * AMB_MAX_PILOTS * 8;
-    float2* tw256 = reinterpret_cast<float2*>(p); p += 256 * 8;
-    float2* tw512 = reinterpret_cast<float2*>(p); p += 256 * 8;
-    float2* G = reinterpret_cast<float2*>(p); p += AMB_FFT * 8;
-    float* invH = reinterpret_cast<float*>(p); p += AMB_FFT * 4;
-    __shared__ float s_mx;
-    __shared__ float red[8];
+    // ---- fast layout
+    float2* hwbuf = reinterpret_cast<float2*>(smem_raw);                         // [16][AMB_FD_HWBUF]
+    float2* tw256 = hwbuf + AMB_FD_HW * AMB_FD_HWBUF;                            // [256]
+    float2* tw512 = tw256 + 256;                                                 // [256]
+    float2* Gq = tw512 + 256;                                                    // [bins] conj(H)/|H|^2 (raw scale)
+    float* invH = reinterpret_cast<float*>(Gq + AMB_FD_MAXBINS);                 // [bins] 1/|H|
+    float* dH = invH + AMB_FD_MAXBINS;                                           // [bins] bound on |dH|/|H|
+    int* role = reinterpret_cast<int*>(dH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 pilot
+    __shared__ float s_red[8];
+    __shared__ float s_mx, s_minhm;
+    __shared__ unsigned s_mask[2];
+    __shared__ int s_all;
     const int j = blockIdx.x;
     if (j >= n_jobs) return;
     AmbJob J = jobs[j];
     if (J.status != 0) return;
     const int g0 = blockIdx.y * AMB_SYM_GROUP;
     if (g0 >= J.nsym) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < AMB_FFT; i += 256) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, l = tid & 15;
+    const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data, mod = T->mod;
+    const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
     for (int i = tid; i < 256; i += 256) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
-    // per-frame peak (app.js:918-925), fused here instead of a separate pass
-    if (J.xf.kind == AMB_XF_SCALE) {
-        float mx = 0.f;
-        for (int64_t i = tid; i < J.len; i += 256) {
-            const int64_t g = J.pos + i;
-            const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
-            mx = fmaxf(mx, fabsf(v));
+    for (int kk = tid; kk < nb; kk += 256) role[kk] = -1;
+    if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
+    __syncthreads();
+    for (int di = tid; di < n_data; di += 256) role[T->data_k[di] - sub_start] = di;
+    float my_mx = 0.f;
+    // ---- channel from the CE symbol (warp 0: both half-warps transform it, the lower one keeps the result; the warp-wide
+    //      shuffles and barriers inside need all 32 lanes); the other warps gather the peak over preamble-1, preamble-2 and
+    //      the CE prefix
+    if (warp == 0) {
+        const int64_t p0 = J.ce_pos + cp;
+        const bool inside = p0 >= J.lo && p0 + AMB_FFT <= J.hi;
+        float S;
+        my_mx = fd_spectrum(J, p0, inside, l, hwbuf + hw * AMB_FD_HWBUF, tw256, &S);
+        float mn = 3.0e38f;
+        for (int kk = l; kk < nb; kk += 16) {
+            const int k = sub_start + kk;
+            const float2 y = fd_split(hwbuf + hw * AMB_FD_HWBUF, tw512, k);
+            const float xr = (float)T->known_re[k];
+            const float d = xr * xr;
+            float hr = 0.f, hi = 0.f;
+            if (d > 1e-10f) { hr = y.x * xr / d; hi = y.y * xr / d; }
+            const float hm = hr * hr + hi * hi;
+            mn = fminf(mn, hm);
+            const float ih = rsqrtf(hm);
+            if (hw == 0) {
+                Gq[kk] = make_float2(hr / hm, -hi / hm);
+                invH[kk] = ih;
+                dH[kk] = 8e-5f * S * ih;
+            }
         }
-        mx = warp_maxf(mx);
-        if (lane == 0) red[warp] = mx;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) s_minhm = mn;
+    } else if (folded) {
+        const int64_t a = J.pos, b = J.ce_pos + cp;                  // [frame start, CE body)
+        for (int64_t g = a + (tid - 32); g < b; g += 224) {
+            const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
+            my_mx = fmaxf(my_mx, fabsf(v));
+        }
+    }
+    __syncthreads();
+    // ---- data symbols
+    const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
+    float2* buf = hwbuf + hw * AMB_FD_HWBUF;
+    const float thr = (float)T->qam_thr;
+    for (int s0 = g0; s0 < s_end; s0 += AMB_FD_HW) {
+        const int sidx = s0 + hw;
+        const bool active = sidx < s_end;                               // uniform per half-warp
+        const int sx = active ? sidx : s_end - 1;
+        const int64_t p0 = J.data_pos + (int64_t)sx * sym + cp;
+        const bool inside = p0 - cp >= J.lo && p0 + AMB_FFT <= J.hi;
+        float S;
+        float smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
+        if (folded) {
+            for (int i = l; i < cp; i += 16) {                          // the cyclic prefix only counts for the peak
+                const int64_t g = p0 - cp + i;
+                const float v = (inside || (g >= J.lo && g < J.hi)) ? J.p[g - J.base] : 0.f;
+                smx = fmaxf(smx, fabsf(v));
+            }
+            if (active) my_mx = fmaxf(my_mx, smx);
+        }
+        // equalised bins of this lane: kk = l + 16 i
+        float2 E[AMB_FD_ITERS];
+        float ph_sum = 0.f, ptol = 0.f;
+        int pc = 0;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < AMB_FD_ITERS; i++) {
+            const int kk = l + 16 * i;
+            E[i] = make_float2(0.f, 0.f);
+            if (kk < nb) {
+                const float2 e = cmulf(fd_split(buf, tw512, sub_start + kk), Gq[kk]);
+                E[i] = e;
+                if (role[kk] < 0) {                                     // pilot (modem.js:398-405)
+                    const float dk = 8e-5f * S * invH[kk] + (fabsf(e.x) + fabsf(e.y)) * dH[kk];     // bound on |e - exact|
+                    const float ar = fabsf(e.x);
+                    if (!(fabsf(ar - 1e-6f) > dk)) bad = true;          // the |eqRe| > 1e-6 test could flip (also catches NaN)
+                    if (ar > 1e-6f) {
+                        ph_sum += e.y / e.x; pc++;
+                        ptol += dk * (1.f + fabsf(e.y) / ar) / ar;      // d(eqIm/eqRe)
+                    }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            ph_sum += __shfl_xor_sync(0xffffffffu, ph_sum, o);
+            ptol += __shfl_xor_sync(0xffffffffu, ptol, o);
+            pc += __shfl_xor_sync(0xffffffffu, pc, o);
+        }
+        const float phase = pc > 0 ? ph_sum / (float)pc : 0.f;
+        const float dphase = pc > 0 ? ptol / (float)pc + 2e-6f * fabsf(phase) : 0.f;
+        uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sx * n_data;
+#pragma unroll
+        for (int i = 0; i < AMB_FD_ITERS; i++) {
+            const int kk = l + 16 * i;
+            if (kk < nb && role[kk] >= 0) {
+                const float2 e = E[i];
+                const float cr = e.x + e.y * phase, ci = e.y - e.x * phase;
+                const float mag = fabsf(e.x) + fabsf(e.y);
+                const float tol = 1e-3f + (8e-5f * S * invH[kk] + mag * dH[kk]) * (1.f + fabsf(phase)) + mag * dphase + 1e-5f * mag;
+                int idx;
+                float margin;
+                if (mod == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
+                else if (mod == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
+                else {
+                    const float ar = fabsf(cr), ai = fabsf(ci);
+                    const int gc = cr < 0.f ? (ar > thr ? 0 : 1) : (ar > thr ? 3 : 2);
+                    const int gr = ci < 0.f ? (ai > thr ? 0 : 1) : (ai > thr ? 3 : 2);
+                    idx = (((gr ^ (gr >> 1))) << 2) | (gc ^ (gc >> 1));
+                    margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
+                }
+                if (!(margin > tol)) bad = true;                        // also catches NaN
+                if (active) idx_out[role[kk]] = (uint8_t)idx;
+            }
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, bad);
+        const bool hw_bad = ((bm >> (lane & 16)) & 0xffffu) != 0u;
+        if (active && hw_bad && l == 0) atomicOr(&s_mask[(sidx - g0) >> 5], 1u << ((sidx - g0) & 31));
+        __syncwarp();
+    }
+    // ---- frame peak, |H|^2 guard
+    if (folded) {
+        my_mx = warp_maxf(my_mx);
+        if (lane == 0) s_red[warp] = my_mx;
         __syncthreads();
-        if (tid == 0) { for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]); s_mx = mx; if (blockIdx.y == 0) jobs[j].xf.mx = mx; }
+        if (tid == 0) { float mx = s_red[0]; for (int w = 1; w < 8; w++) mx = fmaxf(mx, s_red[w]); s_mx = mx; jobs[j].xf.mx = mx; }
         __syncthreads();
         J.xf.mx = s_mx;
+    } else __syncthreads();
+    if (tid == 0) {
+        // modem.js:389 tests |H|^2 > 1e-10 on the normalised frame: H_norm = H_raw / scale
+        const float scale = (J.xf.kind == AMB_XF_SCALE && J.xf.mx > 1e-6f) ? J.xf.mx : 1.f;
+        if (!(s_minhm > 1.01e-10f * scale * scale)) s_all = 1;
     }
+    __syncthreads();
+    const int n_here = s_end - g0;
+    unsigned m0 = s_mask[0], m1 = s_mask[1];
+    if (s_all) { m0 = n_here >= 32 ? 0xffffffffu : ((1u << n_here) - 1u); m1 = n_here > 32 ? (n_here >= 64 ? 0xffffffffu : ((1u << (n_here - 32)) - 1u)) : 0u; }
+    if ((m0 | m1) == 0u) return;
+    // ---- phase 2: float64-faithful redo of the flagged symbols (shared memory re-laid out)
+    __syncthreads();
+    double* tw_re = reinterpret_cast<double*>(smem_raw);
+    double* tw_im = tw_re + AMB_FFT;
+    double* h_re = tw_im + AMB_FFT;
+    double* h_im = h_re + AMB_FFT;
+    double* work = h_im + AMB_FFT;                                       // [AMB_FD_FB_WARPS][2][512]
+    double* qs = work + AMB_FD_FB_WARPS * 2 * AMB_FFT;
+    for (int i = tid; i < AMB_FFT; i += 256) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
     __syncthreads();
     AmbSig sig;
     sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
-    double* re = reinterpret_cast<double*>(work + warp * AMB_FAST_WARP_BYTES);
+    double* re = work + (warp < AMB_FD_FB_WARPS ? warp : 0) * 2 * AMB_FFT;
     double* im = re + AMB_FFT;
     if (warp == 0) {
-        amb_fft512_load(sig, J.ce_pos + T->cp_len, re, im);
+        amb_fft512_load(sig, J.ce_pos + cp, re, im);
         amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
         amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
     }
     __syncthreads();
-    for (int k = T->sub_start + tid; k <= T->sub_end; k += 256) {
-        const double hr = h_re[k], hi = h_im[k], hm = hr * hr + hi * hi;
-        if (hm > 1e-10) { G[k] = make_float2((float)(hr / hm), (float)(-hi / hm)); invH[k] = (float)(1.0 / sqrt(hm)); }
-        else { G[k] = make_float2(1.f, 0.f); invH[k] = -1.f; }                      // modem.js:392-394: bin left unequalised; always re-checked exactly
-    }
-    __syncthreads();
-    float2* za = reinterpret_cast<float2*>(re);
-    float2* zb = za + 256;
-    const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
+    if (warp >= AMB_FD_FB_WARPS) return;
     unsigned long long my_fallbacks = 0;
-    for (int sidx = g0 + warp; sidx < s_end; sidx += AMB_DEMOD_WARPS) {
-        const int64_t p0 = J.data_pos + (int64_t)sidx * T->sym_len + T->cp_len;
-        // load: z[n] = x[2n] + i x[2n+1], with the frame transform; S = sum |x|
-        float S = 0.f;
-        bool bad = false;
-        for (int n = lane; n < 256; n += 32) {
-            float a = amb_sig(sig, p0 + 2 * n), b = amb_sig(sig, p0 + 2 * n + 1);
-            if (a != a) a = 0.f;
-            if (b != b) b = 0.f;
-            S += fabsf(a) + fabsf(b);
-            za[n] = make_float2(a, b);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
-        __syncwarp();
-        fft256_stockham(za, zb, tw256, lane);
-        // split into the real signal's spectrum on the used bins, equalise
-        const int nb = T->sub_end - T->sub_start + 1;
-        float2* E = zb;                                    // equalised bins, indexed k - sub_start (zb is free after the transform)
-        for (int kk = lane; kk < nb; kk += 32) {
-            const int k = T->sub_start + kk;
-            const float2 zk = za[k], zn = za[256 - k];
-            const float2 ze = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-            const float2 zo = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));      // (Z[k] - conj(Z[N-k])) / (2i)
-            const float2 y = make_float2(ze.x + tw512[k].x * zo.x - tw512[k].y * zo.y, ze.y + tw512[k].x * zo.y + tw512[k].y * zo.x);
-            E[kk] = cmulf(y, G[k]);
-        }
-        __syncwarp();
-        // pilot phase (modem.js:398-405)
-        float ph_sum = 0.f, ptol = 0.f;
-        int pc = 0;
-        for (int q = 0; q < T->n_pilots; q++) {
-            const int k = T->pilots[q];
-            if (k < T->sub_start || k > T->sub_end) continue;
-            const float2 e = E[k - T->sub_start];
-            const float ih = invH[k];
-            const float dk = ih < 0.f ? 1e30f : 8e-5f * S * ih;           // bound on |e - exact|
-            const float ar = fabsf(e.x);
-            if (fabsf(ar - 1e-6f) <= dk) bad = true;                       // the |eqRe| > 1e-6 test could flip
-            if (ar > 1e-6f) {
-                ph_sum += e.y / e.x; pc++;
-                ptol += dk * (1.f + fabsf(e.y) / ar) / ar;                 // d(eqIm/eqRe)
-            }
-        }
-        const float phase = pc > 0 ? ph_sum / (float)pc : 0.f;
-        const float dphase = pc > 0 ? ptol / (float)pc + 1e-6f * fabsf(phase) : 0.f;
-        uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * T->n_data;
-        const float thr = (float)T->qam_thr;
-        for (int di = lane; di < T->n_data; di += 32) {
-            const int k = T->data_k[di];
-            const float2 e = E[k - T->sub_start];
-            const float ih = invH[k];
-            const float cr = e.x + e.y * phase, ci = e.y - e.x * phase;
-            const float mag = fabsf(e.x) + fabsf(e.y);
-            const float tol = 1e-3f + (ih < 0.f ? 1e30f : 8e-5f * S * ih * (1.f + fabsf(phase))) + mag * dphase + 1e-5f * mag;
-            int idx;
-            float margin;
-            if (T->mod == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
-            else if (T->mod == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
-            else {
-                const float ar = fabsf(cr), ai = fabsf(ci);
-                const int gc = cr < 0.f ? (ar > thr ? 0 : 1) : (ar > thr ? 3 : 2);
-                const int gr = ci < 0.f ? (ai > thr ? 0 : 1) : (ai > thr ? 3 : 2);
-                idx = (((gr ^ (gr >> 1))) << 2) | (gc ^ (gc >> 1));
-                margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
-            }
-            if (!(margin > tol)) bad = true;                               // also catches NaN
-            idx_out[di] = (uint8_t)idx;
-        }
-        if (__any_sync(0xffffffffu, bad)) {
-            // float64-faithful symbol (bit-identical to the reference arithmetic)
-            __syncwarp();
-            amb_fft512_load(sig, p0, re, im);
-            amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
-            amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, idx_out, nullptr, nullptr);
-            if (lane == 0) my_fallbacks++;
-        }
-        __syncwarp();
+    int ord = 0;
+    for (int t = 0; t < n_here; t++) {
+        if (!(((t < 32 ? m0 : m1) >> (t & 31)) & 1u)) continue;
+        if ((ord++ % AMB_FD_FB_WARPS) != warp) continue;
+        const int sidx = g0 + t;
+        amb_fft512_load(sig, J.data_pos + (int64_t)sidx * sym + cp, re, im);
+        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+        amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * n_data, nullptr, nullptr);
+        my_fallbacks++;
     }
     if (lane == 0 && my_fallbacks && fallback_count) atomicAdd(fallback_count, my_fallbacks);
 }

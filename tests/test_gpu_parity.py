@@ -161,6 +161,34 @@ def test_decode_chunk_frames(O, modems, mode):
         assert objs[i] == O.decodeChunkFrame(cfg, f, mod, rep), (mode, i)
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+def test_fast_demodulator_carries_clean_frames(O, modems, mode):
+    """The float32 symbol pipeline must decide clean frames itself (its float64 fallback is for symbols near a decision
+    boundary): bit-exact results AND (almost) no fallback symbols at 25 dB; pure noise must still be bit-exact."""
+    cfg, mod, rep, chunk = MODES[mode]
+    m = modems(mode)
+    frames = []
+    for i in range(12):
+        f = O.buildDataChunkFrame(cfg, O.randomBytes(300 + i, chunk), i, mod, rep)[2205:]
+        p = O.power(f[: O.estimateFrameSamples(cfg, chunk + 11, mod, rep)])
+        # windows up to 11 samples early (inside the cyclic prefix): a phase ramp the channel estimate absorbs
+        frames.append(np.concatenate([np.zeros(i, np.float32), O.addAwgn(f, np.sqrt(p / 10 ** 2.5), 40 + i)]))
+    before = m.debug_counter(1)
+    got = m.decode_chunk_frames(frames, raw=True)
+    fallbacks = m.debug_counter(1) - before
+    n_sym = sum(len(f) // O.config(cfg)["SYMBOL_LEN"] - 3 for f in frames)
+    for i, f in enumerate(frames):
+        r1, b1 = O.decodeChunkFrame(cfg, f, mod, rep, raw=True)
+        assert results_equal(r1, b1, got[i][0], got[i][1], check_metrics=False) == [], (mode, i)
+    # the symbol after the frame (trailing silence + noise) is garbage and may fall back: one per frame
+    assert fallbacks <= len(frames) + max(2, n_sym // 50), (fallbacks, n_sym)
+    noise = [(np.random.default_rng(50 + i).standard_normal(30000) * 0.05).astype(np.float32) for i in range(4)]
+    got = m.decode_chunk_frames(noise, raw=True)
+    for i, f in enumerate(noise):
+        r1, b1 = O.decodeChunkFrame(cfg, f, mod, rep, raw=True)
+        assert results_equal(r1, b1, got[i][0], got[i][1], check_metrics=False) == [], (mode, i)
+
+
 def test_decode_received_signal_c1(O, amb):
     """BASELINE config 1: QPSK loopback of a 32 KB payload (392,418 samples, noise-free)."""
     data = bytes(O.randomBytes(1, 32768))
