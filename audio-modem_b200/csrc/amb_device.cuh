@@ -32,7 +32,41 @@ AMB_HD double amb_sub(double a, double b) { return __dsub_rn(a, b); }
 AMB_HD double amb_div(double a, double b) { return __ddiv_rn(a, b); }
 AMB_HD double amb_sqrt(double a) { return __dsqrt_rn(a); }
 AMB_HD float amb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+#define AMB_NLANES 32
+__device__ __forceinline__ double amb_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float amb_warp_maxf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double amb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int amb_warp_min_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ bool amb_warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+__device__ __forceinline__ unsigned amb_warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ unsigned amb_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+__device__ __forceinline__ int amb_popc(unsigned v) { return __popc(v); }
 #else
+#define AMB_NLANES 1
+AMB_HD double amb_warp_max(double v) { return v; }
+AMB_HD float amb_warp_maxf(float v) { return v; }
+AMB_HD double amb_warp_sum(double v) { return v; }
+AMB_HD int amb_warp_min_int(int v) { return v; }
+AMB_HD bool amb_warp_any(bool p) { return p; }
+AMB_HD unsigned amb_warp_ballot(bool p) { return p ? 1u : 0u; }
+AMB_HD unsigned amb_lanemask_lt() { return 0u; }
+AMB_HD int amb_popc(unsigned v) { return __builtin_popcount(v); }
 #define AMB_LANE() 0
 #define AMB_WARP_FOR(i, n) for (int i = 0; i < (int)(n); i++)
 #define AMB_WARP_SYNC() ((void)0)
@@ -404,6 +438,26 @@ AMB_HD void amb_parse_received(const uint32_t* crc_table, const uint8_t* bytes, 
 // (direct sum for the first, slide for the rest).
 // ------------------------------------------------------------------------------------------------
 AMB_HD void amb_window_sums(const AmbSig& s, int64_t d0, int cnt, double* P, double* A, double* B) {
+    if (cnt <= 8) {
+        // few offsets: the lanes share the direct sum of the first window, the leader slides
+        double p = 0, a = 0, b = 0;
+        AMB_WARP_FOR(m, AMB_HALF) {
+            const double x = (double)amb_sig(s, d0 + m), y = (double)amb_sig(s, d0 + m + AMB_HALF);
+            p = fma(x, y, p); a = fma(x, x, a); b = fma(y, y, b);
+        }
+        p = amb_warp_sum(p); a = amb_warp_sum(a); b = amb_warp_sum(b);
+        if (AMB_LEADER()) {
+            P[0] = p; A[0] = a; B[0] = b;
+            for (int t = 1; t < cnt; t++) {
+                const double out = (double)amb_sig(s, d0 + t - 1), mid = (double)amb_sig(s, d0 + t - 1 + AMB_HALF),
+                             in = (double)amb_sig(s, d0 + t - 1 + 2 * AMB_HALF);
+                p += mid * in - out * mid; a += mid * mid - out * out; b += in * in - mid * mid;
+                P[t] = p; A[t] = a; B[t] = b;
+            }
+        }
+        AMB_WARP_SYNC();
+        return;
+    }
     const int chunks = (cnt + 7) / 8;
     AMB_WARP_FOR(c, chunks) {
         const int i0 = c * 8;
@@ -429,10 +483,23 @@ AMB_HD void amb_window_sums(const AmbSig& s, int64_t d0, int cnt, double* P, dou
 // the 0.001 test (the reference skips such offsets).
 AMB_HD bool amb_xcorr_at(const AmbTables* T, const AmbSig& s, int64_t d, double* metric) {
     double corr = 0, se = 0;
-    for (int i = 0; i < T->sym_len; i++) {
-        const double v = (double)amb_sig(s, d + i);
-        corr = fma(v, (double)T->pre1[i], corr);   // the product is exact, so fma == mul then add
-        se = fma(v, v, se);
+    const int plen = T->sym_len;
+    if (s.xf.kind == AMB_XF_NONE && d >= s.lo && d + plen <= s.hi) {
+        // whole window readable as stored: no per-tap bounds test, loads can run ahead of the two sum chains
+        const float* p = s.p + (d - s.base);
+        const float* t = T->pre1;
+#pragma unroll 8
+        for (int i = 0; i < plen; i++) {
+            const double v = (double)p[i];
+            corr = fma(v, (double)t[i], corr);     // the product is exact, so fma == mul then add
+            se = fma(v, v, se);
+        }
+    } else {
+        for (int i = 0; i < plen; i++) {
+            const double v = (double)amb_sig(s, d + i);
+            corr = fma(v, (double)T->pre1[i], corr);
+            se = fma(v, v, se);
+        }
     }
     const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
     if (!(denom > 0.001)) { *metric = 0.0; return false; }

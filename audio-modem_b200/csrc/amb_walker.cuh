@@ -183,20 +183,30 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     const int slot = G.xc ? amb_tile_slot_of(G, j) : -1;
     const int64_t base = (j << 8) - 511 - T->fine_radius;
     if (slot < 0 || lo < base || hi >= base + G.xc_w || hi < lo) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
-    const float* v = G.xc + (int64_t)slot * G.xc_w;
+    const float* v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
+    const int n = (int)(hi - lo + 1);
     float mx = -3.0f;
     bool unsure = false;
-    for (int64_t d = lo; d <= hi; d++) {
-        const float x = v[d - base];
+    AMB_WARP_FOR(o, n) {
+        const float x = v[o];
         if (x == AMB_XC_UNSURE) unsure = true;
         else if (x != AMB_XC_FAIL && x > mx) mx = x;
     }
-    if (unsure) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    mx = amb_warp_maxf(mx);
+    if (amb_warp_any(unsure)) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
     if (mx < -2.5f) { *pos_out = p; return -INFINITY; }                 // no offset passes the denominator test
+    // offsets within 1e-3 of the screening maximum, in increasing order (ballot compaction)
     int cnt = 0;
-    for (int64_t d = lo; d <= hi && cnt <= 32; d++) {
-        const float x = v[d - base];
-        if (x != AMB_XC_FAIL && x >= mx - 1e-3f) { if (cnt < 32 && AMB_LEADER()) scratch[32 + cnt] = (double)d; cnt++; }
+    for (int o0 = 0; o0 < n && cnt <= 32; o0 += AMB_NLANES) {
+        const int o = o0 + AMB_LANE();
+        bool take = false;
+        if (o < n) { const float x = v[o]; take = x != AMB_XC_FAIL && x >= mx - 1e-3f; }
+        const unsigned bal = amb_warp_ballot(take);
+        if (take) {
+            const int at = cnt + amb_popc(bal & amb_lanemask_lt());
+            if (at < 32) scratch[32 + at] = (double)(lo + o);
+        }
+        cnt += amb_popc(bal);
     }
     AMB_WARP_SYNC();
     if (cnt > 32) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
@@ -211,6 +221,103 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     AMB_WARP_SYNC();
     *pos_out = bpos;
     return best;
+}
+
+// One evaluated batch of the candidate logic of _scanForPreamble (app.js:806-838): positions d .. d+cnt-1 with their
+// gates W->gate[] and metrics W->M[] (one look-ahead entry at index cnt when the batch does not end at scan_end);
+// running maximum (best, best_pos).  Returns true when the batch commits a preamble (state updated).
+//   reference, per position:  if gate && m > 0.5 && m > best: best = m          (here: must exceed best by 1e-12)
+//                             if best > 0.5 && gate[next] && M[next] < 0.7 best: commit
+// amb_scan_batch_serial is that loop as written.  amb_scan_batch reaches the same result from three reductions:
+// i0 = first candidate; (Bmax, amax) = maximum and its first position from i0 on (including the running best);
+// u = first position >= i0 whose successor metric is below 0.7 Bmax.  Before u no successor is below 0.7 best_i
+// (best_i <= Bmax), and at u the running best already equals Bmax when amax <= u, so the commit happens exactly at
+// u.  The cases this does not cover (near-ties within 1e-12 before the maximum, a maximum that comes after u) take
+// the serial loop.
+AMB_HD bool amb_scan_batch_serial(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
+    for (int i = 0; i < cnt; i++) {
+        const int64_t pos = d + i;
+        if (W->gate[i]) {
+            const double m = W->M[i];
+            if (m > 0.5 && m > best * (1.0 + 1e-12)) { best = m; best_pos = pos; }
+        }
+        const int nxt = pos < scan_end ? i + 1 : i;
+        if (best > 0.5 && best_pos >= 0 && W->gate[nxt] && W->M[nxt] < best * 0.7) {
+            amb_commit(st, best_pos, best, pos + 1, pos < scan_end ? 0 : 1);
+            return true;
+        }
+    }
+    return false;
+}
+
+AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos);
+
+AMB_HD bool amb_scan_batch(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
+#if defined(AMB_EMU_CHECK) && !defined(__CUDA_ARCH__)
+    // test build: the reduction form must agree with the serial loop on every batch
+    AmbStreamState s2 = st;
+    double b2 = best;
+    int64_t p2 = best_pos;
+    const bool r2 = amb_scan_batch_serial(s2, W, d, cnt, scan_end, b2, p2);
+    const bool r1 = amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos);
+    if (r1 != r2 || b2 != best || p2 != best_pos || s2.pre_pos != st.pre_pos || s2.coarse != st.coarse || s2.state != st.state ||
+        s2.ac_scan_pos != st.ac_scan_pos || s2.lag != st.lag) {
+        fprintf(stderr, "amb_scan_batch mismatch: d=%lld cnt=%d r=%d/%d best=%.17g/%.17g pos=%lld/%lld\n", (long long)d, cnt, (int)r1, (int)r2, best, b2,
+                (long long)best_pos, (long long)p2);
+        abort();
+    }
+    return r1;
+#else
+    return amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos);
+#endif
+}
+
+AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
+    const int NONE = 0x7fffffff;
+    const bool tracking = best > 0.5 && best_pos >= 0;
+    int i0 = 0;
+    if (!tracking) {
+        if (best > 0.5) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);      // not a state the walker produces
+        int loc = NONE;
+        AMB_WARP_FOR(i, cnt) if (loc == NONE && W->gate[i] && W->M[i] > 0.5) loc = i;
+        i0 = amb_warp_min_int(loc);
+        if (i0 == NONE) return false;                                  // no candidate: nothing can happen in this batch
+    }
+    // maximum from i0 on and its first position (-1: the running best)
+    double lmax = -1.0;
+    AMB_WARP_FOR(i, cnt) if (i >= i0 && W->gate[i] && W->M[i] > 0.5) lmax = fmax(lmax, W->M[i]);
+    double bmax = amb_warp_max(lmax);
+    int amax = NONE;
+    if (tracking && best >= bmax) { bmax = best; amax = -1; }
+    else {
+        int loc = NONE;
+        AMB_WARP_FOR(i, cnt) if (loc == NONE && i >= i0 && W->gate[i] && W->M[i] == bmax) loc = i;
+        amax = amb_warp_min_int(loc);
+    }
+    // near-ties below the maximum and before it: the 1e-12 rule may keep the earlier value -> serial
+    {
+        bool amb = tracking && amax >= 0 && best < bmax && best * (1.0 + 1e-12) >= bmax;
+        AMB_WARP_FOR(i, cnt) if (i >= i0 && i < amax && W->gate[i] && W->M[i] > 0.5 && W->M[i] < bmax && W->M[i] * (1.0 + 1e-12) >= bmax) amb = true;
+        if (amb_warp_any(amb)) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
+    }
+    // first position whose successor metric is below 0.7 Bmax
+    int loc = NONE;
+    const double thr = bmax * 0.7;
+    AMB_WARP_FOR(i, cnt) {
+        if (loc == NONE && i >= i0) {
+            const int nxt = d + i < scan_end ? i + 1 : i;
+            if (W->gate[nxt] && W->M[nxt] < thr) loc = i;
+        }
+    }
+    const int u = amb_warp_min_int(loc);
+    if (u == NONE) {
+        if (amax >= 0) { best = bmax; best_pos = d + amax; }
+        return false;
+    }
+    if (amax > u) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
+    if (amax >= 0) { best = bmax; best_pos = d + amax; }
+    amb_commit(st, best_pos, best, d + u + 1, d + u < scan_end ? 0 : 1);
+    return true;
 }
 
 // _scanForPreamble, app.js:775-847, for the call whose totalWritten is `tw`
@@ -232,10 +339,19 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
     int64_t d = st.ac_scan_pos;
 
     if (st.lag == 1) {
-        // first position of a call that continues an uninterrupted scan: sums still describe window d-1
-        amb_eval_windows(G, sig, d - 1, 3, W->P, W->A, W->B);
-        double m;
-        if (amb_metric(W->P[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
+        // first position of a call that continues an uninterrupted scan: sums still describe window d-1.  When the
+        // summary of that window's tile proves that no window in it passes the candidate test under the current defect,
+        // nothing but the defect update below can happen and the sums need not be evaluated.
+        bool cold = false;
+        {
+            const int64_t jj = (d - 1 + 511) >> 8, rel = jj - (G.sum_base >> 8);
+            if (d - 1 >= 0 && rel >= 0 && rel < G.sum_tiles && (jj << 8) >= G.sum_lo) cold = !amb_tile_hot(sums + rel * AMB_SUM_W, st.Ep, st.Ea, st.Eb);
+        }
+        if (!cold) {
+            amb_eval_windows(G, sig, d - 1, 3, W->P, W->A, W->B);
+            double m;
+            if (amb_metric(W->P[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
+        }
         if (d < scan_end) {
             // slide with the label d: removes T(d), adds T(d+256)  ->  W(d+1) + [T(d-1) - T(d+255)]
             const double xm1 = (double)amb_sig(sig, d - 1), x255 = (double)amb_sig(sig, d + 255), x511 = (double)amb_sig(sig, d + 511);
@@ -299,19 +415,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             W->M[i] = m;
         }
         AMB_WARP_SYNC();
-        for (int i = 0; i < cnt; i++) {
-            const int64_t pos = d + i;
-            if (W->gate[i]) {
-                const double m = W->M[i];
-                if (m > 0.5 && m > best * (1.0 + 1e-12)) { best = m; best_pos = pos; }
-            }
-            const int nxt = pos < scan_end ? i + 1 : i;
-            if (best > 0.5 && best_pos >= 0 && W->gate[nxt] && W->M[nxt] < best * 0.7) {
-                amb_commit(st, best_pos, best, pos + 1, pos < scan_end ? 0 : 1);
-                AMB_WARP_SYNC();
-                return;
-            }
-        }
+        if (amb_scan_batch(st, W, d, cnt, scan_end, best, best_pos)) { AMB_WARP_SYNC(); return; }
         AMB_WARP_SYNC();
         d = d_end + 1;
     }

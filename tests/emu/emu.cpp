@@ -58,6 +58,42 @@ extern "C" {
 
 int emu_result_size(void) { return (int)sizeof(amb_frame_result); }
 
+// randomised agreement check of the reduction form of the candidate logic against the serial loop (amb_walker.cuh);
+// AMB_EMU_CHECK makes amb_scan_batch abort on a mismatch.  Returns the number of batches that committed.
+int emu_scan_batch_fuzz(uint64_t seed, int n_cases) {
+    AmbWalkScratch W;
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    auto uni = [&]() { return (double)(rnd() >> 11) / 9007199254740992.0; };
+    int commits = 0;
+    for (int c = 0; c < n_cases; c++) {
+        const int cnt = 1 + (int)(rnd() % 256);
+        const int look = (int)(rnd() % 4) != 0;
+        const int shape = (int)(rnd() % 5);
+        const double levels[6] = {0.3, 0.5, 0.62, 0.9, 0.9 * (1.0 + 5e-13), 0.9 * (1.0 - 3e-13)};
+        for (int i = 0; i <= cnt; i++) {
+            double m;
+            if (shape == 0) m = uni();
+            else if (shape == 1) m = levels[rnd() % 6];
+            else if (shape == 2) { const double t = (double)i / cnt; m = (t < 0.4 ? t * 2.4 : t < 0.7 ? 0.96 + 0.02 * uni() : 0.96 - (t - 0.7) * 3.0); }
+            else if (shape == 3) m = 0.45 + 0.5 * uni();
+            else m = (i % 7 == 0) ? 0.9 : levels[rnd() % 6] * (1.0 + 1e-12 * (double)(rnd() % 3));
+            W.M[i] = m;
+            W.gate[i] = (rnd() % 16) != 0;
+            if (!W.gate[i]) W.M[i] = 0.0;
+        }
+        AmbStreamState st;
+        memset(&st, 0, sizeof(st));
+        double best = 0.0;
+        int64_t best_pos = -1;
+        if (rnd() % 3 == 0) { best = 0.5 + 0.5 * uni(); best_pos = 1000; if (rnd() % 2) best = levels[3 + rnd() % 3]; }
+        const int64_t d = 5000;
+        const int64_t scan_end = look ? d + cnt + 10 : d + cnt - 1;
+        commits += amb_scan_batch(st, &W, d, cnt, scan_end, best, best_pos) ? 1 : 0;
+    }
+    return commits;
+}
+
 // the chunked CRC-32 of block_crc32 (amb_kernels.cuh), threads run one after the other
 uint32_t emu_crc32_chunked(const uint8_t* data, int64_t n, int nt) {
     AmbTables T;

@@ -28,7 +28,7 @@ def load_emu():
     srcs = [os.path.join(d, "emu.cpp"), os.path.join(ROOT, "audio-modem_b200", "csrc", "amb_tables.cpp")]
     hdrs = [os.path.join(ROOT, "audio-modem_b200", "csrc", f) for f in ("amb_device.cuh", "amb_walker.cuh", "amb_tables.h")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs + hdrs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so] + srcs)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DAMB_EMU_CHECK", "-shared", "-o", so] + srcs)
     return C.CDLL(so)
 
 

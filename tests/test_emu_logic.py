@@ -153,3 +153,14 @@ def test_chunked_crc32_matches_zlib(emu):
             assert emu.emu_crc32_chunked(d.ctypes.data, n, nt) == zlib.crc32(d[:n].tobytes()), (n, nt)
     d = np.frombuffer(b"123456789", np.uint8).copy()
     assert emu.emu_crc32_chunked(d.ctypes.data, 9, 128) == 0xCBF43926
+
+
+def test_scan_batch_reduction_agrees_with_serial_loop(emu):
+    """amb_scan_batch (three reductions) vs the reference-order loop on random, plateau, near-tie and ramp shapes;
+    the emulation is built with AMB_EMU_CHECK, which aborts the process on any disagreement"""
+    import ctypes as C
+
+    emu.emu_scan_batch_fuzz.restype = C.c_int
+    emu.emu_scan_batch_fuzz.argtypes = [C.c_uint64, C.c_int]
+    commits = sum(emu.emu_scan_batch_fuzz(seed, 20000) for seed in range(1, 6))
+    assert commits > 1000
