@@ -40,6 +40,7 @@ EXPORTS = {
     "amb_debug_counter": (C.c_int64, [C.c_void_p, C.c_int]),
     "amb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "amb_host_free": (C.c_int, [C.c_void_p]),
+    "amb_selftest": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
     "amb_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "amb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
     "amb_estimate_frame_samples": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),

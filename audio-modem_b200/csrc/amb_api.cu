@@ -62,8 +62,10 @@ struct amb_modem {
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
-    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc;
+    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum;
+    int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
     int run_cap = 0;
     int64_t link_iterations = 0, link_passes = 0;
     int slot_cap = 0, xc_w = 0;
@@ -289,15 +291,17 @@ void amb_destroy(amb_modem* m) {
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
-                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
+                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
     if (m->d_ema) cudaFree(m->d_ema);
     if (m->d_fast) cudaFree(m->d_fast);
     if (m->d_fallbacks) cudaFree(m->d_fallbacks);
+    if (m->h_counts) cudaFreeHost(m->h_counts);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -329,6 +333,21 @@ int amb_host_alloc(void** out, uint64_t bytes) {
 }
 
 int amb_host_free(void* p) { if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return AMB_E_CUDA; } return AMB_OK; }
+
+int amb_selftest(amb_modem* m, int which, uint64_t seed, int n, int64_t* out2) {
+    if (!m || !out2 || n <= 0) return AMB_E_INVALID;
+    if (which != 0) return fail(m, AMB_E_INVALID, "unknown self-test");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    CK(m->ctmp.ensure(16));
+    CK(cudaMemsetAsync(m->ctmp.p, 0, 16, m->stream));
+    const int warps = 256, per = (n + warps - 1) / warps;
+    LAUNCH("k_selftest_scan_batch", k_selftest_scan_batch<<<warps, 32, 0, m->stream>>>(seed, per, m->ctmp.as<unsigned long long>()));
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, m->ctmp.p, 16, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
+    return AMB_OK;
+}
 
 int amb_profile(amb_modem* m, int enable) {
     if (!m) return AMB_E_INVALID;
@@ -602,6 +621,16 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     m->run_cap = (int)(max_push / 512) + 2;
     CK(m->l_runs.ensure(ns * m->run_cap * sizeof(AmbRun))); CK(m->l_nruns.ensure(ns * 4)); CK(m->l_runoff.ensure(ns * 4));
     CK(m->l_nlinks.ensure(ns * 4)); CK(m->l_active.ensure(ns * 4)); CK(m->l_nactive.ensure(16));
+    {
+        // per run / per link scratch of the link-parallel resolution, for the largest possible number of candidate runs
+        const size_t nr = ns * m->run_cap + 1, nl = nr + ns;
+        CK(m->l_recA.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_endA.ensure(nr * sizeof(AmbStreamState))); CK(m->l_hasA.ensure(nr * 4));
+        CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
+        CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
+        CK(m->l_hasB.ensure(nl * 4));
+        CK(m->l_first.ensure(ns * sizeof(AmbStreamState))); CK(m->l_firstflag.ensure(ns * 4)); CK(m->l_firststop.ensure(ns * 4)); CK(m->l_fpsum.ensure(ns * 8));
+    }
+    if (!m->h_counts && cudaHostAlloc((void**)&m->h_counts, 64, cudaHostAllocDefault) != cudaSuccess) return fail(m, AMB_E_NOMEM, "cudaHostAlloc failed");
     std::vector<AmbStreamState> init(ns);
     std::memset(init.data(), 0, ns * sizeof(AmbStreamState));
     for (auto& s : init) { s.pre_pos = -1; s.frame_end = -1; }
@@ -617,9 +646,10 @@ int amb_stream_close(amb_modem* m) {
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
-                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive};
+                     &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -694,9 +724,16 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         const int64_t n_warps = (int64_t)ns * tiles;
         LAUNCH("k_scan_fast", k_scan_fast<<<blocks_for(n_warps, 8), 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(),
                                                                                         m->sum_stride, ss, n_warps));
-        LAUNCH("k_tri_store", k_tri_store<<<m->slot_cap, 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
+        LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < 148 * 16 ? (m->slot_cap + 3) / 4 : 148 * 16, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
     }
-    LAUNCH("k_defect_prefix", k_defect_prefix<<<ns, 256, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_new / AMB_TILE, ns));
+    {
+        const int64_t n_calls = n_new / AMB_TILE;
+        const int parts = (int)((n_calls + AMB_DEFECT_PART - 1) / AMB_DEFECT_PART);
+        CK(m->dpart.ensure((size_t)ns * parts * 3 * 8));
+        LAUNCH("k_defect_part", k_defect_part<<<ns * parts, 256, 0, m->stream>>>(m->defect.as<double>(), m->calls_stride, off0 / AMB_TILE, n_calls, parts, m->dpart.as<double>()));
+        LAUNCH("k_defect_scan", k_defect_scan<<<ns * parts, 256, 0, m->stream>>>(m->defect.as<double>(), m->fpre.as<double>(), m->calls_stride, off0 / AMB_TILE, n_calls, parts,
+                                                                                m->dpart.as<double>()));
+    }
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;
     g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
@@ -722,6 +759,20 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     }
     CK(m->jobs.ensure((size_t)ns * m->rec_cap * sizeof(AmbJob)));
     CK(m->s_sel.ensure((size_t)ns * 4));
+    // link buffers (sized at open for the largest possible number of candidate runs)
+    AmbLinkBufs L;
+    std::memset(&L, 0, sizeof(L));
+    L.runs = m->l_runs.as<AmbRun>(); L.n_runs = m->l_nruns.as<int>(); L.run_off = m->l_runoff.as<int>(); L.run_cap = m->run_cap;
+    L.n_links = m->l_nlinks.as<int>(); L.active = m->l_active.as<int>(); L.n_active = m->l_nactive.as<int>();
+    L.recA = m->l_recA.as<AmbFrameRec>(); L.endA = m->l_endA.as<AmbStreamState>(); L.hasA = m->l_hasA.as<int>(); L.next = m->l_next.as<int>();
+    L.vis = m->l_vis.as<unsigned char>(); L.jump_a = m->l_ja.as<int>(); L.jump_b = m->l_jb.as<int>();
+    L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
+    L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
+    L.fp_sum = m->l_fpsum.as<unsigned long long>();
+    const int64_t max_links = (int64_t)ns * m->run_cap + ns;
+    const int walk_grid = (int)(blocks_for(max_links, 4) < 148 * 8 ? blocks_for(max_links, 4) : 148 * 8);
+    const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);
+    int* h = m->h_counts;           // pinned: [0] n_active, [1] total jobs, [2] max nsym, [3] kept, [4] n_redo
     for (int pass = 0; pass < 4096 && n_todo > 0; pass++) {
         CK(cudaMemsetAsync(m->nrec.p, 0, (size_t)ns * 4, m->stream));
         CK(cudaMemsetAsync(m->n_redo.p, 0, 4, m->stream));
@@ -730,85 +781,71 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         LAUNCH("k_walk", k_walk<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                              m->dc_next.as<double>(), todo, n_todo, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), 1));
         // streams with metadata: link-parallel resolution (speculate, then verify; amb_walker.cuh)
+        CK(cudaMemsetAsync(L.n_runs, 0, (size_t)ns * 4, m->stream));
+        CK(cudaMemsetAsync(L.active, 0, (size_t)ns * 4, m->stream));
+        CK(cudaMemsetAsync(L.first_flag, 0, (size_t)ns * 4, m->stream));
+        CK(cudaMemsetAsync(L.n_active, 0, 8, m->stream));
         {
-            AmbLinkBufs L;
-            std::memset(&L, 0, sizeof(L));
-            L.runs = m->l_runs.as<AmbRun>(); L.n_runs = m->l_nruns.as<int>(); L.run_off = m->l_runoff.as<int>(); L.run_cap = m->run_cap;
-            L.n_links = m->l_nlinks.as<int>(); L.active = m->l_active.as<int>(); L.n_active = m->l_nactive.as<int>();
-            CK(cudaMemsetAsync(L.n_runs, 0, (size_t)ns * 4, m->stream));
-            CK(cudaMemsetAsync(L.active, 0, (size_t)ns * 4, m->stream));
-            CK(cudaMemsetAsync(L.n_active, 0, 8, m->stream));
-            {
-                const int64_t tile_lo = off0 / 256, tile_hi = (off0 + n_new) / 256;
-                const int chunks = (int)((tile_hi - tile_lo + AMB_RUN_CHUNK - 1) / AMB_RUN_CHUNK);
-                CK(m->l_chunks.ensure((size_t)ns * chunks * 4));
-                LAUNCH("k_runs_count", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
-                                                                                          todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 0, L));
-                LAUNCH("k_runs_offsets", k_runs_offsets<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->states.as<AmbStreamState>(), todo, n_todo, chunks, m->l_chunks.as<int>(), L));
-                LAUNCH("k_runs_write", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
-                                                                                          todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 1, L));
-            }
-            LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
-            int total_runs = 0;
-            CK(cudaMemcpyAsync(&total_runs, L.n_active + 1, 4, cudaMemcpyDeviceToHost, m->stream));
-            CK(cudaStreamSynchronize(m->stream));
-            const size_t nr = (size_t)total_runs + 1, nl = (size_t)total_runs + ns + 1;
-            CK(m->l_recA.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_endA.ensure(nr * sizeof(AmbStreamState))); CK(m->l_hasA.ensure(nr * 4));
-            CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
-            CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
-            CK(m->l_hasB.ensure(nl * 4));
-            L.recA = m->l_recA.as<AmbFrameRec>(); L.endA = m->l_endA.as<AmbStreamState>(); L.hasA = m->l_hasA.as<int>(); L.next = m->l_next.as<int>();
-            L.vis = m->l_vis.as<unsigned char>(); L.jump_a = m->l_ja.as<int>(); L.jump_b = m->l_jb.as<int>();
-            L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
-            if (total_runs > 0) {
-                LAUNCH("k_link_walk_A", k_link_walk<<<blocks_for(total_runs, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
-                                                                                                    m->states.as<AmbStreamState>(), ns, 0, total_runs, L));
-                LAUNCH("k_chain_next", k_chain_next<<<blocks_for(total_runs, 128), 128, 0, m->stream>>>(ns, total_runs, L));
-            }
-            LAUNCH("k_link_first", k_link_first<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
-                                                                                             m->states.as<AmbStreamState>(), m->dc_next.as<double>(), todo, n_todo,
-                                                                                             m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
-            int n_active = 0;
-            CK(cudaMemcpyAsync(&n_active, L.n_active, 4, cudaMemcpyDeviceToHost, m->stream));
-            CK(cudaStreamSynchronize(m->stream));
-            m->link_passes++;
-            for (int it = 0; n_active > 0 && it < (1 << 20); it++) {
-                m->link_iterations++;
-                CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
-                LAUNCH("k_chain_links", k_chain_links<<<ns, 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
-                LAUNCH("k_link_walk_B", k_link_walk<<<blocks_for(total_runs + ns, 4), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(),
-                                                                                                         m->states.as<AmbStreamState>(), ns, 1, total_runs + ns, L));
-                LAUNCH("k_verify_links", k_verify_links<<<ns, 256, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi,
-                                                                                  m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
-                CK(cudaMemcpyAsync(&n_active, L.n_active, 4, cudaMemcpyDeviceToHost, m->stream));
-                CK(cudaStreamSynchronize(m->stream));
-            }
+            const int64_t tile_lo = off0 / 256, tile_hi = (off0 + n_new) / 256;
+            const int chunks = (int)((tile_hi - tile_lo + AMB_RUN_CHUNK - 1) / AMB_RUN_CHUNK);
+            CK(m->l_chunks.ensure((size_t)ns * chunks * 4));
+            LAUNCH("k_runs_count", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
+                                                                                      todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 0, L));
+            LAUNCH("k_runs_offsets", k_runs_offsets<<<blocks_for(n_todo, 4), 128, 0, m->stream>>>(m->states.as<AmbStreamState>(), todo, n_todo, chunks, m->l_chunks.as<int>(), L));
+            LAUNCH("k_runs_write", k_runs_pass<<<n_todo * chunks, 256, 0, m->stream>>>(g, m->tile_slot.as<int32_t>(), m->slot_info.as<int32_t>(), m->states.as<AmbStreamState>(),
+                                                                                      todo, n_todo, tile_lo, tile_hi, chunks, m->l_chunks.as<int>(), 1, L));
         }
-        LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));
-        LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for((int64_t)ns * m->rec_cap, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
-                                                                  m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1));
-        int tot[2] = {0, 0};   // frames, max data symbols
-        CK(cudaMemcpyAsync(tot, m->total.p, 8, cudaMemcpyDeviceToHost, m->stream));
-        CK(cudaStreamSynchronize(m->stream));
-        const int total = tot[0];
+        LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
+        // phase A over every run, and next to it the first link of every stream
+        LAUNCH("k_link_walk_A", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+                                                                            m->dc_next.as<double>(), todo, n_todo, ns, 0, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+        LAUNCH("k_chain_next", k_chain_next<<<flat_grid, 128, 0, m->stream>>>(ns, L));
+        m->link_passes++;
+        int n_active = 1;            // the first iteration runs unconditionally (its kernels skip inactive streams)
+        for (int it = 0; n_active > 0 && it < (1 << 20); it++) {
+            m->link_iterations++;
+            CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
+            LAUNCH("k_chain_links", k_chain_links<<<ns, 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
+            LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+                                                                                m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+            LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+            LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi,
+                                                                                              m->nrec.as<int>(), L));
+            // frame records -> jobs (redone if another iteration adds records)
+            LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));
+            LAUNCH("k_jobs_stream", k_jobs_stream<<<blocks_for((int64_t)ns * m->rec_cap, 128), 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(),
+                                                                      m->job_off.as<int>(), ns, m->jobs.as<AmbJob>(), m->total.as<int>() + 1));
+            CK(cudaMemcpyAsync(h, L.n_active, 4, cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaMemcpyAsync(h + 1, m->total.p, 8, cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            n_active = h[0];
+        }
+        const int total = h[1];      // frames, h[2] = max data symbols
         if (total == 0) break;
         CK(m->s_res.ensure((size_t)total * sizeof(amb_frame_result)));
         CK(m->s_bytes.ensure((size_t)total * bytes_stride));
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
-        if ((rc = run_demod_parse(m, total, tot[1], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
+        if ((rc = run_demod_parse(m, total, h[2], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
         LAUNCH("k_post_stream", k_post_stream<<<ns, 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                   m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
                                                                   m->redo.as<int>(), m->n_redo.as<int>(), g.k_end));
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
         LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
                                                bytes_stride, n_out, max_results, dst_res, dst_bytes));
-        int kept = 0, n_redo = 0;
-        CK(cudaMemcpyAsync(&kept, m->total.as<int>() + 2, 4, cudaMemcpyDeviceToHost, m->stream));
-        CK(cudaMemcpyAsync(&n_redo, m->n_redo.p, 4, cudaMemcpyDeviceToHost, m->stream));
-        if (n_redo > ns) n_redo = ns;
+        CK(cudaMemcpyAsync(h + 3, m->total.as<int>() + 2, 4, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(h + 4, m->n_redo.p, 4, cudaMemcpyDeviceToHost, m->stream));
+        if (results_mem == AMB_MEM_HOST) {
+            // rows [n_out, n_out + total) cover everything this pass can have kept
+            const int lo = n_out < max_results ? n_out : max_results, hi = n_out + total < max_results ? n_out + total : max_results;
+            if (hi > lo && results) CK(cudaMemcpyAsync(results + lo, m->g_res.as<amb_frame_result>() + lo, (size_t)(hi - lo) * sizeof(amb_frame_result), cudaMemcpyDeviceToHost, m->stream));
+            if (hi > lo && bytes_out) CK(cudaMemcpyAsync(bytes_out + (size_t)lo * bytes_stride, m->g_bytes.as<uint8_t>() + (size_t)lo * bytes_stride, (size_t)(hi - lo) * bytes_stride,
+                                                         cudaMemcpyDeviceToHost, m->stream));
+        }
         CK(cudaStreamSynchronize(m->stream));
-        n_out += kept;
+        int n_redo = h[4];
+        if (n_redo > ns) n_redo = ns;
+        n_out += h[3];
         n_todo = n_redo;
         if (n_todo > 0) {
             // the redo list is rewritten by the next k_post_stream while k_walk may still read it: copy it aside
@@ -817,15 +854,10 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         }
     }
     const bool overflow = n_out > max_results;
-    if (results_mem == AMB_MEM_HOST) {
-        const int n_copy = n_out < max_results ? n_out : max_results;
-        if (n_copy > 0 && results) CK(cudaMemcpyAsync(results, m->g_res.p, (size_t)n_copy * sizeof(amb_frame_result), cudaMemcpyDeviceToHost, m->stream));
-        if (n_copy > 0 && bytes_out) CK(cudaMemcpyAsync(bytes_out, m->g_bytes.p, (size_t)n_copy * bytes_stride, cudaMemcpyDeviceToHost, m->stream));
-    }
     m->written += n_new;
     *n_results = n_out;
+    // history compaction is queued behind everything else; the next call on this handle is ordered after it
     if ((rc = stream_compact(m))) return rc;
-    CK(cudaStreamSynchronize(m->stream));
     return overflow ? AMB_E_OVERFLOW : AMB_OK;
 }
 

@@ -57,6 +57,17 @@ __device__ __forceinline__ bool amb_warp_any(bool p) { return __any_sync(0xfffff
 __device__ __forceinline__ unsigned amb_warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 __device__ __forceinline__ unsigned amb_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 __device__ __forceinline__ int amb_popc(unsigned v) { return __popc(v); }
+__device__ __forceinline__ int amb_ffs(unsigned v) { return __ffs((int)v); }                    // 1-based, 0 if none
+__device__ __forceinline__ double amb_warp_scan_max(double v) {                                  // inclusive prefix maximum over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if ((int)(threadIdx.x & 31) >= o) v = fmax(v, u); }
+    return v;
+}
+__device__ __forceinline__ double amb_warp_prev(double v, double fill) {                         // value of the previous lane
+    const double u = __shfl_up_sync(0xffffffffu, v, 1);
+    return (threadIdx.x & 31) ? u : fill;
+}
+__device__ __forceinline__ double amb_warp_bcast(double v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 #else
 #define AMB_NLANES 1
 AMB_HD double amb_warp_max(double v) { return v; }
@@ -67,6 +78,10 @@ AMB_HD bool amb_warp_any(bool p) { return p; }
 AMB_HD unsigned amb_warp_ballot(bool p) { return p ? 1u : 0u; }
 AMB_HD unsigned amb_lanemask_lt() { return 0u; }
 AMB_HD int amb_popc(unsigned v) { return __builtin_popcount(v); }
+AMB_HD int amb_ffs(unsigned v) { return __builtin_ffs((int)v); }
+AMB_HD double amb_warp_scan_max(double v) { return v; }
+AMB_HD double amb_warp_prev(double v, double fill) { (void)v; return fill; }
+AMB_HD double amb_warp_bcast(double v, int lane) { (void)lane; return v; }
 #define AMB_LANE() 0
 #define AMB_WARP_FOR(i, n) for (int i = 0; i < (int)(n); i++)
 #define AMB_WARP_SYNC() ((void)0)

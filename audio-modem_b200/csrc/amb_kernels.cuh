@@ -262,7 +262,13 @@ __global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cle
             float* o = sums + tix * AMB_SUM_W;
             // widened by the screening error so that the walker's cold test stays conservative
             o[0] = ap + err; o[1] = fmaxf(mnA - err, 0.f); o[2] = mxA + err; o[3] = fmaxf(mnB - err, 0.f); o[4] = mxB + err;
-            if (st.tile_slot && any_hot) {
+            // Slots go to tiles holding a window of metric > 0.25, and to tiles the walker's summary test (amb_tile_hot:
+            // max|P|^2 against min Ra * min Rb, loose where the energy ramps inside the tile) would send it into anyway;
+            // widened for the defect the walker may carry.  Without a slot the walker evaluates the tile's windows itself.
+            const float pw = o[0] * 1.05f;
+            const bool wide = o[2] * 1.05f > 0.0009f && o[4] * 1.05f > 0.0009f &&
+                              pw * pw > 0.4f * fmaxf(o[1] * 0.95f, 0.0009f) * fmaxf(o[3] * 0.95f, 0.0009f);
+            if (st.tile_slot && (any_hot || wide)) {
                 int slot = atomicAdd(st.slot_count, 1);
                 if (slot >= st.slot_cap) slot = -1;
                 else { st.slot_info[slot * 4] = s; st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + m); st.slot_info[slot * 4 + 2] = 0; st.slot_info[slot * 4 + 3] = 0; }
@@ -276,46 +282,67 @@ __global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cle
 }
 
 // Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
-// (metric > 0.5 with the 0.001 energy gate, no defect).  One CTA per slot: 768 samples, float64 prefix sums.
-__global__ void __launch_bounds__(256) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
-    const int slot = blockIdx.x;
-    if (slot >= min(*st.slot_count, st.slot_cap)) return;
-    __shared__ float c[768];
-    __shared__ double ST[513], SQ[769], tt[256], tq[256];
-    const int tid = threadIdx.x;
-    const int s = st.slot_info[slot * 4], tile = st.slot_info[slot * 4 + 1];
-    const int64_t a_first = ((int64_t)tile << 8) - 511;                 // arena index of the tile's first window
-    const float* row = cleaned + (int64_t)s * stride;
-    const int64_t a_hi = avail_hi - base_g;
-    for (int i = tid; i < 768; i += 256) { const int64_t a = a_first + i; c[i] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
-    __syncthreads();
-    double lt = 0.0, lq = 0.0;
-    for (int k = 0; k < 3; k++) {
-        const int i = 3 * tid + k;
-        const double x = c[i];
-        SQ[i] = lq; lq = fma(x, x, lq);
-        if (i < 512) { ST[i] = lt; lt = fma(x, (double)c[i + 256], lt); }
+// (metric > 0.5 with the 0.001 energy gate, no defect).  One WARP per slot, everything in registers: lane l holds
+// samples 256 seg + 8 l + k (seg < 3, k < 8) of the tile's 768-sample span and their exclusive float64 prefixes of x^2
+// and x[i] x[i+256]; the window starting at 8 l + k needs exactly the lane's own three prefix values.
+__device__ __forceinline__ double warp_excl_scan(double v, int lane, double* total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+__global__ void __launch_bounds__(128) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
+    const int lane = threadIdx.x & 31;
+    const int n_slots = min(*st.slot_count, st.slot_cap);
+    for (int slot = blockIdx.x * 4 + (threadIdx.x >> 5); slot < n_slots; slot += gridDim.x * 4) {
+        const int s = st.slot_info[slot * 4], tile = st.slot_info[slot * 4 + 1];
+        const int64_t a_first = ((int64_t)tile << 8) - 511;                 // arena index of the tile's first window
+        const float* row = cleaned + (int64_t)s * stride;
+        const int64_t a_hi = avail_hi - base_g;
+        double x[3][8];
+#pragma unroll
+        for (int seg = 0; seg < 3; seg++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? (double)row[a] : 0.0; }
+        double q[3][8], t[2][8], qb[3], tb[2];       // exclusive prefixes inside the segment; global base of the segment
+        double run_q = 0.0, run_t = 0.0;
+#pragma unroll
+        for (int seg = 0; seg < 3; seg++) {
+            double lq = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fma(x[seg][k], x[seg][k], lq); }
+            double tot;
+            const double off = warp_excl_scan(lq, lane, &tot);
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[seg][k] += off;
+            qb[seg] = run_q; run_q += tot;
+            if (seg < 2) {
+                double lt = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fma(x[seg][k], x[seg + 1][k], lt); }
+                const double offt = warp_excl_scan(lt, lane, &tot);
+#pragma unroll
+                for (int k = 0; k < 8; k++) t[seg][k] += offt;
+                tb[seg] = run_t; run_t += tot;
+            }
+        }
+        double* o = st.tri + ((int64_t)slot * 256 + 8 * lane) * 3;
+        int cand = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
+            const double P = (tb[1] + t[1][k]) - (tb[0] + t[0][k]);
+            const double A = (qb[1] + q[1][k]) - (qb[0] + q[0][k]);
+            const double B = (qb[2] + q[2][k]) - (qb[1] + q[1][k]);
+            const bool valid = base_g + a_first + 8 * lane + k >= 0;
+            o[3 * k] = valid ? P : 0.0; o[3 * k + 1] = valid ? A : 0.0; o[3 * k + 2] = valid ? B : 0.0;
+            cand |= valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+        }
+        const int any = __any_sync(0xffffffffu, cand);
+        if (lane == 0) st.slot_info[slot * 4 + 2] = any;
     }
-    tt[tid] = lt; tq[tid] = lq;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-        double a = 0.0, b = 0.0;
-        if (tid >= o) { a = tt[tid - o]; b = tq[tid - o]; }
-        __syncthreads();
-        if (tid >= o) { tt[tid] += a; tq[tid] += b; }
-        __syncthreads();
-    }
-    const double ot = tid ? tt[tid - 1] : 0.0, oq = tid ? tq[tid - 1] : 0.0;
-    for (int k = 0; k < 3; k++) { const int i = 3 * tid + k; SQ[i] += oq; if (i < 512) ST[i] += ot; }
-    if (tid == 255) { SQ[768] = tq[255]; ST[512] = tt[255]; }
-    __syncthreads();
-    const double P = ST[tid + 256] - ST[tid], A = SQ[tid + 256] - SQ[tid], B = SQ[tid + 512] - SQ[tid + 256];
-    const bool valid = base_g + a_first + tid >= 0;
-    double* o = st.tri + ((int64_t)slot * 256 + tid) * 3;
-    o[0] = valid ? P : 0.0; o[1] = valid ? A : 0.0; o[2] = valid ? B : 0.0;
-    const int cand = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
-    const int any = __syncthreads_or(cand);
-    if (tid == 0) st.slot_info[slot * 4 + 2] = any;
 }
 
 // ================================================================================================
@@ -363,6 +390,51 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
         states[s] = st;
         nrec[s] = n;
     }
+}
+
+// Device self-test of the walker's candidate logic: every warp draws random batches (plateaus, ramps, near-ties, gates)
+// and runs the reduction form against the serial loop; counts the batches on which they disagree (must be 0) and the
+// commits.  Reached through amb_selftest(); the same generator runs on the host in tests/emu.
+__global__ void __launch_bounds__(32) k_selftest_scan_batch(uint64_t seed, int cases_per_warp, unsigned long long* __restrict__ out /*[2]*/) {
+    __shared__ AmbWalkScratch W;
+    const int lane = threadIdx.x;
+    uint64_t s = (seed + blockIdx.x) * 0x9E3779B97F4A7C15ull + 1;
+    unsigned long long bad = 0, commits = 0;
+    for (int c = 0; c < cases_per_warp; c++) {
+        // all lanes run the same generator; lane 0 fills the scratch
+        auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+        auto uni = [&]() { return (double)(rnd() >> 11) / 9007199254740992.0; };
+        const int cnt = 1 + (int)(rnd() % 256);
+        const int look = (int)(rnd() % 4) != 0;
+        const int shape = (int)(rnd() % 5);
+        const double levels[6] = {0.3, 0.5, 0.62, 0.9, 0.9 * (1.0 + 5e-13), 0.9 * (1.0 - 3e-13)};
+        for (int i = 0; i <= cnt; i++) {
+            double m;
+            if (shape == 0) m = uni();
+            else if (shape == 1) m = levels[rnd() % 6];
+            else if (shape == 2) { const double t = (double)i / cnt; m = (t < 0.4 ? t * 2.4 : t < 0.7 ? 0.96 + 0.02 * uni() : 0.96 - (t - 0.7) * 3.0); }
+            else if (shape == 3) m = 0.45 + 0.5 * uni();
+            else m = (i % 7 == 0) ? 0.9 : levels[rnd() % 6] * (1.0 + 1e-12 * (double)(rnd() % 3));
+            const int g = (rnd() % 16) != 0;
+            if (lane == 0) { W.M[i] = g ? m : 0.0; W.gate[i] = g; }
+        }
+        double best = 0.0;
+        int64_t best_pos = -1;
+        if (rnd() % 3 == 0) { best = 0.5 + 0.5 * uni(); best_pos = 1000; if (rnd() % 2) best = levels[3 + rnd() % 3]; }
+        __syncwarp();
+        const int64_t d = 5000, scan_end = look ? d + cnt + 10 : d + cnt - 1;
+        AmbStreamState s1, s2;
+        memset(&s1, 0, sizeof(s1)); memset(&s2, 0, sizeof(s2));
+        double b1 = best, b2 = best;
+        int64_t p1 = best_pos, p2 = best_pos;
+        const bool r1 = amb_scan_batch_reduced(s1, &W, d, cnt, scan_end, b1, p1);
+        const bool r2 = amb_scan_batch_serial(s2, &W, d, cnt, scan_end, b2, p2);
+        if (r1 != r2 || b1 != b2 || p1 != p2 || s1.pre_pos != s2.pre_pos || s1.coarse != s2.coarse || s1.state != s2.state ||
+            s1.ac_scan_pos != s2.ac_scan_pos || s1.lag != s2.lag) bad++;
+        commits += r2 ? 1 : 0;
+        __syncwarp();
+    }
+    if (lane == 0) { atomicAdd(out, bad); atomicAdd(out + 1, commits); }
 }
 
 // ================================================================================================
@@ -1388,17 +1460,34 @@ __global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__
 }
 
 // Inclusive prefix over calls of the defect terms: F[c] = F[c-1] + D[c] for the n new arena calls starting at c0
-// (F[c0-1] is the carry from the previous push, 0 before the stream start).  One CTA per stream: contiguous chunks per
-// thread, block scan of the chunk totals.
-__global__ void __launch_bounds__(256) k_defect_prefix(const double* __restrict__ D, double* __restrict__ F, int64_t calls_stride, int64_t c0, int64_t n,
-                                                       int n_streams) {
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (s >= n_streams) return;
+// (F[c0-1] is the carry from the previous push, 0 before the stream start).  Two passes over parts of 1024 calls:
+// k_defect_part sums each part, k_defect_scan adds the carry and the totals of the parts before it and scans its own.
+#define AMB_DEFECT_PART 1024
+__global__ void __launch_bounds__(256) k_defect_part(const double* __restrict__ D, int64_t calls_stride, int64_t c0, int64_t n, int parts,
+                                                     double* __restrict__ part_tot /*[n_streams][parts][3]*/) {
+    const int s = blockIdx.x / parts, part = blockIdx.x % parts, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* d = D + ((int64_t)s * calls_stride + c0) * 3;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < 4; q++) {
+        const int64_t i = (int64_t)part * AMB_DEFECT_PART + 4 * tid + q;
+        if (i < n) for (int c = 0; c < 3; c++) v[c] += d[i * 3 + c];
+    }
+    __shared__ double w[8][3];
+    for (int c = 0; c < 3; c++) { v[c] = warp_sum(v[c]); if (lane == 0) w[warp][c] = v[c]; }
+    __syncthreads();
+    if (tid < 3) { double t = 0.0; for (int k = 0; k < 8; k++) t += w[k][tid]; part_tot[((int64_t)s * parts + part) * 3 + tid] = t; }
+}
+
+__global__ void __launch_bounds__(256) k_defect_scan(const double* __restrict__ D, double* __restrict__ F, int64_t calls_stride, int64_t c0, int64_t n,
+                                                     int parts, const double* __restrict__ part_tot) {
+    const int s = blockIdx.x / parts, part = blockIdx.x % parts, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* d = D + ((int64_t)s * calls_stride + c0) * 3;
     double* f = F + ((int64_t)s * calls_stride + c0) * 3;
-    const int64_t per = (n + 255) / 256, lo = (int64_t)tid * per, hi = lo + per < n ? lo + per : n;
-    double v[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = lo; i < hi; i++) for (int c = 0; c < 3; c++) v[c] += d[i * 3 + c];
+    double x[4][3], v[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < 4; q++) {
+        const int64_t i = (int64_t)part * AMB_DEFECT_PART + 4 * tid + q;
+        for (int c = 0; c < 3; c++) { x[q][c] = i < n ? d[i * 3 + c] : 0.0; v[c] += x[q][c]; }
+    }
     double inc[3] = {v[0], v[1], v[2]};
     for (int o = 1; o < 32; o <<= 1)
         for (int c = 0; c < 3; c++) { const double u = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += u; }
@@ -1408,10 +1497,14 @@ __global__ void __launch_bounds__(256) k_defect_prefix(const double* __restrict_
     double off[3];
     for (int c = 0; c < 3; c++) {
         off[c] = c0 > 0 ? F[((int64_t)s * calls_stride + c0 - 1) * 3 + c] : 0.0;
-        for (int w = 0; w < warp; w++) off[c] += wtot[w][c];
+        for (int p = 0; p < part; p++) off[c] += part_tot[((int64_t)s * parts + p) * 3 + c];
+        for (int k = 0; k < warp; k++) off[c] += wtot[k][c];
         off[c] += inc[c] - v[c];
     }
-    for (int64_t i = lo; i < hi; i++) for (int c = 0; c < 3; c++) { off[c] += d[i * 3 + c]; f[i * 3 + c] = off[c]; }
+    for (int q = 0; q < 4; q++) {
+        const int64_t i = (int64_t)part * AMB_DEFECT_PART + 4 * tid + q;
+        if (i < n) for (int c = 0; c < 3; c++) { off[c] += x[q][c]; f[i * 3 + c] = off[c]; }
+    }
 }
 
 // Cross-correlation screening values for every slot whose tile holds a candidate: float32 metric of preamble-1 at the
@@ -1507,7 +1600,11 @@ struct AmbLinkBufs {
     AmbStreamState* outB; AmbFrameRec* recB; int* hasB;
     unsigned char* vis; int* jump_a; int* jump_b;     // chain scratch, per flat run index
     int* active;             // [n_streams] 1 = needs another iteration
-    int* n_active;
+    int* n_active;           // [0] streams needing another iteration, [1] total runs of this pass
+    // first link of the pass (walked next to phase A) and the verification scratch
+    AmbStreamState* first_out; int* first_flag;       // [n_streams] state after the first link, applied by k_chain_links
+    int* first_stop;         // [n_streams] first chain link that did not reproduce its speculation
+    unsigned long long* fp_sum;   // [n_streams] refine failures inside the accepted links
 };
 
 __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
@@ -1594,92 +1691,95 @@ __device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n
     return lo;
 }
 
-// One warp per link.  mode 0 (phase A): flat run index, synthetic start before the run.  mode 1 (phase B): flat link
-// index, start state = the stream's current state (link 0) or the phase-A end state of the previous chain run.
+// One warp per link (grid-stride; the totals live on the device so no host round trip sizes the launch).
+// mode 0 (phase A): flat run index f < total_runs: synthetic start before the run.  f - total_runs < n_todo: the FIRST
+//   link of the pass for one stream, from its carried state (which may be mid-frame); its end state goes to first_out
+//   (k_chain_links applies it), so that phase A keeps reading an unchanging states[].
+// mode 1 (phase B): flat link index, start state = the stream's current state (link 0) or the phase-A end state of the
+//   previous chain run; the warp also decides whether its link reproduced the speculation (first_stop).
 __global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
-                                                    const float* __restrict__ sums, const AmbStreamState* __restrict__ states, int n_streams,
-                                                    int mode, int total, AmbLinkBufs L) {
+                                                    const float* __restrict__ sums, const AmbStreamState* __restrict__ states,
+                                                    const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo, int n_streams,
+                                                    int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
     __shared__ AmbWalkScratch scratch[4];
-    const int warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * 4 + warp;
-    if (f >= total) return;
-    const int s = stream_of_flat(L.run_off, n_streams, f, mode);
-    const int i = f - (L.run_off[s] + s * mode);
-    AmbStreamState st;
-    if (mode == 0) {
-        if (i >= L.n_runs[s]) return;
-    } else {
-        if (!L.active[s] || i >= L.n_links[s]) return;
-    }
-    AmbWalkGeom G;
-    G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
-    G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
-    if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
-    else if (i == 0) st = states[s];
-    else st = L.endA[L.run_off[s] + L.link_run[f - 1]];
-    AmbSig sig;
-    sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
-    sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
-    AmbFrameRec* rec = mode == 0 ? L.recA + f : L.recB + f;
-    const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, rec, 1, &scratch[warp], 1);
-    if ((threadIdx.x & 31) == 0) {
-        if (mode == 0) { L.endA[f] = st; L.hasA[f] = has; }
-        else { L.outB[f] = st; L.hasB[f] = has; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_runs = L.n_active[1];
+    const int total = mode == 0 ? total_runs + n_todo : total_runs + n_streams;
+    for (int f = blockIdx.x * 4 + warp; f < total; f += gridDim.x * 4) {
+        const bool first = mode == 0 && f >= total_runs;
+        int s, i = 0;
+        if (first) s = todo ? todo[f - total_runs] : f - total_runs;
+        else { s = stream_of_flat(L.run_off, n_streams, f, mode); i = f - (L.run_off[s] + s * mode); }
+        AmbStreamState st;
+        if (first) {
+            st = states[s];
+            if (!st.meta_received) { if (lane == 0) L.active[s] = 0; continue; }
+        } else if (mode == 0) {
+            if (i >= L.n_runs[s]) continue;
+        } else {
+            if (!L.active[s] || i >= L.n_links[s]) continue;
+        }
+        AmbWalkGeom G;
+        G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+        G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+        G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+        if (first) {}
+        else if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
+        else if (i == 0) st = states[s];
+        else st = L.endA[L.run_off[s] + L.link_run[f - 1]];
+        AmbSig sig;
+        sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
+        sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+        AmbFrameRec* rec = first ? recs + (int64_t)s * g.rec_cap : (mode == 0 ? L.recA + f : L.recB + f);
+        const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, rec, 1, &scratch[warp], 1);
+        if (lane == 0) {
+            if (first) {
+                st.dc_mean = dc_next[s]; st.written = g.avail_hi;
+                L.first_out[s] = st; L.first_flag[s] = 1;
+                nrec[s] = has;
+                L.active[s] = has ? 1 : 0;       // no frame: the push is exhausted for this stream
+                if (has) atomicAdd(L.n_active, 1);
+            } else if (mode == 0) { L.endA[f] = st; L.hasA[f] = has; }
+            else {
+                L.outB[f] = st; L.hasB[f] = has;
+                const int run = L.link_run[f];
+                const bool ok = has && run >= 0 && L.hasA[L.run_off[s] + run] == 1 && amb_same_link_state(st, L.endA[L.run_off[s] + run]);
+                if (!ok) atomicMin(&L.first_stop[s], i);
+            }
+        }
+        __syncwarp();
     }
 }
 
 // next[r] = first run still ahead of run r's frame end (local index; n = none)
-__global__ void k_chain_next(int n_streams, int total, AmbLinkBufs L) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= total) return;
-    const int s = stream_of_flat(L.run_off, n_streams, f, 0);
-    const int r = f - L.run_off[s], n = L.n_runs[s];
-    if (r >= n) return;
-    int nx = n;
-    if (L.hasA[f]) {
-        nx = amb_run_at_or_after(L.runs + (int64_t)s * L.run_cap, n, L.endA[f].ac_scan_pos);
-        if (nx <= r) nx = n;
-    }
-    L.next[f] = nx;
-}
-
-// First link of the pass: one frame from the carried state (which may be mid-frame).  One warp per stream.
-__global__ void __launch_bounds__(128) k_link_first(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
-                                                     const float* __restrict__ sums, AmbStreamState* __restrict__ states,
-                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo,
-                                                     AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
-    __shared__ AmbWalkScratch scratch[4];
-    const int warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * 4 + warp;
-    if (w >= n_todo) return;
-    const int s = todo ? todo[w] : w;
-    AmbStreamState st = states[s];
-    if (!st.meta_received) { if ((threadIdx.x & 31) == 0) L.active[s] = 0; return; }
-    AmbWalkGeom G;
-    G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
-    G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
-    AmbSig sig;
-    sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
-    sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
-    const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, recs + (int64_t)s * g.rec_cap, 1,
-                             &scratch[warp], 1);
-    if ((threadIdx.x & 31) == 0) {
-        st.dc_mean = dc_next[s]; st.written = g.avail_hi;
-        states[s] = st;
-        nrec[s] = has;
-        L.active[s] = has ? 1 : 0;       // no frame: the push is exhausted for this stream
-        if (has) atomicAdd(L.n_active, 1);
+__global__ void k_chain_next(int n_streams, AmbLinkBufs L) {
+    const int total = L.n_active[1];
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+        const int s = stream_of_flat(L.run_off, n_streams, f, 0);
+        const int r = f - L.run_off[s], n = L.n_runs[s];
+        if (r >= n) continue;
+        int nx = n;
+        if (L.hasA[f]) {
+            nx = amb_run_at_or_after(L.runs + (int64_t)s * L.run_cap, n, L.endA[f].ac_scan_pos);
+            if (nx <= r) nx = n;
+        }
+        L.next[f] = nx;
     }
 }
 
 // Speculated chain of an active stream from its current (post-reset) state: the runs reachable through next[],
 // in order, plus a tail link when the last of them is expected to emit a frame.  One CTA per stream.
-__global__ void __launch_bounds__(256) k_chain_links(int n_streams, const AmbStreamState* __restrict__ states, AmbLinkBufs L) {
+__global__ void __launch_bounds__(256) k_chain_links(int n_streams, AmbStreamState* __restrict__ states, AmbLinkBufs L) {
     const int s = blockIdx.x;
-    if (s >= n_streams || !L.active[s]) return;
+    if (s >= n_streams) return;
     const int tid = threadIdx.x;
+    if (L.first_flag[s]) {
+        // end state of the pass's first link (walked next to phase A)
+        __syncthreads();
+        if (tid == 0) { states[s] = L.first_out[s]; L.first_flag[s] = 0; }
+        __syncthreads();
+    }
+    if (!L.active[s]) return;
     const int n = L.n_runs[s], off = L.run_off[s];
     const AmbRun* runs = L.runs + (int64_t)s * L.run_cap;
     unsigned char* vis = L.vis + off;
@@ -1727,54 +1827,46 @@ __global__ void __launch_bounds__(256) k_chain_links(int n_streams, const AmbStr
         const bool tail = m == 0 || L.hasA[off + link_run[m - 1]];
         if (tail) link_run[m++] = -1;
         L.n_links[s] = m;
+        L.first_stop[s] = m - 1;
+        L.fp_sum[s] = 0ull;
     }
 }
 
 // Accepts the verified prefix of the chain (see amb_walker.cuh) and leaves the stream either finished for this push or
-// ready for another chain from the exact state where the speculation failed.  One CTA per stream.
-__global__ void __launch_bounds__(256) k_verify_links(int n_streams, int rec_cap, AmbStreamState* __restrict__ states, const double* __restrict__ dc_next,
-                                                       int64_t avail_hi, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
-    const int s = blockIdx.x;
-    if (s >= n_streams || !L.active[s]) return;
-    const int tid = threadIdx.x;
-    const int off = L.run_off[s], lo = off + s, m = L.n_links[s];
-    __shared__ int first_stop;
-    __shared__ unsigned long long fp_sum;
-    if (tid == 0) { first_stop = m - 1; fp_sum = 0ull; }
-    __syncthreads();
-    for (int i = tid; i < m; i += 256) {
-        const int run = L.link_run[lo + i];
-        bool stop = !L.hasB[lo + i];
-        if (!stop) {
-            const bool ok = run >= 0 && L.hasA[off + run] == 1 && amb_same_link_state(L.outB[lo + i], L.endA[off + run]);
-            stop = !ok;
-        }
-        if (stop) atomicMin(&first_stop, i);
-    }
-    __syncthreads();
-    const int stop = first_stop;
-    const int have = nrec[s];
-    const int64_t fp_base = states[s].false_pos;
-    for (int i = tid; i <= stop; i += 256) {
-        if (L.hasB[lo + i] && have + i < rec_cap) recs[(int64_t)s * rec_cap + have + i] = L.recB[lo + i];
+// ready for another chain from the exact state where the speculation failed.  k_verify_copy (one thread per link) moves
+// the accepted records, k_verify_final (one thread per stream) sets the stream state.
+__global__ void __launch_bounds__(128) k_verify_copy(int n_streams, int rec_cap, const AmbStreamState* __restrict__ states, AmbFrameRec* __restrict__ recs,
+                                                      const int* __restrict__ nrec, AmbLinkBufs L) {
+    const int total = L.n_active[1] + n_streams;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+        const int s = stream_of_flat(L.run_off, n_streams, f, 1);
+        const int off = L.run_off[s], lo = off + s, i = f - lo;
+        if (!L.active[s] || i >= L.n_links[s] || i > L.first_stop[s]) continue;
+        const int have = nrec[s];
+        if (L.hasB[f] && have + i < rec_cap) recs[(int64_t)s * rec_cap + have + i] = L.recB[f];
         // refine failures (app.js:879-884) are counted per link: end-state counter minus the link's start-state counter
-        const int64_t in_fp = i == 0 ? fp_base : L.endA[off + L.link_run[lo + i - 1]].false_pos;
-        const int64_t d = L.outB[lo + i].false_pos - in_fp;
-        if (d > 0) atomicAdd(&fp_sum, (unsigned long long)d);
+        const int64_t in_fp = i == 0 ? states[s].false_pos : L.endA[off + L.link_run[f - 1]].false_pos;
+        const int64_t d = L.outB[f].false_pos - in_fp;
+        if (d > 0) atomicAdd(&L.fp_sum[s], (unsigned long long)d);
     }
-    __syncthreads();
-    if (tid == 0) {
-        // links before `stop` all emitted a frame
-        const int acc = L.hasB[lo + stop] ? stop + 1 : stop;
-        int total = have + acc;
-        if (total > rec_cap) total = rec_cap;
-        nrec[s] = total;
-        AmbStreamState st = L.outB[lo + stop];
-        st.dc_mean = dc_next[s]; st.written = avail_hi;
-        st.false_pos = fp_base + (int64_t)fp_sum;
-        states[s] = st;
-        const int again = L.hasB[lo + stop] && total < rec_cap ? 1 : 0;      // stopped at a frame: chain again from its exact end state
-        L.active[s] = again;
-        if (again) atomicAdd(L.n_active, 1);
-    }
+}
+
+__global__ void __launch_bounds__(128) k_verify_final(int n_streams, int rec_cap, AmbStreamState* __restrict__ states, const double* __restrict__ dc_next,
+                                                       int64_t avail_hi, int* __restrict__ nrec, AmbLinkBufs L) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams || !L.active[s]) return;
+    const int lo = L.run_off[s] + s, stop = L.first_stop[s];
+    // links before `stop` all emitted a frame
+    const int acc = L.hasB[lo + stop] ? stop + 1 : stop;
+    int total = nrec[s] + acc;
+    if (total > rec_cap) total = rec_cap;
+    nrec[s] = total;
+    const int64_t fp_base = states[s].false_pos;
+    AmbStreamState st = L.outB[lo + stop];
+    st.dc_mean = dc_next[s]; st.written = avail_hi;
+    st.false_pos = fp_base + (int64_t)L.fp_sum[s];
+    states[s] = st;
+    const int again = L.hasB[lo + stop] && total < rec_cap ? 1 : 0;      // stopped at a frame: chain again from its exact end state
+    L.active[s] = again;
+    if (again) atomicAdd(L.n_active, 1);
 }

@@ -228,12 +228,10 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
 // running maximum (best, best_pos).  Returns true when the batch commits a preamble (state updated).
 //   reference, per position:  if gate && m > 0.5 && m > best: best = m          (here: must exceed best by 1e-12)
 //                             if best > 0.5 && gate[next] && M[next] < 0.7 best: commit
-// amb_scan_batch_serial is that loop as written.  amb_scan_batch reaches the same result from three reductions:
-// i0 = first candidate; (Bmax, amax) = maximum and its first position from i0 on (including the running best);
-// u = first position >= i0 whose successor metric is below 0.7 Bmax.  Before u no successor is below 0.7 best_i
-// (best_i <= Bmax), and at u the running best already equals Bmax when amax <= u, so the commit happens exactly at
-// u.  The cases this does not cover (near-ties within 1e-12 before the maximum, a maximum that comes after u) take
-// the serial loop.
+// amb_scan_batch_serial is that loop as written.  amb_scan_batch_reduced walks the batch in chunks of one position per
+// lane: a prefix-maximum scan gives the running best at every position, the commit test is then independent per
+// position and a ballot finds the first one.  The running best equals the plain prefix maximum unless some update is
+// suppressed by the 1e-12 rule (a near-tie, e.g. a noise-free plateau); such batches take the serial loop.
 AMB_HD bool amb_scan_batch_serial(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
     for (int i = 0; i < cnt; i++) {
         const int64_t pos = d + i;
@@ -273,51 +271,40 @@ AMB_HD bool amb_scan_batch(AmbStreamState& st, const AmbWalkScratch* W, int64_t 
 }
 
 AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
-    const int NONE = 0x7fffffff;
     const bool tracking = best > 0.5 && best_pos >= 0;
-    int i0 = 0;
-    if (!tracking) {
-        if (best > 0.5) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);      // not a state the walker produces
-        int loc = NONE;
-        AMB_WARP_FOR(i, cnt) if (loc == NONE && W->gate[i] && W->M[i] > 0.5) loc = i;
-        i0 = amb_warp_min_int(loc);
-        if (i0 == NONE) return false;                                  // no candidate: nothing can happen in this batch
-    }
-    // maximum from i0 on and its first position (-1: the running best)
-    double lmax = -1.0;
-    AMB_WARP_FOR(i, cnt) if (i >= i0 && W->gate[i] && W->M[i] > 0.5) lmax = fmax(lmax, W->M[i]);
-    double bmax = amb_warp_max(lmax);
-    int amax = NONE;
-    if (tracking && best >= bmax) { bmax = best; amax = -1; }
-    else {
-        int loc = NONE;
-        AMB_WARP_FOR(i, cnt) if (loc == NONE && i >= i0 && W->gate[i] && W->M[i] == bmax) loc = i;
-        amax = amb_warp_min_int(loc);
-    }
-    // near-ties below the maximum and before it: the 1e-12 rule may keep the earlier value -> serial
-    {
-        bool amb = tracking && amax >= 0 && best < bmax && best * (1.0 + 1e-12) >= bmax;
-        AMB_WARP_FOR(i, cnt) if (i >= i0 && i < amax && W->gate[i] && W->M[i] > 0.5 && W->M[i] < bmax && W->M[i] * (1.0 + 1e-12) >= bmax) amb = true;
-        if (amb_warp_any(amb)) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
-    }
-    // first position whose successor metric is below 0.7 Bmax
-    int loc = NONE;
-    const double thr = bmax * 0.7;
-    AMB_WARP_FOR(i, cnt) {
-        if (loc == NONE && i >= i0) {
+    if (!tracking && best > 0.5) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);      // not a state the walker produces
+    double carry = tracking ? best : 0.0;          // running maximum before the current chunk (0: none yet)
+    int64_t carry_pos = best_pos;
+    for (int c0 = 0; c0 < cnt; c0 += AMB_NLANES) {
+        const int i = c0 + AMB_LANE();
+        const bool in = i < cnt;
+        const double v = (in && W->gate[i] && W->M[i] > 0.5) ? W->M[i] : -1.0;
+        const double pm = amb_warp_scan_max(v);
+        const double prev = fmax(carry, amb_warp_prev(pm, -1.0));       // running maximum before position i
+        const double r = fmax(carry, pm);                               // ... and at position i
+        const bool amb = v > prev && !(v > prev * (1.0 + 1e-12));       // an update the 1e-12 rule would suppress
+        bool trig = false;
+        if (in && r > 0.5) {
             const int nxt = d + i < scan_end ? i + 1 : i;
-            if (W->gate[nxt] && W->M[nxt] < thr) loc = i;
+            trig = W->gate[nxt] && W->M[nxt] < r * 0.7;
+        }
+        const unsigned tb = amb_warp_ballot(trig), ab = amb_warp_ballot(amb);
+        const int u = tb ? amb_ffs(tb) - 1 : AMB_NLANES;                // lane of the first commit in this chunk
+        if (ab & (u < AMB_NLANES ? ((2u << u) - 1u) : 0xffffffffu)) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
+        const double top = amb_warp_bcast(u < AMB_NLANES ? r : pm, u < AMB_NLANES ? u : AMB_NLANES - 1);
+        if (top > carry) {
+            // the running maximum (at the commit, or at the end of the chunk) was first attained inside this chunk
+            const unsigned eb = amb_warp_ballot(v == top);
+            carry = top; carry_pos = d + c0 + amb_ffs(eb) - 1;
+        }
+        if (u < AMB_NLANES) {
+            best = carry; best_pos = carry_pos;
+            amb_commit(st, best_pos, best, d + c0 + u + 1, d + c0 + u < scan_end ? 0 : 1);
+            return true;
         }
     }
-    const int u = amb_warp_min_int(loc);
-    if (u == NONE) {
-        if (amax >= 0) { best = bmax; best_pos = d + amax; }
-        return false;
-    }
-    if (amax > u) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
-    if (amax >= 0) { best = bmax; best_pos = d + amax; }
-    amb_commit(st, best_pos, best, d + u + 1, d + u < scan_end ? 0 : 1);
-    return true;
+    if (carry > 0.5) { best = carry; best_pos = carry_pos; }
+    return false;
 }
 
 // _scanForPreamble, app.js:775-847, for the call whose totalWritten is `tw`

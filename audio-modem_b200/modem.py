@@ -165,6 +165,12 @@ class Modem:
         """0 launches, 1 fast-demod fallback symbols, 2 link iterations, 3 link passes"""
         return int(self._L.amb_debug_counter(self._h, which))
 
+    def selftest(self, which=0, seed=1, n=100000):
+        """device self-test (amb_selftest): returns (disagreements, commits)"""
+        out = (C.c_int64 * 2)()
+        self._ck(self._L.amb_selftest(self._h, which, seed, n, out))
+        return int(out[0]), int(out[1])
+
     def profile(self, enable=True):
         """bracket every kernel launch with CUDA events on the handle's stream (device time per kernel)"""
         self._ck(self._L.amb_profile(self._h, int(enable)))

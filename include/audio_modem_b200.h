@@ -128,6 +128,10 @@ int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by t
 /* development counters: 0 kernel launches, 1 data symbols redone by the float64-faithful fallback of the fast
  * demodulator, 2 link-resolution iterations, 3 link-resolution passes */
 int64_t amb_debug_counter(amb_modem* m, int which);
+/* development self-tests that need the device's 32-lane execution: which = 0 runs n random batches of the streaming
+ * scanner's candidate logic (app.js:806-838) through its warp-parallel form and through the reference-order loop;
+ * out2[0] = disagreements (must be 0), out2[1] = batches that committed a preamble */
+int amb_selftest(amb_modem* m, int which, uint64_t seed, int n, int64_t* out2);
 int amb_profile(amb_modem* m, int enable);
 int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n);
 

@@ -40,6 +40,12 @@ def test_extension_is_loaded_and_launches_kernels(amb, modems):
     assert "libaudiomodem_b200.so" in maps
 
 
+def test_scan_batch_selftest(modems):
+    """warp-parallel candidate logic of the streaming scanner vs the reference-order loop, on the device (32 lanes)"""
+    bad, commits = modems("QPSK").selftest(0, seed=7, n=200000)
+    assert bad == 0 and commits > 10000, (bad, commits)
+
+
 def test_crc32(O, modems):
     import zlib
 
