@@ -597,12 +597,13 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
                                   : amb_tables_estimate_frame_samples(T.cfg_id, T.mod, 11, T.rep);
     m->rec_cap = (int)(max_push / min_frame) + 3;
     const size_t ns = (size_t)n_streams;
-    CK(m->raw.ensure(ns * m->stride * 4)); CK(m->cleaned.ensure(ns * m->stride * 4));
+    // `raw` only stages the samples of one push (host input, unaligned device input, in-place writers); the history
+    // lives in `cleaned`
+    CK(m->raw.ensure(ns * m->max_push * 4)); CK(m->cleaned.ensure(ns * m->stride * 4));
     CK(m->sums.ensure(ns * m->sum_stride * AMB_SUM_W * 4));
     CK(m->agg.ensure(ns * (size_t)(max_push / AMB_CHUNK) * 8)); CK(m->dc_next.ensure(ns * 8));
     CK(m->states.ensure(ns * sizeof(AmbStreamState))); CK(m->recs.ensure(ns * m->rec_cap * sizeof(AmbFrameRec)));
     CK(m->nrec.ensure(ns * 4)); CK(m->job_off.ensure(ns * 4)); CK(m->total.ensure(16)); CK(m->redo.ensure(ns * 4)); CK(m->n_redo.ensure(16));
-    CK(cudaMemsetAsync(m->raw.p, 0, ns * m->stride * 4, m->stream));
     CK(cudaMemsetAsync(m->cleaned.p, 0, ns * m->stride * 4, m->stream));
     CK(cudaMemsetAsync(m->sums.p, 0, ns * m->sum_stride * AMB_SUM_W * 4, m->stream));
     CK(cudaMemsetAsync(m->dc_next.p, 0, ns * 8, m->stream));
@@ -617,7 +618,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
-    cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     m->run_cap = (int)(max_push / 512) + 2;
     CK(m->l_runs.ensure(ns * m->run_cap * sizeof(AmbRun))); CK(m->l_nruns.ensure(ns * 4)); CK(m->l_runoff.ensure(ns * 4));
     CK(m->l_nlinks.ensure(ns * 4)); CK(m->l_active.ensure(ns * 4)); CK(m->l_nactive.ensure(16));
@@ -657,8 +658,8 @@ int amb_stream_close(amb_modem* m) {
 
 int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride) {
     if (!m || !m->open) return m ? fail(m, AMB_E_STATE, "stream not open") : AMB_E_INVALID;
-    if (dev_ptr) *dev_ptr = m->raw.as<float>() + (m->written - m->base_g);
-    if (stride) *stride = m->stride;
+    if (dev_ptr) *dev_ptr = m->raw.as<float>();
+    if (stride) *stride = m->max_push;
     return AMB_OK;
 }
 
@@ -670,7 +671,7 @@ static int stream_compact(amb_modem* m) {
     const int64_t shift = off - m->hist;               // multiple of 4096
     const size_t row = (size_t)m->hist * 4;
     CK(m->ctmp.ensure((size_t)m->n_streams * row));
-    float* bases[2] = {m->raw.as<float>(), m->cleaned.as<float>()};
+    float* bases[1] = {m->cleaned.as<float>()};
     for (float* b : bases) {
         CK(cudaMemcpy2DAsync(m->ctmp.p, row, b + shift, (size_t)m->stride * 4, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
         CK(cudaMemcpy2DAsync(b, (size_t)m->stride * 4, m->ctmp.p, row, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
@@ -701,17 +702,20 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     const int ns = m->n_streams;
     const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
-    float* raw = m->raw.as<float>();
+    // samples are read where they are when they sit in device memory with 16-byte aligned rows; otherwise they are staged
+    const float* src = m->raw.as<float>();
+    int64_t src_stride = m->max_push;
     if (mem != AMB_MEM_INPLACE) {
         if (!x) return fail(m, AMB_E_INVALID, "x required");
-        CK(cudaMemcpy2DAsync(raw + off0, (size_t)m->stride * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
-                             mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
+        if (mem == AMB_MEM_DEVICE && ((uintptr_t)x & 15) == 0 && (x_stride & 3) == 0) { src = x; src_stride = x_stride; }
+        else CK(cudaMemcpy2DAsync(m->raw.p, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
+                                  mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
     }
     // 1. DC removal
     const int64_t n_chunks = n_new / AMB_CHUNK;
     const int per = blocks_for(n_chunks, 4);
-    LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(raw, m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>()));
-    LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(raw, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
+    LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(src, src_stride, n_chunks, per, m->d_ema, m->agg.as<double>()));
+    LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(src, src_stride, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
                                                  m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
     // 2. window-sum summaries of the new window-end samples
     const int tiles = (int)(n_new / AMB_TILE);
@@ -743,8 +747,11 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
     {
         const int L = m->xc_w + T.sym_len;
-        const size_t smem = (size_t)L * 8 + (size_t)((T.sym_len + 1) & ~1) * 4 + (size_t)(L + 1) * 8 + 16;
-        LAUNCH("k_xcorr_store", k_xcorr_store<<<m->slot_cap, 128, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
+        const size_t smem = (size_t)L * 4 * 3 + 256 * 4 + (size_t)(L + 1) * 8 + 64;
+        int threads = ((m->xc_w + AMB_XC_PER - 1) / AMB_XC_PER + 31) / 32 * 32;
+        if (threads > 256) threads = 256;
+        const int grid = m->slot_cap < 148 * 16 ? m->slot_cap : 148 * 16;
+        LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
                                                                                      m->slot_count.as<int>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
     }
     int n_out = 0;

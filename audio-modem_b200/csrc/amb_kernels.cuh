@@ -56,13 +56,13 @@ struct AmbEmaTables {
     double alpha, beta;
 };
 
-__global__ void k_ema_agg(const float* __restrict__ x, int64_t stride, int64_t off0, int64_t n_chunks, int per,
+__global__ void k_ema_agg(const float* __restrict__ x, int64_t x_stride, int64_t n_chunks, int per,
                           const AmbEmaTables* __restrict__ E, double* __restrict__ agg) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     AMB_SPLIT_BID(per, s, cb)
     const int64_t c = (int64_t)cb * (blockDim.x >> 5) + warp;
     if (c >= n_chunks) return;
-    const float* p = x + (int64_t)s * stride + off0 + c * AMB_CHUNK;
+    const float* p = x + (int64_t)s * x_stride + c * AMB_CHUNK;
     double acc = 0.0;
 #pragma unroll
     for (int t = 0; t < AMB_CHUNK / 32; t++) {
@@ -73,7 +73,7 @@ __global__ void k_ema_agg(const float* __restrict__ x, int64_t stride, int64_t o
     if (lane == 0) agg[(int64_t)s * n_chunks + c] = acc;
 }
 
-__global__ void k_ema_apply(const float* __restrict__ x, float* __restrict__ cleaned, int64_t stride, int64_t off0,
+__global__ void k_ema_apply(const float* __restrict__ x, int64_t x_stride, float* __restrict__ cleaned, int64_t stride, int64_t off0,
                             int64_t n_chunks, int per, const AmbEmaTables* __restrict__ E, const double* __restrict__ agg,
                             const AmbStreamState* __restrict__ states, double* __restrict__ dc_next) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,10 +87,11 @@ __global__ void k_ema_apply(const float* __restrict__ x, float* __restrict__ cle
     double m = warp_sum(part);
     if (c <= AMB_EMA_TERMS) m = fma(E->w_chunk[c], states[s].dc_mean, m);
     const int64_t at = (int64_t)s * stride + off0 + c * AMB_CHUNK + lane * 16;
+    const int64_t xat = (int64_t)s * x_stride + c * AMB_CHUNK + lane * 16;
     float xv[16];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const float4 v = reinterpret_cast<const float4*>(x + at)[q];
+        const float4 v = reinterpret_cast<const float4*>(x + xat)[q];
         xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
     }
     double bl = 0.0;   // lane-local response from a zero state
@@ -879,13 +880,15 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint8
         for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
         c ^= 0xFFFFFFFFu;
     }
-    uint32_t op = amb_gf_xpow8((uint32_t)((n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS));
+    // level l of the tree multiplies by x^(8 L 2^l): one thread per level computes its constant, the rest wait
+    __shared__ uint32_t ops[8];
+    if (tid < 7) ops[tid] = amb_gf_xpow8((uint32_t)(((n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS) << tid));
     sh[tid] = c;
     __syncthreads();
-    for (int span = 1; span < AMB_CRC_THREADS; span <<= 1) {
+    int level = 0;
+    for (int span = 1; span < AMB_CRC_THREADS; span <<= 1, level++) {
         const bool act = (tid & (2 * span - 1)) == 0;
-        if (act) c = amb_gf_mul(c, op) ^ sh[tid + span];
-        op = amb_gf_mul(op, op);
+        if (act) c = amb_gf_mul(c, ops[level]) ^ sh[tid + span];
         __syncthreads();
         if (act) sh[tid] = c;
         __syncthreads();
@@ -1509,75 +1512,99 @@ __global__ void __launch_bounds__(256) k_defect_scan(const double* __restrict__ 
 
 // Cross-correlation screening values for every slot whose tile holds a candidate: float32 metric of preamble-1 at the
 // xc_w = 256 + 2R offsets  tile_first - R + i  (amb_fine_xcorr_store re-evaluates the near-maximal ones exactly).
-// The preamble's two body halves are equal up to the sign pre1_sign, so the body taps are folded:
-//   corr(o) = sum_{i<cp} pre1[i] s[o+i] + sum_{r<256} pre1[cp+r] (s[o+cp+r] + sign * s[o+cp+256+r]).
-// Each thread carries 4 consecutive offsets in registers (one new sample and one tap per 4 FMAs).
+// Preamble-1 is [prefix | body], the two halves of the body are equal up to the sign pre1_sign and the prefix repeats the
+// end of the body, so the 576/640/768 taps fold onto the 256 taps of the first half:
+//   corr(o) = sum_{r<256} body[r] * w_r[o + cp + r],   w_r = u                      for r <  256 - cp
+//                                                      w_r = u2                     for r >= 256 - cp
+//   u[p] = s[p] + sign s[p + 256],   u2[p] = u[p] + sign s[p - 256].
+// Each thread carries 8 consecutive offsets in registers: per 4 taps two 128-bit shared loads feed 32 FMAs.
 #define AMB_XC_MAXW (256 + 2 * 768)
-__global__ void __launch_bounds__(128) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+#define AMB_XC_PER 8
+__global__ void __launch_bounds__(256) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                       const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count, int slot_cap,
                                                       float* __restrict__ xc, int xc_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int slot = blockIdx.x;
     const int n_slots = min(*slot_count, slot_cap);
-    if (slot >= n_slots || !slot_info[slot * 4 + 2]) return;
-    const int s = slot_info[slot * 4], tile = slot_info[slot * 4 + 1];
     const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
-    const int L = xc_w + plen;                                         // samples needed
+    const int L = xc_w + plen;                                         // samples needed (multiple of 4 for every config)
     float* sg = reinterpret_cast<float*>(smem_raw);                    // [L]
-    float* u = sg + L;                                                 // [L] folded
-    float* tp = u + L;                                                 // [plen] template
-    double* SQ = reinterpret_cast<double*>(tp + ((plen + 1) & ~1));    // [L + 1] prefix of squares
-    const int tid = threadIdx.x;
-    const int64_t tile_first = g.base_g + ((int64_t)tile << 8) - 511;  // global position of the tile's first window
-    const int64_t base = tile_first - R;
-    const float* src = cleaned + (int64_t)s * g.stride;
-    const int64_t lo = g.base_g > 0 ? g.base_g : 0;
-    for (int i = tid; i < L; i += 128) {
-        const int64_t p = base + i;
-        sg[i] = (p >= lo && p < g.avail_hi) ? src[p - g.base_g] : 0.f;
-    }
-    for (int i = tid; i < plen; i += 128) tp[i] = T->pre1[i];
-    __syncthreads();
+    float* u = sg + L;                                                 // [L]
+    float* u2 = u + L;                                                 // [L]
+    float* tp = u2 + L;                                                // [256] first half of the body
+    double* SQ = reinterpret_cast<double*>(tp + 256);                  // [L + 1] prefix of squares
+    __shared__ double tot[256];
+    const int tid = threadIdx.x, nt = blockDim.x;
     const float sign = (float)T->pre1_sign;
-    for (int i = tid; i < L; i += 128) u[i] = (i + 256 < L) ? sg[i] + sign * sg[i + 256] : sg[i];
-    // prefix of squares (float64): 128 threads x contiguous chunks, then a serial pass over the 128 totals
-    const int per = (L + 127) / 128;
-    __shared__ double tot[128];
-    {
-        double acc = 0.0;
-        for (int i = tid * per; i < min(L, (tid + 1) * per); i++) { SQ[i] = acc; acc += (double)sg[i] * (double)sg[i]; }
-        tot[tid] = acc;
-    }
-    __syncthreads();
-    if (tid == 0) { double acc = 0.0; for (int t = 0; t < 128; t++) { const double v = tot[t]; tot[t] = acc; acc += v; } SQ[L] = acc; }
-    __syncthreads();
-    { const double o = tot[tid]; for (int i = tid * per; i < min(L, (tid + 1) * per); i++) SQ[i] += o; }
-    __syncthreads();
     const double tE = T->pre1_energy;
-    float* out = xc + (int64_t)slot * xc_w;
-    for (int o0 = tid * 4; o0 < xc_w; o0 += 128 * 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        float x0 = sg[o0], x1 = sg[o0 + 1], x2 = sg[o0 + 2];
-        for (int i = 0; i < cp; i++) {                                 // cyclic-prefix taps on the raw samples
-            const float x3 = sg[o0 + i + 3], t = tp[i];
-            a0 = fmaf(t, x0, a0); a1 = fmaf(t, x1, a1); a2 = fmaf(t, x2, a2); a3 = fmaf(t, x3, a3);
-            x0 = x1; x1 = x2; x2 = x3;
+    for (int i = tid; i < 256; i += nt) tp[i] = T->pre1[cp + i];
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        if (!slot_info[slot * 4 + 2]) continue;
+        const int s = slot_info[slot * 4], tile = slot_info[slot * 4 + 1];
+        const int64_t tile_first = g.base_g + ((int64_t)tile << 8) - 511;  // global position of the tile's first window
+        const int64_t base = tile_first - R;
+        const float* src = cleaned + (int64_t)s * g.stride;
+        const int64_t lo = g.base_g > 0 ? g.base_g : 0;
+        __syncthreads();
+        for (int i = tid; i < L; i += nt) {
+            const int64_t p = base + i;
+            sg[i] = (p >= lo && p < g.avail_hi) ? src[p - g.base_g] : 0.f;
         }
-        x0 = u[o0 + cp]; x1 = u[o0 + cp + 1]; x2 = u[o0 + cp + 2];
-        for (int r = 0; r < 256; r++) {                                // folded body taps
-            const float x3 = u[o0 + cp + r + 3], t = tp[cp + r];
-            a0 = fmaf(t, x0, a0); a1 = fmaf(t, x1, a1); a2 = fmaf(t, x2, a2); a3 = fmaf(t, x3, a3);
-            x0 = x1; x1 = x2; x2 = x3;
+        __syncthreads();
+        for (int i = tid; i < L; i += nt) {
+            const float a = (i + 256 < L) ? sg[i] + sign * sg[i + 256] : sg[i];
+            u[i] = a;
+            u2[i] = i >= 256 ? a + sign * sg[i - 256] : a;
         }
-        const float acc[4] = {a0, a1, a2, a3};
-        for (int q = 0; q < 4 && o0 + q < xc_w; q++) {
-            const double se = SQ[o0 + q + plen] - SQ[o0 + q];
-            const double denom = sqrt(se * tE);
-            float v;
-            if (denom > 0.001 * (1.0 + 1e-4)) v = (float)((double)acc[q] / denom);
-            else if (denom < 0.001 * (1.0 - 1e-4)) v = AMB_XC_FAIL;
-            else v = AMB_XC_UNSURE;
-            out[o0 + q] = v;
+        // prefix of squares (float64): contiguous chunks per thread, then a serial pass over the chunk totals
+        const int per = (L + nt - 1) / nt;
+        {
+            double acc = 0.0;
+            for (int i = tid * per; i < min(L, (tid + 1) * per); i++) { SQ[i] = acc; acc += (double)sg[i] * (double)sg[i]; }
+            tot[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) { double acc = 0.0; for (int t = 0; t < nt; t++) { const double v = tot[t]; tot[t] = acc; acc += v; } SQ[L] = acc; }
+        __syncthreads();
+        { const double o = tot[tid]; for (int i = tid * per; i < min(L, (tid + 1) * per); i++) SQ[i] += o; }
+        __syncthreads();
+        float* out = xc + (int64_t)slot * xc_w;
+        const int split = 256 - cp;                                    // taps below use u, taps from here on use u2 (multiple of 4)
+        for (int o0 = tid * AMB_XC_PER; o0 < xc_w; o0 += nt * AMB_XC_PER) {
+            float acc[AMB_XC_PER];
+#pragma unroll
+            for (int q = 0; q < AMB_XC_PER; q++) acc[q] = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const float* w = half == 0 ? u : u2;
+                const int r0 = half == 0 ? 0 : split, r1 = half == 0 ? split : 256;
+                if (r0 >= r1) continue;
+                const float4* wp = reinterpret_cast<const float4*>(w + o0 + cp + r0);
+                float x[12];
+                { const float4 a = wp[0], b = wp[1]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w; }
+                for (int r = r0; r < r1; r += 4) {
+                    const float4 nx = wp[((r - r0) >> 2) + 2];
+                    x[8] = nx.x; x[9] = nx.y; x[10] = nx.z; x[11] = nx.w;
+                    const float4 t4 = *reinterpret_cast<const float4*>(tp + r);
+                    const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                        for (int q = 0; q < AMB_XC_PER; q++) acc[q] = fmaf(t[jj], x[q + jj], acc[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) x[q] = x[q + 4];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < AMB_XC_PER; q++) {
+                if (o0 + q >= xc_w) break;
+                const double se = SQ[o0 + q + plen] - SQ[o0 + q];
+                const double denom = sqrt(se * tE);
+                float v;
+                if (denom > 0.001 * (1.0 + 1e-4)) v = (float)((double)acc[q] / denom);
+                else if (denom < 0.001 * (1.0 - 1e-4)) v = AMB_XC_FAIL;
+                else v = AMB_XC_UNSURE;
+                out[o0 + q] = v;
+            }
         }
     }
 }
