@@ -604,6 +604,7 @@ __device__ __forceinline__ void fft16f(float2* v) {
 #define AMB_FD_MAXBINS 224
 #define AMB_FD_ITERS (AMB_FD_MAXBINS / 16)              // 14
 #define AMB_FD_FB_WARPS 4                               // warps that run the float64-faithful fallback
+#define AMB_FD_CPV 4                                    // cyclic-prefix samples per lane loaded ahead of the transform
 #define AMB_FD_SMEM_FAST (AMB_FD_HW * AMB_FD_HWBUF * 8 + 2 * 256 * 8 + AMB_FD_MAXBINS * (8 + 4 + 4 + 4))
 #define AMB_FD_SMEM_FB (4 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS * 8)
 #define AMB_DEMOD_FAST_SMEM ((AMB_FD_SMEM_FAST > AMB_FD_SMEM_FB ? AMB_FD_SMEM_FAST : AMB_FD_SMEM_FB) + 64)
@@ -665,7 +666,7 @@ __device__ __forceinline__ float2 fd_split(const float2* buf, const float2* __re
     return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
 }
 
-__global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
+__global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
                                                      int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- fast layout
@@ -675,8 +676,11 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
     float2* Gq = tw512 + 256;                                                    // [bins] conj(H)/|H|^2 (raw scale)
     float* invH = reinterpret_cast<float*>(Gq + AMB_FD_MAXBINS);                 // [bins] 1/|H|
     float* dH = invH + AMB_FD_MAXBINS;                                           // [bins] bound on |dH|/|H|
+    float* cH = invH;                                                            // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
     int* role = reinterpret_cast<int*>(dH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 pilot
     __shared__ float s_red[8];
+    __shared__ float4 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
+    __shared__ int pilot_in_band[AMB_MAX_PILOTS];
     __shared__ float s_mx, s_minhm;
     __shared__ unsigned s_mask[2];
     __shared__ int s_all;
@@ -690,10 +694,16 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
     const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data, mod = T->mod;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
     for (int i = tid; i < 256; i += 256) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
-    for (int kk = tid; kk < nb; kk += 256) role[kk] = -1;
+    // role[kk]: data index of the bin, or -1 - q for pilot q
+    if (tid < AMB_MAX_PILOTS) {
+        const int k = tid < T->n_pilots ? T->pilots[tid] : -1;
+        const bool inb = k >= T->sub_start && k <= T->sub_end;
+        pilot_in_band[tid] = inb ? 1 : 0;
+        if (inb) role[k - sub_start] = -1 - tid;
+    }
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
-    __syncthreads();
     for (int di = tid; di < n_data; di += 256) role[T->data_k[di] - sub_start] = di;
+    __syncthreads();
     float my_mx = 0.f;
     // ---- channel from the CE symbol (warp 0: both half-warps transform it, the lower one keeps the result; the warp-wide
     //      shuffles and barriers inside need all 32 lanes); the other warps gather the peak over preamble-1, preamble-2 and
@@ -716,7 +726,7 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
             const float ih = rsqrtf(hm);
             if (hw == 0) {
                 Gq[kk] = make_float2(hr / hm, -hi / hm);
-                invH[kk] = ih;
+                cH[kk] = 8e-5f * ih;
                 dH[kk] = 8e-5f * S * ih;
             }
         }
@@ -730,32 +740,48 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
             my_mx = fmaxf(my_mx, fabsf(v));
         }
     }
-    __syncthreads();
-    // ---- data symbols
+    // ---- data symbols.  In the first round warps 1..7 transform their symbols while warp 0 is still busy with the channel:
+    //      the barrier sits between their transform and their equaliser.
     const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
     float2* buf = hwbuf + hw * AMB_FD_HWBUF;
+    float* pe = reinterpret_cast<float*>(s_pilot[hw]);                   // pilot bins of the symbol in flight: (re, im, bound)
     const float thr = (float)T->qam_thr;
+    const int n_pilots = T->n_pilots;
     for (int s0 = g0; s0 < s_end; s0 += AMB_FD_HW) {
         const int sidx = s0 + hw;
         const bool active = sidx < s_end;                               // uniform per half-warp
         const int sx = active ? sidx : s_end - 1;
         const int64_t p0 = J.data_pos + (int64_t)sx * sym + cp;
         const bool inside = p0 - cp >= J.lo && p0 + AMB_FFT <= J.hi;
-        float S;
-        float smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
+        // the cyclic prefix only counts for the peak: issue the loads of its first 64 samples now, use them after the transform
+        float cpv[AMB_FD_CPV];
         if (folded) {
-            for (int i = l; i < cp; i += 16) {                          // the cyclic prefix only counts for the peak
-                const int64_t g = p0 - cp + i;
-                const float v = (inside || (g >= J.lo && g < J.hi)) ? J.p[g - J.base] : 0.f;
+#pragma unroll
+            for (int q = 0; q < AMB_FD_CPV; q++) {
+                const int i = l + 16 * q;
+                const int64_t gq = p0 - cp + i;
+                cpv[q] = (i < cp && (inside || (gq >= J.lo && gq < J.hi))) ? J.p[gq - J.base] : 0.f;
+            }
+        }
+        float S = 0.f, smx = 0.f;
+        const bool first_round = s0 == g0;
+        if (!(first_round && warp == 0)) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
+        if (first_round) {
+            __syncthreads();                                            // channel tables ready
+            if (warp == 0) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
+        }
+        if (folded) {
+#pragma unroll
+            for (int q = 0; q < AMB_FD_CPV; q++) smx = fmaxf(smx, fabsf(cpv[q]));
+            for (int i = 16 * AMB_FD_CPV + l; i < cp; i += 16) {             // longer prefixes (acoustic, narrowband)
+                const int64_t gq = p0 - cp + i;
+                const float v = (inside || (gq >= J.lo && gq < J.hi)) ? J.p[gq - J.base] : 0.f;
                 smx = fmaxf(smx, fabsf(v));
             }
             if (active) my_mx = fmaxf(my_mx, smx);
         }
-        // equalised bins of this lane: kk = l + 16 i
+        // equalised bins of this lane: kk = l + 16 i; pilot bins also go to shared memory for the phase estimate
         float2 E[AMB_FD_ITERS];
-        float ph_sum = 0.f, ptol = 0.f;
-        int pc = 0;
-        bool bad = false;
 #pragma unroll
         for (int i = 0; i < AMB_FD_ITERS; i++) {
             const int kk = l + 16 * i;
@@ -763,18 +789,27 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
             if (kk < nb) {
                 const float2 e = cmulf(fd_split(buf, tw512, sub_start + kk), Gq[kk]);
                 E[i] = e;
-                if (role[kk] < 0) {                                     // pilot (modem.js:398-405)
-                    const float dk = 8e-5f * S * invH[kk] + (fabsf(e.x) + fabsf(e.y)) * dH[kk];     // bound on |e - exact|
-                    const float ar = fabsf(e.x);
-                    if (!(fabsf(ar - 1e-6f) > dk)) bad = true;          // the |eqRe| > 1e-6 test could flip (also catches NaN)
-                    if (ar > 1e-6f) {
-                        ph_sum += e.y / e.x; pc++;
-                        ptol += dk * (1.f + fabsf(e.y) / ar) / ar;      // d(eqIm/eqRe)
-                    }
+                const int rl = role[kk];
+                if (rl < 0) {
+                    float* o = pe + 4 * (-1 - rl);
+                    o[0] = e.x; o[1] = e.y; o[2] = S * cH[kk] + (fabsf(e.x) + fabsf(e.y)) * dH[kk];      // bound on |e - exact|
                 }
             }
         }
         __syncwarp();
+        // pilot phase (modem.js:398-405): lane q takes pilot q
+        float ph_sum = 0.f, ptol = 0.f;
+        int pc = 0;
+        bool bad = false;
+        if (l < n_pilots && pilot_in_band[l]) {
+            const float ex = pe[4 * l], ey = pe[4 * l + 1], dk = pe[4 * l + 2];
+            const float ar = fabsf(ex);
+            if (!(fabsf(ar - 1e-6f) > dk)) bad = true;                  // the |eqRe| > 1e-6 test could flip (also catches NaN)
+            if (ar > 1e-6f) {
+                ph_sum = ey / ex; pc = 1;
+                ptol = dk * (1.f + fabsf(ey) / ar) / ar;                // d(eqIm/eqRe)
+            }
+        }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
             ph_sum += __shfl_xor_sync(0xffffffffu, ph_sum, o);
@@ -783,15 +818,17 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
         }
         const float phase = pc > 0 ? ph_sum / (float)pc : 0.f;
         const float dphase = pc > 0 ? ptol / (float)pc + 2e-6f * fabsf(phase) : 0.f;
+        const float ph1 = 1.f + fabsf(phase);
         uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sx * n_data;
 #pragma unroll
         for (int i = 0; i < AMB_FD_ITERS; i++) {
             const int kk = l + 16 * i;
-            if (kk < nb && role[kk] >= 0) {
+            const int rl = kk < nb ? role[kk] : -1;
+            if (rl >= 0) {
                 const float2 e = E[i];
                 const float cr = e.x + e.y * phase, ci = e.y - e.x * phase;
                 const float mag = fabsf(e.x) + fabsf(e.y);
-                const float tol = 1e-3f + (8e-5f * S * invH[kk] + mag * dH[kk]) * (1.f + fabsf(phase)) + mag * dphase + 1e-5f * mag;
+                const float tol = 1e-3f + (S * cH[kk] + mag * dH[kk]) * ph1 + mag * (dphase + 1e-5f);
                 int idx;
                 float margin;
                 if (mod == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
@@ -804,7 +841,7 @@ __global__ void __launch_bounds__(256) k_demod_fast(const AmbTables* __restrict_
                     margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
                 }
                 if (!(margin > tol)) bad = true;                        // also catches NaN
-                if (active) idx_out[role[kk]] = (uint8_t)idx;
+                if (active) idx_out[rl] = (uint8_t)idx;
             }
         }
         const unsigned bm = __ballot_sync(0xffffffffu, bad);
