@@ -45,6 +45,7 @@ struct amb_modem {
     AmbFastTables* d_fast = nullptr;
     unsigned long long* d_fallbacks = nullptr;
     bool fast_demod = true;
+    bool fused_front = true;
     std::string err;
     int64_t launches = 0;
     // optional per-kernel device timing (CUDA events on the handle's stream)
@@ -262,6 +263,9 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     for (int k = 0; k < AMB_CHUNK; k++) e.w_in[k] = (double)((long double)m->tables.dc_beta * powl(a, (long double)(AMB_CHUNK - 1 - k)));
     for (int j = 0; j <= AMB_EMA_TERMS; j++) e.w_chunk[j] = (double)powl(a, (long double)(AMB_CHUNK * j));
     e.a16 = (double)powl(a, 16.0L); e.alpha = m->tables.dc_alpha; e.beta = m->tables.dc_beta;
+    for (int i = 0; i < 32; i++) e.lanepow[i] = (double)powl(a, 16.0L * i);
+    for (int k = 0; k < 5; k++) e.steppow[k] = (double)powl(a, 16.0L * (1 << k));
+    e.a8 = (double)powl(a, 8.0L);
     if (cudaMemcpy(m->d_tables, &m->tables, sizeof(AmbTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
     if (cudaMemcpy(m->d_ema, &e, sizeof(e), cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
     {
@@ -274,8 +278,11 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
+        const char* f = std::getenv("AMB_FUSED_FRONT");
+        m->fused_front = !(f && f[0] == '0');
     }
     cudaFuncSetAttribute(k_demod_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
@@ -711,25 +718,38 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         else CK(cudaMemcpy2DAsync(m->raw.p, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
                                   mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
     }
-    // 1. DC removal
-    const int64_t n_chunks = n_new / AMB_CHUNK;
-    const int per = blocks_for(n_chunks, 4);
-    LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(src, src_stride, n_chunks, per, m->d_ema, m->agg.as<double>()));
-    LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(src, src_stride, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
-                                                 m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
-    // 2. window-sum summaries of the new window-end samples
     const int tiles = (int)(n_new / AMB_TILE);
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
     CK(cudaMemsetAsync(m->tile_slot.p, 0xFF, (size_t)ns * m->sum_stride * 4, m->stream));      // history tiles: no slot (-1)
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
-    {
+    if (m->fused_front) {
+        // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
+        AmbFrontArgs fa;
+        fa.x = src; fa.x_stride = src_stride; fa.cleaned = m->cleaned.as<float>(); fa.stride = m->stride; fa.off0 = off0;
+        fa.tiles = tiles;
+        // spans: enough CTAs to fill the GPU, long enough that the 10-tile warm-up of the EMA state stays a small part
+        int64_t span = ((int64_t)ns * tiles + 148 * 3 - 1) / (148 * 3);      // one wave of 3 CTAs per SM
+        if (span < 16) span = 16;
+        if (span > tiles) span = tiles;
+        fa.span = (int)span; fa.spans = (int)((tiles + span - 1) / span); fa.warm = 10;
+        fa.E = m->d_ema; fa.states = m->states.as<AmbStreamState>(); fa.dc_next = m->dc_next.as<double>();
+        fa.sums = m->sums.as<float>(); fa.sum_stride = m->sum_stride; fa.st = ss;
+        LAUNCH("k_front", k_front<<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa));
+    } else {
+        // 1. DC removal
+        const int64_t n_chunks = n_new / AMB_CHUNK;
+        const int per = blocks_for(n_chunks, 4);
+        LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(src, src_stride, n_chunks, per, m->d_ema, m->agg.as<double>()));
+        LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(src, src_stride, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
+                                                     m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
+        // 2. window-sum summaries of the new window-end samples
         const int64_t n_warps = (int64_t)ns * tiles;
         LAUNCH("k_scan_fast", k_scan_fast<<<blocks_for(n_warps, 8), 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(),
                                                                                         m->sum_stride, ss, n_warps));
-        LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < 148 * 16 ? (m->slot_cap + 3) / 4 : 148 * 16, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
     }
+    LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < 148 * 16 ? (m->slot_cap + 3) / 4 : 148 * 16, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
     {
         const int64_t n_calls = n_new / AMB_TILE;
         const int parts = (int)((n_calls + AMB_DEFECT_PART - 1) / AMB_DEFECT_PART);

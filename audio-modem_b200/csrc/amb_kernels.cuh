@@ -54,6 +54,9 @@ struct AmbEmaTables {
     double w_chunk[AMB_EMA_TERMS + 1]; // alpha^(512 j)
     double a16;                        // alpha^16
     double alpha, beta;
+    double lanepow[32];                // alpha^(16 i)
+    double steppow[5];                 // alpha^(16 * 2^k)
+    double a8;                         // alpha^8
 };
 
 __global__ void k_ema_agg(const float* __restrict__ x, int64_t x_stride, int64_t n_chunks, int per,
@@ -280,6 +283,246 @@ __global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cle
         for (int k = 0; k < 8; k++) { X0[k] = X1[k]; X1[k] = X2[k]; PQ0[k] = PQ1[k]; PQ1[k] = PQ2[k]; PT0[k] = PT1[k]; }
         TQ0 = TQ1; TQ1 = TQ2; TT0 = TT1;
     }
+}
+
+// ================================================================================================
+// k_front: the streaming front end in one pass over the new samples - EMA DC removal (app.js:750-755) and the
+// Schmidl-Cox tile summaries the walker screens with.  One CTA walks a span of consecutive 4096-sample tiles of one
+// stream; thread t owns samples 16 t .. 16 t + 15 of every tile.
+//   EMA: m <- alpha m + beta x is linear, so each thread first runs its 16 samples from a zero state, a warp scan
+//   (weights alpha^(16 2^k)) and an 8-step chain over the warp totals give the state entering every thread, and a
+//   second 16-step run produces cleaned = f32(x - m).  A span that does not start at the push start warms the state up
+//   over the 10 tiles before it (alpha^40960 ~ 1.6e-18: older samples cannot change a float64 state).
+//   Summaries: with q_e = sum c^2, t_e = sum c[i-256] c[i], a_e = sum |c[i-256] c[i]| over the 16-sample sub-block e,
+//   every window starting in sub-block j = e - 32 (at 16 j + r, 0 <= r <= 16) obeys
+//       Ra in [Q(j,j+16) - q_j, Q(j,j+16) + q_{j+16}],  Rb in [Q(j+16,j+32) - q_{j+16}, Q(j+16,j+32) + q_e],
+//       |P| <= |T(j+16,j+32)| + a_{j+16} + a_e,
+//   (Q, T: sums over whole sub-blocks, from block-wide prefix sums).  The 16 sub-blocks e of a 256-sample summary
+//   tile cover exactly its window-end samples, so the tile summary {max|P|, min/max Ra, min/max Rb} is the
+//   half-warp reduction of these bounds: conservative (the walker only uses it to skip tiles), ~10 instructions per
+//   sample, and no per-window work at all.  Tiles the walker could enter get a slot; k_tri_store then computes their
+//   exact float64 window sums.
+// Replaces k_ema_agg + k_ema_apply + k_scan_fast: the samples are read once and cleaned is written once.
+// ================================================================================================
+struct AmbFrontArgs {
+    const float* x; int64_t x_stride;                 // rows of this push
+    float* cleaned; int64_t stride, off0;             // arena; the push starts at arena index off0
+    int tiles, span, spans, warm;                     // tiles in the push, tiles per CTA, CTAs per stream, warm-up tiles
+    const AmbEmaTables* E; const AmbStreamState* states; double* dc_next;
+    float* sums; int64_t sum_stride;
+    AmbScanStore st;
+};
+
+#define AMB_FR_PAD(i) ((i) + (((i) >> 4) << 2))       // 4 floats of padding per 16: conflict-free 128-bit rows per thread
+#define AMB_FR_BUF AMB_FR_PAD(AMB_TILE)               // floats per padded tile buffer (5120)
+#define AMB_FRONT_SMEM (3 * AMB_FR_BUF * 4)           // two cleaned tiles (double buffer) + one staged input tile
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Shared-memory layout: cleaned tiles are double-buffered (tile n in buffer n & 1), so the 256 samples and the 32
+// sub-block sums a tile needs from its predecessor are read in place and nothing is shifted; the per-sub-block arrays
+// hold q, a and the warp-inclusive scans of q and t, from which any block-wide prefix is one addition away.  The next
+// tile's input is copied global -> shared asynchronously (cp.async, coalesced) while the current one is processed.
+// Three barriers per tile.
+__global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* R = reinterpret_cast<float*>(smem_raw);                     // [2][AMB_FR_BUF]
+    float* XS = R + 2 * AMB_FR_BUF;                                    // [AMB_FR_BUF] staged input
+    __shared__ float sq[2][256], sa[2][256], sT[2][256], sI[2][256], sJ[2][256];   // q_e, a_e, t_e, warp-inclusive scans of q_e and t_e
+    __shared__ float sWq[2][8], sWt[2][8];                             // warp totals of q and t
+    __shared__ double sW[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x / a.spans, p = blockIdx.x % a.spans;
+    const int t0 = p * a.span, t1 = min(a.tiles, t0 + a.span);
+    if (t0 >= t1) return;
+    const AmbEmaTables* E = a.E;
+    const double alpha = E->alpha, beta = E->beta, a512 = E->w_chunk[1];
+    const double lp = E->lanepow[lane];
+    const float* xrow = a.x + (int64_t)s * a.x_stride;
+    float* crow = a.cleaned + (int64_t)s * a.stride + a.off0;
+    const int tb = t0 - a.warm > 0 ? t0 - a.warm : 0;
+    double m_tile = tb == 0 ? a.states[s].dc_mean : 0.0;
+    // ---- history of the scan part: lives in buffer 1 (the first full tile goes to buffer 0)
+    for (int i = tid; i < 2 * AMB_FR_BUF; i += 256) R[i] = 0.f;
+    sq[0][tid] = sa[0][tid] = sT[0][tid] = sI[0][tid] = sJ[0][tid] = 0.f;
+    sq[1][tid] = sa[1][tid] = sT[1][tid] = sI[1][tid] = sJ[1][tid] = 0.f;
+    if (tid < 8) { sWq[0][tid] = sWt[0][tid] = sWq[1][tid] = sWt[1][tid] = 0.f; }
+    __syncthreads();
+    if (t0 == 0) {
+        // push start: the 768 cleaned samples before it come from the arena (zeros before the stream start)
+        R[AMB_FR_BUF + AMB_FR_PAD(AMB_TILE - 256 + tid)] = crow[tid - 256];
+        if (tid == 0) R[AMB_FR_BUF + AMB_FR_PAD(AMB_TILE - 512)] = crow[-512];
+        if (tid < 32) {
+            float q = 0.f, tt = 0.f, at = 0.f;
+            for (int k = 0; k < 16; k++) {
+                const float c = crow[16 * (tid - 32) + k], pr = crow[16 * (tid - 32) + k - 256];
+                q = fmaf(c, c, q); tt = fmaf(pr, c, tt); at += fabsf(pr * c);
+            }
+            float iq = q, it = tt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float uq = __shfl_up_sync(0xffffffffu, iq, o), ut = __shfl_up_sync(0xffffffffu, it, o);
+                if (lane >= o) { iq += uq; it += ut; }
+            }
+            sq[1][224 + tid] = q; sa[1][224 + tid] = at; sT[1][224 + tid] = tt; sI[1][224 + tid] = iq; sJ[1][224 + tid] = it;
+            if (tid == 31) { sWq[1][7] = iq; sWt[1][7] = it; }
+        }
+    }
+    // stage the first tile's input
+    {
+        const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)tb * AMB_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; cp_async16(XS + AMB_FR_PAD(4 * f), src + f); }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    int n = 0;                                                          // full tiles done: the current one uses buffer n & 1
+    for (int t = tb; t < t1; t++) {
+        const bool ema_only = t < t0 - 1;
+        const bool emit = t >= t0;
+        // ---- this thread's 16 input samples (staged), then start staging the next tile
+        float x[16];
+        {
+            const float4* src = reinterpret_cast<const float4*>(XS + AMB_FR_PAD(16 * tid));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) { const float4 v = src[q4]; x[4 * q4] = v.x; x[4 * q4 + 1] = v.y; x[4 * q4 + 2] = v.z; x[4 * q4 + 3] = v.w; }
+        }
+        // ---- EMA over the tile: response of the 16 samples from a zero state (two independent chains of 8) ...
+        double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { r1 = fma(alpha, r1, beta * (double)x[k]); r2 = fma(alpha, r2, beta * (double)x[8 + k]); }
+        const double a8 = E->a8;
+        double B = fma(a8, r1, r2);
+#pragma unroll
+        for (int k = 0; k < 5; k++) { const double u = __shfl_up_sync(0xffffffffu, B, 1 << k); if (lane >= (1 << k)) B = fma(E->steppow[k], u, B); }
+        if (lane == 31) sW[warp] = B;
+        __syncthreads();                                                // (1) warp totals; every thread has read its staged input
+        if (t + 1 < t1) {
+            const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)(t + 1) * AMB_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; cp_async16(XS + AMB_FR_PAD(4 * f), src + f); }
+        }
+        double S = m_tile, m_next = m_tile;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { m_next = fma(a512, m_next, sW[w]); if (w + 1 == warp) S = m_next; }
+        m_tile = m_next;
+        if (ema_only) { cp_async_wait_all(); __syncthreads(); continue; }
+        // ... then the true state entering the thread, and the cleaned samples (two chains again)
+        const double Bex = __shfl_up_sync(0xffffffffu, B, 1);
+        double mA = fma(lp, S, lane ? Bex : 0.0);
+        double mB = fma(a8, mA, r1);
+        float c[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            mA = fma(alpha, mA, beta * (double)x[k]); c[k] = (float)((double)x[k] - mA);
+            mB = fma(alpha, mB, beta * (double)x[8 + k]); c[8 + k] = (float)((double)x[8 + k] - mB);
+        }
+        float* Rc = R + (n & 1) * AMB_FR_BUF;                           // this tile
+        const float* Rp = R + ((n + 1) & 1) * AMB_FR_BUF;               // its predecessor
+        const int cb = n & 1, pb = (n + 1) & 1;
+        {
+            float4* dst = reinterpret_cast<float4*>(Rc + AMB_FR_PAD(16 * tid));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) dst[q4] = make_float4(c[4 * q4], c[4 * q4 + 1], c[4 * q4 + 2], c[4 * q4 + 3]);
+        }
+        __syncthreads();                                                // (2) cleaned tile in shared memory
+        if (emit) {
+            float4* g = reinterpret_cast<float4*>(crow + (int64_t)t * AMB_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; g[f] = *reinterpret_cast<const float4*>(Rc + AMB_FR_PAD(4 * f)); }
+        }
+        // ---- sub-block sums against the partner samples 256 behind
+        float q = 0.f, tt = 0.f, at = 0.f;
+        {
+            const float4* pr4 = tid < 16 ? reinterpret_cast<const float4*>(Rp + AMB_FR_PAD(AMB_TILE - 256 + 16 * tid))
+                                         : reinterpret_cast<const float4*>(Rc + AMB_FR_PAD(16 * (tid - 16)));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+                const float4 v = pr4[q4];
+                const float pr[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float cc = c[4 * q4 + k], pc = pr[k] * cc;
+                    q = fmaf(cc, cc, q); tt += pc; at += fabsf(pc);
+                }
+            }
+        }
+        float iq = q, it = tt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float uq = __shfl_up_sync(0xffffffffu, iq, o), ut = __shfl_up_sync(0xffffffffu, it, o);
+            if (lane >= o) { iq += uq; it += ut; }
+        }
+        sq[cb][tid] = q; sa[cb][tid] = at; sT[cb][tid] = tt; sI[cb][tid] = iq; sJ[cb][tid] = it;
+        if (lane == 31) { sWq[cb][warp] = iq; sWt[cb][warp] = it; }
+        cp_async_wait_all();
+        __syncthreads();                                                // (3) sub-block arrays; the next input tile is staged
+        if (emit) {
+            // block-wide exclusive prefixes, relative to the tile start: QS(e) = off(warp of e) + sI[e] - sq[e]; in the
+            // predecessor's last warp (e < 0): QS(e) = sI_p[256 + e] - sq_p[256 + e] - sWq_p[7]
+            float oq = 0.f, ot = 0.f, totq = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const float wq = sWq[cb][w]; if (w < warp) { oq += wq; ot += sWt[cb][w]; } totq += wq; }
+            const float QSe = oq + iq - q, TSe = ot + it - tt;
+            float QS16, TS16, QS32, q16, a16v, q32;
+            {
+                const int e = tid - 16;
+                if (e >= 0) {
+                    const bool same = (e >> 5) == warp;
+                    const float o2 = same ? oq : oq - sWq[cb][warp - 1], o2t = same ? ot : ot - sWt[cb][warp - 1];
+                    q16 = sq[cb][e]; a16v = sa[cb][e]; QS16 = o2 + sI[cb][e] - q16; TS16 = o2t + sJ[cb][e] - sT[cb][e];
+                } else {
+                    const int k = 256 + e;
+                    q16 = sq[pb][k]; a16v = sa[pb][k]; QS16 = sI[pb][k] - q16 - sWq[pb][7]; TS16 = sJ[pb][k] - sT[pb][k] - sWt[pb][7];
+                }
+            }
+            {
+                const int e = tid - 32;
+                if (e >= 0) { q32 = sq[cb][e]; QS32 = (oq - sWq[cb][warp - 1]) + sI[cb][e] - q32; }
+                else { const int k = 256 + e; q32 = sq[pb][k]; QS32 = sI[pb][k] - q32 - sWq[pb][7]; }
+            }
+            const float Aal = QS16 - QS32, Bal = QSe - QS16, Pal = TSe - TS16;
+            float mxA = Aal + q16, mnA = Aal - q32, mxB = Bal + q, mnB = Bal - q16;
+            float mxP = fabsf(Pal) + a16v + at;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, o)); mnA = fminf(mnA, __shfl_xor_sync(0xffffffffu, mnA, o));
+                mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, o)); mnB = fminf(mnB, __shfl_xor_sync(0xffffffffu, mnB, o));
+                mxP = fmaxf(mxP, __shfl_xor_sync(0xffffffffu, mxP, o));
+            }
+            if ((tid & 15) == 0) {
+                const float err = 4e-6f * (totq + sWq[pb][7]) + 1e-12f;     // float32 prefix sums over the tile and its history
+                const int64_t a0 = a.off0 + (int64_t)t * AMB_TILE;
+                const int64_t tix = (int64_t)s * a.sum_stride + ((a0 >> 8) + (tid >> 4));
+                float* o = a.sums + tix * AMB_SUM_W;
+                o[0] = mxP + err; o[1] = fmaxf(mnA - err, 0.f); o[2] = mxA + err; o[3] = fmaxf(mnB - err, 0.f); o[4] = mxB + err;
+                // Slots go to the tiles the walker's summary test (amb_tile_hot) could send it into, widened for the defect it
+                // may carry; without a slot the walker evaluates the tile's windows itself.
+                const float pw = o[0] * 1.05f;
+                const bool wide = o[2] * 1.05f > 0.0009f && o[4] * 1.05f > 0.0009f &&
+                                  pw * pw > 0.4f * fmaxf(o[1] * 0.95f, 0.0009f) * fmaxf(o[3] * 0.95f, 0.0009f);
+                if (a.st.tile_slot && wide) {
+                    int slot = atomicAdd(a.st.slot_count, 1);
+                    if (slot >= a.st.slot_cap) slot = -1;
+                    else { a.st.slot_info[slot * 4] = s; a.st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + (tid >> 4)); a.st.slot_info[slot * 4 + 2] = 0; a.st.slot_info[slot * 4 + 3] = 0; }
+                    a.st.tile_slot[tix] = slot;
+                }
+            }
+            if (tid == 0 && a.st.defect) {
+                // defect of the block boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
+                const int64_t a0 = a.off0 + (int64_t)t * AMB_TILE;
+                const double xm1 = Rp[AMB_FR_PAD(AMB_TILE - 512)], x255 = Rp[AMB_FR_PAD(AMB_TILE - 256)], x511 = c[0];
+                double* D = a.st.defect + ((int64_t)s * a.st.calls_stride + (a0 >> 12)) * 3;
+                D[0] = xm1 * x255 - x255 * x511; D[1] = xm1 * xm1 - x255 * x255; D[2] = x255 * x255 - x511 * x511;
+            }
+        }
+        n++;
+    }
+    if (t1 == a.tiles && tid == 0) a.dc_next[s] = m_tile;
 }
 
 // Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
