@@ -41,12 +41,12 @@ UNIT = "Msamples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=int(os.environ.get("AMB_FRAMES_PER_STEP", "4096")))
     ap.add_argument("--segments", type=int, default=4, help="distinct resident input segments cycled through")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -127,39 +127,58 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up until after the last timed leg;
+    only the samples taken between mark_begin() and mark_end() (GPU under load: warm-up, timed steps, profiling pass,
+    end-to-end leg) are summarised."""
+    Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
+
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, reasons, all_sm = [], [], [], set(), []
         for ln in out.strip().splitlines():
             f = [c.strip() for c in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                v_sm, v_mx, v_pw = float(f[2]), float(f[3]), float(f[4])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            all_sm.append(v_sm)
+            if self.t0 is not None and self.t1 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                continue
+            sm.append(v_sm); mx.append(v_mx); pw.append(v_pw)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if not sm and all_sm:      # clock skew between nvidia-smi's timestamps and time.time(): fall back to every sample
+            sm = all_sm
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -181,6 +200,8 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -231,6 +252,7 @@ def run_b200(args, rank, world, local_rank):
     d_res = torch.empty(cap * 88, dtype=torch.uint8, device=dev)
     d_bytes = torch.empty((cap, m.bytes_stride), dtype=torch.uint8, device=dev)
     dres = (d_res, d_bytes)
+    clocks.mark_begin()
     for w in range(args.warmup):
         m.stream_push(segs[w % len(segs)], device_results=dres)
     m.synchronize()
@@ -238,8 +260,6 @@ def run_b200(args, rank, world, local_rank):
     c0 = m.stream_counters()
     if dist:
         dist.barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     launches0 = m.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
@@ -252,7 +272,6 @@ def run_b200(args, rank, world, local_rank):
     if dist:
         dist.barrier()
     dev_ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
     launches = m.kernel_launches - launches0
     c1 = m.stream_counters()
     decoded = c1["framesDecoded"] - c0["framesDecoded"]
@@ -287,6 +306,9 @@ def run_b200(args, rank, world, local_rank):
     m.synchronize()
     e2e_s = time.perf_counter() - t0
     assert e2e_frames == args.e2e_steps * F, e2e_frames
+    clocks.mark_end()
+    clk = clocks.stop()
+    clk["window"] = "warm-up + timed steps + profiling pass + end-to-end leg (the same workload throughout)"
     d2h = F * (m.bytes_stride + 88)
     m.stream_close()
     del hx
@@ -304,14 +326,24 @@ def run_b200(args, rank, world, local_rank):
     # roofline of the dominant kernel (largest share of the timed region on this rank)
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     algo_step = 4 * step_samples + F * (CHUNK + 64)                 # 4 B/sample once + payload + 64 B result per frame
-    per_launch = {"k_demod": F * (4 * 44 * 576 + CHUNK + 64), "k_demod_fast": F * (4 * 44 * 576 + CHUNK + 64), "k_parse": F * (4202 + CHUNK + 64), "k_frame_max": F * 4 * CORE}
+    per_launch = {"k_demod": F * (4 * 44 * 576 + CHUNK + 64), "k_demod_fast": F * (4 * 44 * 576 + CHUNK + 64), "k_front": 4 * step_samples, "k_parse": F * (4202 + CHUNK + 64), "k_frame_max": F * 4 * CORE}
     roof = None
     if dom:
         name, (ms, cnt) = dom
         b = per_launch.get(name, 4 * step_samples)
         achieved = b / (ms / cnt / 1e3) / 1e9
+        # measured DRAM traffic of that kernel (ncu --set full capture committed under profiles/), scaled to this launch
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json"))).get(name)
+            if tj and "dram_bytes_per_frame" in tj:
+                traffic = tj["dram_bytes_per_frame"] * F
+            elif tj and "dram_bytes_per_sample" in tj:
+                traffic = tj["dram_bytes_per_sample"] * step_samples
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "mean_launch_ms": ms / cnt,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "mean_launch_ms": ms / cnt,
                 "share_of_step": ms / prof_ms,
                 "whole_step": {"algorithmic_bytes": algo_step, "achieved": algo_step * args.steps / (dev_ms / 1e3) / 1e9,
                                "frac": algo_step * args.steps / (dev_ms / 1e3) / 1e9 / hbm_peak},
