@@ -67,6 +67,8 @@ struct amb_modem {
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     DevBuf l_first, l_firstflag, l_firststop, l_fpsum;
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
+    cudaStream_t copy_stream = nullptr;          // host->device copies of sectioned pushes
+    std::vector<cudaEvent_t> copy_events;
     int run_cap = 0;
     int64_t link_iterations = 0, link_passes = 0;
     int slot_cap = 0, xc_w = 0;
@@ -309,6 +311,8 @@ void amb_destroy(amb_modem* m) {
     if (m->d_fast) cudaFree(m->d_fast);
     if (m->d_fallbacks) cudaFree(m->d_fallbacks);
     if (m->h_counts) cudaFreeHost(m->h_counts);
+    for (cudaEvent_t e : m->copy_events) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -695,29 +699,13 @@ static int stream_compact(amb_modem* m) {
     return AMB_OK;
 }
 
-int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
-                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
-    if (!m) return AMB_E_INVALID;
-    m->pending.clear();
-    if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
-    if (n_new <= 0 || n_new > m->max_push || n_new % m->block_len) return fail(m, AMB_E_INVALID, "n_new must be a positive multiple of block_len, at most max_push");
-    if (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE && mem != AMB_MEM_INPLACE) return fail(m, AMB_E_INVALID, "bad mem");
-    if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
-    if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
-    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+// One push of n_new samples per stream, read from device memory (src rows 16-byte aligned).
+static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t n_new, amb_frame_result* results,
+                     int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
     const AmbTables& T = m->tables;
     const int ns = m->n_streams;
     const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
-    // samples are read where they are when they sit in device memory with 16-byte aligned rows; otherwise they are staged
-    const float* src = m->raw.as<float>();
-    int64_t src_stride = m->max_push;
-    if (mem != AMB_MEM_INPLACE) {
-        if (!x) return fail(m, AMB_E_INVALID, "x required");
-        if (mem == AMB_MEM_DEVICE && ((uintptr_t)x & 15) == 0 && (x_stride & 3) == 0) { src = x; src_stride = x_stride; }
-        else CK(cudaMemcpy2DAsync(m->raw.p, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
-                                  mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
-    }
     const int tiles = (int)(n_new / AMB_TILE);
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
@@ -886,6 +874,59 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     // history compaction is queued behind everything else; the next call on this handle is ordered after it
     if ((rc = stream_compact(m))) return rc;
     return overflow ? AMB_E_OVERFLOW : AMB_OK;
+}
+
+int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
+    if (!m) return AMB_E_INVALID;
+    m->pending.clear();
+    if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
+    if (n_new <= 0 || n_new > m->max_push || n_new % m->block_len) return fail(m, AMB_E_INVALID, "n_new must be a positive multiple of block_len, at most max_push");
+    if (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE && mem != AMB_MEM_INPLACE) return fail(m, AMB_E_INVALID, "bad mem");
+    if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
+    if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
+    if (mem != AMB_MEM_INPLACE && !x) return fail(m, AMB_E_INVALID, "x required");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    const int ns = m->n_streams;
+    // samples are read where they are when they sit in device memory with 16-byte aligned rows; otherwise they are staged
+    if (mem == AMB_MEM_DEVICE && ((uintptr_t)x & 15) == 0 && (x_stride & 3) == 0)
+        return push_core(m, x, x_stride, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
+    float* raw = m->raw.as<float>();
+    if (mem == AMB_MEM_INPLACE) return push_core(m, raw, m->max_push, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
+    // Large host pushes are cut into sections: all host->device copies are queued at once on a second stream, and
+    // section k is processed (as a push of its own: same results, the receiver state carries over) while the sections
+    // after it are still in flight.
+    const int64_t blocks = n_new / m->block_len;
+    int64_t n_sec = 1;
+    if (mem == AMB_MEM_HOST && (int64_t)ns * n_new * 4 >= (64ll << 20) && blocks >= 8) n_sec = 8;
+    if (n_sec == 1) {
+        CK(cudaMemcpy2DAsync(raw, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
+                             mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
+        return push_core(m, raw, m->max_push, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
+    }
+    if (!m->copy_stream) CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    while ((int64_t)m->copy_events.size() < n_sec) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->copy_events.push_back(e); }
+    const int64_t sec_blocks = (blocks + n_sec - 1) / n_sec;
+    std::vector<int64_t> sec_off, sec_len;
+    for (int64_t b = 0; b < blocks; b += sec_blocks) { sec_off.push_back(b * m->block_len); sec_len.push_back((b + sec_blocks < blocks ? sec_blocks : blocks - b) * m->block_len); }
+    // the staging buffer is free: the previous push synchronised after its last reader
+    for (size_t k = 0; k < sec_off.size(); k++) {
+        CK(cudaMemcpy2DAsync(raw + sec_off[k], (size_t)m->max_push * 4, x + sec_off[k], (size_t)x_stride * 4, (size_t)sec_len[k] * 4, ns, cudaMemcpyHostToDevice, m->copy_stream));
+        CK(cudaEventRecord(m->copy_events[k], m->copy_stream));
+    }
+    int total = 0, rc_all = AMB_OK;
+    for (size_t k = 0; k < sec_off.size(); k++) {
+        CK(cudaStreamWaitEvent(m->stream, m->copy_events[k], 0));
+        const int room = max_results - total > 0 ? max_results - total : 0;
+        int got = 0;
+        const int rc = push_core(m, raw + sec_off[k], m->max_push, sec_len[k], results ? results + (total < max_results ? total : max_results) : nullptr, room, &got,
+                                 bytes_out ? bytes_out + (size_t)(total < max_results ? total : max_results) * bytes_stride : nullptr, bytes_stride, results_mem);
+        if (rc != AMB_OK && rc != AMB_E_OVERFLOW) return rc;
+        if (rc == AMB_E_OVERFLOW) rc_all = AMB_E_OVERFLOW;
+        total += got;
+    }
+    *n_results = total;
+    return rc_all;
 }
 
 // ---------------------------------------------------------------------------------------------- transmit side
