@@ -599,7 +599,12 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     // the refine radius and a tile of slack, rounded to whole tiles
     int64_t h = m->ring_cap + block_len + T.fine_radius + T.sym_len + 2 * AMB_TILE;
     m->hist = (h + AMB_TILE - 1) / AMB_TILE * AMB_TILE;
-    m->stride = m->hist + max_push;
+    // the arena holds several pushes beyond the history, so the history is moved to the front only every `reps` pushes
+    // (compaction traffic stays below the push traffic even when pushes are much shorter than the history)
+    int64_t reps = (m->hist + max_push - 1) / max_push;
+    if (reps > 32) reps = 32;
+    while (reps > 1 && (double)n_streams * (double)(m->hist + reps * max_push) * 4.0 > 48e9) reps--;
+    m->stride = m->hist + reps * max_push;
     m->base_g = -m->hist;
     m->written = 0;
     m->sum_stride = m->stride / 256;
@@ -674,27 +679,29 @@ int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride) {
     return AMB_OK;
 }
 
+// rows [n_streams][pitch] -> move `bytes` bytes per row from byte offset `from` to the row start (through a scratch
+// copy when source and destination overlap)
+static int move_rows(amb_modem* m, void* base, size_t pitch, size_t from, size_t bytes) {
+    char* b = static_cast<char*>(base);
+    if (from >= bytes) {
+        CK(cudaMemcpy2DAsync(b, pitch, b + from, pitch, bytes, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+        return AMB_OK;
+    }
+    CK(m->ctmp.ensure((size_t)m->n_streams * bytes));
+    CK(cudaMemcpy2DAsync(m->ctmp.p, bytes, b + from, pitch, bytes, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaMemcpy2DAsync(b, pitch, m->ctmp.p, bytes, bytes, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    return AMB_OK;
+}
+
 static int stream_compact(amb_modem* m) {
-    // keep `hist` samples of history: move [written - hist, written) to the arena front (raw, cleaned, summaries).
-    // Source and destination rows overlap when the push was shorter than the history, so go through a scratch copy.
+    // keep `hist` samples of history: move [written - hist, written) to the arena front (cleaned, summaries, defect prefix)
     const int64_t off = m->written - m->base_g;        // arena index of the next sample
     if (off == m->hist) return AMB_OK;
     const int64_t shift = off - m->hist;               // multiple of 4096
-    const size_t row = (size_t)m->hist * 4;
-    CK(m->ctmp.ensure((size_t)m->n_streams * row));
-    float* bases[1] = {m->cleaned.as<float>()};
-    for (float* b : bases) {
-        CK(cudaMemcpy2DAsync(m->ctmp.p, row, b + shift, (size_t)m->stride * 4, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
-        CK(cudaMemcpy2DAsync(b, (size_t)m->stride * 4, m->ctmp.p, row, row, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
-    }
-    const size_t srow = (size_t)(m->hist / 256) * AMB_SUM_W * 4;
-    CK(cudaMemcpy2DAsync(m->ctmp.p, srow, m->sums.as<float>() + (shift / 256) * AMB_SUM_W, (size_t)m->sum_stride * AMB_SUM_W * 4, srow, m->n_streams,
-                         cudaMemcpyDeviceToDevice, m->stream));
-    CK(cudaMemcpy2DAsync(m->sums.p, (size_t)m->sum_stride * AMB_SUM_W * 4, m->ctmp.p, srow, srow, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
-    const size_t frow = (size_t)(m->hist / AMB_TILE) * 3 * 8;
-    CK(cudaMemcpy2DAsync(m->ctmp.p, frow, m->fpre.as<double>() + (shift / AMB_TILE) * 3, (size_t)m->calls_stride * 3 * 8, frow, m->n_streams,
-                         cudaMemcpyDeviceToDevice, m->stream));
-    CK(cudaMemcpy2DAsync(m->fpre.p, (size_t)m->calls_stride * 3 * 8, m->ctmp.p, frow, frow, m->n_streams, cudaMemcpyDeviceToDevice, m->stream));
+    int rc;
+    if ((rc = move_rows(m, m->cleaned.p, (size_t)m->stride * 4, (size_t)shift * 4, (size_t)m->hist * 4))) return rc;
+    if ((rc = move_rows(m, m->sums.p, (size_t)m->sum_stride * AMB_SUM_W * 4, (size_t)(shift / 256) * AMB_SUM_W * 4, (size_t)(m->hist / 256) * AMB_SUM_W * 4))) return rc;
+    if ((rc = move_rows(m, m->fpre.p, (size_t)m->calls_stride * 3 * 8, (size_t)(shift / AMB_TILE) * 3 * 8, (size_t)(m->hist / AMB_TILE) * 3 * 8))) return rc;
     m->base_g += shift;
     return AMB_OK;
 }
@@ -704,13 +711,15 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
                      int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
     const AmbTables& T = m->tables;
     const int ns = m->n_streams;
+    if (m->written - m->base_g + n_new > m->stride) { const int rcc = stream_compact(m); if (rcc) return rcc; }     // arena full: history to the front
     const int64_t off0 = m->written - m->base_g;       // arena index where the new samples go
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
     const int tiles = (int)(n_new / AMB_TILE);
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
-    CK(cudaMemsetAsync(m->tile_slot.p, 0xFF, (size_t)ns * m->sum_stride * 4, m->stream));      // history tiles: no slot (-1)
+    // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
+    CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
     if (m->fused_front) {
         // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
@@ -749,7 +758,8 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     // 3. walk / decode / apply, repeated for streams whose collection window changed
     AmbStreamGeom g;
     g.stride = m->stride; g.base_g = m->base_g; g.avail_hi = m->written + n_new; g.sum_stride = m->sum_stride;
-    g.sum_lo = m->base_g > 0 ? m->base_g : 0; g.block_len = m->block_len; g.ring_cap = m->ring_cap;
+    g.sum_lo = m->written - m->hist > 0 ? m->written - m->hist : 0;       // summaries and slots are kept for the last `hist` samples
+    g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
     g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w;
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
@@ -871,8 +881,6 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     const bool overflow = n_out > max_results;
     m->written += n_new;
     *n_results = n_out;
-    // history compaction is queued behind everything else; the next call on this handle is ordered after it
-    if ((rc = stream_compact(m))) return rc;
     return overflow ? AMB_E_OVERFLOW : AMB_OK;
 }
 

@@ -61,7 +61,7 @@ struct AmbWalkGeom {
 AMB_HD int amb_tile_slot_of(const AmbWalkGeom& G, int64_t j) {
     if (!G.tile_slot) return -1;
     const int64_t rel = j - (G.sum_base >> 8);
-    if (rel < 0 || rel >= G.sum_tiles) return -1;
+    if (rel < 0 || rel >= G.sum_tiles || (j << 8) < G.sum_lo) return -1;       // below sum_lo: entries of an earlier push
     return G.tile_slot[rel];
 }
 
