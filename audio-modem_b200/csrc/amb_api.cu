@@ -24,7 +24,12 @@ struct DevBuf {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) {
+            cap = want;
+            // AMB_POISON=1 (tests): fresh scratch memory starts as garbage, so a read of something no kernel wrote shows up
+            static const bool poison = std::getenv("AMB_POISON") != nullptr;
+            if (poison) cudaMemset(p, 0xCD, want);
+        }
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -761,7 +766,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     g.sum_lo = m->written - m->hist > 0 ? m->written - m->hist : 0;       // summaries and slots are kept for the last `hist` samples
     g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
-    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w;
+    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
     {
         const int L = m->xc_w + T.sym_len;

@@ -603,6 +603,7 @@ struct AmbStreamGeom {
     int rec_cap;           // frame records per stream
     // stores of the scan kernels (see AmbWalkGeom)
     const int32_t* tile_slot; const double* tri; const float* xc; int xc_w;
+    const int32_t* slot_info;
     const double* F; int64_t calls_stride;
 };
 
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     if (pre_meta_only && st.meta_received) return;
     AmbWalkGeom G;
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
@@ -2028,7 +2029,7 @@ __global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__
         }
         AmbWalkGeom G;
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-        G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w;
+        G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
         G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
         if (first) {}
         else if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);

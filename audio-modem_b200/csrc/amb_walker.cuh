@@ -49,6 +49,7 @@ struct AmbWalkGeom {
     const double* tri;          // [slot][256][3]  (P, Ra, Rb) of the tile's 256 windows
     const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
     int xc_w;
+    const int32_t* slot_info;   // [slot][4], entry 2 = the slot's xc row was computed (NULL: every row is valid or marked UNSURE)
     const double* F;            // per call: inclusive prefix of the block-boundary defect terms (3 doubles per call)
     int64_t F_call0, F_calls;   // F[(call - F_call0) * 3 + c] valid for 0 <= call - F_call0 < F_calls
 };
@@ -182,7 +183,8 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     const int64_t j = (p + 511) >> 8;
     const int slot = G.xc ? amb_tile_slot_of(G, j) : -1;
     const int64_t base = (j << 8) - 511 - T->fine_radius;
-    if (slot < 0 || lo < base || hi >= base + G.xc_w || hi < lo) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    if (slot < 0 || lo < base || hi >= base + G.xc_w || hi < lo || (G.slot_info && !G.slot_info[slot * 4 + 2]))
+        return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
     const float* v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
     const int n = (int)(hi - lo + 1);
     float mx = -3.0f;

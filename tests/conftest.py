@@ -1,7 +1,13 @@
 import os
 import sys
 
+import os
+
 import pytest
+
+# fresh device scratch memory starts as garbage in the tests, so that a read of something no kernel wrote cannot pass
+# by luck on zero-filled pages (audio-modem_b200/csrc/amb_api.cu, DevBuf::ensure)
+os.environ.setdefault("AMB_POISON", "1")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
