@@ -1,8 +1,6 @@
 import os
 import sys
 
-import os
-
 import pytest
 
 # fresh device scratch memory starts as garbage in the tests, so that a read of something no kernel wrote cannot pass
