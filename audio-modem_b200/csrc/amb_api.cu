@@ -49,6 +49,7 @@ struct amb_modem {
     AmbEmaTables* d_ema = nullptr;
     AmbFastTables* d_fast = nullptr;
     unsigned long long* d_fallbacks = nullptr;
+    uint32_t* d_crc_ops = nullptr;       // [AMB_CRC_MAXL][8] x^(8 L 2^k) mod P, the CRC combine constants per chunk length L
     bool fast_demod = true;
     bool fused_front = true;
     std::string err;
@@ -70,7 +71,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo;
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
     cudaStream_t copy_stream = nullptr;          // host->device copies of sectioned pushes
     std::vector<cudaEvent_t> copy_events;
@@ -182,7 +183,7 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
     }
     LAUNCH("k_parse", k_parse<<<n_jobs < 65536 ? n_jobs : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
-                                                          d_res, d_bytes, bytes_stride));
+                                                          d_res, d_bytes, bytes_stride, m->d_crc_ops));
     return AMB_OK;
 }
 
@@ -283,6 +284,11 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         }
         if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 8) != cudaSuccess) return bail(AMB_E_NOMEM);
         if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
+        std::vector<uint32_t> ops((size_t)AMB_CRC_MAXL * 8, 0u);
+        for (int L = 0; L < AMB_CRC_MAXL; L++)
+            for (int k = 0; k < 8; k++) ops[(size_t)L * 8 + k] = amb_gf_xpow8((uint32_t)L << k);
+        if (cudaMalloc(&m->d_crc_ops, ops.size() * 4) != cudaSuccess) return bail(AMB_E_NOMEM);
+        if (cudaMemcpy(m->d_crc_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
         const char* f = std::getenv("AMB_FUSED_FRONT");
@@ -308,13 +314,14 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
     if (m->d_ema) cudaFree(m->d_ema);
     if (m->d_fast) cudaFree(m->d_fast);
     if (m->d_fallbacks) cudaFree(m->d_fallbacks);
+    if (m->d_crc_ops) cudaFree(m->d_crc_ops);
     if (m->h_counts) cudaFreeHost(m->h_counts);
     for (cudaEvent_t e : m->copy_events) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -430,7 +437,7 @@ int amb_crc32(amb_modem* m, const uint8_t* data, int64_t stride, const int64_t* 
     if ((rc = in_ptr(m, data, (size_t)n * stride, mem, m->in_a, &d_data))) return rc;
     if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
     if ((rc = out_ptr(m, out, (size_t)n, mem, m->out_a, &d_out))) return rc;
-    LAUNCH("k_crc32", k_crc32<<<n < 65536 ? n : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out));
+    LAUNCH("k_crc32", k_crc32<<<n < 65536 ? n : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, d_data, stride, d_lens, stride, n, d_out, m->d_crc_ops));
     return flush(m);
 }
 
@@ -649,7 +656,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
         CK(m->l_recA.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_endA.ensure(nr * sizeof(AmbStreamState))); CK(m->l_hasA.ensure(nr * 4));
         CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
         CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
-        CK(m->l_hasB.ensure(nl * 4));
+        CK(m->l_hasB.ensure(nl * 4)); CK(m->l_memo.ensure(nr * sizeof(AmbRefineMemo)));
         CK(m->l_first.ensure(ns * sizeof(AmbStreamState))); CK(m->l_firstflag.ensure(ns * 4)); CK(m->l_firststop.ensure(ns * 4)); CK(m->l_fpsum.ensure(ns * 8));
     }
     if (!m->h_counts && cudaHostAlloc((void**)&m->h_counts, 64, cudaHostAllocDefault) != cudaSuccess) return fail(m, AMB_E_NOMEM, "cudaHostAlloc failed");
@@ -671,7 +678,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -798,7 +805,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     L.vis = m->l_vis.as<unsigned char>(); L.jump_a = m->l_ja.as<int>(); L.jump_b = m->l_jb.as<int>();
     L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
     L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
-    L.fp_sum = m->l_fpsum.as<unsigned long long>();
+    L.fp_sum = m->l_fpsum.as<unsigned long long>(); L.memo = m->l_memo.as<AmbRefineMemo>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
     const int walk_grid = (int)(blocks_for(max_links, 4) < 148 * 8 ? blocks_for(max_links, 4) : 148 * 8);
     const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);

@@ -624,6 +624,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
     G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+    G.memo_out = nullptr; G.memo_in = nullptr;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
     sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
@@ -1151,7 +1152,9 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
 // by a tree of GF(2) multiplications with x^(8 * chunk length * 2^level).  blockDim.x = AMB_CRC_THREADS; all threads
 // call; the result is returned to all.  tab: the 256-entry table in shared memory; sh: AMB_CRC_THREADS words.
 #define AMB_CRC_THREADS 128
-__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint8_t* data, int64_t n, uint32_t* sh) {
+#define AMB_CRC_MAXL 768        // chunk lengths with precomputed combine constants (rows up to 128 * 767 bytes)
+__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint32_t* __restrict__ ops_table /*[AMB_CRC_MAXL][8]*/, const uint8_t* data,
+                                                int64_t n, uint32_t* sh) {
     const int tid = threadIdx.x;
     int64_t lo, hi;
     amb_crc_chunk(n, AMB_CRC_THREADS, tid, &lo, &hi);
@@ -1161,9 +1164,11 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint8
         for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
         c ^= 0xFFFFFFFFu;
     }
-    // level l of the tree multiplies by x^(8 L 2^l): one thread per level computes its constant, the rest wait
+    // level l of the tree multiplies by x^(8 L 2^l): host-made table for the usual chunk lengths, otherwise one thread
+    // per level computes its constant
     __shared__ uint32_t ops[8];
-    if (tid < 7) ops[tid] = amb_gf_xpow8((uint32_t)(((n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS) << tid));
+    const int64_t L = (n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS;
+    if (tid < 7) ops[tid] = (ops_table && L < AMB_CRC_MAXL) ? ops_table[L * 8 + tid] : amb_gf_xpow8((uint32_t)(L << tid));
     sh[tid] = c;
     __syncthreads();
     int level = 0;
@@ -1180,7 +1185,7 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint8
 // majorityVote + bitsToBytes + frame parser + crc32 (modem.js:487-495, :468-476, :793-849, :607-653): one CTA per frame.
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride, amb_frame_result* __restrict__ results,
-                                                uint8_t* __restrict__ bytes_out, int64_t bytes_stride) {
+                                                uint8_t* __restrict__ bytes_out, int64_t bytes_stride, const uint32_t* __restrict__ crc_ops) {
     __shared__ uint32_t tab[256];
     __shared__ uint32_t sh[AMB_CRC_THREADS];
     __shared__ amb_frame_result sr;
@@ -1225,7 +1230,7 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
         __syncthreads();
         const int64_t crc_len = s_crc_len;
         if (crc_len >= 0) {
-            const uint32_t c = block_crc32(tab, bytes, crc_len, sh);
+            const uint32_t c = block_crc32(tab, crc_ops, bytes, crc_len, sh);
             if (tid == 0) { sr.actual_crc = c; sr.crc_valid = sr.expected_crc == c; }
         }
         if (tid == 0) results[j] = sr;
@@ -1515,13 +1520,14 @@ __global__ void __launch_bounds__(128) k_xcorr_pick(const AmbTables* __restrict_
 
 // crc32 of n byte rows, one CTA per row (modem.js:453-457)
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_crc32(const AmbTables* __restrict__ T, const uint8_t* __restrict__ data, int64_t stride,
-                                                          const int64_t* __restrict__ lens, int64_t n_default, int n, uint32_t* __restrict__ out) {
+                                                          const int64_t* __restrict__ lens, int64_t n_default, int n, uint32_t* __restrict__ out,
+                                                          const uint32_t* __restrict__ crc_ops) {
     __shared__ uint32_t tab[256];
     __shared__ uint32_t sh[AMB_CRC_THREADS];
     for (int i = threadIdx.x; i < 256; i += AMB_CRC_THREADS) tab[i] = T->crc_table[i];
     __syncthreads();
     for (int r = blockIdx.x; r < n; r += gridDim.x) {
-        const uint32_t c = block_crc32(tab, data + (int64_t)r * stride, lens ? lens[r] : n_default, sh);
+        const uint32_t c = block_crc32(tab, crc_ops, data + (int64_t)r * stride, lens ? lens[r] : n_default, sh);
         if (threadIdx.x == 0) out[r] = c;
         __syncthreads();
     }
@@ -1913,6 +1919,7 @@ struct AmbLinkBufs {
     AmbStreamState* first_out; int* first_flag;       // [n_streams] state after the first link, applied by k_chain_links
     int* first_stop;         // [n_streams] first chain link that did not reproduce its speculation
     unsigned long long* fp_sum;   // [n_streams] refine failures inside the accepted links
+    AmbRefineMemo* memo;     // per flat run index: phase A's refine, reused by phase B
 };
 
 __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
@@ -2031,6 +2038,9 @@ __global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
         G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
         G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+        G.memo_out = nullptr; G.memo_in = nullptr;
+        if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) L.memo[f].valid = 0; __syncwarp(); }
+        if (mode == 1 && L.link_run[f] >= 0) G.memo_in = L.memo + L.run_off[s] + L.link_run[f];
         if (first) {}
         else if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
         else if (i == 0) st = states[s];

@@ -38,6 +38,8 @@ struct AmbFrameRec {
     AmbStreamState snap;   // walker state right after the frame's reset to IDLE
 };
 
+struct AmbRefineMemo { int64_t coarse, fs, fe, pos; double fine; int32_t valid, pad; };
+
 struct AmbWalkGeom {
     int64_t block_len;     // samples per emulated processAudioBlock call
     int64_t ring_cap;      // RingBuffer capacity, app.js:712-715
@@ -50,6 +52,10 @@ struct AmbWalkGeom {
     const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
     int xc_w;
     const int32_t* slot_info;   // [slot][4], entry 2 = the slot's xc row was computed (NULL: every row is valid or marked UNSURE)
+    // Refine memo between the two phases of the link-parallel resolution: the refine (app.js:862-877) is a pure function
+    // of (coarse position, search range), so phase B reuses what phase A computed for the same run when these agree.
+    struct AmbRefineMemo* memo_out;    // phase A: the last successful refine of the walk is recorded here (or NULL)
+    const struct AmbRefineMemo* memo_in;   // phase B: consulted before computing (or NULL)
     const double* F;            // per call: inclusive prefix of the block-boundary defect terms (3 doubles per call)
     int64_t F_call0, F_calls;   // F[(call - F_call0) * 3 + c] valid for 0 <= call - F_call0 < F_calls
 };
@@ -423,8 +429,12 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
     if (fs < tw - G.ring_cap) fs = tw - G.ring_cap;
     if (fe > tw - plen) fe = tw - plen;
     int64_t pos;
-    const double best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos);
+    double best;
+    const AmbRefineMemo* mi = G.memo_in;
+    if (mi && mi->valid && mi->coarse == st.pre_pos && mi->fs == fs && mi->fe == fe) { pos = mi->pos; best = mi->fine; }
+    else best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos);
     if (best < 0.1) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
+    if (G.memo_out && AMB_LEADER()) { AmbRefineMemo* mo = G.memo_out; mo->coarse = st.pre_pos; mo->fs = fs; mo->fe = fe; mo->pos = pos; mo->fine = best; mo->valid = 1; }
     st.pre_pos = pos; st.fine = best;
     const int64_t max_payload = st.meta_received ? (int64_t)(st.chunk_size ? st.chunk_size : 4096) + 11 : 280;
     st.frame_end = st.pre_pos + amb_frame_samples(T, max_payload);
