@@ -173,7 +173,7 @@ __device__ __forceinline__ void block_prefix(const float* c, double* ST, double*
 // the exact float64 sums of those tiles only.
 struct AmbScanStore {
     int32_t* tile_slot;      // [n_streams][sum_stride]
-    double* tri;             // [slot_cap][256][3]
+    double* tri;             // [slot_cap][3][256]
     int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate (k_tri_store), unused
     int* slot_count;
     int slot_cap;
@@ -537,7 +537,7 @@ __device__ __forceinline__ double warp_excl_scan(double v, int lane, double* tot
     return inc - v;
 }
 
-__global__ void __launch_bounds__(128) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
+__global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
     const int lane = threadIdx.x & 31;
     const int n_slots = min(*st.slot_count, st.slot_cap);
     for (int slot = blockIdx.x * 4 + (threadIdx.x >> 5); slot < n_slots; slot += gridDim.x * 4) {
@@ -545,18 +545,18 @@ __global__ void __launch_bounds__(128) k_tri_store(const float* __restrict__ cle
         const int64_t a_first = ((int64_t)tile << 8) - 511;                 // arena index of the tile's first window
         const float* row = cleaned + (int64_t)s * stride;
         const int64_t a_hi = avail_hi - base_g;
-        double x[3][8];
+        float x[3][8];
 #pragma unroll
         for (int seg = 0; seg < 3; seg++)
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? (double)row[a] : 0.0; }
+            for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
         double q[3][8], t[2][8], qb[3], tb[2];       // exclusive prefixes inside the segment; global base of the segment
         double run_q = 0.0, run_t = 0.0;
 #pragma unroll
         for (int seg = 0; seg < 3; seg++) {
             double lq = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fma(x[seg][k], x[seg][k], lq); }
+            for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fma((double)x[seg][k], (double)x[seg][k], lq); }
             double tot;
             const double off = warp_excl_scan(lq, lane, &tot);
 #pragma unroll
@@ -565,15 +565,16 @@ __global__ void __launch_bounds__(128) k_tri_store(const float* __restrict__ cle
             if (seg < 2) {
                 double lt = 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fma(x[seg][k], x[seg + 1][k], lt); }
+                for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fma((double)x[seg][k], (double)x[seg + 1][k], lt); }
                 const double offt = warp_excl_scan(lt, lane, &tot);
 #pragma unroll
                 for (int k = 0; k < 8; k++) t[seg][k] += offt;
                 tb[seg] = run_t; run_t += tot;
             }
         }
-        double* o = st.tri + ((int64_t)slot * 256 + 8 * lane) * 3;
+        double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
         int cand = 0;
+        double oP[8], oA[8], oB[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
@@ -581,8 +582,14 @@ __global__ void __launch_bounds__(128) k_tri_store(const float* __restrict__ cle
             const double A = (qb[1] + q[1][k]) - (qb[0] + q[0][k]);
             const double B = (qb[2] + q[2][k]) - (qb[1] + q[1][k]);
             const bool valid = base_g + a_first + 8 * lane + k >= 0;
-            o[3 * k] = valid ? P : 0.0; o[3 * k + 1] = valid ? A : 0.0; o[3 * k + 2] = valid ? B : 0.0;
+            oP[k] = valid ? P : 0.0; oA[k] = valid ? A : 0.0; oB[k] = valid ? B : 0.0;
             cand |= valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
+            *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
+            *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
         }
         const int any = __any_sync(0xffffffffu, cand);
         if (lane == 0) st.slot_info[slot * 4 + 2] = any;

@@ -48,7 +48,7 @@ struct AmbWalkGeom {
     int64_t sum_lo;        // summaries valid for window-end samples q >= sum_lo
     // Optional stores written by the scan kernels (NULL = evaluate inline):
     const int32_t* tile_slot;   // per summary tile: slot in the stores, -1 = none
-    const double* tri;          // [slot][256][3]  (P, Ra, Rb) of the tile's 256 windows
+    const double* tri;          // [slot][3][256]  P, Ra, Rb of the tile's 256 windows
     const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
     int xc_w;
     const int32_t* slot_info;   // [slot][4], entry 2 = the slot's xc row was computed (NULL: every row is valid or marked UNSURE)
@@ -123,8 +123,8 @@ AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0
         if (seg > cnt - done) seg = cnt - done;
         const int slot = amb_tile_slot_of(G, j);
         if (slot >= 0 && G.tri) {
-            const double* src = G.tri + ((int64_t)slot * 256 + (d - tile_first)) * 3;
-            AMB_WARP_FOR(i, seg) { P[done + i] = src[3 * i]; A[done + i] = src[3 * i + 1]; B[done + i] = src[3 * i + 2]; }
+            const double* src = G.tri + (int64_t)slot * 768 + (d - tile_first);          // [slot][P | Ra | Rb][256]
+            AMB_WARP_FOR(i, seg) { P[done + i] = src[i]; A[done + i] = src[256 + i]; B[done + i] = src[512 + i]; }
             AMB_WARP_SYNC();
         } else {
             amb_window_sums(sig, d, seg, P + done, A + done, B + done);

@@ -251,7 +251,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 if (d < 0) continue;
                 double P = 0, A = 0, B = 0;
                 for (int t = 0; t < 256; t++) { const double a = cleaned[d + t], b = cleaned[d + t + 256]; P += a * b; A += a * a; B += b * b; }
-                t3[(q - j * 256) * 3] = P; t3[(q - j * 256) * 3 + 1] = A; t3[(q - j * 256) * 3 + 2] = B;
+                t3[q - j * 256] = P; t3[256 + (q - j * 256)] = A; t3[512 + (q - j * 256)] = B;
                 hot |= A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
                 cand |= A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
                 ap = fmaxf(ap, (float)fabs(P)); mnA = fminf(mnA, (float)A); mxA = fmaxf(mxA, (float)A); mnB = fminf(mnB, (float)B); mxB = fmaxf(mxB, (float)B);
