@@ -345,6 +345,19 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
     }
     if (which == 2) return m->link_iterations;
     if (which == 3) return m->link_passes;
+    if ((which == 4 || which == 5) && m->open) {
+        // slotted tiles (4) and tiles holding an exact candidate window (5) in the last push
+        int n = 0;
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpy(&n, m->slot_count.p, 4, cudaMemcpyDeviceToHost);
+        if (n > m->slot_cap) n = m->slot_cap;
+        if (which == 4) return n;
+        std::vector<int32_t> info((size_t)n * 4);
+        if (n > 0) cudaMemcpy(info.data(), m->slot_info.p, (size_t)n * 16, cudaMemcpyDeviceToHost);
+        int64_t c = 0;
+        for (int i = 0; i < n; i++) c += info[(size_t)i * 4 + 2] != 0;
+        return c;
+    }
     return -1;
 }
 

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             }
         }
         double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
-        int cand = 0;
+        int cand = 0, c_lo = 255, c_hi = 0;
         double oP[8], oA[8], oB[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -583,7 +583,9 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             const double B = (qb[2] + q[2][k]) - (qb[1] + q[1][k]);
             const bool valid = base_g + a_first + 8 * lane + k >= 0;
             oP[k] = valid ? P : 0.0; oA[k] = valid ? A : 0.0; oB[k] = valid ? B : 0.0;
-            cand |= valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+            const bool c = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+            cand |= c;
+            if (c) { c_lo = min(c_lo, 8 * lane + k); c_hi = max(c_hi, 8 * lane + k); }
         }
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
@@ -592,7 +594,9 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
         }
         const int any = __any_sync(0xffffffffu, cand);
-        if (lane == 0) st.slot_info[slot * 4 + 2] = any;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
+        if (lane == 0) { st.slot_info[slot * 4 + 2] = any; st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16); }     // candidate windows span [c_lo, c_hi]
     }
 }
 
@@ -1863,7 +1867,12 @@ __global__ void __launch_bounds__(256) k_xcorr_store(const AmbTables* __restrict
         __syncthreads();
         float* out = xc + (int64_t)slot * xc_w;
         const int split = 256 - cp;                                    // taps below use u, taps from here on use u2 (multiple of 4)
-        for (int o0 = tid * AMB_XC_PER; o0 < xc_w; o0 += nt * AMB_XC_PER) {
+        // a refine around candidate window w reads offsets w .. w + 2R: only the span of the tile's candidate windows (plus a
+        // margin for candidates that exist only under the walker's defect) is computed, the rest is marked UNSURE
+        const int c_lo = slot_info[slot * 4 + 3] & 0xffff, c_hi = (slot_info[slot * 4 + 3] >> 16) & 0xffff;
+        const int o_lo = max(0, (c_lo - 16) & ~7), o_hi = min(xc_w, (c_hi + 2 * R + 1 + 16 + 7) & ~7);
+        for (int i = tid; i < xc_w; i += nt) if (i < o_lo || i >= o_hi) out[i] = AMB_XC_UNSURE;
+        for (int o0 = o_lo + tid * AMB_XC_PER; o0 < o_hi; o0 += nt * AMB_XC_PER) {
             float acc[AMB_XC_PER];
 #pragma unroll
             for (int q = 0; q < AMB_XC_PER; q++) acc[q] = 0.f;

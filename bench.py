@@ -292,6 +292,8 @@ def run_b200(args, rank, world, local_rank):
     prof_ms = p0.elapsed_time(p1)
     prof = m.profile_read()
     m.profile(False)
+    slots = {"slotted_tiles_per_frame": m.debug_counter(4) / F, "candidate_tiles_per_frame": m.debug_counter(5) / F,
+             "link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
 
     # end-to-end: host buffers (page-locked), H2D of the samples + D2H of results and decoded bytes inside the timed region
     host = amb.modem.pinned_empty((1, step_samples), np.float32)
@@ -355,7 +357,7 @@ def run_b200(args, rank, world, local_rank):
             "config": config_dict(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * step_samples, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": tot["launches"], "roofline": roof,
-            "check": {"frames_per_step_found": frames_found // args.steps, "crc_valid_frames": tot["crcValidFrames"], "crc_errors": crc_bad}}
+            "walker": slots, "check": {"frames_per_step_found": frames_found // args.steps, "crc_valid_frames": tot["crcValidFrames"], "crc_errors": crc_bad}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, pmb, cores, sample, _ = cpu_leg(steps=1000, warmup=1, frames_per_thread=64, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "payload_mb_per_s": pmb}
