@@ -1,0 +1,125 @@
+"""Parity at larger sizes, shaped like BASELINE.json's configs 2-5 (reduced so the oracle finishes in seconds), plus
+size-independent properties on what the oracle does not replay.  GPU only."""
+import numpy as np
+import pytest
+
+from helpers import MODES, make_stream, pad_blocks, results_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _events_equal(O, amb, mode, x, pushes):
+    cfg, mod, rep, _ = MODES[mode]
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        m.stream_open(1, 4096, max(pushes))
+        got, off = [], 0
+        for p in pushes:
+            got += m.stream_push(x[None, off:off + p], raw=True)
+            off += p
+        assert off == len(x)
+        rx = O.StreamingReceiver(cfg, mod, rep)
+        want = rx.push(x, 4096, raw=True)
+        assert len(got) == len(want), (len(got), len(want))
+        for (r1, b1), (r2, b2) in zip(want, got):
+            assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (mode, r1.preamble_idx)
+        c, w = m.stream_counters(), rx.counters()
+        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived"):
+            assert c[k] == w[k], (k, c, w)
+        return want
+    finally:
+        m.close()
+
+
+def test_c2_chunk_stream_400_frames(O, amb):
+    """config 2 in small: 16-QAM, 4 KB chunks, AWGN 25 dB, 400 frames, three unequal pushes - every event equal to the oracle's"""
+    x, pay = make_stream(O, "16-QAM", 400, 77)
+    n = len(x)
+    a, b = (n // 3) // 4096 * 4096, (n // 2) // 4096 * 4096
+    ev = _events_equal(O, amb, "16-QAM", x, [a, b, n - a - b])
+    data = [bytes(bb[r.data_off:r.data_off + r.data_len]) for r, bb in ev if r.status == 0 and r.frame_type == 0xFF and r.crc_valid]
+    assert len(data) >= 398 and set(data) <= set(pay)
+
+
+def test_c4_narrowband_sparse_capture(O, amb):
+    """config 4 in small: narrowband frames far apart in a long noisy capture (scan dominated)"""
+    cfg, mod, rep, chunk = MODES["BPSK-NARROW"]
+    rng = np.random.default_rng(9)
+    parts = [np.zeros(5 * 4410, np.float32), O.buildMetadataFrame(cfg, 3, 3 * chunk, chunk, "cap.bin", mod, rep)]
+    for i, gap in enumerate((300000, 441000, 250000)):
+        parts.append(np.zeros(gap, np.float32))
+        parts.append(O.buildDataChunkFrame(cfg, O.randomBytes(600 + i, chunk), i, mod, rep))
+    x = np.concatenate(parts)
+    x = pad_blocks((x + rng.standard_normal(len(x)).astype(np.float32) * np.float32(10 ** (-30 / 20))).astype(np.float32), tail=3 * 4096)
+    n = len(x)
+    pushes = [64 * 4096] * (n // (64 * 4096)) + ([n % (64 * 4096)] if n % (64 * 4096) else [])
+    ev = _events_equal(O, amb, "BPSK-NARROW", x, pushes)
+    assert sum(1 for r, _ in ev if r.status == 0 and r.crc_valid) >= 3
+
+
+@pytest.mark.parametrize("mode", ["BPSK-ACOUSTIC", "BPSK-REPEAT"])
+def test_c3_recordings_batch(O, amb, mode):
+    """config 3 in small: 48 recordings through multipath, CFO (10 % at +-1 Hz: the reference has no CFO correction, the
+    failures must be identical) and AWGN 20 dB, decoded as one batch"""
+    cfg, mod, rep, _ = MODES[mode]
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(48):
+        tx = O.buildTransmitSignal(cfg, O.randomBytes(1000 + i, 512), mod, "rec", rep)
+        y = O.multipath(tx, [0, 23, 57], [1.0, 0.5, 0.25])
+        y = O.cfo(y, rng.choice([-1.0, 1.0]) if i % 10 == 3 else rng.uniform(-0.05, 0.05))
+        recs.append(O.addAwgn(y, float(np.sqrt(O.power(tx[22050:][:20000]) / 100.0)), 1000 + i))
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        got = m.decode_received_signals(recs, raw=True)
+    finally:
+        m.close()
+    ok = 0
+    for i, r in enumerate(recs):
+        r1, b1 = O.decodeReceivedSignal(cfg, r, mod, rep, raw=True)
+        assert results_equal(r1, b1, got[i][0], got[i][1], metric_tol=1e-9) == [], (mode, i)
+        ok += int(r1.status == 0 and r1.crc_valid)
+    assert ok >= 30
+
+
+def test_c5_many_streams(O, amb):
+    """config 5 in small: 192 independent 16-QAM streams built on the device (metadata + 3 chunks, own payload and noise),
+    pushed in sections; eight of them replayed by the oracle, all of them checked through the counters"""
+    import torch
+
+    cfg, mod, rep, chunk = MODES["16-QAM"]
+    ns, K = 192, 3
+    dev = torch.device("cuda", 0)
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        meta_len = m.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len("s.bin") + 4, True)
+        flen = m.chunk_frame_samples(chunk + 11, False)
+        push = 8 * 4096
+        n = (meta_len + K * flen + 8192 + push - 1) // push * push
+        x = torch.zeros((ns, n), dtype=torch.float32, device=dev)
+        clean = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+        m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+        sigma = float((clean[0, 2205:flen - 882].double().pow(2).mean() / 10 ** 2.5).sqrt())       # 25 dB below the frame core
+        for s in range(ns):
+            m.build_metadata_frame(K, K * chunk, chunk, "s.bin", noise_sigma=sigma, noise_seed=5000 + s, noise_g0=0, out=x[s, :meta_len])
+            m.build_data_chunk_frames(n=K, data_len=chunk, seq0=0, synth_seed=9000 + s, noise_sigma=sigma, noise_seed=5000 + s, noise_g0=meta_len,
+                                      out=x[s, meta_len:meta_len + K * flen].view(K, flen))
+        m.synchronize()
+        m.stream_open(ns, 4096, push)
+        got = [[] for _ in range(ns)]
+        for p0 in range(0, n, push):
+            for r, b in m.stream_push(x[:, p0:p0 + push], raw=True):
+                got[r.stream].append((r, b))
+        c = m.stream_counters()
+        assert c["metaReceived"] == ns and c["framesDecoded"] == ns * (K + 1) and c["frameErrors"] == 0
+        assert c["receivedCount"] + c["crcErrors"] == ns * K
+        host = x[:8].cpu().numpy()
+        for s in range(8):
+            want = O.StreamingReceiver(cfg, mod, rep).push(host[s], 4096, raw=True)
+            g = sorted(got[s], key=lambda t: t[0].preamble_idx)
+            assert len(g) == len(want) == K + 1
+            for (r1, b1), (r2, b2) in zip(want, g):
+                assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (s, r1.preamble_idx)
+        m.stream_close()
+    finally:
+        m.close()
