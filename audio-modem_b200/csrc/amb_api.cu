@@ -28,7 +28,7 @@ struct DevBuf {
             cap = want;
             // AMB_POISON=1 (tests): fresh scratch memory starts as garbage, so a read of something no kernel wrote shows up
             static const bool poison = std::getenv("AMB_POISON") != nullptr;
-            if (poison) cudaMemset(p, 0xCD, want);
+            if (poison) { cudaMemset(p, 0xCD, want); cudaDeviceSynchronize(); }   // (the handle's stream does not order against the default stream)
         }
         return e;
     }
@@ -855,7 +855,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         for (int it = 0; n_active > 0 && it < (1 << 20); it++) {
             m->link_iterations++;
             CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
-            LAUNCH("k_chain_links", k_chain_links<<<ns, 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
+            LAUNCH("k_chain_links", k_chain_links<<<ns, ns < 64 ? 1024 : 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
             LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
@@ -877,7 +877,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
         if ((rc = run_demod_parse(m, total, h[2], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
-        LAUNCH("k_post_stream", k_post_stream<<<ns, 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+        LAUNCH("k_post_stream", k_post_stream<<<ns, (int64_t)total > 8192ll * ns ? 1024 : 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                   m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
                                                                   m->redo.as<int>(), m->n_redo.as<int>(), g.k_end));
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));

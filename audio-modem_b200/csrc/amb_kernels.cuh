@@ -886,13 +886,24 @@ __device__ __forceinline__ float fd_spectrum(const AmbJob& J, int64_t p0, bool i
     }
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
-        if (v[n1].x != v[n1].x) v[n1].x = 0.f;                     // `x || 0` (modem.js:377, :425)
-        if (v[n1].y != v[n1].y) v[n1].y = 0.f;
         const float ax = fabsf(v[n1].x), ay = fabsf(v[n1].y);
         S += ax + ay; mx = fmaxf(mx, fmaxf(ax, ay));
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    if (__any_sync(0xffffffffu, !(S <= 3.0e38f))) {
+        // a NaN among the samples (S is NaN): `x || 0` maps it to 0 (modem.js:377, :425); redo the sums without it
+        S = 0.f; mx = 0.f;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            if (v[n1].x != v[n1].x) v[n1].x = 0.f;
+            if (v[n1].y != v[n1].y) v[n1].y = 0.f;
+            const float ax = fabsf(v[n1].x), ay = fabsf(v[n1].y);
+            S += ax + ay; mx = fmaxf(mx, fmaxf(ax, ay));
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    }
     *S_out = S;
     // pass 1: lane n2 = l transforms z[16 n1 + n2] over n1, scales by W256^(n2 k1), stores row k1
     fft16f(v);
@@ -935,8 +946,8 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     float* cH = invH;                                                            // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
     int* role = reinterpret_cast<int*>(dH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 pilot
     __shared__ float s_red[8];
-    __shared__ float4 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
-    __shared__ int pilot_in_band[AMB_MAX_PILOTS];
+    __shared__ float2 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
+    __shared__ int pilot_kk[AMB_MAX_PILOTS];                                     // bin (relative to sub_start) of pilot q, -1 outside the band
     __shared__ float s_mx, s_minhm;
     __shared__ unsigned s_mask[2];
     __shared__ int s_all;
@@ -954,7 +965,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     if (tid < AMB_MAX_PILOTS) {
         const int k = tid < T->n_pilots ? T->pilots[tid] : -1;
         const bool inb = k >= T->sub_start && k <= T->sub_end;
-        pilot_in_band[tid] = inb ? 1 : 0;
+        pilot_kk[tid] = inb ? k - sub_start : -1;
         if (inb) role[k - sub_start] = -1 - tid;
     }
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
@@ -1000,7 +1011,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     //      the barrier sits between their transform and their equaliser.
     const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
     float2* buf = hwbuf + hw * AMB_FD_HWBUF;
-    float* pe = reinterpret_cast<float*>(s_pilot[hw]);                   // pilot bins of the symbol in flight: (re, im, bound)
+    float2* pe = s_pilot[hw];                                            // pilot bins of the symbol in flight
     const float thr = (float)T->qam_thr;
     const int n_pilots = T->n_pilots;
     for (int s0 = g0; s0 < s_end; s0 += AMB_FD_HW) {
@@ -1046,10 +1057,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
                 const float2 e = cmulf(fd_split(buf, tw512, sub_start + kk), Gq[kk]);
                 E[i] = e;
                 const int rl = role[kk];
-                if (rl < 0) {
-                    float* o = pe + 4 * (-1 - rl);
-                    o[0] = e.x; o[1] = e.y; o[2] = S * cH[kk] + (fabsf(e.x) + fabsf(e.y)) * dH[kk];      // bound on |e - exact|
-                }
+                if (rl < 0) pe[-1 - rl] = e;
             }
         }
         __syncwarp();
@@ -1057,8 +1065,9 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         float ph_sum = 0.f, ptol = 0.f;
         int pc = 0;
         bool bad = false;
-        if (l < n_pilots && pilot_in_band[l]) {
-            const float ex = pe[4 * l], ey = pe[4 * l + 1], dk = pe[4 * l + 2];
+        if (l < n_pilots && pilot_kk[l] >= 0) {
+            const float ex = pe[l].x, ey = pe[l].y;
+            const float dk = S * cH[pilot_kk[l]] + (fabsf(ex) + fabsf(ey)) * dH[pilot_kk[l]];          // bound on |e - exact|
             const float ar = fabsf(ex);
             if (!(fabsf(ar - 1e-6f) > dk)) bad = true;                  // the |eqRe| > 1e-6 test could flip (also catches NaN)
             if (ar > 1e-6f) {
@@ -1649,7 +1658,7 @@ __global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __rest
 // Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the streams whose
 // collection window changed for another walk.  One CTA per stream.  Without a CRC-valid metadata frame among them (the
 // steady state) the frames only move counters, which is a parallel count; otherwise thread 0 applies them sequentially.
-__global__ void __launch_bounds__(128) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
+__global__ void __launch_bounds__(1024) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
                               const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
                               AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
                               int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end) {
@@ -2103,7 +2112,7 @@ __global__ void k_chain_next(int n_streams, AmbLinkBufs L) {
 
 // Speculated chain of an active stream from its current (post-reset) state: the runs reachable through next[],
 // in order, plus a tail link when the last of them is expected to emit a frame.  One CTA per stream.
-__global__ void __launch_bounds__(256) k_chain_links(int n_streams, AmbStreamState* __restrict__ states, AmbLinkBufs L) {
+__global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamState* __restrict__ states, AmbLinkBufs L) {
     const int s = blockIdx.x;
     if (s >= n_streams) return;
     const int tid = threadIdx.x;
@@ -2123,30 +2132,30 @@ __global__ void __launch_bounds__(256) k_chain_links(int n_streams, AmbStreamSta
     const AmbStreamState st = states[s];
     int first = n;
     if (st.state == AMB_RX_IDLE && !st.ac_init) first = amb_run_at_or_after(runs, n, st.ac_scan_pos);
-    for (int r = tid; r < n; r += 256) { vis[r] = r == first; ja[r] = L.next[off + r]; }
+    for (int r = tid; r < n; r += blockDim.x) { vis[r] = r == first; ja[r] = L.next[off + r]; }
     __syncthreads();
     // pointer doubling: after round k every run within distance < 2^(k+1) of `first` is marked
     for (int span = 1; span < n; span <<= 1) {
-        for (int r = tid; r < n; r += 256) if (vis[r] && ja[r] < n) vis[ja[r]] = 1;
+        for (int r = tid; r < n; r += blockDim.x) if (vis[r] && ja[r] < n) vis[ja[r]] = 1;
         __syncthreads();
-        for (int r = tid; r < n; r += 256) { const int j = ja[r]; jb[r] = j < n ? ja[j] : n; }
+        for (int r = tid; r < n; r += blockDim.x) { const int j = ja[r]; jb[r] = j < n ? ja[j] : n; }
         __syncthreads();
         int* t = ja; ja = jb; jb = t;
     }
     // ordered compaction of the visited runs
-    __shared__ int wsum[8];
+    __shared__ int wsum[32];
     __shared__ int base;
     if (tid == 0) base = 0;
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
-    for (int c0 = 0; c0 < n; c0 += 256) {
+    for (int c0 = 0; c0 < n; c0 += blockDim.x) {
         const int r = c0 + tid;
         const int v = r < n && vis[r];
         const unsigned m = __ballot_sync(0xffffffffu, v);
         if (lane == 0) wsum[warp] = __popc(m);
         __syncthreads();
         int woff = 0, tot = 0;
-        for (int w = 0; w < 8; w++) { if (w < warp) woff += wsum[w]; tot += wsum[w]; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < warp) woff += wsum[w]; tot += wsum[w]; }
         if (v) {
             const int idx = base + woff + __popc(m & ((1u << lane) - 1));
             link_run[idx] = r;

@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=int(os.environ.get("AMB_FRAMES_PER_STEP", "4096")))
-    ap.add_argument("--segments", type=int, default=4, help="distinct resident input segments cycled through")
+    ap.add_argument("--frames-per-step", type=int, default=int(os.environ.get("AMB_FRAMES_PER_STEP", "16384")))
+    ap.add_argument("--segments", type=int, default=3, help="distinct resident input segments cycled through")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
