@@ -69,7 +69,7 @@ struct amb_modem {
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
-    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart;
+    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo;
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
@@ -311,7 +311,7 @@ void amb_destroy(amb_modem* m) {
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
                      &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
@@ -654,7 +654,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     const int64_t tiles_per_push = (max_push / 256) * n_streams;
     m->slot_cap = (int)(tiles_per_push / 8 + 64 < 2000000 ? tiles_per_push / 8 + 64 : 2000000);
     CK(m->tile_slot.ensure(ns * m->sum_stride * 4)); CK(m->tri.ensure((size_t)m->slot_cap * 256 * 3 * 8));
-    CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16));
+    CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16)); CK(m->tsum.ensure((size_t)m->slot_cap * 16));
     CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8));
     CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
@@ -688,7 +688,7 @@ int amb_stream_close(amb_modem* m) {
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
                      &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
@@ -743,6 +743,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
+    ss.tsum = m->tsum.as<float>();
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
@@ -786,7 +787,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     g.sum_lo = m->written - m->hist > 0 ? m->written - m->hist : 0;       // summaries and slots are kept for the last `hist` samples
     g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
-    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>();
+    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
     {
         const int L = m->xc_w + T.sym_len;

@@ -177,6 +177,7 @@ struct AmbScanStore {
     int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate (k_tri_store), unused
     int* slot_count;
     int slot_cap;
+    float* tsum;             // [slot_cap][4] exact extremes of the slot's windows (amb_slot_cold)
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
         double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
         int cand = 0, c_lo = 255, c_hi = 0;
         double oP[8], oA[8], oB[8];
+        double mmax = 0.0, mnA = 1.0, mnB = 1.0;          // over the windows with Ra, Rb > 0.0005 (amb_slot_cold)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
@@ -585,15 +587,27 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             oP[k] = valid ? P : 0.0; oA[k] = valid ? A : 0.0; oB[k] = valid ? B : 0.0;
             const bool c = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
             cand |= c;
+            if (valid && A > 0.0005 && B > 0.0005) { mnA = fmin(mnA, A); mnB = fmin(mnB, B); mmax = fmax(mmax, (P * P) / (A * B)); }
             if (c) { c_lo = min(c_lo, 8 * lane + k); c_hi = max(c_hi, 8 * lane + k); }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
-            *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
-            *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
-        }
         const int any = __any_sync(0xffffffffu, cand);
+        if (any) {
+            // the rows are only kept for tiles with a candidate: the walker skips the others by their extremes (amb_slot_cold)
+            // and, if its defect makes one of them hot after all, evaluates it itself
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
+                *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
+                *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
+            }
+        }
+        mmax = warp_maxd(mmax);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) { mnA = fmin(mnA, __shfl_xor_sync(0xffffffffu, mnA, o2)); mnB = fmin(mnB, __shfl_xor_sync(0xffffffffu, mnB, o2)); }
+        if (lane == 0 && st.tsum) {
+            float* ts = st.tsum + (int64_t)slot * 4;
+            ts[0] = (float)mmax * (1.f + 1e-6f) + 1e-30f; ts[1] = fmaxf((float)mnA * (1.f - 1e-6f), 0.f); ts[2] = fmaxf((float)mnB * (1.f - 1e-6f), 0.f); ts[3] = 0.f;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
         if (lane == 0) { st.slot_info[slot * 4 + 2] = any; st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16); }     // candidate windows span [c_lo, c_hi]
@@ -614,7 +628,7 @@ struct AmbStreamGeom {
     int rec_cap;           // frame records per stream
     // stores of the scan kernels (see AmbWalkGeom)
     const int32_t* tile_slot; const double* tri; const float* xc; int xc_w;
-    const int32_t* slot_info;
+    const int32_t* slot_info; const float* tsum;
     const double* F; int64_t calls_stride;
 };
 
@@ -633,7 +647,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     if (pre_meta_only && st.meta_received) return;
     AmbWalkGeom G;
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
+    G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
     G.memo_out = nullptr; G.memo_in = nullptr;
     AmbSig sig;
@@ -2061,7 +2075,7 @@ __global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__
         }
         AmbWalkGeom G;
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
-        G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info;
+        G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
         G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
         G.memo_out = nullptr; G.memo_in = nullptr;
         if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) L.memo[f].valid = 0; __syncwarp(); }

@@ -51,7 +51,9 @@ struct AmbWalkGeom {
     const double* tri;          // [slot][3][256]  P, Ra, Rb of the tile's 256 windows
     const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
     int xc_w;
-    const int32_t* slot_info;   // [slot][4], entry 2 = the slot's xc row was computed (NULL: every row is valid or marked UNSURE)
+    const int32_t* slot_info;   // [slot][4], entry 2 = the slot's tri / xc rows were computed (NULL: every row is valid or marked UNSURE)
+    const float* tsum;          // [slot][4]: exact extremes over the slot's 256 windows: max metric (no defect, rounded up), min Ra,
+                                // min Rb (rounded down); NULL = not available
     // Refine memo between the two phases of the link-parallel resolution: the refine (app.js:862-877) is a pure function
     // of (coarse position, search range), so phase B reuses what phase A computed for the same run when these agree.
     struct AmbRefineMemo* memo_out;    // phase A: the last successful refine of the walk is recorded here (or NULL)
@@ -87,6 +89,26 @@ AMB_HD bool amb_tile_hot(const float* s, double Ep, double Ea, double Eb) {
     return pm * pm > 0.5 * minA * minB * (1.0 - 1e-5);
 }
 
+// Second, sharper test for a slotted tile, from the exact per-window values k_tri_store reduced over the windows with
+// Ra > 0.0005 and Rb > 0.0005 (half the energy gate; with |Ea|, |Eb| < 0.0004 no other window can pass the gate of 0.001):
+// max metric (no defect, rounded up), min Ra, min Rb (rounded down).  With the defect E in force,
+//   sqrt(metric') = |P + Ep| / sqrt((Ra + Ea)(Rb + Eb)) <= sqrt(metric) sqrt(Ra Rb / (Ra' Rb')) + |Ep| / sqrt(Ra' Rb'),
+// Ra' >= Ra - |Ea| >= minRa - |Ea| (and Ra / Ra' is largest at the smallest Ra).  True = no window of the tile can be a
+// candidate.
+AMB_HD bool amb_slot_cold(const float* ts, double Ep, double Ea, double Eb) {
+    if (!(fabs(Ea) < 0.0004) || !(fabs(Eb) < 0.0004)) return false;
+    const double mA = (double)ts[1] - fabs(Ea), mB = (double)ts[2] - fabs(Eb);      // > 0.0001
+    if (!(mA > 0.0) || !(mB > 0.0)) return false;
+    const double ka = (double)ts[1] / mA, kb = (double)ts[2] / mB;
+    const double r = sqrt((double)ts[0] * ka * kb) * (1.0 + 1e-6) + fabs(Ep) / sqrt(mA * mB);
+    return r * r < 0.5 * (1.0 - 1e-6);
+}
+
+AMB_HD int amb_tile_slot_of(const struct AmbWalkGeom& G, int64_t j);
+
+// amb_tile_hot, refined by amb_slot_cold where the tile has a slot (rel = tile index relative to the summary base)
+AMB_HD bool amb_tile_hot2(const struct AmbWalkGeom& G, const float* sums, int64_t jj, int64_t rel, double Ep, double Ea, double Eb);
+
 struct AmbWalkScratch {      // per-warp shared memory
     double P[264], A[264], B[264], M[264];
     double x[64];
@@ -111,6 +133,15 @@ AMB_HD void amb_commit(AmbStreamState& st, int64_t best_pos, double best, int64_
     st.pre_pos = best_pos; st.coarse = best; st.state = AMB_RX_PREAMBLE; st.ac_scan_pos = next_pos; st.lag = lag;
 }
 
+AMB_HD bool amb_tile_hot2(const AmbWalkGeom& G, const float* sums, int64_t jj, int64_t rel, double Ep, double Ea, double Eb) {
+    if (!amb_tile_hot(sums + rel * AMB_SUM_W, Ep, Ea, Eb)) return false;
+    if (G.tsum) {
+        const int slot = amb_tile_slot_of(G, jj);
+        if (slot >= 0 && amb_slot_cold(G.tsum + (int64_t)slot * 4, Ep, Ea, Eb)) return false;
+    }
+    return true;
+}
+
 // Window sums at cnt consecutive offsets from d0: copied from the scan kernel's store where the tile has a slot,
 // evaluated directly otherwise.
 AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0, int cnt, double* P, double* A, double* B) {
@@ -122,7 +153,7 @@ AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0
         int seg = (int)(tile_first + 256 - d);
         if (seg > cnt - done) seg = cnt - done;
         const int slot = amb_tile_slot_of(G, j);
-        if (slot >= 0 && G.tri) {
+        if (slot >= 0 && G.tri && (!G.slot_info || G.slot_info[slot * 4 + 2])) {
             const double* src = G.tri + (int64_t)slot * 768 + (d - tile_first);          // [slot][P | Ra | Rb][256]
             AMB_WARP_FOR(i, seg) { P[done + i] = src[i]; A[done + i] = src[256 + i]; B[done + i] = src[512 + i]; }
             AMB_WARP_SYNC();
@@ -139,7 +170,7 @@ AMB_HD int amb_call_cold(const AmbWalkGeom& G, const float* sums, int64_t k, dou
     for (int64_t t = 0; t < n; t++) {
         const int64_t jj = j0 + t, rel = jj - (G.sum_base >> 8);
         if (rel < 0 || rel >= G.sum_tiles || (jj << 8) < G.sum_lo) return 0;
-        if (amb_tile_hot(sums + rel * AMB_SUM_W, Ep, Ea, Eb)) return 0;
+        if (amb_tile_hot2(G, sums, jj, rel, Ep, Ea, Eb)) return 0;
     }
     return 1;
 }
@@ -340,7 +371,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
         bool cold = false;
         {
             const int64_t jj = (d - 1 + 511) >> 8, rel = jj - (G.sum_base >> 8);
-            if (d - 1 >= 0 && rel >= 0 && rel < G.sum_tiles && (jj << 8) >= G.sum_lo) cold = !amb_tile_hot(sums + rel * AMB_SUM_W, st.Ep, st.Ea, st.Eb);
+            if (d - 1 >= 0 && rel >= 0 && rel < G.sum_tiles && (jj << 8) >= G.sum_lo) cold = !amb_tile_hot2(G, sums, jj, rel, st.Ep, st.Ea, st.Eb);
         }
         if (!cold) {
             amb_eval_windows(G, sig, d - 1, 3, W->P, W->A, W->B);
@@ -381,7 +412,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
                     if (jj <= j_end) {
                         const int64_t rel = jj - (G.sum_base >> 8);
                         if (rel < 0 || rel >= G.sum_tiles || (jj << 8) < G.sum_lo) h = 1;   // no summary: must evaluate
-                        else h = amb_tile_hot(sums + rel * AMB_SUM_W, st.Ep, st.Ea, st.Eb) ? 1 : 0;
+                        else h = amb_tile_hot2(G, sums, jj, rel, st.Ep, st.Ea, st.Eb) ? 1 : 0;
                     }
                     W->hot[t] = h;
                 }

@@ -225,9 +225,10 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     // current push, float64 triples, float32 screening correlation, per-call defect prefix
     std::vector<int32_t> tile_slot((size_t)n_tiles, -1);
     std::vector<double> tri, Fpre((size_t)(n / block_len + 2) * 3, 0.0);
+    std::vector<float> tsum;
     std::vector<float> xc;
     const int xc_w = 256 + 2 * T.fine_radius;
-    G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.slot_info = nullptr; G.memo_out = nullptr; G.memo_in = nullptr; G.F = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
+    G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.slot_info = nullptr; G.tsum = nullptr; G.memo_out = nullptr; G.memo_in = nullptr; G.F = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
     AmbStreamState st;
     std::memset(&st, 0, sizeof(st));
     st.pre_pos = -1; st.frame_end = -1;
@@ -239,12 +240,13 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
         const int64_t w1 = std::min(n, w0 + push_len);
         if ((w1 - w0) % block_len) break;
         sig.hi = w1;
-        if (g_use_stores) { std::fill(tile_slot.begin(), tile_slot.end(), -1); tri.clear(); xc.clear(); }
+        if (g_use_stores) { std::fill(tile_slot.begin(), tile_slot.end(), -1); tri.clear(); xc.clear(); tsum.clear(); }
         int n_slots = 0;
         // summaries of the window-end samples that became available
         for (int64_t j = tiles_done; (j + 1) * 256 <= w1; j++, tiles_done = j) {
             float ap = 0, mnA = 3e38f, mxA = 0, mnB = 3e38f, mxB = 0;
             bool hot = false, cand = false;
+            double mmax = 0.0, xmnA = 1.0, xmnB = 1.0;
             std::vector<double> t3(256 * 3, 0.0);
             for (int64_t q = j * 256; q < (j + 1) * 256; q++) {
                 const int64_t d = q - 511;
@@ -254,12 +256,20 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 t3[q - j * 256] = P; t3[256 + (q - j * 256)] = A; t3[512 + (q - j * 256)] = B;
                 hot |= A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
                 cand |= A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
+                if (A > 0.0005 && B > 0.0005) { xmnA = fmin(xmnA, A); xmnB = fmin(xmnB, B); mmax = fmax(mmax, (P * P) / (A * B)); }
                 ap = fmaxf(ap, (float)fabs(P)); mnA = fminf(mnA, (float)A); mxA = fmaxf(mxA, (float)A); mnB = fminf(mnB, (float)B); mxB = fmaxf(mxB, (float)B);
             }
             float* o = &sums[(size_t)j * AMB_SUM_W];
             o[0] = ap; o[1] = mnA; o[2] = mxA; o[3] = mnB; o[4] = mxB;
+            // slots as k_front assigns them: every tile the walker's summary test could enter (widened for the defect)
+            {
+                const float pw = o[0] * 1.05f;
+                hot = hot || (o[2] * 1.05f > 0.0009f && o[4] * 1.05f > 0.0009f && pw * pw > 0.4f * fmaxf(o[1] * 0.95f, 0.0009f) * fmaxf(o[3] * 0.95f, 0.0009f));
+            }
             if (g_use_stores && hot) {
                 tile_slot[(size_t)j] = n_slots++;
+                tsum.push_back((float)mmax * (1.f + 1e-6f) + 1e-30f); tsum.push_back(fmaxf((float)xmnA * (1.f - 1e-6f), 0.f));
+                tsum.push_back(fmaxf((float)xmnB * (1.f - 1e-6f), 0.f)); tsum.push_back(0.f);
                 tri.insert(tri.end(), t3.begin(), t3.end());
                 xc.resize((size_t)n_slots * xc_w, AMB_XC_UNSURE);
                 if (cand) {
@@ -280,7 +290,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 const double D[3] = {xm1 * x255 - x255 * x511, xm1 * xm1 - x255 * x255, x255 * x255 - x511 * x511};
                 for (int q = 0; q < 3; q++) Fpre[(size_t)k * 3 + q] = (k > 0 ? Fpre[(size_t)(k - 1) * 3 + q] : 0.0) + D[q];
             }
-            G.tile_slot = tile_slot.data(); G.tri = tri.data(); G.xc = xc.data(); G.F = Fpre.data();
+            G.tile_slot = tile_slot.data(); G.tri = tri.data(); G.xc = xc.data(); G.F = Fpre.data(); G.tsum = tsum.data();
         }
         const int64_t k_end = w1 / block_len;
         for (int pass = 0; pass < 4096; pass++) {
