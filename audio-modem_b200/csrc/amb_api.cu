@@ -167,7 +167,7 @@ inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
 int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_frame_result* d_res, uint8_t* d_bytes, int64_t bytes_stride) {
     if (n_jobs == 0) return AMB_OK;
     const AmbTables& T = m->tables;
-    const int64_t idx_stride = (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data;
+    const int64_t idx_stride = ((int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data + 15) / 16 * 16;      // rows 16-byte aligned for k_parse's vector loads
     CK(m->idx.ensure((size_t)n_jobs * idx_stride));
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));

@@ -1217,16 +1217,21 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint3
 }
 
 // majorityVote + bitsToBytes + frame parser + crc32 (modem.js:487-495, :468-476, :793-849, :607-653): one CTA per frame.
+#define AMB_PARSE_SMEM 8192      // decoded frames up to this many bytes are packed, parsed and checksummed in shared memory
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
-                                                const uint8_t* __restrict__ idx, int64_t idx_stride, amb_frame_result* __restrict__ results,
+                                                const uint8_t* __restrict__ idx, int64_t idx_stride /*multiple of 16*/, amb_frame_result* __restrict__ results,
                                                 uint8_t* __restrict__ bytes_out, int64_t bytes_stride, const uint32_t* __restrict__ crc_ops) {
     __shared__ uint32_t tab[256];
     __shared__ uint32_t sh[AMB_CRC_THREADS];
+    __shared__ __align__(16) uint8_t sb[AMB_PARSE_SMEM];
     __shared__ amb_frame_result sr;
     __shared__ long long s_crc_len;
     const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += AMB_CRC_THREADS) tab[i] = T->crc_table[i];
+    const int bps = T->bps, rep = T->rep;
     for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
         const AmbJob J = jobs[j];
+        __syncthreads();
         if (J.status != 0) {
             if (tid == 0) {
                 amb_frame_result r;
@@ -1238,25 +1243,52 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
             }
             continue;
         }
-        for (int i = tid; i < 256; i += AMB_CRC_THREADS) tab[i] = T->crc_table[i];
         uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
         const uint8_t* ix = idx + (int64_t)j * idx_stride;
         const int64_t n_elems = (int64_t)J.nsym * T->n_data;
-        const int64_t nb_full = amb_num_bytes(n_elems, T->bps, T->rep);
+        const int64_t nb_full = amb_num_bytes(n_elems, bps, rep);
         const int64_t nb = nb_full < bytes_stride ? nb_full : bytes_stride;
-        const int bps = T->bps, rep = T->rep;
-        for (int64_t b = tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = amb_pack_byte(ix, bps, rep, b);
+        const bool in_smem = nb <= AMB_PARSE_SMEM;
+        uint8_t* dst = in_smem ? sb : bytes;
+        // majorityVote + bitsToBytes.  Without repetition whole constellation indices pack into bytes: 8 (16-QAM) or 16 (QPSK)
+        // indices per 128-bit / 64-bit load make 4 bytes.
+        int64_t b0 = 0;
+        if (rep == 1 && bps == 4) {
+            const int64_t quads = nb / 4;
+            for (int64_t q = tid; q < quads; q += AMB_CRC_THREADS) {
+                const uint2 v = *reinterpret_cast<const uint2*>(ix + 8 * q);
+                // index bytes i0..i7 (little endian in v.x, v.y) -> output bytes (i0<<4|i1), (i2<<4|i3), ...
+                const uint32_t lo = v.x, hi = v.y;
+                const uint32_t o0 = ((lo & 0xF) << 4) | ((lo >> 8) & 0xF), o1 = (((lo >> 16) & 0xF) << 4) | ((lo >> 24) & 0xF);
+                const uint32_t o2 = ((hi & 0xF) << 4) | ((hi >> 8) & 0xF), o3 = (((hi >> 16) & 0xF) << 4) | ((hi >> 24) & 0xF);
+                const uint32_t w = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+                if (in_smem) *reinterpret_cast<uint32_t*>(sb + 4 * q) = w;
+                else { dst[4 * q] = (uint8_t)o0; dst[4 * q + 1] = (uint8_t)o1; dst[4 * q + 2] = (uint8_t)o2; dst[4 * q + 3] = (uint8_t)o3; }
+            }
+            b0 = quads * 4;
+        }
+        for (int64_t b = b0 + tid; b < nb; b += AMB_CRC_THREADS) dst[b] = amb_pack_byte(ix, bps, rep, b);
         __syncthreads();
+        if (in_smem) {
+            // decoded bytes to the caller's row (16-byte stores where the row allows)
+            if ((((uintptr_t)bytes) & 15) == 0) {
+                const int64_t vec = nb / 16;
+                for (int64_t q = tid; q < vec; q += AMB_CRC_THREADS) reinterpret_cast<uint4*>(bytes)[q] = reinterpret_cast<const uint4*>(sb)[q];
+                for (int64_t b = vec * 16 + tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = sb[b];
+            } else {
+                for (int64_t b = tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = sb[b];
+            }
+        }
         if (tid == 0) {
             amb_frame_result r;
             amb_result_clear(&r);
             r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
             int64_t crc_len = -1;
-            if (J.mode == 0) amb_parse_chunk_frame(tab, bytes, nb, &r, &crc_len);
-            else amb_parse_received(tab, bytes, nb, &r, &crc_len);
+            if (J.mode == 0) amb_parse_chunk_frame(tab, dst, nb, &r, &crc_len);
+            else amb_parse_received(tab, dst, nb, &r, &crc_len);
             r.n_bytes = (int32_t)nb_full;
             // decodeReceivedSignal attaches preambleIdx to chunk-type results even when their parser failed (modem.js:611-619)
-            const bool chunk_type = nb >= 10 && (bytes[0] == AMB_FRAME_META || bytes[0] == AMB_FRAME_DATA);
+            const bool chunk_type = nb >= 10 && (dst[0] == AMB_FRAME_META || dst[0] == AMB_FRAME_DATA);
             if (J.mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = J.result_pos;
             sr = r;
             s_crc_len = crc_len;
@@ -1264,11 +1296,10 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
         __syncthreads();
         const int64_t crc_len = s_crc_len;
         if (crc_len >= 0) {
-            const uint32_t c = block_crc32(tab, crc_ops, bytes, crc_len, sh);
+            const uint32_t c = block_crc32(tab, crc_ops, dst, crc_len, sh);
             if (tid == 0) { sr.actual_crc = c; sr.crc_valid = sr.expected_crc == c; }
         }
         if (tid == 0) results[j] = sr;
-        __syncthreads();
     }
 }
 
