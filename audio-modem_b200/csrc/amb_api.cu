@@ -49,7 +49,7 @@ struct amb_modem {
     AmbEmaTables* d_ema = nullptr;
     AmbFastTables* d_fast = nullptr;
     unsigned long long* d_fallbacks = nullptr;
-    uint32_t* d_crc_ops = nullptr;       // [AMB_CRC_MAXL][8] x^(8 L 2^k) mod P, the CRC combine constants per chunk length L
+    uint32_t* d_crc_ops = nullptr;       // [AMB_CRC_MAXL][AMB_CRC_OPS] powers of x mod P, the CRC combine constants per chunk length L
     bool fast_demod = true;
     bool fused_front = true;
     std::string err;
@@ -284,9 +284,11 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         }
         if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 8) != cudaSuccess) return bail(AMB_E_NOMEM);
         if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
-        std::vector<uint32_t> ops((size_t)AMB_CRC_MAXL * 8, 0u);
-        for (int L = 0; L < AMB_CRC_MAXL; L++)
-            for (int k = 0; k < 8; k++) ops[(size_t)L * 8 + k] = amb_gf_xpow8((uint32_t)L << k);
+        std::vector<uint32_t> ops((size_t)AMB_CRC_MAXL * AMB_CRC_OPS, 0u);
+        for (int L = 0; L < AMB_CRC_MAXL; L++) {
+            for (int k = 0; k < 32; k++) ops[(size_t)L * AMB_CRC_OPS + k] = amb_gf_xpow8((uint32_t)(L * k));
+            for (int k = 0; k < 4; k++) ops[(size_t)L * AMB_CRC_OPS + 32 + k] = amb_gf_xpow8((uint32_t)(L * 32 * k));
+        }
         if (cudaMalloc(&m->d_crc_ops, ops.size() * 4) != cudaSuccess) return bail(AMB_E_NOMEM);
         if (cudaMemcpy(m->d_crc_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
         const char* e = std::getenv("AMB_FAST_DEMOD");

@@ -547,10 +547,18 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
         const float* row = cleaned + (int64_t)s * stride;
         const int64_t a_hi = avail_hi - base_g;
         float x[3][8];
+        if (a_first >= 0 && a_first + 768 <= a_hi) {
+            const float* p0 = row + a_first + 8 * lane;
 #pragma unroll
-        for (int seg = 0; seg < 3; seg++)
+            for (int seg = 0; seg < 3; seg++)
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
+                for (int k = 0; k < 8; k++) x[seg][k] = p0[256 * seg + k];
+        } else {
+#pragma unroll
+            for (int seg = 0; seg < 3; seg++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
+        }
         double q[3][8], t[2][8], qb[3], tb[2];       // exclusive prefixes inside the segment; global base of the segment
         double run_q = 0.0, run_t = 0.0;
 #pragma unroll
@@ -576,7 +584,8 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
         double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
         int cand = 0, c_lo = 255, c_hi = 0;
         double oP[8], oA[8], oB[8];
-        double mmax = 0.0, mnA = 1.0, mnB = 1.0;          // over the windows with Ra, Rb > 0.0005 (amb_slot_cold)
+        float mmax = 0.f;                                 // over the windows with Ra, Rb > 0.0005 (amb_slot_cold); float: rounded up below
+        double mnA = 1.0, mnB = 1.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             oP[k] = valid ? P : 0.0; oA[k] = valid ? A : 0.0; oB[k] = valid ? B : 0.0;
             const bool c = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
             cand |= c;
-            if (valid && A > 0.0005 && B > 0.0005) { mnA = fmin(mnA, A); mnB = fmin(mnB, B); mmax = fmax(mmax, (P * P) / (A * B)); }
+            if (valid && A > 0.0005 && B > 0.0005) { mnA = fmin(mnA, A); mnB = fmin(mnB, B); mmax = fmaxf(mmax, (float)(P * P) / (float)(A * B)); }
             if (c) { c_lo = min(c_lo, 8 * lane + k); c_hi = max(c_hi, 8 * lane + k); }
         }
         const int any = __any_sync(0xffffffffu, cand);
@@ -601,12 +610,12 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
                 *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
             }
         }
-        mmax = warp_maxd(mmax);
+        mmax = warp_maxf(mmax);
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) { mnA = fmin(mnA, __shfl_xor_sync(0xffffffffu, mnA, o2)); mnB = fmin(mnB, __shfl_xor_sync(0xffffffffu, mnB, o2)); }
         if (lane == 0 && st.tsum) {
             float* ts = st.tsum + (int64_t)slot * 4;
-            ts[0] = (float)mmax * (1.f + 1e-6f) + 1e-30f; ts[1] = fmaxf((float)mnA * (1.f - 1e-6f), 0.f); ts[2] = fmaxf((float)mnB * (1.f - 1e-6f), 0.f); ts[3] = 0.f;
+            ts[0] = mmax * (1.f + 1e-6f) + 1e-30f; ts[1] = fmaxf((float)mnA * (1.f - 1e-6f), 0.f); ts[2] = fmaxf((float)mnB * (1.f - 1e-6f), 0.f); ts[3] = 0.f;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
@@ -1187,9 +1196,13 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
 // call; the result is returned to all.  tab: the 256-entry table in shared memory; sh: AMB_CRC_THREADS words.
 #define AMB_CRC_THREADS 128
 #define AMB_CRC_MAXL 768        // chunk lengths with precomputed combine constants (rows up to 128 * 767 bytes)
-__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint32_t* __restrict__ ops_table /*[AMB_CRC_MAXL][8]*/, const uint8_t* data,
+#define AMB_CRC_OPS 36          // per chunk length L: x^(8 L k), k = 0..31, then x^(8 L 32 k), k = 0..3
+// CTA-wide CRC-32 of data[0, n): thread t takes the end-aligned chunk t (amb_crc_chunk), then
+//   crc = XOR_t c_t * x^(8 L (127 - t)) = XOR_w [ (XOR_l c_{32 w + l} * x^(8 L (31 - l))) * x^(8 L 32 (3 - w)) ]:
+// one GF(2) multiplication per lane, a shuffle XOR reduction per warp, one more multiplication per warp.
+__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint32_t* __restrict__ ops_table /*[AMB_CRC_MAXL][AMB_CRC_OPS]*/, const uint8_t* data,
                                                 int64_t n, uint32_t* sh) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int64_t lo, hi;
     amb_crc_chunk(n, AMB_CRC_THREADS, tid, &lo, &hi);
     uint32_t c = 0;
@@ -1198,25 +1211,25 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint3
         for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
         c ^= 0xFFFFFFFFu;
     }
-    // level l of the tree multiplies by x^(8 L 2^l): host-made table for the usual chunk lengths, otherwise one thread
-    // per level computes its constant
-    __shared__ uint32_t ops[8];
     const int64_t L = (n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS;
-    if (tid < 7) ops[tid] = (ops_table && L < AMB_CRC_MAXL) ? ops_table[L * 8 + tid] : amb_gf_xpow8((uint32_t)(L << tid));
-    sh[tid] = c;
-    __syncthreads();
-    int level = 0;
-    for (int span = 1; span < AMB_CRC_THREADS; span <<= 1, level++) {
-        const bool act = (tid & (2 * span - 1)) == 0;
-        if (act) c = amb_gf_mul(c, ops[level]) ^ sh[tid + span];
-        __syncthreads();
-        if (act) sh[tid] = c;
-        __syncthreads();
+    const bool tabled = ops_table && L < AMB_CRC_MAXL;
+    const uint32_t pl = tabled ? ops_table[L * AMB_CRC_OPS + (31 - lane)] : amb_gf_xpow8((uint32_t)(L * (31 - lane)));
+    uint32_t v = amb_gf_mul(c, pl);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+        const int k = AMB_CRC_THREADS / 32 - 1 - warp;
+        const uint32_t pw = tabled ? ops_table[L * AMB_CRC_OPS + 32 + k] : amb_gf_xpow8((uint32_t)(L * 32 * k));
+        sh[warp] = amb_gf_mul(v, pw);
     }
-    return sh[0];
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int w = 0; w < AMB_CRC_THREADS / 32; w++) r ^= sh[w];
+    __syncthreads();
+    return r;
 }
 
-// majorityVote + bitsToBytes + frame parser + crc32 (modem.js:487-495, :468-476, :793-849, :607-653): one CTA per frame.
 #define AMB_PARSE_SMEM 8192      // decoded frames up to this many bytes are packed, parsed and checksummed in shared memory
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride /*multiple of 16*/, amb_frame_result* __restrict__ results,

@@ -96,20 +96,23 @@ int emu_scan_batch_fuzz(uint64_t seed, int n_cases) {
 
 // the chunked CRC-32 of block_crc32 (amb_kernels.cuh), threads run one after the other
 uint32_t emu_crc32_chunked(const uint8_t* data, int64_t n, int nt) {
+    // crc = XOR_t c_t * x^(8 L (nt - 1 - t)), grouped per 32 chunks as block_crc32 does (nt a multiple of 32, or < 32)
     AmbTables T;
     amb_tables_build(&T, 0, 1, 1);
-    std::vector<uint32_t> c((size_t)nt, 0);
-    for (int t = 0; t < nt; t++) {
-        int64_t lo, hi;
-        amb_crc_chunk(n, nt, t, &lo, &hi);
-        if (hi > lo) c[t] = amb_crc32_bytes(T.crc_table, data + lo, hi - lo);
+    const int64_t L = (n + nt - 1) / nt;
+    const int per = nt < 32 ? nt : 32, groups = nt / per;
+    uint32_t total = 0;
+    for (int w = 0; w < groups; w++) {
+        uint32_t v = 0;
+        for (int l = 0; l < per; l++) {
+            int64_t lo, hi;
+            amb_crc_chunk(n, nt, w * per + l, &lo, &hi);
+            const uint32_t c = hi > lo ? amb_crc32_bytes(T.crc_table, data + lo, hi - lo) : 0u;
+            v ^= amb_gf_mul(c, amb_gf_xpow8((uint32_t)(L * (per - 1 - l))));
+        }
+        total ^= amb_gf_mul(v, amb_gf_xpow8((uint32_t)(L * per * (groups - 1 - w))));
     }
-    uint32_t op = amb_gf_xpow8((uint32_t)((n + nt - 1) / nt));
-    for (int span = 1; span < nt; span <<= 1) {
-        for (int t = 0; t + span < nt; t += 2 * span) c[t] = amb_gf_mul(c[t], op) ^ c[t + span];
-        op = amb_gf_mul(op, op);
-    }
-    return c[0];
+    return total;
 }
 
 // decodeChunkFrame through the device logic
