@@ -71,7 +71,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc;
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
     cudaStream_t copy_stream = nullptr;          // host->device copies of sectioned pushes
     std::vector<cudaEvent_t> copy_events;
@@ -316,7 +316,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -693,7 +693,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -875,27 +875,53 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         }
         const int total = h[1];      // frames, h[2] = max data symbols
         if (total == 0) break;
-        CK(m->s_res.ensure((size_t)total * sizeof(amb_frame_result)));
-        CK(m->s_bytes.ensure((size_t)total * bytes_stride));
+        // Frames are decoded straight into the caller's rows [n_out, n_out + total): every frame is kept unless a metadata
+        // frame rewinds its stream (app.js:619-625 semantics in amb_post_frames), which is rare; only then (or when the rows
+        // would overflow) the frames go through a scratch copy and are compacted.
+        const bool direct = dst_res && dst_bytes && (int64_t)n_out + total <= max_results;
+        if (!direct) { CK(m->s_res.ensure((size_t)total * sizeof(amb_frame_result))); CK(m->s_bytes.ensure((size_t)total * bytes_stride)); }
+        amb_frame_result* pres = direct ? dst_res + n_out : m->s_res.as<amb_frame_result>();
+        uint8_t* pbytes = direct ? dst_bytes + (size_t)n_out * bytes_stride : m->s_bytes.as<uint8_t>();
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
-        if ((rc = run_demod_parse(m, total, h[2], true, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(), bytes_stride))) return rc;
-        LAUNCH("k_post_stream", k_post_stream<<<ns, (int64_t)total > 8192ll * ns ? 1024 : 128, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
-                                                                  m->s_res.as<amb_frame_result>(), ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
-                                                                  m->redo.as<int>(), m->n_redo.as<int>(), g.k_end));
+        if ((rc = run_demod_parse(m, total, h[2], true, pres, pbytes, bytes_stride))) return rc;
+        {
+            int64_t parts = ((int64_t)total / ns + 1023) / 1024;
+            if (parts < 1) parts = 1;
+            if (parts > 64) parts = 64;
+            CK(m->post_acc.ensure((size_t)ns * 6 * 8));
+            CK(cudaMemsetAsync(m->post_acc.p, 0, (size_t)ns * 6 * 8, m->stream));
+            LAUNCH("k_post_stream", k_post_stream<<<ns * (int)parts, 256, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+                                                                      pres, ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
+                                                                      m->redo.as<int>(), m->n_redo.as<int>(), g.k_end, (int)parts, m->post_acc.as<unsigned long long>()));
+        }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
-        LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
-                                               bytes_stride, n_out, max_results, dst_res, dst_bytes));
+        if (!direct) {
+            LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, pres, pbytes, bytes_stride, n_out, max_results, dst_res, dst_bytes));
+        }
         CK(cudaMemcpyAsync(h + 3, m->total.as<int>() + 2, 4, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaMemcpyAsync(h + 4, m->n_redo.p, 4, cudaMemcpyDeviceToHost, m->stream));
-        if (results_mem == AMB_MEM_HOST) {
-            // rows [n_out, n_out + total) cover everything this pass can have kept
-            const int lo = n_out < max_results ? n_out : max_results, hi = n_out + total < max_results ? n_out + total : max_results;
+        auto rows_to_host = [&](int count) -> int {
+            // rows [n_out, n_out + count) of the device staging to the caller's host buffers
+            if (results_mem != AMB_MEM_HOST) return AMB_OK;
+            const int lo = n_out < max_results ? n_out : max_results, hi = n_out + count < max_results ? n_out + count : max_results;
             if (hi > lo && results) CK(cudaMemcpyAsync(results + lo, m->g_res.as<amb_frame_result>() + lo, (size_t)(hi - lo) * sizeof(amb_frame_result), cudaMemcpyDeviceToHost, m->stream));
             if (hi > lo && bytes_out) CK(cudaMemcpyAsync(bytes_out + (size_t)lo * bytes_stride, m->g_bytes.as<uint8_t>() + (size_t)lo * bytes_stride, (size_t)(hi - lo) * bytes_stride,
                                                          cudaMemcpyDeviceToHost, m->stream));
-        }
+            return AMB_OK;
+        };
+        if ((rc = rows_to_host(total))) return rc;      // everything this pass can have kept
         CK(cudaStreamSynchronize(m->stream));
+        if (direct && h[3] < total) {
+            // some frames were dropped: compact the rows through a scratch copy
+            CK(m->s_res.ensure((size_t)total * sizeof(amb_frame_result))); CK(m->s_bytes.ensure((size_t)total * bytes_stride));
+            CK(cudaMemcpyAsync(m->s_res.p, pres, (size_t)total * sizeof(amb_frame_result), cudaMemcpyDeviceToDevice, m->stream));
+            CK(cudaMemcpyAsync(m->s_bytes.p, pbytes, (size_t)total * bytes_stride, cudaMemcpyDeviceToDevice, m->stream));
+            LAUNCH("k_gather", k_gather<<<total, 128, 0, m->stream>>>(m->keep.as<int>(), m->keep_off.as<int>(), total, m->s_res.as<amb_frame_result>(), m->s_bytes.as<uint8_t>(),
+                                                   bytes_stride, n_out, max_results, dst_res, dst_bytes));
+            if ((rc = rows_to_host(h[3]))) return rc;
+            CK(cudaStreamSynchronize(m->stream));
+        }
         int n_redo = h[4];
         if (n_redo > ns) n_redo = ns;
         n_out += h[3];

@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     const float* xrow = a.x + (int64_t)s * a.x_stride;
     float* crow = a.cleaned + (int64_t)s * a.stride + a.off0;
     const int tb = t0 - a.warm > 0 ? t0 - a.warm : 0;
-    double m_tile = tb == 0 ? a.states[s].dc_mean : 0.0;
+    // The EMA runs on u = m / beta (u <- alpha u + x: one FMA per sample instead of a multiplication and an FMA), and
+    // cleaned = x - beta u is one more FMA.
+    double m_tile = tb == 0 ? a.states[s].dc_mean / beta : 0.0;
     // ---- history of the scan part: lives in buffer 1 (the first full tile goes to buffer 0)
     for (int i = tid; i < 2 * AMB_FR_BUF; i += 256) R[i] = 0.f;
     sq[0][tid] = sa[0][tid] = sT[0][tid] = sI[0][tid] = sJ[0][tid] = 0.f;
@@ -373,11 +375,14 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
             if (tid == 31) { sWq[1][7] = iq; sWt[1][7] = it; }
         }
     }
-    // stage the first tile's input
-    {
-        const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)tb * AMB_TILE);
+    // stage the first tile's input (thread t copies the 16-byte pieces t, t + 256, ...: coalesced)
+    unsigned xs_dst[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; cp_async16(XS + AMB_FR_PAD(4 * f), src + f); }
+    for (int k = 0; k < 4; k++) xs_dst[k] = (unsigned)__cvta_generic_to_shared(XS + AMB_FR_PAD(4 * (tid + 256 * k)));
+    {
+        const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)tb * AMB_TILE) + tid;
+#pragma unroll
+        for (int k = 0; k < 4; k++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(xs_dst[k]), "l"(src + 256 * k));
         cp_async_wait_all();
     }
     __syncthreads();
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         // ---- EMA over the tile: response of the 16 samples from a zero state (two independent chains of 8) ...
         double r1 = 0.0, r2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) { r1 = fma(alpha, r1, beta * (double)x[k]); r2 = fma(alpha, r2, beta * (double)x[8 + k]); }
+        for (int k = 0; k < 8; k++) { r1 = fma(alpha, r1, (double)x[k]); r2 = fma(alpha, r2, (double)x[8 + k]); }
         const double a8 = E->a8;
         double B = fma(a8, r1, r2);
 #pragma unroll
@@ -403,9 +408,9 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         if (lane == 31) sW[warp] = B;
         __syncthreads();                                                // (1) warp totals; every thread has read its staged input
         if (t + 1 < t1) {
-            const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)(t + 1) * AMB_TILE);
+            const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)(t + 1) * AMB_TILE) + tid;
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; cp_async16(XS + AMB_FR_PAD(4 * f), src + f); }
+            for (int k = 0; k < 4; k++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(xs_dst[k]), "l"(src + 256 * k));
         }
         double S = m_tile, m_next = m_tile;
 #pragma unroll
@@ -419,8 +424,8 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         float c[16];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            mA = fma(alpha, mA, beta * (double)x[k]); c[k] = (float)((double)x[k] - mA);
-            mB = fma(alpha, mB, beta * (double)x[8 + k]); c[8 + k] = (float)((double)x[8 + k] - mB);
+            mA = fma(alpha, mA, (double)x[k]); c[k] = (float)fma(-beta, mA, (double)x[k]);
+            mB = fma(alpha, mB, (double)x[8 + k]); c[8 + k] = (float)fma(-beta, mB, (double)x[8 + k]);
         }
         float* Rc = R + (n & 1) * AMB_FR_BUF;                           // this tile
         const float* Rp = R + ((n + 1) & 1) * AMB_FR_BUF;               // its predecessor
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         }
         n++;
     }
-    if (t1 == a.tiles && tid == 0) a.dc_next[s] = m_tile;
+    if (t1 == a.tiles && tid == 0) a.dc_next[s] = m_tile * beta;
 }
 
 // Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
@@ -1716,38 +1721,55 @@ __global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __rest
 // Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the streams whose
 // collection window changed for another walk.  One CTA per stream.  Without a CRC-valid metadata frame among them (the
 // steady state) the frames only move counters, which is a parallel count; otherwise thread 0 applies them sequentially.
-__global__ void __launch_bounds__(1024) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
+__global__ void __launch_bounds__(256) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
                               const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
                               AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
-                              int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end) {
-    const int s = blockIdx.x;
+                              int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end, int parts,
+                              unsigned long long* __restrict__ acc /*[n_streams][6], zeroed: fd, fe, rc, ce, valid metadata, finished parts*/) {
+    // `parts` CTAs share one stream: each counts a slice of its frames into acc, the last one to finish applies the result
+    const int s = blockIdx.x / parts, part = blockIdx.x % parts;
     if (s >= n_streams) return;
     const int cnt = nrec[s], o = job_off[s], tid = threadIdx.x;
     if (cnt == 0) return;
-    __shared__ int n_valid_meta;
-    __shared__ unsigned long long c_fd, c_fe, c_rc, c_ce;
-    if (tid == 0) { n_valid_meta = 0; c_fd = c_fe = c_rc = c_ce = 0ull; }
+    __shared__ unsigned c_fd, c_fe, c_rc, c_ce, c_vm;
+    __shared__ int is_last;
+    if (tid == 0) { c_fd = c_fe = c_rc = c_ce = c_vm = 0u; }
     __syncthreads();
     const AmbStreamState cur = states[s];
-    unsigned fd = 0, fe = 0, rc = 0, ce = 0;
-    for (int i = tid; i < cnt; i += blockDim.x) {
+    unsigned fd = 0, fe = 0, rc = 0, ce = 0, vm = 0;
+    for (int i = part * blockDim.x + tid; i < cnt; i += parts * blockDim.x) {
         const amb_frame_result& r = results[o + i];
         keep[o + i] = 1;
         if (r.status != 0) { fe++; continue; }
         fd++;
-        if (r.frame_type == AMB_FRAME_META) { if (r.crc_valid) atomicAdd(&n_valid_meta, 1); else fe++; }
+        if (r.frame_type == AMB_FRAME_META) { if (r.crc_valid) vm++; else fe++; }
         else if (r.frame_type == AMB_FRAME_DATA && cur.meta_received == 1 && !(r.seq_num >= cur.total_chunks)) { if (r.crc_valid) rc++; else ce++; }
     }
-    atomicAdd(&c_fd, (unsigned long long)fd); atomicAdd(&c_fe, (unsigned long long)fe);
-    atomicAdd(&c_rc, (unsigned long long)rc); atomicAdd(&c_ce, (unsigned long long)ce);
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+        fd += __shfl_xor_sync(0xffffffffu, fd, of); fe += __shfl_xor_sync(0xffffffffu, fe, of); rc += __shfl_xor_sync(0xffffffffu, rc, of);
+        ce += __shfl_xor_sync(0xffffffffu, ce, of); vm += __shfl_xor_sync(0xffffffffu, vm, of);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&c_fd, fd); atomicAdd(&c_fe, fe); atomicAdd(&c_rc, rc); atomicAdd(&c_ce, ce); atomicAdd(&c_vm, vm); }
     __syncthreads();
-    if (tid != 0) return;
+    unsigned long long* A = acc + (int64_t)s * 6;
+    if (tid == 0) {
+        atomicAdd(A, (unsigned long long)c_fd); atomicAdd(A + 1, (unsigned long long)c_fe); atomicAdd(A + 2, (unsigned long long)c_rc);
+        atomicAdd(A + 3, (unsigned long long)c_ce); atomicAdd(A + 4, (unsigned long long)c_vm);
+        __threadfence();
+        is_last = atomicAdd(A + 5, 1ull) == (unsigned long long)(parts - 1);
+    }
+    __syncthreads();
+    if (!is_last || tid != 0) return;
+    __threadfence();
+    const unsigned long long t_fd = atomicAdd(A, 0ull), t_fe = atomicAdd(A + 1, 0ull), t_rc = atomicAdd(A + 2, 0ull), t_ce = atomicAdd(A + 3, 0ull),
+                             t_vm = atomicAdd(A + 4, 0ull);
     AmbStreamState st;
     int redo = 0;
-    if (n_valid_meta > 0) redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o);
+    if (t_vm > 0) redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o);
     else {
         st = cur;
-        st.frames_decoded += (int64_t)c_fd; st.frame_errors += (int64_t)c_fe; st.received += (int64_t)c_rc; st.crc_errors += (int64_t)c_ce;
+        st.frames_decoded += (int64_t)t_fd; st.frame_errors += (int64_t)t_fe; st.received += (int64_t)t_rc; st.crc_errors += (int64_t)t_ce;
     }
     states[s] = st;
     // a stream still waiting for its metadata frame advances one frame per pass (k_walk, pre_meta_only)
