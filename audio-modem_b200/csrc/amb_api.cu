@@ -298,6 +298,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     }
     cudaFuncSetAttribute(k_demod_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
+    cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
@@ -858,7 +859,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         for (int it = 0; n_active > 0 && it < (1 << 20); it++) {
             m->link_iterations++;
             CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
-            LAUNCH("k_chain_links", k_chain_links<<<ns, ns < 64 ? 1024 : 256, 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L));
+            LAUNCH("k_chain_links", k_chain_links<<<ns, ns < 64 ? 1024 : 256, ns < 64 ? AMB_CHAIN_SMEM : 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L, ns < 64 ? AMB_CHAIN_SMEM_RUNS : 0));
             LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));

@@ -1692,30 +1692,35 @@ __global__ void __launch_bounds__(128) k_gather(const int* __restrict__ keep, co
     }
 }
 
-// exclusive prefix of nrec over streams (single block), total in *total
-__global__ void k_prefix_counts(const int* __restrict__ nrec, int n, int* __restrict__ off, int* __restrict__ total) {
+// exclusive prefix of nrec over streams (single block of 1024 threads), total in *total
+__global__ void __launch_bounds__(1024) k_prefix_counts(const int* __restrict__ nrec, int n, int* __restrict__ off, int* __restrict__ total) {
+    __shared__ int wtot[32];
     __shared__ int carry;
-    __shared__ int buf[1024];
-    if (threadIdx.x == 0) carry = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
+        const int i = base + tid;
         const int v = i < n ? nrec[i] : 0;
-        buf[threadIdx.x] = v;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) wtot[warp] = inc;
         __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int a = 0;
-            if ((int)threadIdx.x >= o) a = buf[threadIdx.x - o];
-            __syncthreads();
-            buf[threadIdx.x] += a;
-            __syncthreads();
+        if (warp == 0) {
+            int w = wtot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+            wtot[lane] = w;                      // inclusive totals of the warps
         }
-        if (i < n) off[i] = carry + buf[threadIdx.x] - v;
         __syncthreads();
-        if (threadIdx.x == 1023) carry += buf[1023];
+        const int c = carry + (warp ? wtot[warp - 1] : 0);
+        if (i < n) off[i] = c + inc - v;
+        __syncthreads();
+        if (tid == 1023) carry = c + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (tid == 0) *total = carry;
 }
 
 // Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the streams whose
@@ -2192,7 +2197,9 @@ __global__ void k_chain_next(int n_streams, AmbLinkBufs L) {
 
 // Speculated chain of an active stream from its current (post-reset) state: the runs reachable through next[],
 // in order, plus a tail link when the last of them is expected to emit a frame.  One CTA per stream.
-__global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamState* __restrict__ states, AmbLinkBufs L) {
+#define AMB_CHAIN_SMEM_RUNS 20480
+#define AMB_CHAIN_SMEM (AMB_CHAIN_SMEM_RUNS * 5)
+__global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamState* __restrict__ states, AmbLinkBufs L, int smem_runs) {
     const int s = blockIdx.x;
     if (s >= n_streams) return;
     const int tid = threadIdx.x;
@@ -2212,6 +2219,24 @@ __global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamSt
     const AmbStreamState st = states[s];
     int first = n;
     if (st.state == AMB_RX_IDLE && !st.ac_init) first = amb_run_at_or_after(runs, n, st.ac_scan_pos);
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    if (n <= smem_runs && n < 65535) {
+        // the whole pointer-doubling runs in shared memory (16-bit run indices)
+        unsigned short* sa = reinterpret_cast<unsigned short*>(chain_smem);
+        unsigned short* sb2 = sa + AMB_CHAIN_SMEM_RUNS;
+        unsigned char* sv = reinterpret_cast<unsigned char*>(sb2 + AMB_CHAIN_SMEM_RUNS);
+        for (int r = tid; r < n; r += blockDim.x) { sv[r] = r == first; sa[r] = (unsigned short)L.next[off + r]; }
+        __syncthreads();
+        for (int span = 1; span < n; span <<= 1) {
+            for (int r = tid; r < n; r += blockDim.x) if (sv[r] && sa[r] < n) sv[sa[r]] = 1;
+            __syncthreads();
+            for (int r = tid; r < n; r += blockDim.x) { const int j = sa[r]; sb2[r] = (unsigned short)(j < n ? sa[j] : n); }
+            __syncthreads();
+            unsigned short* t = sa; sa = sb2; sb2 = t;
+        }
+        for (int r = tid; r < n; r += blockDim.x) vis[r] = sv[r];
+        __syncthreads();
+    } else {
     for (int r = tid; r < n; r += blockDim.x) { vis[r] = r == first; ja[r] = L.next[off + r]; }
     __syncthreads();
     // pointer doubling: after round k every run within distance < 2^(k+1) of `first` is marked
@@ -2221,6 +2246,7 @@ __global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamSt
         for (int r = tid; r < n; r += blockDim.x) { const int j = ja[r]; jb[r] = j < n ? ja[j] : n; }
         __syncthreads();
         int* t = ja; ja = jb; jb = t;
+    }
     }
     // ordered compaction of the visited runs
     __shared__ int wsum[32];
