@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             }
         }
         double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
-        int cand = 0, c_lo = 255, c_hi = 0;
+        int cand = 0, c_lo = 255, c_hi = 0, excluded = 0;
         double oP[8], oA[8], oB[8];
         float mmax = 0.f;                                 // over the windows with Ra, Rb > 0.0005 (amb_slot_cold); float: rounded up below
         double mnA = 1.0, mnB = 1.0;
@@ -602,25 +602,25 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
             const bool c = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
             cand |= c;
             if (valid && A > 0.0005 && B > 0.0005) { mnA = fmin(mnA, A); mnB = fmin(mnB, B); mmax = fmaxf(mmax, (float)(P * P) / (float)(A * B)); }
+            else if (valid) excluded = 1;
             if (c) { c_lo = min(c_lo, 8 * lane + k); c_hi = max(c_hi, 8 * lane + k); }
         }
         const int any = __any_sync(0xffffffffu, cand);
-        if (any) {
-            // the rows are only kept for tiles with a candidate: the walker skips the others by their extremes (amb_slot_cold)
-            // and, if its defect makes one of them hot after all, evaluates it itself
+        // (the rows are kept for every slot: the walker skips most non-candidate tiles by their extremes (amb_slot_cold), but a
+        // large defect - long idle stretches over a noise floor - defeats that test and the tile is then evaluated from its rows)
 #pragma unroll
-            for (int k = 0; k < 8; k += 2) {
-                *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
-                *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
-                *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
-            }
+        for (int k = 0; k < 8; k += 2) {
+            *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
+            *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
+            *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
         }
         mmax = warp_maxf(mmax);
+        const int any_excluded = __any_sync(0xffffffffu, excluded);
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) { mnA = fmin(mnA, __shfl_xor_sync(0xffffffffu, mnA, o2)); mnB = fmin(mnB, __shfl_xor_sync(0xffffffffu, mnB, o2)); }
         if (lane == 0 && st.tsum) {
             float* ts = st.tsum + (int64_t)slot * 4;
-            ts[0] = mmax * (1.f + 1e-6f) + 1e-30f; ts[1] = fmaxf((float)mnA * (1.f - 1e-6f), 0.f); ts[2] = fmaxf((float)mnB * (1.f - 1e-6f), 0.f); ts[3] = 0.f;
+            ts[0] = mmax * (1.f + 1e-6f) + 1e-30f; ts[1] = fmaxf((float)mnA * (1.f - 1e-6f), 0.f); ts[2] = fmaxf((float)mnB * (1.f - 1e-6f), 0.f); ts[3] = any_excluded ? 1.f : 0.f;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }

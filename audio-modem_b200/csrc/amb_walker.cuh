@@ -90,15 +90,16 @@ AMB_HD bool amb_tile_hot(const float* s, double Ep, double Ea, double Eb) {
 }
 
 // Second, sharper test for a slotted tile, from the exact per-window values k_tri_store reduced over the windows with
-// Ra > 0.0005 and Rb > 0.0005 (half the energy gate; with |Ea|, |Eb| < 0.0004 no other window can pass the gate of 0.001):
-// max metric (no defect, rounded up), min Ra, min Rb (rounded down).  With the defect E in force,
+// Ra > 0.0005 and Rb > 0.0005 (half the energy gate): max metric (no defect, rounded up), min Ra, min Rb (rounded down), and
+// whether any window was left out.  Left-out windows cannot pass the gate of 0.001 unless the defect adds more than 0.0004
+// to an energy.  With the defect E in force,
 //   sqrt(metric') = |P + Ep| / sqrt((Ra + Ea)(Rb + Eb)) <= sqrt(metric) sqrt(Ra Rb / (Ra' Rb')) + |Ep| / sqrt(Ra' Rb'),
 // Ra' >= Ra - |Ea| >= minRa - |Ea| (and Ra / Ra' is largest at the smallest Ra).  True = no window of the tile can be a
 // candidate.
 AMB_HD bool amb_slot_cold(const float* ts, double Ep, double Ea, double Eb) {
-    if (!(fabs(Ea) < 0.0004) || !(fabs(Eb) < 0.0004)) return false;
-    const double mA = (double)ts[1] - fabs(Ea), mB = (double)ts[2] - fabs(Eb);      // > 0.0001
-    if (!(mA > 0.0) || !(mB > 0.0)) return false;
+    if (ts[3] != 0.f && (!(Ea < 0.0004) || !(Eb < 0.0004))) return false;
+    const double mA = (double)ts[1] - fabs(Ea), mB = (double)ts[2] - fabs(Eb);
+    if (!(mA > 1e-4) || !(mB > 1e-4)) return false;
     const double ka = (double)ts[1] / mA, kb = (double)ts[2] / mB;
     const double r = sqrt((double)ts[0] * ka * kb) * (1.0 + 1e-6) + fabs(Ep) / sqrt(mA * mB);
     return r * r < 0.5 * (1.0 - 1e-6);

@@ -250,6 +250,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
             float ap = 0, mnA = 3e38f, mxA = 0, mnB = 3e38f, mxB = 0;
             bool hot = false, cand = false;
             double mmax = 0.0, xmnA = 1.0, xmnB = 1.0;
+            bool excluded = false;
             std::vector<double> t3(256 * 3, 0.0);
             for (int64_t q = j * 256; q < (j + 1) * 256; q++) {
                 const int64_t d = q - 511;
@@ -260,6 +261,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 hot |= A > 0.0009 && B > 0.0009 && P * P > 0.25 * A * B;
                 cand |= A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
                 if (A > 0.0005 && B > 0.0005) { xmnA = fmin(xmnA, A); xmnB = fmin(xmnB, B); mmax = fmax(mmax, (P * P) / (A * B)); }
+                else excluded = true;
                 ap = fmaxf(ap, (float)fabs(P)); mnA = fminf(mnA, (float)A); mxA = fmaxf(mxA, (float)A); mnB = fminf(mnB, (float)B); mxB = fmaxf(mxB, (float)B);
             }
             float* o = &sums[(size_t)j * AMB_SUM_W];
@@ -272,7 +274,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
             if (g_use_stores && hot) {
                 tile_slot[(size_t)j] = n_slots++;
                 tsum.push_back((float)mmax * (1.f + 1e-6f) + 1e-30f); tsum.push_back(fmaxf((float)xmnA * (1.f - 1e-6f), 0.f));
-                tsum.push_back(fmaxf((float)xmnB * (1.f - 1e-6f), 0.f)); tsum.push_back(0.f);
+                tsum.push_back(fmaxf((float)xmnB * (1.f - 1e-6f), 0.f)); tsum.push_back(excluded ? 1.f : 0.f);
                 tri.insert(tri.end(), t3.begin(), t3.end());
                 xc.resize((size_t)n_slots * xc_w, AMB_XC_UNSURE);
                 if (cand) {
