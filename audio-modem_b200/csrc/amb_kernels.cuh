@@ -316,23 +316,46 @@ struct AmbFrontArgs {
 
 #define AMB_FR_PAD(i) ((i) + (((i) >> 4) << 2))       // 4 floats of padding per 16: conflict-free 128-bit rows per thread
 #define AMB_FR_BUF AMB_FR_PAD(AMB_TILE)               // floats per padded tile buffer (5120)
-#define AMB_FRONT_SMEM (3 * AMB_FR_BUF * 4)           // two cleaned tiles (double buffer) + one staged input tile
+#define AMB_FRONT_SMEM (2 * AMB_FR_BUF * 4 + AMB_TILE * 4)   // two cleaned tiles (double buffer, padded) + one staged input tile (linear)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+// TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk; UBLKCP in SASS)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // Shared-memory layout: cleaned tiles are double-buffered (tile n in buffer n & 1), so the 256 samples and the 32
 // sub-block sums a tile needs from its predecessor are read in place and nothing is shifted; the per-sub-block arrays
 // hold q, a and the warp-inclusive scans of q and t, from which any block-wide prefix is one addition away.  The next
-// tile's input is copied global -> shared asynchronously (cp.async, coalesced) while the current one is processed.
-// Three barriers per tile.
+// tile's input (16 KB) is staged global -> shared by one TMA bulk copy (cp.async.bulk, completion on an mbarrier) while
+// the current one is processed.  Three barriers per tile.
 __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* R = reinterpret_cast<float*>(smem_raw);                     // [2][AMB_FR_BUF]
-    float* XS = R + 2 * AMB_FR_BUF;                                    // [AMB_FR_BUF] staged input
+    float* XS = R + 2 * AMB_FR_BUF;                                    // [AMB_TILE] staged input, linear (bulk-copy destination)
+    __shared__ __align__(8) uint64_t xs_bar;
     __shared__ float sq[2][256], sa[2][256], sT[2][256], sI[2][256], sJ[2][256];   // q_e, a_e, t_e, warp-inclusive scans of q_e and t_e
     __shared__ float sWq[2][8], sWt[2][8];                             // warp totals of q and t
     __shared__ double sW[8];
@@ -375,25 +398,21 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
             if (tid == 31) { sWq[1][7] = iq; sWt[1][7] = it; }
         }
     }
-    // stage the first tile's input (thread t copies the 16-byte pieces t, t + 256, ...: coalesced)
-    unsigned xs_dst[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) xs_dst[k] = (unsigned)__cvta_generic_to_shared(XS + AMB_FR_PAD(4 * (tid + 256 * k)));
-    {
-        const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)tb * AMB_TILE) + tid;
-#pragma unroll
-        for (int k = 0; k < 4; k++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(xs_dst[k]), "l"(src + 256 * k));
-        cp_async_wait_all();
-    }
+    // stage the first tile's input
+    if (tid == 0) { mbar_init(&xs_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     __syncthreads();
+    if (tid == 0) { mbar_expect_tx(&xs_bar, AMB_TILE * 4); bulk_g2s(XS, xrow + (int64_t)tb * AMB_TILE, AMB_TILE * 4, &xs_bar); }
+    unsigned xs_phase = 0;
     int n = 0;                                                          // full tiles done: the current one uses buffer n & 1
     for (int t = tb; t < t1; t++) {
         const bool ema_only = t < t0 - 1;
         const bool emit = t >= t0;
         // ---- this thread's 16 input samples (staged), then start staging the next tile
         float x[16];
+        mbar_wait(&xs_bar, xs_phase);
+        xs_phase ^= 1u;
         {
-            const float4* src = reinterpret_cast<const float4*>(XS + AMB_FR_PAD(16 * tid));
+            const float4* src = reinterpret_cast<const float4*>(XS + 16 * tid);
 #pragma unroll
             for (int q4 = 0; q4 < 4; q4++) { const float4 v = src[q4]; x[4 * q4] = v.x; x[4 * q4 + 1] = v.y; x[4 * q4 + 2] = v.z; x[4 * q4 + 3] = v.w; }
         }
@@ -407,16 +426,16 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         for (int k = 0; k < 5; k++) { const double u = __shfl_up_sync(0xffffffffu, B, 1 << k); if (lane >= (1 << k)) B = fma(E->steppow[k], u, B); }
         if (lane == 31) sW[warp] = B;
         __syncthreads();                                                // (1) warp totals; every thread has read its staged input
-        if (t + 1 < t1) {
-            const float4* src = reinterpret_cast<const float4*>(xrow + (int64_t)(t + 1) * AMB_TILE) + tid;
-#pragma unroll
-            for (int k = 0; k < 4; k++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(xs_dst[k]), "l"(src + 256 * k));
+        if (t + 1 < t1 && tid == 0) {
+            fence_proxy_async();                                        // the threads' reads of XS are ordered before the bulk write
+            mbar_expect_tx(&xs_bar, AMB_TILE * 4);
+            bulk_g2s(XS, xrow + (int64_t)(t + 1) * AMB_TILE, AMB_TILE * 4, &xs_bar);
         }
         double S = m_tile, m_next = m_tile;
 #pragma unroll
         for (int w = 0; w < 8; w++) { m_next = fma(a512, m_next, sW[w]); if (w + 1 == warp) S = m_next; }
         m_tile = m_next;
-        if (ema_only) { cp_async_wait_all(); __syncthreads(); continue; }
+        if (ema_only) { __syncthreads(); continue; }
         // ... then the true state entering the thread, and the cleaned samples (two chains again)
         const double Bex = __shfl_up_sync(0xffffffffu, B, 1);
         double mA = fma(lp, S, lane ? Bex : 0.0);
@@ -465,8 +484,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         }
         sq[cb][tid] = q; sa[cb][tid] = at; sT[cb][tid] = tt; sI[cb][tid] = iq; sJ[cb][tid] = it;
         if (lane == 31) { sWq[cb][warp] = iq; sWt[cb][warp] = it; }
-        cp_async_wait_all();
-        __syncthreads();                                                // (3) sub-block arrays; the next input tile is staged
+        __syncthreads();                                                // (3) sub-block arrays
         if (emit) {
             // block-wide exclusive prefixes, relative to the tile start: QS(e) = off(warp of e) + sI[e] - sq[e]; in the
             // predecessor's last warp (e < 0): QS(e) = sI_p[256 + e] - sq_p[256 + e] - sWq_p[7]

@@ -45,6 +45,8 @@ def test_sass_is_sm100_and_has_no_tensor_core_ops(amb):
     assert "sm_100" in out.stdout
     # nothing on this path is a dense contraction: no HMMA / UTC*MMA / GMMA may appear
     assert not re.search(r"\b(HMMA|UTC[A-Z]*MMA|HGMMA|IGMMA|QGMMA)\b", out.stdout)
+    # the scanner front end stages its input tiles with TMA bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier
+    assert re.search(r"\bUBLKCP\b", out.stdout) and re.search(r"\bSYNCS\b", out.stdout)
 
 
 def test_host_helpers_need_no_gpu(amb, O):
