@@ -961,7 +961,8 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     // after it are still in flight.
     const int64_t blocks = n_new / m->block_len;
     int64_t n_sec = 1;
-    if (mem == AMB_MEM_HOST && (int64_t)ns * n_new * 4 >= (64ll << 20) && blocks >= 8) n_sec = 8;
+    static const int64_t sec_min_bytes = std::getenv("AMB_SECTION_MIN_BYTES") ? std::atoll(std::getenv("AMB_SECTION_MIN_BYTES")) : (64ll << 20);
+    if (mem == AMB_MEM_HOST && (int64_t)ns * n_new * 4 >= sec_min_bytes && blocks >= 8) n_sec = 8;
     if (n_sec == 1) {
         CK(cudaMemcpy2DAsync(raw, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
                              mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));

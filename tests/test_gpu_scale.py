@@ -123,3 +123,32 @@ def test_c5_many_streams(O, amb):
         m.stream_close()
     finally:
         m.close()
+
+
+def test_sectioned_host_push_equals_one_push(O, amb):
+    """large host pushes are cut into sections whose copies overlap the processing (amb_stream_push): same events as the
+    oracle, also when the results of several sections land in the caller's buffers back to back"""
+    import os
+    import subprocess
+    import sys
+
+    # the threshold is read once per process: run the comparison in a child with a small one
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "import audio_modem_b200 as amb\n"
+        "from oracle import oracle as O\n"
+        "from helpers import make_stream, results_equal\n"
+        "x, pay = make_stream(O, '16-QAM', 40, 123)\n"
+        "m = amb.Modem('standard', 'QAM16', 1, device=0)\n"
+        "m.stream_open(1, 4096, len(x))\n"
+        "got = m.stream_push(x[None, :], raw=True)\n"
+        "want = O.StreamingReceiver('standard', 'QAM16', 1).push(x, 4096, raw=True)\n"
+        "assert len(got) == len(want) == 41, (len(got), len(want))\n"
+        "for (r1, b1), (r2, b2) in zip(want, got):\n"
+        "    assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], r1.preamble_idx\n"
+        "print('sections ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AMB_SECTION_MIN_BYTES="65536")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "sections ok" in out.stdout, out.stdout + out.stderr
