@@ -51,7 +51,6 @@ struct amb_modem {
     unsigned long long* d_fallbacks = nullptr;
     uint32_t* d_crc_ops = nullptr;       // [AMB_CRC_MAXL][AMB_CRC_OPS] powers of x mod P, the CRC combine constants per chunk length L
     bool fast_demod = true;
-    bool fused_front = true;
     std::string err;
     int64_t launches = 0;
     // optional per-kernel device timing (CUDA events on the handle's stream)
@@ -68,7 +67,7 @@ struct amb_modem {
     int n_streams = 0;
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
-    DevBuf raw, cleaned, sums, agg, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
+    DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc;
@@ -268,9 +267,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     if (cudaMalloc(&m->d_ema, sizeof(AmbEmaTables)) != cudaSuccess) return bail(AMB_E_NOMEM);
     AmbEmaTables e;
     const long double a = (long double)m->tables.dc_alpha;
-    for (int k = 0; k < AMB_CHUNK; k++) e.w_in[k] = (double)((long double)m->tables.dc_beta * powl(a, (long double)(AMB_CHUNK - 1 - k)));
-    for (int j = 0; j <= AMB_EMA_TERMS; j++) e.w_chunk[j] = (double)powl(a, (long double)(AMB_CHUNK * j));
-    e.a16 = (double)powl(a, 16.0L); e.alpha = m->tables.dc_alpha; e.beta = m->tables.dc_beta;
+    e.a512 = (double)powl(a, 512.0L); e.alpha = m->tables.dc_alpha; e.beta = m->tables.dc_beta;
     for (int i = 0; i < 32; i++) e.lanepow[i] = (double)powl(a, 16.0L * i);
     for (int k = 0; k < 5; k++) e.steppow[k] = (double)powl(a, 16.0L * (1 << k));
     e.a8 = (double)powl(a, 8.0L);
@@ -293,8 +290,6 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         if (cudaMemcpy(m->d_crc_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
-        const char* f = std::getenv("AMB_FUSED_FRONT");
-        m->fused_front = !(f && f[0] == '0');
     }
     cudaFuncSetAttribute(k_demod_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
@@ -312,7 +307,7 @@ void amb_destroy(amb_modem* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx,
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
-                     &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
+                     &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
@@ -645,7 +640,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     // lives in `cleaned`
     CK(m->raw.ensure(ns * m->max_push * 4)); CK(m->cleaned.ensure(ns * m->stride * 4));
     CK(m->sums.ensure(ns * m->sum_stride * AMB_SUM_W * 4));
-    CK(m->agg.ensure(ns * (size_t)(max_push / AMB_CHUNK) * 8)); CK(m->dc_next.ensure(ns * 8));
+    CK(m->dc_next.ensure(ns * 8));
     CK(m->states.ensure(ns * sizeof(AmbStreamState))); CK(m->recs.ensure(ns * m->rec_cap * sizeof(AmbFrameRec)));
     CK(m->nrec.ensure(ns * 4)); CK(m->job_off.ensure(ns * 4)); CK(m->total.ensure(16)); CK(m->redo.ensure(ns * 4)); CK(m->n_redo.ensure(16));
     CK(cudaMemsetAsync(m->cleaned.p, 0, ns * m->stride * 4, m->stream));
@@ -689,7 +684,7 @@ int amb_stream_close(amb_modem* m) {
     if (!m) return AMB_E_INVALID;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
-    DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->agg, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
+    DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
@@ -750,7 +745,7 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
     CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
-    if (m->fused_front) {
+    {
         // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
         AmbFrontArgs fa;
         fa.x = src; fa.x_stride = src_stride; fa.cleaned = m->cleaned.as<float>(); fa.stride = m->stride; fa.off0 = off0;
@@ -763,17 +758,6 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         fa.E = m->d_ema; fa.states = m->states.as<AmbStreamState>(); fa.dc_next = m->dc_next.as<double>();
         fa.sums = m->sums.as<float>(); fa.sum_stride = m->sum_stride; fa.st = ss;
         LAUNCH("k_front", k_front<<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa));
-    } else {
-        // 1. DC removal
-        const int64_t n_chunks = n_new / AMB_CHUNK;
-        const int per = blocks_for(n_chunks, 4);
-        LAUNCH("k_ema_agg", k_ema_agg<<<ns * per, 128, 0, m->stream>>>(src, src_stride, n_chunks, per, m->d_ema, m->agg.as<double>()));
-        LAUNCH("k_ema_apply", k_ema_apply<<<ns * per, 128, 0, m->stream>>>(src, src_stride, m->cleaned.as<float>(), m->stride, off0, n_chunks, per, m->d_ema, m->agg.as<double>(),
-                                                     m->states.as<AmbStreamState>(), m->dc_next.as<double>()));
-        // 2. window-sum summaries of the new window-end samples
-        const int64_t n_warps = (int64_t)ns * tiles;
-        LAUNCH("k_scan_fast", k_scan_fast<<<blocks_for(n_warps, 8), 256, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, off0, m->written, tiles, m->sums.as<float>(),
-                                                                                        m->sum_stride, ss, n_warps));
     }
     LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < 148 * 16 ? (m->slot_cap + 3) / 4 : 148 * 16, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
     {

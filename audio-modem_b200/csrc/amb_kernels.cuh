@@ -7,8 +7,6 @@
 #include "amb_tx.cuh"
 
 #define AMB_TILE 4096        // samples per scan tile (= the reference's audio block, app.js:1107)
-#define AMB_CHUNK 512        // EMA carry granularity
-#define AMB_EMA_TERMS 80     // alpha^(512*80) ~ 1.6e-18: older chunks cannot change a float64 EMA
 #define AMB_SYM_GROUP 64     // data symbols per demod CTA
 #define AMB_HALO 512
 // 1-D grids: blockIdx.x = outer * per + inner (gridDim.y would cap streams at 65535)
@@ -41,83 +39,16 @@ __device__ __forceinline__ double warp_maxd(double v) {
 }
 
 // ================================================================================================
-// EMA DC removal (app.js:750-755):  m <- alpha*m + beta*x,  cleaned = f32(x - m)
-// The recurrence is linear, so the state entering 512-sample chunk c of a push is
-//   m_c = alpha^(512 c) m_0 + sum_{i<c} alpha^(512 (c-1-i)) B_i,   B_i = sum_k beta alpha^(511-k) x_{512 i + k}
-// and terms older than 80 chunks are below float64 resolution.  k_ema_agg computes B_i (one warp per
-// chunk); k_ema_apply rebuilds m_c from at most 80 aggregates, then each lane runs 16 samples and the
-// lane carries are chained in lane order.  Regrouped float64 sums differ from the sequential recurrence
-// by ~1e-16 relative: the float32 rounding of x - m flips for about one sample in 1e9.
+// EMA DC removal (app.js:750-755):  m <- alpha*m + beta*x,  cleaned = f32(x - m).  Constants of the parallel evaluation
+// in k_front (powers of alpha, computed in long double on the host).  Regrouped float64 sums differ from the sequential
+// recurrence by ~1e-16 relative: the float32 rounding of x - m flips for about one sample in 1e9.
 // ================================================================================================
 struct AmbEmaTables {
-    double w_in[AMB_CHUNK];            // beta * alpha^(511-k)
-    double w_chunk[AMB_EMA_TERMS + 1]; // alpha^(512 j)
-    double a16;                        // alpha^16
     double alpha, beta;
+    double a8, a512;                   // alpha^8, alpha^512
     double lanepow[32];                // alpha^(16 i)
     double steppow[5];                 // alpha^(16 * 2^k)
-    double a8;                         // alpha^8
 };
-
-__global__ void k_ema_agg(const float* __restrict__ x, int64_t x_stride, int64_t n_chunks, int per,
-                          const AmbEmaTables* __restrict__ E, double* __restrict__ agg) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    AMB_SPLIT_BID(per, s, cb)
-    const int64_t c = (int64_t)cb * (blockDim.x >> 5) + warp;
-    if (c >= n_chunks) return;
-    const float* p = x + (int64_t)s * x_stride + c * AMB_CHUNK;
-    double acc = 0.0;
-#pragma unroll
-    for (int t = 0; t < AMB_CHUNK / 32; t++) {
-        const int k = t * 32 + lane;
-        acc = fma(E->w_in[k], (double)p[k], acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) agg[(int64_t)s * n_chunks + c] = acc;
-}
-
-__global__ void k_ema_apply(const float* __restrict__ x, int64_t x_stride, float* __restrict__ cleaned, int64_t stride, int64_t off0,
-                            int64_t n_chunks, int per, const AmbEmaTables* __restrict__ E, const double* __restrict__ agg,
-                            const AmbStreamState* __restrict__ states, double* __restrict__ dc_next) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    AMB_SPLIT_BID(per, s, cb)
-    const int64_t c = (int64_t)cb * (blockDim.x >> 5) + warp;
-    if (c >= n_chunks) return;
-    const double alpha = E->alpha, beta = E->beta, a16 = E->a16;
-    double part = 0.0;
-    for (int j = lane; j < AMB_EMA_TERMS && j < c; j += 32)
-        part = fma(E->w_chunk[j], agg[(int64_t)s * n_chunks + (c - 1 - j)], part);
-    double m = warp_sum(part);
-    if (c <= AMB_EMA_TERMS) m = fma(E->w_chunk[c], states[s].dc_mean, m);
-    const int64_t at = (int64_t)s * stride + off0 + c * AMB_CHUNK + lane * 16;
-    const int64_t xat = (int64_t)s * x_stride + c * AMB_CHUNK + lane * 16;
-    float xv[16];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float4 v = reinterpret_cast<const float4*>(x + xat)[q];
-        xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
-    }
-    double bl = 0.0;   // lane-local response from a zero state
-#pragma unroll
-    for (int t = 0; t < 16; t++) bl = fma(alpha, bl, beta * (double)xv[t]);
-    double carry = m, my_in = m;
-    for (int u = 0; u < 32; u++) {
-        const double bu = __shfl_sync(0xffffffffu, bl, u);
-        if (lane == u) my_in = carry;
-        carry = fma(a16, carry, bu);
-    }
-    double mm = my_in;
-    float out[16];
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        mm = fma(alpha, mm, beta * (double)xv[t]);
-        out[t] = (float)((double)xv[t] - mm);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        reinterpret_cast<float4*>(cleaned + at)[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-    if (c == n_chunks - 1 && lane == 31) dc_next[s] = mm;
-}
 
 // ================================================================================================
 // Window-sum prefix machinery shared by the streaming summary scan and the batch metric kernel.
@@ -159,18 +90,7 @@ __device__ __forceinline__ void block_prefix(const float* c, double* ST, double*
     __syncthreads();
 }
 
-// Streaming summary scan.  cleaned: arena [n_streams][stride]; tile t of the push covers window-end samples
-// [off0 + 4096 t, +4096) in arena coordinates; g0 = global sample index of arena index off0.
-// sums: [n_streams][sum_stride][5]; summary tile index of arena sample a is a >> 8.
-//
-// One WARP per 4096-sample call tile, everything in registers.  The warp streams over 18 blocks of 256 samples (block
-// m = local samples 256m+1 .. 256m+256, local index 0 = arena a0-512; the +1 makes block m exactly the window starts of
-// summary tile m).  Lane l owns 8 consecutive samples of each block; per block it forms the exclusive prefix of x^2 and of
-// x[i]*x[i+256] (8 local adds + one warp shuffle scan each), and the window starting at (m, r) is then
-//   Ra = (totQ_m - preQ_m[r]) + preQ_{m+1}[r],  Rb = (totQ_{m+1} - preQ_{m+1}[r]) + preQ_{m+2}[r],  P likewise from T,
-// all from the lane's own registers.  This pass is float32 SCREENING: the summaries are widened by a bound on its
-// rounding error so that amb_tile_hot stays conservative, and tiles that might matter get a slot; k_tri_store then writes
-// the exact float64 sums of those tiles only.
+// Stores the scan front end (k_front) and the exact-sum kernel (k_tri_store) fill for the walker.
 struct AmbScanStore {
     int32_t* tile_slot;      // [n_streams][sum_stride]
     double* tri;             // [slot_cap][3][256]
@@ -181,110 +101,6 @@ struct AmbScanStore {
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
-
-__device__ __forceinline__ void scan_load_block(const float* __restrict__ row, int64_t a_base, int64_t limit, int m, int lane, float* x) {
-    // samples local 256m + 1 + 8*lane + k, k < 8: three aligned float4 loads, elements 1..8
-    const int64_t a = a_base + 256 * m + 8 * lane;
-    float e[12];
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a + 4 * q + 3 < limit) v = __ldg(reinterpret_cast<const float4*>(row + a + 4 * q));
-        else { float t[4]; for (int j = 0; j < 4; j++) t[j] = (a + 4 * q + j < limit) ? row[a + 4 * q + j] : 0.f; v = make_float4(t[0], t[1], t[2], t[3]); }
-        e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = e[k + 1];
-}
-
-// exclusive prefix (within the 256-sample block) of v[k] over lanes and k; returns the block total
-__device__ __forceinline__ float scan_block_prefix(const float* v, int lane, float* pre) {
-    float run = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { pre[k] = run; run += v[k]; }
-    float inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    const float base = inc - run;
-#pragma unroll
-    for (int k = 0; k < 8; k++) pre[k] += base;
-    return __shfl_sync(0xffffffffu, inc, 31);
-}
-
-__global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cleaned, int64_t stride, int64_t off0, int64_t g0, int per,
-                                                    float* __restrict__ sums, int64_t sum_stride, AmbScanStore st, int64_t n_warps) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (w >= n_warps) return;
-    const int s = (int)(w / per), tile = (int)(w % per);
-    const int64_t a0 = off0 + (int64_t)tile * AMB_TILE;
-    const float* row = cleaned + (int64_t)s * stride;
-    const int64_t a_base = a0 - AMB_HALO;                      // arena index of local sample 0
-    if (lane == 0 && st.defect) {
-        // defect of the block boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
-        const double xm1 = row[a_base], x255 = row[a_base + 256], x511 = row[a_base + 512];
-        double* D = st.defect + ((int64_t)s * st.calls_stride + (a0 >> 12)) * 3;
-        D[0] = xm1 * x255 - x255 * x511; D[1] = xm1 * xm1 - x255 * x255; D[2] = x255 * x255 - x511 * x511;
-    }
-    float X0[8], X1[8], X2[8], PQ0[8], PQ1[8], PQ2[8], PT0[8], PT1[8], v[8];
-    float TQ0, TQ1, TQ2, TT0, TT1;
-    scan_load_block(row, a_base, stride, 0, lane, X0);
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = X0[k] * X0[k];
-    TQ0 = scan_block_prefix(v, lane, PQ0);
-    scan_load_block(row, a_base, stride, 1, lane, X1);
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = X1[k] * X1[k];
-    TQ1 = scan_block_prefix(v, lane, PQ1);
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = X0[k] * X1[k];
-    TT0 = scan_block_prefix(v, lane, PT0);
-    for (int m = 0; m < AMB_TILE / 256; m++) {
-        scan_load_block(row, a_base, stride, m + 2, lane, X2);
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = X2[k] * X2[k];
-        TQ2 = scan_block_prefix(v, lane, PQ2);
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = X1[k] * X2[k];
-        TT1 = scan_block_prefix(v, lane, PT1);
-        // windows (m, r = 8*lane + k): local start 256m + 1 + r
-        const float err = 4e-7f * (TQ0 + TQ1 + TQ2) + 1e-12f;
-        float ap = 0.f, mnA = 3.0e38f, mxA = 0.f, mnB = 3.0e38f, mxB = 0.f;
-        int hot = 0;
-        const int64_t d0 = g0 + (int64_t)tile * AMB_TILE - AMB_HALO + 256 * m + 1 + 8 * lane;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (d0 + k < 0) continue;
-            const float A = (TQ0 - PQ0[k]) + PQ1[k], B = (TQ1 - PQ1[k]) + PQ2[k], P = (TT0 - PT0[k]) + PT1[k];
-            ap = fmaxf(ap, fabsf(P)); mnA = fminf(mnA, A); mxA = fmaxf(mxA, A); mnB = fminf(mnB, B); mxB = fmaxf(mxB, B);
-            const float Pa = fabsf(P) + err;
-            hot |= (A + err > 0.0009f) && (B + err > 0.0009f) && Pa * Pa > 0.25f * fmaxf(A - err, 0.0009f) * fmaxf(B - err, 0.0009f);
-        }
-        ap = warp_maxf(ap); mnA = warp_minf(mnA); mxA = warp_maxf(mxA); mnB = warp_minf(mnB); mxB = warp_maxf(mxB);
-        const int any_hot = __any_sync(0xffffffffu, hot);
-        if (lane == 0) {
-            const int64_t tix = (int64_t)s * sum_stride + ((a0 >> 8) + m);
-            float* o = sums + tix * AMB_SUM_W;
-            // widened by the screening error so that the walker's cold test stays conservative
-            o[0] = ap + err; o[1] = fmaxf(mnA - err, 0.f); o[2] = mxA + err; o[3] = fmaxf(mnB - err, 0.f); o[4] = mxB + err;
-            // Slots go to tiles holding a window of metric > 0.25, and to tiles the walker's summary test (amb_tile_hot:
-            // max|P|^2 against min Ra * min Rb, loose where the energy ramps inside the tile) would send it into anyway;
-            // widened for the defect the walker may carry.  Without a slot the walker evaluates the tile's windows itself.
-            const float pw = o[0] * 1.05f;
-            const bool wide = o[2] * 1.05f > 0.0009f && o[4] * 1.05f > 0.0009f &&
-                              pw * pw > 0.4f * fmaxf(o[1] * 0.95f, 0.0009f) * fmaxf(o[3] * 0.95f, 0.0009f);
-            if (st.tile_slot && (any_hot || wide)) {
-                int slot = atomicAdd(st.slot_count, 1);
-                if (slot >= st.slot_cap) slot = -1;
-                else { st.slot_info[slot * 4] = s; st.slot_info[slot * 4 + 1] = (int32_t)((a0 >> 8) + m); st.slot_info[slot * 4 + 2] = 0; st.slot_info[slot * 4 + 3] = 0; }
-                st.tile_slot[tix] = slot;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) { X0[k] = X1[k]; X1[k] = X2[k]; PQ0[k] = PQ1[k]; PQ1[k] = PQ2[k]; PT0[k] = PT1[k]; }
-        TQ0 = TQ1; TQ1 = TQ2; TT0 = TT1;
-    }
-}
 
 // ================================================================================================
 // k_front: the streaming front end in one pass over the new samples - EMA DC removal (app.js:750-755) and the
@@ -303,7 +119,7 @@ __global__ void __launch_bounds__(256) k_scan_fast(const float* __restrict__ cle
 //   half-warp reduction of these bounds: conservative (the walker only uses it to skip tiles), ~10 instructions per
 //   sample, and no per-window work at all.  Tiles the walker could enter get a slot; k_tri_store then computes their
 //   exact float64 window sums.
-// Replaces k_ema_agg + k_ema_apply + k_scan_fast: the samples are read once and cleaned is written once.
+// The samples are read once and cleaned is written once.
 // ================================================================================================
 struct AmbFrontArgs {
     const float* x; int64_t x_stride;                 // rows of this push
@@ -364,7 +180,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     const int t0 = p * a.span, t1 = min(a.tiles, t0 + a.span);
     if (t0 >= t1) return;
     const AmbEmaTables* E = a.E;
-    const double alpha = E->alpha, beta = E->beta, a512 = E->w_chunk[1];
+    const double alpha = E->alpha, beta = E->beta, a512 = E->a512;
     const double lp = E->lanepow[lane];
     const float* xrow = a.x + (int64_t)s * a.x_stride;
     float* crow = a.cleaned + (int64_t)s * a.stride + a.off0;
