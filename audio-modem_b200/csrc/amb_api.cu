@@ -70,7 +70,8 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc, bitmaps;
+    int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
     cudaStream_t copy_stream = nullptr;          // host->device copies of sectioned pushes
     std::vector<cudaEvent_t> copy_events;
@@ -312,7 +313,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -670,6 +671,15 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
         CK(m->l_hasB.ensure(nl * 4)); CK(m->l_memo.ensure(nr * sizeof(AmbRefineMemo)));
         CK(m->l_first.ensure(ns * sizeof(AmbStreamState))); CK(m->l_firstflag.ensure(ns * 4)); CK(m->l_firststop.ensure(ns * 4)); CK(m->l_fpsum.ensure(ns * 8));
     }
+    {
+        // ChunkAssembler.receivedBitmap per stream: 2 Mi chunks (8 GiB files at 4 KB chunks) unless that would take more than
+        // 512 MiB over all streams; chunks beyond the capacity are not tracked for duplicates
+        int64_t bits = 1ll << 21;
+        while (bits > 65536 && (double)ns * (double)bits / 8.0 > 512.0 * 1024 * 1024) bits >>= 1;
+        m->bitmap_bits = bits;
+        CK(m->bitmaps.ensure(ns * (size_t)(bits / 8)));
+        CK(cudaMemsetAsync(m->bitmaps.p, 0, ns * (size_t)(bits / 8), m->stream));
+    }
     if (!m->h_counts && cudaHostAlloc((void**)&m->h_counts, 64, cudaHostAllocDefault) != cudaSuccess) return fail(m, AMB_E_NOMEM, "cudaHostAlloc failed");
     std::vector<AmbStreamState> init(ns);
     std::memset(init.data(), 0, ns * sizeof(AmbStreamState));
@@ -689,7 +699,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps};
     for (DevBuf* b : all) b->release();
     m->open = false;
     return AMB_OK;
@@ -874,11 +884,14 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
             int64_t parts = ((int64_t)total / ns + 1023) / 1024;
             if (parts < 1) parts = 1;
             if (parts > 64) parts = 64;
-            CK(m->post_acc.ensure((size_t)ns * 6 * 8));
-            CK(cudaMemsetAsync(m->post_acc.p, 0, (size_t)ns * 6 * 8, m->stream));
-            LAUNCH("k_post_stream", k_post_stream<<<ns * (int)parts, 256, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
-                                                                      pres, ns, m->states.as<AmbStreamState>(), m->keep.as<int>(),
-                                                                      m->redo.as<int>(), m->n_redo.as<int>(), g.k_end, (int)parts, m->post_acc.as<unsigned long long>()));
+            CK(m->post_acc.ensure((size_t)ns * 8 * 8));
+            CK(cudaMemsetAsync(m->post_acc.p, 0, (size_t)ns * 8 * 8, m->stream));
+            LAUNCH("k_post_count", k_post_count<<<ns * (int)parts, 256, 0, m->stream>>>(m->nrec.as<int>(), m->job_off.as<int>(), pres, ns, m->states.as<AmbStreamState>(),
+                                                                                    m->keep.as<int>(), (int)parts, m->post_acc.as<unsigned long long>()));
+            LAUNCH("k_post_apply", k_post_apply<<<ns * (int)parts, 256, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
+                                                                                    pres, ns, m->states.as<AmbStreamState>(), m->keep.as<int>(), m->redo.as<int>(),
+                                                                                    m->n_redo.as<int>(), g.k_end, (int)parts, m->post_acc.as<unsigned long long>(),
+                                                                                    m->bitmaps.as<uint32_t>(), m->bitmap_bits));
         }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
         if (!direct) {

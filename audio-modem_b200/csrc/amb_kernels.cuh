@@ -1560,60 +1560,89 @@ __global__ void __launch_bounds__(1024) k_prefix_counts(const int* __restrict__ 
 // Applies the decoded frames of each stream in time order (amb_post_frames, amb_walker.cuh) and queues the streams whose
 // collection window changed for another walk.  One CTA per stream.  Without a CRC-valid metadata frame among them (the
 // steady state) the frames only move counters, which is a parallel count; otherwise thread 0 applies them sequentially.
-__global__ void __launch_bounds__(256) k_post_stream(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
-                              const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
-                              AmbStreamState* __restrict__ states, int* __restrict__ keep /*[n_jobs] 1 = report*/,
-                              int* __restrict__ redo_list, int* __restrict__ n_redo, int64_t k_end, int parts,
-                              unsigned long long* __restrict__ acc /*[n_streams][6], zeroed: fd, fe, rc, ce, valid metadata, finished parts*/) {
-    // `parts` CTAs share one stream: each counts a slice of its frames into acc, the last one to finish applies the result
+// acc per stream: [0] framesDecoded, [1] frameErrors, [2] received, [3] crcErrors, [4] CRC-valid metadata frames,
+// [5] finished parts of k_post_apply, [6] duplicates, [7] unused
+__global__ void __launch_bounds__(256) k_post_count(const int* __restrict__ nrec, const int* __restrict__ job_off,
+                                                     const amb_frame_result* __restrict__ results, int n_streams, const AmbStreamState* __restrict__ states,
+                                                     int* __restrict__ keep /*[n_jobs] 1 = report*/, int parts, unsigned long long* __restrict__ acc) {
     const int s = blockIdx.x / parts, part = blockIdx.x % parts;
     if (s >= n_streams) return;
     const int cnt = nrec[s], o = job_off[s], tid = threadIdx.x;
     if (cnt == 0) return;
-    __shared__ unsigned c_fd, c_fe, c_rc, c_ce, c_vm;
-    __shared__ int is_last;
-    if (tid == 0) { c_fd = c_fe = c_rc = c_ce = c_vm = 0u; }
-    __syncthreads();
     const AmbStreamState cur = states[s];
-    unsigned fd = 0, fe = 0, rc = 0, ce = 0, vm = 0;
+    unsigned fd = 0, fe = 0, ce = 0, vm = 0;
     for (int i = part * blockDim.x + tid; i < cnt; i += parts * blockDim.x) {
         const amb_frame_result& r = results[o + i];
         keep[o + i] = 1;
         if (r.status != 0) { fe++; continue; }
         fd++;
         if (r.frame_type == AMB_FRAME_META) { if (r.crc_valid) vm++; else fe++; }
-        else if (r.frame_type == AMB_FRAME_DATA && cur.meta_received == 1 && !(r.seq_num >= cur.total_chunks)) { if (r.crc_valid) rc++; else ce++; }
+        else if (r.frame_type == AMB_FRAME_DATA && cur.meta_received == 1 && !(r.seq_num >= cur.total_chunks) && !r.crc_valid) ce++;
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) {
-        fd += __shfl_xor_sync(0xffffffffu, fd, of); fe += __shfl_xor_sync(0xffffffffu, fe, of); rc += __shfl_xor_sync(0xffffffffu, rc, of);
+        fd += __shfl_xor_sync(0xffffffffu, fd, of); fe += __shfl_xor_sync(0xffffffffu, fe, of);
         ce += __shfl_xor_sync(0xffffffffu, ce, of); vm += __shfl_xor_sync(0xffffffffu, vm, of);
     }
-    if ((tid & 31) == 0) { atomicAdd(&c_fd, fd); atomicAdd(&c_fe, fe); atomicAdd(&c_rc, rc); atomicAdd(&c_ce, ce); atomicAdd(&c_vm, vm); }
-    __syncthreads();
-    unsigned long long* A = acc + (int64_t)s * 6;
-    if (tid == 0) {
-        atomicAdd(A, (unsigned long long)c_fd); atomicAdd(A + 1, (unsigned long long)c_fe); atomicAdd(A + 2, (unsigned long long)c_rc);
-        atomicAdd(A + 3, (unsigned long long)c_ce); atomicAdd(A + 4, (unsigned long long)c_vm);
-        __threadfence();
-        is_last = atomicAdd(A + 5, 1ull) == (unsigned long long)(parts - 1);
+    unsigned long long* A = acc + (int64_t)s * 8;
+    if ((tid & 31) == 0) {
+        if (fd) atomicAdd(A, (unsigned long long)fd);
+        if (fe) atomicAdd(A + 1, (unsigned long long)fe);
+        if (ce) atomicAdd(A + 3, (unsigned long long)ce);
+        if (vm) atomicAdd(A + 4, (unsigned long long)vm);
     }
+}
+
+// Second half: the chunk bitmap (ChunkAssembler.receivedBitmap, app.js:628-643) and the stream state.  Without a CRC-valid
+// metadata frame in the batch the order of the frames does not matter: every CTA marks its slice of CRC-valid chunks
+// (atomicOr: first mark = received, later ones = duplicates) and the last one to finish applies the sums.  With one, thread
+// 0 of part 0 applies the batch in order (amb_post_frames: the metadata frame resets the bitmap and may rewind the stream).
+__global__ void __launch_bounds__(256) k_post_apply(const AmbFrameRec* __restrict__ recs, int rec_cap, const int* __restrict__ nrec,
+                                                     const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
+                                                     AmbStreamState* __restrict__ states, int* __restrict__ keep, int* __restrict__ redo_list,
+                                                     int* __restrict__ n_redo, int64_t k_end, int parts, unsigned long long* __restrict__ acc,
+                                                     uint32_t* __restrict__ bitmaps /*[n_streams][bitmap_bits / 32]*/, int64_t bitmap_bits) {
+    const int s = blockIdx.x / parts, part = blockIdx.x % parts;
+    if (s >= n_streams) return;
+    const int cnt = nrec[s], o = job_off[s], tid = threadIdx.x;
+    if (cnt == 0) return;
+    unsigned long long* A = acc + (int64_t)s * 8;
+    uint32_t* bitmap = bitmaps ? bitmaps + (int64_t)s * ((bitmap_bits + 31) / 32) : nullptr;
+    const AmbStreamState cur = states[s];
+    const bool ordered = A[4] > 0;                               // written by k_post_count, the launch before
+    __shared__ int is_last;
+    if (ordered) {
+        if (part != 0 || tid != 0) return;
+        AmbStreamState st;
+        int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o, bitmap, bitmap_bits);
+        states[s] = st;
+        if (!st.meta_received && st.next_call < k_end) redo = 1;
+        if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
+        return;
+    }
+    unsigned rc = 0, du = 0;
+    if (cur.meta_received == 1) {
+        for (int i = part * blockDim.x + tid; i < cnt; i += parts * blockDim.x) {
+            const amb_frame_result& r = results[o + i];
+            if (r.status == 0 && r.frame_type == AMB_FRAME_DATA && !(r.seq_num >= cur.total_chunks) && r.crc_valid) {
+                if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) rc++; else du++;
+            }
+        }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) { rc += __shfl_xor_sync(0xffffffffu, rc, of); du += __shfl_xor_sync(0xffffffffu, du, of); }
+    if ((tid & 31) == 0) { if (rc) atomicAdd(A + 2, (unsigned long long)rc); if (du) atomicAdd(A + 6, (unsigned long long)du); }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); is_last = atomicAdd(A + 5, 1ull) == (unsigned long long)(parts - 1); }
     __syncthreads();
     if (!is_last || tid != 0) return;
     __threadfence();
-    const unsigned long long t_fd = atomicAdd(A, 0ull), t_fe = atomicAdd(A + 1, 0ull), t_rc = atomicAdd(A + 2, 0ull), t_ce = atomicAdd(A + 3, 0ull),
-                             t_vm = atomicAdd(A + 4, 0ull);
-    AmbStreamState st;
-    int redo = 0;
-    if (t_vm > 0) redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o);
-    else {
-        st = cur;
-        st.frames_decoded += (int64_t)t_fd; st.frame_errors += (int64_t)t_fe; st.received += (int64_t)t_rc; st.crc_errors += (int64_t)t_ce;
-    }
+    AmbStreamState st = cur;
+    st.frames_decoded += (int64_t)A[0]; st.frame_errors += (int64_t)A[1]; st.received += (int64_t)atomicAdd(A + 2, 0ull);
+    st.crc_errors += (int64_t)A[3]; st.dups += (int64_t)atomicAdd(A + 6, 0ull);
     states[s] = st;
     // a stream still waiting for its metadata frame advances one frame per pass (k_walk, pre_meta_only)
-    if (!st.meta_received && st.next_call < k_end) redo = 1;
-    if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
+    if (!st.meta_received && st.next_call < k_end) redo_list[atomicAdd(n_redo, 1)] = s;
 }
 
 // ================================================================================================

@@ -509,10 +509,25 @@ AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig,
 // metadata, or a different chunkSize) invalidates everything the walker did after it: the state is rewound to
 // the snapshot taken after that frame, with the new flags, and 1 is returned so that the caller walks again.
 // keep[i] = 1 for frames to report.
+// ChunkAssembler.handleDataChunk's bitmap (app.js:628-643) for one CRC-valid chunk with seq < totalChunks: 1 = newly
+// received, 0 = duplicate.  A negative seqNum indexes the typed array out of range, which reads undefined and writes
+// nothing in JS: it counts as received every time.  Chunks beyond the bitmap capacity are not tracked (always new).
+AMB_HD int amb_bitmap_mark(uint32_t* bitmap, int64_t bitmap_bits, int32_t seq) {
+    if (seq < 0 || !bitmap || seq >= bitmap_bits) return 1;
+    const uint32_t bit = 1u << (seq & 31);
+#if defined(__CUDA_ARCH__)
+    const uint32_t old = atomicOr(bitmap + (seq >> 5), bit);
+#else
+    const uint32_t old = bitmap[seq >> 5];
+    bitmap[seq >> 5] = old | bit;
+#endif
+    return (old & bit) ? 0 : 1;
+}
+
 AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_result* res, const AmbStreamState& cur,
-                           AmbStreamState* out, int* keep) {
+                           AmbStreamState* out, int* keep, uint32_t* bitmap = nullptr, int64_t bitmap_bits = 0) {
     AmbStreamState st = cur;
-    int64_t fd = cur.frames_decoded, fe = cur.frame_errors, rc = cur.received, ce = cur.crc_errors;
+    int64_t fd = cur.frames_decoded, fe = cur.frame_errors, rc = cur.received, ce = cur.crc_errors, du = cur.dups;
     int meta = cur.meta_received, chunk = cur.chunk_size, total = cur.total_chunks;
     int rewind = -1;
     for (int i = 0; i < cnt; i++) {
@@ -524,10 +539,20 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
             if (r.crc_valid) {
                 const bool changes = !meta || chunk != r.chunk_size;
                 meta = 1; chunk = r.chunk_size; total = r.total_chunks; rc = 0; ce = 0;
+                // handleMetadataFrame (app.js:610-618): a fresh bitmap of ceil(totalChunks / 8) bytes
+                if (bitmap) {
+                    int64_t words = ((int64_t)total + 31) / 32;
+                    if (words > (bitmap_bits + 31) / 32) words = (bitmap_bits + 31) / 32;
+                    for (int64_t w = 0; w < words; w++) bitmap[w] = 0u;
+                }
                 if (changes) { rewind = i; break; }
             } else fe++;
         } else if (r.frame_type == AMB_FRAME_DATA) {
-            if (meta == 1 && !(r.seq_num >= total)) { if (!r.crc_valid) ce++; else rc++; }
+            if (meta == 1 && !(r.seq_num >= total)) {
+                if (!r.crc_valid) ce++;
+                else if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) rc++;
+                else du++;
+            }
         }
     }
     if (rewind >= 0) {
@@ -536,7 +561,7 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
         st.dc_mean = cur.dc_mean; st.written = cur.written;
     }
     st.meta_received = meta; st.chunk_size = chunk; st.total_chunks = total;
-    st.frames_decoded = fd; st.frame_errors = fe; st.received = rc; st.crc_errors = ce;
+    st.frames_decoded = fd; st.frame_errors = fe; st.received = rc; st.crc_errors = ce; st.dups = du;
     *out = st;
     return rewind >= 0 ? 1 : 0;
 }

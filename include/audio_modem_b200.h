@@ -194,8 +194,8 @@ int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride);
 int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
                     int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem);
 /* per-stream counters (stream = -1: sum over streams): framesDecoded, frameErrors (app.js:738-739),
- * falsePositives (app.js:879-884), receivedCount, crcErrors (app.js:604-605), duplicates, metaReceived,
- * samplesWritten */
+ * falsePositives (app.js:879-884), receivedCount, crcErrors (app.js:604-605, ChunkAssembler's bitmap semantics of
+ * app.js:628-643 without the chunk store), duplicates (chunks whose bit was already set), metaReceived, samplesWritten */
 int amb_stream_counters(amb_modem* m, int stream, int64_t* out8);
 
 /* ---- transmit side (the "next" row of the scope table; also synthesises bench / test input on the device) ---- */

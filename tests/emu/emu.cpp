@@ -229,6 +229,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     std::vector<int32_t> tile_slot((size_t)n_tiles, -1);
     std::vector<double> tri, Fpre((size_t)(n / block_len + 2) * 3, 0.0);
     std::vector<float> tsum;
+    std::vector<uint32_t> bitmap(1 << 16, 0u);        // ChunkAssembler.receivedBitmap (2 Mi chunks)
     std::vector<float> xc;
     const int xc_w = 256 + 2 * T.fine_radius;
     G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.slot_info = nullptr; G.tsum = nullptr; G.memo_out = nullptr; G.memo_in = nullptr; G.F = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
@@ -333,7 +334,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
             }
             std::vector<int> keep((size_t)cnt, 0);
             AmbStreamState nst;
-            const int redo = amb_post_frames(recs.data(), cnt, rr.data(), st, &nst, keep.data());
+            const int redo = amb_post_frames(recs.data(), cnt, rr.data(), st, &nst, keep.data(), bitmap.data(), (int64_t)bitmap.size() * 32);
             st = nst;
             for (int i = 0; i < cnt; i++) {
                 if (!keep[i]) continue;

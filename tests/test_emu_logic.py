@@ -36,7 +36,7 @@ def _compare_stream(O, emu, mode, x, push=None):
     for (r1, b1), (r2, b2) in zip(want, got):
         assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == []
     c = rx.counters()
-    for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived"):
+    for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived", "receivedCount", "duplicates"):
         assert c[k] == cnt[k], k
     return want
 
@@ -164,3 +164,23 @@ def test_scan_batch_reduction_agrees_with_serial_loop(emu):
     emu.emu_scan_batch_fuzz.argtypes = [C.c_uint64, C.c_int]
     commits = sum(emu.emu_scan_batch_fuzz(seed, 20000) for seed in range(1, 6))
     assert commits > 1000
+
+
+def test_chunk_bitmap_duplicates_and_reset(O, emu):
+    """ChunkAssembler semantics without storage (app.js:610-643): retransmitted chunks count as duplicates, a chunk beyond
+    totalChunks is ignored, a new metadata frame starts a fresh bitmap"""
+    cfg, mod, rep, chunk = MODES["QPSK"]
+    seqs = [0, 1, 1, 2, 0, 7, 2]                      # 7 >= totalChunks (4): ignored
+    parts = [O.buildMetadataFrame(cfg, 4, 4 * chunk, chunk, "a.bin", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(50 + q, chunk), q, mod, rep) for q in seqs]
+    parts.append(O.buildMetadataFrame(cfg, 4, 4 * chunk, chunk, "a.bin", mod, rep)[13230 - 2205:])     # same chunk size: no rewind, bitmap reset
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(50 + q, chunk), q, mod, rep) for q in (1, 3, 3)]
+    x = O.addAwgn(np.concatenate(parts), 0.003, 5)
+    from helpers import pad_blocks
+    x = pad_blocks(x)
+    rx = O.StreamingReceiver(cfg, mod, rep)
+    rx.push(x, 4096)
+    c = rx.counters()
+    assert c["duplicates"] >= 3 and c["receivedCount"] >= 1, c          # the fixture does exercise duplicates and the reset
+    _compare_stream(O, emu, "QPSK", x)
+    _compare_stream(O, emu, "QPSK", x, push=8 * 4096)

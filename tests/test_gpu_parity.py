@@ -256,7 +256,7 @@ def _stream_compare(O, amb, mode, x, pushes=None, n_streams=1):
             d = results_equal(r1, b1, r2, b2, metric_tol=1e-9)
             assert d == [], (mode, s, r1.preamble_idx, d)
         c, cc = rx.counters(), m.stream_counters(s)
-        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived"):
+        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived", "receivedCount", "duplicates"):
             assert c[k] == cc[k], (mode, s, k, c[k], cc[k])
         assert cc["samplesWritten"] == n
     m.stream_close()
@@ -310,6 +310,21 @@ def test_stream_second_metadata_changes_chunk_size(O, amb):
     parts += [O.buildDataChunkFrame(cfg, O.randomBytes(10 + i, 512), i, mod, rep) for i in range(3)]
     x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 3))
     _stream_compare(O, amb, "QPSK", x)
+
+
+def test_chunk_bitmap_duplicates_and_reset(O, amb):
+    """ChunkAssembler semantics without storage (app.js:610-643): duplicates, out-of-range chunks, bitmap reset by a new
+    metadata frame; in one push (metadata inside the batch: ordered path) and in small pushes (parallel marking)"""
+    cfg, mod, rep, chunk = MODES["QPSK"]
+    seqs = [0, 1, 1, 2, 0, 7, 2]
+    parts = [O.buildMetadataFrame(cfg, 4, 4 * chunk, chunk, "a.bin", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(50 + q, chunk), q, mod, rep) for q in seqs]
+    parts.append(O.buildMetadataFrame(cfg, 4, 4 * chunk, chunk, "a.bin", mod, rep)[13230 - 2205:])
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(50 + q, chunk), q, mod, rep) for q in (1, 3, 3)]
+    x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 5))
+    _stream_compare(O, amb, "QPSK", x)
+    n = len(x)
+    _stream_compare(O, amb, "QPSK", x, pushes=[8 * 4096] * (n // (8 * 4096)) + ([n % (8 * 4096)] if n % (8 * 4096) else []))
 
 
 def test_many_streams_one_handle(O, amb):

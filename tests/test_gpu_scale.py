@@ -24,7 +24,7 @@ def _events_equal(O, amb, mode, x, pushes):
         for (r1, b1), (r2, b2) in zip(want, got):
             assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (mode, r1.preamble_idx)
         c, w = m.stream_counters(), rx.counters()
-        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived"):
+        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived", "receivedCount", "duplicates"):
             assert c[k] == w[k], (k, c, w)
         return want
     finally:
