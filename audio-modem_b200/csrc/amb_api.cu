@@ -70,7 +70,8 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc, bitmaps;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc, bitmaps, files, file_reset, store_off;
+    int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
     int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
     cudaStream_t copy_stream = nullptr;          // host->device copies of sectioned pushes
@@ -313,7 +314,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -699,9 +700,10 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     m->open = false;
+    m->file_cap = 0;
     return AMB_OK;
 }
 
@@ -884,6 +886,8 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
             int64_t parts = ((int64_t)total / ns + 1023) / 1024;
             if (parts < 1) parts = 1;
             if (parts > 64) parts = 64;
+            int64_t* store_off = nullptr;
+            if (m->file_cap > 0) { CK(m->store_off.ensure((size_t)total * 8)); store_off = m->store_off.as<int64_t>(); }
             CK(m->post_acc.ensure((size_t)ns * 8 * 8));
             CK(cudaMemsetAsync(m->post_acc.p, 0, (size_t)ns * 8 * 8, m->stream));
             LAUNCH("k_post_count", k_post_count<<<ns * (int)parts, 256, 0, m->stream>>>(m->nrec.as<int>(), m->job_off.as<int>(), pres, ns, m->states.as<AmbStreamState>(),
@@ -891,7 +895,15 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
             LAUNCH("k_post_apply", k_post_apply<<<ns * (int)parts, 256, 0, m->stream>>>(m->recs.as<AmbFrameRec>(), m->rec_cap, m->nrec.as<int>(), m->job_off.as<int>(),
                                                                                     pres, ns, m->states.as<AmbStreamState>(), m->keep.as<int>(), m->redo.as<int>(),
                                                                                     m->n_redo.as<int>(), g.k_end, (int)parts, m->post_acc.as<unsigned long long>(),
-                                                                                    m->bitmaps.as<uint32_t>(), m->bitmap_bits));
+                                                                                    m->bitmaps.as<uint32_t>(), m->bitmap_bits, store_off, m->file_cap > 0 ? m->file_reset.as<int>() : nullptr));
+            if (m->file_cap > 0) {
+                // chunk store (amb_stream_enable_assembly): clear the files a metadata frame reset, then write the new chunks
+                const int rparts = (int)(m->file_cap / (1 << 20) + 1 < 256 ? m->file_cap / (1 << 20) + 1 : 256);
+                LAUNCH("k_file_reset", k_file_reset<<<ns * rparts, 256, 0, m->stream>>>(m->files.as<uint8_t>(), m->file_cap, m->file_reset.as<int>(), ns, rparts));
+                LAUNCH("k_file_reset_done", k_file_reset_done<<<blocks_for(ns, 128), 128, 0, m->stream>>>(m->file_reset.as<int>(), ns));
+                LAUNCH("k_store_chunks", k_store_chunks<<<total < 65536 ? total : 65536, 128, 0, m->stream>>>(pres, pbytes, bytes_stride, store_off, m->keep.as<int>(), total,
+                                                                                                   m->files.as<uint8_t>(), m->file_cap));
+            }
         }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->keep.as<int>(), total, m->keep_off.as<int>(), m->total.as<int>() + 2));
         if (!direct) {
@@ -1040,6 +1052,40 @@ int amb_build_metadata_frame(amb_modem* m, int32_t total_chunks, int32_t total_f
     const int64_t total = amb_tx_frame_samples(&m->tables, pay_len, 1);
     if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, 1, 1, out, total, noise_sigma, noise_seed, noise_g0, mem))) return rc;
     return flush(m);
+}
+
+int amb_stream_enable_assembly(amb_modem* m, int64_t max_file_bytes) {
+    if (!m) return AMB_E_INVALID;
+    if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
+    if (max_file_bytes <= 0) return fail(m, AMB_E_INVALID, "max_file_bytes must be positive");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    const int64_t cap = (max_file_bytes + 15) / 16 * 16;
+    CK(m->files.ensure((size_t)m->n_streams * cap)); CK(m->file_reset.ensure((size_t)m->n_streams * 4));
+    CK(cudaMemsetAsync(m->files.p, 0, (size_t)m->n_streams * cap, m->stream));
+    CK(cudaMemsetAsync(m->file_reset.p, 0, (size_t)m->n_streams * 4, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->file_cap = cap;
+    return AMB_OK;
+}
+
+int amb_stream_assemble(amb_modem* m, int stream, uint8_t* out, int64_t cap, int64_t* size_out, int mem) {
+    if (!m || !size_out) return AMB_E_INVALID;
+    if (!m->open || m->file_cap <= 0) return fail(m, AMB_E_STATE, "assembly not enabled (amb_stream_enable_assembly)");
+    if (stream < 0 || stream >= m->n_streams || cap < 0 || (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE)) return fail(m, AMB_E_INVALID, "bad argument");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
+    AmbStreamState st;
+    CK(cudaMemcpyAsync(&st, m->states.as<AmbStreamState>() + stream, sizeof(st), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    int64_t size = st.meta_received ? (int64_t)st.total_file_size : 0;       // new Uint8Array(totalFileSize), app.js:667
+    if (size < 0) size = 0;
+    if (size > m->file_cap) size = m->file_cap;
+    *size_out = size;
+    const int64_t n = size < cap ? size : cap;
+    if (out && n > 0) {
+        CK(cudaMemcpyAsync(out, m->files.as<uint8_t>() + (int64_t)stream * m->file_cap, (size_t)n, mem == AMB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    }
+    return AMB_OK;
 }
 
 int amb_stream_counters(amb_modem* m, int stream, int64_t* out8) {

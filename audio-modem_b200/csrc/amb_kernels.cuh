@@ -1601,7 +1601,8 @@ __global__ void __launch_bounds__(256) k_post_apply(const AmbFrameRec* __restric
                                                      const int* __restrict__ job_off, const amb_frame_result* __restrict__ results, int n_streams,
                                                      AmbStreamState* __restrict__ states, int* __restrict__ keep, int* __restrict__ redo_list,
                                                      int* __restrict__ n_redo, int64_t k_end, int parts, unsigned long long* __restrict__ acc,
-                                                     uint32_t* __restrict__ bitmaps /*[n_streams][bitmap_bits / 32]*/, int64_t bitmap_bits) {
+                                                     uint32_t* __restrict__ bitmaps /*[n_streams][bitmap_bits / 32]*/, int64_t bitmap_bits,
+                                                     int64_t* __restrict__ store_off /*[n_jobs] or NULL*/, int* __restrict__ file_reset /*[n_streams] or NULL*/) {
     const int s = blockIdx.x / parts, part = blockIdx.x % parts;
     if (s >= n_streams) return;
     const int cnt = nrec[s], o = job_off[s], tid = threadIdx.x;
@@ -1614,20 +1615,22 @@ __global__ void __launch_bounds__(256) k_post_apply(const AmbFrameRec* __restric
     if (ordered) {
         if (part != 0 || tid != 0) return;
         AmbStreamState st;
-        int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o, bitmap, bitmap_bits);
+        int redo = amb_post_frames(recs + (int64_t)s * rec_cap, cnt, results + o, cur, &st, keep + o, bitmap, bitmap_bits, store_off ? store_off + o : nullptr,
+                                   file_reset ? file_reset + s : nullptr);
         states[s] = st;
         if (!st.meta_received && st.next_call < k_end) redo = 1;
         if (redo) redo_list[atomicAdd(n_redo, 1)] = s;
         return;
     }
     unsigned rc = 0, du = 0;
-    if (cur.meta_received == 1) {
-        for (int i = part * blockDim.x + tid; i < cnt; i += parts * blockDim.x) {
-            const amb_frame_result& r = results[o + i];
-            if (r.status == 0 && r.frame_type == AMB_FRAME_DATA && !(r.seq_num >= cur.total_chunks) && r.crc_valid) {
-                if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) rc++; else du++;
-            }
+    for (int i = part * blockDim.x + tid; i < cnt; i += parts * blockDim.x) {
+        const amb_frame_result& r = results[o + i];
+        int64_t so = -1;
+        if (cur.meta_received == 1 && r.status == 0 && r.frame_type == AMB_FRAME_DATA && !(r.seq_num >= cur.total_chunks) && r.crc_valid) {
+            if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) { rc++; if (r.seq_num >= 0) so = (int64_t)r.seq_num * cur.chunk_size; }
+            else du++;
         }
+        if (store_off) store_off[o + i] = so;
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) { rc += __shfl_xor_sync(0xffffffffu, rc, of); du += __shfl_xor_sync(0xffffffffu, du, of); }
@@ -1643,6 +1646,37 @@ __global__ void __launch_bounds__(256) k_post_apply(const AmbFrameRec* __restric
     states[s] = st;
     // a stream still waiting for its metadata frame advances one frame per pass (k_walk, pre_meta_only)
     if (!st.meta_received && st.next_call < k_end) redo_list[atomicAdd(n_redo, 1)] = s;
+}
+
+// ChunkAssembler's chunk store without IndexedDB (app.js:610-680): one file buffer per stream; a metadata frame clears it,
+// a newly received chunk is written at seqNum * chunkSize (the offset assembleFile uses).
+__global__ void __launch_bounds__(256) k_file_reset(uint8_t* __restrict__ files, int64_t file_cap, int* __restrict__ file_reset, int n_streams, int parts) {
+    const int s = blockIdx.x / parts, part = blockIdx.x % parts;
+    if (s >= n_streams || !file_reset[s]) return;
+    uint4* f = reinterpret_cast<uint4*>(files + (int64_t)s * file_cap);
+    const int64_t n16 = file_cap / 16;
+    for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < n16; i += (int64_t)parts * blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void k_file_reset_done(int* __restrict__ file_reset, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams) file_reset[s] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_store_chunks(const amb_frame_result* __restrict__ results, const uint8_t* __restrict__ bytes, int64_t bytes_stride,
+                                                       const int64_t* __restrict__ store_off, const int* __restrict__ keep, int n_jobs,
+                                                       uint8_t* __restrict__ files, int64_t file_cap) {
+    for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
+        const int64_t off = store_off[j];
+        if (off < 0 || !keep[j]) continue;
+        const amb_frame_result& r = results[j];
+        int64_t len = r.data_len;
+        if (off >= file_cap) continue;
+        if (off + len > file_cap) len = file_cap - off;
+        const uint8_t* src = bytes + (int64_t)j * bytes_stride + r.data_off;
+        uint8_t* dst = files + (int64_t)r.stream * file_cap + off;
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+    }
 }
 
 // ================================================================================================

@@ -22,6 +22,7 @@ enum { AMB_RX_IDLE = 0, AMB_RX_PREAMBLE = 1, AMB_RX_COLLECT = 2 };
 
 struct AmbStreamState {
     int32_t state, ac_init, lag, meta_received, chunk_size, total_chunks;
+    int32_t total_file_size, pad0;      // of the metadata frame in force (ChunkAssembler.totalFileSize)
     int64_t ac_scan_pos, pre_pos, frame_end;
     double Ep, Ea, Eb;
     double coarse, fine;
@@ -524,12 +525,17 @@ AMB_HD int amb_bitmap_mark(uint32_t* bitmap, int64_t bitmap_bits, int32_t seq) {
     return (old & bit) ? 0 : 1;
 }
 
+// store_off (optional, [cnt]): where a newly received chunk goes in the stream's file buffer (seqNum * chunkSize, the
+// ChunkAssembler.assembleFile offset, app.js:676-677), -1 = not stored; file_reset (optional): set when a metadata frame
+// cleared the chunk store (app.js:619-625).
 AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_result* res, const AmbStreamState& cur,
-                           AmbStreamState* out, int* keep, uint32_t* bitmap = nullptr, int64_t bitmap_bits = 0) {
+                           AmbStreamState* out, int* keep, uint32_t* bitmap = nullptr, int64_t bitmap_bits = 0,
+                           int64_t* store_off = nullptr, int* file_reset = nullptr) {
     AmbStreamState st = cur;
     int64_t fd = cur.frames_decoded, fe = cur.frame_errors, rc = cur.received, ce = cur.crc_errors, du = cur.dups;
-    int meta = cur.meta_received, chunk = cur.chunk_size, total = cur.total_chunks;
+    int meta = cur.meta_received, chunk = cur.chunk_size, total = cur.total_chunks, fsize = cur.total_file_size;
     int rewind = -1;
+    if (store_off) for (int i = 0; i < cnt; i++) store_off[i] = -1;
     for (int i = 0; i < cnt; i++) {
         const amb_frame_result& r = res[i];
         keep[i] = 1;
@@ -538,7 +544,9 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
         if (r.frame_type == AMB_FRAME_META) {
             if (r.crc_valid) {
                 const bool changes = !meta || chunk != r.chunk_size;
-                meta = 1; chunk = r.chunk_size; total = r.total_chunks; rc = 0; ce = 0;
+                meta = 1; chunk = r.chunk_size; total = r.total_chunks; fsize = r.total_file_size; rc = 0; ce = 0;
+                if (file_reset) *file_reset = 1;
+                if (store_off) for (int q = 0; q < i; q++) store_off[q] = -1;       // chunks stored before the reset are gone
                 // handleMetadataFrame (app.js:610-618): a fresh bitmap of ceil(totalChunks / 8) bytes
                 if (bitmap) {
                     int64_t words = ((int64_t)total + 31) / 32;
@@ -550,7 +558,7 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
         } else if (r.frame_type == AMB_FRAME_DATA) {
             if (meta == 1 && !(r.seq_num >= total)) {
                 if (!r.crc_valid) ce++;
-                else if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) rc++;
+                else if (amb_bitmap_mark(bitmap, bitmap_bits, r.seq_num)) { rc++; if (store_off && r.seq_num >= 0) store_off[i] = (int64_t)r.seq_num * chunk; }
                 else du++;
             }
         }
@@ -560,7 +568,7 @@ AMB_HD int amb_post_frames(const AmbFrameRec* recs, int cnt, const amb_frame_res
         st = recs[rewind].snap;
         st.dc_mean = cur.dc_mean; st.written = cur.written;
     }
-    st.meta_received = meta; st.chunk_size = chunk; st.total_chunks = total;
+    st.meta_received = meta; st.chunk_size = chunk; st.total_chunks = total; st.total_file_size = fsize;
     st.frames_decoded = fd; st.frame_errors = fe; st.received = rc; st.crc_errors = ce; st.dups = du;
     *out = st;
     return rewind >= 0 ? 1 : 0;

@@ -394,6 +394,18 @@ class Modem:
                 out.append(o)
         return out
 
+    def stream_enable_assembly(self, max_file_bytes):
+        """ChunkAssembler without IndexedDB: keep the received chunks of every stream on the device (app.js:597-704)"""
+        self._ck(self._L.amb_stream_enable_assembly(self._h, int(max_file_bytes)))
+        self._file_cap = int(max_file_bytes)
+
+    def stream_assemble(self, stream=0):
+        """assembleFile (app.js:666-682): the file of the metadata frame in force, missing chunks as zeros"""
+        out = np.zeros(max(1, self._file_cap), dtype=np.uint8)
+        size = C.c_int64(0)
+        self._ck(self._L.amb_stream_assemble(self._h, stream, _ptr(out), len(out), C.byref(size), MEM_HOST))
+        return bytes(out[: size.value])
+
     def stream_counters(self, stream=-1):
         a = (C.c_int64 * 8)()
         self._ck(self._L.amb_stream_counters(self._h, stream, a))

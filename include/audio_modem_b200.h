@@ -198,6 +198,13 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
  * app.js:628-643 without the chunk store), duplicates (chunks whose bit was already set), metaReceived, samplesWritten */
 int amb_stream_counters(amb_modem* m, int stream, int64_t* out8);
 
+/* ChunkAssembler without IndexedDB (app.js:597-704): keep the received chunks of every stream in a device buffer of
+ * max_file_bytes per stream - a CRC-valid metadata frame clears it (app.js:619-625), a newly received chunk is written at
+ * seqNum * chunkSize (app.js:676-677) - and hand the file out like assembleFile (app.js:666-682): size = totalFileSize of
+ * the metadata frame in force (0 before one arrived; clipped to max_file_bytes), missing chunks read as zeros. */
+int amb_stream_enable_assembly(amb_modem* m, int64_t max_file_bytes);
+int amb_stream_assemble(amb_modem* m, int stream, uint8_t* out, int64_t cap, int64_t* size_out, int mem);
+
 /* ---- transmit side (the "next" row of the scope table; also synthesises bench / test input on the device) ---- */
 /* samples of one chunk frame incl. its silences: estimateFrameSamplesWithSilence, modem.js:876-884 */
 int64_t amb_chunk_frame_samples(amb_modem* m, int64_t payload_bytes, int is_first_frame);

@@ -327,6 +327,61 @@ def test_chunk_bitmap_duplicates_and_reset(O, amb):
     _stream_compare(O, amb, "QPSK", x, pushes=[8 * 4096] * (n // (8 * 4096)) + ([n % (8 * 4096)] if n % (8 * 4096) else []))
 
 
+def _assemble_from_events(events):
+    """ChunkAssembler.handleMetadataFrame / handleDataChunk / assembleFile (app.js:610-682) over a list of result objects"""
+    total = fsize = csize = 0
+    seen, store = None, {}
+    for r in events:
+        if "error" in r:
+            continue
+        if r["frameType"] == 0xFE and r["crcValid"]:
+            total, fsize, csize, seen, store = r["totalChunks"], r["totalFileSize"], r["chunkSize"], set(), {}
+        elif r["frameType"] == 0xFF and seen is not None and not r["seqNum"] >= total and r["crcValid"] and r["seqNum"] not in seen:
+            seen.add(r["seqNum"])
+            store[r["seqNum"]] = r["data"]
+    out = bytearray(max(fsize, 0))
+    for i in range(max(total, 0)):
+        if i in store:
+            out[i * csize:i * csize + len(store[i])] = store[i]
+    return bytes(out[:max(fsize, 0)])
+
+
+def test_chunk_store_assembles_the_file(O, amb):
+    """the storage-free ChunkAssembler on the device: chunks out of order, a duplicate, a missing chunk (zeros), a short last
+    chunk; then a second file announced by a new metadata frame replaces the first"""
+    cfg, mod, rep, chunk = MODES["QPSK"]
+    data = [bytes(O.randomBytes(70 + i, chunk if i < 4 else 1000)) for i in range(5)]
+    fsize = 4 * chunk + 1000
+    parts = [O.buildMetadataFrame(cfg, 5, fsize, chunk, "f.bin", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, data[q], q, mod, rep) for q in (0, 2, 2, 4, 1)]
+    x1 = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 8))
+    second = [bytes(O.randomBytes(90 + i, 512)) for i in range(3)]
+    parts2 = [O.buildMetadataFrame(cfg, 3, 3 * 512, 512, "g.bin", mod, rep)[13230 - 2205:]]
+    parts2 += [O.buildDataChunkFrame(cfg, second[q], q, mod, rep) for q in (2, 0, 1)]
+    x2 = pad_blocks(O.addAwgn(np.concatenate(parts2), 0.003, 9))
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        m.stream_open(1, 4096, max(len(x1), len(x2)))
+        m.stream_enable_assembly(1 << 16)
+        assert m.stream_assemble(0) == b""
+        m.stream_push(x1[None, :])
+        rx = O.StreamingReceiver(cfg, mod, rep)
+        ev = rx.push(x1, 4096)
+        want = _assemble_from_events(ev)
+        got = m.stream_assemble(0)
+        assert len(got) == fsize and got == want
+        assert got[:chunk] == data[0] and got[3 * chunk:4 * chunk] == bytes(chunk) and got[4 * chunk:] == data[4]
+        n = len(x2)
+        for p0 in range(0, n, 8 * 4096):                       # the second file in small pushes
+            m.stream_push(x2[None, p0:p0 + 8 * 4096])
+        ev += rx.push(x2, 4096)
+        assert m.stream_assemble(0) == _assemble_from_events(ev)
+        c, w = m.stream_counters(), rx.counters()
+        assert c["receivedCount"] == w["receivedCount"] and c["duplicates"] == w["duplicates"]
+    finally:
+        m.close()
+
+
 def test_many_streams_one_handle(O, amb):
     """BASELINE config 5 in small: independent streams (different payload, noise seed and lead-in) side by side."""
     xs, pays = [], []
