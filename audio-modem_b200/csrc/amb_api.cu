@@ -178,7 +178,14 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
         // float32 symbol pipeline with margin guard and float64-faithful fallback; gathers the per-frame peak itself when one
         // CTA covers the whole frame
         if (frame_max && groups > 1) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
-        LAUNCH("k_demod_fast", k_demod_fast<<<dim3(n_jobs, groups), 256, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        // warps per CTA (two symbols each per round): the count that leaves the fewest symbol slots empty for the longest frame
+        int nw = 8;
+        {
+            const int ns_grp = max_nsym < AMB_SYM_GROUP ? (max_nsym > 0 ? max_nsym : 1) : AMB_SYM_GROUP;
+            int best_cost = 1 << 30;
+            for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
+        }
+        LAUNCH("k_demod_fast", k_demod_fast<<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));

@@ -822,7 +822,8 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, l = tid & 15;
     const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data, mod = T->mod;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
-    for (int i = tid; i < 256; i += 256) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
+    const int nthr = blockDim.x, nhw = nthr >> 4, nwarps = nthr >> 5;      // 5..8 warps: the launch picks the count that wastes the fewest symbol slots
+    for (int i = tid; i < 256; i += nthr) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
     // role[kk]: data index of the bin, or -1 - q for pilot q
     if (tid < AMB_MAX_PILOTS) {
         const int k = tid < T->n_pilots ? T->pilots[tid] : -1;
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         if (inb) role[k - sub_start] = -1 - tid;
     }
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
-    for (int di = tid; di < n_data; di += 256) role[T->data_k[di] - sub_start] = di;
+    for (int di = tid; di < n_data; di += nthr) role[T->data_k[di] - sub_start] = di;
     __syncthreads();
     float my_mx = 0.f;
     // ---- channel from the CE symbol (warp 0: both half-warps transform it, the lower one keeps the result; the warp-wide
@@ -864,7 +865,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         if (lane == 0) s_minhm = mn;
     } else if (folded) {
         const int64_t a = J.pos, b = J.ce_pos + cp;                  // [frame start, CE body)
-        for (int64_t g = a + (tid - 32); g < b; g += 224) {
+        for (int64_t g = a + (tid - 32); g < b; g += nthr - 32) {
             const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
             my_mx = fmaxf(my_mx, fabsf(v));
         }
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     float2* pe = s_pilot[hw];                                            // pilot bins of the symbol in flight
     const float thr = (float)T->qam_thr;
     const int n_pilots = T->n_pilots;
-    for (int s0 = g0; s0 < s_end; s0 += AMB_FD_HW) {
+    for (int s0 = g0; s0 < s_end; s0 += nhw) {
         const int sidx = s0 + hw;
         const bool active = sidx < s_end;                               // uniform per half-warp
         const int sx = active ? sidx : s_end - 1;
@@ -981,7 +982,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         my_mx = warp_maxf(my_mx);
         if (lane == 0) s_red[warp] = my_mx;
         __syncthreads();
-        if (tid == 0) { float mx = s_red[0]; for (int w = 1; w < 8; w++) mx = fmaxf(mx, s_red[w]); s_mx = mx; jobs[j].xf.mx = mx; }
+        if (tid == 0) { float mx = s_red[0]; for (int w = 1; w < nwarps; w++) mx = fmaxf(mx, s_red[w]); s_mx = mx; jobs[j].xf.mx = mx; }
         __syncthreads();
         J.xf.mx = s_mx;
     } else __syncthreads();
@@ -1003,7 +1004,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     double* h_im = h_re + AMB_FFT;
     double* work = h_im + AMB_FFT;                                       // [AMB_FD_FB_WARPS][2][512]
     double* qs = work + AMB_FD_FB_WARPS * 2 * AMB_FFT;
-    for (int i = tid; i < AMB_FFT; i += 256) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+    for (int i = tid; i < AMB_FFT; i += nthr) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
     __syncthreads();
     AmbSig sig;
     sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
