@@ -185,7 +185,13 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
             int best_cost = 1 << 30;
             for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
         }
-        LAUNCH("k_demod_fast", k_demod_fast<<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        if (T.mod == AMB_MOD_QAM16) {
+            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_QAM16><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        } else if (T.mod == AMB_MOD_QPSK) {
+            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_QPSK><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        } else {
+            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_BPSK><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        }
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
@@ -300,7 +306,9 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
     }
-    cudaFuncSetAttribute(k_demod_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);

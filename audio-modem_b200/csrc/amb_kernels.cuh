@@ -795,6 +795,7 @@ __device__ __forceinline__ float2 fd_split(const float2* buf, const float2* __re
     return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
 }
 
+template <int MOD>
 __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
                                                      int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     const int g0 = blockIdx.y * AMB_SYM_GROUP;
     if (g0 >= J.nsym) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, l = tid & 15;
-    const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data, mod = T->mod;
+    const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
     const int nthr = blockDim.x, nhw = nthr >> 4, nwarps = nthr >> 5;      // 5..8 warps: the launch picks the count that wastes the fewest symbol slots
     for (int i = tid; i < 256; i += nthr) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
@@ -959,8 +960,8 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
                 const float tol = 1e-3f + (S * cH[kk] + mag * dH[kk]) * ph1 + mag * (dphase + 1e-5f);
                 int idx;
                 float margin;
-                if (mod == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
-                else if (mod == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
+                if (MOD == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
+                else if (MOD == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
                 else {
                     const float ar = fabsf(cr), ai = fabsf(ci);
                     const int gc = cr < 0.f ? (ar > thr ? 0 : 1) : (ar > thr ? 3 : 2);
