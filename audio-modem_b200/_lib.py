@@ -23,6 +23,12 @@ class FrameResult(C.Structure):
     ]
 
 
+class LoopbackResult(C.Structure):
+    """amb_loopback_result"""
+    _fields_ = [("detected", C.c_int32), ("quality", C.c_int32), ("start_idx", C.c_int64), ("n_mag", C.c_int32), ("status", C.c_int32),
+                ("correlation", C.c_double), ("ber", C.c_double), ("snr_estimate", C.c_double), ("pilot_mag", C.c_double)]
+
+
 class AmbError(RuntimeError):
     pass
 
@@ -56,6 +62,8 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "amb_decode_chunk_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "amb_decode_received_signals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "amb_analyze_loopback": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_int]),
     "amb_stream_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64]),
     "amb_stream_close": (C.c_int, [C.c_void_p]),
     "amb_stream_input_window": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

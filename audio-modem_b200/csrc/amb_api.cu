@@ -238,6 +238,18 @@ int run_detect(amb_modem* m, const float* d_y, int64_t stride, const int64_t* d_
     return AMB_OK;
 }
 
+// detectPreambleCrossCorr over rows -> d_idx / d_best (device)
+int run_detect_xcorr(amb_modem* m, const float* d_x, int64_t stride, const int64_t* d_lens, int n, int64_t* d_idx, double* d_best) {
+    const int64_t plen = m->tables.sym_len;
+    const int64_t step = plen / 10 > 1 ? plen / 10 : 1;
+    const int64_t max_pos = stride >= plen ? (stride - plen) / step + 1 : 1;
+    CK(m->metric.ensure((size_t)n * max_pos * 8));
+    const int per = blocks_for(max_pos, 128);
+    LAUNCH("k_xcorr_coarse", k_xcorr_coarse<<<n * per, 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, step, per, m->metric.as<double>(), max_pos));
+    LAUNCH("k_xcorr_pick", k_xcorr_pick<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, step, m->metric.as<double>(), max_pos, d_idx, d_best));
+    return AMB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -510,13 +522,7 @@ int amb_detect_preamble_xcorr(amb_modem* m, const float* x, int64_t stride, cons
     if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
     CK(m->cidx.ensure((size_t)n * 8)); CK(m->cbest.ensure((size_t)n * 8));
     d_idx = m->cidx.as<int64_t>(); d_best = m->cbest.as<double>();
-    const int64_t plen = m->tables.sym_len;
-    const int64_t step = plen / 10 > 1 ? plen / 10 : 1;
-    const int64_t max_pos = stride >= plen ? (stride - plen) / step + 1 : 1;
-    CK(m->metric.ensure((size_t)n * max_pos * 8));
-    const int per = blocks_for(max_pos, 128);
-    LAUNCH("k_xcorr_coarse", k_xcorr_coarse<<<n * per, 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, step, per, m->metric.as<double>(), max_pos));
-    LAUNCH("k_xcorr_pick", k_xcorr_pick<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, d_x, stride, d_lens, stride, n, step, m->metric.as<double>(), max_pos, d_idx, d_best));
+    if ((rc = run_detect_xcorr(m, d_x, stride, d_lens, n, d_idx, d_best))) return rc;
     if (mem == AMB_MEM_HOST) {
         if (idx_out) m->pending.push_back({idx_out, d_idx, (size_t)n * 8});
         if (metric_out) m->pending.push_back({metric_out, d_best, (size_t)n * 8});
@@ -617,10 +623,56 @@ int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, co
     if ((rc = run_detect(m, m->norm.as<float>(), stride, d_lens, n, max_len))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
     LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
-                                                             m->cbest.as<double>(), m->jobs.as<AmbJob>()));
+                                                             m->cbest.as<double>(), nullptr, 0, m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(max_len / T.sym_len);
     if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
     return flush(m);
+}
+
+int amb_analyze_loopback(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, const uint8_t* test_data, int test_len,
+                         amb_loopback_result* results, double* channel_magnitude, int64_t mag_stride, int mem) {
+    int rc = check_common(m, n, stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    const AmbTables& T = m->tables;
+    const int nb = T.sub_end - T.sub_start + 1;
+    if (!results || !test_data || test_len < 0 || test_len > 65536) return fail(m, AMB_E_INVALID, "results/test_data required");
+    if (channel_magnitude && mag_stride < nb) return fail(m, AMB_E_INVALID, "mag_stride below the number of subcarriers in the band");
+    const float* d_x; const int64_t* d_lens;
+    if ((rc = in_ptr(m, x, (size_t)n * stride, mem, m->in_a, &d_x))) return rc;
+    if ((rc = in_ptr(m, lens, (size_t)n, mem, m->in_lens, &d_lens))) return rc;
+    const int64_t max_len = mem == AMB_MEM_HOST ? max_len_of(lens, n, stride) : stride;
+    // decoded bytes kept per recording: the name length byte, up to 255 name bytes, the length field and the fixture
+    const int64_t bytes_stride = (1 + 255 + 4 + (int64_t)test_len + 15) / 16 * 16;
+    CK(m->norm.ensure((size_t)n * stride * 4));
+    CK(m->out_res.ensure((size_t)n * sizeof(amb_frame_result))); CK(m->out_bytes.ensure((size_t)n * bytes_stride));
+    CK(m->out_a.ensure((size_t)n * sizeof(amb_loopback_result))); CK(m->out_b.ensure((size_t)n * nb * 8)); CK(m->in_b.ensure((size_t)(test_len > 0 ? test_len : 1)));
+    CK(m->in_c.ensure((size_t)n * 16));
+    if (test_len > 0) CK(cudaMemcpyAsync(m->in_b.p, test_data, (size_t)test_len, cudaMemcpyHostToDevice, m->stream));
+    if ((rc = run_stats(m, d_x, stride, d_lens, n, max_len))) return rc;
+    if ((rc = run_apply(m, d_x, stride, d_lens, n, max_len, m->norm.as<float>()))) return rc;
+    if ((rc = run_detect(m, m->norm.as<float>(), stride, d_lens, n, max_len))) return rc;
+    int64_t* d_xidx = m->in_c.as<int64_t>();
+    double* d_xbest = reinterpret_cast<double*>(d_xidx + n);
+    if ((rc = run_detect_xcorr(m, m->norm.as<float>(), stride, d_lens, n, d_xidx, d_xbest))) return rc;
+    CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
+    LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
+                                                             m->cbest.as<double>(), d_xidx, 1, m->jobs.as<AmbJob>()));
+    const int max_nsym = (int)(max_len / T.sym_len);
+    if ((rc = run_demod_parse(m, n, max_nsym, false, m->out_res.as<amb_frame_result>(), m->out_bytes.as<uint8_t>(), bytes_stride))) return rc;
+    LAUNCH("k_loopback_report", k_loopback_report<<<n, 32, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n, m->out_res.as<amb_frame_result>(), m->out_bytes.as<uint8_t>(),
+                                                                           bytes_stride, m->in_b.as<uint8_t>(), test_len, m->out_a.as<amb_loopback_result>(),
+                                                                           m->out_b.as<double>(), nb));
+    CK(cudaMemcpyAsync(results, m->out_a.p, (size_t)n * sizeof(amb_loopback_result), cudaMemcpyDeviceToHost, m->stream));
+    if (channel_magnitude)
+        CK(cudaMemcpy2DAsync(channel_magnitude, (size_t)mag_stride * 8, m->out_b.p, (size_t)nb * 8, (size_t)nb * 8, n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < n; i++) {
+        amb_loopback_result& r = results[i];
+        // modem.js:1048-1049; the early returns (:989, :1021) report 0
+        if (r.n_mag > 0) r.snr_estimate = r.pilot_mag > 0.0 ? 20.0 * std::log10(r.pilot_mag) : -INFINITY;
+        if (channel_magnitude && r.n_mag == 0) for (int k = 0; k < nb; k++) channel_magnitude[(int64_t)i * mag_stride + k] = 0.0;
+    }
+    return AMB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- streaming

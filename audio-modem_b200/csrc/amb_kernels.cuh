@@ -1341,7 +1341,7 @@ __global__ void k_replay(const float* __restrict__ y, int64_t stride, const int6
 __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restrict__ T, const float* __restrict__ y, int64_t stride,
                                                        const int64_t* __restrict__ lens, int64_t n_default, int n,
                                                        const int64_t* __restrict__ coarse_idx, const double* __restrict__ coarse_best,
-                                                       AmbJob* __restrict__ jobs) {
+                                                       const int64_t* __restrict__ alt_idx, int analyze, AmbJob* __restrict__ jobs) {
     __shared__ double scratch[4][64];
     const int warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
@@ -1352,7 +1352,10 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
     J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
     J.stream = r; J.mode = 1; J.status = 0; J.nsym = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
     J.coarse = coarse_best[r]; J.fine = 0.0; J.result_pos = -1;
-    const int64_t c = coarse_idx[r];
+    // analyzeLoopback falls back to the cross-correlation detector (modem.js:983-987), keeps a weak refinement (no 0.1
+    // test, :1016) and still reports the channel when no data follows the CE symbol (:1052)
+    int64_t c = coarse_idx[r];
+    if (c < 0 && alt_idx) c = alt_idx[r];
     if (c < 0) J.status = AMB_ST_PREAMBLE_NOT_DETECTED;
     else {
         AmbSig sig; sig.p = J.p; sig.base = 0; sig.lo = 0; sig.hi = len; sig.xf = J.xf;
@@ -1361,17 +1364,77 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
         int64_t pos;
         const double best = amb_fine_xcorr(T, sig, fs, fe, c, scratch[warp], &pos);
         J.fine = best;
-        if (best < 0.1) J.status = AMB_ST_PREAMBLE_LOW_CORRELATION;
+        if (!analyze && best < 0.1) J.status = AMB_ST_PREAMBLE_LOW_CORRELATION;
         else {
             J.pos = pos; J.result_pos = pos;
             J.ce_pos = pos + 2 * plen;
             J.data_pos = J.ce_pos + plen;
             if (J.ce_pos + plen > len) J.status = AMB_ST_SIGNAL_TOO_SHORT_FOR_CE;
-            else if (J.data_pos >= len) J.status = AMB_ST_NO_DATA_AFTER_CE;
+            else if (J.data_pos >= len) { if (!analyze) J.status = AMB_ST_NO_DATA_AFTER_CE; }
             else J.nsym = (int32_t)((len - J.data_pos) / plen);
         }
     }
     if ((threadIdx.x & 31) == 0) jobs[r] = J;
+}
+
+// analyzeLoopback's report (modem.js:1016-1081) for recordings refined by k_refine_batch(analyze) and decoded by the
+// demodulator + k_parse: channel magnitude per subcarrier and the mean pilot magnitude from the float64-faithful channel
+// estimate, the bit error rate of the fixture bytes inside the decoded packet, the quality class.  One warp per recording.
+// snr_estimate is left to the host (20 log10 of pilot_mag with the C library, like the reference's Math.log10).
+__global__ void __launch_bounds__(32) k_loopback_report(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n,
+                                                        const amb_frame_result* __restrict__ parsed, const uint8_t* __restrict__ bytes, int64_t bytes_stride,
+                                                        const uint8_t* __restrict__ test_data, int test_len,
+                                                        amb_loopback_result* __restrict__ out, double* __restrict__ mags, int64_t mag_stride) {
+    __shared__ double tw_re[AMB_FFT], tw_im[AMB_FFT], h_re[AMB_FFT], h_im[AMB_FFT], re[AMB_FFT], im[AMB_FFT];
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (r >= n) return;
+    const AmbJob J = jobs[r];
+    amb_loopback_result R;
+    R.detected = J.status != AMB_ST_PREAMBLE_NOT_DETECTED; R.quality = 0; R.start_idx = R.detected ? J.pos : -1; R.n_mag = 0; R.status = J.status;
+    R.correlation = (R.detected && J.fine > 0.0) ? J.fine : 0.0;          // Math.max(0, bestMetric)
+    R.ber = 1.0; R.snr_estimate = 0.0; R.pilot_mag = 0.0;
+    if (J.status == 0) {
+        for (int i = lane; i < AMB_FFT; i += 32) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+        __syncwarp();
+        AmbSig sig;
+        sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
+        amb_fft512_load(sig, J.ce_pos + T->cp_len, re, im);
+        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+        amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
+        __syncwarp();
+        const int nb = T->sub_end - T->sub_start + 1;
+        for (int kk = lane; kk < nb && kk < mag_stride; kk += 32) {
+            const int k = T->sub_start + kk;
+            mags[(int64_t)r * mag_stride + kk] = amb_sqrt(amb_add(amb_mul(h_re[k], h_re[k]), amb_mul(h_im[k], h_im[k])));
+        }
+        R.n_mag = nb;
+        // pilots in table order, sequential float64 sum (modem.js:1036-1047)
+        double snr_sum = 0.0;
+        int snr_count = 0;
+        for (int q = 0; q < T->n_pilots; q++) {
+            const int k = T->pilots[q];
+            if (k < T->sub_start || k > T->sub_end) continue;
+            const double mag = amb_sqrt(amb_add(amb_mul(h_re[k], h_re[k]), amb_mul(h_im[k], h_im[k])));
+            if (mag > 1e-6) { snr_sum = amb_add(snr_sum, mag); snr_count++; }
+        }
+        R.pilot_mag = snr_count > 0 ? amb_div(snr_sum, (double)snr_count) : 0.0;
+        // bit errors of the fixture inside the decoded packet (modem.js:1057-1071)
+        const int64_t n_bytes = parsed[r].n_bytes;
+        const uint8_t* d = bytes + (int64_t)r * bytes_stride;
+        if (J.nsym > 0 && n_bytes >= 29) {
+            const int64_t off = 1 + (int64_t)d[0] + 4;
+            if (off + test_len <= n_bytes) {
+                int errs = 0;
+                for (int i = lane; i < test_len; i += 32) errs += __popc((unsigned)(d[off + i] ^ test_data[i]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
+                R.ber = amb_div((double)errs, (double)(test_len * 8));
+            }
+        }
+    }
+    if (R.ber == 0.0 && R.correlation > 0.8) R.quality = 2;
+    else if (R.ber < 0.05) R.quality = 1;
+    if (lane == 0) out[r] = R;
 }
 
 // detectPreambleCrossCorr, modem.js:235-283: coarse metric at every `step`-th offset (one warp per offset

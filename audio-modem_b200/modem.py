@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import CFG, MOD, MEM_DEVICE, MEM_HOST, MEM_INPLACE, AmbError, FrameResult
+from ._lib import CFG, MOD, MEM_DEVICE, MEM_HOST, MEM_INPLACE, AmbError, FrameResult, LoopbackResult
 
 FRAME_META = 0xFE   # modem.js:661
 FRAME_DATA = 0xFF   # modem.js:662
@@ -275,6 +275,21 @@ class Modem:
         """decodeReceivedSignal (modem.js:557) over many recordings"""
         return self._decode(self._L.amb_decode_received_signals, recordings, raw)
 
+    def analyze_loopback(self, recordings, testData=bytes(range(16))):
+        """analyzeLoopback (modem.js:978-1081) over many recordings -> list of
+        {detected, correlation, ber, channelMagnitude, snrEstimate, quality} (+ startIdx)."""
+        x, lens = _pack_rows(recordings)
+        n, stride = x.shape
+        td = np.frombuffer(bytes(testData), np.uint8).copy() if not isinstance(testData, np.ndarray) else np.ascontiguousarray(testData, np.uint8)
+        nb = self.SUB_END - self.SUB_START + 1
+        res = (LoopbackResult * max(n, 1))()
+        mags = np.zeros((max(n, 1), nb), np.float64)
+        self._ck(self._L.amb_analyze_loopback(self._h, _ptr(x), stride, _ptr(lens), n, _ptr(td), len(td), C.cast(res, C.c_void_p), _ptr(mags), nb,
+                                              MEM_HOST))
+        return [{"detected": bool(r.detected), "correlation": r.correlation, "ber": r.ber, "channelMagnitude": mags[i, : r.n_mag].copy(),
+                 "snrEstimate": r.snr_estimate, "quality": ("poor", "good", "excellent")[r.quality], "startIdx": int(r.start_idx)}
+                for i, r in enumerate(res[:n])]
+
     # ------------------------------------------------------------------ transmit side
     def chunk_frame_samples(self, payload_bytes, first=False):
         """estimateFrameSamplesWithSilence (modem.js:876-884)"""
@@ -482,6 +497,11 @@ def demodulateOFDM(signal, modName, channelRe, channelIm):
 
 def decodeReceivedSignal(signal, modName, repetition=1):
     return _modem(modName, repetition).decode_received_signals([signal])[0]
+
+
+def analyzeLoopback(recorded, modName, repetition=1, testData=bytes(range(16))):
+    """modem.js:978-1081"""
+    return _modem(modName, repetition).analyze_loopback([recorded], testData)[0]
 
 
 def decodeChunkFrame(frameSamples, modName, repetition=1):

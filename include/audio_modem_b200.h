@@ -181,6 +181,25 @@ int amb_decode_chunk_frames(amb_modem* m, const float* frames, int64_t stride, c
 int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n,
                                 amb_frame_result* results, uint8_t* bytes_out, int64_t bytes_stride, int mem);
 
+/* analyzeLoopback, modem.js:978-1081 (the reference's only fixture check): preprocess, detectPreamble with the
+ * detectPreambleCrossCorr fallback, refine, channel estimate, demodulate, compare against the fixture bytes.
+ * One recording per row.  test_data = the bytes sent (generateTestSignal's 00..0F, modem.js:914-916), host memory.
+ * results (host memory) mirrors the returned object; channel_magnitude (host memory, optional) = [n][mag_stride]
+ * doubles, SUB_END - SUB_START + 1 per detected recording whose CE symbol fits (n_mag), zeros otherwise. */
+typedef struct amb_loopback_result {
+    int32_t detected;
+    int32_t quality;      /* 0 'poor', 1 'good', 2 'excellent' (modem.js:1075-1081) */
+    int64_t start_idx;    /* refined preamble start; -1 when not detected */
+    int32_t n_mag;        /* channelMagnitude.length */
+    int32_t status;       /* AMB_ST_* of the refinement: 0, PREAMBLE_NOT_DETECTED or SIGNAL_TOO_SHORT_FOR_CE */
+    double correlation;   /* max(0, refined cross-correlation peak) */
+    double ber;           /* bit error rate over the fixture bytes; 1 when they cannot be located */
+    double snr_estimate;  /* 20 log10(pilot_mag); -Infinity when no pilot qualifies; 0 on the early returns */
+    double pilot_mag;     /* mean |H| over the pilots above 1e-6 (modem.js:1036-1047) */
+} amb_loopback_result;
+int amb_analyze_loopback(amb_modem* m, const float* x, int64_t stride, const int64_t* lens, int n, const uint8_t* test_data,
+                         int test_len, amb_loopback_result* results, double* channel_magnitude, int64_t mag_stride, int mem);
+
 /* ---- streaming receiver: new StreamingReceiver(modName, repetition) / processAudioBlock,
  *      app.js:706-981, for n_streams independent streams at once ------------------------- */
 /* block_len = the ScriptProcessor block size whose call cadence is emulated (app.js:1107: 4096);

@@ -127,6 +127,29 @@ napi_value DecodeOne(napi_env env, napi_callback_info info) {
     return result_object(env, r, bytes.data());
 }
 
+// analyzeLoopback(handle, Float32Array recorded, Uint8Array testData) -> {detected, correlation, ber, channelMagnitude, snrEstimate, quality}
+napi_value AnalyzeLoopback(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; const float* x; size_t n;
+    if (!get_modem(env, a[0], &m) || !get_f32(env, a[1], &x, &n)) return nullptr;
+    napi_typedarray_type tt; size_t tn = 0; void* td = nullptr;
+    NAPI_CALL(env, napi_get_typedarray_info(env, a[2], &tt, &tn, &td, nullptr, nullptr));
+    amb_loopback_result r;
+    double mags[256];
+    if (amb_analyze_loopback(m, x, (int64_t)n, nullptr, 1, (const uint8_t*)td, (int)tn, &r, mags, 256, AMB_MEM_HOST) != AMB_OK) { napi_throw_error(env, nullptr, amb_last_error(m)); return nullptr; }
+    napi_value o, b, arr, q;
+    napi_create_object(env, &o);
+    napi_get_boolean(env, r.detected != 0, &b); napi_set_named_property(env, o, "detected", b);
+    set_num(env, o, "correlation", r.correlation); set_num(env, o, "ber", r.ber); set_num(env, o, "snrEstimate", r.snr_estimate);
+    napi_create_array_with_length(env, (size_t)r.n_mag, &arr);
+    for (int k = 0; k < r.n_mag; k++) { napi_value v; napi_create_double(env, mags[k], &v); napi_set_element(env, arr, (uint32_t)k, v); }
+    napi_set_named_property(env, o, "channelMagnitude", arr);
+    static const char* names[3] = {"poor", "good", "excellent"};
+    napi_create_string_utf8(env, names[r.quality], NAPI_AUTO_LENGTH, &q); napi_set_named_property(env, o, "quality", q);
+    return o;
+}
+
 // streamOpen(handle, nStreams, blockLen, maxPush); streamPush(handle, Float32Array[nStreams*nNew], nNew) -> result[]
 napi_value StreamOpen(napi_env env, napi_callback_info info) {
     size_t argc = 4; napi_value a[4];
@@ -165,6 +188,7 @@ napi_value Init(napi_env env, napi_value exports) {
         {"detectPreamble", nullptr, DetectPreamble, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"decodeReceivedSignal", nullptr, DecodeOne<amb_decode_received_signals>, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"decodeChunkFrame", nullptr, DecodeOne<amb_decode_chunk_frames>, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"analyzeLoopback", nullptr, AnalyzeLoopback, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamOpen", nullptr, StreamOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamPush", nullptr, StreamPush, nullptr, nullptr, nullptr, napi_default, nullptr},
     };

@@ -23,6 +23,7 @@ module.exports = {
   detectPreamble(signal) { return addon.detectPreamble(modem('QPSK', 1), Float32Array.from(signal)); },
   decodeReceivedSignal(signal, modName, repetition) { return addon.decodeReceivedSignal(modem(modName, repetition), Float32Array.from(signal)); },
   decodeChunkFrame(frameSamples, modName, repetition) { return addon.decodeChunkFrame(modem(modName, repetition), Float32Array.from(frameSamples)); },
+  analyzeLoopback(recorded, modName, repetition, testData) { return addon.analyzeLoopback(modem(modName, repetition), Float32Array.from(recorded), Uint8Array.from(testData)); },
   // app.js:706-981 without DOM / IndexedDB: processAudioBlock returns the frames it completed
   StreamingReceiver: class {
     constructor(modName, repetition) {

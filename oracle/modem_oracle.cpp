@@ -767,6 +767,78 @@ static void decode_received_signal_impl(const Ofdm& o, const float* raw, int64_t
     r->frame_type = 0;
 }
 
+// modem.js:978-1081 analyzeLoopback.  `channelMagnitude` has SUB_END-SUB_START+1 entries when the channel was
+// estimated, none otherwise (n_mag says which); quality: 0 'poor', 1 'good', 2 'excellent'.
+typedef struct {
+    int32_t detected;
+    int32_t quality;
+    int64_t start_idx;        // refined start (the coarse index when no offset passed the denominator test); -1 when not detected
+    int32_t n_mag;
+    int32_t pad;
+    double correlation;
+    double ber;
+    double snr_estimate;      // 20 log10(mean pilot |H|); -Infinity when no pilot qualifies; 0 on the early returns
+} OrcLoopback;
+
+static void analyze_loopback_impl(const Ofdm& o, const float* recorded, int64_t n, int mod, int repetition,
+                                  const uint8_t* testData, int testLen, OrcLoopback* r, double* mags) {
+    std::memset(r, 0, sizeof(*r));
+    r->start_idx = -1; r->ber = 1.0;
+    const fvec signal = preprocess(recorded, n);                                            // :980
+    double best = 0;
+    int64_t coarseIdx = detect_autocorr(o, signal.data(), n, &best);                        // :983
+    if (coarseIdx < 0) coarseIdx = detect_xcorr(o, signal.data(), n, &best);                // :984-987
+    if (coarseIdx < 0) return;                                                              // :988-990
+    r->detected = 1;
+    const fvec pre1 = preamble1(o);
+    double tEnergy = 0;
+    for (float v : pre1) tEnergy += (double)v * v;
+    const int64_t searchRadius = o.CP_LEN * 3;
+    const int64_t fineStart = std::max<int64_t>(0, coarseIdx - searchRadius);
+    const int64_t fineEnd = std::min<int64_t>(n - (int64_t)pre1.size(), coarseIdx + searchRadius);
+    double bestMetric;
+    const int64_t startIdx = fine_xcorr(pre1, tEnergy, signal.data(), fineStart, fineEnd, coarseIdx, &bestMetric);   // :993-1014
+    r->start_idx = startIdx;
+    r->correlation = bestMetric > 0 ? bestMetric : 0.0;                                     // :1016 Math.max(0, bestMetric)
+    const int64_t ceStart = startIdx + 2 * o.SYMBOL_LEN;
+    if (ceStart + o.SYMBOL_LEN > n) return;                                                 // :1020-1022
+    dvec knownRe; ce_symbol(o, knownRe);
+    dvec knownIm(o.FFT_SIZE, 0.0), chRe, chIm;
+    estimate_channel(o, signal.data() + ceStart, o.SYMBOL_LEN, knownRe, knownIm, chRe, chIm);
+    for (int k = o.SUB_START; k <= o.SUB_END; k++)                                          // :1029-1033
+        mags[r->n_mag++] = std::sqrt(chRe[k] * chRe[k] + chIm[k] * chIm[k]);
+    double snrSum = 0; int snrCount = 0;                                                    // :1036-1047
+    for (int p : o.PILOTS) {
+        if (p >= o.SUB_START && p <= o.SUB_END) {
+            const double mag = std::sqrt(chRe[p] * chRe[p] + chIm[p] * chIm[p]);
+            if (mag > 1e-6) { snrSum += mag; snrCount++; }
+        }
+    }
+    const double avgPilotMag = snrCount > 0 ? snrSum / snrCount : 0.0;
+    r->snr_estimate = avgPilotMag > 0 ? 20 * std::log10(avgPilotMag) : -INFINITY;
+    const int64_t dataStart = ceStart + o.SYMBOL_LEN;
+    if (dataStart < n) {                                                                    // :1052-1072
+        bvec bits = demodulate(o, signal.data() + dataStart, n - dataStart, mod, chRe, chIm, nullptr);
+        if (repetition > 1) bits = majority_vote(bits, repetition);
+        const bvec decoded = bits_to_bytes(bits);
+        if (decoded.size() >= 29) {
+            const int nameLen = decoded[0];
+            const size_t dataOffset = 1 + nameLen + 4;
+            if (dataOffset + (size_t)testLen <= decoded.size()) {
+                int errorBits = 0;
+                for (int i = 0; i < testLen; i++) {
+                    const int x = decoded[dataOffset + i] ^ testData[i];
+                    for (int b = 0; b < 8; b++) errorBits += (x >> b) & 1;
+                }
+                r->ber = (double)errorBits / (double)(testLen * 8);                         // 0/0 = NaN for empty test data, as in JS
+            }
+        }
+    }
+    if (r->ber == 0 && r->correlation > 0.8) r->quality = 2;                                // :1075-1081
+    else if (r->ber < 0.05) r->quality = 1;
+    else r->quality = 0;
+}
+
 // ---------------------------------------------------------------- exports ---
 int orc_result_size(void) { return (int)sizeof(OrcResult); }
 
@@ -929,6 +1001,13 @@ void orc_decode_chunk_frame(int cfg, int mod, int rep, const float* frame, int64
 }
 void orc_decode_received_signal(int cfg, int mod, int rep, const float* x, int64_t n, OrcResult* r, uint8_t* bytes_out, int64_t cap) {
     decode_received_signal_impl(ofdm_config(cfg), x, n, mod, rep, r, bytes_out, cap);
+}
+
+int orc_loopback_size(void) { return (int)sizeof(OrcLoopback); }
+// analyzeLoopback (modem.js:978-1081); mags needs SUB_END-SUB_START+1 doubles
+void orc_analyze_loopback(int cfg, int mod, int rep, const float* x, int64_t n, const uint8_t* test_data, int test_len,
+                          OrcLoopback* r, double* mags) {
+    analyze_loopback_impl(ofdm_config(cfg), x, n, mod, rep <= 0 ? 1 : rep, test_data, test_len, r, mags);
 }
 
 // ============================================================================

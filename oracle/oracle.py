@@ -48,6 +48,14 @@ class OrcResult(C.Structure):
     ]
 
 
+class OrcLoopback(C.Structure):
+    _fields_ = [("detected", C.c_int32), ("quality", C.c_int32), ("start_idx", C.c_int64), ("n_mag", C.c_int32),
+                ("pad", C.c_int32), ("correlation", C.c_double), ("ber", C.c_double), ("snr_estimate", C.c_double)]
+
+
+QUALITY = ("poor", "good", "excellent")
+
+
 def build(force=False):
     """Compile the oracle if needed (gcc only; never touches /root/reference)."""
     src = os.path.join(_HERE, "modem_oracle.cpp")
@@ -94,6 +102,8 @@ def lib():
             "orc_estimate_frame_samples": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
             "orc_decode_chunk_frame": (None, [C.c_int, C.c_int, C.c_int, f32p, C.c_int64, C.POINTER(OrcResult), u8p, C.c_int64]),
             "orc_decode_received_signal": (None, [C.c_int, C.c_int, C.c_int, f32p, C.c_int64, C.POINTER(OrcResult), u8p, C.c_int64]),
+            "orc_loopback_size": (C.c_int, []),
+            "orc_analyze_loopback": (None, [C.c_int, C.c_int, C.c_int, f32p, C.c_int64, u8p, C.c_int, C.POINTER(OrcLoopback), f64p]),
             "orc_stream_new": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
             "orc_stream_free": (None, [C.c_void_p]),
             "orc_stream_push": (None, [C.c_void_p, f32p, C.c_int64, C.c_int64]),
@@ -116,6 +126,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         assert L.orc_result_size() == C.sizeof(OrcResult)
+        assert L.orc_loopback_size() == C.sizeof(OrcLoopback)
         _lib = L
     return _lib
 
@@ -364,6 +375,27 @@ def decodeChunkFrame(cfg, frame, mod, rep=1, raw=False):
 
 def decodeReceivedSignal(cfg, x, mod, rep=1, raw=False):
     return _decode(lib().orc_decode_received_signal, cfg, x, mod, rep, raw)
+
+
+TEST_DATA = bytes(range(16))      # modem.js:914-916
+
+
+def generateTestSignal(cfg, mod, rep=1):
+    """modem.js:913-975: the same construction as buildTransmitSignal over 00..0F named 'test'."""
+    return {"signal": buildTransmitSignal(cfg, TEST_DATA, mod, "test", rep), "testData": np.frombuffer(TEST_DATA, dtype=np.uint8).copy()}
+
+
+def analyzeLoopback(cfg, recorded, mod, rep=1, testData=TEST_DATA):
+    """modem.js:978-1081 -> {detected, correlation, ber, channelMagnitude, snrEstimate, quality} (+ startIdx)."""
+    x = _f32(recorded)
+    td = _u8(testData)
+    c = config(cfg)
+    mags = np.zeros(c["SUB_END"] - c["SUB_START"] + 1, dtype=np.float64)
+    r = OrcLoopback()
+    lib().orc_analyze_loopback(_cfg(cfg), _mod(mod), rep, _p(x, C.c_float), len(x), _p(td, C.c_uint8), len(td), C.byref(r),
+                               _p(mags, C.c_double))
+    return {"detected": bool(r.detected), "correlation": r.correlation, "ber": r.ber, "channelMagnitude": mags[: r.n_mag].copy(),
+            "snrEstimate": r.snr_estimate, "quality": QUALITY[r.quality], "startIdx": int(r.start_idx)}
 
 
 class StreamingReceiver:

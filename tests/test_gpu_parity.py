@@ -232,6 +232,58 @@ def test_decode_received_signals_batch(O, modems, mode):
         assert objs[i] == O.decodeReceivedSignal(cfg, r, mod, rep), (mode, i)
 
 
+def _loopback_cases(O, cfg, mod, rep):
+    """generateTestSignal (modem.js:913-975) clean and through channels, plus the early-return and fallback cases"""
+    t = O.generateTestSignal(cfg, mod, rep)["signal"]
+    lead = 13230 if cfg == "standard" else 22050
+    sym = O.config(cfg)["SYMBOL_LEN"]
+    p = O.power(t[lead:][:5000])
+    cases = [t]
+    cases.append(O.addAwgn(t, np.sqrt(p / 10 ** 2.0), 3))                                    # 20 dB
+    cases.append(O.addAwgn(O.multipath(t, [0, 23, 57], [1.0, 0.5, 0.25]), np.sqrt(p / 10 ** 1.2), 4))
+    cases.append(O.addAwgn(t, np.sqrt(p / 10 ** 0.3), 5))                                    # 3 dB: bit errors
+    spike = t.copy(); spike[5] = 60.0                                                        # energy gate of detectPreamble fails -> cross-correlation fallback
+    cases.append(spike)
+    cases.append(t[: lead + 2 * sym + 10])                                                   # CE does not fit
+    cases.append(t[: lead + 3 * sym])                                                        # channel, but no data symbols
+    cases.append(t[: lead + 3 * sym + 5 * sym // 2])                                         # packet cut short
+    cases.append(np.zeros(30000, np.float32))                                                # nothing detected
+    cases.append((np.random.default_rng(1).standard_normal(20000) * 0.1).astype(np.float32))
+    return cases
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_analyze_loopback(O, modems, mode):
+    """analyzeLoopback (modem.js:978-1081): every field of the report against the oracle; float64 fields bit-equal
+    (the device path repeats the reference's operation order; snrEstimate's log10 runs in the C library on both sides)."""
+    cfg, mod, rep, _ = MODES[mode]
+    cases = _loopback_cases(O, cfg, mod, rep)
+    got = modems(mode).analyze_loopback(cases)
+    seen = set()
+    for i, (x, g) in enumerate(zip(cases, got)):
+        w = O.analyzeLoopback(cfg, x, mod, rep)
+        for k in ("detected", "quality", "startIdx", "ber"):
+            assert g[k] == w[k] or (k == "ber" and np.isnan(g[k]) and np.isnan(w[k])), (mode, i, k, g[k], w[k])
+        assert g["correlation"] == pytest.approx(w["correlation"], rel=1e-12, abs=1e-15), (mode, i)
+        assert len(g["channelMagnitude"]) == len(w["channelMagnitude"]), (mode, i)
+        assert np.array_equal(g["channelMagnitude"], w["channelMagnitude"]), (mode, i)
+        assert g["snrEstimate"] == w["snrEstimate"], (mode, i, g["snrEstimate"], w["snrEstimate"])
+        seen.add((w["detected"], len(w["channelMagnitude"]) > 0, w["quality"]))
+    if cfg != "narrowband":
+        assert got[0]["quality"] == "excellent" and got[0]["ber"] == 0.0
+    assert (False, False, "poor") in seen and (True, False, "poor") in seen
+
+
+def test_analyze_loopback_global_function(O, amb):
+    amb.setOFDMConfig("standard")
+    t = O.generateTestSignal("standard", "QPSK", 1)
+    g = amb.analyzeLoopback(t["signal"], "QPSK", 1, t["testData"])
+    w = O.analyzeLoopback("standard", t["signal"], "QPSK", 1)
+    assert g["quality"] == w["quality"] == "excellent" and g["startIdx"] == 13230
+    wrong = bytes(range(1, 17))
+    assert amb.analyzeLoopback(t["signal"], "QPSK", 1, wrong)["ber"] == O.analyzeLoopback("standard", t["signal"], "QPSK", 1, wrong)["ber"] > 0
+
+
 def _stream_compare(O, amb, mode, x, pushes=None, n_streams=1):
     cfg, mod, rep, _ = MODES[mode]
     xs = x if isinstance(x, list) else [x]
