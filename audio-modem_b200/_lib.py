@@ -69,6 +69,8 @@ EXPORTS = {
     "amb_stream_input_window": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "amb_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                   C.c_void_p, C.c_int64, C.c_int]),
+    "amb_stream_push_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                        C.c_void_p, C.c_int64, C.c_int]),
     "amb_stream_counters": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "amb_stream_enable_assembly": (C.c_int, [C.c_void_p, C.c_int64]),
     "amb_stream_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int]),

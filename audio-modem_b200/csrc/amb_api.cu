@@ -64,6 +64,7 @@ struct amb_modem {
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
+    bool push_pcm16 = false;          // input format of the push in progress
     int n_streams = 0;
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
@@ -321,7 +322,8 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
+    cudaFuncSetAttribute(k_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
+    cudaFuncSetAttribute(k_front<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
@@ -809,7 +811,7 @@ static int stream_compact(amb_modem* m) {
 }
 
 // One push of n_new samples per stream, read from device memory (src rows 16-byte aligned).
-static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t n_new, amb_frame_result* results,
+static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t n_new, amb_frame_result* results,
                      int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
     const AmbTables& T = m->tables;
     const int ns = m->n_streams;
@@ -836,7 +838,8 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
         fa.span = (int)span; fa.spans = (int)((tiles + span - 1) / span); fa.warm = 10;
         fa.E = m->d_ema; fa.states = m->states.as<AmbStreamState>(); fa.dc_next = m->dc_next.as<double>();
         fa.sums = m->sums.as<float>(); fa.sum_stride = m->sum_stride; fa.st = ss;
-        LAUNCH("k_front", k_front<<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa));
+        if (m->push_pcm16) { LAUNCH("k_front", k_front<int16_t><<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa)); }
+        else { LAUNCH("k_front", k_front<float><<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa)); }
     }
     LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < 148 * 16 ? (m->slot_cap + 3) / 4 : 148 * 16, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
     {
@@ -1015,8 +1018,9 @@ static int push_core(amb_modem* m, const float* src, int64_t src_stride, int64_t
     return overflow ? AMB_E_OVERFLOW : AMB_OK;
 }
 
-int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
-                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
+// samples of one push in either input format (es = bytes per sample: 4 float32, 2 16-bit PCM)
+static int stream_push_any(amb_modem* m, const void* xv, int es, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                           int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
     if (!m) return AMB_E_INVALID;
     m->pending.clear();
     if (!m->open) return fail(m, AMB_E_STATE, "stream not open");
@@ -1024,13 +1028,17 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     if (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE && mem != AMB_MEM_INPLACE) return fail(m, AMB_E_INVALID, "bad mem");
     if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
     if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
-    if (mem != AMB_MEM_INPLACE && !x) return fail(m, AMB_E_INVALID, "x required");
+    if (mem != AMB_MEM_INPLACE && !xv) return fail(m, AMB_E_INVALID, "x required");
+    if (mem == AMB_MEM_INPLACE && es != 4) return fail(m, AMB_E_INVALID, "the in-place window holds float32 samples");
     if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");
     const int ns = m->n_streams;
+    m->push_pcm16 = es == 2;
+    const char* x = static_cast<const char*>(xv);
     // samples are read where they are when they sit in device memory with 16-byte aligned rows; otherwise they are staged
-    if (mem == AMB_MEM_DEVICE && ((uintptr_t)x & 15) == 0 && (x_stride & 3) == 0)
+    if (mem == AMB_MEM_DEVICE && ((uintptr_t)x & 15) == 0 && ((x_stride * es) & 15) == 0)
         return push_core(m, x, x_stride, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
-    float* raw = m->raw.as<float>();
+    char* raw = m->raw.as<char>();                      // rows of max_push samples in the input's own format
+    const size_t pitch = (size_t)m->max_push * es;
     if (mem == AMB_MEM_INPLACE) return push_core(m, raw, m->max_push, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
     // Large host pushes are cut into sections: all host->device copies are queued at once on a second stream, and
     // section k is processed (as a push of its own: same results, the receiver state carries over) while the sections
@@ -1038,9 +1046,9 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     const int64_t blocks = n_new / m->block_len;
     int64_t n_sec = 1;
     static const int64_t sec_min_bytes = std::getenv("AMB_SECTION_MIN_BYTES") ? std::atoll(std::getenv("AMB_SECTION_MIN_BYTES")) : (64ll << 20);
-    if (mem == AMB_MEM_HOST && (int64_t)ns * n_new * 4 >= sec_min_bytes && blocks >= 8) n_sec = 8;
+    if (mem == AMB_MEM_HOST && (int64_t)ns * n_new * es >= sec_min_bytes && blocks >= 8) n_sec = 8;
     if (n_sec == 1) {
-        CK(cudaMemcpy2DAsync(raw, (size_t)m->max_push * 4, x, (size_t)x_stride * 4, (size_t)n_new * 4, ns,
+        CK(cudaMemcpy2DAsync(raw, pitch, x, (size_t)x_stride * es, (size_t)n_new * es, ns,
                              mem == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, m->stream));
         return push_core(m, raw, m->max_push, n_new, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
     }
@@ -1051,7 +1059,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     for (int64_t b = 0; b < blocks; b += sec_blocks) { sec_off.push_back(b * m->block_len); sec_len.push_back((b + sec_blocks < blocks ? sec_blocks : blocks - b) * m->block_len); }
     // the staging buffer is free: the previous push synchronised after its last reader
     for (size_t k = 0; k < sec_off.size(); k++) {
-        CK(cudaMemcpy2DAsync(raw + sec_off[k], (size_t)m->max_push * 4, x + sec_off[k], (size_t)x_stride * 4, (size_t)sec_len[k] * 4, ns, cudaMemcpyHostToDevice, m->copy_stream));
+        CK(cudaMemcpy2DAsync(raw + sec_off[k] * es, pitch, x + sec_off[k] * es, (size_t)x_stride * es, (size_t)sec_len[k] * es, ns, cudaMemcpyHostToDevice, m->copy_stream));
         CK(cudaEventRecord(m->copy_events[k], m->copy_stream));
     }
     int total = 0, rc_all = AMB_OK;
@@ -1059,7 +1067,7 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
         CK(cudaStreamWaitEvent(m->stream, m->copy_events[k], 0));
         const int room = max_results - total > 0 ? max_results - total : 0;
         int got = 0;
-        const int rc = push_core(m, raw + sec_off[k], m->max_push, sec_len[k], results ? results + (total < max_results ? total : max_results) : nullptr, room, &got,
+        const int rc = push_core(m, raw + sec_off[k] * es, m->max_push, sec_len[k], results ? results + (total < max_results ? total : max_results) : nullptr, room, &got,
                                  bytes_out ? bytes_out + (size_t)(total < max_results ? total : max_results) * bytes_stride : nullptr, bytes_stride, results_mem);
         if (rc != AMB_OK && rc != AMB_E_OVERFLOW) return rc;
         if (rc == AMB_E_OVERFLOW) rc_all = AMB_E_OVERFLOW;
@@ -1067,6 +1075,16 @@ int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_ne
     }
     *n_results = total;
     return rc_all;
+}
+
+int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                    int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
+    return stream_push_any(m, x, 4, x_stride, n_new, mem, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
+}
+
+int amb_stream_push_pcm16(amb_modem* m, const int16_t* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                          int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem) {
+    return stream_push_any(m, x, 2, x_stride, n_new, mem, results, max_results, n_results, bytes_out, bytes_stride, results_mem);
 }
 
 // ---------------------------------------------------------------------------------------------- transmit side

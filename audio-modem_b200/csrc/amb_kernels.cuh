@@ -122,7 +122,7 @@ struct AmbScanStore {
 // The samples are read once and cleaned is written once.
 // ================================================================================================
 struct AmbFrontArgs {
-    const float* x; int64_t x_stride;                 // rows of this push
+    const void* x; int64_t x_stride;                  // rows of this push (float32, or 16-bit PCM: sample = s / 32768), stride in samples
     float* cleaned; int64_t stride, off0;             // arena; the push starts at arena index off0
     int tiles, span, spans, warm;                     // tiles in the push, tiles per CTA, CTAs per stream, warm-up tiles
     const AmbEmaTables* E; const AmbStreamState* states; double* dc_next;
@@ -167,6 +167,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // hold q, a and the warp-inclusive scans of q and t, from which any block-wide prefix is one addition away.  The next
 // tile's input (16 KB) is staged global -> shared by one TMA bulk copy (cp.async.bulk, completion on an mbarrier) while
 // the current one is processed.  Three barriers per tile.
+template <typename IN>
 __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* R = reinterpret_cast<float*>(smem_raw);                     // [2][AMB_FR_BUF]
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     const AmbEmaTables* E = a.E;
     const double alpha = E->alpha, beta = E->beta, a512 = E->a512;
     const double lp = E->lanepow[lane];
-    const float* xrow = a.x + (int64_t)s * a.x_stride;
+    const IN* xrow = reinterpret_cast<const IN*>(a.x) + (int64_t)s * a.x_stride;
+    const unsigned tile_bytes = AMB_TILE * sizeof(IN);
     float* crow = a.cleaned + (int64_t)s * a.stride + a.off0;
     const int tb = t0 - a.warm > 0 ? t0 - a.warm : 0;
     // The EMA runs on u = m / beta (u <- alpha u + x: one FMA per sample instead of a multiplication and an FMA), and
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     // stage the first tile's input
     if (tid == 0) { mbar_init(&xs_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     __syncthreads();
-    if (tid == 0) { mbar_expect_tx(&xs_bar, AMB_TILE * 4); bulk_g2s(XS, xrow + (int64_t)tb * AMB_TILE, AMB_TILE * 4, &xs_bar); }
+    if (tid == 0) { mbar_expect_tx(&xs_bar, tile_bytes); bulk_g2s(XS, xrow + (int64_t)tb * AMB_TILE, tile_bytes, &xs_bar); }
     unsigned xs_phase = 0;
     int n = 0;                                                          // full tiles done: the current one uses buffer n & 1
     for (int t = tb; t < t1; t++) {
@@ -227,10 +229,23 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         float x[16];
         mbar_wait(&xs_bar, xs_phase);
         xs_phase ^= 1u;
-        {
+        if (sizeof(IN) == 4) {
             const float4* src = reinterpret_cast<const float4*>(XS + 16 * tid);
 #pragma unroll
             for (int q4 = 0; q4 < 4; q4++) { const float4 v = src[q4]; x[4 * q4] = v.x; x[4 * q4 + 1] = v.y; x[4 * q4 + 2] = v.z; x[4 * q4 + 3] = v.w; }
+        } else {
+            // 16-bit PCM: s / 32768 is exact in float32 (what an audio front end hands the reference for a 16-bit capture)
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(XS) + 16 * tid);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint4 v = src[h];
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    x[8 * h + 2 * k] = (float)(int16_t)(w[k] & 0xFFFFu) * (1.f / 32768.f);
+                    x[8 * h + 2 * k + 1] = (float)(int16_t)(w[k] >> 16) * (1.f / 32768.f);
+                }
+            }
         }
         // ---- EMA over the tile: response of the 16 samples from a zero state (two independent chains of 8) ...
         double r1 = 0.0, r2 = 0.0;
@@ -244,8 +259,8 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         __syncthreads();                                                // (1) warp totals; every thread has read its staged input
         if (t + 1 < t1 && tid == 0) {
             fence_proxy_async();                                        // the threads' reads of XS are ordered before the bulk write
-            mbar_expect_tx(&xs_bar, AMB_TILE * 4);
-            bulk_g2s(XS, xrow + (int64_t)(t + 1) * AMB_TILE, AMB_TILE * 4, &xs_bar);
+            mbar_expect_tx(&xs_bar, tile_bytes);
+            bulk_g2s(XS, xrow + (int64_t)(t + 1) * AMB_TILE, tile_bytes, &xs_bar);
         }
         double S = m_tile, m_next = m_tile;
 #pragma unroll

@@ -365,18 +365,28 @@ class Modem:
         return p.value, s.value
 
     def stream_push(self, x=None, n_new=None, raw=False, collect=True, device_results=None):
-        """x: [n_streams][n_new] float32 (numpy = host, torch.cuda tensor = device, None = already written in place).
+        """x: [n_streams][n_new] float32, or int16 for 16-bit PCM (numpy = host, torch.cuda tensor = device, None = already
+        written in place).
         device_results: optional (results, bytes) torch.cuda uint8 tensors ([max_results * sizeof(amb_frame_result)] and
         [max_results][bytes_stride]) that receive the frames on the device instead of the host buffers; returns the count."""
         if not self._stream_open:
             raise AmbError("stream not open")
+        push = self._L.amb_stream_push
         if x is None:
             mem, ptr, xs = MEM_INPLACE, None, 0
         elif _is_torch(x):
-            assert x.is_cuda and x.dtype.is_floating_point and x.element_size() == 4 and x.dim() == 2 and x.stride(1) == 1
+            assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+            if x.element_size() == 2 and not x.dtype.is_floating_point:
+                push = self._L.amb_stream_push_pcm16          # torch.int16: 16-bit PCM, sample = s / 32768
+            else:
+                assert x.dtype.is_floating_point and x.element_size() == 4
             mem, ptr, xs, n_new = MEM_DEVICE, _ptr(x), x.stride(0), x.shape[1]
         else:
-            x = np.ascontiguousarray(x, dtype=np.float32)
+            if isinstance(x, np.ndarray) and x.dtype == np.int16:
+                x = np.ascontiguousarray(x)
+                push = self._L.amb_stream_push_pcm16
+            else:
+                x = np.ascontiguousarray(x, dtype=np.float32)
             if x.ndim == 1:
                 x = x[None, :]
             mem, ptr, xs, n_new = MEM_HOST, _ptr(x), x.shape[1], x.shape[1]
@@ -385,12 +395,12 @@ class Modem:
             dres, dbytes = device_results
             assert dres.is_cuda and dbytes.is_cuda and dbytes.stride(0) == self.bytes_stride
             cap = min(dres.numel() // C.sizeof(FrameResult), dbytes.shape[0])
-            rc = self._L.amb_stream_push(self._h, ptr, xs, n_new, mem, _ptr(dres), cap, C.byref(n), _ptr(dbytes), self.bytes_stride, MEM_DEVICE)
+            rc = push(self._h, ptr, xs, n_new, mem, _ptr(dres), cap, C.byref(n), _ptr(dbytes), self.bytes_stride, MEM_DEVICE)
             self._ck(rc, allow_overflow=True)
             self.last_push_frames = n.value
             return n.value
-        rc = self._L.amb_stream_push(self._h, ptr, xs, n_new, mem, C.cast(self._res, C.c_void_p), self.max_results, C.byref(n),
-                                     _ptr(self._dec), self.bytes_stride, MEM_HOST)
+        rc = push(self._h, ptr, xs, n_new, mem, C.cast(self._res, C.c_void_p), self.max_results, C.byref(n),
+                  _ptr(self._dec), self.bytes_stride, MEM_HOST)
         self._ck(rc, allow_overflow=True)
         self.last_push_frames = n.value
         if not collect:

@@ -308,13 +308,40 @@ def run_b200(args, rank, world, local_rank):
     m.synchronize()
     e2e_s = time.perf_counter() - t0
     assert e2e_frames == args.e2e_steps * F, e2e_frames
+    # wire-format ingest (reported apart: 2 B per sample changes the byte count): the same samples as signed
+    # 16-bit PCM through amb_stream_push_pcm16, device-resident and end to end
+    pcm_dev = (segs[0] * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+    for w in range(2):
+        assert m.stream_push(pcm_dev, device_results=dres) == F
+    m.synchronize()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pcm_steps = min(args.steps, 6)
+    q0.record(ext)
+    for k in range(pcm_steps):
+        m.stream_push(pcm_dev, device_results=dres)
+    q1.record(ext)
+    m.synchronize()
+    pcm_ms = q0.elapsed_time(q1) / pcm_steps
+    host16 = amb.modem.pinned_empty((1, step_samples), np.int16)
+    hp = host16.array
+    hp[...] = pcm_dev.cpu().numpy()
+    m.stream_push(hp, collect=False)
+    m.synchronize()
+    t0 = time.perf_counter()
+    pcm_frames = 0
+    for k in range(args.e2e_steps):
+        pcm_frames += m.stream_push(hp, collect=False)
+    m.synchronize()
+    pcm_e2e_s = time.perf_counter() - t0
+    assert pcm_frames == args.e2e_steps * F, pcm_frames
     clocks.mark_end()
     clk = clocks.stop()
-    clk["window"] = "warm-up + timed steps + profiling pass + end-to-end leg (the same workload throughout)"
+    clk["window"] = "warm-up + timed steps + profiling pass + end-to-end legs (the same workload throughout)"
     d2h = F * (m.bytes_stride + 88)
     m.stream_close()
-    del hx
+    del hx, hp
     host.free()
+    host16.free()
 
     # aggregate over ranks
     total_ms = amb.shard.max_over_ranks(dev_ms, device=dev) if dist else dev_ms
@@ -324,6 +351,12 @@ def run_b200(args, rank, world, local_rank):
     tot = amb.shard.gather_counters(counters, device=dev) if dist else counters
     value = tot["samples"] / (total_ms / 1e3) / 1e6
     e2e_value = world * args.e2e_steps * step_samples / e2e_s_max / 1e6
+    pcm_ms_max = amb.shard.max_over_ranks(pcm_ms, device=dev) if dist else pcm_ms
+    pcm_e2e_s_max = amb.shard.max_over_ranks(pcm_e2e_s, device=dev) if dist else pcm_e2e_s
+    pcm16 = {"input": "signed 16-bit PCM, sample = s / 32768 (amb_stream_push_pcm16); same frames as the float32 legs",
+             "value": world * step_samples / (pcm_ms_max / 1e3) / 1e6, "ms_per_step": pcm_ms_max, "unit": UNIT,
+             "e2e": {"value": world * args.e2e_steps * step_samples / pcm_e2e_s_max / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * step_samples,
+                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps}}
 
     # roofline of the dominant kernel (largest share of the timed region on this rank)
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
@@ -356,7 +389,7 @@ def run_b200(args, rank, world, local_rank):
             "data": "synthetic", "payload_mb_per_s": tot["payloadBytes"] / (total_ms / 1e3) / 1e6,
             "config": config_dict(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * step_samples, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
-            "gpu_launches": tot["launches"], "roofline": roof,
+            "gpu_launches": tot["launches"], "roofline": roof, "pcm16": pcm16,
             "walker": slots, "check": {"frames_per_step_found": frames_found // args.steps, "crc_valid_frames": tot["crcValidFrames"], "crc_errors": crc_bad}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, pmb, cores, sample, _ = cpu_leg(steps=1000, warmup=1, frames_per_thread=64, budget_s=args.cpu_seconds)

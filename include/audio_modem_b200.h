@@ -212,6 +212,12 @@ int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride);
  * these samples come back in stream-major, time order; bytes_out row j belongs to results[j]. */
 int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
                     int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem);
+/* Wire-format ingest: the same push with signed 16-bit PCM samples; sample value = s / 32768 (exact in
+ * float32), i.e. the results are those of amb_stream_push on the float32 array an audio front end would hand the
+ * reference for a 16-bit capture.  Half the bytes per sample over PCIe and out of HBM.  mem = AMB_MEM_HOST or
+ * AMB_MEM_DEVICE. */
+int amb_stream_push_pcm16(amb_modem* m, const int16_t* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
+                          int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem);
 /* per-stream counters (stream = -1: sum over streams): framesDecoded, frameErrors (app.js:738-739),
  * falsePositives (app.js:879-884), receivedCount, crcErrors (app.js:604-605, ChunkAssembler's bitmap semantics of
  * app.js:628-643 without the chunk store), duplicates (chunks whose bit was already set), metaReceived, samplesWritten */

@@ -152,3 +152,55 @@ def test_sectioned_host_push_equals_one_push(O, amb):
     env = dict(os.environ, AMB_SECTION_MIN_BYTES="65536")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "sections ok" in out.stdout, out.stdout + out.stderr
+
+
+def _quantise(x):
+    """float samples -> 16-bit PCM and the float32 array an audio front end makes of it (s / 32768, exact)"""
+    pcm = np.clip(np.rint(np.asarray(x, np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    return pcm, (pcm.astype(np.float32) / np.float32(32768.0))
+
+
+@pytest.mark.parametrize("mode", ["16-QAM", "BPSK-REPEAT"])
+def test_pcm16_push_equals_float_push(O, amb, mode):
+    """wire-format ingest: 16-bit PCM pushed from host memory, from device memory and in several pushes gives
+    the oracle's events for the float32 samples s / 32768"""
+    import torch
+
+    cfg, mod, rep, _ = MODES[mode]
+    xs = []
+    for s in range(3):
+        x, _ = make_stream(O, mode, 6, 40 + s, lead=1000 * s + 17)
+        xs.append(x)
+    n = max(len(x) for x in xs)
+    pcm = np.zeros((3, n), np.int16)
+    flt = np.zeros((3, n), np.float32)
+    for s, x in enumerate(xs):
+        pcm[s, : len(x)], flt[s, : len(x)] = _quantise(x)
+    want = [O.StreamingReceiver(cfg, mod, rep).push(flt[s], 4096, raw=True) for s in range(3)]
+    assert all(len(w) >= 5 for w in want)
+    blocks = n // 4096
+    splits = [blocks // 3 * 4096, (blocks - blocks // 3) * 4096]
+    for where in ("host", "device", "device_unaligned"):
+        m = amb.Modem(cfg, mod, rep, device=0)
+        try:
+            m.stream_open(3, 4096, max(splits))
+            got = [[] for _ in range(3)]
+            off = 0
+            for p in splits:
+                blk = np.ascontiguousarray(pcm[:, off:off + p])
+                if where == "device":
+                    blk = torch.from_numpy(blk).cuda()
+                elif where == "device_unaligned":
+                    t = torch.zeros((3, p + 3), dtype=torch.int16, device="cuda")
+                    t[:, 3:] = torch.from_numpy(blk).cuda()
+                    blk = t[:, 3:]
+                for r, b in m.stream_push(blk, raw=True):
+                    got[r.stream].append((r, b))
+                off += p
+            for s in range(3):
+                assert len(got[s]) == len(want[s]), (where, s, len(got[s]))
+                for (r1, b1), (r2, b2) in zip(want[s], got[s]):
+                    assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (where, s, r1.preamble_idx)
+            assert m.stream_counters()["samplesWritten"] == 3 * n
+        finally:
+            m.close()
