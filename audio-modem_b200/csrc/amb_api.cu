@@ -186,13 +186,19 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
             int best_cost = 1 << 30;
             for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
         }
-        if (T.mod == AMB_MOD_QAM16) {
-            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_QAM16><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
-        } else if (T.mod == AMB_MOD_QPSK) {
-            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_QPSK><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+        // instantiated per constellation and per CTA size class (7 warps or fewer leave registers for a fourth resident CTA)
+#define AMB_DEMOD_LAUNCH(MODV, NTV) \
+    LAUNCH("k_demod_fast", (k_demod_fast<MODV, NTV><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks)))
+        if (nw <= 7) {
+            if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, 224); }
+            else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, 224); }
+            else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, 224); }
         } else {
-            LAUNCH("k_demod_fast", k_demod_fast<AMB_MOD_BPSK><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks));
+            if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, 256); }
+            else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, 256); }
+            else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, 256); }
         }
+#undef AMB_DEMOD_LAUNCH
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
@@ -307,6 +313,17 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
             ft.tw256[k] = make_float2((float)std::cos(-2.0 * M_PI * k / 256.0), (float)std::sin(-2.0 * M_PI * k / 256.0));
             ft.tw512[k] = make_float2((float)std::cos(-2.0 * M_PI * k / 512.0), (float)std::sin(-2.0 * M_PI * k / 512.0));
         }
+        {
+            const AmbTables& T = m->tables;
+            for (int i = 0; i < AMB_FD_MAXBINS; i++) ft.role[i] = -1000;
+            for (int q = 0; q < AMB_MAX_PILOTS; q++) {
+                const int k = q < T.n_pilots ? T.pilots[q] : -1;
+                const bool inb = k >= T.sub_start && k <= T.sub_end;
+                ft.pilot_kk[q] = inb ? k - T.sub_start : -1;
+                if (inb) ft.role[k - T.sub_start] = -1 - q;
+            }
+            for (int di = 0; di < T.n_data; di++) ft.role[T.data_k[di] - T.sub_start] = di;
+        }
         if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 8) != cudaSuccess) return bail(AMB_E_NOMEM);
         if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
         std::vector<uint32_t> ops((size_t)AMB_CRC_MAXL * AMB_CRC_OPS, 0u);
@@ -319,9 +336,12 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
     }
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_front<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);

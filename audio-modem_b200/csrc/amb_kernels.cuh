@@ -698,16 +698,26 @@ __global__ void __launch_bounds__(256) k_demod(const AmbTables* __restrict__ T, 
 // Phase 2 (flagged symbols only): the float64-faithful channel estimate and symbol routine (amb_device.cuh), so the
 // emitted indices are the reference's in every case.  Clean 16-QAM frames at 25 dB never reach phase 2; garbage does.
 // ------------------------------------------------------------------------------------------------
-struct AmbFastTables { float2 tw256[256]; float2 tw512[256]; };     // exp(-2 pi i k / 256), exp(-2 pi i k / 512)
+#define AMB_FD_MAXBINS 224
+struct AmbFastTables {
+    float2 tw256[256]; float2 tw512[256];      // exp(-2 pi i k / 256), exp(-2 pi i k / 512)
+    int role[AMB_FD_MAXBINS];                  // per band bin (relative to SUB_START): data index, or -1 - q for pilot q
+    int pilot_kk[AMB_MAX_PILOTS];              // band bin of pilot q, -1 outside the band
+};
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex float32 arithmetic on the packed two-lane FP32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue slot
+// per complex add, two per complex multiply; the operand swizzle, per-lane negate and scalar broadcast are free modifiers).
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {      // a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+    return __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), b));
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 
 // forward 4-point transform, outputs in natural order
 __device__ __forceinline__ void fft4f(float2& a, float2& b, float2& c, float2& d) {
     const float2 t0 = caddf(a, c), t1 = csubf(a, c), t2 = caddf(b, d);
-    const float2 t3 = make_float2(b.y - d.y, -(b.x - d.x));        // (b - d) * (-i)
+    const float2 u = csubf(b, d);
+    const float2 t3 = make_float2(u.y, -u.x);                      // (b - d) * (-i)
     a = caddf(t0, t2); b = caddf(t1, t3); c = csubf(t0, t2); d = csubf(t1, t3);
 }
 
@@ -734,11 +744,10 @@ __device__ __forceinline__ void fft16f(float2* v) {
 #define AMB_FD_HW 16                                    // half-warps (symbols in flight) per CTA
 #define AMB_FD_TSTRIDE 17                               // padded row of the 16x16 transpose
 #define AMB_FD_HWBUF (16 * AMB_FD_TSTRIDE)              // float2 per half-warp
-#define AMB_FD_MAXBINS 224
 #define AMB_FD_ITERS (AMB_FD_MAXBINS / 16)              // 14
 #define AMB_FD_FB_WARPS 4                               // warps that run the float64-faithful fallback
 #define AMB_FD_CPV 4                                    // cyclic-prefix samples per lane loaded ahead of the transform
-#define AMB_FD_SMEM_FAST (AMB_FD_HW * AMB_FD_HWBUF * 8 + 2 * 256 * 8 + AMB_FD_MAXBINS * (8 + 4 + 4 + 4))
+#define AMB_FD_SMEM_FAST (AMB_FD_HW * AMB_FD_HWBUF * 8 + 256 * 8 + AMB_FD_MAXBINS * (8 + 8 + 4 + 4))
 #define AMB_FD_SMEM_FB (4 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS * 8)
 #define AMB_DEMOD_FAST_SMEM ((AMB_FD_SMEM_FAST > AMB_FD_SMEM_FB ? AMB_FD_SMEM_FAST : AMB_FD_SMEM_FB) + 64)
 
@@ -803,30 +812,28 @@ __device__ __forceinline__ float fd_spectrum(const AmbJob& J, int64_t p0, bool i
 }
 
 // bin k of the real signal's spectrum from the packed transform (k in 1..255)
-__device__ __forceinline__ float2 fd_split(const float2* buf, const float2* __restrict__ tw512, int k) {
-    const float2 zk = buf[k], zn = buf[256 - k], w = tw512[k];
+__device__ __forceinline__ float2 fd_split(const float2* buf, const float2 w /* W512^k */, int k) {
+    const float2 zk = buf[k], zn = buf[256 - k];
     const float2 ze = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
     const float2 zo = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));      // (Z[k] - conj(Z[256-k])) / (2i)
     return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
 }
 
-template <int MOD>
-__global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
+template <int MOD, int NT>
+__global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
                                                      int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- fast layout
     float2* hwbuf = reinterpret_cast<float2*>(smem_raw);                         // [16][AMB_FD_HWBUF]
     float2* tw256 = hwbuf + AMB_FD_HW * AMB_FD_HWBUF;                            // [256]
-    float2* tw512 = tw256 + 256;                                                 // [256]
-    float2* Gq = tw512 + 256;                                                    // [bins] conj(H)/|H|^2 (raw scale)
-    float* invH = reinterpret_cast<float*>(Gq + AMB_FD_MAXBINS);                 // [bins] 1/|H|
-    float* dH = invH + AMB_FD_MAXBINS;                                           // [bins] bound on |dH|/|H|
-    float* cH = invH;                                                            // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
-    int* role = reinterpret_cast<int*>(dH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 pilot
+    float2* Gq = tw256 + 256;                                                    // [bins] 0.5 conj(H)/|H|^2 (raw scale)
+    float2* WG = Gq + AMB_FD_MAXBINS;                                            // [bins] 0.5 W512^k conj(H)/|H|^2
+    float* cH = reinterpret_cast<float*>(WG + AMB_FD_MAXBINS);                   // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
+    int* role = reinterpret_cast<int*>(cH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 - q for pilot q
     __shared__ float s_red[8];
     __shared__ float2 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
     __shared__ int pilot_kk[AMB_MAX_PILOTS];                                     // bin (relative to sub_start) of pilot q, -1 outside the band
-    __shared__ float s_mx, s_minhm;
+    __shared__ float s_mx, s_minhm, s_Sce;
     __shared__ unsigned s_mask[2];
     __shared__ int s_all;
     const int j = blockIdx.x;
@@ -839,21 +846,16 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
     const int nthr = blockDim.x, nhw = nthr >> 4, nwarps = nthr >> 5;      // 5..8 warps: the launch picks the count that wastes the fewest symbol slots
-    for (int i = tid; i < 256; i += nthr) { tw256[i] = FT->tw256[i]; tw512[i] = FT->tw512[i]; }
-    // role[kk]: data index of the bin, or -1 - q for pilot q
-    if (tid < AMB_MAX_PILOTS) {
-        const int k = tid < T->n_pilots ? T->pilots[tid] : -1;
-        const bool inb = k >= T->sub_start && k <= T->sub_end;
-        pilot_kk[tid] = inb ? k - sub_start : -1;
-        if (inb) role[k - sub_start] = -1 - tid;
-    }
+    for (int i = tid; i < 256; i += nthr) tw256[i] = FT->tw256[i];
+    for (int i = tid; i < nb; i += nthr) role[i] = FT->role[i];
+    if (tid < AMB_MAX_PILOTS) pilot_kk[tid] = FT->pilot_kk[tid];
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
-    for (int di = tid; di < n_data; di += nthr) role[T->data_k[di] - sub_start] = di;
     __syncthreads();
     float my_mx = 0.f;
     // ---- channel from the CE symbol (warp 0: both half-warps transform it, the lower one keeps the result; the warp-wide
     //      shuffles and barriers inside need all 32 lanes); the other warps gather the peak over preamble-1, preamble-2 and
-    //      the CE prefix
+    //      the CE prefix.  The equaliser tables fold the real-FFT split in: with A = Z[k] + conj(Z[256-k]) and
+    //      B = -i (Z[k] - conj(Z[256-k])), Y[k] = (A + W512^k B) / 2, so Y conj(H)/|H|^2 = A Gq + B WG.
     if (warp == 0) {
         const int64_t p0 = J.ce_pos + cp;
         const bool inside = p0 >= J.lo && p0 + AMB_FFT <= J.hi;
@@ -862,23 +864,25 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         float mn = 3.0e38f;
         for (int kk = l; kk < nb; kk += 16) {
             const int k = sub_start + kk;
-            const float2 y = fd_split(hwbuf + hw * AMB_FD_HWBUF, tw512, k);
+            const float2 w = FT->tw512[k];
+            const float2 y = fd_split(hwbuf + hw * AMB_FD_HWBUF, w, k);
             const float xr = (float)T->known_re[k];
             const float d = xr * xr;
             float hr = 0.f, hi = 0.f;
-            if (d > 1e-10f) { hr = y.x * xr / d; hi = y.y * xr / d; }
+            if (d > 1e-10f) { const float q = __fdividef(xr, d); hr = y.x * q; hi = y.y * q; }
             const float hm = hr * hr + hi * hi;
             mn = fminf(mn, hm);
-            const float ih = rsqrtf(hm);
             if (hw == 0) {
-                Gq[kk] = make_float2(hr / hm, -hi / hm);
-                cH[kk] = 8e-5f * ih;
-                dH[kk] = 8e-5f * S * ih;
+                const float ihm = 0.5f * __frcp_rn(hm);
+                const float2 g = make_float2(hr * ihm, -hi * ihm);
+                Gq[kk] = g;
+                WG[kk] = cmulf(w, g);
+                cH[kk] = 8e-5f * rsqrtf(hm);
             }
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (lane == 0) s_minhm = mn;
+        if (lane == 0) { s_minhm = mn; s_Sce = S; }
     } else if (folded) {
         const int64_t a = J.pos, b = J.ce_pos + cp;                  // [frame start, CE body)
         for (int64_t g = a + (tid - 32); g < b; g += nthr - 32) {
@@ -893,6 +897,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
     float2* pe = s_pilot[hw];                                            // pilot bins of the symbol in flight
     const float thr = (float)T->qam_thr;
     const int n_pilots = T->n_pilots;
+    float Sce = 0.f;
     for (int s0 = g0; s0 < s_end; s0 += nhw) {
         const int sidx = s0 + hw;
         const bool active = sidx < s_end;                               // uniform per half-warp
@@ -914,6 +919,7 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         if (!(first_round && warp == 0)) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
         if (first_round) {
             __syncthreads();                                            // channel tables ready
+            Sce = s_Sce;
             if (warp == 0) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
         }
         if (folded) {
@@ -933,7 +939,11 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
             const int kk = l + 16 * i;
             E[i] = make_float2(0.f, 0.f);
             if (kk < nb) {
-                const float2 e = cmulf(fd_split(buf, tw512, sub_start + kk), Gq[kk]);
+                const int k = sub_start + kk;
+                const float2 zk = buf[k], zn = buf[256 - k], g = Gq[kk], w = WG[kk];
+                const float2 A = __ffma2_rn(zn, make_float2(1.f, -1.f), zk);          // Z[k] + conj(Z[256-k])
+                const float2 Br = __ffma2_rn(zk, make_float2(-1.f, 1.f), zn);         // (B.y, B.x), B = -i (Z[k] - conj(Z[256-k]))
+                const float2 e = caddf(cmulf(A, g), cmulf(make_float2(Br.y, Br.x), w));
                 E[i] = e;
                 const int rl = role[kk];
                 if (rl < 0) pe[-1 - rl] = e;
@@ -946,12 +956,13 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
         bool bad = false;
         if (l < n_pilots && pilot_kk[l] >= 0) {
             const float ex = pe[l].x, ey = pe[l].y;
-            const float dk = S * cH[pilot_kk[l]] + (fabsf(ex) + fabsf(ey)) * dH[pilot_kk[l]];          // bound on |e - exact|
+            const float dk = cH[pilot_kk[l]] * fmaf(fabsf(ex) + fabsf(ey), Sce, S);          // bound on |e - exact|
             const float ar = fabsf(ex);
             if (!(fabsf(ar - 1e-6f) > dk)) bad = true;                  // the |eqRe| > 1e-6 test could flip (also catches NaN)
             if (ar > 1e-6f) {
-                ph_sum = ey / ex; pc = 1;
-                ptol = dk * (1.f + fabsf(ey) / ar) / ar;                // d(eqIm/eqRe)
+                const float ir = __frcp_rn(ar);
+                ph_sum = __fdividef(ey, ex); pc = 1;
+                ptol = dk * (1.f + fabsf(ey) * ir) * ir;                // d(eqIm/eqRe)
             }
         }
 #pragma unroll
@@ -960,9 +971,11 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
             ptol += __shfl_xor_sync(0xffffffffu, ptol, o);
             pc += __shfl_xor_sync(0xffffffffu, pc, o);
         }
-        const float phase = pc > 0 ? ph_sum / (float)pc : 0.f;
-        const float dphase = pc > 0 ? ptol / (float)pc + 2e-6f * fabsf(phase) : 0.f;
+        const float ipc = pc > 0 ? __frcp_rn((float)pc) : 0.f;
+        const float phase = ph_sum * ipc;
+        const float dphase = pc > 0 ? ptol * ipc + 4e-6f * fabsf(phase) : 0.f;       // + the approximate divisions above
         const float ph1 = 1.f + fabsf(phase);
+        const float dph5 = dphase + 1e-5f;
         uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sx * n_data;
 #pragma unroll
         for (int i = 0; i < AMB_FD_ITERS; i++) {
@@ -970,18 +983,19 @@ __global__ void __launch_bounds__(256, 3) k_demod_fast(const AmbTables* __restri
             const int rl = kk < nb ? role[kk] : -1;
             if (rl >= 0) {
                 const float2 e = E[i];
-                const float cr = e.x + e.y * phase, ci = e.y - e.x * phase;
+                const float2 c2 = __ffma2_rn(make_float2(e.y, -e.x), make_float2(phase, phase), e);
+                const float cr = c2.x, ci = c2.y;                       // e.x + e.y phase, e.y - e.x phase
                 const float mag = fabsf(e.x) + fabsf(e.y);
-                const float tol = 1e-3f + (S * cH[kk] + mag * dH[kk]) * ph1 + mag * (dphase + 1e-5f);
+                // |d cr| <= |dY|/|H| (1 + |phase|) + |e| d(phase), |dY|/|H| <= cH (S + |e| S_ce)
+                const float tol = fmaf(cH[kk] * ph1, fmaf(mag, Sce, S), fmaf(mag, dph5, 1e-3f));
                 int idx;
                 float margin;
                 if (MOD == AMB_MOD_BPSK) { idx = cr > 0.f ? 0 : 1; margin = fabsf(cr); }
                 else if (MOD == AMB_MOD_QPSK) { idx = cr > 0.f ? (ci > 0.f ? 0 : 3) : (ci > 0.f ? 1 : 2); margin = fminf(fabsf(cr), fabsf(ci)); }
                 else {
+                    // Gray per axis (modem.js:118-128): column = (I >= 0) << 1 | (|I| <= thr), row likewise from Q; ties have margin 0
                     const float ar = fabsf(cr), ai = fabsf(ci);
-                    const int gc = cr < 0.f ? (ar > thr ? 0 : 1) : (ar > thr ? 3 : 2);
-                    const int gr = ci < 0.f ? (ai > thr ? 0 : 1) : (ai > thr ? 3 : 2);
-                    idx = (((gr ^ (gr >> 1))) << 2) | (gc ^ (gc >> 1));
+                    idx = (ci < 0.f ? 0 : 8) | (ai > thr ? 0 : 4) | (cr < 0.f ? 0 : 2) | (ar > thr ? 0 : 1);
                     margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
                 }
                 if (!(margin > tol)) bad = true;                        // also catches NaN
