@@ -43,6 +43,7 @@ EXPORTS = {
     "amb_synchronize": (C.c_int, [C.c_void_p]),
     "amb_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "amb_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "amb_debug_read": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "amb_debug_counter": (C.c_int64, [C.c_void_p, C.c_int]),
     "amb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "amb_host_free": (C.c_int, [C.c_void_p]),

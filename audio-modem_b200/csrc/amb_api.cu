@@ -410,6 +410,20 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
     return -1;
 }
 
+int64_t amb_debug_read(amb_modem* m, int which, void* out, int64_t cap_bytes) {
+    if (!m || !m->open || !out) return -1;
+    cudaStreamSynchronize(m->stream);
+    int n = 0;
+    cudaMemcpy(&n, m->slot_count.p, 4, cudaMemcpyDeviceToHost);
+    if (n > m->slot_cap) n = m->slot_cap;
+    const void* src = which == 0 ? m->slot_info.p : which == 1 ? m->tsum.p : nullptr;
+    if (!src) return -1;
+    int64_t bytes = (int64_t)n * 16;
+    if (bytes > cap_bytes) bytes = cap_bytes;
+    if (bytes > 0) cudaMemcpy(out, src, (size_t)bytes, cudaMemcpyDeviceToHost);
+    return n;
+}
+
 int amb_host_alloc(void** out, uint64_t bytes) {
     if (!out) return AMB_E_INVALID;
     *out = nullptr;
@@ -748,7 +762,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
-    cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMB_XC_SMEM(AMB_XC_MAXW + 768));
     m->run_cap = (int)(max_push / 512) + 2;
     CK(m->l_runs.ensure(ns * m->run_cap * sizeof(AmbRun))); CK(m->l_nruns.ensure(ns * 4)); CK(m->l_runoff.ensure(ns * 4));
     CK(m->l_nlinks.ensure(ns * 4)); CK(m->l_active.ensure(ns * 4)); CK(m->l_nactive.ensure(16));
@@ -880,8 +894,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
     {
         const int L = m->xc_w + T.sym_len;
-        const size_t smem = (size_t)L * 4 * 3 + 256 * 4 + (size_t)(L + 1) * 8 + 64;
-        int threads = ((m->xc_w + AMB_XC_PER - 1) / AMB_XC_PER + 31) / 32 * 32;
+        const size_t smem = AMB_XC_SMEM(L);
+        int threads = ((m->xc_w + 15) / 16 + 15) / 16 * 32;               // a warp takes 16 blocks of 16 offsets (8 per lane, by parity)
         if (threads > 256) threads = 256;
         const int grid = m->slot_cap < 148 * 16 ? m->slot_cap : 148 * 16;
         LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),

@@ -1900,98 +1900,142 @@ __global__ void __launch_bounds__(256) k_defect_scan(const double* __restrict__ 
 //   corr(o) = sum_{r<256} body[r] * w_r[o + cp + r],   w_r = u                      for r <  256 - cp
 //                                                      w_r = u2                     for r >= 256 - cp
 //   u[p] = s[p] + sign s[p + 256],   u2[p] = u[p] + sign s[p - 256].
-// Each thread carries 8 consecutive offsets in registers: per 4 taps two 128-bit shared loads feed 32 FMAs.
+// Each thread carries 8 offsets of one parity, o = 16 b + par + 2 q, and accumulates even and odd taps in the two lanes of a
+// packed FFMA2:  acc2[q] += (t'[2m], t'[2m+1]) * (X[2(q+m)], X[2(q+m)+1]),  X[i] = w[16 b + cp + i]  (aligned register pairs
+// straight from 128-bit shared loads).  Odd offsets use the taps shifted by one, t'[r] = t[r-1], so that their products line
+// up with the same pairs; the two taps this leaves out (the last u tap and tap 255) are added singly.  Per 32 taps: 8 + 8
+// 128-bit shared loads feed 128 FFMA2 (256 multiply-adds).  u and u2 are padded by 4 floats per 16 so that the 8 lanes of a
+// quarter-warp (80 bytes apart) hit distinct banks.  The samples of the CTA's next slot are copied global -> shared
+// (cp.async) while the current slot's offsets are computed.
 #define AMB_XC_MAXW (256 + 2 * 768)
 #define AMB_XC_PER 8
-__global__ void __launch_bounds__(256) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+#define AMB_XC_PADI(i) ((i) + (((i) >> 4) << 2))
+#define AMB_XC_SMEM(L) ((size_t)((L) + 2 * (AMB_XC_PADI(L) + 4) + 512) * 4 + (size_t)((L) + 1) * 8 + 64)
+__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                       const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count, int slot_cap,
                                                       float* __restrict__ xc, int xc_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_slots = min(*slot_count, slot_cap);
     const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
-    const int L = xc_w + plen;                                         // samples needed (multiple of 4 for every config)
+    const int L = xc_w + plen;                                         // samples needed (multiple of 16 for every config)
+    const int LP = AMB_XC_PADI(L) + 4;
     float* sg = reinterpret_cast<float*>(smem_raw);                    // [L]
-    float* u = sg + L;                                                 // [L]
-    float* u2 = u + L;                                                 // [L]
-    float* tp = u2 + L;                                                // [256] first half of the body
-    double* SQ = reinterpret_cast<double*>(tp + 256);                  // [L + 1] prefix of squares
-    __shared__ double tot[256];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    float* wu = sg + L;                                                // [LP] u, padded
+    float* wv = wu + LP;                                               // [LP] u2, padded
+    float* tp = wv + LP;                                               // [2][256] taps by offset parity: t[r], and t[r - 1] with the two single taps zeroed
+    double* SQ = reinterpret_cast<double*>(tp + 512);                  // [L + 1] prefix of squares
+    __shared__ double wtot[8];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const float sign = (float)T->pre1_sign;
-    const double tE = T->pre1_energy;
-    for (int i = tid; i < 256; i += nt) tp[i] = T->pre1[cp + i];
-    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-        if (!slot_info[slot * 4 + 2]) continue;
-        const int s = slot_info[slot * 4], tile = slot_info[slot * 4 + 1];
-        const int64_t tile_first = g.base_g + ((int64_t)tile << 8) - 511;  // global position of the tile's first window
-        const int64_t base = tile_first - R;
-        const float* src = cleaned + (int64_t)s * g.stride;
-        const int64_t lo = g.base_g > 0 ? g.base_g : 0;
-        __syncthreads();
-        for (int i = tid; i < L; i += nt) {
-            const int64_t p = base + i;
-            sg[i] = (p >= lo && p < g.avail_hi) ? src[p - g.base_g] : 0.f;
-        }
-        __syncthreads();
+    const float tEf = (float)T->pre1_energy;
+    const int split = 256 - cp;                                        // taps below use u, taps from here on use u2 (multiple of 32)
+    for (int i = tid; i < 256; i += nt) {
+        tp[i] = T->pre1[cp + i];
+        tp[256 + i] = (i == 0 || i == split) ? 0.f : T->pre1[cp + i - 1];
+    }
+    const float t_last_u = split > 0 ? T->pre1[cp + split - 1] : 0.f, t_last = T->pre1[cp + 255];
+    const int64_t lo = g.base_g > 0 ? g.base_g : 0;
+    int slot = blockIdx.x;
+    while (slot < n_slots && !slot_info[slot * 4 + 2]) slot += gridDim.x;
+    if (slot < n_slots) {
+        const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
+        const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
+        for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    while (slot < n_slots) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                                               // sg holds this slot's samples; the previous slot's readers of u, u2, SQ are done
         for (int i = tid; i < L; i += nt) {
             const float a = (i + 256 < L) ? sg[i] + sign * sg[i + 256] : sg[i];
-            u[i] = a;
-            u2[i] = i >= 256 ? a + sign * sg[i - 256] : a;
+            wu[AMB_XC_PADI(i)] = a;
+            wv[AMB_XC_PADI(i)] = i >= 256 ? a + sign * sg[i - 256] : a;
         }
-        // prefix of squares (float64): contiguous chunks per thread, then a serial pass over the chunk totals
+        // prefix of squares (float64): a contiguous chunk per thread, a scan over the chunk totals
         const int per = (L + nt - 1) / nt;
+        const int c0 = min(L, tid * per), c1 = min(L, (tid + 1) * per);
+        double ctot = 0.0;
+        for (int i = c0; i < c1; i++) ctot = fma((double)sg[i], (double)sg[i], ctot);
+        double inc = ctot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
         {
-            double acc = 0.0;
-            for (int i = tid * per; i < min(L, (tid + 1) * per); i++) { SQ[i] = acc; acc += (double)sg[i] * (double)sg[i]; }
-            tot[tid] = acc;
+            double off = inc - ctot;
+            for (int w = 0; w < warp; w++) off += wtot[w];
+            for (int i = c0; i < c1; i++) { SQ[i] = off; off = fma((double)sg[i], (double)sg[i], off); }
+            if (tid == nt - 1) SQ[L] = off;
         }
-        __syncthreads();
-        if (tid == 0) { double acc = 0.0; for (int t = 0; t < nt; t++) { const double v = tot[t]; tot[t] = acc; acc += v; } SQ[L] = acc; }
-        __syncthreads();
-        { const double o = tot[tid]; for (int i = tid * per; i < min(L, (tid + 1) * per); i++) SQ[i] += o; }
-        __syncthreads();
-        float* out = xc + (int64_t)slot * xc_w;
-        const int split = 256 - cp;                                    // taps below use u, taps from here on use u2 (multiple of 4)
+        __syncthreads();                                               // u, u2, SQ complete; sg is free
+        const int cur = slot;
+        slot += gridDim.x;
+        while (slot < n_slots && !slot_info[slot * 4 + 2]) slot += gridDim.x;
+        if (slot < n_slots) {
+            const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
+            const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
+            for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        float* out = xc + (int64_t)cur * xc_w;
         // a refine around candidate window w reads offsets w .. w + 2R: only the span of the tile's candidate windows (plus a
         // margin for candidates that exist only under the walker's defect) is computed, the rest is marked UNSURE
-        const int c_lo = slot_info[slot * 4 + 3] & 0xffff, c_hi = (slot_info[slot * 4 + 3] >> 16) & 0xffff;
-        const int o_lo = max(0, (c_lo - 16) & ~7), o_hi = min(xc_w, (c_hi + 2 * R + 1 + 16 + 7) & ~7);
+        const int c_lo = slot_info[cur * 4 + 3] & 0xffff, c_hi = (slot_info[cur * 4 + 3] >> 16) & 0xffff;
+        const int o_lo = max(0, (c_lo - 16) & ~15), o_hi = min(xc_w, (c_hi + 2 * R + 1 + 16 + 15) & ~15);
         for (int i = tid; i < xc_w; i += nt) if (i < o_lo || i >= o_hi) out[i] = AMB_XC_UNSURE;
-        for (int o0 = o_lo + tid * AMB_XC_PER; o0 < o_hi; o0 += nt * AMB_XC_PER) {
-            float acc[AMB_XC_PER];
+        const int par = (lane >> 4) & 1;
+        const float* tpar = tp + 256 * par;
+        for (int blk = (o_lo >> 4) + warp * 16 + (lane & 15); 16 * blk < o_hi; blk += nwarps * 16) {
+            float2 acc2[AMB_XC_PER];
 #pragma unroll
-            for (int q = 0; q < AMB_XC_PER; q++) acc[q] = 0.f;
+            for (int q = 0; q < AMB_XC_PER; q++) acc2[q] = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
-                const float* w = half == 0 ? u : u2;
+                const float* w = half == 0 ? wu : wv;
                 const int r0 = half == 0 ? 0 : split, r1 = half == 0 ? split : 256;
                 if (r0 >= r1) continue;
-                const float4* wp = reinterpret_cast<const float4*>(w + o0 + cp + r0);
-                float x[12];
-                { const float4 a = wp[0], b = wp[1]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w; }
-                for (int r = r0; r < r1; r += 4) {
-                    const float4 nx = wp[((r - r0) >> 2) + 2];
-                    x[8] = nx.x; x[9] = nx.y; x[10] = nx.z; x[11] = nx.w;
-                    const float4 t4 = *reinterpret_cast<const float4*>(tp + r);
-                    const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+                const int b0 = 16 * blk + cp + r0;                                      // multiple of 16
+                const float4* wp = reinterpret_cast<const float4*>(w + AMB_XC_PADI(b0));   // float4 j of the window: wp[j + (j >> 2)]
+                const float4* tq = reinterpret_cast<const float4*>(tpar + r0);
+                float2 X[16];                                                           // ring of pairs: X[j & 15] = (w[b0 + 2j], w[b0 + 2j + 1])
 #pragma unroll
-                    for (int jj = 0; jj < 4; jj++)
+                for (int j = 0; j < 4; j++) { const float4 v = wp[j + (j >> 2)]; X[2 * j] = make_float2(v.x, v.y); X[2 * j + 1] = make_float2(v.z, v.w); }
+                for (int c = 0; c < (r1 - r0) / 32; c++) {
+                    // 32 taps = 16 tap pairs m; pair m needs X[m .. m + 7]: the ring holds 16 pairs, refilled 2 pairs at a time
 #pragma unroll
-                        for (int q = 0; q < AMB_XC_PER; q++) acc[q] = fmaf(t[jj], x[q + jj], acc[q]);
+                    for (int mm = 0; mm < 16; mm += 2) {
+                        const int j = 8 * c + (mm >> 1) + 4;                             // next float4 of the window (2 pairs)
+                        const float4 v = wp[j + (j >> 2)];
+                        X[(mm + 8) & 15] = make_float2(v.x, v.y); X[(mm + 9) & 15] = make_float2(v.z, v.w);
+                        const float4 t4 = tq[8 * c + (mm >> 1)];
+                        const float2 ta = make_float2(t4.x, t4.y), tb = make_float2(t4.z, t4.w);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) x[q] = x[q + 4];
+                        for (int q = 0; q < AMB_XC_PER; q++) acc2[q] = __ffma2_rn(ta, X[(mm + q) & 15], acc2[q]);
+#pragma unroll
+                        for (int q = 0; q < AMB_XC_PER; q++) acc2[q] = __ffma2_rn(tb, X[(mm + 1 + q) & 15], acc2[q]);
+                    }
                 }
             }
+            // odd offsets: the two taps the shifted table leaves out, t[split - 1] on u and t[255] on u2
+            const float fu = par ? t_last_u : 0.f, fv = par ? t_last : 0.f;
+            const int bq = 16 * blk + cp;
 #pragma unroll
             for (int q = 0; q < AMB_XC_PER; q++) {
-                if (o0 + q >= xc_w) break;
-                const double se = SQ[o0 + q + plen] - SQ[o0 + q];
-                const double denom = sqrt(se * tE);
+                const int o = 16 * blk + par + 2 * q;
+                float corr = acc2[q].x + acc2[q].y;
+                corr = fmaf(fu, wu[AMB_XC_PADI(bq + 2 * q + split)], corr);
+                corr = fmaf(fv, wv[AMB_XC_PADI(bq + 2 * q + 256)], corr);
+                if (o >= xc_w || o >= o_hi) continue;
+                // metric = corr / sqrt(se tE) where that denominator clears 0.001 (squared: 1e-6), UNSURE within 2e-4 of it
+                const float d2 = (float)(SQ[o + plen] - SQ[o]) * tEf;
                 float v;
-                if (denom > 0.001 * (1.0 + 1e-4)) v = (float)((double)acc[q] / denom);
-                else if (denom < 0.001 * (1.0 - 1e-4)) v = AMB_XC_FAIL;
+                if (d2 > 1e-6f * (1.f + 2e-4f)) v = corr * rsqrtf(d2);
+                else if (d2 < 1e-6f * (1.f - 2e-4f)) v = AMB_XC_FAIL;
                 else v = AMB_XC_UNSURE;
-                out[o0 + q] = v;
+                out[o] = v;
             }
         }
     }

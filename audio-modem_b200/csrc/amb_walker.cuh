@@ -52,7 +52,7 @@ struct AmbWalkGeom {
     const double* tri;          // [slot][3][256]  P, Ra, Rb of the tile's 256 windows
     const float* xc;            // [slot][xc_w]    preamble-1 correlation metric (screening values) at tile_first - R + i
     int xc_w;
-    const int32_t* slot_info;   // [slot][4], entry 2 = the slot's tri / xc rows were computed (NULL: every row is valid or marked UNSURE)
+    const int32_t* slot_info;   // [slot][4], entry 2 = the slot's xc row was computed (NULL: every row is valid or marked UNSURE)
     const float* tsum;          // [slot][4]: exact extremes over the slot's 256 windows: max metric (no defect, rounded up), min Ra,
                                 // min Rb (rounded down); NULL = not available
     // Refine memo between the two phases of the link-parallel resolution: the refine (app.js:862-877) is a pure function
@@ -155,7 +155,7 @@ AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0
         int seg = (int)(tile_first + 256 - d);
         if (seg > cnt - done) seg = cnt - done;
         const int slot = amb_tile_slot_of(G, j);
-        if (slot >= 0 && G.tri && (!G.slot_info || G.slot_info[slot * 4 + 2])) {
+        if (slot >= 0 && G.tri) {                                                         // (k_tri_store writes the rows of every slot)
             const double* src = G.tri + (int64_t)slot * 768 + (d - tile_first);          // [slot][P | Ra | Rb][256]
             AMB_WARP_FOR(i, seg) { P[done + i] = src[i]; A[done + i] = src[256 + i]; B[done + i] = src[512 + i]; }
             AMB_WARP_SYNC();

@@ -165,6 +165,16 @@ class Modem:
         """0 launches, 1 fast-demod fallback symbols, 2 link iterations, 3 link passes"""
         return int(self._L.amb_debug_counter(self._h, which))
 
+    def debug_slots(self):
+        """development: (slot_info [n][4] int32, slot extremes [n][4] float32) of the last push"""
+        cap = 1 << 22
+        info = np.zeros((cap // 16, 4), np.int32)
+        ts = np.zeros((cap // 16, 4), np.float32)
+        n = int(self._L.amb_debug_read(self._h, 0, _ptr(info), cap))
+        self._L.amb_debug_read(self._h, 1, _ptr(ts), cap)
+        n = max(0, min(n, cap // 16))
+        return info[:n], ts[:n]
+
     def selftest(self, which=0, seed=1, n=100000):
         """device self-test (amb_selftest): returns (disagreements, commits)"""
         out = (C.c_int64 * 2)()

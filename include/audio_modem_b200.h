@@ -128,6 +128,9 @@ int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by t
 /* development counters: 0 kernel launches, 1 data symbols redone by the float64-faithful fallback of the fast
  * demodulator, 2 link-resolution iterations, 3 link-resolution passes */
 int64_t amb_debug_counter(amb_modem* m, int which);
+/* development: copies the last push's per-slot records to host memory (which = 0: {stream, arena tile, has-candidate,
+ * candidate span} int32 x 4; which = 1: {max metric, min Ra, min Rb, excluded} float x 4); returns the slot count */
+int64_t amb_debug_read(amb_modem* m, int which, void* out, int64_t cap_bytes);
 /* development self-tests that need the device's 32-lane execution: which = 0 runs n random batches of the streaming
  * scanner's candidate logic (app.js:806-838) through its warp-parallel form and through the reference-order loop;
  * out2[0] = disagreements (must be 0), out2[1] = batches that committed a preamble */
