@@ -64,6 +64,7 @@ struct amb_modem {
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
+    int walk_ctas = 148 * 4;          // CTAs of k_link_walk resident on the device
     bool push_pcm16 = false;          // input format of the push in progress
     int n_streams = 0;
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
@@ -342,6 +343,12 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
     cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+    {
+        int occ = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk, 128, 0) == cudaSuccess && occ > 0 &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+            m->walk_ctas = occ * sms;
+    }
     cudaFuncSetAttribute(k_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_front<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);
@@ -924,7 +931,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
     L.fp_sum = m->l_fpsum.as<unsigned long long>(); L.memo = m->l_memo.as<AmbRefineMemo>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
-    const int walk_grid = (int)(blocks_for(max_links, 4) < 148 * 8 ? blocks_for(max_links, 4) : 148 * 8);
+    // one resident wave: the walks differ in length, a second wave of CTAs would start behind the longest of the first
+    const int walk_grid = (int)(blocks_for(max_links, 4) < m->walk_ctas ? blocks_for(max_links, 4) : m->walk_ctas);
     const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);
     int* h = m->h_counts;           // pinned: [0] n_active, [1] total jobs, [2] max nsym, [3] kept, [4] n_redo
     for (int pass = 0; pass < 4096 && n_todo > 0; pass++) {
@@ -985,6 +993,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         uint8_t* pbytes = direct ? dst_bytes + (size_t)n_out * bytes_stride : m->s_bytes.as<uint8_t>();
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
+        LAUNCH("k_fine_exact", k_fine_exact<<<blocks_for(total, 4) < 148 * 16 ? blocks_for(total, 4) : 148 * 16, 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), total));
         if ((rc = run_demod_parse(m, total, h[2], true, pres, pbytes, bytes_stride))) return rc;
         {
             int64_t parts = ((int64_t)total / ns + 1023) / 1024;

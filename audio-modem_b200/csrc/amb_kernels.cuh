@@ -1602,6 +1602,40 @@ __global__ void k_jobs_stream(const AmbTables* __restrict__ T, AmbStreamGeom g, 
     if (J.nsym > 0) atomicMax(max_nsym, J.nsym);
 }
 
+// The exact refined metric of the frames whose walker left it out (amb_fine_xcorr_store / amb_resolve_fine): one warp per
+// frame.  The products s[i] t[i] and s[i]^2 are exact in float64 (24-bit factors), so they are formed by all lanes at once;
+// the two running sums keep the reference's order (modem.js:577-580), one lane each.
+__global__ void __launch_bounds__(128) k_fine_exact(const AmbTables* __restrict__ T, AmbJob* __restrict__ jobs, int n_jobs) {
+    __shared__ double prod[4][768], sq[4][768];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int plen = T->sym_len;
+    for (int j = blockIdx.x * 4 + warp; j < n_jobs; j += gridDim.x * 4) {
+        const double fine = jobs[j].fine;
+        if (!AMB_FINE_DEFERRED(fine)) continue;
+        const AmbJob J = jobs[j];
+        AmbSig sig;
+        sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+        for (int i = lane; i < plen; i += 32) {
+            const double v = (double)amb_sig(sig, J.pos + i);
+            prod[warp][i] = amb_mul(v, (double)T->pre1[i]);
+            sq[warp][i] = amb_mul(v, v);
+        }
+        __syncwarp();
+        double acc = 0.0;
+        if (lane < 2) {
+            const double* a = lane == 0 ? prod[warp] : sq[warp];
+#pragma unroll 8
+            for (int i = 0; i < plen; i++) acc = amb_add(acc, a[i]);
+        }
+        const double se = __shfl_sync(0xffffffffu, acc, 1);
+        if (lane == 0) {
+            const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
+            jobs[j].fine = denom > 0.001 ? amb_div(acc, denom) : -INFINITY;
+        }
+        __syncwarp();
+    }
+}
+
 // Copies the kept frames (results + decoded bytes) to consecutive output rows starting at out_base.
 __global__ void __launch_bounds__(128) k_gather(const int* __restrict__ keep, const int* __restrict__ keep_off, int n_jobs,
                                                  const amb_frame_result* __restrict__ res, const uint8_t* __restrict__ bytes, int64_t bytes_stride,
@@ -2157,7 +2191,7 @@ __device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n
 //   (k_chain_links applies it), so that phase A keeps reading an unchanging states[].
 // mode 1 (phase B): flat link index, start state = the stream's current state (link 0) or the phase-A end state of the
 //   previous chain run; the warp also decides whether its link reproduced the speculation (first_stop).
-__global__ void __launch_bounds__(128) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+__global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                     const float* __restrict__ sums, const AmbStreamState* __restrict__ states,
                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo, int n_streams,
                                                     int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {

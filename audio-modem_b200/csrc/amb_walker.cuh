@@ -112,7 +112,7 @@ AMB_HD int amb_tile_slot_of(const struct AmbWalkGeom& G, int64_t j);
 AMB_HD bool amb_tile_hot2(const struct AmbWalkGeom& G, const float* sums, int64_t jj, int64_t rel, double Ep, double Ea, double Eb);
 
 struct AmbWalkScratch {      // per-warp shared memory
-    double P[264], A[264], B[264], M[264];
+    double M[264], A[264], B[264];   // M: the window sums P on the way in (amb_eval_windows), the metrics once a batch is formed
     double x[64];
     int32_t hot[32];
     int32_t gate[264];
@@ -214,6 +214,14 @@ AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums,
     return skipped;
 }
 
+// A refined metric whose exact evaluation was deferred is carried as -1 - (screening value), i.e. inside (-4, -1).
+#define AMB_FINE_DEFERRED(x) ((x) < -1.0 && (x) > -4.0)
+AMB_HD double amb_resolve_fine(const AmbTables* T, const AmbSig& sig, int64_t pos, double fine) {
+    if (!AMB_FINE_DEFERRED(fine)) return fine;
+    double m;
+    return amb_xcorr_at(T, sig, pos, &m) ? m : -INFINITY;
+}
+
 // Refine with the scan kernel's float32 screening values: offsets whose screening metric is within 1e-3 of the
 // maximum are re-evaluated exactly (amb_xcorr_at), so the argmax and the reported metric are the reference's.
 // Falls back to the direct evaluation when the store does not cover [lo, hi] or cannot decide.
@@ -251,6 +259,14 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     }
     AMB_WARP_SYNC();
     if (cnt > 32) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+    if (cnt == 1 && mx > 0.102f) {
+        // a single offset within 1e-3 of the screening maximum is the reference's argmax, and its exact metric clears the 0.1
+        // test (the screening values are within 5e-4 of the exact ones).  Nothing else in the walk depends on the value, so
+        // its 2 x sym_len-step float64 summation is left to amb_resolve_fine, which runs one frame per lane afterwards.
+        *pos_out = (int64_t)scratch[32];
+        AMB_WARP_SYNC();
+        return -1.0 - (double)mx;
+    }
     AMB_WARP_FOR(i, cnt) {
         double m;
         scratch[i] = amb_xcorr_at(T, sig, (int64_t)scratch[32 + i], &m) ? m : -INFINITY;
@@ -376,9 +392,9 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             if (d - 1 >= 0 && rel >= 0 && rel < G.sum_tiles && (jj << 8) >= G.sum_lo) cold = !amb_tile_hot2(G, sums, jj, rel, st.Ep, st.Ea, st.Eb);
         }
         if (!cold) {
-            amb_eval_windows(G, sig, d - 1, 3, W->P, W->A, W->B);
+            amb_eval_windows(G, sig, d - 1, 3, W->M, W->A, W->B);
             double m;
-            if (amb_metric(W->P[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
+            if (amb_metric(W->M[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
         }
         if (d < scan_end) {
             // slide with the label d: removes T(d), adds T(d+256)  ->  W(d+1) + [T(d-1) - T(d+255)]
@@ -389,7 +405,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             st.lag = 0;
             if (best > 0.5) {
                 double cur;
-                if (amb_metric(W->P[2], W->A[2], W->B[2], st, &cur) && cur < best * 0.7) { amb_commit(st, best_pos, best, d + 1, 0); return; }
+                if (amb_metric(W->M[2], W->A[2], W->B[2], st, &cur) && cur < best * 0.7) { amb_commit(st, best_pos, best, d + 1, 0); return; }
             }
             d = d + 1;
         } else {
@@ -436,10 +452,10 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
         if (d_end > scan_end) d_end = scan_end;
         const int cnt = (int)(d_end - d + 1);
         const int look = d_end < scan_end ? 1 : 0;
-        amb_eval_windows(G, sig, d, cnt + look, W->P, W->A, W->B);
+        amb_eval_windows(G, sig, d, cnt + look, W->M, W->A, W->B);
         AMB_WARP_FOR(i, cnt + look) {
             double m;
-            W->gate[i] = amb_metric(W->P[i], W->A[i], W->B[i], st, &m);
+            W->gate[i] = amb_metric(W->M[i], W->A[i], W->B[i], st, &m);
             W->M[i] = m;
         }
         AMB_WARP_SYNC();
@@ -466,7 +482,7 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
     const AmbRefineMemo* mi = G.memo_in;
     if (mi && mi->valid && mi->coarse == st.pre_pos && mi->fs == fs && mi->fe == fe) { pos = mi->pos; best = mi->fine; }
     else best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos);
-    if (best < 0.1) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
+    if (best < 0.1 && !AMB_FINE_DEFERRED(best)) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
     if (G.memo_out && AMB_LEADER()) { AmbRefineMemo* mo = G.memo_out; mo->coarse = st.pre_pos; mo->fs = fs; mo->fe = fe; mo->pos = pos; mo->fine = best; mo->valid = 1; }
     st.pre_pos = pos; st.fine = best;
     const int64_t max_payload = st.meta_received ? (int64_t)(st.chunk_size ? st.chunk_size : 4096) + 11 : 280;

@@ -329,7 +329,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                     else nsym = (int)((R.len - 3 * (int64_t)T.sym_len) / T.sym_len);
                 }
                 decode_job(T, sig, R.pos, R.len, R.pos + 2 * T.sym_len, R.pos + 3 * T.sym_len, nsym, status, 0, true, R.pos, &fr[i]);
-                fr[i].res.coarse_metric = R.coarse; fr[i].res.fine_metric = R.fine;
+                fr[i].res.coarse_metric = R.coarse; fr[i].res.fine_metric = amb_resolve_fine(&T, sig, R.pos, R.fine);
                 rr[i] = fr[i].res;
             }
             std::vector<int> keep((size_t)cnt, 0);
