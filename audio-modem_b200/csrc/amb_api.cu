@@ -993,7 +993,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         uint8_t* pbytes = direct ? dst_bytes + (size_t)n_out * bytes_stride : m->s_bytes.as<uint8_t>();
         CK(m->keep.ensure((size_t)total * 4)); CK(m->keep_off.ensure((size_t)total * 4));
         CK(cudaMemsetAsync(m->keep.p, 0, (size_t)total * 4, m->stream));
-        LAUNCH("k_fine_exact", k_fine_exact<<<blocks_for(total, 4) < 148 * 16 ? blocks_for(total, 4) : 148 * 16, 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), total));
+        LAUNCH("k_fine_exact", k_fine_exact<<<blocks_for(total, 64), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), total));
         if ((rc = run_demod_parse(m, total, h[2], true, pres, pbytes, bytes_stride))) return rc;
         {
             int64_t parts = ((int64_t)total / ns + 1023) / 1024;

@@ -1602,35 +1602,67 @@ __global__ void k_jobs_stream(const AmbTables* __restrict__ T, AmbStreamGeom g, 
     if (J.nsym > 0) atomicMax(max_nsym, J.nsym);
 }
 
-// The exact refined metric of the frames whose walker left it out (amb_fine_xcorr_store / amb_resolve_fine): one warp per
-// frame.  The products s[i] t[i] and s[i]^2 are exact in float64 (24-bit factors), so they are formed by all lanes at once;
-// the two running sums keep the reference's order (modem.js:577-580), one lane each.
+// The exact refined metric of the frames whose walker left it out (amb_fine_xcorr_store / amb_resolve_fine).  A warp takes
+// 16 frames; lane 2 f + c runs chain c of frame f (c = 0: sum s[i] t[i], c = 1: sum s[i]^2) in the reference's order
+// (modem.js:577-580), so all 32 lanes carry a dependent float64 chain (a float64 instruction costs the same with one lane
+// active).  The products are exact in float64 (24-bit factors); they are formed 32 taps at a time from 16 coalesced loads
+// in flight at once and handed over through shared memory (rows padded to 33).
 __global__ void __launch_bounds__(128) k_fine_exact(const AmbTables* __restrict__ T, AmbJob* __restrict__ jobs, int n_jobs) {
-    __shared__ double prod[4][768], sq[4][768];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int plen = T->sym_len;
-    for (int j = blockIdx.x * 4 + warp; j < n_jobs; j += gridDim.x * 4) {
-        const double fine = jobs[j].fine;
-        if (!AMB_FINE_DEFERRED(fine)) continue;
-        const AmbJob J = jobs[j];
-        AmbSig sig;
-        sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
-        for (int i = lane; i < plen; i += 32) {
-            const double v = (double)amb_sig(sig, J.pos + i);
-            prod[warp][i] = amb_mul(v, (double)T->pre1[i]);
-            sq[warp][i] = amb_mul(v, v);
+    __shared__ double buf[4][32][33];
+    __shared__ const float* srcp[4][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, f = lane >> 1, c = lane & 1;
+    const int plen = T->sym_len;                                       // multiple of 32 for every config
+    for (int j0 = (blockIdx.x * 4 + warp) * 16; j0 < n_jobs; j0 += gridDim.x * 64) {
+        const int jm = j0 + f;
+        bool mine = false, whole = false;
+        AmbJob J;
+        if (jm < n_jobs && AMB_FINE_DEFERRED(jobs[jm].fine)) {
+            J = jobs[jm];
+            mine = true;
+            whole = J.pos >= J.lo && J.pos + plen <= J.hi;
         }
+        // frames that are not deferred (or not wholly readable) read the table instead: their chains are discarded
+        if (c == 0) srcp[warp][f] = (mine && whole) ? J.p + (J.pos - J.base) : T->pre1;
         __syncwarp();
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const float* sp[16];
+#pragma unroll
+        for (int ff = 0; ff < 16; ff++) sp[ff] = srcp[warp][ff] + lane;
         double acc = 0.0;
-        if (lane < 2) {
-            const double* a = lane == 0 ? prod[warp] : sq[warp];
-#pragma unroll 8
-            for (int i = 0; i < plen; i++) acc = amb_add(acc, a[i]);
+        float vv[16];
+#pragma unroll
+        for (int ff = 0; ff < 16; ff++) vv[ff] = sp[ff][0];
+        for (int c0 = 0; c0 < plen; c0 += 32) {
+            const double t = (double)T->pre1[c0 + lane];
+#pragma unroll
+            for (int ff = 0; ff < 16; ff++) {
+                const double v = (double)vv[ff];
+                buf[warp][2 * ff][lane] = amb_mul(v, t);
+                buf[warp][2 * ff + 1][lane] = amb_mul(v, v);
+            }
+            if (c0 + 32 < plen) {
+#pragma unroll
+                for (int ff = 0; ff < 16; ff++) vv[ff] = sp[ff][c0 + 32];          // next chunk's samples, in flight during the chains
+            }
+            __syncwarp();
+            const double* a = buf[warp][lane];
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc = amb_add(acc, a[i]);
+            __syncwarp();
         }
-        const double se = __shfl_sync(0xffffffffu, acc, 1);
-        if (lane == 0) {
-            const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
-            jobs[j].fine = denom > 0.001 ? amb_div(acc, denom) : -INFINITY;
+        const double se = __shfl_down_sync(0xffffffffu, acc, 1);
+        if (mine && c == 0) {
+            double fine;
+            if (whole) {
+                const double denom = amb_sqrt(amb_mul(se, T->pre1_energy));
+                fine = denom > 0.001 ? amb_div(acc, denom) : -INFINITY;
+            } else {
+                // the window leaves the readable range (cannot happen for a refined frame; kept for completeness)
+                AmbSig sig;
+                sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
+                fine = amb_resolve_fine(T, sig, J.pos, J.fine);
+            }
+            jobs[jm].fine = fine;
         }
         __syncwarp();
     }
