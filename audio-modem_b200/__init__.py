@@ -7,7 +7,7 @@ GPUs).  Import as `audio_modem_b200` (see the shim at the repository root).
 from . import _build, _lib, shard  # noqa: F401
 from ._lib import AmbError, FrameResult  # noqa: F401
 from .modem import (  # noqa: F401
-    FRAME_DATA, FRAME_META, Modem, StreamingReceiver, analyzeLoopback, buildDataChunkFrame, buildMetadataFrame, crc32, decodeChunkFrame, decodeReceivedSignal, demodulateOFDM,
+    FRAME_DATA, FRAME_META, Modem, StreamingReceiver, analyzeLoopback, buildDataChunkFrame, buildTransmitSignal, generateTestSignal, buildMetadataFrame, crc32, decodeChunkFrame, decodeReceivedSignal, demodulateOFDM,
     detectPreamble, detectPreambleCrossCorr, estimateChannel, estimateFrameSamples, generateChannelEstSymbol,
     generatePreambleSymbol1, preprocessSignal, result_to_object, setDevice, setOFDMConfig,
 )

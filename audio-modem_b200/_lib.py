@@ -75,6 +75,8 @@ EXPORTS = {
     "amb_stream_counters": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "amb_stream_enable_assembly": (C.c_int, [C.c_void_p, C.c_int64]),
     "amb_stream_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
+    "amb_transmit_signal_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
+    "amb_build_transmit_signals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "amb_chunk_frame_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
     "amb_build_data_chunk_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int32, C.c_uint64, C.c_void_p,
                                               C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_int]),

@@ -1137,14 +1137,14 @@ int64_t amb_chunk_frame_samples(amb_modem* m, int64_t payload_bytes, int is_firs
 }
 
 static int tx_run(amb_modem* m, const uint8_t* d_pay, int64_t pay_stride, int pay_len, int n, int first, float* out, int64_t out_stride,
-                  double sigma, uint64_t seed, int64_t g0, int mem) {
-    const int64_t total = amb_tx_frame_samples(&m->tables, pay_len, first);
+                  double sigma, uint64_t seed, int64_t g0, int mem, int64_t pre = -1, int64_t post = -1) {
+    const int64_t total = pre >= 0 ? pre + (3 + amb_tx_num_symbols(&m->tables, pay_len)) * m->tables.sym_len + post : amb_tx_frame_samples(&m->tables, pay_len, first);
     if (out_stride < total) return fail(m, AMB_E_INVALID, "out_stride smaller than the frame");
     float* d_out = out;
     if (mem == AMB_MEM_HOST) { CK(m->tx_out.ensure((size_t)n * out_stride * 4)); d_out = m->tx_out.as<float>(); CK(cudaMemsetAsync(d_out, 0, (size_t)n * out_stride * 4, m->stream)); }
     AmbTxArgs a;
     a.payloads = d_pay; a.payload_stride = pay_stride; a.payload_len = pay_len; a.first = first; a.out = d_out; a.out_stride = out_stride;
-    a.noise_sigma = sigma; a.noise_seed = seed; a.noise_g0 = g0;
+    a.noise_sigma = sigma; a.noise_seed = seed; a.noise_g0 = g0; a.pre = pre; a.post = post;
     LAUNCH("k_tx_frames", k_tx_frames<<<n, 256, AMB_TX_SMEM, m->stream>>>(m->d_tables, a, n));
     if (mem == AMB_MEM_HOST) m->pending.push_back({out, d_out, (size_t)n * out_stride * 4});
     return AMB_OK;
@@ -1180,6 +1180,53 @@ int amb_build_metadata_frame(amb_modem* m, int32_t total_chunks, int32_t total_f
     const int64_t total = amb_tx_frame_samples(&m->tables, pay_len, 1);
     if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, 1, 1, out, total, noise_sigma, noise_seed, noise_g0, mem))) return rc;
     return flush(m);
+}
+
+// silences of buildTransmitSignal, modem.js:533-535 (`new Float32Array(44100 * x)` truncates)
+static void legacy_silences(const AmbTables& T, int64_t* pre, int64_t* post) {
+    const bool acoustic = T.cp_len >= 128;
+    *pre = (int64_t)std::floor(44100.0 * (acoustic ? 0.5 : 0.3));
+    *post = (int64_t)std::floor(44100.0 * (acoustic ? 0.5 : 0.2));
+}
+
+int64_t amb_transmit_signal_samples(amb_modem* m, int64_t data_len, int name_len) {
+    if (!m || data_len < 0) return -1;
+    if (name_len <= 0) name_len = 4;
+    if (name_len > 255) name_len = 255;
+    int64_t pre, post;
+    legacy_silences(m->tables, &pre, &post);
+    return pre + (3 + amb_tx_num_symbols(&m->tables, 1 + name_len + 4 + data_len + 4)) * m->tables.sym_len + post;
+}
+
+int amb_build_transmit_signals(amb_modem* m, const uint8_t* data, int64_t data_stride, int data_len, int n, const uint8_t* name,
+                               int name_len, float* out, int64_t out_stride, int mem) {
+    int rc = check_common(m, n, out_stride, mem); if (rc) return rc;
+    if (n == 0) return AMB_OK;
+    if (!out || !data || data_len < 0 || data_len > (1 << 24) || data_stride < data_len) return fail(m, AMB_E_INVALID, "bad argument");
+    static const uint8_t dflt[4] = {'f', 'i', 'l', 'e'};                 // `fileName || 'file'`
+    if (!name || name_len <= 0) { name = dflt; name_len = 4; }
+    if (name_len > 255) name_len = 255;                                  // Math.min(nameBytes.length, 255)
+    // packet [nameLen:1][name][dataLen:4][data][CRC-32:4] (modem.js:504-523), assembled on the host: the data arrives in
+    // host memory (the payloads are small next to the signal they turn into)
+    if (mem != AMB_MEM_HOST) return fail(m, AMB_E_INVALID, "data and out are host memory for this call");
+    const int pay_len = 1 + name_len + 4 + data_len + 4;
+    std::vector<uint8_t> pay((size_t)n * pay_len);
+    for (int i = 0; i < n; i++) {
+        uint8_t* p = pay.data() + (size_t)i * pay_len;
+        int off = 0;
+        p[off++] = (uint8_t)name_len;
+        std::memcpy(p + off, name, (size_t)name_len); off += name_len;
+        p[off++] = (uint8_t)(data_len >> 24); p[off++] = (uint8_t)(data_len >> 16); p[off++] = (uint8_t)(data_len >> 8); p[off++] = (uint8_t)data_len;
+        std::memcpy(p + off, data + (size_t)i * data_stride, (size_t)data_len); off += data_len;
+        const uint32_t cs = amb_crc32_bytes(m->tables.crc_table, p, off);
+        p[off++] = (uint8_t)(cs >> 24); p[off++] = (uint8_t)(cs >> 16); p[off++] = (uint8_t)(cs >> 8); p[off++] = (uint8_t)cs;
+    }
+    CK(m->tx_pay.ensure(pay.size()));
+    CK(cudaMemcpyAsync(m->tx_pay.p, pay.data(), pay.size(), cudaMemcpyHostToDevice, m->stream));
+    int64_t pre, post;
+    legacy_silences(m->tables, &pre, &post);
+    if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, n, 1, out, out_stride, 0.0, 0, 0, mem, pre, post))) return rc;
+    return flush(m);        // synchronises: `pay` stays alive until the copy has run
 }
 
 int amb_stream_enable_assembly(amb_modem* m, int64_t max_file_bytes) {

@@ -1867,6 +1867,7 @@ __global__ void k_tx_chunk_payloads(const AmbTables* __restrict__ T, const uint8
 struct AmbTxArgs {
     const uint8_t* payloads; int64_t payload_stride; int payload_len;
     int first;                 // 1: metadata-style lead-in silence (isFirstFrame)
+    int64_t pre, post;         // silences in samples; -1 = buildChunkOFDMFrame's (by `first`)
     float* out; int64_t out_stride;
     double noise_sigma; uint64_t noise_seed; int64_t noise_g0;
 };
@@ -1882,7 +1883,7 @@ __global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__
     const int warp = threadIdx.x >> 5, tid = threadIdx.x;
     const uint8_t* payload = a.payloads + (int64_t)f * a.payload_stride;
     const int64_t nsym = amb_tx_num_symbols(T, a.payload_len);
-    const int64_t pre = amb_tx_silence_pre(T, a.first), post = amb_tx_silence_post();
+    const int64_t pre = a.pre >= 0 ? a.pre : amb_tx_silence_pre(T, a.first), post = a.post >= 0 ? a.post : amb_tx_silence_post();
     const int64_t sym = T->sym_len, total = pre + (3 + nsym) * sym + post;
     float* out = a.out + (int64_t)f * a.out_stride;
     for (int64_t i = tid; i < pre; i += 256) out[i] = 0.f;

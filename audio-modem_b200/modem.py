@@ -329,6 +329,18 @@ class Modem:
                                                     noise_seed, noise_g0, None, MEM_DEVICE))
         return out
 
+    def build_transmit_signals(self, datas, fileName="file"):
+        """buildTransmitSignal (modem.js:498-555) for many payloads of equal length -> [n][samples] float32"""
+        data = np.ascontiguousarray(np.stack([np.frombuffer(bytes(d), np.uint8) if isinstance(d, (bytes, bytearray)) else np.asarray(d, np.uint8)
+                                              for d in datas]))
+        n, data_len = data.shape
+        name = np.ascontiguousarray(np.frombuffer((fileName or "file").encode("utf-8"), np.uint8)[:255])
+        flen = int(self._L.amb_transmit_signal_samples(self._h, data_len, len(name)))
+        out = np.zeros((n, flen), np.float32)
+        self._ck(self._L.amb_build_transmit_signals(self._h, _ptr(data), max(data_len, 1) if data_len else 0, data_len, n, _ptr(name), len(name),
+                                                    _ptr(out), flen, MEM_HOST))
+        return out
+
     def build_metadata_frame(self, totalChunks, totalFileSize, chunkSize, fileName="file", noise_sigma=0.0, noise_seed=0, noise_g0=0, out=None):
         """buildMetadataFrame (modem.js:758)"""
         name = np.frombuffer((fileName or "file").encode("utf-8"), np.uint8)
@@ -526,6 +538,23 @@ def analyzeLoopback(recorded, modName, repetition=1, testData=bytes(range(16))):
 
 def decodeChunkFrame(frameSamples, modName, repetition=1):
     return _modem(modName, repetition).decode_chunk_frames([frameSamples])[0]
+
+
+def buildTransmitSignal(fileData, modName, fileName="file", repetition=1):
+    """modem.js:498-555 -> {signal, numSymbols, bitsPerSymbol, totalBits, dataLen}"""
+    m = _modem(modName, repetition)
+    data = bytes(fileData)
+    sig = m.build_transmit_signals([data], fileName)[0]
+    name_len = min(len((fileName or "file").encode("utf-8")), 255)
+    bps = m.NUM_DATA_SUBS * m.bps
+    total_bits = (1 + name_len + 4 + len(data) + 4) * 8 * m.repetition
+    return {"signal": sig, "numSymbols": -(-total_bits // bps), "bitsPerSymbol": bps, "totalBits": total_bits, "dataLen": len(data)}
+
+
+def generateTestSignal(modName, repetition=1):
+    """modem.js:913-975"""
+    td = bytes(range(16))
+    return {"signal": buildTransmitSignal(td, modName, "test", repetition)["signal"], "testData": np.frombuffer(td, np.uint8).copy()}
 
 
 def buildDataChunkFrame(chunkData, seqNum, modName, rep=1):

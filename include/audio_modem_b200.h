@@ -248,6 +248,15 @@ int amb_build_data_chunk_frames(amb_modem* m, const uint8_t* data, int64_t data_
 int amb_build_metadata_frame(amb_modem* m, int32_t total_chunks, int32_t total_file_size, int32_t chunk_size, const uint8_t* name,
                              int name_len, float* out, double noise_sigma, uint64_t noise_seed, int64_t noise_g0, int mem);
 
+/* buildTransmitSignal, modem.js:498-555 (and generateTestSignal, :913-975, which is the same construction over the bytes
+ * 00..0F named "test"): n legacy frames [silence | preamble-1 | preamble-2 | CE | data symbols | silence], each carrying
+ * the packet [nameLen][name][dataLen:4][data][CRC-32:4] of data row i, normalised to a peak of 0.8; bit-identical to the
+ * reference's Float32Array.  data = [n][data_stride] and out = [n][out_stride] are host memory (mem = AMB_MEM_HOST);
+ * amb_transmit_signal_samples gives the length of one signal. */
+int64_t amb_transmit_signal_samples(amb_modem* m, int64_t data_len, int name_len);
+int amb_build_transmit_signals(amb_modem* m, const uint8_t* data, int64_t data_stride, int data_len, int n, const uint8_t* name,
+                               int name_len, float* out, int64_t out_stride, int mem);
+
 #ifdef __cplusplus
 }
 #endif

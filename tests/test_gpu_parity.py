@@ -505,3 +505,29 @@ def test_tx_frames_bit_identical(O, modems, mode):
     assert abs(float(d.std()) - 0.001) < 1e-4 and abs(float(d.mean())) < 1e-4
     r = m.decode_chunk_frames([noisy[0][2205:]])[0]
     assert r["crcValid"] and r["data"] == bytes(chunks[0])
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tx_transmit_signal_bit_identical(O, amb, modems, mode):
+    """buildTransmitSignal / generateTestSignal (modem.js:498-555, :913-975) on the device: bit-identical to the oracle's
+    frames, and the loop closes through decodeReceivedSignal and analyzeLoopback"""
+    cfg, mod, rep, _ = MODES[mode]
+    m = modems(mode)
+    datas = [bytes(O.randomBytes(300 + i, 200) | 0x01) for i in range(3)]
+    sigs = m.build_transmit_signals(datas, "ünï-name.bin")
+    for i, d in enumerate(datas):
+        assert np.array_equal(sigs[i], O.buildTransmitSignal(cfg, d, mod, "ünï-name.bin", rep)), (mode, i)
+    one = m.build_transmit_signals([b"\x07"], None)
+    assert np.array_equal(one[0], O.buildTransmitSignal(cfg, b"\x07", mod, "file", rep))
+    amb.setOFDMConfig(cfg)
+    t = amb.generateTestSignal(mod, rep)
+    assert np.array_equal(t["signal"], O.generateTestSignal(cfg, mod, rep)["signal"]) and bytes(t["testData"]) == bytes(range(16))
+    full = amb.buildTransmitSignal(datas[0], mod, "a.bin", rep)
+    assert full["dataLen"] == 200 and full["totalBits"] == (1 + 5 + 4 + 200 + 4) * 8 * rep
+    assert full["numSymbols"] == (len(full["signal"]) - len(O.buildTransmitSignal(cfg, b"", mod, "a.bin", rep))) // O.config(cfg)["SYMBOL_LEN"] + \
+        -(-((1 + 5 + 4 + 4) * 8 * rep) // full["bitsPerSymbol"])
+    if cfg != "narrowband":
+        r = amb.decodeReceivedSignal(full["signal"], mod, rep)
+        assert r["crcValid"] and r["data"] == datas[0] and r["fileName"] == "a.bin"
+        assert amb.analyzeLoopback(t["signal"], mod, rep, t["testData"])["quality"] == "excellent"
+    amb.setOFDMConfig("standard")
