@@ -185,7 +185,8 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
         {
             const int ns_grp = max_nsym < AMB_SYM_GROUP ? (max_nsym > 0 ? max_nsym : 1) : AMB_SYM_GROUP;
             int best_cost = 1 << 30;
-            for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
+            // (+1: the CE symbol takes one half-warp slot of the first round)
+            for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 1 + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
         }
         // instantiated per constellation and per CTA size class (7 warps or fewer leave registers for a fourth resident CTA)
 #define AMB_DEMOD_LAUNCH(MODV, NTV) \

@@ -852,57 +852,32 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
     __syncthreads();
     float my_mx = 0.f;
-    // ---- channel from the CE symbol (warp 0: both half-warps transform it, the lower one keeps the result; the warp-wide
-    //      shuffles and barriers inside need all 32 lanes); the other warps gather the peak over preamble-1, preamble-2 and
-    //      the CE prefix.  The equaliser tables fold the real-FFT split in: with A = Z[k] + conj(Z[256-k]) and
-    //      B = -i (Z[k] - conj(Z[256-k])), Y[k] = (A + W512^k B) / 2, so Y conj(H)/|H|^2 = A Gq + B WG.
-    if (warp == 0) {
-        const int64_t p0 = J.ce_pos + cp;
-        const bool inside = p0 >= J.lo && p0 + AMB_FFT <= J.hi;
-        float S;
-        my_mx = fd_spectrum(J, p0, inside, l, hwbuf + hw * AMB_FD_HWBUF, tw256, &S);
-        float mn = 3.0e38f;
-        for (int kk = l; kk < nb; kk += 16) {
-            const int k = sub_start + kk;
-            const float2 w = FT->tw512[k];
-            const float2 y = fd_split(hwbuf + hw * AMB_FD_HWBUF, w, k);
-            const float xr = (float)T->known_re[k];
-            const float d = xr * xr;
-            float hr = 0.f, hi = 0.f;
-            if (d > 1e-10f) { const float q = __fdividef(xr, d); hr = y.x * q; hi = y.y * q; }
-            const float hm = hr * hr + hi * hi;
-            mn = fminf(mn, hm);
-            if (hw == 0) {
-                const float ihm = 0.5f * __frcp_rn(hm);
-                const float2 g = make_float2(hr * ihm, -hi * ihm);
-                Gq[kk] = g;
-                WG[kk] = cmulf(w, g);
-                cH[kk] = 8e-5f * rsqrtf(hm);
-            }
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (lane == 0) { s_minhm = mn; s_Sce = S; }
-    } else if (folded) {
+    // ---- peak over preamble-1, preamble-2 and the CE prefix (the symbols' own samples are gathered on the way below)
+    if (folded) {
         const int64_t a = J.pos, b = J.ce_pos + cp;                  // [frame start, CE body)
-        for (int64_t g = a + (tid - 32); g < b; g += nthr - 32) {
+        for (int64_t g = a + tid; g < b; g += nthr) {
             const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
             my_mx = fmaxf(my_mx, fabsf(v));
         }
     }
-    // ---- data symbols.  In the first round warps 1..7 transform their symbols while warp 0 is still busy with the channel:
-    //      the barrier sits between their transform and their equaliser.
+    // ---- items: the CE symbol (item 0, half-warp 0 of the first round) and the data symbols of this group, one per half-warp
+    //      and round, all through the same transform.  In the first round half-warp 0 turns the CE spectrum into the
+    //      equaliser tables while the others hold their transformed symbols; the barrier sits between the transforms and the
+    //      equalisers.  The tables fold the real-FFT split in: with A = Z[k] + conj(Z[256-k]) and
+    //      B = -i (Z[k] - conj(Z[256-k])), Y[k] = (A + W512^k B) / 2, so Y conj(H)/|H|^2 = A Gq + B WG.
     const int s_end = min(J.nsym, g0 + AMB_SYM_GROUP);
     float2* buf = hwbuf + hw * AMB_FD_HWBUF;
     float2* pe = s_pilot[hw];                                            // pilot bins of the symbol in flight
     const float thr = (float)T->qam_thr;
     const int n_pilots = T->n_pilots;
     float Sce = 0.f;
-    for (int s0 = g0; s0 < s_end; s0 += nhw) {
-        const int sidx = s0 + hw;
-        const bool active = sidx < s_end;                               // uniform per half-warp
-        const int sx = active ? sidx : s_end - 1;
-        const int64_t p0 = J.data_pos + (int64_t)sx * sym + cp;
+    for (int q0 = 0; q0 <= s_end - g0; q0 += nhw) {
+        const bool first_round = q0 == 0;
+        const bool is_ce = first_round && hw == 0;
+        const int sidx = g0 + q0 + hw - 1;
+        const bool active = !is_ce && sidx < s_end;                     // uniform per half-warp
+        const int sx = (!is_ce && sidx < s_end) ? sidx : s_end - 1;
+        const int64_t p0 = is_ce ? J.ce_pos + cp : J.data_pos + (int64_t)sx * sym + cp;
         const bool inside = p0 - cp >= J.lo && p0 + AMB_FFT <= J.hi;
         // the cyclic prefix only counts for the peak: issue the loads of its first 64 samples now, use them after the transform
         float cpv[AMB_FD_CPV];
@@ -914,13 +889,33 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
                 cpv[q] = (i < cp && (inside || (gq >= J.lo && gq < J.hi))) ? J.p[gq - J.base] : 0.f;
             }
         }
-        float S = 0.f, smx = 0.f;
-        const bool first_round = s0 == g0;
-        if (!(first_round && warp == 0)) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
+        float S = 0.f;
+        float smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
         if (first_round) {
+            if (hw == 0) {
+                float mn = 3.0e38f;
+                for (int kk = l; kk < nb; kk += 16) {
+                    const int k = sub_start + kk;
+                    const float2 w = FT->tw512[k];
+                    const float2 y = fd_split(buf, w, k);
+                    const float xr = (float)T->known_re[k];
+                    const float d = xr * xr;
+                    float hr = 0.f, hi = 0.f;
+                    if (d > 1e-10f) { const float q = __fdividef(xr, d); hr = y.x * q; hi = y.y * q; }
+                    const float hm = hr * hr + hi * hi;
+                    mn = fminf(mn, hm);
+                    const float ihm = 0.5f * __frcp_rn(hm);
+                    const float2 g = make_float2(hr * ihm, -hi * ihm);
+                    Gq[kk] = g;
+                    WG[kk] = cmulf(w, g);
+                    cH[kk] = 8e-5f * rsqrtf(hm);
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0x0000ffffu, mn, o));
+                if (l == 0) { s_minhm = mn; s_Sce = S; }
+            }
             __syncthreads();                                            // channel tables ready
             Sce = s_Sce;
-            if (warp == 0) smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
         }
         if (folded) {
 #pragma unroll
@@ -930,7 +925,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
                 const float v = (inside || (gq >= J.lo && gq < J.hi)) ? J.p[gq - J.base] : 0.f;
                 smx = fmaxf(smx, fabsf(v));
             }
-            if (active) my_mx = fmaxf(my_mx, smx);
+            if (active || is_ce) my_mx = fmaxf(my_mx, smx);
         }
         // equalised bins of this lane: kk = l + 16 i; pilot bins also go to shared memory for the phase estimate
         float2 E[AMB_FD_ITERS];
