@@ -833,7 +833,8 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     __shared__ float s_red[8];
     __shared__ float2 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
     __shared__ int pilot_kk[AMB_MAX_PILOTS];                                     // bin (relative to sub_start) of pilot q, -1 outside the band
-    __shared__ float s_mx, s_minhm, s_Sce;
+    __shared__ float s_mx, s_Sce;
+    __shared__ unsigned s_minhm_bits;
     __shared__ unsigned s_mask[2];
     __shared__ int s_all;
     const int j = blockIdx.x;
@@ -849,7 +850,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     for (int i = tid; i < 256; i += nthr) tw256[i] = FT->tw256[i];
     for (int i = tid; i < nb; i += nthr) role[i] = FT->role[i];
     if (tid < AMB_MAX_PILOTS) pilot_kk[tid] = FT->pilot_kk[tid];
-    if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; }
+    if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; s_minhm_bits = 0x7f800000u; }
     __syncthreads();
     float my_mx = 0.f;
     // ---- peak over preamble-1, preamble-2 and the CE prefix (the symbols' own samples are gathered on the way below)
@@ -892,27 +893,24 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
         float S = 0.f;
         float smx = fd_spectrum(J, p0, inside, l, buf, tw256, &S);
         if (first_round) {
-            if (hw == 0) {
-                float mn = 3.0e38f;
-                for (int kk = l; kk < nb; kk += 16) {
-                    const int k = sub_start + kk;
-                    const float2 w = FT->tw512[k];
-                    const float2 y = fd_split(buf, w, k);
-                    const float xr = (float)T->known_re[k];
-                    const float d = xr * xr;
-                    float hr = 0.f, hi = 0.f;
-                    if (d > 1e-10f) { const float q = __fdividef(xr, d); hr = y.x * q; hi = y.y * q; }
-                    const float hm = hr * hr + hi * hi;
-                    mn = fminf(mn, hm);
-                    const float ihm = 0.5f * __frcp_rn(hm);
-                    const float2 g = make_float2(hr * ihm, -hi * ihm);
-                    Gq[kk] = g;
-                    WG[kk] = cmulf(w, g);
-                    cH[kk] = 8e-5f * rsqrtf(hm);
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0x0000ffffu, mn, o));
-                if (l == 0) { s_minhm = mn; s_Sce = S; }
+            if (is_ce && l == 0) s_Sce = S;
+            __syncthreads();                                            // CE spectrum (half-warp 0's buffer) complete
+            // equaliser tables: one band bin per thread
+            for (int kk = tid; kk < nb; kk += nthr) {
+                const int k = sub_start + kk;
+                const float2 w = FT->tw512[k];
+                const float2 y = fd_split(hwbuf, w, k);
+                const float xr = (float)T->known_re[k];
+                const float d = xr * xr;
+                float hr = 0.f, hi = 0.f;
+                if (d > 1e-10f) { const float q = __fdividef(xr, d); hr = y.x * q; hi = y.y * q; }
+                const float hm = hr * hr + hi * hi;
+                atomicMin(&s_minhm_bits, __float_as_uint(hm));          // non-negative floats order like their bit patterns (NaN sorts high: caught by the guard below)
+                const float ihm = 0.5f * __frcp_rn(hm);
+                const float2 g = make_float2(hr * ihm, -hi * ihm);
+                Gq[kk] = g;
+                WG[kk] = cmulf(w, g);
+                cH[kk] = 8e-5f * rsqrtf(hm);
             }
             __syncthreads();                                            // channel tables ready
             Sce = s_Sce;
@@ -1014,7 +1012,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     if (tid == 0) {
         // modem.js:389 tests |H|^2 > 1e-10 on the normalised frame: H_norm = H_raw / scale
         const float scale = (J.xf.kind == AMB_XF_SCALE && J.xf.mx > 1e-6f) ? J.xf.mx : 1.f;
-        if (!(s_minhm > 1.01e-10f * scale * scale)) s_all = 1;
+        if (!(__uint_as_float(s_minhm_bits) > 1.01e-10f * scale * scale)) s_all = 1;
     }
     __syncthreads();
     const int n_here = s_end - g0;
