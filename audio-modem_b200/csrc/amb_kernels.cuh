@@ -402,11 +402,14 @@ __global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ 
         const int64_t a_hi = avail_hi - base_g;
         float x[3][8];
         if (a_first >= 0 && a_first + 768 <= a_hi) {
-            const float* p0 = row + a_first + 8 * lane;
+            // a_first = 256 tile - 511 sits one float past a 16-byte boundary: two aligned 128-bit loads and one scalar per segment
+            const float* pa = row + (a_first - 1) + 8 * lane;
 #pragma unroll
-            for (int seg = 0; seg < 3; seg++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[seg][k] = p0[256 * seg + k];
+            for (int seg = 0; seg < 3; seg++) {
+                const float4 u = *reinterpret_cast<const float4*>(pa + 256 * seg), v = *reinterpret_cast<const float4*>(pa + 256 * seg + 4);
+                x[seg][0] = u.y; x[seg][1] = u.z; x[seg][2] = u.w; x[seg][3] = v.x; x[seg][4] = v.y; x[seg][5] = v.z; x[seg][6] = v.w;
+                x[seg][7] = pa[256 * seg + 8];
+            }
         } else {
 #pragma unroll
             for (int seg = 0; seg < 3; seg++)
