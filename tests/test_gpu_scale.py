@@ -126,8 +126,9 @@ def test_c5_many_streams(O, amb):
 
 
 def test_sectioned_host_push_equals_one_push(O, amb):
-    """large host pushes are cut into sections whose copies overlap the processing (amb_stream_push): same events as the
-    oracle, also when the results of several sections land in the caller's buffers back to back"""
+    """large host pushes are cut into sections whose copies overlap the processing (amb_stream_push and
+    amb_stream_push_pcm16): same events as the oracle, also when the results of several sections land in the caller's
+    buffers back to back"""
     import os
     import subprocess
     import sys
@@ -146,6 +147,13 @@ def test_sectioned_host_push_equals_one_push(O, amb):
         "want = O.StreamingReceiver('standard', 'QAM16', 1).push(x, 4096, raw=True)\n"
         "assert len(got) == len(want) == 41, (len(got), len(want))\n"
         "for (r1, b1), (r2, b2) in zip(want, got):\n"
+        "    assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], r1.preamble_idx\n"
+        "pcm = np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)\n"
+        "m.stream_close(); m.stream_open(1, 4096, len(x))\n"
+        "got16 = m.stream_push(pcm[None, :], raw=True)\n"
+        "want16 = O.StreamingReceiver('standard', 'QAM16', 1).push(pcm.astype(np.float32) / np.float32(32768.0), 4096, raw=True)\n"
+        "assert len(got16) == len(want16) == 41, (len(got16), len(want16))\n"
+        "for (r1, b1), (r2, b2) in zip(want16, got16):\n"
         "    assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], r1.preamble_idx\n"
         "print('sections ok')\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
