@@ -64,7 +64,7 @@ struct amb_modem {
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
-    int walk_ctas = 148 * 4;          // CTAs of k_link_walk resident on the device
+    int walk_ctas = 148 * 16;         // grid of k_link_walk (set from the occupancy at create)
     bool push_pcm16 = false;          // input format of the push in progress
     int n_streams = 0;
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
@@ -348,7 +348,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         int occ = 0, sms = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk, 128, 0) == cudaSuccess && occ > 0 &&
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
-            m->walk_ctas = occ * sms;
+            m->walk_ctas = 4 * occ * sms;          // a few waves: the walks differ in length (measured flat from 4 to 16 waves, 7 % slower at one)
     }
     cudaFuncSetAttribute(k_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
     cudaFuncSetAttribute(k_front<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
@@ -935,7 +935,6 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
     L.fp_sum = m->l_fpsum.as<unsigned long long>(); L.memo = m->l_memo.as<AmbRefineMemo>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
-    // one resident wave: the walks differ in length, a second wave of CTAs would start behind the longest of the first
     const int walk_grid = (int)(blocks_for(max_links, 4) < m->walk_ctas ? blocks_for(max_links, 4) : m->walk_ctas);
     const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);
     int* h = m->h_counts;           // pinned: [0] n_active, [1] total jobs, [2] max nsym, [3] kept, [4] n_redo
