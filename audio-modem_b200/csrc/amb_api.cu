@@ -350,8 +350,10 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
             m->walk_ctas = 4 * occ * sms;          // a few waves: the walks differ in length (measured flat from 4 to 16 waves, 7 % slower at one)
     }
-    cudaFuncSetAttribute(k_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
-    cudaFuncSetAttribute(k_front<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM);
+    cudaFuncSetAttribute(k_front<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(256));
+    cudaFuncSetAttribute(k_front<int16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(256));
+    cudaFuncSetAttribute(k_front<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(128));
+    cudaFuncSetAttribute(k_front<int16_t, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(128));
     cudaFuncSetAttribute(k_chain_links, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_CHAIN_SMEM);
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
@@ -872,16 +874,26 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
         AmbFrontArgs fa;
         fa.x = src; fa.x_stride = src_stride; fa.cleaned = m->cleaned.as<float>(); fa.stride = m->stride; fa.off0 = off0;
-        fa.tiles = tiles;
-        // spans: enough CTAs to fill the GPU, long enough that the 10-tile warm-up of the EMA state stays a small part
-        int64_t span = ((int64_t)ns * tiles + 148 * 3 - 1) / (148 * 3);      // one wave of 3 CTAs per SM
-        if (span < 16) span = 16;
-        if (span > tiles) span = tiles;
-        fa.span = (int)span; fa.spans = (int)((tiles + span - 1) / span); fa.warm = 10;
+        // tile steps of 16 x threads samples.  128-thread CTAs (2048-sample steps, six per SM) measured 5 % faster than 256
+        // (three per SM) and the same as 64 (twelve per SM); AMB_FRONT_NT=256 selects the larger step for comparison.
+        static const int front_nt = (std::getenv("AMB_FRONT_NT") && std::atoi(std::getenv("AMB_FRONT_NT")) == 256) ? 256 : 128;
+        const int per_block = AMB_TILE / (16 * front_nt);                    // tile steps per 4096-sample block: 1 or 2
+        const int ftiles = tiles * per_block, ctas_per_sm = 768 / front_nt;
+        fa.tiles = ftiles;
+        // spans: enough CTAs to fill the GPU, long enough that the 40,960-sample warm-up of the EMA state stays a small part
+        int64_t span = ((int64_t)ns * ftiles + 148 * ctas_per_sm - 1) / (148 * ctas_per_sm);      // one wave
+        if (span < 16 * per_block) span = 16 * per_block;
+        if (span > ftiles) span = ftiles;
+        fa.span = (int)span; fa.spans = (int)((ftiles + span - 1) / span); fa.warm = 10 * per_block;
         fa.E = m->d_ema; fa.states = m->states.as<AmbStreamState>(); fa.dc_next = m->dc_next.as<double>();
         fa.sums = m->sums.as<float>(); fa.sum_stride = m->sum_stride; fa.st = ss;
-        if (m->push_pcm16) { LAUNCH("k_front", k_front<int16_t><<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa)); }
-        else { LAUNCH("k_front", k_front<float><<<ns * fa.spans, 256, AMB_FRONT_SMEM, m->stream>>>(fa)); }
+        if (front_nt == 128) {
+            if (m->push_pcm16) { LAUNCH("k_front", (k_front<int16_t, 128><<<ns * fa.spans, 128, AMB_FRONT_SMEM(128), m->stream>>>(fa))); }
+            else { LAUNCH("k_front", (k_front<float, 128><<<ns * fa.spans, 128, AMB_FRONT_SMEM(128), m->stream>>>(fa))); }
+        } else {
+            if (m->push_pcm16) { LAUNCH("k_front", (k_front<int16_t, 256><<<ns * fa.spans, 256, AMB_FRONT_SMEM(256), m->stream>>>(fa))); }
+            else { LAUNCH("k_front", (k_front<float, 256><<<ns * fa.spans, 256, AMB_FRONT_SMEM(256), m->stream>>>(fa))); }
+        }
     }
     const int tri_grid_max = 148 * 64;
     LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < tri_grid_max ? (m->slot_cap + 3) / 4 : tri_grid_max, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));

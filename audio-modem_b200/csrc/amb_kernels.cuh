@@ -104,8 +104,8 @@ struct AmbScanStore {
 
 // ================================================================================================
 // k_front: the streaming front end in one pass over the new samples - EMA DC removal (app.js:750-755) and the
-// Schmidl-Cox tile summaries the walker screens with.  One CTA walks a span of consecutive 4096-sample tiles of one
-// stream; thread t owns samples 16 t .. 16 t + 15 of every tile.
+// Schmidl-Cox tile summaries the walker screens with.  One CTA of NT threads walks a span of consecutive tile steps of
+// 16 NT samples (2048 with the 128 threads used) of one stream; thread t owns samples 16 t .. 16 t + 15 of every step.
 //   EMA: m <- alpha m + beta x is linear, so each thread first runs its 16 samples from a zero state, a warp scan
 //   (weights alpha^(16 2^k)) and an 8-step chain over the warp totals give the state entering every thread, and a
 //   second 16-step run produces cleaned = f32(x - m).  A span that does not start at the push start warms the state up
@@ -132,7 +132,7 @@ struct AmbFrontArgs {
 
 #define AMB_FR_PAD(i) ((i) + (((i) >> 4) << 2))       // 4 floats of padding per 16: conflict-free 128-bit rows per thread
 #define AMB_FR_BUF AMB_FR_PAD(AMB_TILE)               // floats per padded tile buffer (5120)
-#define AMB_FRONT_SMEM (2 * AMB_FR_BUF * 4 + AMB_TILE * 4)   // two cleaned tiles (double buffer, padded) + one staged input tile (linear)
+#define AMB_FRONT_SMEM(NT) ((2 * AMB_FR_PAD(16 * (NT)) + 16 * (NT)) * 4)   // two cleaned tiles (double buffer, padded) + one staged input tile (linear)
 
 // TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk; UBLKCP in SASS)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -167,15 +167,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // hold q, a and the warp-inclusive scans of q and t, from which any block-wide prefix is one addition away.  The next
 // tile's input (16 KB) is staged global -> shared by one TMA bulk copy (cp.async.bulk, completion on an mbarrier) while
 // the current one is processed.  Three barriers per tile.
-template <typename IN>
-__global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
+template <typename IN, int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
+    constexpr int FT = 16 * NT, NW = NT / 32, FBUF = AMB_FR_PAD(FT);     // samples per tile step, warps, padded tile buffer
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* R = reinterpret_cast<float*>(smem_raw);                     // [2][AMB_FR_BUF]
-    float* XS = R + 2 * AMB_FR_BUF;                                    // [AMB_TILE] staged input, linear (bulk-copy destination)
+    float* R = reinterpret_cast<float*>(smem_raw);                     // [2][FBUF]
+    float* XS = R + 2 * FBUF;                                          // [FT] staged input, linear (bulk-copy destination)
     __shared__ __align__(8) uint64_t xs_bar;
-    __shared__ float sq[2][256], sa[2][256], sT[2][256], sI[2][256], sJ[2][256];   // q_e, a_e, t_e, warp-inclusive scans of q_e and t_e
-    __shared__ float sWq[2][8], sWt[2][8];                             // warp totals of q and t
-    __shared__ double sW[8];
+    __shared__ float sq[2][NT], sa[2][NT], sT[2][NT], sI[2][NT], sJ[2][NT];   // q_e, a_e, t_e, warp-inclusive scans of q_e and t_e
+    __shared__ float sWq[2][NW], sWt[2][NW];                             // warp totals of q and t
+    __shared__ double sW[NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x / a.spans, p = blockIdx.x % a.spans;
     const int t0 = p * a.span, t1 = min(a.tiles, t0 + a.span);
@@ -184,22 +185,22 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
     const double alpha = E->alpha, beta = E->beta, a512 = E->a512;
     const double lp = E->lanepow[lane];
     const IN* xrow = reinterpret_cast<const IN*>(a.x) + (int64_t)s * a.x_stride;
-    const unsigned tile_bytes = AMB_TILE * sizeof(IN);
+    const unsigned tile_bytes = FT * sizeof(IN);
     float* crow = a.cleaned + (int64_t)s * a.stride + a.off0;
     const int tb = t0 - a.warm > 0 ? t0 - a.warm : 0;
     // The EMA runs on u = m / beta (u <- alpha u + x: one FMA per sample instead of a multiplication and an FMA), and
     // cleaned = x - beta u is one more FMA.
     double m_tile = tb == 0 ? a.states[s].dc_mean / beta : 0.0;
     // ---- history of the scan part: lives in buffer 1 (the first full tile goes to buffer 0)
-    for (int i = tid; i < 2 * AMB_FR_BUF; i += 256) R[i] = 0.f;
+    for (int i = tid; i < 2 * FBUF; i += NT) R[i] = 0.f;
     sq[0][tid] = sa[0][tid] = sT[0][tid] = sI[0][tid] = sJ[0][tid] = 0.f;
     sq[1][tid] = sa[1][tid] = sT[1][tid] = sI[1][tid] = sJ[1][tid] = 0.f;
-    if (tid < 8) { sWq[0][tid] = sWt[0][tid] = sWq[1][tid] = sWt[1][tid] = 0.f; }
+    if (tid < NW) { sWq[0][tid] = sWt[0][tid] = sWq[1][tid] = sWt[1][tid] = 0.f; }
     __syncthreads();
     if (t0 == 0) {
         // push start: the 768 cleaned samples before it come from the arena (zeros before the stream start)
-        R[AMB_FR_BUF + AMB_FR_PAD(AMB_TILE - 256 + tid)] = crow[tid - 256];
-        if (tid == 0) R[AMB_FR_BUF + AMB_FR_PAD(AMB_TILE - 512)] = crow[-512];
+        for (int i = tid; i < 256; i += NT) R[FBUF + AMB_FR_PAD(FT - 256 + i)] = crow[i - 256];
+        if (tid == 0) R[FBUF + AMB_FR_PAD(FT - 512)] = crow[-512];
         if (tid < 32) {
             float q = 0.f, tt = 0.f, at = 0.f;
             for (int k = 0; k < 16; k++) {
@@ -212,14 +213,14 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
                 const float uq = __shfl_up_sync(0xffffffffu, iq, o), ut = __shfl_up_sync(0xffffffffu, it, o);
                 if (lane >= o) { iq += uq; it += ut; }
             }
-            sq[1][224 + tid] = q; sa[1][224 + tid] = at; sT[1][224 + tid] = tt; sI[1][224 + tid] = iq; sJ[1][224 + tid] = it;
-            if (tid == 31) { sWq[1][7] = iq; sWt[1][7] = it; }
+            sq[1][NT - 32 + tid] = q; sa[1][NT - 32 + tid] = at; sT[1][NT - 32 + tid] = tt; sI[1][NT - 32 + tid] = iq; sJ[1][NT - 32 + tid] = it;
+            if (tid == 31) { sWq[1][NW - 1] = iq; sWt[1][NW - 1] = it; }
         }
     }
     // stage the first tile's input
     if (tid == 0) { mbar_init(&xs_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     __syncthreads();
-    if (tid == 0) { mbar_expect_tx(&xs_bar, tile_bytes); bulk_g2s(XS, xrow + (int64_t)tb * AMB_TILE, tile_bytes, &xs_bar); }
+    if (tid == 0) { mbar_expect_tx(&xs_bar, tile_bytes); bulk_g2s(XS, xrow + (int64_t)tb * FT, tile_bytes, &xs_bar); }
     unsigned xs_phase = 0;
     int n = 0;                                                          // full tiles done: the current one uses buffer n & 1
     for (int t = tb; t < t1; t++) {
@@ -260,11 +261,11 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         if (t + 1 < t1 && tid == 0) {
             fence_proxy_async();                                        // the threads' reads of XS are ordered before the bulk write
             mbar_expect_tx(&xs_bar, tile_bytes);
-            bulk_g2s(XS, xrow + (int64_t)(t + 1) * AMB_TILE, tile_bytes, &xs_bar);
+            bulk_g2s(XS, xrow + (int64_t)(t + 1) * FT, tile_bytes, &xs_bar);
         }
         double S = m_tile, m_next = m_tile;
 #pragma unroll
-        for (int w = 0; w < 8; w++) { m_next = fma(a512, m_next, sW[w]); if (w + 1 == warp) S = m_next; }
+        for (int w = 0; w < NW; w++) { m_next = fma(a512, m_next, sW[w]); if (w + 1 == warp) S = m_next; }
         m_tile = m_next;
         if (ema_only) { __syncthreads(); continue; }
         // ... then the true state entering the thread, and the cleaned samples (two chains again)
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
             mA = fma(alpha, mA, (double)x[k]); c[k] = (float)fma(-beta, mA, (double)x[k]);
             mB = fma(alpha, mB, (double)x[8 + k]); c[8 + k] = (float)fma(-beta, mB, (double)x[8 + k]);
         }
-        float* Rc = R + (n & 1) * AMB_FR_BUF;                           // this tile
-        const float* Rp = R + ((n + 1) & 1) * AMB_FR_BUF;               // its predecessor
+        float* Rc = R + (n & 1) * FBUF;                           // this tile
+        const float* Rp = R + ((n + 1) & 1) * FBUF;               // its predecessor
         const int cb = n & 1, pb = (n + 1) & 1;
         {
             float4* dst = reinterpret_cast<float4*>(Rc + AMB_FR_PAD(16 * tid));
@@ -287,14 +288,14 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
         }
         __syncthreads();                                                // (2) cleaned tile in shared memory
         if (emit) {
-            float4* g = reinterpret_cast<float4*>(crow + (int64_t)t * AMB_TILE);
+            float4* g = reinterpret_cast<float4*>(crow + (int64_t)t * FT);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const int f = tid + 256 * k; g[f] = *reinterpret_cast<const float4*>(Rc + AMB_FR_PAD(4 * f)); }
+            for (int k = 0; k < 4; k++) { const int f = tid + NT * k; g[f] = *reinterpret_cast<const float4*>(Rc + AMB_FR_PAD(4 * f)); }
         }
         // ---- sub-block sums against the partner samples 256 behind
         float q = 0.f, tt = 0.f, at = 0.f;
         {
-            const float4* pr4 = tid < 16 ? reinterpret_cast<const float4*>(Rp + AMB_FR_PAD(AMB_TILE - 256 + 16 * tid))
+            const float4* pr4 = tid < 16 ? reinterpret_cast<const float4*>(Rp + AMB_FR_PAD(FT - 256 + 16 * tid))
                                          : reinterpret_cast<const float4*>(Rc + AMB_FR_PAD(16 * (tid - 16)));
 #pragma unroll
             for (int q4 = 0; q4 < 4; q4++) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
             // predecessor's last warp (e < 0): QS(e) = sI_p[256 + e] - sq_p[256 + e] - sWq_p[7]
             float oq = 0.f, ot = 0.f, totq = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const float wq = sWq[cb][w]; if (w < warp) { oq += wq; ot += sWt[cb][w]; } totq += wq; }
+            for (int w = 0; w < NW; w++) { const float wq = sWq[cb][w]; if (w < warp) { oq += wq; ot += sWt[cb][w]; } totq += wq; }
             const float QSe = oq + iq - q, TSe = ot + it - tt;
             float QS16, TS16, QS32, q16, a16v, q32;
             {
@@ -331,14 +332,14 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
                     const float o2 = same ? oq : oq - sWq[cb][warp - 1], o2t = same ? ot : ot - sWt[cb][warp - 1];
                     q16 = sq[cb][e]; a16v = sa[cb][e]; QS16 = o2 + sI[cb][e] - q16; TS16 = o2t + sJ[cb][e] - sT[cb][e];
                 } else {
-                    const int k = 256 + e;
-                    q16 = sq[pb][k]; a16v = sa[pb][k]; QS16 = sI[pb][k] - q16 - sWq[pb][7]; TS16 = sJ[pb][k] - sT[pb][k] - sWt[pb][7];
+                    const int k = NT + e;
+                    q16 = sq[pb][k]; a16v = sa[pb][k]; QS16 = sI[pb][k] - q16 - sWq[pb][NW - 1]; TS16 = sJ[pb][k] - sT[pb][k] - sWt[pb][NW - 1];
                 }
             }
             {
                 const int e = tid - 32;
                 if (e >= 0) { q32 = sq[cb][e]; QS32 = (oq - sWq[cb][warp - 1]) + sI[cb][e] - q32; }
-                else { const int k = 256 + e; q32 = sq[pb][k]; QS32 = sI[pb][k] - q32 - sWq[pb][7]; }
+                else { const int k = NT + e; q32 = sq[pb][k]; QS32 = sI[pb][k] - q32 - sWq[pb][NW - 1]; }
             }
             const float Aal = QS16 - QS32, Bal = QSe - QS16, Pal = TSe - TS16;
             float mxA = Aal + q16, mnA = Aal - q32, mxB = Bal + q, mnB = Bal - q16;
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
                 mxP = fmaxf(mxP, __shfl_xor_sync(0xffffffffu, mxP, o));
             }
             if ((tid & 15) == 0) {
-                const float err = 4e-6f * (totq + sWq[pb][7]) + 1e-12f;     // float32 prefix sums over the tile and its history
-                const int64_t a0 = a.off0 + (int64_t)t * AMB_TILE;
+                const float err = 4e-6f * (totq + sWq[pb][NW - 1]) + 1e-12f;     // float32 prefix sums over the tile and its history
+                const int64_t a0 = a.off0 + (int64_t)t * FT;
                 const int64_t tix = (int64_t)s * a.sum_stride + ((a0 >> 8) + (tid >> 4));
                 float* o = a.sums + tix * AMB_SUM_W;
                 o[0] = mxP + err; o[1] = fmaxf(mnA - err, 0.f); o[2] = mxA + err; o[3] = fmaxf(mnB - err, 0.f); o[4] = mxB + err;
@@ -367,10 +368,10 @@ __global__ void __launch_bounds__(256, 3) k_front(AmbFrontArgs a) {
                     a.st.tile_slot[tix] = slot;
                 }
             }
-            if (tid == 0 && a.st.defect) {
+            if (tid == 0 && a.st.defect && ((a.off0 + (int64_t)t * FT) & (AMB_TILE - 1)) == 0) {
                 // defect of the block boundary into this call: samples t0-512, t0-256, t0 (amb_walk_scan, lag branch)
-                const int64_t a0 = a.off0 + (int64_t)t * AMB_TILE;
-                const double xm1 = Rp[AMB_FR_PAD(AMB_TILE - 512)], x255 = Rp[AMB_FR_PAD(AMB_TILE - 256)], x511 = c[0];
+                const int64_t a0 = a.off0 + (int64_t)t * FT;
+                const double xm1 = Rp[AMB_FR_PAD(FT - 512)], x255 = Rp[AMB_FR_PAD(FT - 256)], x511 = c[0];
                 double* D = a.st.defect + ((int64_t)s * a.st.calls_stride + (a0 >> 12)) * 3;
                 D[0] = xm1 * x255 - x255 * x511; D[1] = xm1 * xm1 - x255 * x255; D[2] = x255 * x255 - x511 * x511;
             }
