@@ -231,15 +231,25 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
         mbar_wait(&xs_bar, xs_phase);
         xs_phase ^= 1u;
         if (sizeof(IN) == 4) {
+            // The staging buffer is linear, so the four 128-bit loads of a thread sit 64 bytes from its neighbour's: taken in
+            // the same order by everyone they would hit 2 of the 8 bank groups (4-way conflict).  Lane i starts at chunk
+            // (i >> 1) & 3 instead, which spreads a quarter-warp over all 8 groups, and puts the chunks back with selects.
             const float4* src = reinterpret_cast<const float4*>(XS + 16 * tid);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) { const float4 v = src[q4]; x[4 * q4] = v.x; x[4 * q4 + 1] = v.y; x[4 * q4 + 2] = v.z; x[4 * q4 + 3] = v.w; }
+            const int r = (tid >> 1) & 3;
+            float4 v0 = src[r], v1 = src[(r + 1) & 3], v2 = src[(r + 2) & 3], v3 = src[(r + 3) & 3];     // v_j = chunk (j + r) & 3
+            if (r & 2) { float4 t = v0; v0 = v2; v2 = t; t = v1; v1 = v3; v3 = t; }                       // rotate by two
+            if (r & 1) { const float4 t = v3; v3 = v2; v2 = v1; v1 = v0; v0 = t; }                        // rotate by one
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w; x[12] = v3.x; x[13] = v3.y; x[14] = v3.z; x[15] = v3.w;
         } else {
             // 16-bit PCM: s / 32768 is exact in float32 (what an audio front end hands the reference for a 16-bit capture)
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(XS) + 16 * tid);
+            const int r = (tid >> 2) & 1;                               // (same idea: 32-byte stride, two chunks per thread)
+            uint4 u0 = src[r], u1 = src[r ^ 1];
+            if (r) { const uint4 t = u0; u0 = u1; u1 = t; }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const uint4 v = src[h];
+                const uint4 v = h ? u1 : u0;
                 const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
