@@ -810,7 +810,7 @@ __device__ __forceinline__ float fd_spectrum(const AmbJob& J, int64_t p0, bool i
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
         float2 a = v[AMB_R16(k1)];
-        if (k1 > 0) a = cmulf(a, tw256[(l * k1) & 255]);
+        if (k1 > 0) a = cmulf(a, tw256[16 * k1 + l]);                 // W256^(l k1), row k1 of the [16][16] table: lanes read consecutive entries
         buf[k1 * AMB_FD_TSTRIDE + l] = a;
     }
     __syncwarp();
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- fast layout
     float2* hwbuf = reinterpret_cast<float2*>(smem_raw);                         // [16][AMB_FD_HWBUF]
-    float2* tw256 = hwbuf + AMB_FD_HW * AMB_FD_HWBUF;                            // [256]
+    float2* tw256 = hwbuf + AMB_FD_HW * AMB_FD_HWBUF;                            // [16][16] first-pass twiddles W256^(l k1)
     float2* Gq = tw256 + 256;                                                    // [bins] 0.5 conj(H)/|H|^2 (raw scale)
     float2* WG = Gq + AMB_FD_MAXBINS;                                            // [bins] 0.5 W512^k conj(H)/|H|^2
     float* cH = reinterpret_cast<float*>(WG + AMB_FD_MAXBINS);                   // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
     const int nthr = blockDim.x, nhw = nthr >> 4, nwarps = nthr >> 5;      // 5..8 warps: the launch picks the count that wastes the fewest symbol slots
-    for (int i = tid; i < 256; i += nthr) tw256[i] = FT->tw256[i];
+    for (int i = tid; i < 256; i += nthr) tw256[i] = FT->tw256[((i & 15) * (i >> 4)) & 255];     // [k1][l] = W256^(l k1): conflict-free rows for the first pass
     for (int i = tid; i < nb; i += nthr) role[i] = FT->role[i];
     if (tid < AMB_MAX_PILOTS) pilot_kk[tid] = FT->pilot_kk[tid];
     if (tid == 0) { s_mask[0] = 0u; s_mask[1] = 0u; s_all = 0; s_minhm_bits = 0x7f800000u; }
