@@ -130,7 +130,7 @@ struct AmbFrontArgs {
     AmbScanStore st;
 };
 
-#define AMB_FR_PAD(i) ((i) + (((i) >> 4) << 2))       // 4 floats of padding per 16: conflict-free 128-bit rows per thread
+#define AMB_FR_PAD(i) ((i) + (((i) >> 5) << 2))       // 4 floats of padding per 32: 128-bit accesses are conflict-free both per thread (16-float rows, 64 bytes apart) and consecutive
 #define AMB_FR_BUF AMB_FR_PAD(AMB_TILE)               // floats per padded tile buffer (5120)
 #define AMB_FRONT_SMEM(NT) ((2 * AMB_FR_PAD(16 * (NT)) + 16 * (NT)) * 4)   // two cleaned tiles (double buffer, padded) + one staged input tile (linear)
 
