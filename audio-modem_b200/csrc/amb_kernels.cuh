@@ -1984,7 +1984,8 @@ __global__ void __launch_bounds__(256) k_defect_scan(const double* __restrict__ 
 #define AMB_XC_MAXW (256 + 2 * 768)
 #define AMB_XC_PER 8
 #define AMB_XC_PADI(i) ((i) + (((i) >> 4) << 2))
-#define AMB_XC_SMEM(L) ((size_t)((L) + 2 * (AMB_XC_PADI(L) + 4) + 512) * 4 + (size_t)((L) + 1) * 8 + 64)
+#define AMB_XC_SQI(i) ((i) + ((i) >> 4))                 // prefix of squares: one double of padding per 16 (the epilogue reads it 16 apart)
+#define AMB_XC_SMEM(L) ((size_t)((L) + 2 * (AMB_XC_PADI(L) + 4) + 512) * 4 + (size_t)(AMB_XC_SQI(L) + 2) * 8 + 64)
 __device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
@@ -2000,7 +2001,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
     float* wu = sg + L;                                                // [LP] u, padded
     float* wv = wu + LP;                                               // [LP] u2, padded
     float* tp = wv + LP;                                               // [2][256] taps by offset parity: t[r], and t[r - 1] with the two single taps zeroed
-    double* SQ = reinterpret_cast<double*>(tp + 512);                  // [L + 1] prefix of squares
+    double* SQ = reinterpret_cast<double*>(tp + 512);                  // [AMB_XC_SQI(L) + 1] prefix of squares, padded
     __shared__ double wtot[8];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const float sign = (float)T->pre1_sign;
@@ -2041,8 +2042,8 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
         {
             double off = inc - ctot;
             for (int w = 0; w < warp; w++) off += wtot[w];
-            for (int i = c0; i < c1; i++) { SQ[i] = off; off = fma((double)sg[i], (double)sg[i], off); }
-            if (tid == nt - 1) SQ[L] = off;
+            for (int i = c0; i < c1; i++) { SQ[AMB_XC_SQI(i)] = off; off = fma((double)sg[i], (double)sg[i], off); }
+            if (tid == nt - 1) SQ[AMB_XC_SQI(L)] = off;
         }
         __syncthreads();                                               // u, u2, SQ complete; sg is free
         const int cur = slot;
@@ -2104,7 +2105,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
                 corr = fmaf(fv, wv[AMB_XC_PADI(bq + 2 * q + 256)], corr);
                 if (o >= xc_w || o >= o_hi) continue;
                 // metric = corr / sqrt(se tE) where that denominator clears 0.001 (squared: 1e-6), UNSURE within 2e-4 of it
-                const float d2 = (float)(SQ[o + plen] - SQ[o]) * tEf;
+                const float d2 = (float)(SQ[AMB_XC_SQI(o + plen)] - SQ[AMB_XC_SQI(o)]) * tEf;
                 float v;
                 if (d2 > 1e-6f * (1.f + 2e-4f)) v = corr * rsqrtf(d2);
                 else if (d2 < 1e-6f * (1.f - 2e-4f)) v = AMB_XC_FAIL;
