@@ -403,7 +403,7 @@ __device__ __forceinline__ double warp_excl_scan(double v, int lane, double* tot
     return inc - v;
 }
 
-__global__ void __launch_bounds__(128, 5) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
+__global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
     const int lane = threadIdx.x & 31;
     const int n_slots = min(*st.slot_count, st.slot_cap);
     for (int slot = blockIdx.x * 4 + (threadIdx.x >> 5); slot < n_slots; slot += gridDim.x * 4) {
