@@ -127,6 +127,52 @@ napi_value DecodeOne(napi_env env, napi_callback_info info) {
     return result_object(env, r, bytes.data());
 }
 
+// streamPushPCM16(handle, Int16Array[nStreams*nNew], nNew, bytesStride) -> result[]  (amb_stream_push_pcm16)
+napi_value StreamPushPCM16(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value a[4];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; if (!get_modem(env, a[0], &m)) return nullptr;
+    napi_typedarray_type tt; size_t n = 0; void* x = nullptr;
+    NAPI_CALL(env, napi_get_typedarray_info(env, a[1], &tt, &n, &x, nullptr, nullptr));
+    if (tt != napi_int16_array) { napi_throw_type_error(env, nullptr, "Int16Array expected"); return nullptr; }
+    int64_t n_new = 0, stride = 0; napi_get_value_int64(env, a[2], &n_new); napi_get_value_int64(env, a[3], &stride);
+    const int max_res = 4096;
+    std::vector<amb_frame_result> res(max_res);
+    std::vector<uint8_t> bytes((size_t)max_res * (size_t)stride);
+    int got = 0;
+    const int rc = amb_stream_push_pcm16(m, (const int16_t*)x, n_new, n_new, AMB_MEM_HOST, res.data(), max_res, &got, bytes.data(), stride, AMB_MEM_HOST);
+    if (rc != AMB_OK && rc != AMB_E_OVERFLOW) { napi_throw_error(env, nullptr, amb_last_error(m)); return nullptr; }
+    napi_value arr; napi_create_array_with_length(env, (size_t)(got < max_res ? got : max_res), &arr);
+    for (int i = 0; i < got && i < max_res; i++) {
+        napi_value o = result_object(env, res[i], bytes.data() + (size_t)i * (size_t)stride);
+        set_num(env, o, "stream", res[i].stream);
+        napi_set_element(env, arr, (uint32_t)i, o);
+    }
+    return arr;
+}
+
+// buildTransmitSignal(handle, Uint8Array fileData, string fileName) -> {signal: Float32Array, dataLen}  (modem.js:498-555)
+napi_value BuildTransmitSignal(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; if (!get_modem(env, a[0], &m)) return nullptr;
+    napi_typedarray_type tt; size_t n = 0; void* d = nullptr;
+    NAPI_CALL(env, napi_get_typedarray_info(env, a[1], &tt, &n, &d, nullptr, nullptr));
+    char name[768]; size_t name_len = 0;
+    NAPI_CALL(env, napi_get_value_string_utf8(env, a[2], name, sizeof(name), &name_len));
+    const int64_t len = amb_transmit_signal_samples(m, (int64_t)n, (int)name_len);
+    void* out = nullptr; napi_value ab, sig, o;
+    NAPI_CALL(env, napi_create_arraybuffer(env, (size_t)len * 4, &out, &ab));
+    if (amb_build_transmit_signals(m, (const uint8_t*)d, (int64_t)n, (int)n, 1, (const uint8_t*)name, (int)name_len, (float*)out, len, AMB_MEM_HOST) != AMB_OK) {
+        napi_throw_error(env, nullptr, amb_last_error(m)); return nullptr;
+    }
+    NAPI_CALL(env, napi_create_typedarray(env, napi_float32_array, (size_t)len, ab, 0, &sig));
+    napi_create_object(env, &o);
+    napi_set_named_property(env, o, "signal", sig);
+    set_num(env, o, "dataLen", (double)n);
+    return o;
+}
+
 // analyzeLoopback(handle, Float32Array recorded, Uint8Array testData) -> {detected, correlation, ber, channelMagnitude, snrEstimate, quality}
 napi_value AnalyzeLoopback(napi_env env, napi_callback_info info) {
     size_t argc = 3; napi_value a[3];
@@ -189,6 +235,8 @@ napi_value Init(napi_env env, napi_value exports) {
         {"decodeReceivedSignal", nullptr, DecodeOne<amb_decode_received_signals>, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"decodeChunkFrame", nullptr, DecodeOne<amb_decode_chunk_frames>, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"analyzeLoopback", nullptr, AnalyzeLoopback, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"streamPushPCM16", nullptr, StreamPushPCM16, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"buildTransmitSignal", nullptr, BuildTransmitSignal, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamOpen", nullptr, StreamOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamPush", nullptr, StreamPush, nullptr, nullptr, nullptr, napi_default, nullptr},
     };

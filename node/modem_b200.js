@@ -24,6 +24,11 @@ module.exports = {
   decodeReceivedSignal(signal, modName, repetition) { return addon.decodeReceivedSignal(modem(modName, repetition), Float32Array.from(signal)); },
   decodeChunkFrame(frameSamples, modName, repetition) { return addon.decodeChunkFrame(modem(modName, repetition), Float32Array.from(frameSamples)); },
   analyzeLoopback(recorded, modName, repetition, testData) { return addon.analyzeLoopback(modem(modName, repetition), Float32Array.from(recorded), Uint8Array.from(testData)); },
+  buildTransmitSignal(fileData, modName, fileName, repetition) { return addon.buildTransmitSignal(modem(modName, repetition), Uint8Array.from(fileData), fileName || 'file'); },
+  generateTestSignal(modName, repetition) {
+    const testData = Uint8Array.from({ length: 16 }, (_, i) => i);
+    return { signal: addon.buildTransmitSignal(modem(modName, repetition), testData, 'test').signal, testData };
+  },
   // app.js:706-981 without DOM / IndexedDB: processAudioBlock returns the frames it completed
   StreamingReceiver: class {
     constructor(modName, repetition) {
@@ -32,5 +37,7 @@ module.exports = {
       this.bytesStride = 8192;
     }
     processAudioBlock(inputSamples) { return addon.streamPush(this.h, Float32Array.from(inputSamples), inputSamples.length, this.bytesStride); }
+    // the same block as the 16-bit PCM a capture device delivers (sample = s / 32768): half the bytes across the bus
+    processAudioBlockPCM16(int16Samples) { return addon.streamPushPCM16(this.h, Int16Array.from(int16Samples), int16Samples.length, this.bytesStride); }
   },
 };
