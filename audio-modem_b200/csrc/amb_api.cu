@@ -70,7 +70,7 @@ struct amb_modem {
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
-    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum;
+    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
@@ -370,7 +370,7 @@ void amb_destroy(amb_modem* m) {
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
                      &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
@@ -767,7 +767,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     const int64_t tiles_per_push = (max_push / 256) * n_streams;
     m->slot_cap = (int)(tiles_per_push / 8 + 64 < 2000000 ? tiles_per_push / 8 + 64 : 2000000);
     CK(m->tile_slot.ensure(ns * m->sum_stride * 4)); CK(m->tri.ensure((size_t)m->slot_cap * 256 * 3 * 8));
-    CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16)); CK(m->tsum.ensure((size_t)m->slot_cap * 16));
+    CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16)); CK(m->tsum.ensure((size_t)m->slot_cap * 16)); CK(m->cand_list.ensure((size_t)m->slot_cap * 4));
     CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8));
     CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
@@ -810,7 +810,7 @@ int amb_stream_close(amb_modem* m) {
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
                      &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
-                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum,
+                     &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
                      &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
@@ -866,10 +866,10 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
-    ss.tsum = m->tsum.as<float>();
+    ss.tsum = m->tsum.as<float>(); ss.cand_list = m->cand_list.as<int32_t>();
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
-    CK(cudaMemsetAsync(m->slot_count.p, 0, 4, m->stream));
+    CK(cudaMemsetAsync(m->slot_count.p, 0, 8, m->stream));          // [0] slots, [1] slots holding a candidate
     {
         // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
         AmbFrontArgs fa;
@@ -918,11 +918,12 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         const size_t smem = AMB_XC_SMEM(L);
         int threads = ((m->xc_w + 15) / 16 + 15) / 16 * 32;               // a warp takes 16 blocks of 16 offsets (8 per lane, by parity)
         if (threads > 256) threads = 256;
-        // many short-lived CTAs: the candidate slots are sparse in the slot list (about one in four), so a CTA of a small grid
-        // strides over a very uneven share of them (measured: 148 x 128 CTAs 0.48 ms, 148 x 16 CTAs 0.54 ms per 33 k slots)
+        // the CTAs stride over the compact list of candidate slots (k_tri_store): even shares, and each CTA prefetches its
+        // next slot while it works on the current one
+        // (measured per 33 k candidate slots: 148 x 8 CTAs 0.49 ms, x 16 0.45, x 32 0.43, x 64 0.42, x 128 0.41)
         const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
         LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
-                                                                                     m->slot_count.as<int>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
+                                                                                     m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
     }
     int n_out = 0;
     int n_todo = ns;

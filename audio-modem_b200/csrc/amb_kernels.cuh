@@ -98,6 +98,7 @@ struct AmbScanStore {
     int* slot_count;
     int slot_cap;
     float* tsum;             // [slot_cap][4] exact extremes of the slot's windows (amb_slot_cold)
+    int32_t* cand_list;      // [slot_cap] slots holding a candidate, in no particular order; their number is slot_count[1]
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
@@ -487,7 +488,10 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
-        if (lane == 0) { st.slot_info[slot * 4 + 2] = any; st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16); }     // candidate windows span [c_lo, c_hi]
+        if (lane == 0) {
+            st.slot_info[slot * 4 + 2] = any; st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16);      // candidate windows span [c_lo, c_hi]
+            if (any && st.cand_list) st.cand_list[atomicAdd(st.slot_count + 1, 1)] = slot;
+        }
     }
 }
 
@@ -1990,10 +1994,10 @@ __device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
 __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
-                                                      const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count, int slot_cap,
-                                                      float* __restrict__ xc, int xc_w) {
+                                                      const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count,
+                                                      const int32_t* __restrict__ cand_list, int slot_cap, float* __restrict__ xc, int xc_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n_slots = min(*slot_count, slot_cap);
+    const int n_cand = min(slot_count[1], slot_cap);
     const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
     const int L = xc_w + plen;                                         // samples needed (multiple of 16 for every config)
     const int LP = AMB_XC_PADI(L) + 4;
@@ -2013,15 +2017,15 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
     }
     const float t_last_u = split > 0 ? T->pre1[cp + split - 1] : 0.f, t_last = T->pre1[cp + 255];
     const int64_t lo = g.base_g > 0 ? g.base_g : 0;
-    int slot = blockIdx.x;
-    while (slot < n_slots && !slot_info[slot * 4 + 2]) slot += gridDim.x;
-    if (slot < n_slots) {
+    int ci = blockIdx.x;
+    int slot = ci < n_cand ? cand_list[ci] : -1;
+    if (slot >= 0) {
         const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
         const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
         for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    while (slot < n_slots) {
+    while (slot >= 0) {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                                               // sg holds this slot's samples; the previous slot's readers of u, u2, SQ are done
         for (int i = tid; i < L; i += nt) {
@@ -2047,9 +2051,9 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
         }
         __syncthreads();                                               // u, u2, SQ complete; sg is free
         const int cur = slot;
-        slot += gridDim.x;
-        while (slot < n_slots && !slot_info[slot * 4 + 2]) slot += gridDim.x;
-        if (slot < n_slots) {
+        ci += gridDim.x;
+        slot = ci < n_cand ? cand_list[ci] : -1;
+        if (slot >= 0) {
             const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
             const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
             for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
