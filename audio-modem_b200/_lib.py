@@ -43,11 +43,8 @@ EXPORTS = {
     "amb_synchronize": (C.c_int, [C.c_void_p]),
     "amb_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "amb_kernel_launches": (C.c_int64, [C.c_void_p]),
-    "amb_debug_read": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
-    "amb_debug_counter": (C.c_int64, [C.c_void_p, C.c_int]),
     "amb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "amb_host_free": (C.c_int, [C.c_void_p]),
-    "amb_selftest": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
     "amb_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "amb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
     "amb_estimate_frame_samples": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
@@ -77,11 +74,19 @@ EXPORTS = {
     "amb_stream_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
     "amb_transmit_signal_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
     "amb_build_transmit_signals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
+    "amb_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int]),
     "amb_chunk_frame_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
     "amb_build_data_chunk_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int32, C.c_uint64, C.c_void_p,
                                               C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_int]),
     "amb_build_metadata_frame": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
                                            C.c_uint64, C.c_int64, C.c_int]),
+}
+
+# development entry points (audio-modem_b200/csrc/amb_private.h): exported by the library, not part of the boundary header
+PRIVATE_EXPORTS = {
+    "amb_debug_read": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "amb_debug_counter": (C.c_int64, [C.c_void_p, C.c_int]),
+    "amb_selftest": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -99,7 +104,7 @@ def load():
             raise AmbError(f"{_build.LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(nvcc, sm_100a). The package has no CPU or PyTorch fallback.")
         L = C.CDLL(_build.LIB)
-        for name, (res, args) in EXPORTS.items():
+        for name, (res, args) in list(EXPORTS.items()) + list(PRIVATE_EXPORTS.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

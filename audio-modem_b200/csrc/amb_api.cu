@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "amb_kernels.cuh"
+#include "amb_private.h"
 
 namespace {
 
@@ -51,6 +52,10 @@ struct amb_modem {
     unsigned long long* d_fallbacks = nullptr;
     uint32_t* d_crc_ops = nullptr;       // [AMB_CRC_MAXL][AMB_CRC_OPS] powers of x mod P, the CRC combine constants per chunk length L
     bool fast_demod = true;
+    // AMB_FUSE_PARSE=1: single-group frames are demodulated, packed, parsed and checksummed by one CTA (k_demod_fast<.., true>).
+    // Measured on C2 (16,384 frames): 1.04 ms fused against 0.81 + 0.14 ms for k_demod_fast + k_parse - the serial tail of a
+    // 7-warp CTA hides worse than a separate 128-thread kernel does - so the two-kernel form stays the default.
+    bool fuse_parse = false;
     std::string err;
     int64_t launches = 0;
     // optional per-kernel device timing (CUDA events on the handle's stream)
@@ -171,11 +176,20 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     if (n_jobs == 0) return AMB_OK;
     const AmbTables& T = m->tables;
     const int64_t idx_stride = ((int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data + 15) / 16 * 16;      // rows 16-byte aligned for k_parse's vector loads
-    CK(m->idx.ensure((size_t)n_jobs * idx_stride));
+    const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
+    // one CTA per frame does everything (demodulate, vote, pack, parse, CRC-32) when the frame is a single symbol group whose
+    // constellation indices fit in shared memory; longer frames go through the index array in HBM and k_parse
+    const bool fused = m->fast_demod && m->fuse_parse && groups == 1 && (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data <= AMB_FD_IDX_CAP;
+    // a decoded frame longer than k_parse's shared-memory staging is packed straight into the caller's row, which must hold it
+    if (!fused && amb_num_bytes((int64_t)(max_nsym > 0 ? max_nsym : 0) * T.n_data, T.bps, T.rep) > AMB_PARSE_SMEM &&
+        bytes_stride < amb_num_bytes((int64_t)max_nsym * T.n_data, T.bps, T.rep))
+        return fail(m, AMB_E_INVALID, "bytes_stride smaller than the decoded frame");
+    if (!fused) CK(m->idx.ensure((size_t)n_jobs * idx_stride));
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));
-    o.idx = m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
-    const int groups = max_nsym > 0 ? (max_nsym + AMB_SYM_GROUP - 1) / AMB_SYM_GROUP : 1;
+    o.idx = fused ? nullptr : m->idx.as<uint8_t>(); o.idx_stride = idx_stride;
+    AmbParseOut po;
+    po.results = d_res; po.bytes_out = d_bytes; po.bytes_stride = bytes_stride; po.crc_ops = m->d_crc_ops;
     if (m->fast_demod) {
         // float32 symbol pipeline with margin guard and float64-faithful fallback; gathers the per-frame peak itself when one
         // CTA covers the whole frame
@@ -189,24 +203,26 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
             for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 1 + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
         }
         // instantiated per constellation and per CTA size class (7 warps or fewer leave registers for a fourth resident CTA)
-#define AMB_DEMOD_LAUNCH(MODV, NTV) \
-    LAUNCH("k_demod_fast", (k_demod_fast<MODV, NTV><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM, m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks)))
-        if (nw <= 7) {
-            if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, 224); }
-            else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, 224); }
-            else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, 224); }
-        } else {
-            if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, 256); }
-            else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, 256); }
-            else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, 256); }
-        }
+#define AMB_DEMOD_LAUNCH(MODV, NTV, FUSEDV) \
+    LAUNCH("k_demod_fast", (k_demod_fast<MODV, NTV, FUSEDV><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM(NTV, FUSEDV), m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks, po)))
+#define AMB_DEMOD_LAUNCH_MOD(NTV, FUSEDV) \
+    do { \
+        if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, NTV, FUSEDV); } \
+        else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, NTV, FUSEDV); } \
+        else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, NTV, FUSEDV); } \
+    } while (0)
+        if (nw <= 7) { if (fused) AMB_DEMOD_LAUNCH_MOD(224, true); else AMB_DEMOD_LAUNCH_MOD(224, false); }
+        else { if (fused) AMB_DEMOD_LAUNCH_MOD(256, true); else AMB_DEMOD_LAUNCH_MOD(256, false); }
+#undef AMB_DEMOD_LAUNCH_MOD
 #undef AMB_DEMOD_LAUNCH
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
     }
-    LAUNCH("k_parse", k_parse<<<n_jobs < 65536 ? n_jobs : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
-                                                          d_res, d_bytes, bytes_stride, m->d_crc_ops));
+    if (!fused) {
+        LAUNCH("k_parse", k_parse<<<n_jobs < 65536 ? n_jobs : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
+                                                              d_res, d_bytes, bytes_stride, m->d_crc_ops));
+    }
     return AMB_OK;
 }
 
@@ -337,13 +353,24 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         if (cudaMemcpy(m->d_crc_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail(AMB_E_CUDA);
         const char* e = std::getenv("AMB_FAST_DEMOD");
         m->fast_demod = !(e && e[0] == '0');
+        const char* fz = std::getenv("AMB_FUSE_PARSE");
+        m->fuse_parse = fz && fz[0] == '1';
     }
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_BPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QPSK, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
-    cudaFuncSetAttribute(k_demod_fast<AMB_MOD_QAM16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM);
+#define AMB_DEMOD_ATTR(MODV) \
+    cudaFuncSetAttribute(k_demod_fast<MODV, 224, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM(224, false)); \
+    cudaFuncSetAttribute(k_demod_fast<MODV, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM(256, false)); \
+    cudaFuncSetAttribute(k_demod_fast<MODV, 224, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM(224, true)); \
+    cudaFuncSetAttribute(k_demod_fast<MODV, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_FAST_SMEM(256, true));
+    AMB_DEMOD_ATTR(AMB_MOD_BPSK) AMB_DEMOD_ATTR(AMB_MOD_QPSK) AMB_DEMOD_ATTR(AMB_MOD_QAM16)
+#undef AMB_DEMOD_ATTR
+    if (std::getenv("AMB_DEBUG_OCC")) {
+        int o1 = 0, o2 = 0, o3 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_demod_fast<AMB_MOD_QAM16, 224, false>, 224, AMB_DEMOD_FAST_SMEM(224, false));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_demod_fast<AMB_MOD_QAM16, 224, true>, 224, AMB_DEMOD_FAST_SMEM(224, true));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_front<float, 128>, 128, AMB_FRONT_SMEM(128));
+        std::fprintf(stderr, "occupancy (CTAs/SM): demod 224 unfused %d, fused %d (dynamic smem %d / %d), front %d\n", o1, o2, (int)AMB_DEMOD_FAST_SMEM(224, false),
+                     (int)AMB_DEMOD_FAST_SMEM(224, true), o3);
+    }
     {
         int occ = 0, sms = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk, 128, 0) == cudaSuccess && occ > 0 &&
@@ -358,6 +385,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
+    cudaFuncSetAttribute(k_modulate, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
     *out = m;
     return AMB_OK;
 }
@@ -414,7 +442,7 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
         std::vector<int32_t> info((size_t)n * 4);
         if (n > 0) cudaMemcpy(info.data(), m->slot_info.p, (size_t)n * 16, cudaMemcpyDeviceToHost);
         int64_t c = 0;
-        for (int i = 0; i < n; i++) c += info[(size_t)i * 4 + 2] != 0;
+        for (int i = 0; i < n; i++) c += (info[(size_t)i * 4 + 2] & AMB_SLOT_CAND) != 0;
         return c;
     }
     return -1;
@@ -864,7 +892,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     if (off0 + n_new > m->stride) return fail(m, AMB_E_STATE, "arena overflow (internal)");
     const int tiles = (int)(n_new / AMB_TILE);
     AmbScanStore ss;
-    ss.tile_slot = m->tile_slot.as<int32_t>(); ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
+    ss.tile_slot = m->tile_slot.as<int32_t>(); ss.sum_stride = m->sum_stride; ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
     ss.tsum = m->tsum.as<float>(); ss.cand_list = m->cand_list.as<int32_t>();
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
@@ -1243,6 +1271,32 @@ int amb_build_transmit_signals(amb_modem* m, const uint8_t* data, int64_t data_s
     legacy_silences(m->tables, &pre, &post);
     if ((rc = tx_run(m, m->tx_pay.as<uint8_t>(), pay_len, pay_len, n, 1, out, out_stride, 0.0, 0, 0, mem, pre, post))) return rc;
     return flush(m);        // synchronises: `pay` stays alive until the copy has run
+}
+
+int amb_modulate(amb_modem* m, uint8_t* bits, int64_t bits_stride, int64_t n_bits, int n, float* samples, int64_t samples_stride, int32_t* out3,
+                 int mem) {
+    int rc = check_common(m, n, bits_stride, mem); if (rc) return rc;
+    const AmbTables& T = m->tables;
+    const int64_t per = (int64_t)T.n_data * T.bps;                     // bitsPerSymbol, modem.js:326
+    if (n_bits < 0 || n_bits > bits_stride) return fail(m, AMB_E_INVALID, "n_bits outside the row");
+    const int64_t nsym = (n_bits + per - 1) / per, padded = nsym * per;
+    if (out3) { out3[0] = (int32_t)nsym; out3[1] = (int32_t)per; out3[2] = (int32_t)padded; }
+    if (n == 0 || nsym == 0) return AMB_OK;
+    if (!bits || !samples || samples_stride < nsym * T.sym_len) return fail(m, AMB_E_INVALID, "bits/samples required; samples_stride >= numSymbols * SYMBOL_LEN");
+    if (nsym * n > 0x7fffffff / 2) return fail(m, AMB_E_INVALID, "too many symbols in one call");
+    // the reference pads its caller's array in place (modem.js:329); done here when the row has room for the padding
+    const int pad_rows = bits_stride >= padded ? 1 : 0;
+    uint8_t* d_bits = bits; float* d_out = samples;
+    if (mem == AMB_MEM_HOST) {
+        CK(m->in_a.ensure((size_t)n * bits_stride));
+        CK(cudaMemcpyAsync(m->in_a.p, bits, (size_t)n * bits_stride, cudaMemcpyHostToDevice, m->stream));
+        d_bits = m->in_a.as<uint8_t>();
+        if ((rc = out_ptr(m, samples, (size_t)n * samples_stride, mem, m->tx_out, &d_out))) return rc;
+        if (pad_rows) m->pending.push_back({bits, m->in_a.p, (size_t)n * bits_stride});
+    }
+    const int64_t groups = (nsym + AMB_TX_WARPS - 1) / AMB_TX_WARPS;
+    LAUNCH("k_modulate", k_modulate<<<(unsigned)(n * groups), 256, AMB_TX_SMEM, m->stream>>>(m->d_tables, d_bits, bits_stride, n_bits, n, nsym, d_out, samples_stride, pad_rows));
+    return flush(m);
 }
 
 int amb_stream_enable_assembly(amb_modem* m, int64_t max_file_bytes) {

@@ -446,6 +446,108 @@ AMB_HD void amb_parse_received(const uint32_t* crc_table, const uint8_t* bytes, 
     r->frame_type = AMB_FRAME_LEGACY;
 }
 
+#if defined(__CUDACC__)
+// Exact float64 window sums of 256 consecutive windows from 768 samples held by one warp: lane l holds samples
+// 256 seg + 8 l + k (seg < 3, k < 8) of the span that starts at the first window; on return oP/oA/oB[k] are P, Ra, Rb of
+// window 8 l + k.  Exclusive float64 prefixes of x^2 and x[i] x[i+256] inside each 256-sample segment (registers + one warp
+// scan per segment and array); the window starting at 8 l + k needs exactly the lane's own prefix values.
+__device__ __forceinline__ double amb_warp_excl_scan(double v, int lane, double* total) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ void amb_tile_sums_regs(const float (&x)[3][8], int lane, double* oP, double* oA, double* oB) {
+    double q[3][8], t[2][8], qb[3], tb[2];       // exclusive prefixes inside the segment; global base of the segment
+    double run_q = 0.0, run_t = 0.0;
+#pragma unroll
+    for (int seg = 0; seg < 3; seg++) {
+        double lq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fma((double)x[seg][k], (double)x[seg][k], lq); }
+        double tot;
+        const double off = amb_warp_excl_scan(lq, lane, &tot);
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[seg][k] += off;
+        qb[seg] = run_q; run_q += tot;
+        if (seg < 2) {
+            double lt = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fma((double)x[seg][k], (double)x[seg + 1][k], lt); }
+            const double offt = amb_warp_excl_scan(lt, lane, &tot);
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[seg][k] += offt;
+            tb[seg] = run_t; run_t += tot;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
+        oP[k] = (tb[1] + t[1][k]) - (tb[0] + t[0][k]);
+        oA[k] = (qb[1] + q[1][k]) - (qb[0] + q[0][k]);
+        oB[k] = (qb[2] + q[2][k]) - (qb[1] + q[1][k]);
+    }
+}
+#endif
+
+#if defined(__CUDACC__)
+// cnt > 8 consecutive windows from d0, in blocks of 256: lane l owns the 8 windows 8 l .. 8 l + 7 of a block and needs the
+// exclusive float64 prefixes of x^2 (three 256-sample segments) and x[i] x[i+256] (two) at its first sample.  Pass 1 sums
+// the lane's own 8 samples per segment, five warp scans turn the sums into those prefixes, pass 2 walks the 8 samples again
+// (reloaded: they sit in L1) with five running sums and writes the window sums.  Few live registers on purpose: the walker
+// kernels that inline this are register-bound.
+__device__ __forceinline__ void amb_window_sums_blocks(const float* sp, int64_t sbase, int64_t slo, int64_t shi, int64_t d0, int cnt, double* P, double* A, double* B) {
+    const int lane = threadIdx.x & 31;
+    for (int b0 = 0; b0 < cnt; b0 += 256) {
+        const int64_t g0 = d0 + b0 + 8 * lane;                     // this lane's first sample in segment 0
+        const bool inside = d0 + b0 >= slo && d0 + b0 + 768 <= shi;
+        const float* pa = sp + (g0 - sbase);
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            float x0, x1, x2;
+            if (inside) { x0 = pa[k]; x1 = pa[256 + k]; x2 = pa[512 + k]; }
+            else {
+                const int64_t g = g0 + k;
+                x0 = (g >= slo && g < shi) ? sp[g - sbase] : 0.f;
+                x1 = (g + 256 >= slo && g + 256 < shi) ? sp[g + 256 - sbase] : 0.f;
+                x2 = (g + 512 >= slo && g + 512 < shi) ? sp[g + 512 - sbase] : 0.f;
+            }
+            q0 = fma((double)x0, (double)x0, q0); q1 = fma((double)x1, (double)x1, q1); q2 = fma((double)x2, (double)x2, q2);
+            t0 = fma((double)x0, (double)x1, t0); t1 = fma((double)x1, (double)x2, t1);
+        }
+        // exclusive prefixes over the lanes; segment totals of x^2 (segment 0, 1) and of the cross products (segment 0)
+        double e0 = q0, e1 = q1, e2 = q2, f0 = t0, f1 = t1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u0 = __shfl_up_sync(0xffffffffu, e0, o), u1 = __shfl_up_sync(0xffffffffu, e1, o), u2 = __shfl_up_sync(0xffffffffu, e2, o);
+            const double v0 = __shfl_up_sync(0xffffffffu, f0, o), v1 = __shfl_up_sync(0xffffffffu, f1, o);
+            if (lane >= o) { e0 += u0; e1 += u1; e2 += u2; f0 += v0; f1 += v1; }
+        }
+        const double Q0 = __shfl_sync(0xffffffffu, e0, 31), Q1 = __shfl_sync(0xffffffffu, e1, 31), T0 = __shfl_sync(0xffffffffu, f0, 31);
+        // running prefixes at the lane's first window: S_q[256 seg + w], S_t[256 seg + w]
+        double pq0 = e0 - q0, pq1 = Q0 + (e1 - q1), pq2 = Q0 + Q1 + (e2 - q2), pt0 = f0 - t0, pt1 = T0 + (f1 - t1);
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            const int i = b0 + 8 * lane + k;
+            if (i < cnt) { P[i] = pt1 - pt0; A[i] = pq1 - pq0; B[i] = pq2 - pq1; }
+            float x0, x1, x2;
+            if (inside) { x0 = pa[k]; x1 = pa[256 + k]; x2 = pa[512 + k]; }
+            else {
+                const int64_t g = g0 + k;
+                x0 = (g >= slo && g < shi) ? sp[g - sbase] : 0.f;
+                x1 = (g + 256 >= slo && g + 256 < shi) ? sp[g + 256 - sbase] : 0.f;
+                x2 = (g + 512 >= slo && g + 512 < shi) ? sp[g + 512 - sbase] : 0.f;
+            }
+            pq0 = fma((double)x0, (double)x0, pq0); pq1 = fma((double)x1, (double)x1, pq1); pq2 = fma((double)x2, (double)x2, pq2);
+            pt0 = fma((double)x0, (double)x1, pt0); pt1 = fma((double)x1, (double)x2, pt1);
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Schmidl-Cox window sums at `cnt` consecutive offsets d0.. (modem.js:292-298 evaluated directly at
 // every offset, float64, exact products of float32 samples): P = sum s[d+m]s[d+m+256],
@@ -473,6 +575,9 @@ AMB_HD void amb_window_sums(const AmbSig& s, int64_t d0, int cnt, double* P, dou
         AMB_WARP_SYNC();
         return;
     }
+#if defined(__CUDA_ARCH__) && !defined(AMB_NO_FAST_WS)
+    if (s.xf.kind == AMB_XF_NONE) { amb_window_sums_blocks(s.p, s.base, s.lo, s.hi, d0, cnt, P, A, B); return; }
+#endif
     const int chunks = (cnt + 7) / 8;
     AMB_WARP_FOR(c, chunks) {
         const int i0 = c * 8;

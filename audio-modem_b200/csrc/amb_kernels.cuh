@@ -93,6 +93,7 @@ __device__ __forceinline__ void block_prefix(const float* c, double* ST, double*
 // Stores the scan front end (k_front) and the exact-sum kernel (k_tri_store) fill for the walker.
 struct AmbScanStore {
     int32_t* tile_slot;      // [n_streams][sum_stride]
+    int64_t sum_stride;
     double* tri;             // [slot_cap][3][256]
     int32_t* slot_info;      // [slot_cap][4]: stream, arena tile, has-candidate (k_tri_store), unused
     int* slot_count;
@@ -393,17 +394,12 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
 }
 
 // Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
-// (metric > 0.5 with the 0.001 energy gate, no defect).  One WARP per slot, everything in registers: lane l holds
-// samples 256 seg + 8 l + k (seg < 3, k < 8) of the tile's 768-sample span and their exclusive float64 prefixes of x^2
-// and x[i] x[i+256]; the window starting at 8 l + k needs exactly the lane's own three prefix values.
-__device__ __forceinline__ double warp_excl_scan(double v, int lane, double* total) {
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    *total = __shfl_sync(0xffffffffu, inc, 31);
-    return inc - v;
-}
-
+// (metric > 0.5 with the 0.001 energy gate, no defect).  One WARP per slot, everything in registers
+// (amb_tile_sums_regs, amb_device.cuh).  The float64 rows are written only for the slots the walker may have to evaluate
+// (slot_info[2] bit 1): the ones holding a candidate, a window left out of the extremes, or a maximum metric above 0.2.
+// The rest (most of them: the zero-padded last symbol of a chunk and the silence after it, flagged by the conservative
+// tile summary) are settled by their extremes alone (amb_slot_cold); should a large carried defect make the walker want
+// such a tile after all, it evaluates the windows itself (amb_eval_windows).
 __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
     const int lane = threadIdx.x & 31;
     const int n_slots = min(*st.slot_count, st.slot_cap);
@@ -428,41 +424,16 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
         }
-        double q[3][8], t[2][8], qb[3], tb[2];       // exclusive prefixes inside the segment; global base of the segment
-        double run_q = 0.0, run_t = 0.0;
-#pragma unroll
-        for (int seg = 0; seg < 3; seg++) {
-            double lq = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fma((double)x[seg][k], (double)x[seg][k], lq); }
-            double tot;
-            const double off = warp_excl_scan(lq, lane, &tot);
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[seg][k] += off;
-            qb[seg] = run_q; run_q += tot;
-            if (seg < 2) {
-                double lt = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fma((double)x[seg][k], (double)x[seg + 1][k], lt); }
-                const double offt = warp_excl_scan(lt, lane, &tot);
-#pragma unroll
-                for (int k = 0; k < 8; k++) t[seg][k] += offt;
-                tb[seg] = run_t; run_t += tot;
-            }
-        }
-        double* o = st.tri + (int64_t)slot * 768 + 8 * lane;                 // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
-        int cand = 0, c_lo = 255, c_hi = 0, excluded = 0;
         double oP[8], oA[8], oB[8];
+        amb_tile_sums_regs(x, lane, oP, oA, oB);
+        int cand = 0, c_lo = 255, c_hi = 0, excluded = 0;
         float mmax = 0.f;                                 // over the windows with Ra, Rb > 0.0005 (amb_slot_cold); float: rounded up below
         double mnA = 1.0, mnB = 1.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            // prefix S[256 seg + w] = base[seg] + prefix[seg][k],  w = 8 lane + k
-            const double P = (tb[1] + t[1][k]) - (tb[0] + t[0][k]);
-            const double A = (qb[1] + q[1][k]) - (qb[0] + q[0][k]);
-            const double B = (qb[2] + q[2][k]) - (qb[1] + q[1][k]);
             const bool valid = base_g + a_first + 8 * lane + k >= 0;
-            oP[k] = valid ? P : 0.0; oA[k] = valid ? A : 0.0; oB[k] = valid ? B : 0.0;
+            const double P = valid ? oP[k] : 0.0, A = valid ? oA[k] : 0.0, B = valid ? oB[k] : 0.0;
+            oP[k] = P; oA[k] = A; oB[k] = B;
             const bool c = valid && A > 0.001 && B > 0.001 && P * P > 0.5 * A * B;
             cand |= c;
             if (valid && A > 0.0005 && B > 0.0005) { mnA = fmin(mnA, A); mnB = fmin(mnB, B); mmax = fmaxf(mmax, (float)(P * P) / (float)(A * B)); }
@@ -470,16 +441,18 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
             if (c) { c_lo = min(c_lo, 8 * lane + k); c_hi = max(c_hi, 8 * lane + k); }
         }
         const int any = __any_sync(0xffffffffu, cand);
-        // (the rows are kept for every slot: the walker skips most non-candidate tiles by their extremes (amb_slot_cold), but a
-        // large defect - long idle stretches over a noise floor - defeats that test and the tile is then evaluated from its rows)
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
-            *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
-            *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
-        }
         mmax = warp_maxf(mmax);
         const int any_excluded = __any_sync(0xffffffffu, excluded);
+        const bool rows = any || any_excluded || mmax > 0.2f;
+        if (rows) {
+            double* o = st.tri + (int64_t)slot * 768 + 8 * lane;             // [slot][P | Ra | Rb][256]: 64 contiguous bytes per lane and array
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                *reinterpret_cast<double2*>(o + k) = make_double2(oP[k], oP[k + 1]);
+                *reinterpret_cast<double2*>(o + 256 + k) = make_double2(oA[k], oA[k + 1]);
+                *reinterpret_cast<double2*>(o + 512 + k) = make_double2(oB[k], oB[k + 1]);
+            }
+        }
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) { mnA = fmin(mnA, __shfl_xor_sync(0xffffffffu, mnA, o2)); mnB = fmin(mnB, __shfl_xor_sync(0xffffffffu, mnB, o2)); }
         if (lane == 0 && st.tsum) {
@@ -489,7 +462,9 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o)); }
         if (lane == 0) {
-            st.slot_info[slot * 4 + 2] = any; st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16);      // candidate windows span [c_lo, c_hi]
+            st.slot_info[slot * 4 + 2] = (any ? AMB_SLOT_CAND : 0) | (rows ? AMB_SLOT_ROWS : 0);
+            st.tile_slot[(int64_t)s * st.sum_stride + tile] = slot | (any ? AMB_TS_CAND : 0) | (rows ? AMB_TS_ROWS : 0);
+            st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16);               // candidate windows span [c_lo, c_hi]
             if (any && st.cand_list) st.cand_list[atomicAdd(st.slot_count + 1, 1)] = slot;
         }
     }
@@ -699,6 +674,45 @@ __global__ void __launch_bounds__(256) k_demod(const AmbTables* __restrict__ T, 
     }
 }
 
+// CTA-wide CRC-32 of data[0, n): every thread takes one end-aligned chunk (amb_crc_chunk), the chunk CRCs are combined
+// by a tree of GF(2) multiplications with x^(8 * chunk length * 2^level).  blockDim.x = AMB_CRC_THREADS; all threads
+// call; the result is returned to all.  tab: the 256-entry table in shared memory; sh: AMB_CRC_THREADS words.
+#define AMB_CRC_THREADS 128
+#define AMB_CRC_MAXL 768        // chunk lengths with precomputed combine constants (rows up to 128 * 767 bytes)
+#define AMB_CRC_OPS 36          // per chunk length L: x^(8 L k), k = 0..31, then x^(8 L 32 k), k = 0..3
+// CTA-wide CRC-32 of data[0, n): thread t takes the end-aligned chunk t (amb_crc_chunk), then
+//   crc = XOR_t c_t * x^(8 L (127 - t)) = XOR_w [ (XOR_l c_{32 w + l} * x^(8 L (31 - l))) * x^(8 L 32 (3 - w)) ]:
+// one GF(2) multiplication per lane, a shuffle XOR reduction per warp, one more multiplication per warp.
+__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint32_t* __restrict__ ops_table /*[AMB_CRC_MAXL][AMB_CRC_OPS]*/, const uint8_t* data,
+                                                int64_t n, uint32_t* sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t lo, hi;
+    amb_crc_chunk(n, AMB_CRC_THREADS, tid, &lo, &hi);
+    uint32_t c = 0;
+    if (hi > lo) {
+        c = 0xFFFFFFFFu;
+        for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
+        c ^= 0xFFFFFFFFu;
+    }
+    const int64_t L = (n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS;
+    const bool tabled = ops_table && L < AMB_CRC_MAXL;
+    const uint32_t pl = tabled ? ops_table[L * AMB_CRC_OPS + (31 - lane)] : amb_gf_xpow8((uint32_t)(L * (31 - lane)));
+    uint32_t v = amb_gf_mul(c, pl);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+        const int k = AMB_CRC_THREADS / 32 - 1 - warp;
+        const uint32_t pw = tabled ? ops_table[L * AMB_CRC_OPS + 32 + k] : amb_gf_xpow8((uint32_t)(L * 32 * k));
+        sh[warp] = amb_gf_mul(v, pw);
+    }
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int w = 0; w < AMB_CRC_THREADS / 32; w++) r ^= sh[w];
+    __syncthreads();
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fast demodulation: float32 symbol pipeline with a margin guard, float64-faithful fallback per symbol.
 //
@@ -759,15 +773,18 @@ __device__ __forceinline__ void fft16f(float2* v) {
     for (int c = 0; c < 4; c++) fft4f(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);   // over b: v[4c + d] = X[c + 4d]
 }
 
-#define AMB_FD_HW 16                                    // half-warps (symbols in flight) per CTA
 #define AMB_FD_TSTRIDE 17                               // padded row of the 16x16 transpose
 #define AMB_FD_HWBUF (16 * AMB_FD_TSTRIDE)              // float2 per half-warp
 #define AMB_FD_ITERS (AMB_FD_MAXBINS / 16)              // 14
-#define AMB_FD_FB_WARPS 4                               // warps that run the float64-faithful fallback
+#define AMB_FD_FB_WARPS 2                               // warps that run the float64-faithful fallback
 #define AMB_FD_CPV 4                                    // cyclic-prefix samples per lane loaded ahead of the transform
-#define AMB_FD_SMEM_FAST (AMB_FD_HW * AMB_FD_HWBUF * 8 + 256 * 8 + AMB_FD_MAXBINS * (8 + 8 + 4 + 4))
+// shared memory: the fast layout (one transpose buffer per half-warp, twiddles, equaliser tables) and the fallback layout
+// share one region; the fused kernel keeps the frame's constellation indices behind it (one byte per data subcarrier)
+#define AMB_FD_SMEM_FAST(NT) (((NT) / 16) * AMB_FD_HWBUF * 8 + 256 * 8 + AMB_FD_MAXBINS * (8 + 8 + 4 + 4))
 #define AMB_FD_SMEM_FB (4 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_FFT * 8 + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS * 8)
-#define AMB_DEMOD_FAST_SMEM ((AMB_FD_SMEM_FAST > AMB_FD_SMEM_FB ? AMB_FD_SMEM_FAST : AMB_FD_SMEM_FB) + 64)
+#define AMB_FD_UNION(NT) (((AMB_FD_SMEM_FAST(NT) > AMB_FD_SMEM_FB ? AMB_FD_SMEM_FAST(NT) : AMB_FD_SMEM_FB) + 63) / 64 * 64)
+#define AMB_FD_IDX_CAP (64 * 208)                       // fused: frames of up to this many data subcarriers in all (C2: 41 x 205)
+#define AMB_DEMOD_FAST_SMEM(NT, FUSED) (AMB_FD_UNION(NT) + ((FUSED) ? AMB_FD_IDX_CAP : 0))
 
 // complex 256-point spectrum of the 512 real samples starting at global position p0 (raw values, NaN -> 0), by the
 // 16 lanes of a half-warp (l = lane & 15).  On return buf[k], k < 256, holds Z[k]; *S_out = sum |x| (half-warp total);
@@ -837,19 +854,26 @@ __device__ __forceinline__ float2 fd_split(const float2* buf, const float2 w /* 
     return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
 }
 
-template <int MOD, int NT>
+// FUSED (frames of one symbol group whose indices fit AMB_FD_IDX_CAP: every chunk frame of the standard config): the CTA
+// also does what k_parse does - majority vote, byte packing, header parse, CRC-32 - from the constellation indices it
+// keeps in shared memory, and writes the decoded bytes and the result itself; the index array never goes to HBM.
+struct AmbParseOut { amb_frame_result* results; uint8_t* bytes_out; int64_t bytes_stride; const uint32_t* crc_ops; };
+
+template <int MOD, int NT, bool FUSED>
 __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbTables* __restrict__ T, const AmbFastTables* __restrict__ FT, AmbJob* __restrict__ jobs,
-                                                     int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count) {
+                                                     int n_jobs, AmbDemodOut out, unsigned long long* __restrict__ fallback_count, AmbParseOut po) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- fast layout
-    float2* hwbuf = reinterpret_cast<float2*>(smem_raw);                         // [16][AMB_FD_HWBUF]
-    float2* tw256 = hwbuf + AMB_FD_HW * AMB_FD_HWBUF;                            // [16][16] first-pass twiddles W256^(l k1)
+    float2* hwbuf = reinterpret_cast<float2*>(smem_raw);                         // [NT / 16][AMB_FD_HWBUF]
+    float2* tw256 = hwbuf + (NT / 16) * AMB_FD_HWBUF;                            // [16][16] first-pass twiddles W256^(l k1)
     float2* Gq = tw256 + 256;                                                    // [bins] 0.5 conj(H)/|H|^2 (raw scale)
     float2* WG = Gq + AMB_FD_MAXBINS;                                            // [bins] 0.5 W512^k conj(H)/|H|^2
     float* cH = reinterpret_cast<float*>(WG + AMB_FD_MAXBINS);                   // [bins] 8e-5 / |H|: |dY|/|H| per unit of S
     int* role = reinterpret_cast<int*>(cH + AMB_FD_MAXBINS);                     // [bins] data index, or -1 - q for pilot q
+    uint8_t* s_idx = smem_raw + AMB_FD_UNION(NT);                                // FUSED: [nsym][n_data] constellation indices
+    const unsigned s_idx_u32 = smem_u32(s_idx);
     __shared__ float s_red[8];
-    __shared__ float2 s_pilot[AMB_FD_HW][AMB_MAX_PILOTS];
+    __shared__ float2 s_pilot[NT / 16][AMB_MAX_PILOTS];
     __shared__ int pilot_kk[AMB_MAX_PILOTS];                                     // bin (relative to sub_start) of pilot q, -1 outside the band
     __shared__ float s_mx, s_Sce;
     __shared__ unsigned s_minhm_bits;
@@ -858,9 +882,19 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     const int j = blockIdx.x;
     if (j >= n_jobs) return;
     AmbJob J = jobs[j];
-    if (J.status != 0) return;
+    if (J.status != 0) {
+        if (FUSED && threadIdx.x == 0) {
+            amb_frame_result r;
+            amb_result_clear(&r);
+            r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
+            r.status = J.status;
+            if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
+            po.results[j] = r;
+        }
+        return;
+    }
     const int g0 = blockIdx.y * AMB_SYM_GROUP;
-    if (g0 >= J.nsym) return;
+    if (!FUSED && g0 >= J.nsym) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, l = tid & 15;
     const int sub_start = T->sub_start, nb = T->sub_end - T->sub_start + 1, cp = T->cp_len, sym = T->sym_len, n_data = T->n_data;
     const bool folded = J.xf.kind == AMB_XF_SCALE && gridDim.y == 1;      // gather the frame peak here (otherwise k_frame_max ran, or no scaling)
@@ -890,7 +924,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     const float thr = (float)T->qam_thr;
     const int n_pilots = T->n_pilots;
     float Sce = 0.f;
-    for (int q0 = 0; q0 <= s_end - g0; q0 += nhw) {
+    for (int q0 = 0; q0 <= s_end - g0 && J.nsym > 0; q0 += nhw) {
         const bool first_round = q0 == 0;
         const bool is_ce = first_round && hw == 0;
         const int sidx = g0 + q0 + hw - 1;
@@ -987,7 +1021,8 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
         const float dphase = pc > 0 ? ptol * ipc + 4e-6f * fabsf(phase) : 0.f;       // + the approximate divisions above
         const float ph1 = 1.f + fabsf(phase);
         const float dph5 = dphase + 1e-5f;
-        uint8_t* idx_out = out.idx + (int64_t)j * out.idx_stride + (int64_t)sx * n_data;
+        uint8_t* idx_out = FUSED ? nullptr : out.idx + (int64_t)j * out.idx_stride + (int64_t)sx * n_data;
+        const unsigned idx_sh = s_idx_u32 + (unsigned)(sx * n_data);          // FUSED: 32-bit shared address of the symbol's indices
 #pragma unroll
         for (int i = 0; i < AMB_FD_ITERS; i++) {
             const int kk = l + 16 * i;
@@ -1010,7 +1045,10 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
                     margin = fminf(fminf(ar, ai), fminf(fabsf(ar - thr), fabsf(ai - thr)));
                 }
                 if (!(margin > tol)) bad = true;                        // also catches NaN
-                if (active) idx_out[rl] = (uint8_t)idx;
+                if (active) {
+                    if (FUSED) asm volatile("st.shared.u8 [%0], %1;" ::"r"(idx_sh + (unsigned)rl), "r"(idx) : "memory");
+                    else idx_out[rl] = (uint8_t)idx;
+                }
             }
         }
         const unsigned bm = __ballot_sync(0xffffffffu, bad);
@@ -1036,79 +1074,136 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     const int n_here = s_end - g0;
     unsigned m0 = s_mask[0], m1 = s_mask[1];
     if (s_all) { m0 = n_here >= 32 ? 0xffffffffu : ((1u << n_here) - 1u); m1 = n_here > 32 ? (n_here >= 64 ? 0xffffffffu : ((1u << (n_here - 32)) - 1u)) : 0u; }
-    if ((m0 | m1) == 0u) return;
-    // ---- phase 2: float64-faithful redo of the flagged symbols (shared memory re-laid out)
-    __syncthreads();
-    double* tw_re = reinterpret_cast<double*>(smem_raw);
-    double* tw_im = tw_re + AMB_FFT;
-    double* h_re = tw_im + AMB_FFT;
-    double* h_im = h_re + AMB_FFT;
-    double* work = h_im + AMB_FFT;                                       // [AMB_FD_FB_WARPS][2][512]
-    double* qs = work + AMB_FD_FB_WARPS * 2 * AMB_FFT;
-    for (int i = tid; i < AMB_FFT; i += nthr) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
-    __syncthreads();
-    AmbSig sig;
-    sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
-    double* re = work + (warp < AMB_FD_FB_WARPS ? warp : 0) * 2 * AMB_FFT;
-    double* im = re + AMB_FFT;
-    if (warp == 0) {
-        amb_fft512_load(sig, J.ce_pos + cp, re, im);
-        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
-        amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
+    if (n_here <= 0) { m0 = 0u; m1 = 0u; }
+    if ((m0 | m1) != 0u) {
+        // ---- phase 2: float64-faithful redo of the flagged symbols (shared memory re-laid out)
+        __syncthreads();
+        double* tw_re = reinterpret_cast<double*>(smem_raw);
+        double* tw_im = tw_re + AMB_FFT;
+        double* h_re = tw_im + AMB_FFT;
+        double* h_im = h_re + AMB_FFT;
+        double* work = h_im + AMB_FFT;                                       // [AMB_FD_FB_WARPS][2][512]
+        double* qs = work + AMB_FD_FB_WARPS * 2 * AMB_FFT;
+        for (int i = tid; i < AMB_FFT; i += nthr) { tw_re[i] = T->tw_re[i]; tw_im[i] = T->tw_im[i]; h_re[i] = 0.0; h_im[i] = 0.0; }
+        __syncthreads();
+        AmbSig sig;
+        sig.p = J.p; sig.base = J.base; sig.lo = J.lo; sig.hi = J.hi; sig.xf = J.xf;
+        double* re = work + (warp < AMB_FD_FB_WARPS ? warp : 0) * 2 * AMB_FFT;
+        double* im = re + AMB_FFT;
+        if (warp == 0) {
+            amb_fft512_load(sig, J.ce_pos + cp, re, im);
+            amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+            amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
+        }
+        __syncthreads();
+        if (warp < AMB_FD_FB_WARPS) {
+            unsigned long long my_fallbacks = 0;
+            int ord = 0;
+            for (int t = 0; t < n_here; t++) {
+                if (!(((t < 32 ? m0 : m1) >> (t & 31)) & 1u)) continue;
+                if ((ord++ % AMB_FD_FB_WARPS) != warp) continue;
+                const int sidx = g0 + t;
+                uint8_t* io = FUSED ? s_idx + sidx * n_data : out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * n_data;
+                amb_fft512_load(sig, J.data_pos + (int64_t)sidx * sym + cp, re, im);
+                amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+                amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, io, nullptr, nullptr);
+                my_fallbacks++;
+            }
+            if (lane == 0 && my_fallbacks && fallback_count) atomicAdd(fallback_count, my_fallbacks);
+        }
+    }
+    if (!FUSED) return;
+    // ---- fused tail (k_parse's work): majorityVote + bitsToBytes into shared memory (over the transform buffers), the
+    //      decoded bytes to the caller's row, header parse by thread 0, CRC-32 by the first AMB_CRC_THREADS threads
+    __shared__ uint32_t p_tab[256];
+    __shared__ uint32_t p_sh[AMB_CRC_THREADS / 32];
+    __shared__ amb_frame_result p_res;
+    __shared__ long long p_crc_len;
+    __syncthreads();                                                         // indices complete; the transform buffers are free
+    uint8_t* sb = smem_raw;
+    // (the job's bookkeeping fields are read again here rather than carried in registers through the symbol rounds)
+    const AmbJob* Jg = jobs + j;
+    const int t_nsym = Jg->nsym, t_mode = Jg->mode;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) p_tab[i] = T->crc_table[i];
+    const int bps = T->bps, rep = T->rep;
+    const int nb_full = (int)amb_num_bytes((int64_t)t_nsym * T->n_data, bps, rep);       // <= AMB_FD_IDX_CAP / 2
+    {
+        int b0 = 0;
+        if (rep == 1 && bps == 4) {
+            const int quads = nb_full / 4;
+            const uint2* src = reinterpret_cast<const uint2*>(s_idx);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sb);
+            for (int q = tid; q < quads; q += nthr) {
+                const uint2 v = src[q];
+                const uint32_t lo = v.x, hi = v.y;
+                // index bytes i0..i7 -> output bytes (i0<<4|i1), (i2<<4|i3), ...: nibble pairs of each 16-bit half swap places
+                const uint32_t a = ((lo & 0x000F000Fu) << 4) | ((lo >> 8) & 0x000F000Fu), b = ((hi & 0x000F000Fu) << 4) | ((hi >> 8) & 0x000F000Fu);
+                dst[q] = (a & 0xFFu) | ((a >> 8) & 0xFF00u) | ((b & 0xFFu) << 16) | ((b << 8) & 0xFF000000u);
+            }
+            b0 = quads * 4;
+        }
+        for (int b = b0 + tid; b < nb_full; b += nthr) sb[b] = amb_pack_byte(s_idx, bps, rep, b);
     }
     __syncthreads();
-    if (warp >= AMB_FD_FB_WARPS) return;
-    unsigned long long my_fallbacks = 0;
-    int ord = 0;
-    for (int t = 0; t < n_here; t++) {
-        if (!(((t < 32 ? m0 : m1) >> (t & 31)) & 1u)) continue;
-        if ((ord++ % AMB_FD_FB_WARPS) != warp) continue;
-        const int sidx = g0 + t;
-        amb_fft512_load(sig, J.data_pos + (int64_t)sidx * sym + cp, re, im);
-        amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
-        amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * n_data, nullptr, nullptr);
-        my_fallbacks++;
+    {
+        // decoded bytes to the caller's row, clipped to its stride (parse and CRC below see the whole frame)
+        uint8_t* bytes = po.bytes_out + (int64_t)j * po.bytes_stride;
+        const int nbc = (int64_t)nb_full < po.bytes_stride ? nb_full : (int)po.bytes_stride;
+        if ((((uintptr_t)bytes) & 15) == 0) {
+            const int vec = nbc / 16;
+            for (int q = tid; q < vec; q += nthr) reinterpret_cast<uint4*>(bytes)[q] = reinterpret_cast<const uint4*>(sb)[q];
+            for (int b = vec * 16 + tid; b < nbc; b += nthr) bytes[b] = sb[b];
+        } else {
+            for (int b = tid; b < nbc; b += nthr) bytes[b] = sb[b];
+        }
     }
-    if (lane == 0 && my_fallbacks && fallback_count) atomicAdd(fallback_count, my_fallbacks);
-}
-
-// CTA-wide CRC-32 of data[0, n): every thread takes one end-aligned chunk (amb_crc_chunk), the chunk CRCs are combined
-// by a tree of GF(2) multiplications with x^(8 * chunk length * 2^level).  blockDim.x = AMB_CRC_THREADS; all threads
-// call; the result is returned to all.  tab: the 256-entry table in shared memory; sh: AMB_CRC_THREADS words.
-#define AMB_CRC_THREADS 128
-#define AMB_CRC_MAXL 768        // chunk lengths with precomputed combine constants (rows up to 128 * 767 bytes)
-#define AMB_CRC_OPS 36          // per chunk length L: x^(8 L k), k = 0..31, then x^(8 L 32 k), k = 0..3
-// CTA-wide CRC-32 of data[0, n): thread t takes the end-aligned chunk t (amb_crc_chunk), then
-//   crc = XOR_t c_t * x^(8 L (127 - t)) = XOR_w [ (XOR_l c_{32 w + l} * x^(8 L (31 - l))) * x^(8 L 32 (3 - w)) ]:
-// one GF(2) multiplication per lane, a shuffle XOR reduction per warp, one more multiplication per warp.
-__device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, const uint32_t* __restrict__ ops_table /*[AMB_CRC_MAXL][AMB_CRC_OPS]*/, const uint8_t* data,
-                                                int64_t n, uint32_t* sh) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int64_t lo, hi;
-    amb_crc_chunk(n, AMB_CRC_THREADS, tid, &lo, &hi);
-    uint32_t c = 0;
-    if (hi > lo) {
-        c = 0xFFFFFFFFu;
-        for (int64_t i = lo; i < hi; i++) c = tab[(c ^ data[i]) & 0xFF] ^ (c >> 8);
-        c ^= 0xFFFFFFFFu;
+    if (tid == 0) {
+        amb_frame_result r;
+        amb_result_clear(&r);
+        r.stream = Jg->stream; r.coarse_metric = Jg->coarse; r.fine_metric = Jg->fine;
+        int64_t crc_len = -1;
+        if (t_mode == 0) amb_parse_chunk_frame(p_tab, sb, nb_full, &r, &crc_len);
+        else amb_parse_received(p_tab, sb, nb_full, &r, &crc_len);
+        r.n_bytes = (int32_t)nb_full;
+        const bool chunk_type = nb_full >= 10 && (sb[0] == AMB_FRAME_META || sb[0] == AMB_FRAME_DATA);
+        if (t_mode == 0 || r.status == 0 || chunk_type) r.preamble_idx = Jg->result_pos;
+        p_res = r;
+        p_crc_len = crc_len;
     }
-    const int64_t L = (n + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS;
-    const bool tabled = ops_table && L < AMB_CRC_MAXL;
-    const uint32_t pl = tabled ? ops_table[L * AMB_CRC_OPS + (31 - lane)] : amb_gf_xpow8((uint32_t)(L * (31 - lane)));
-    uint32_t v = amb_gf_mul(c, pl);
+    __syncthreads();
+    const int64_t crc_len = p_crc_len;
+    if (crc_len >= 0) {
+        // block_crc32 with the first AMB_CRC_THREADS threads of the CTA (every launch has at least 160)
+        if (tid < AMB_CRC_THREADS) {
+            int64_t lo64, hi64;
+            amb_crc_chunk(crc_len, AMB_CRC_THREADS, tid, &lo64, &hi64);
+            const int lo = (int)lo64, hi = (int)hi64;
+            uint32_t c = 0;
+            if (hi > lo) {
+                c = 0xFFFFFFFFu;
+                for (int i = lo; i < hi; i++) c = p_tab[(c ^ sb[i]) & 0xFF] ^ (c >> 8);
+                c ^= 0xFFFFFFFFu;
+            }
+            const int L = (int)((crc_len + AMB_CRC_THREADS - 1) / AMB_CRC_THREADS);
+            const bool tabled = po.crc_ops && L < AMB_CRC_MAXL;
+            const uint32_t pl = tabled ? po.crc_ops[L * AMB_CRC_OPS + (31 - lane)] : amb_gf_xpow8((uint32_t)(L * (31 - lane)));
+            uint32_t v = amb_gf_mul(c, pl);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) {
-        const int k = AMB_CRC_THREADS / 32 - 1 - warp;
-        const uint32_t pw = tabled ? ops_table[L * AMB_CRC_OPS + 32 + k] : amb_gf_xpow8((uint32_t)(L * 32 * k));
-        sh[warp] = amb_gf_mul(v, pw);
+            for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                const int k = AMB_CRC_THREADS / 32 - 1 - warp;
+                const uint32_t pw = tabled ? po.crc_ops[L * AMB_CRC_OPS + 32 + k] : amb_gf_xpow8((uint32_t)(L * 32 * k));
+                p_sh[warp] = amb_gf_mul(v, pw);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t c = 0;
+            for (int w = 0; w < AMB_CRC_THREADS / 32; w++) c ^= p_sh[w];
+            p_res.actual_crc = c; p_res.crc_valid = p_res.expected_crc == c;
+        }
     }
-    __syncthreads();
-    uint32_t r = 0;
-#pragma unroll
-    for (int w = 0; w < AMB_CRC_THREADS / 32; w++) r ^= sh[w];
-    __syncthreads();
-    return r;
+    if (tid == 0) po.results[j] = p_res;
 }
 
 #define AMB_PARSE_SMEM 8192      // decoded frames up to this many bytes are packed, parsed and checksummed in shared memory
@@ -1923,6 +2018,28 @@ __global__ void __launch_bounds__(256) k_tx_frames(const AmbTables* __restrict__
     }
 }
 
+// modulateOFDM (modem.js:322-362) for n rows of bits (one byte per bit): a warp per symbol; row r's symbol s goes to
+// samples[r][s * SYMBOL_LEN ..].  pad_rows != 0: the zero padding of modem.js:329 is written back into the caller's row.
+__global__ void __launch_bounds__(256) k_modulate(const AmbTables* __restrict__ T, uint8_t* __restrict__ bits, int64_t bits_stride, int64_t n_bits,
+                                                   int n, int64_t nsym, float* __restrict__ samples, int64_t samples_stride, int pad_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    const int64_t groups = (nsym + AMB_TX_WARPS - 1) / AMB_TX_WARPS;
+    const int64_t r = blockIdx.x / groups, s = (blockIdx.x % groups) * AMB_TX_WARPS + warp;
+    if (r >= n) return;
+    uint8_t* row = bits + r * bits_stride;
+    if (s < nsym) {
+        double* re = work + warp * 2 * AMB_FFT;
+        double* im = re + AMB_FFT;
+        amb_tx_symbol_bits(T, row, n_bits, s, re, im, samples + r * samples_stride + s * T->sym_len);
+    }
+    if (pad_rows && blockIdx.x % groups == 0) {
+        const int64_t padded = nsym * (int64_t)T->n_data * T->bps;
+        for (int64_t i = n_bits + threadIdx.x; i < padded; i += blockDim.x) row[i] = 0;
+    }
+}
+
 // Inclusive prefix over calls of the defect terms: F[c] = F[c-1] + D[c] for the n new arena calls starting at c0
 // (F[c0-1] is the carry from the previous push, 0 before the stream start).  Two passes over parts of 1024 calls:
 // k_defect_part sums each part, k_defect_scan adds the carry and the totals of the parts before it and scans its own.
@@ -2148,7 +2265,7 @@ struct AmbLinkBufs {
 
 __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
     const int sl = tile_slot[idx];
-    return sl >= 0 && slot_info[sl * 4 + 2] != 0;
+    return sl >= 0 && (sl & AMB_TS_CAND) != 0;
 }
 
 // Ordered list of the candidate runs of this push for every stream on the link path.  A chunk is 4096 tiles (256

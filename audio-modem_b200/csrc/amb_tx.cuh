@@ -70,17 +70,16 @@ AMB_HD int amb_tx_bit(const uint8_t* payload, int64_t payload_bits, int rep, int
     return (payload[q >> 3] >> (7 - (int)(q & 7))) & 1;
 }
 
-// re/im: 512 doubles each (scratch).  out: sym_len float32 samples (CP + body, un-normalised).
-AMB_HD void amb_tx_symbol(const AmbTables* T, const uint8_t* payload, int64_t payload_bytes, int64_t sym, double* re, double* im, float* out) {
-    const int64_t payload_bits = payload_bytes * 8;
-    const int64_t bit0 = sym * (int64_t)T->n_data * T->bps;
+// re/im: 512 doubles each (scratch).  out: sym_len float32 samples (CP + body, un-normalised).  idx_of(di) = constellation
+// index of data subcarrier di (constellationMap, modem.js:133-138).
+template <class IdxFn>
+AMB_HD void amb_tx_symbol_from(const AmbTables* T, IdxFn idx_of, double* re, double* im, float* out) {
     AMB_WARP_FOR(i, AMB_FFT) { re[i] = 0.0; im[i] = 0.0; }
     AMB_WARP_SYNC();
     // spectrum written straight into bit-reversed order (the reference's permutation is an involution)
     AMB_WARP_FOR(di, T->n_data) {
         const int k = T->data_k[di];
-        int idx = 0;                                                          // constellationMap, modem.js:133-138
-        for (int b = 0; b < T->bps; b++) idx = (idx << 1) | amb_tx_bit(payload, payload_bits, T->rep, bit0 + (int64_t)di * T->bps + b);
+        const int idx = idx_of(di);
         const double vr = T->pts[2 * (idx % T->n_points)], vi = T->pts[2 * (idx % T->n_points) + 1];
         re[amb_rev9(k)] = vr; im[amb_rev9(k)] = vi;
         re[amb_rev9(AMB_FFT - k)] = vr; im[amb_rev9(AMB_FFT - k)] = -vi;     // Hermitian, modem.js:353
@@ -117,6 +116,30 @@ AMB_HD void amb_tx_symbol(const AmbTables* T, const uint8_t* payload, int64_t pa
         if (i >= AMB_FFT - cp) out[i - (AMB_FFT - cp)] = v;
     }
     AMB_WARP_SYNC();
+}
+
+// symbol `sym` of a byte payload: serial bit b of the transmitted stream is bit (7 - (q & 7)) of payload[q >> 3], q = b / rep
+AMB_HD void amb_tx_symbol(const AmbTables* T, const uint8_t* payload, int64_t payload_bytes, int64_t sym, double* re, double* im, float* out) {
+    const int64_t payload_bits = payload_bytes * 8;
+    const int64_t bit0 = sym * (int64_t)T->n_data * T->bps;
+    const int bps = T->bps, rep = T->rep;
+    amb_tx_symbol_from(T, [=](int di) {
+        int idx = 0;
+        for (int b = 0; b < bps; b++) idx = (idx << 1) | amb_tx_bit(payload, payload_bits, rep, bit0 + (int64_t)di * bps + b);
+        return idx;
+    }, re, im, out);
+}
+
+// symbol `sym` of modulateOFDM(bits, modName) (modem.js:322-362): bits = one byte per bit, `b & 1` counts (modem.js:135),
+// zeros past n_bits (the in-place padding of modem.js:329); no repetition (the caller applies repeatBits)
+AMB_HD void amb_tx_symbol_bits(const AmbTables* T, const uint8_t* bits, int64_t n_bits, int64_t sym, double* re, double* im, float* out) {
+    const int64_t bit0 = sym * (int64_t)T->n_data * T->bps;
+    const int bps = T->bps;
+    amb_tx_symbol_from(T, [=](int di) {
+        int idx = 0;
+        for (int b = 0; b < bps; b++) { const int64_t q = bit0 + (int64_t)di * bps + b; idx = (idx << 1) | (q < n_bits ? (bits[q] & 1) : 0); }
+        return idx;
+    }, re, im, out);
 }
 
 // silences of buildChunkOFDMFrame, modem.js:728-733 (Math.round of the float64 products)

@@ -65,14 +65,27 @@ struct AmbWalkGeom {
 
 // screening values in the xc store: a metric in [-1, 1]; AMB_XC_FAIL where the denominator fails its 0.001 test;
 // AMB_XC_UNSURE where float32 cannot tell
+// slot_info[slot * 4 + 2] (written by k_tri_store): the tile holds a candidate window (its screening row in xc is computed);
+// its float64 rows in tri are written
+#define AMB_SLOT_CAND 1
+#define AMB_SLOT_ROWS 2
 #define AMB_XC_FAIL (-2.0f)
 #define AMB_XC_UNSURE (2.0f)
 
-AMB_HD int amb_tile_slot_of(const AmbWalkGeom& G, int64_t j) {
+// tile_slot entry: -1 = no slot, else the slot number with two flags k_tri_store adds once it has looked at the tile
+// (the same flags as slot_info[2], here so that the walker learns them with the slot number in one load)
+#define AMB_TS_ROWS (1 << 30)
+#define AMB_TS_CAND (1 << 29)
+#define AMB_TS_MASK ((1 << 29) - 1)
+AMB_HD int amb_tile_slot_raw(const AmbWalkGeom& G, int64_t j) {
     if (!G.tile_slot) return -1;
     const int64_t rel = j - (G.sum_base >> 8);
     if (rel < 0 || rel >= G.sum_tiles || (j << 8) < G.sum_lo) return -1;       // below sum_lo: entries of an earlier push
     return G.tile_slot[rel];
+}
+AMB_HD int amb_tile_slot_of(const AmbWalkGeom& G, int64_t j) {
+    const int raw = amb_tile_slot_raw(G, j);
+    return raw < 0 ? -1 : (raw & AMB_TS_MASK);
 }
 
 // tile summary: {max|P|, minRa, maxRa, minRb, maxRb}
@@ -154,8 +167,9 @@ AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0
         const int64_t tile_first = (j << 8) - 511;
         int seg = (int)(tile_first + 256 - d);
         if (seg > cnt - done) seg = cnt - done;
-        const int slot = amb_tile_slot_of(G, j);
-        if (slot >= 0 && G.tri) {                                                         // (k_tri_store writes the rows of every slot)
+        const int raw = amb_tile_slot_raw(G, j);
+        const int slot = raw & AMB_TS_MASK;
+        if (raw >= 0 && G.tri && (raw & AMB_TS_ROWS)) {
             const double* src = G.tri + (int64_t)slot * 768 + (d - tile_first);          // [slot][P | Ra | Rb][256]
             AMB_WARP_FOR(i, seg) { P[done + i] = src[i]; A[done + i] = src[256 + i]; B[done + i] = src[512 + i]; }
             AMB_WARP_SYNC();
@@ -228,9 +242,10 @@ AMB_HD double amb_resolve_fine(const AmbTables* T, const AmbSig& sig, int64_t po
 AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, int64_t lo, int64_t hi, int64_t p,
                                    double* scratch, int64_t* pos_out) {
     const int64_t j = (p + 511) >> 8;
-    const int slot = G.xc ? amb_tile_slot_of(G, j) : -1;
+    const int raw = G.xc ? amb_tile_slot_raw(G, j) : -1;
+    const int slot = raw & AMB_TS_MASK;
     const int64_t base = (j << 8) - 511 - T->fine_radius;
-    if (slot < 0 || lo < base || hi >= base + G.xc_w || hi < lo || (G.slot_info && !G.slot_info[slot * 4 + 2]))
+    if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND))
         return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
     const float* v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
     const int n = (int)(hi - lo + 1);

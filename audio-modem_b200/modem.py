@@ -329,6 +329,23 @@ class Modem:
                                                     noise_seed, noise_g0, None, MEM_DEVICE))
         return out
 
+    def modulate(self, bits_rows):
+        """modulateOFDM (modem.js:322-362) for rows of equal length: -> (samples [n][numSymbols][SYMBOL_LEN] float32,
+        numSymbols, bitsPerSymbol, padded [n][paddedLength] uint8: the rows as the reference leaves its caller's array)"""
+        rows = [np.asarray(b, dtype=np.int64) & 1 for b in bits_rows]
+        n, n_bits = len(rows), (len(rows[0]) if rows else 0)
+        assert all(len(r) == n_bits for r in rows), "rows of equal length"
+        out3 = (C.c_int32 * 3)()
+        self._ck(self._L.amb_modulate(self._h, None, n_bits, n_bits, 0, None, 0, out3, MEM_HOST))
+        nsym, per, padded = int(out3[0]), int(out3[1]), int(out3[2])
+        bits = np.zeros((max(n, 1), max(padded, 1)), np.uint8)
+        for i, r in enumerate(rows):
+            bits[i, :n_bits] = r
+        samples = np.zeros((max(n, 1), max(nsym, 1) * self.SYMBOL_LEN), np.float32)
+        if n and nsym:
+            self._ck(self._L.amb_modulate(self._h, _ptr(bits), bits.shape[1], n_bits, n, _ptr(samples), samples.shape[1], out3, MEM_HOST))
+        return samples[:n, : nsym * self.SYMBOL_LEN].reshape(n, nsym, self.SYMBOL_LEN), nsym, per, bits[:n, :padded]
+
     def build_transmit_signals(self, datas, fileName="file"):
         """buildTransmitSignal (modem.js:498-555) for many payloads of equal length -> [n][samples] float32"""
         data = np.ascontiguousarray(np.stack([np.frombuffer(bytes(d), np.uint8) if isinstance(d, (bytes, bytearray)) else np.asarray(d, np.uint8)
@@ -525,6 +542,15 @@ def estimateChannel(receivedSamples, knownRe, knownIm):
 
 def demodulateOFDM(signal, modName, channelRe, channelIm):
     return _modem(modName).demodulate([signal], channelRe, channelIm)[0]
+
+
+def modulateOFDM(bits, modName):
+    """modem.js:322-362 -> {samples: [Float32Array per symbol], numSymbols, bitsPerSymbol}.  Like the reference it pads the
+    CALLER's bit array in place with zeros up to a whole number of symbols (modem.js:329) when that array can grow (a list)."""
+    samples, nsym, per, padded = _modem(modName).modulate([bits])
+    if isinstance(bits, list) and len(bits) < padded.shape[1]:
+        bits.extend([0] * (padded.shape[1] - len(bits)))
+    return {"samples": [samples[0, s] for s in range(nsym)], "numSymbols": nsym, "bitsPerSymbol": per}
 
 
 def decodeReceivedSignal(signal, modName, repetition=1):

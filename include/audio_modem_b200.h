@@ -125,16 +125,6 @@ int64_t amb_kernel_launches(const amb_modem* m); /* kernels launched so far by t
 /* per-kernel device time: amb_profile(m, 1) brackets every kernel launch with CUDA events on the handle's stream;
  * amb_profile_read returns, per kernel name (names = [cap][32] chars), the summed milliseconds and launch count since
  * the last read, and clears them */
-/* development counters: 0 kernel launches, 1 data symbols redone by the float64-faithful fallback of the fast
- * demodulator, 2 link-resolution iterations, 3 link-resolution passes */
-int64_t amb_debug_counter(amb_modem* m, int which);
-/* development: copies the last push's per-slot records to host memory (which = 0: {stream, arena tile, has-candidate,
- * candidate span} int32 x 4; which = 1: {max metric, min Ra, min Rb, excluded} float x 4); returns the slot count */
-int64_t amb_debug_read(amb_modem* m, int which, void* out, int64_t cap_bytes);
-/* development self-tests that need the device's 32-lane execution: which = 0 runs n random batches of the streaming
- * scanner's candidate logic (app.js:806-838) through its warp-parallel form and through the reference-order loop;
- * out2[0] = disagreements (must be 0), out2[1] = batches that committed a preamble */
-int amb_selftest(amb_modem* m, int which, uint64_t seed, int n, int64_t* out2);
 int amb_profile(amb_modem* m, int enable);
 int amb_profile_read(amb_modem* m, char* names, double* total_ms, int64_t* launches, int cap, int* n);
 
@@ -234,6 +224,15 @@ int amb_stream_enable_assembly(amb_modem* m, int64_t max_file_bytes);
 int amb_stream_assemble(amb_modem* m, int stream, uint8_t* out, int64_t cap, int64_t* size_out, int mem);
 
 /* ---- transmit side (the "next" row of the scope table; also synthesises bench / test input on the device) ---- */
+/* modulateOFDM(bits, modName), modem.js:322-362, for n rows of bits: bits = [n][bits_stride], one byte per bit like the
+ * reference's number[] (only `b & 1` counts, modem.js:135), n_bits valid per row.  samples = [n][samples_stride] float32:
+ * numSymbols symbols of SYMBOL_LEN samples each (cyclic prefix + body: the Float32Arrays of addCP, modem.js:202-208),
+ * bit-identical to the reference's.  out3 = {numSymbols, bitsPerSymbol, padded length}.  The reference pads the CALLER's
+ * array in place with zeros up to a whole symbol (modem.js:329); this call does the same when the row has room
+ * (bits_stride >= padded length) and otherwise only reports the padded length.  No repetition is applied (the reference
+ * calls repeatBits before modulateOFDM, modem.js:721).  A first call with samples = NULL and n = 0 returns the sizes. */
+int amb_modulate(amb_modem* m, uint8_t* bits, int64_t bits_stride, int64_t n_bits, int n, float* samples, int64_t samples_stride,
+                 int32_t* out3, int mem);
 /* samples of one chunk frame incl. its silences: estimateFrameSamplesWithSilence, modem.js:876-884 */
 int64_t amb_chunk_frame_samples(amb_modem* m, int64_t payload_bytes, int is_first_frame);
 /* buildDataChunkFrame, modem.js:763-766 (+ buildDataChunkPayload :694-714, buildChunkOFDMFrame :718-756) for n chunks of

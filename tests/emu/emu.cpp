@@ -273,7 +273,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 hot = hot || (o[2] * 1.05f > 0.0009f && o[4] * 1.05f > 0.0009f && pw * pw > 0.4f * fmaxf(o[1] * 0.95f, 0.0009f) * fmaxf(o[3] * 0.95f, 0.0009f));
             }
             if (g_use_stores && hot) {
-                tile_slot[(size_t)j] = n_slots++;
+                tile_slot[(size_t)j] = (n_slots++) | AMB_TS_ROWS | (cand ? AMB_TS_CAND : 0);
                 tsum.push_back((float)mmax * (1.f + 1e-6f) + 1e-30f); tsum.push_back(fmaxf((float)xmnA * (1.f - 1e-6f), 0.f));
                 tsum.push_back(fmaxf((float)xmnB * (1.f - 1e-6f), 0.f)); tsum.push_back(excluded ? 1.f : 0.f);
                 tri.insert(tri.end(), t3.begin(), t3.end());
@@ -309,7 +309,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
                 std::vector<AmbRun> runs;
                 for (int64_t j = 0; j < n_tiles; j++) {
                     const int sl = tile_slot[(size_t)j];
-                    const bool c = sl >= 0 && xc[(size_t)sl * xc_w] != AMB_XC_UNSURE;     // emu marks candidate tiles by filling xc
+                    const bool c = sl >= 0 && (sl & AMB_TS_CAND);
                     if (!c) continue;
                     const int64_t first = j * 256 - 511, last = first + 255;
                     if (!runs.empty() && runs.back().last_pos + 1 == first) runs.back().last_pos = last;
