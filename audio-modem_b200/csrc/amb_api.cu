@@ -77,7 +77,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, post_acc, bitmaps, files, file_reset, store_off;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
     int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
@@ -193,7 +193,10 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     if (m->fast_demod) {
         // float32 symbol pipeline with margin guard and float64-faithful fallback; gathers the per-frame peak itself when one
         // CTA covers the whole frame
-        if (frame_max && groups > 1) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
+        if (frame_max && groups > 1) {
+            const int parts = max_nsym * T.sym_len / 32768 + 1;          // a CTA per 32 K samples of the longest frame
+            LAUNCH("k_frame_max", k_frame_max<<<n_jobs * parts, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs, parts));
+        }
         // warps per CTA (two symbols each per round): the count that leaves the fewest symbol slots empty for the longest frame
         int nw = 8;
         {
@@ -216,7 +219,7 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
 #undef AMB_DEMOD_LAUNCH_MOD
 #undef AMB_DEMOD_LAUNCH
     } else {
-        if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs)); }
+        if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs, 1)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
     }
     if (!fused) {
@@ -401,7 +404,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -430,6 +433,14 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
         cudaMemcpy(&v, m->d_fallbacks, 8, cudaMemcpyDeviceToHost);
         return (int64_t)v;
     }
+#if defined(AMB_WALK_STATS)
+    if (which >= 16 && which < 32) {
+        unsigned long long v[16];
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpyFromSymbol(v, g_amb_walk_stats, sizeof(v));
+        return (int64_t)v[which - 16];
+    }
+#endif
     if (which == 2) return m->link_iterations;
     if (which == 3) return m->link_passes;
     if ((which == 4 || which == 5) && m->open) {
@@ -796,7 +807,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     m->slot_cap = (int)(tiles_per_push / 8 + 64 < 2000000 ? tiles_per_push / 8 + 64 : 2000000);
     CK(m->tile_slot.ensure(ns * m->sum_stride * 4)); CK(m->tri.ensure((size_t)m->slot_cap * 256 * 3 * 8));
     CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16)); CK(m->tsum.ensure((size_t)m->slot_cap * 16)); CK(m->cand_list.ensure((size_t)m->slot_cap * 4));
-    CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8));
+    CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8)); CK(m->cold_tag.ensure(ns * m->calls_stride * 4));
     CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
@@ -811,6 +822,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
         CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
         CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
         CK(m->l_hasB.ensure(nl * 4)); CK(m->l_memo.ensure(nr * sizeof(AmbRefineMemo)));
+        CK(m->l_bmout.ensure(nr * sizeof(AmbStreamState))); CK(m->l_bmrec.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_bmhas.ensure(nr * 4));
         CK(m->l_first.ensure(ns * sizeof(AmbStreamState))); CK(m->l_firstflag.ensure(ns * 4)); CK(m->l_firststop.ensure(ns * 4)); CK(m->l_fpsum.ensure(ns * 8));
     }
     {
@@ -841,7 +853,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     m->open = false;
     m->file_cap = 0;
@@ -941,6 +953,16 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
     g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
+    // idle-call screening (k_cold_calls) pays when pushes are long; AMB_COLD_CALLS=0 switches it off (comparison runs)
+    static const bool cold_on = !(std::getenv("AMB_COLD_CALLS") && std::getenv("AMB_COLD_CALLS")[0] == '0');
+    const bool use_cold = cold_on && n_new / m->block_len >= 64;
+    g.cold_tag = use_cold ? m->cold_tag.as<int32_t>() : nullptr;
+    if (use_cold) {
+        // a tag states a fact about the data (call k is cold under the defect of a receiver re-initialised in call c): the
+        // tags of this push's calls start empty and accumulate over the link iterations
+        const int64_t call_lo = m->written / m->block_len, call_hi = (m->written + n_new) / m->block_len;
+        CK(cudaMemset2DAsync(m->cold_tag.as<int32_t>() + (call_lo - m->base_g / m->block_len), (size_t)m->calls_stride * 4, 0xFF, (size_t)(call_hi - call_lo) * 4, ns, m->stream));
+    }
     {
         const int L = m->xc_w + T.sym_len;
         const size_t smem = AMB_XC_SMEM(L);
@@ -975,6 +997,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
     L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
     L.fp_sum = m->l_fpsum.as<unsigned long long>(); L.memo = m->l_memo.as<AmbRefineMemo>();
+    L.bm_out = m->l_bmout.as<AmbStreamState>(); L.bm_rec = m->l_bmrec.as<AmbFrameRec>(); L.bm_has = m->l_bmhas.as<int>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
     const int walk_grid = (int)(blocks_for(max_links, 4) < m->walk_ctas ? blocks_for(max_links, 4) : m->walk_ctas);
     const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);
@@ -1012,6 +1035,13 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
             m->link_iterations++;
             CK(cudaMemsetAsync(L.n_active, 0, 4, m->stream));
             LAUNCH("k_chain_links", k_chain_links<<<ns, ns < 64 ? 1024 : 256, ns < 64 ? AMB_CHAIN_SMEM : 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L, ns < 64 ? AMB_CHAIN_SMEM_RUNS : 0));
+            if (use_cold) {
+                const int64_t call_lo = m->written / m->block_len, call_hi = (m->written + n_new) / m->block_len;
+                const int64_t warps = (int64_t)ns * (call_hi - call_lo);
+                const int cgrid = (int)(blocks_for(warps, 4) < 148 * 32 ? blocks_for(warps, 4) : 148 * 32);
+                LAUNCH("k_cold_calls", k_cold_calls<<<cgrid, 128, 0, m->stream>>>(g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(), ns, L,
+                                                                                  m->cold_tag.as<int32_t>(), call_lo, call_hi));
+            }
             LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));

@@ -497,6 +497,19 @@ __device__ __forceinline__ void amb_tile_sums_regs(const float (&x)[3][8], int l
 // the lane's own 8 samples per segment, five warp scans turn the sums into those prefixes, pass 2 walks the 8 samples again
 // (reloaded: they sit in L1) with five running sums and writes the window sums.  Few live registers on purpose: the walker
 // kernels that inline this are register-bound.
+__device__ __forceinline__ void amb_ws_load4(const float* sp, int64_t sbase, int64_t slo, int64_t shi, bool inside, const float* pa, int64_t g0, int k0,
+                                             float (&x0)[4], float (&x1)[4], float (&x2)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (inside) { x0[k] = pa[k0 + k]; x1[k] = pa[256 + k0 + k]; x2[k] = pa[512 + k0 + k]; }
+        else {
+            const int64_t g = g0 + k0 + k;
+            x0[k] = (g >= slo && g < shi) ? sp[g - sbase] : 0.f;
+            x1[k] = (g + 256 >= slo && g + 256 < shi) ? sp[g + 256 - sbase] : 0.f;
+            x2[k] = (g + 512 >= slo && g + 512 < shi) ? sp[g + 512 - sbase] : 0.f;
+        }
+    }
+}
 __device__ __forceinline__ void amb_window_sums_blocks(const float* sp, int64_t sbase, int64_t slo, int64_t shi, int64_t d0, int cnt, double* P, double* A, double* B) {
     const int lane = threadIdx.x & 31;
     for (int b0 = 0; b0 < cnt; b0 += 256) {
@@ -504,18 +517,16 @@ __device__ __forceinline__ void amb_window_sums_blocks(const float* sp, int64_t 
         const bool inside = d0 + b0 >= slo && d0 + b0 + 768 <= shi;
         const float* pa = sp + (g0 - sbase);
         double q0 = 0.0, q1 = 0.0, q2 = 0.0, t0 = 0.0, t1 = 0.0;
+        // (the samples are fetched twelve at a time: the loads of a group are in flight together)
 #pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            float x0, x1, x2;
-            if (inside) { x0 = pa[k]; x1 = pa[256 + k]; x2 = pa[512 + k]; }
-            else {
-                const int64_t g = g0 + k;
-                x0 = (g >= slo && g < shi) ? sp[g - sbase] : 0.f;
-                x1 = (g + 256 >= slo && g + 256 < shi) ? sp[g + 256 - sbase] : 0.f;
-                x2 = (g + 512 >= slo && g + 512 < shi) ? sp[g + 512 - sbase] : 0.f;
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            float x0[4], x1[4], x2[4];
+            amb_ws_load4(sp, sbase, slo, shi, inside, pa, g0, k0, x0, x1, x2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                q0 = fma((double)x0[k], (double)x0[k], q0); q1 = fma((double)x1[k], (double)x1[k], q1); q2 = fma((double)x2[k], (double)x2[k], q2);
+                t0 = fma((double)x0[k], (double)x1[k], t0); t1 = fma((double)x1[k], (double)x2[k], t1);
             }
-            q0 = fma((double)x0, (double)x0, q0); q1 = fma((double)x1, (double)x1, q1); q2 = fma((double)x2, (double)x2, q2);
-            t0 = fma((double)x0, (double)x1, t0); t1 = fma((double)x1, (double)x2, t1);
         }
         // exclusive prefixes over the lanes; segment totals of x^2 (segment 0, 1) and of the cross products (segment 0)
         double e0 = q0, e1 = q1, e2 = q2, f0 = t0, f1 = t1;
@@ -529,19 +540,16 @@ __device__ __forceinline__ void amb_window_sums_blocks(const float* sp, int64_t 
         // running prefixes at the lane's first window: S_q[256 seg + w], S_t[256 seg + w]
         double pq0 = e0 - q0, pq1 = Q0 + (e1 - q1), pq2 = Q0 + Q1 + (e2 - q2), pt0 = f0 - t0, pt1 = T0 + (f1 - t1);
 #pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            const int i = b0 + 8 * lane + k;
-            if (i < cnt) { P[i] = pt1 - pt0; A[i] = pq1 - pq0; B[i] = pq2 - pq1; }
-            float x0, x1, x2;
-            if (inside) { x0 = pa[k]; x1 = pa[256 + k]; x2 = pa[512 + k]; }
-            else {
-                const int64_t g = g0 + k;
-                x0 = (g >= slo && g < shi) ? sp[g - sbase] : 0.f;
-                x1 = (g + 256 >= slo && g + 256 < shi) ? sp[g + 256 - sbase] : 0.f;
-                x2 = (g + 512 >= slo && g + 512 < shi) ? sp[g + 512 - sbase] : 0.f;
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            float x0[4], x1[4], x2[4];
+            amb_ws_load4(sp, sbase, slo, shi, inside, pa, g0, k0, x0, x1, x2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = b0 + 8 * lane + k0 + k;
+                if (i < cnt) { P[i] = pt1 - pt0; A[i] = pq1 - pq0; B[i] = pq2 - pq1; }
+                pq0 = fma((double)x0[k], (double)x0[k], pq0); pq1 = fma((double)x1[k], (double)x1[k], pq1); pq2 = fma((double)x2[k], (double)x2[k], pq2);
+                pt0 = fma((double)x0[k], (double)x1[k], pt0); pt1 = fma((double)x1[k], (double)x2[k], pt1);
             }
-            pq0 = fma((double)x0, (double)x0, pq0); pq1 = fma((double)x1, (double)x1, pq1); pq2 = fma((double)x2, (double)x2, pq2);
-            pt0 = fma((double)x0, (double)x1, pt0); pt1 = fma((double)x1, (double)x2, pt1);
         }
     }
     __syncwarp();

@@ -486,6 +486,7 @@ struct AmbStreamGeom {
     const int32_t* tile_slot; const double* tri; const float* xc; int xc_w;
     const int32_t* slot_info; const float* tsum;
     const double* F; int64_t calls_stride;
+    const int32_t* cold_tag;   // [n_streams][calls_stride] (k_cold_calls), or NULL
 };
 
 __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
     G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+        G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
     G.memo_out = nullptr; G.memo_in = nullptr;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
@@ -586,13 +588,15 @@ struct AmbJob {
     int64_t result_pos;      // preamble_idx to report (-1: none)
 };
 
-__global__ void k_frame_max(AmbJob* __restrict__ jobs, int n_jobs) {
-    const int j = blockIdx.x;
+// per-frame peak (app.js:918-925) of frames too long for one demodulator CTA: `parts` CTAs per frame, combined by an atomic
+// maximum on the bit pattern (non-negative floats order like their bits; J.xf.mx starts at 0)
+__global__ void __launch_bounds__(256) k_frame_max(AmbJob* __restrict__ jobs, int n_jobs, int parts) {
+    const int j = blockIdx.x / parts, part = blockIdx.x % parts;
     if (j >= n_jobs) return;
     AmbJob& J = jobs[j];
     if (J.xf.kind != AMB_XF_SCALE || J.status != 0) return;
     float mx = 0.f;
-    for (int64_t i = threadIdx.x; i < J.len; i += blockDim.x) {
+    for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < J.len; i += (int64_t)parts * blockDim.x) {
         const int64_t g = J.pos + i;
         const float v = (g >= J.lo && g < J.hi) ? J.p[g - J.base] : 0.f;
         mx = fmaxf(mx, fabsf(v));
@@ -603,7 +607,7 @@ __global__ void k_frame_max(AmbJob* __restrict__ jobs, int n_jobs) {
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmaxf(mx, red[w]);
-        J.xf.mx = mx;
+        if (mx > 0.f) atomicMax(reinterpret_cast<unsigned*>(&J.xf.mx), __float_as_uint(mx));      // (a NaN sample compares false everywhere and is skipped, like Math.abs(NaN) > mx)
     }
 }
 
@@ -2261,6 +2265,10 @@ struct AmbLinkBufs {
     int* first_stop;         // [n_streams] first chain link that did not reproduce its speculation
     unsigned long long* fp_sum;   // [n_streams] refine failures inside the accepted links
     AmbRefineMemo* memo;     // per flat run index: phase A's refine, reused by phase B
+    // Phase B's walk from the phase-A end state of run p is a function of p alone within a pass (the start state, the data and
+    // the successor next[p] are fixed), and a chain rebuilt after a failed speculation mostly consists of the same links: the
+    // outcome is kept per flat run index p and reused by later iterations.  bm_has: 0 = not walked yet, 1 + has otherwise.
+    AmbStreamState* bm_out; AmbFrameRec* bm_rec; int* bm_has;
 };
 
 __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
@@ -2379,8 +2387,27 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
         G.tile_slot = g.tile_slot ? g.tile_slot + (int64_t)s * g.sum_stride : nullptr; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
         G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
+        G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
         G.memo_out = nullptr; G.memo_in = nullptr;
-        if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) L.memo[f].valid = 0; __syncwarp(); }
+        if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) { L.memo[f].valid = 0; L.bm_has[f] = 0; } __syncwarp(); }
+        int bm = -1;                                     // phase B, link after run p: flat index of p
+        if (mode == 1 && i > 0) {
+            bm = L.run_off[s] + L.link_run[f - 1];
+            const int have = L.bm_has[bm];
+            if (have != 0) {
+                // walked in an earlier iteration of this pass: same outcome
+                if (lane == 0) {
+                    const AmbStreamState so = L.bm_out[bm];
+                    L.outB[f] = so; L.hasB[f] = have - 1;
+                    if (have == 2) L.recB[f] = L.bm_rec[bm];
+                    const int run = L.link_run[f];
+                    const bool ok = have == 2 && run >= 0 && L.hasA[L.run_off[s] + run] == 1 && amb_same_link_state(so, L.endA[L.run_off[s] + run]);
+                    if (!ok) atomicMin(&L.first_stop[s], i);
+                }
+                __syncwarp();
+                continue;
+            }
+        }
         if (mode == 1 && L.link_run[f] >= 0) G.memo_in = L.memo + L.run_off[s] + L.link_run[f];
         if (first) {}
         else if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
@@ -2401,12 +2428,99 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
             } else if (mode == 0) { L.endA[f] = st; L.hasA[f] = has; }
             else {
                 L.outB[f] = st; L.hasB[f] = has;
+                if (bm >= 0) { L.bm_out[bm] = st; if (has) L.bm_rec[bm] = *rec; L.bm_has[bm] = 1 + (has ? 1 : 0); }
                 const int run = L.link_run[f];
                 const bool ok = has && run >= 0 && L.hasA[L.run_off[s] + run] == 1 && amb_same_link_state(st, L.endA[L.run_off[s] + run]);
                 if (!ok) atomicMin(&L.first_stop[s], i);
             }
         }
         __syncwarp();
+    }
+}
+
+// Parallel screening of the idle calls of a speculated chain (long captures: a link's idle span can be thousands of calls).
+// After a frame the receiver re-initialises its sums in a call c that follows from the link's start state, and the defect it
+// carries in call k > c is F[k] - F[c]; so whether call k is "cold" - none of its windows a candidate, nothing but the defect
+// update can happen - is known per call and does not need the sequential walker.  One warp per (stream, call): the 16
+// tile summaries under that defect, then the exact float64 window sums of the tiles the summaries cannot clear.  Exact
+// means: decided with a relative margin of 1e-6 on the gates and the candidate test, far above the rounding difference
+// between this defect and the walker's own accumulation of the same terms; a call that is not clearly cold is left to the
+// walker.  cold_tag[call] = c for cold calls (the walker accepts it when its own init_call is c), -1 otherwise.
+__device__ __forceinline__ int64_t amb_link_init_call(const AmbStreamState& st, int64_t block_len) {
+    if (st.state != AMB_RX_IDLE) return -1;
+    if (st.ac_init) return st.init_call;
+    const int64_t c = (st.ac_scan_pos + 2 * AMB_HALF + block_len - 1) / block_len - 1;
+    return c > st.next_call ? c : st.next_call;
+}
+
+__global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float* __restrict__ cleaned, const float* __restrict__ sums,
+                                                    const AmbStreamState* __restrict__ states, int n_streams, AmbLinkBufs L,
+                                                    int32_t* __restrict__ cold_tag, int64_t call_lo, int64_t call_hi) {
+    const int lane = threadIdx.x & 31;
+    const int64_t per = call_hi - call_lo;
+    const int64_t total = (int64_t)n_streams * per;
+    for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * 4) {
+        const int s = (int)(w / per);
+        const int64_t k = call_lo + w % per;
+        if (!L.active[s]) continue;
+        const int n_links = L.n_links[s];
+        // (dense streams - a link every few calls - have nothing to skip)
+        if (n_links <= 0 || (int64_t)n_links * 64 > per) continue;
+        const AmbStreamState cur = states[s];
+        if (k < cur.next_call) continue;
+        const int off = L.run_off[s], lo_f = off + s;
+        // governing link: the last one whose re-initialisation call is before k (binary search; link 0 starts from the current
+        // state, link i from the phase-A end state of the run before it)
+        int a = 0, b = n_links - 1;
+        while (a < b) {
+            const int mid = (a + b + 1) >> 1;
+            const int64_t c = amb_link_init_call(L.endA[off + L.link_run[lo_f + mid - 1]], g.block_len);
+            if (c >= 0 && c < k) a = mid; else b = mid - 1;
+        }
+        const int64_t c = amb_link_init_call(a == 0 ? cur : L.endA[off + L.link_run[lo_f + a - 1]], g.block_len);
+        const int64_t F0 = g.base_g / g.block_len;
+        const int64_t fc = c - F0, fk = k - F0;
+        if (c < 0 || c >= k || fc < 0 || fk >= g.calls_stride) continue;
+        const double* F = g.F + (int64_t)s * g.calls_stride * 3;
+        const double Ep = F[fk * 3] - F[fc * 3], Ea = F[fk * 3 + 1] - F[fc * 3 + 1], Eb = F[fk * 3 + 2] - F[fc * 3 + 2];
+        AmbWalkGeom G;
+        G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
+        G.tile_slot = g.tile_slot + (int64_t)s * g.sum_stride; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
+        G.F = nullptr; G.F_call0 = 0; G.F_calls = 0; G.cold_tag = nullptr; G.memo_out = nullptr; G.memo_in = nullptr;
+        const float* srow = sums + (int64_t)s * g.sum_stride * AMB_SUM_W;
+        const int64_t j0 = (k * g.block_len) >> 8, nt = g.block_len >> 8;          // 16 tiles
+        int hot = 0, unknown = 0;
+        if (lane < nt) {
+            const int64_t jj = j0 + lane, rel = jj - (g.base_g >> 8);
+            if (rel < 0 || rel >= g.sum_stride || (jj << 8) < g.sum_lo) unknown = 1;
+            else hot = amb_tile_hot2(G, srow, jj, rel, Ep, Ea, Eb) ? 1 : 0;
+        }
+        if (__any_sync(0xffffffffu, unknown)) continue;
+        unsigned hm = __ballot_sync(0xffffffffu, hot);
+        bool cold = true;
+        const float* row = cleaned + (int64_t)s * g.stride;
+        const int64_t lo = g.base_g > 0 ? g.base_g : 0;
+        while (hm && cold) {
+            const int t = __ffs((int)hm) - 1;
+            hm &= hm - 1;
+            const int64_t d = ((j0 + t) << 8) - 511;                             // first window of the tile (global position)
+            float x[3][8];
+#pragma unroll
+            for (int seg = 0; seg < 3; seg++)
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const int64_t p = d + 256 * seg + 8 * lane + q; x[seg][q] = (p >= lo && p < g.avail_hi) ? row[p - g.base_g] : 0.f; }
+            double oP[8], oA[8], oB[8];
+            amb_tile_sums_regs(x, lane, oP, oA, oB);
+            int maybe = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (d + 8 * lane + q < 0) continue;
+                const double pa = oP[q] + Ep, aa = oA[q] + Ea, bb = oB[q] + Eb;
+                if (aa > 0.001 * (1.0 - 1e-6) && bb > 0.001 * (1.0 - 1e-6) && pa * pa > 0.5 * aa * bb * (1.0 - 1e-6)) maybe = 1;
+            }
+            if (__any_sync(0xffffffffu, maybe)) cold = false;
+        }
+        if (cold && lane == 0) cold_tag[(int64_t)s * g.calls_stride + fk] = (int32_t)c;
     }
 }
 

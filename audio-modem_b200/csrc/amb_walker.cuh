@@ -20,9 +20,34 @@
 
 enum { AMB_RX_IDLE = 0, AMB_RX_PREAMBLE = 1, AMB_RX_COLLECT = 2 };
 
+// development build (-DAMB_WALK_STATS): event counts of the walkers, read through amb_debug_counter(16 + i)
+//   0 window batches copied from the stored rows, 1 evaluated directly, 2 refines from the screening store, 3 direct refines,
+//   4 refines answered by the memo, 5 cold-call skip rounds, 6 scan calls, 7 refine failures, 8 exact offsets after screening
+#if defined(AMB_WALK_STATS) && defined(__CUDACC__)
+__device__ unsigned long long g_amb_walk_stats[16];
+__device__ __forceinline__ void amb_stat_add(int i, unsigned long long n) { if ((threadIdx.x & 31) == 0) atomicAdd(&g_amb_walk_stats[i], n); }
+#if defined(__CUDA_ARCH__)
+#define AMB_STAT(i) amb_stat_add(i, 1ull)
+#define AMB_STAT_ADD(i, n) amb_stat_add(i, (unsigned long long)(n))
+#define AMB_STAT_T0() const long long stat_t0__ = clock64()
+#define AMB_STAT_T1(i) amb_stat_add(i, (unsigned long long)(clock64() - stat_t0__))
+#else
+#define AMB_STAT_T0() do { } while (0)
+#define AMB_STAT_T1(i) do { } while (0)
+#define AMB_STAT(i) do { } while (0)
+#define AMB_STAT_ADD(i, n) do { } while (0)
+#endif
+#else
+#define AMB_STAT(i) do { } while (0)
+#define AMB_STAT_ADD(i, n) do { } while (0)
+#define AMB_STAT_T0() do { } while (0)
+#define AMB_STAT_T1(i) do { } while (0)
+#endif
+
 struct AmbStreamState {
     int32_t state, ac_init, lag, meta_received, chunk_size, total_chunks;
-    int32_t total_file_size, pad0;      // of the metadata frame in force (ChunkAssembler.totalFileSize)
+    int32_t total_file_size;            // of the metadata frame in force (ChunkAssembler.totalFileSize)
+    int32_t init_call;                  // call in which the running sums were last re-initialised (meaningful while ac_init)
     int64_t ac_scan_pos, pre_pos, frame_end;
     double Ep, Ea, Eb;
     double coarse, fine;
@@ -61,6 +86,9 @@ struct AmbWalkGeom {
     const struct AmbRefineMemo* memo_in;   // phase B: consulted before computing (or NULL)
     const double* F;            // per call: inclusive prefix of the block-boundary defect terms (3 doubles per call)
     int64_t F_call0, F_calls;   // F[(call - F_call0) * 3 + c] valid for 0 <= call - F_call0 < F_calls
+    // Optional (k_cold_calls): cold_tag[call - F_call0] = c when the call was evaluated exactly, in parallel, under the defect a
+    // receiver carries there after re-initialising its sums in call c, and holds no candidate window; -1 otherwise
+    const int32_t* cold_tag;
 };
 
 // screening values in the xc store: a metric in [-1, 1]; AMB_XC_FAIL where the denominator fails its 0.001 test;
@@ -160,6 +188,7 @@ AMB_HD bool amb_tile_hot2(const AmbWalkGeom& G, const float* sums, int64_t jj, i
 // Window sums at cnt consecutive offsets from d0: copied from the scan kernel's store where the tile has a slot,
 // evaluated directly otherwise.
 AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0, int cnt, double* P, double* A, double* B) {
+    AMB_STAT_T0();
     int done = 0;
     while (done < cnt) {
         const int64_t d = d0 + done;
@@ -173,11 +202,14 @@ AMB_HD void amb_eval_windows(const AmbWalkGeom& G, const AmbSig& sig, int64_t d0
             const double* src = G.tri + (int64_t)slot * 768 + (d - tile_first);          // [slot][P | Ra | Rb][256]
             AMB_WARP_FOR(i, seg) { P[done + i] = src[i]; A[done + i] = src[256 + i]; B[done + i] = src[512 + i]; }
             AMB_WARP_SYNC();
+            AMB_STAT(0);
         } else {
+            AMB_STAT(1);
             amb_window_sums(sig, d, seg, P + done, A + done, B + done);
         }
         done += seg;
     }
+    AMB_STAT_T1(9);
 }
 
 // 1 if none of the 16 summary tiles of call k (window-end samples [k*B, (k+1)*B)) can hold a candidate under E
@@ -195,7 +227,9 @@ AMB_HD int amb_call_cold(const AmbWalkGeom& G, const float* sums, int64_t k, dou
 // position = first position of the next call) nothing can happen in a call whose 16 tiles are cold under the defect
 // that will be in force there, E_k = E + F[k] - F[k_now - 1].  Returns how many whole calls from st.next_call can be
 // skipped (< k_end) and advances the state over them.
-AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums, AmbStreamState& st, int64_t k_end, AmbWalkScratch* W) {
+struct AmbColdCache { int64_t base; unsigned hot; int32_t init_call; };     // hot flags of calls base .. base + 31 on the trajectory of init_call
+
+AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums, AmbStreamState& st, int64_t k_end, AmbWalkScratch* W, AmbColdCache& cc) {
     if (!G.F || st.state != AMB_RX_IDLE || !st.ac_init || st.lag != 1) return 0;
     int64_t k = st.next_call;
     if (st.ac_scan_pos != k * G.block_len - 511) return 0;
@@ -205,19 +239,34 @@ AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums,
     const double b0 = G.F[f0 * 3], b1 = G.F[f0 * 3 + 1], b2 = G.F[f0 * 3 + 2];
     int64_t skipped = 0;
     while (k < k_end) {
-        AMB_WARP_FOR(t, 32) {
-            const int64_t kk = k + t, fi = kk - G.F_call0;
-            int cold = 0;
-            if (kk < k_end && fi >= 0 && fi < G.F_calls)
-                cold = amb_call_cold(G, sums, kk, st.Ep + (G.F[fi * 3] - b0), st.Ea + (G.F[fi * 3 + 1] - b1), st.Eb + (G.F[fi * 3 + 2] - b2));
-            W->hot[t] = cold ? 0 : 1;
+        unsigned hot;
+        int valid;
+        if (cc.base >= 0 && cc.init_call == st.init_call && k >= cc.base && k < cc.base + 32) {
+            // flags of an earlier round on the same defect trajectory (a hot call in between was processed by the scan)
+            hot = cc.hot >> (int)(k - cc.base);
+            valid = 32 - (int)(k - cc.base);
+        } else {
+            AMB_STAT(5);
+            AMB_WARP_FOR(t, 32) {
+                const int64_t kk = k + t, fi = kk - G.F_call0;
+                int cold = 0;
+                if (kk < k_end && fi >= 0 && fi < G.F_calls) {
+                    if (G.cold_tag && G.cold_tag[fi] == st.init_call) cold = 1;
+                    else cold = amb_call_cold(G, sums, kk, st.Ep + (G.F[fi * 3] - b0), st.Ea + (G.F[fi * 3 + 1] - b1), st.Eb + (G.F[fi * 3 + 2] - b2));
+                }
+                W->hot[t] = cold ? 0 : 1;
+            }
+            AMB_WARP_SYNC();
+            hot = 0u;
+            for (int t = 0; t < 32; t++) if (W->hot[t]) hot |= 1u << t;
+            AMB_WARP_SYNC();
+            cc.base = k; cc.hot = hot; cc.init_call = st.init_call;
+            valid = 32;
         }
-        AMB_WARP_SYNC();
-        int first = 32;
-        for (int t = 0; t < 32; t++) if (W->hot[t]) { first = t; break; }
-        AMB_WARP_SYNC();
+        int first = hot ? amb_ffs(hot) - 1 : 32;
+        if (first > valid) first = valid;
         k += first; skipped += first;
-        if (first < 32) break;
+        if (first < valid) break;
     }
     if (skipped > 0) {
         const int64_t fi = k - 1 - G.F_call0;
@@ -236,19 +285,77 @@ AMB_HD double amb_resolve_fine(const AmbTables* T, const AmbSig& sig, int64_t po
     return amb_xcorr_at(T, sig, pos, &m) ? m : -INFINITY;
 }
 
-// Refine with the scan kernel's float32 screening values: offsets whose screening metric is within 1e-3 of the
-// maximum are re-evaluated exactly (amb_xcorr_at), so the argmax and the reported metric are the reference's.
-// Falls back to the direct evaluation when the store does not cover [lo, hi] or cannot decide.
+// float32 screening values of preamble-1's correlation metric (modem.js:577-585) at the n offsets lo, lo + 1, ... into v,
+// one warp: a lane takes four consecutive offsets at a time, so a tap is loaded once for four multiply-adds.  Same
+// encoding as the scan kernel's store: the metric, AMB_XC_FAIL where the denominator clearly fails its 0.001 test,
+// AMB_XC_UNSURE where float32 cannot tell.  |value - exact| < 1e-4 (768 taps, sequential float32 sums: n u sum|s t| <=
+// 768 * 6e-8 of the denominator, by Cauchy-Schwarz), inside the 5e-4 the consumers allow.
+AMB_HD void amb_xcorr_screen(const AmbTables* T, const AmbSig& s, int64_t lo, int n, float* v) {
+    const int plen = T->sym_len;
+    const float tE = (float)T->pre1_energy;
+    const float* t = T->pre1;
+    AMB_WARP_FOR(gq, (n + 3) / 4) {
+        const int64_t d = lo + 4 * (int64_t)gq;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s.xf.kind == AMB_XF_NONE && d >= s.lo && d + plen + 3 <= s.hi) {
+            const float* p = s.p + (d - s.base);
+            float a0 = p[0], a1 = p[1], a2 = p[2];
+            for (int i = 0; i < plen; i += 4) {                         // (sym_len is a multiple of 4 in every config)
+                const float a3 = p[i + 3], a4 = p[i + 4], a5 = p[i + 5], a6 = p[i + 6];
+                const float t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3];
+                c[0] = fmaf(a0, t0, c[0]); c[1] = fmaf(a1, t0, c[1]); c[2] = fmaf(a2, t0, c[2]); c[3] = fmaf(a3, t0, c[3]);
+                c[0] = fmaf(a1, t1, c[0]); c[1] = fmaf(a2, t1, c[1]); c[2] = fmaf(a3, t1, c[2]); c[3] = fmaf(a4, t1, c[3]);
+                c[0] = fmaf(a2, t2, c[0]); c[1] = fmaf(a3, t2, c[1]); c[2] = fmaf(a4, t2, c[2]); c[3] = fmaf(a5, t2, c[3]);
+                c[0] = fmaf(a3, t3, c[0]); c[1] = fmaf(a4, t3, c[1]); c[2] = fmaf(a5, t3, c[2]); c[3] = fmaf(a6, t3, c[3]);
+                e[0] = fmaf(a0, a0, e[0]); e[0] = fmaf(a1, a1, e[0]); e[0] = fmaf(a2, a2, e[0]); e[0] = fmaf(a3, a3, e[0]);
+                a0 = a4; a1 = a5; a2 = a6;
+            }
+            // the four windows share all but three samples at either end: Sum s^2 of offset q = that of offset 0 minus the
+            // first q samples plus the q after the window (float32 differences of a few terms: error far below the 1e-3 band)
+            e[1] = e[0] - p[0] * p[0] + p[plen] * p[plen];
+            e[2] = e[1] - p[1] * p[1] + p[plen + 1] * p[plen + 1];
+            e[3] = e[2] - p[2] * p[2] + p[plen + 2] * p[plen + 2];
+        } else {
+            for (int i = 0; i < plen; i++) {
+                const float ti = t[i];
+                for (int q = 0; q < 4; q++) { const float a = amb_sig(s, d + q + i); c[q] = fmaf(a, ti, c[q]); e[q] = fmaf(a, a, e[q]); }
+            }
+        }
+        for (int q = 0; q < 4; q++) {
+            if (4 * gq + q >= n) break;
+            const float d2 = e[q] * tE;
+            float r;
+            if (d2 > 1e-6f * (1.f + 1e-3f)) r = c[q] / sqrtf(d2);
+            else if (d2 < 1e-6f * (1.f - 1e-3f)) r = AMB_XC_FAIL;
+            else r = AMB_XC_UNSURE;
+            if (!(r == r)) r = AMB_XC_UNSURE;                           // NaN samples: let the exact evaluation decide
+            v[4 * gq + q] = r;
+        }
+    }
+    AMB_WARP_SYNC();
+}
+
+// Refine with float32 screening values - the scan kernel's store where it covers [lo, hi], otherwise computed here into vbuf
+// (capacity vcap floats) - : offsets whose screening metric is within 1e-3 of the maximum are re-evaluated exactly
+// (amb_xcorr_at), so the argmax and the reported metric are the reference's.  Falls back to the exact evaluation of every
+// offset when the screening cannot decide.
 AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, int64_t lo, int64_t hi, int64_t p,
-                                   double* scratch, int64_t* pos_out) {
+                                   double* scratch, int64_t* pos_out, float* vbuf = nullptr, int vcap = 0) {
     const int64_t j = (p + 511) >> 8;
     const int raw = G.xc ? amb_tile_slot_raw(G, j) : -1;
     const int slot = raw & AMB_TS_MASK;
     const int64_t base = (j << 8) - 511 - T->fine_radius;
-    if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND))
-        return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
-    const float* v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
     const int n = (int)(hi - lo + 1);
+    const float* v;
+    if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND)) {
+        AMB_STAT(3);
+        if (!vbuf || hi < lo || n > vcap) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
+        amb_xcorr_screen(T, sig, lo, n, vbuf);
+        v = vbuf;
+    } else {
+        AMB_STAT(2);
+        v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
+    }
     float mx = -3.0f;
     bool unsure = false;
     AMB_WARP_FOR(o, n) {
@@ -282,6 +389,7 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
         AMB_WARP_SYNC();
         return -1.0 - (double)mx;
     }
+    AMB_STAT_ADD(8, cnt);
     AMB_WARP_FOR(i, cnt) {
         double m;
         scratch[i] = amb_xcorr_at(T, sig, (int64_t)scratch[32 + i], &m) ? m : -INFINITY;
@@ -391,7 +499,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
     if (st.ac_scan_pos > scan_end) return;
     if (!st.ac_init) {
         if (st.ac_scan_pos < oldest) return;
-        st.Ep = st.Ea = st.Eb = 0.0; st.lag = 0; st.ac_init = 1;
+        st.Ep = st.Ea = st.Eb = 0.0; st.lag = 0; st.ac_init = 1; st.init_call = (int32_t)(tw / G.block_len - 1);
     }
     double best = 0.0;
     int64_t best_pos = -1;
@@ -468,6 +576,16 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
         const int cnt = (int)(d_end - d + 1);
         const int look = d_end < scan_end ? 1 : 0;
         amb_eval_windows(G, sig, d, cnt + look, W->M, W->A, W->B);
+        if (!(best > 0.5)) {
+            // idle: unless some window can pass metric > 0.5 (p^2 > 0.5 a b, tested with a margin far above the rounding of the
+            // reference's quotient) the batch changes nothing - no division, no candidate logic
+            bool maybe = false;
+            AMB_WARP_FOR(i, cnt + look) {
+                const double a = W->A[i] + st.Ea, b = W->B[i] + st.Eb, pp = W->M[i] + st.Ep;
+                if (a > 0.001 && b > 0.001 && pp * pp > 0.5 * a * b * (1.0 - 1e-12)) maybe = true;
+            }
+            if (!amb_warp_any(maybe)) { AMB_WARP_SYNC(); d = d_end + 1; continue; }
+        }
         AMB_WARP_FOR(i, cnt + look) {
             double m;
             W->gate[i] = amb_metric(W->M[i], W->A[i], W->B[i], st, &m);
@@ -495,9 +613,14 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
     int64_t pos;
     double best;
     const AmbRefineMemo* mi = G.memo_in;
-    if (mi && mi->valid && mi->coarse == st.pre_pos && mi->fs == fs && mi->fe == fe) { pos = mi->pos; best = mi->fine; }
-    else best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos);
-    if (best < 0.1 && !AMB_FINE_DEFERRED(best)) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; return; }
+    if (mi && mi->valid && mi->coarse == st.pre_pos && mi->fs == fs && mi->fe == fe) { pos = mi->pos; best = mi->fine; AMB_STAT(4); }
+    else {
+        // (the window-sum arrays of the scratch are free during a refine: they hold the screening row of a direct refine)
+        AMB_STAT_T0();
+        best = amb_fine_xcorr_store(T, G, sig, fs, fe, st.pre_pos, W->x, &pos, reinterpret_cast<float*>(W->M), (int)(3 * 264 * sizeof(double) / sizeof(float)));
+        AMB_STAT_T1(10);
+    }
+    if (best < 0.1 && !AMB_FINE_DEFERRED(best)) { st.state = AMB_RX_IDLE; st.ac_init = 0; st.false_pos++; AMB_STAT(7); return; }
     if (G.memo_out && AMB_LEADER()) { AmbRefineMemo* mo = G.memo_out; mo->coarse = st.pre_pos; mo->fs = fs; mo->fe = fe; mo->pos = pos; mo->fine = best; mo->valid = 1; }
     st.pre_pos = pos; st.fine = best;
     const int64_t max_payload = st.meta_received ? (int64_t)(st.chunk_size ? st.chunk_size : 4096) + 11 : 280;
@@ -510,10 +633,12 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
 AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums, AmbStreamState& st,
                     int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W, int stop_after = 0x7fffffff) {
     int n = 0;
+    AmbColdCache cc;
+    cc.base = -1; cc.hot = 0u; cc.init_call = -1;
     while (st.next_call < k_end) {
-        if (amb_walk_skip_cold_calls(G, sums, st, k_end, W) > 0) continue;
+        { AMB_STAT_T0(); const int64_t sk = amb_walk_skip_cold_calls(G, sums, st, k_end, W, cc); AMB_STAT_T1(11); if (sk > 0) continue; }
         const int64_t tw = (st.next_call + 1) * G.block_len;
-        if (st.state == AMB_RX_IDLE) amb_walk_scan(T, G, sig, sums, st, tw, W);
+        if (st.state == AMB_RX_IDLE) { AMB_STAT(6); AMB_STAT_T0(); amb_walk_scan(T, G, sig, sums, st, tw, W); AMB_STAT_T1(12); }
         else if (st.state == AMB_RX_PREAMBLE) amb_walk_refine(T, G, sig, st, tw, W);
         else if (tw >= st.frame_end) {
             // _checkFrameComplete + _demodulateFrame + _resetToIdle, app.js:900-981
@@ -644,5 +769,5 @@ AMB_HD int amb_run_at_or_after(const AmbRun* runs, int n, int64_t e) {
 AMB_HD bool amb_same_link_state(const AmbStreamState& a, const AmbStreamState& b) {
     return a.state == b.state && a.ac_init == b.ac_init && a.ac_scan_pos == b.ac_scan_pos && a.next_call == b.next_call &&
            a.pre_pos == b.pre_pos && a.frame_end == b.frame_end && a.meta_received == b.meta_received && a.chunk_size == b.chunk_size &&
-           (a.ac_init == 0 || (a.lag == b.lag && a.Ep == b.Ep && a.Ea == b.Ea && a.Eb == b.Eb));
+           (a.ac_init == 0 || (a.lag == b.lag && a.init_call == b.init_call && a.Ep == b.Ep && a.Ea == b.Ea && a.Eb == b.Eb));
 }

@@ -232,7 +232,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     std::vector<uint32_t> bitmap(1 << 16, 0u);        // ChunkAssembler.receivedBitmap (2 Mi chunks)
     std::vector<float> xc;
     const int xc_w = 256 + 2 * T.fine_radius;
-    G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.slot_info = nullptr; G.tsum = nullptr; G.memo_out = nullptr; G.memo_in = nullptr; G.F = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
+    G.tile_slot = nullptr; G.tri = nullptr; G.xc = nullptr; G.xc_w = xc_w; G.slot_info = nullptr; G.tsum = nullptr; G.memo_out = nullptr; G.memo_in = nullptr; G.F = nullptr; G.cold_tag = nullptr; G.F_call0 = 0; G.F_calls = (int64_t)Fpre.size() / 3;
     AmbStreamState st;
     std::memset(&st, 0, sizeof(st));
     st.pre_pos = -1; st.frame_end = -1;

@@ -52,6 +52,10 @@ for it in range(REPS):
     n = m.stream_push(x, device_results=(d_res, d_bytes))
     m.synchronize()
     dt = time.perf_counter() - t0
+    if os.environ.get("AMB_LIB", "").endswith("stats.so"):
+        names = ["rows", "direct", "refine_store", "refine_direct", "refine_memo", "skip_rounds", "scan_calls", "refine_fail", "exact_offsets",
+                 "cyc_eval", "cyc_refine", "cyc_skip", "cyc_scan"]
+        print("walk stats (cumulative):", dict(zip(names, [m.debug_counter(16 + i) for i in range(13)])))
     print("link iterations", m.debug_counter(2) - i0, "passes", m.debug_counter(3) - p0, "slots", m.debug_counter(4), "cand", m.debug_counter(5))
     c = m.stream_counters()
     print(f"[{it}] {N} samples in {dt * 1e3:.2f} ms -> {N / dt / 1e6:.0f} Msamples/s ({4 * N / dt / 1e9:.0f} GB/s), frames {n}, {c}")
