@@ -465,6 +465,20 @@ int64_t amb_debug_read(amb_modem* m, int which, void* out, int64_t cap_bytes) {
     int n = 0;
     cudaMemcpy(&n, m->slot_count.p, 4, cudaMemcpyDeviceToHost);
     if (n > m->slot_cap) n = m->slot_cap;
+#if defined(AMB_WALK_STATS)
+    if (which == 2) {
+        // walk trace (development): rows of AMB_TRACE_W words; reading resets it
+        unsigned int rows = 0;
+        cudaMemcpyFromSymbol(&rows, g_amb_walk_trace_n, 4);
+        if (rows > AMB_TRACE_ROWS) rows = AMB_TRACE_ROWS;
+        int64_t bytes = (int64_t)rows * AMB_TRACE_W * 8;
+        if (bytes > cap_bytes) bytes = cap_bytes;
+        if (bytes > 0) cudaMemcpyFromSymbol(out, g_amb_walk_trace, (size_t)bytes);
+        const unsigned int zero = 0;
+        cudaMemcpyToSymbol(g_amb_walk_trace_n, &zero, 4);
+        return rows;
+    }
+#endif
     const void* src = which == 0 ? m->slot_info.p : which == 1 ? m->tsum.p : nullptr;
     if (!src) return -1;
     int64_t bytes = (int64_t)n * 16;
@@ -1026,6 +1040,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         }
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
         // phase A over every run, and next to it the first link of every stream
+        L.trace_iter = (int)(m->link_iterations * 2);
         LAUNCH("k_link_walk_A", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                             m->dc_next.as<double>(), todo, n_todo, ns, 0, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
         LAUNCH("k_chain_next", k_chain_next<<<flat_grid, 128, 0, m->stream>>>(ns, L));
@@ -1042,10 +1057,11 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
                 LAUNCH("k_cold_calls", k_cold_calls<<<cgrid, 128, 0, m->stream>>>(g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(), ns, L,
                                                                                   m->cold_tag.as<int32_t>(), call_lo, call_hi));
             }
+            L.trace_iter = (int)(m->link_iterations * 2 + 1);
             LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
-            LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi,
+            LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi, g.k_end,
                                                                                               m->nrec.as<int>(), L));
             // frame records -> jobs (redone if another iteration adds records)
             LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(m->nrec.as<int>(), ns, m->job_off.as<int>(), m->total.as<int>()));

@@ -2269,6 +2269,7 @@ struct AmbLinkBufs {
     // the successor next[p] are fixed), and a chain rebuilt after a failed speculation mostly consists of the same links: the
     // outcome is kept per flat run index p and reused by later iterations.  bm_has: 0 = not walked yet, 1 + has otherwise.
     AmbStreamState* bm_out; AmbFrameRec* bm_rec; int* bm_has;
+    int trace_iter;          // development (-DAMB_WALK_STATS): launch sequence number recorded in the walk trace
 };
 
 __device__ __forceinline__ bool tile_is_cand(const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_info, int64_t idx) {
@@ -2417,14 +2418,34 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
         sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
         AmbFrameRec* rec = first ? recs + (int64_t)s * g.rec_cap : (mode == 0 ? L.recA + f : L.recB + f);
-        const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, rec, 1, &scratch[warp], 1);
+#if defined(AMB_WALK_STATS)
+        const long long tr_t0 = clock64();
+        const long long tr_call0 = st.next_call;
+#endif
+        // long pushes (idle-call screening on): phase B and the first link also end at a failed refine (see amb_walk)
+        const int stop_fp = (g.cold_tag != nullptr && (first || mode == 1)) ? 1 : 0;
+        const int has = amb_walk(T, G, sig, sums + (int64_t)s * g.sum_stride * AMB_SUM_W, st, g.k_end, s, rec, 1, &scratch[warp], 1, stop_fp);
+#if defined(AMB_WALK_STATS)
+        if (lane == 0) {
+            unsigned long long* acc = g_amb_warp_acc[(blockIdx.x * 4 + warp) & 16383];
+            const unsigned row = atomicAdd(&g_amb_walk_trace_n, 1u);
+            if (row < AMB_TRACE_ROWS) {
+                unsigned long long* tr = g_amb_walk_trace[row];
+                tr[0] = (unsigned long long)L.trace_iter; tr[1] = (unsigned long long)(mode + (first ? 2 : 0)); tr[2] = (unsigned long long)i; tr[3] = (unsigned long long)has;
+                tr[4] = (unsigned long long)tr_call0; tr[5] = (unsigned long long)st.next_call; tr[6] = (unsigned long long)(clock64() - tr_t0); tr[7] = (unsigned long long)st.false_pos;
+                for (int q = 0; q < 16; q++) tr[8 + q] = acc[q];
+            }
+            for (int q = 0; q < 16; q++) acc[q] = 0ull;
+        }
+#endif
         if (lane == 0) {
             if (first) {
                 st.dc_mean = dc_next[s]; st.written = g.avail_hi;
                 L.first_out[s] = st; L.first_flag[s] = 1;
                 nrec[s] = has;
-                L.active[s] = has ? 1 : 0;       // no frame: the push is exhausted for this stream
-                if (has) atomicAdd(L.n_active, 1);
+                const int more = (has || st.next_call < g.k_end) ? 1 : 0;       // no frame and all calls done: the push is exhausted for this stream
+                L.active[s] = more;
+                if (more) atomicAdd(L.n_active, 1);
             } else if (mode == 0) { L.endA[f] = st; L.hasA[f] = has; }
             else {
                 L.outB[f] = st; L.hasB[f] = has;
@@ -2646,7 +2667,7 @@ __global__ void __launch_bounds__(128) k_verify_copy(int n_streams, int rec_cap,
 }
 
 __global__ void __launch_bounds__(128) k_verify_final(int n_streams, int rec_cap, AmbStreamState* __restrict__ states, const double* __restrict__ dc_next,
-                                                       int64_t avail_hi, int* __restrict__ nrec, AmbLinkBufs L) {
+                                                       int64_t avail_hi, int64_t k_end, int* __restrict__ nrec, AmbLinkBufs L) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams || !L.active[s]) return;
     const int lo = L.run_off[s] + s, stop = L.first_stop[s];
@@ -2660,7 +2681,29 @@ __global__ void __launch_bounds__(128) k_verify_final(int n_streams, int rec_cap
     st.dc_mean = dc_next[s]; st.written = avail_hi;
     st.false_pos = fp_base + (int64_t)L.fp_sum[s];
     states[s] = st;
-    const int again = L.hasB[lo + stop] && total < rec_cap ? 1 : 0;      // stopped at a frame: chain again from its exact end state
+#if defined(AMB_WALK_STATS)
+    {
+        const unsigned row = atomicAdd(&g_amb_walk_trace_n, 1u);
+        if (row < AMB_TRACE_ROWS) {
+            unsigned long long* tr = g_amb_walk_trace[row];
+            const int run = L.link_run[lo + stop];
+            const AmbStreamState o = L.outB[lo + stop];
+            AmbStreamState a = o;
+            int hasA = -1;
+            if (run >= 0) { a = L.endA[L.run_off[s] + run]; hasA = L.hasA[L.run_off[s] + run]; }
+            tr[0] = (unsigned long long)L.trace_iter; tr[1] = 9ull; tr[2] = (unsigned long long)L.n_links[s]; tr[3] = (unsigned long long)stop;
+            tr[4] = (unsigned long long)L.hasB[lo + stop]; tr[5] = (unsigned long long)(long long)run; tr[6] = (unsigned long long)(long long)hasA;
+            tr[7] = (unsigned long long)o.state; tr[8] = (unsigned long long)a.state; tr[9] = (unsigned long long)o.ac_init; tr[10] = (unsigned long long)a.ac_init;
+            tr[11] = (unsigned long long)o.ac_scan_pos; tr[12] = (unsigned long long)a.ac_scan_pos; tr[13] = (unsigned long long)o.next_call; tr[14] = (unsigned long long)a.next_call;
+            tr[15] = (unsigned long long)o.pre_pos; tr[16] = (unsigned long long)a.pre_pos; tr[17] = (unsigned long long)o.frame_end; tr[18] = (unsigned long long)a.frame_end;
+            tr[19] = (unsigned long long)L.n_runs[s];
+            tr[20] = run >= 0 ? (unsigned long long)L.runs[(int64_t)s * L.run_cap + run].first_pos : 0ull;
+            tr[21] = run >= 0 ? (unsigned long long)L.next[L.run_off[s] + run] : 0ull;
+        }
+    }
+#endif
+    // stopped at a frame (or at a failed refine, before the end of the push): chain again from its exact end state
+    const int again = (L.hasB[lo + stop] || st.next_call < k_end) && total < rec_cap ? 1 : 0;
     L.active[s] = again;
     if (again) atomicAdd(L.n_active, 1);
 }

@@ -25,7 +25,15 @@ enum { AMB_RX_IDLE = 0, AMB_RX_PREAMBLE = 1, AMB_RX_COLLECT = 2 };
 //   4 refines answered by the memo, 5 cold-call skip rounds, 6 scan calls, 7 refine failures, 8 exact offsets after screening
 #if defined(AMB_WALK_STATS) && defined(__CUDACC__)
 __device__ unsigned long long g_amb_walk_stats[16];
-__device__ __forceinline__ void amb_stat_add(int i, unsigned long long n) { if ((threadIdx.x & 31) == 0) atomicAdd(&g_amb_walk_stats[i], n); }
+// per-warp accumulators and a trace of the individual walks of k_link_walk (one row per walk: see k_link_walk)
+#define AMB_TRACE_ROWS 16384
+#define AMB_TRACE_W 24
+__device__ unsigned long long g_amb_warp_acc[16384][16];
+__device__ unsigned long long g_amb_walk_trace[AMB_TRACE_ROWS][AMB_TRACE_W];
+__device__ unsigned int g_amb_walk_trace_n;
+__device__ __forceinline__ void amb_stat_add(int i, unsigned long long n) {
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_amb_walk_stats[i], n); g_amb_warp_acc[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & 16383][i] += n; }
+}
 #if defined(__CUDA_ARCH__)
 #define AMB_STAT(i) amb_stat_add(i, 1ull)
 #define AMB_STAT_ADD(i, n) amb_stat_add(i, (unsigned long long)(n))
@@ -629,9 +637,10 @@ AMB_HD void amb_walk_refine(const AmbTables* T, const AmbWalkGeom& G, const AmbS
 }
 
 // Runs calls [st.next_call, k_end) of one stream.  Emits one record per completed frame.
-// Returns the number of records written (stops early, leaving st.next_call behind k_end, if `cap` is hit).
+// Returns the number of records written (stops early, leaving st.next_call behind k_end, if `cap` or `stop_after` is hit,
+// or - with stop_on_fp - right after a failed refine).
 AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums, AmbStreamState& st,
-                    int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W, int stop_after = 0x7fffffff) {
+                    int64_t k_end, int stream, AmbFrameRec* out, int cap, AmbWalkScratch* W, int stop_after = 0x7fffffff, int stop_on_fp = 0) {
     int n = 0;
     AmbColdCache cc;
     cc.base = -1; cc.hot = 0u; cc.init_call = -1;
@@ -639,7 +648,12 @@ AMB_HD int amb_walk(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig,
         { AMB_STAT_T0(); const int64_t sk = amb_walk_skip_cold_calls(G, sums, st, k_end, W, cc); AMB_STAT_T1(11); if (sk > 0) continue; }
         const int64_t tw = (st.next_call + 1) * G.block_len;
         if (st.state == AMB_RX_IDLE) { AMB_STAT(6); AMB_STAT_T0(); amb_walk_scan(T, G, sig, sums, st, tw, W); AMB_STAT_T1(12); }
-        else if (st.state == AMB_RX_PREAMBLE) amb_walk_refine(T, G, sig, st, tw, W);
+        else if (st.state == AMB_RX_PREAMBLE) {
+            amb_walk_refine(T, G, sig, st, tw, W);
+            // a failed refine (app.js:879-884) re-initialises the scan in the next call, like a frame end does: with stop_on_fp the
+            // link ends here too, so that the caller can screen the idle calls after it under the new defect (k_cold_calls)
+            if (stop_on_fp && st.state == AMB_RX_IDLE) { st.next_call++; return n; }
+        }
         else if (tw >= st.frame_end) {
             // _checkFrameComplete + _demodulateFrame + _resetToIdle, app.js:900-981
             if (n >= cap) return n;

@@ -134,7 +134,8 @@ int emu_decode_chunk_frame(int cfg, int mod, int rep, const float* x, int64_t n,
 
 // streaming receiver through the device logic: EMA (sequential, as the reference), tile summaries computed
 // directly, then walk / decode / post until no stream needs another walk.  Pushes of `push_len` samples.
-static int g_use_stores = 1, g_use_links = 1;
+static int g_use_stores = 1, g_use_links = 1, g_stop_fp = 1;      // (g_stop_fp: links also end at a failed refine, as the CUDA path does on long pushes)
+void emu_stop_fp(int on) { g_stop_fp = on; }
 static int64_t g_link_iters = 0, g_link_walks = 0, g_link_pushes = 0;
 void emu_use_stores(int on) { g_use_stores = on; }
 void emu_use_links(int on) { g_use_links = on; }
@@ -160,10 +161,10 @@ static int resolve_links(const AmbTables& T, const AmbWalkGeom& G, const AmbSig&
     // first link from the carried state (always exact)
     {
         AmbFrameRec rec;
-        const int got = amb_walk(&T, G, sig, sums, cur, k_end, 0, &rec, 1, W, 1);
+        const int got = amb_walk(&T, G, sig, sums, cur, k_end, 0, &rec, 1, W, 1, g_stop_fp);
         g_link_walks++;
-        if (!got) { st = cur; return 0; }
-        out[n_out++] = rec;
+        if (!got && cur.next_call >= k_end) { st = cur; return 0; }
+        if (got) out[n_out++] = rec;
     }
     for (int iter = 0; iter < 1 << 20; iter++) {
         g_link_iters++;
@@ -187,12 +188,13 @@ static int resolve_links(const AmbTables& T, const AmbWalkGeom& G, const AmbSig&
         for (int i = 0; i < m; i++) in[i] = i == 0 ? cur : endA[chain[i - 1]];
         for (int i = 0; i < m; i++) {          // phase B: independent walks (parallel on the GPU)
             AmbStreamState s = in[i];
-            hasB[i] = amb_walk(&T, G, sig, sums, s, k_end, 0, &recB[i], 1, W, 1);
+            hasB[i] = amb_walk(&T, G, sig, sums, s, k_end, 0, &recB[i], 1, W, 1, g_stop_fp);
             outB[i] = s; g_link_walks++;
         }
         bool redo = false;
         for (int i = 0; i < m; i++) {
             if (hasB[i]) out[n_out++] = recB[i];
+            if (!hasB[i] && outB[i].next_call < k_end) { cur = outB[i]; redo = true; break; }      // ended at a failed refine (stop_on_fp)
             if (!hasB[i]) { st = outB[i]; if (getenv("EMU_DEBUG")) fprintf(stderr, "resolve: meta %d runs %d frames %d iterations %d\n", st.meta_received, n, n_out, iter + 1); return n_out; }
             const bool is_run = i < (int)chain.size();
             const bool ok = is_run && hasA[chain[i]] == hasB[i] && amb_same_link_state(outB[i], endA[chain[i]]);

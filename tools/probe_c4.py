@@ -56,6 +56,23 @@ for it in range(REPS):
         names = ["rows", "direct", "refine_store", "refine_direct", "refine_memo", "skip_rounds", "scan_calls", "refine_fail", "exact_offsets",
                  "cyc_eval", "cyc_refine", "cyc_skip", "cyc_scan"]
         print("walk stats (cumulative):", dict(zip(names, [m.debug_counter(16 + i) for i in range(13)])))
+    if os.environ.get("AMB_LIB", "").endswith("stats.so"):
+        import ctypes as C
+        import numpy as np
+        tr = np.zeros((16384, 24), np.uint64)
+        rows = int(m._L.amb_debug_read(m._h, 2, C.c_void_p(tr.ctypes.data), tr.nbytes))
+        tr = tr[:max(0, min(rows, 16384))].astype(np.int64)
+        print("trace rows", rows)
+        for r in tr[tr[:, 1] == 9]:
+            print("  verify launch %d: n_links %d stop %d hasB %d run %d hasA %d | state %d/%d ac_init %d/%d scan_pos %d/%d next_call %d/%d pre_pos %d/%d frame_end %d/%d | n_runs %d run.first_pos %d next[run] %d" % tuple(r[[0] + list(range(2, 22))]))
+        tr = tr[tr[:, 1] != 9]
+        for it in sorted(set(tr[:, 0].tolist())):
+            sel = tr[tr[:, 0] == it]
+            top = sel[np.argsort(-sel[:, 6])][:4]
+            print(f" launch {it} ({'B' if it & 1 else 'A'}): {len(sel)} walks, sum {sel[:, 6].sum() / 1e6:.2f} Mcyc, max {sel[:, 6].max() / 1e6:.3f} Mcyc")
+            for r in top:
+                print("   mode %d link %d has %d calls %d..%d cyc %d fp %d | rows %d direct %d rstore %d rdirect %d memo %d skiprounds %d scancalls %d rfail %d exact %d | cyc eval %d refine %d skip %d scan %d" %
+                      (r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], r[16], r[17], r[18], r[19], r[20]))
     print("link iterations", m.debug_counter(2) - i0, "passes", m.debug_counter(3) - p0, "slots", m.debug_counter(4), "cand", m.debug_counter(5))
     c = m.stream_counters()
     print(f"[{it}] {N} samples in {dt * 1e3:.2f} ms -> {N / dt / 1e6:.0f} Msamples/s ({4 * N / dt / 1e9:.0f} GB/s), frames {n}, {c}")
