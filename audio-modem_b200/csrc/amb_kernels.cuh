@@ -1351,47 +1351,61 @@ __global__ void k_apply_xform(const float* __restrict__ x, int64_t stride, const
         out[(int64_t)r * stride + i] = amb_xform(f, x[(int64_t)r * stride + i]);
 }
 
-// Schmidl-Cox metric at every offset of a recording (modem.js:304-309), float64, gate = min_energy.
-// tile t covers window-end samples [4096 t, +4096), i.e. offsets d = q - 511.  metric[d] = -1 where the
-// gate fails.  Also writes the per-tile maximum.
+// Schmidl-Cox metric of a recording (modem.js:304-309), float64, gate = min_energy.
+// tile t covers window-end samples [4096 t, +4096), i.e. offsets d = q - 511.  k_metric writes only the per-tile maximum;
+// k_argmax evaluates the few tiles that can hold the maximum again (same routine, same values) instead of reading a stored
+// metric per sample back from HBM.
+struct AmbTileScratch { float* c; double* ST; double* SQ; double* tot_t; double* tot_q; };
+__device__ __forceinline__ AmbTileScratch amb_tile_scratch(unsigned char* smem_raw) {
+    AmbTileScratch w;
+    w.c = reinterpret_cast<float*>(smem_raw);
+    w.ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
+    w.SQ = w.ST + (AMB_SPAN + 1);
+    w.tot_t = w.SQ + (AMB_SPAN + 1);
+    w.tot_q = w.tot_t + 256;
+    return w;
+}
+// prefix sums of one tile (256 threads); afterwards amb_tile_metric(w, jj, ...) gives the metric of offset index jj * 256 + 1 + tid
+__device__ __forceinline__ void amb_tile_prefix(const AmbTileScratch& w, const float* __restrict__ src, int64_t n, int64_t q0) {
+    for (int i = threadIdx.x; i < AMB_SPAN; i += 256) {
+        const int64_t a = q0 - AMB_HALO + i;
+        w.c[i] = (a >= 0 && a < n) ? src[a] : 0.0f;
+    }
+    __syncthreads();
+    block_prefix(w.c, w.ST, w.SQ, w.tot_t, w.tot_q);
+}
+// metric at local index dl (offset d = q0 - 512 + dl), -1 where the gate fails; false when d is outside the recording
+__device__ __forceinline__ bool amb_tile_metric(const AmbTileScratch& w, int dl, int64_t q0, int64_t n, double min_energy, int64_t* d_out, double* m_out) {
+    const int64_t d = q0 - AMB_HALO + dl;
+    if (!(d >= 0 && d + 2 * AMB_HALF <= n)) return false;
+    const double P = w.ST[dl + 256] - w.ST[dl], A = w.SQ[dl + 256] - w.SQ[dl], B = w.SQ[dl + 512] - w.SQ[dl + 256];
+    double m = -1.0;
+    if (A > min_energy && B > min_energy) m = (P * P) / (A * B);
+    *d_out = d; *m_out = m;
+    return true;
+}
+
 __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
-                                                 int64_t n_default, double min_energy, double* __restrict__ metric, int tiles,
-                                                 double* __restrict__ tile_max) {
+                                                 int64_t n_default, double min_energy, int tiles, double* __restrict__ tile_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* c = reinterpret_cast<float*>(smem_raw);
-    double* ST = reinterpret_cast<double*>(smem_raw + AMB_SPAN * 4);
-    double* SQ = ST + (AMB_SPAN + 1);
-    double* tot_t = SQ + (AMB_SPAN + 1);
-    double* tot_q = tot_t + 256;
+    const AmbTileScratch w = amb_tile_scratch(smem_raw);
     const int tid = threadIdx.x;
     AMB_SPLIT_BID(tiles, r, tile)
     const int64_t n = lens ? lens[r] : n_default;
     const int64_t q0 = (int64_t)tile * AMB_TILE;
-    const float* src = y + (int64_t)r * stride;
-    for (int i = tid; i < AMB_SPAN; i += 256) {
-        const int64_t a = q0 - AMB_HALO + i;
-        c[i] = (a >= 0 && a < n) ? src[a] : 0.0f;
-    }
-    __syncthreads();
-    block_prefix(c, ST, SQ, tot_t, tot_q);
+    if (q0 - AMB_HALO + 1 + 2 * AMB_HALF > n) { if (tid == 0) tile_max[(int64_t)r * tiles + tile] = -1.0; return; }      // no window of this tile lies inside the recording
+    amb_tile_prefix(w, y + (int64_t)r * stride, n, q0);
     double best = -1.0;
     for (int jj = 0; jj < AMB_TILE / 256; jj++) {
-        const int dl = jj * 256 + 1 + tid;
-        const int64_t d = q0 - AMB_HALO + dl;
-        if (d >= 0 && d + 2 * AMB_HALF <= n) {
-            const double P = ST[dl + 256] - ST[dl], A = SQ[dl + 256] - SQ[dl], B = SQ[dl + 512] - SQ[dl + 256];
-            double m = -1.0;
-            if (A > min_energy && B > min_energy) m = (P * P) / (A * B);
-            metric[(int64_t)r * stride + d] = m;
-            best = fmax(best, m);
-        }
+        int64_t d; double m;
+        if (amb_tile_metric(w, jj * 256 + 1 + tid, q0, n, min_energy, &d, &m)) best = fmax(best, m);
     }
     __shared__ double red[8];
     best = warp_maxd(best);
     if ((tid & 31) == 0) red[tid >> 5] = best;
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < 8; w++) best = fmax(best, red[w]);
+        for (int wv = 1; wv < 8; wv++) best = fmax(best, red[wv]);
         tile_max[(int64_t)r * tiles + tile] = best;
     }
 }
@@ -1401,11 +1415,14 @@ __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int
 // within 1e-9 of the maximum count as tied.  With noise in the signal the maximum is unique and this kernel
 // decides.  Any tie (a noise-free plateau, or separate offsets such as a junction of two identical symbols)
 // is decided in the reference by its own rounding sequence: exactly equal values on an even-bin plateau (first
-// wins), last-ulp differences on an odd-bin plateau after DC removal.  `ambiguous` is then set and k_replay
-// settles it with the reference's own sequential recurrence.
-__global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metric, int64_t stride, const int64_t* __restrict__ lens,
-                                                 int64_t n_default, const double* __restrict__ tile_max, int tiles,
-                                                 int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous) {
+// wins), last-ulp differences on an odd-bin plateau after DC removal.  `ambiguous` is then set, tie_range gets the
+// first and last tied offset, and k_replay settles it with the reference's own sequential recurrence.
+__global__ void __launch_bounds__(256) k_argmax(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
+                                                 int64_t n_default, double min_energy, const double* __restrict__ tile_max, int tiles,
+                                                 int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous,
+                                                 int64_t* __restrict__ tie_range /*[n][2]*/) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AmbTileScratch w = amb_tile_scratch(smem_raw);
     const int r = blockIdx.x, tid = threadIdx.x;
     const int64_t n = lens ? lens[r] : n_default;
     __shared__ double sbest;
@@ -1420,19 +1437,20 @@ __global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metri
     b = warp_maxd(b);
     if ((tid & 31) == 0) red[tid >> 5] = b;
     __syncthreads();
-    if (tid == 0) { for (int w = 1; w < 8; w++) b = fmax(b, red[w]); sbest = b; }
+    if (tid == 0) { for (int wv = 1; wv < 8; wv++) b = fmax(b, red[wv]); sbest = b; }
     __syncthreads();
     const double best = sbest;
     if (!(best > 0.0)) { if (tid == 0) { idx_out[r] = -1; best_out[r] = 0.0; ambiguous[r] = 0; } return; }
     const double thr = best * (1.0 - 1e-9);
-    const int64_t end = n - 2 * AMB_HALF;
     long long first = (long long)1 << 62, last = -1, count = 0;
     for (int t = 0; t < used && t < tiles; t++) {
-        if (tile_max[(int64_t)r * tiles + t] < thr) continue;
-        const int64_t d_lo = (int64_t)t * AMB_TILE - 511, d_hi = d_lo + AMB_TILE - 1;
-        for (int64_t d = d_lo + tid; d <= d_hi; d += 256) {
-            if (d < 0 || d > end) continue;
-            if (metric[(int64_t)r * stride + d] >= thr) { if (d < first) first = d; if (d > last) last = d; count++; }
+        if (tile_max[(int64_t)r * tiles + t] < thr) continue;            // (uniform over the CTA)
+        const int64_t q0 = (int64_t)t * AMB_TILE;
+        __syncthreads();
+        amb_tile_prefix(w, y + (int64_t)r * stride, n, q0);
+        for (int jj = 0; jj < AMB_TILE / 256; jj++) {
+            int64_t d; double m;
+            if (amb_tile_metric(w, jj * 256 + 1 + tid, q0, n, min_energy, &d, &m) && m >= thr) { if (d < first) first = d; if (d > last) last = d; count++; }
         }
     }
     atomicMin(&sfirst, first); atomicMax(&slast, last); atomicAdd((unsigned long long*)&scount, (unsigned long long)count);
@@ -1440,14 +1458,19 @@ __global__ void __launch_bounds__(256) k_argmax(const double* __restrict__ metri
     if (tid == 0) {
         best_out[r] = best;
         ambiguous[r] = scount > 1 ? 1 : 0;
+        tie_range[2 * r] = (int64_t)sfirst; tie_range[2 * r + 1] = (int64_t)slast;
         idx_out[r] = best > 0.5 ? (int64_t)sfirst : -1;
     }
 }
 
-// Sequential float64 replay of detectPreamble (modem.js:292-318) for recordings whose maximum is tied
-// between separate offsets: one thread per recording, same operation order as the reference.
+// Sequential float64 replay of detectPreamble (modem.js:292-318) for recordings whose maximum is tied between separate
+// offsets: one thread per recording, same operation order as the reference.  The sliding sums must be carried from offset 0
+// (their rounding depends on the whole history), but the metric only matters at the tied offsets [lo, hi]: every other offset
+// is below the maximum by more than the two evaluations can differ, and the first maximum among the tied ones is the answer.
+// Eight samples of each of the three taps are loaded ahead of the dependent additions.
 __global__ void k_replay(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int n,
-                         double min_energy, const int* __restrict__ ambiguous, int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
+                         double min_energy, const int* __restrict__ ambiguous, const int64_t* __restrict__ tie_range,
+                         int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n || !ambiguous[r]) return;
     const int64_t len = lens ? lens[r] : n_default;
@@ -1459,8 +1482,23 @@ __global__ void k_replay(const float* __restrict__ y, int64_t stride, const int6
     }
     double best = 0; int64_t best_idx = -1;
     const int64_t end = len - 2 * AMB_HALF;
-    for (int64_t d = 0; d <= end; d++) {
-        if (ra > min_energy && rb > min_energy) {
+    const int64_t lo = tie_range[2 * r], hi = tie_range[2 * r + 1] < end ? tie_range[2 * r + 1] : end;
+    int64_t d = 0;
+    // offsets before the tied range: slide only
+    for (; d + 8 <= lo; d += 8) {
+        float ao[8], mid[8], bi[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { ao[k] = s[d + k]; mid[k] = s[d + k + AMB_HALF]; bi[k] = s[d + k + 2 * AMB_HALF]; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double a0 = ao[k], m0 = mid[k], b0 = bi[k];
+            p = amb_add(p, amb_sub(amb_mul(m0, b0), amb_mul(a0, m0)));
+            ra = amb_add(ra, amb_sub(amb_mul(m0, m0), amb_mul(a0, a0)));
+            rb = amb_add(rb, amb_sub(amb_mul(b0, b0), amb_mul(m0, m0)));
+        }
+    }
+    for (; d <= hi; d++) {
+        if (d >= lo && ra > min_energy && rb > min_energy) {
             const double m = amb_div(amb_mul(p, p), amb_mul(ra, rb));
             if (m > best) { best = m; best_idx = d; }
         }

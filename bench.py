@@ -1,23 +1,38 @@
 #!/usr/bin/env python
-"""bench.py — throughput of the OFDM receive hot path on B200, BASELINE.json's metric on its config C2.
+"""bench.py — throughput of the OFDM receive hot path on B200, BASELINE.json's metric (RX audio Msamples/s, payload MB/s)
+on its five configs.
 
-Workload (config.workload = "C2"): a 16-QAM chunked stream — 4 KB chunks as OFDM frames of 28,431 samples
-(buildDataChunkFrame, modem.js:763), AWGN at 25 dB relative to the frame-core power, received by the streaming
-path (EMA DC removal, Schmidl-Cox scan, refine, collect, demodulate, CRC-32; app.js:749-981).  Synthetic data:
-chunk bytes and noise come from counter-based generators, frames are built on the device by the float64-faithful
-transmit path (bit-identical to the reference's frames).  One "step" = one push of `frames_per_step` whole frames.
+  --workload c2 (default at --gpus 1): 16-QAM chunked stream — 4 KB chunks as OFDM frames of 28,431 samples
+      (buildDataChunkFrame, modem.js:763), AWGN 25 dB relative to the frame-core power, received by the streaming path
+      (EMA DC removal, Schmidl-Cox scan, refine, collect, demodulate, CRC-32; app.js:749-981).  One step = one push of
+      `--frames-per-step` whole frames of one stream.
+  --workload c5 (default at --gpus N > 1): many concurrent 16-QAM streams, each metadata + 8 data frames as in c2,
+      pushed as [n_streams][8 x 4096] sections.  8,192 streams per GPU (65,536 over the 8 GPUs of a box): weak scaling,
+      streams sharded by rank (audio_modem_b200.shard), no collective on the hot path.  One step = one push of all the
+      rank's streams; the resident signal is periodic (the streams repeat their 9 frames).
+  --workload c4: narrowband long-capture search — one 1-hour 44.1 kHz capture (158.76 M samples) with a metadata frame
+      and 12 data frames far apart over a -30 dBFS noise floor.  One step = one push of the whole capture.
+  --workload c3: BPSK / BPSK-repeat acoustic recordings through multipath + CFO + AWGN 20 dB, 10,000 recordings per
+      step (half each mode), decoded as two batches (decodeReceivedSignal, modem.js:557-654).
+  --workload c1: QPSK loopback — buildTransmitSignal(32 KB) -> decodeReceivedSignal, a batch of 64 recordings per step.
+  --workload all: every workload in turn, one JSON line each (c2 last).
 
-  value : whole-job Msamples/s with the step inputs already resident in HBM (device time, CUDA events on the
-          library's stream, max over ranks).  Inputs cycle over several distinct segments, each larger than L2.
-  e2e   : the same metric through the host-buffer call (amb_stream_push with AMB_MEM_HOST from pinned memory):
-          host->device copy of the samples and device->host copy of results and decoded bytes inside the timed region.
+Synthetic data: payload bytes and noise come from counter-based generators; frames are built by the library's own
+float64-faithful transmit path (bit-identical to the reference's frames).
+
+  value : whole-job Msamples/s with the step inputs already resident in HBM (device time, CUDA events on the library's
+          stream, max over ranks).  Inputs are larger than L2 and cycle over distinct segments.
+  e2e   : the same metric through the host-buffer call (AMB_MEM_HOST from page-locked memory): host->device copy of the
+          samples and device->host copy of results and decoded bytes inside the timed region.
   roofline : the kernel with the largest share of the timed region, algorithmic bytes / its mean launch duration
-          (per-kernel CUDA events recorded by the library during the timed region) against MEASURED_PEAKS.json.
+          (per-kernel CUDA events recorded by the library in a separate pass over the same steps) against
+          MEASURED_PEAKS.json; `whole_step` is the same for the whole step.
   cpu_baseline : the oracle (C++ float64 restatement of modem.js/app.js; Node is not available) on the host cores.
 
-`--impl reference` times that CPU path alone (all host cores) on the same config, metric and unit.
+`--impl reference` times that CPU path alone (all host cores) on the same workload, metric and unit.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -29,13 +44,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG, MOD, REP, CHUNK = "standard", "QAM16", 1, 4096
-FRAME = 28431            # samples per data-chunk frame incl. silences (2205 + 44*576 + 882)
+FRAME = 28431            # samples per 16-QAM data-chunk frame incl. silences (2205 + 44*576 + 882)
 CORE = 25344             # preamble-1 .. last data symbol
 META = 16416
 SNR_DB = 25.0
 METRIC = "rx_audio_msamples_per_s"
 UNIT = "Msamples/s"
+DTYPE = "f32+f64-guard"  # float32 symbol pipeline with a float64 margin guard and float64-faithful fallback; float64 window sums
+C5_STREAMS_PER_GPU = 8192
+C5_K = 8
+C5_PUSH_BLOCKS = 8
+MODES = {"16-QAM": ("standard", "QAM16", 1, 4096), "QPSK": ("standard", "QPSK", 1, 2048), "BPSK-ACOUSTIC": ("acoustic", "BPSK", 1, 512),
+         "BPSK-REPEAT": ("acoustic", "BPSK", 3, 512), "BPSK-NARROW": ("narrowband", "BPSK", 3, 512)}
+WORKLOAD_TEXT = {
+    "c1": "C1: QPSK loopback, buildTransmitSignal(32 KB) -> decodeReceivedSignal, 392,418-sample recordings, batch per step",
+    "c2": "C2: 16-QAM chunked stream, 4 KB chunks as 28,431-sample OFDM frames, AWGN 25 dB, streaming preamble scan + CRC-32",
+    "c3": "C3: BPSK and BPSK-repeat acoustic recordings over multipath + CFO + AWGN 20 dB, batched decodeReceivedSignal",
+    "c4": "C4: narrowband long-capture search, 1-hour 44.1 kHz capture with sparse frames over a -30 dBFS noise floor, one push",
+    "c5": "C5: concurrent 16-QAM streams (metadata + 8 chunk frames each, AWGN 25 dB), pushed as [n_streams][8 x 4096] sections",
+}
 
 
 def parse():
@@ -44,92 +71,152 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5", "all"])
     ap.add_argument("--frames-per-step", type=int, default=int(os.environ.get("AMB_FRAMES_PER_STEP", "16384")))
-    ap.add_argument("--segments", type=int, default=3, help="distinct resident input segments cycled through")
+    ap.add_argument("--segments", type=int, default=3, help="c2: distinct resident input segments cycled through")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("AMB_C5_STREAMS", str(C5_STREAMS_PER_GPU))), help="c5: streams per GPU")
+    ap.add_argument("--recordings", type=int, default=10000, help="c3: recordings per step (half per mode)")
+    ap.add_argument("--c1-batch", type=int, default=64)
+    ap.add_argument("--c4-seconds", type=int, default=3600)
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shard-probe", action="store_true", help="c2 at one GPU: skip the extra c5 measurement (the N = 1 point of the c5 scaling curve)")
     return ap.parse_args()
 
 
-def config_dict(args, extra=None):
-    d = {"workload": "C2: 16-QAM chunked stream, 4 KB chunks as 28,431-sample OFDM frames, AWGN 25 dB, streaming preamble scan + CRC-32",
-         "ofdm_config": CFG, "constellation": MOD, "repetition": REP, "chunk_bytes": CHUNK, "frames_per_step": args.frames_per_step,
-         "samples_per_step": args.frames_per_step * FRAME, "block_len": 4096, "snr_db": SNR_DB,
-         "l2_policy": "inputs larger than L2 (step input %.0f MB, %d distinct segments cycled)" % (args.frames_per_step * FRAME * 4 / 1e6, args.segments),
-         "parallelism": "streams sharded by rank, no collective on the hot path"}
-    if extra:
-        d.update(extra)
-    return d
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+def _threads_run(work, threads):
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0
 
 
-# ------------------------------------------------------------------------------------------------ CPU leg (oracle)
-def cpu_leg(steps, warmup, frames_per_thread, threads=None, budget_s=None):
-    """Times the oracle's streaming receiver on `threads` host threads, each decoding its own copy of one stream
-    segment (metadata + frames_per_thread data frames) per step.  Returns (Msamples/s, payload MB/s, cores, sample)."""
+def _cpu_loop(one_step, steps, warmup, budget_s):
+    for _ in range(warmup):
+        one_step()
+    times, t_begin = [], time.perf_counter()
+    for _ in range(steps):
+        times.append(one_step())
+        if budget_s and time.perf_counter() - t_begin > budget_s:
+            break
+    return times
+
+
+def cpu_leg_stream(mode, frames_per_thread, steps, warmup, threads=None, budget_s=None, long_capture_s=0):
+    """The oracle's StreamingReceiver (app.js:749-981 restated) on `threads` host threads, each decoding its own copy of
+    one stream segment per step.  c2 / c5: metadata + frames_per_thread data frames with AWGN 25 dB; c4: `long_capture_s`
+    seconds of the narrowband capture (noise floor -30 dBFS, metadata frame + one data frame)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    cfg, mod, rep, chunk = MODES[mode]
+    threads = threads or (os.cpu_count() or 1)
+    if long_capture_s:
+        n = long_capture_s * 44100 // 4096 * 4096
+        rng = np.random.default_rng(4)
+        x = (rng.standard_normal(n) * 10 ** (-30 / 20)).astype(np.float32)
+        meta = O.buildMetadataFrame(cfg, 1, chunk, chunk, "cap.bin", mod, rep)
+        fr = O.buildDataChunkFrame(cfg, O.synthBytes(40, 0, chunk), 0, mod, rep)
+        p = 2 * 44100
+        x[p:p + len(meta)] += meta
+        p += len(meta) + 8 * 44100
+        x[p:p + len(fr)] += fr
+        expect_ok = 2
+        what = f"{long_capture_s} s of the capture ({n} samples: metadata + 1 data frame over the noise floor)"
+    else:
+        parts = [O.buildMetadataFrame(cfg, frames_per_thread, frames_per_thread * chunk, chunk, "bench.bin", mod, rep)]
+        for i in range(frames_per_thread):
+            parts.append(O.buildDataChunkFrame(cfg, O.synthBytes(2, i, chunk), i, mod, rep))
+        x = np.concatenate(parts)
+        p = O.power(parts[1][2205:2205 + CORE])
+        x = O.addAwgnCtr(x, (p / 10 ** (SNR_DB / 10)) ** 0.5, 3)
+        n = (len(x) + 4095) // 4096 * 4096
+        x = np.concatenate([x, np.zeros(n - len(x), np.float32)])
+        expect_ok = frames_per_thread + 1
+        what = f"metadata + {frames_per_thread} data frames = {n} samples"
+    ok, pb = [0] * threads, [0] * threads
+
+    def work(t):
+        ok[t], pb[t] = O.benchStream(cfg, mod, rep, x)     # ctypes releases the GIL: the C++ runs in parallel
+
+    times = _cpu_loop(lambda: _threads_run(work, threads), steps, warmup, budget_s)
+    assert all(o >= expect_ok - (1 if long_capture_s else 0) for o in ok), ok
+    total = sum(times)
+    return {"value": len(times) * threads * n / total / 1e6, "payload_mb_per_s": len(times) * sum(pb) / total / 1e6, "cores": threads,
+            "sample": f"{threads} threads x ({what}) per step, {len(times)} steps", "ms_per_step": total / len(times) * 1e3,
+            "samples_per_step": threads * n}
+
+
+def cpu_leg_batch(modes, payload, steps, warmup, threads=None, budget_s=None, channel=True):
+    """The oracle's decodeReceivedSignal (modem.js:557-654 restated) on `threads` host threads, one recording per thread and step."""
     import numpy as np
 
     from oracle import oracle as O
 
     threads = threads or (os.cpu_count() or 1)
-    parts = [O.buildMetadataFrame(CFG, frames_per_thread, frames_per_thread * CHUNK, CHUNK, "bench.bin", MOD, REP)]
-    for i in range(frames_per_thread):
-        parts.append(O.buildDataChunkFrame(CFG, O.synthBytes(2, i, CHUNK), i, MOD, REP))
-    x = np.concatenate(parts)
-    p = O.power(parts[1][2205:2205 + CORE])
-    x = O.addAwgnCtr(x, (p / 10 ** (SNR_DB / 10)) ** 0.5, 3)
-    n = (len(x) + 4095) // 4096 * 4096
-    x = np.concatenate([x, np.zeros(n - len(x), np.float32)])
-    ok = [0] * threads
-    pb = [0] * threads
+    recs = []
+    for i, mode in enumerate(modes):
+        cfg, mod, rep, _ = MODES[mode]
+        x = O.buildTransmitSignal(cfg, O.randomBytes(1000 + i, payload), mod, "rec", rep)
+        if channel:
+            y = O.multipath(x, [0, 23, 57], [1.0, 0.5, 0.25])
+            y = O.cfo(y, 0.03)
+            x = O.addAwgn(y, float(np.sqrt(O.power(x[22050:][:20000]) / 100.0)), 1000 + i)
+        recs.append((cfg, mod, rep, x.astype(np.float32)))
+    ok, pb = [0] * threads, [0] * threads
 
     def work(t):
-        ok[t], pb[t] = O.benchStream(CFG, MOD, REP, x)     # ctypes releases the GIL: the C++ runs in parallel
+        cfg, mod, rep, x = recs[t % len(recs)]
+        r = O.decodeReceivedSignal(cfg, x, mod, rep)
+        ok[t] = int(bool(r.get("crcValid")))
+        pb[t] = r.get("dataLen", 0) if r.get("crcValid") else 0
 
-    def one_step():
-        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        t0 = time.perf_counter()
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        return time.perf_counter() - t0
-
-    for _ in range(warmup):
-        one_step()
-    times = []
-    t_begin = time.perf_counter()
-    for _ in range(steps):
-        times.append(one_step())
-        if budget_s and time.perf_counter() - t_begin > budget_s:
-            break
-    assert all(o == frames_per_thread + 1 for o in ok), ok       # every frame found with a valid CRC
+    times = _cpu_loop(lambda: _threads_run(work, threads), steps, warmup, budget_s)
     total = sum(times)
-    samples = len(times) * threads * n
-    payload = len(times) * sum(pb)
-    sample = f"{threads} threads x (metadata + {frames_per_thread} data frames = {n} samples) per step, {len(times)} steps"
-    return samples / total / 1e6, payload / total / 1e6, threads, sample, total / len(times) * 1e3
+    n = sum(len(recs[t % len(recs)][3]) for t in range(threads))
+    return {"value": len(times) * n / total / 1e6, "payload_mb_per_s": len(times) * sum(pb) / total / 1e6, "cores": threads,
+            "sample": f"{threads} threads x one recording ({', '.join(modes)}; {n // threads} samples on average) per step, {len(times)} steps",
+            "ms_per_step": total / len(times) * 1e3, "samples_per_step": n}
 
 
-def run_reference(args, rank):
+def cpu_leg(workload, steps, warmup, budget_s=None, threads=None):
+    if workload == "c2":
+        return cpu_leg_stream("16-QAM", 64, steps, warmup, threads, budget_s)
+    if workload == "c5":
+        return cpu_leg_stream("16-QAM", C5_K, steps, warmup, threads, budget_s)
+    if workload == "c4":
+        return cpu_leg_stream("BPSK-NARROW", 0, steps, warmup, threads, budget_s, long_capture_s=30)
+    if workload == "c3":
+        return cpu_leg_batch(["BPSK-ACOUSTIC", "BPSK-REPEAT"], 512, steps, warmup, threads, budget_s)
+    return cpu_leg_batch(["QPSK"], 32768, steps, warmup, threads, budget_s, channel=False)
+
+
+def run_reference(args, rank, workload):
     if rank != 0:
         return
-    v, pmb, cores, sample, ms = cpu_leg(args.steps, args.warmup, frames_per_thread=64)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "payload_mb_per_s": pmb,
-            "config": config_dict(args, {"reference_note": "CPU path = C++ float64 restatement of modem.js + app.js StreamingReceiver (oracle/); "
-                                         "Node.js is not installed, so modem.js itself cannot run here"}),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    r = cpu_leg(workload, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "payload_mb_per_s": r["payload_mb_per_s"],
+            "config": {"workload": WORKLOAD_TEXT[workload], "samples_per_step": r["samples_per_step"], "cpu_threads": r["cores"], "block_len": 4096,
+                       "note": "CPU path = C++ float64 restatement of modem.js + app.js StreamingReceiver (oracle/), one stream or recording per "
+                               "host thread; Node.js is not installed, so modem.js itself cannot run here.  The step is a bounded sample of the "
+                               "workload (the GPU arm's step is larger); the metric is a rate, so the two compare"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up until after the last timed leg;
-    only the samples taken between mark_begin() and mark_end() (GPU under load: warm-up, timed steps, profiling pass,
-    end-to-end leg) are summarised."""
+    only the samples taken between mark_begin() and mark_end() (GPU under load) are summarised."""
     Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -183,7 +270,135 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
+# ------------------------------------------------------------------------------------------------ GPU arm: shared pieces
+class Ctx:
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist_mod
+
+            self.dist = dist_mod
+            if not dist_mod.is_initialized():
+                dist_mod.init_process_group("nccl", device_id=self.dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak, self.peak_src = ((peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)") if "hbm_gbs" in peaks
+                                        else (6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"))
+        self.traffic = {}
+        try:
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "r02", "traffic.json")))
+        except Exception:
+            pass
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max_ranks(self, v):
+        import audio_modem_b200 as amb
+
+        return amb.shard.max_over_ranks(v, device=self.dev) if self.dist else float(v)
+
+    def sum_ranks(self, d):
+        import audio_modem_b200 as amb
+
+        return amb.shard.gather_counters(d, device=self.dev) if self.dist else {k: int(v) for k, v in d.items()}
+
+
+def timed_steps(ctx, m, step, steps, warmup, k0=0):
+    """`warmup` untimed steps, then `steps` timed ones bracketed by barrier + synchronize on both sides; device time by CUDA
+    events on the library's stream.  step(k) performs step number k and returns the number of frames it delivered."""
+    import torch
+
+    ext = torch.cuda.ExternalStream(m.cuda_stream(), device=ctx.dev)
+    for w in range(warmup):
+        step(k0 + w)
+    m.synchronize()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    launches0 = m.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    frames = 0
+    for k in range(steps):
+        frames += step(k0 + warmup + k)
+    e1.record(ext)
+    m.synchronize()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    return e0.elapsed_time(e1), frames, m.kernel_launches - launches0
+
+
+def profile_pass(ctx, m, step, steps, k0):
+    """per-kernel device time of `steps` more steps (separate pass: the event pairs around every launch perturb the step time)"""
+    import torch
+
+    ext = torch.cuda.ExternalStream(m.cuda_stream(), device=ctx.dev)
+    m.profile(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(ext)
+    for k in range(steps):
+        step(k0 + k)
+    p1.record(ext)
+    m.synchronize()
+    ms = p0.elapsed_time(p1)
+    prof = m.profile_read()
+    m.profile(False)
+    return prof, ms
+
+
+def roofline(ctx, workload, prof, prof_ms, prof_steps, per_launch_bytes, algo_step, dev_ms, steps, units):
+    """units: {"frames": per step, "samples": per step} for scaling the committed per-unit DRAM traffic figures"""
+    if not prof:
+        return None
+    name, (ms, cnt) = max(prof.items(), key=lambda kv: kv[1][0])
+    b = per_launch_bytes(name) * prof_steps / cnt            # bytes per launch (a step may launch the kernel more than once)
+    achieved = b / (ms / cnt / 1e3) / 1e9
+    traffic = None
+    tj = (ctx.traffic.get(workload) or {}).get(name) or ctx.traffic.get(name)
+    if tj and "dram_bytes_per_frame" in tj:
+        traffic = tj["dram_bytes_per_frame"] * units["frames"] * prof_steps / cnt
+    elif tj and "dram_bytes_per_sample" in tj:
+        traffic = tj["dram_bytes_per_sample"] * units["samples"] * prof_steps / cnt
+    whole = algo_step * steps / (dev_ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": achieved / ctx.hbm_peak,
+            "traffic": traffic, "traffic_source": "profiles/r02/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, scaled per unit)" if traffic else None,
+            "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": b, "mean_launch_ms": ms / cnt, "share_of_step": ms / prof_ms,
+            "whole_step": {"algorithmic_bytes": algo_step, "achieved": whole, "frac": whole / ctx.hbm_peak},
+            "profiled_steps": prof_steps, "profiled_ms_per_step": prof_ms / prof_steps,
+            "kernels_ms_per_step": {k: v[0] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+
+def e2e_obj(value, h2d, d2h, steps, seconds, world):
+    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "h2d_gb_per_s_per_rank": h2d * steps / seconds / 1e9 / max(world, 1) if seconds > 0 else None}
+
+
+def base_line(ctx, workload, value, total_ms, steps, warmup, payload_bytes, config, clocks, e2e, launches, roof, scaling="weak"):
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": DTYPE,
+            "data": "synthetic", "payload_mb_per_s": payload_bytes / (total_ms / 1e3) / 1e6, "config": config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof}
+
+
+def frame_results(dres_t, n):
+    """first n amb_frame_result records of a device result buffer -> ctypes array (host copy)"""
+    import audio_modem_b200 as amb
+
+    FR = amb._lib.FrameResult
+    raw = dres_t[: n * C.sizeof(FR)].cpu().numpy().tobytes()
+    return (FR * n).from_buffer_copy(raw)
+
+
+# ------------------------------------------------------------------------------------------------ c2
 def prologue_frames():
     """data frames after the metadata frame that make the prologue a whole number of 4096-sample blocks"""
     for k in range(1, 4097):
@@ -192,106 +407,86 @@ def prologue_frames():
     raise AssertionError
 
 
-def run_b200(args, rank, world, local_rank):
+def run_c2(ctx, clocks):
     import numpy as np
     import torch
 
     import audio_modem_b200 as amb
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s (of fallback)")
-
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
+    cfg, mod, rep, chunk = MODES["16-QAM"]
     F = args.frames_per_step
     step_samples = F * FRAME
-    m = amb.Modem(CFG, MOD, REP, device=local_rank)
+    m = amb.Modem(cfg, mod, rep, device=ctx.local_rank)
     # noise level: 25 dB below the power of a frame core (preamble-1 .. last data symbol), measured on one clean frame
+    # (the library works on its own non-blocking stream: torch's fills must have finished before it writes into a tensor, and
+    # its kernels before torch reads one)
     clean = torch.zeros((1, FRAME), dtype=torch.float32, device=dev)
-    m.build_data_chunk_frames(n=1, data_len=CHUNK, seq0=0, synth_seed=2, out=clean)
+    torch.cuda.synchronize()
+    m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+    m.synchronize()
     sigma = float((clean[0, 2205:2205 + CORE].double().pow(2).mean() / 10 ** (SNR_DB / 10)).sqrt())
     del clean
-
     kp = prologue_frames()
     pro_samples = META + kp * FRAME
     max_push = max(step_samples, pro_samples)
     seed_payload, seed_noise = 2 + 1000 * rank, 3 + 1000 * rank
     # resident inputs: prologue + `segments` distinct steps
     pro = torch.zeros((1, pro_samples), dtype=torch.float32, device=dev)
-    m.build_metadata_frame(128000, 500 * 1024 * 1024, CHUNK, "bench.bin", noise_sigma=sigma, noise_seed=seed_noise, noise_g0=0, out=pro[0, :META])
-    m.build_data_chunk_frames(n=kp, data_len=CHUNK, seq0=0, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise, noise_g0=META,
+    segs = [torch.zeros((1, step_samples), dtype=torch.float32, device=dev) for _ in range(args.segments)]
+    torch.cuda.synchronize()
+    m.build_metadata_frame(128000, 500 * 1024 * 1024, chunk, "bench.bin", noise_sigma=sigma, noise_seed=seed_noise, noise_g0=0, out=pro[0, :META])
+    m.build_data_chunk_frames(n=kp, data_len=chunk, seq0=0, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise, noise_g0=META,
                               out=pro[0, META:].view(kp, FRAME))
-    segs = []
     for s in range(args.segments):
-        t = torch.zeros((1, step_samples), dtype=torch.float32, device=dev)
-        m.build_data_chunk_frames(n=F, data_len=CHUNK, seq0=kp + s * F, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise,
+        t = segs[s]
+        m.build_data_chunk_frames(n=F, data_len=chunk, seq0=kp + s * F, synth_seed=seed_payload, noise_sigma=sigma, noise_seed=seed_noise,
                                   noise_g0=pro_samples + s * step_samples, out=t[0].view(F, FRAME))
-        segs.append(t)
     m.synchronize()
-
     m.stream_open(1, 4096, max_push, max_results=max(F, kp) + 64)
     got = m.stream_push(pro, collect=False)
     c0 = m.stream_counters()
     assert c0["metaReceived"] == 1 and got == kp + 1, (c0, got, kp)
-
-    ext = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
     # device-resident leg: results and decoded bytes stay in HBM too
     cap = max(F, kp) + 64
     d_res = torch.empty(cap * 88, dtype=torch.uint8, device=dev)
     d_bytes = torch.empty((cap, m.bytes_stride), dtype=torch.uint8, device=dev)
     dres = (d_res, d_bytes)
+
+    def step(k):
+        return m.stream_push(segs[k % len(segs)], device_results=dres)
+
     clocks.mark_begin()
-    for w in range(args.warmup):
-        m.stream_push(segs[w % len(segs)], device_results=dres)
+    for w in range(2):
+        step(w)
     m.synchronize()
-    torch.cuda.synchronize()
     c0 = m.stream_counters()
-    if dist:
-        dist.barrier()
-    launches0 = m.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    frames_found = 0
-    for k in range(args.steps):
-        frames_found += m.stream_push(segs[(args.warmup + k) % len(segs)], device_results=dres)
-    e1.record(ext)
-    m.synchronize()
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = m.kernel_launches - launches0
+    fb0 = m.debug_counter(1)
+    dev_ms, frames_found, launches = timed_steps(ctx, m, step, args.steps, args.warmup)
     c1 = m.stream_counters()
+    fallbacks = m.debug_counter(1) - fb0
+    n_done = args.steps + args.warmup
     decoded = c1["framesDecoded"] - c0["framesDecoded"]
     crc_bad = c1["crcErrors"] - c0["crcErrors"]
     # every frame must be found and parsed; at 25 dB a few frames per 10,000 fail their CRC (real bit errors: the zero-padded
     # last symbol sets the frame peak, so the payload symbols sit ~24 dB below full scale)
-    assert frames_found == args.steps * F and decoded == args.steps * F and crc_bad <= max(2, decoded // 500) and c1["frameErrors"] == c0["frameErrors"], (frames_found, c0, c1)
-
-    # per-kernel device time of the same steps (separate pass: the event pairs around every launch perturb the step time)
-    m.profile(True)
+    assert frames_found == args.steps * F and decoded == n_done * F and crc_bad <= max(2, decoded // 500) and c1["frameErrors"] == c0["frameErrors"], (frames_found, c0, c1)
+    # payload check: the decoded bytes of the last step against the chunk bytes that were sent (regenerated by the library's
+    # own transmit path for a sample of the frames)
+    last_seg = (n_done - 1) % len(segs)               # segment of the last timed step
+    fr = frame_results(d_res, F)
+    sample_n = min(F, 256)
+    _, sent = m.build_data_chunk_frames(n=sample_n, data_len=chunk, seq0=kp + last_seg * F, synth_seed=seed_payload, return_data=True)
+    dec = d_bytes[:sample_n].cpu().numpy()
+    payload_ok = payload_bad = 0
+    for i in range(sample_n):
+        r = fr[i]
+        assert r.status == 0 and r.frame_type == 0xFF and r.seq_num == kp + last_seg * F + i, (i, r.status, r.frame_type, r.seq_num)
+        same = bytes(dec[i, r.data_off:r.data_off + r.data_len]) == bytes(sent[i])
+        assert same == bool(r.crc_valid), (i, same, r.crc_valid)      # a CRC-valid frame carries exactly the bytes sent
+        payload_ok += int(same); payload_bad += int(not same)
     prof_steps = min(args.steps, 4)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(ext)
-    for k in range(prof_steps):
-        m.stream_push(segs[(args.warmup + args.steps + k) % len(segs)], device_results=dres)
-    p1.record(ext)
-    m.synchronize()
-    prof_ms = p0.elapsed_time(p1)
-    prof = m.profile_read()
-    m.profile(False)
+    prof, prof_ms = profile_pass(ctx, m, step, prof_steps, n_done + 2)
     slots = {"slotted_tiles_per_frame": m.debug_counter(4) / F, "candidate_tiles_per_frame": m.debug_counter(5) / F,
              "link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
 
@@ -314,6 +509,7 @@ def run_b200(args, rank, world, local_rank):
     for w in range(2):
         assert m.stream_push(pcm_dev, device_results=dres) == F
     m.synchronize()
+    ext = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
     q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pcm_steps = min(args.steps, 6)
     q0.record(ext)
@@ -335,70 +531,488 @@ def run_b200(args, rank, world, local_rank):
     pcm_e2e_s = time.perf_counter() - t0
     assert pcm_frames == args.e2e_steps * F, pcm_frames
     clocks.mark_end()
-    clk = clocks.stop()
-    clk["window"] = "warm-up + timed steps + profiling pass + end-to-end legs (the same workload throughout)"
     d2h = F * (m.bytes_stride + 88)
     m.stream_close()
     del hx, hp
     host.free()
     host16.free()
+    m.close()
 
-    # aggregate over ranks
-    total_ms = amb.shard.max_over_ranks(dev_ms, device=dev) if dist else dev_ms
-    e2e_s_max = amb.shard.max_over_ranks(e2e_s, device=dev) if dist else e2e_s
-    counters = {"frames": args.steps * F, "payloadBytes": args.steps * F * CHUNK, "samples": args.steps * step_samples,
-                "crcValidFrames": decoded - crc_bad, "launches": launches}
-    tot = amb.shard.gather_counters(counters, device=dev) if dist else counters
+    total_ms = ctx.max_ranks(dev_ms)
+    e2e_s_max = ctx.max_ranks(e2e_s)
+    tot = ctx.sum_ranks({"frames": args.steps * F, "payloadBytes": args.steps * F * chunk, "samples": args.steps * step_samples,
+                         "launches": launches})
     value = tot["samples"] / (total_ms / 1e3) / 1e6
-    e2e_value = world * args.e2e_steps * step_samples / e2e_s_max / 1e6
-    pcm_ms_max = amb.shard.max_over_ranks(pcm_ms, device=dev) if dist else pcm_ms
-    pcm_e2e_s_max = amb.shard.max_over_ranks(pcm_e2e_s, device=dev) if dist else pcm_e2e_s
+    pcm_ms_max = ctx.max_ranks(pcm_ms)
+    pcm_e2e_s_max = ctx.max_ranks(pcm_e2e_s)
     pcm16 = {"input": "signed 16-bit PCM, sample = s / 32768 (amb_stream_push_pcm16); same frames as the float32 legs",
              "value": world * step_samples / (pcm_ms_max / 1e3) / 1e6, "ms_per_step": pcm_ms_max, "unit": UNIT,
-             "e2e": {"value": world * args.e2e_steps * step_samples / pcm_e2e_s_max / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * step_samples,
-                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps}}
+             "e2e": e2e_obj(world * args.e2e_steps * step_samples / pcm_e2e_s_max / 1e6, 2 * step_samples, d2h, args.e2e_steps, pcm_e2e_s_max, 1)}
+    algo_step = 4 * step_samples + F * (chunk + 64)                 # 4 B/sample once + payload + 64 B result per frame
+    per = {"k_demod": F * (4 * 44 * 576 + chunk + 64), "k_demod_fast": F * (4 * 44 * 576 + chunk + 64), "k_parse": F * (4202 + chunk + 64), "k_frame_max": F * 4 * CORE}
+    roof = roofline(ctx, "c2", prof, prof_ms, prof_steps, lambda name: per.get(name, 4 * step_samples), algo_step, dev_ms, args.steps,
+                    {"frames": F, "samples": step_samples})
+    config = {"workload": WORKLOAD_TEXT["c2"], "ofdm_config": cfg, "constellation": mod, "repetition": rep, "chunk_bytes": chunk, "frames_per_step": F,
+              "samples_per_step": step_samples, "block_len": 4096, "snr_db": SNR_DB, "streams_per_gpu": 1,
+              "l2_policy": "inputs larger than L2 (step input %.0f MB, %d distinct segments cycled)" % (step_samples * 4 / 1e6, args.segments),
+              "parallelism": "streams sharded by rank, no collective on the hot path"}
+    line = base_line(ctx, "c2", value, total_ms, args.steps, args.warmup, tot["payloadBytes"], config, None,
+                     e2e_obj(world * args.e2e_steps * step_samples / e2e_s_max / 1e6, 4 * step_samples, d2h, args.e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["pcm16"] = pcm16
+    line["walker"] = slots
+    line["check"] = {"frames_per_step_found": frames_found // args.steps, "frames_decoded_warmup_and_timed": decoded, "crc_errors_warmup_and_timed": crc_bad,
+                     "payload_bytes_equal_sent": payload_ok, "payload_bytes_differ_crc_invalid": payload_bad, "payload_frames_compared": sample_n,
+                     "fallback_symbols_per_step": fallbacks / n_done}
+    return line
 
-    # roofline of the dominant kernel (largest share of the timed region on this rank)
-    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
-    algo_step = 4 * step_samples + F * (CHUNK + 64)                 # 4 B/sample once + payload + 64 B result per frame
-    per_launch = {"k_demod": F * (4 * 44 * 576 + CHUNK + 64), "k_demod_fast": F * (4 * 44 * 576 + CHUNK + 64), "k_front": 4 * step_samples, "k_parse": F * (4202 + CHUNK + 64), "k_frame_max": F * 4 * CORE}
-    roof = None
-    if dom:
-        name, (ms, cnt) = dom
-        b = per_launch.get(name, 4 * step_samples)
-        achieved = b / (ms / cnt / 1e3) / 1e9
-        # measured DRAM traffic of that kernel (ncu --set full capture committed under profiles/), scaled to this launch
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json"))).get(name)
-            if tj and "dram_bytes_per_frame" in tj:
-                traffic = tj["dram_bytes_per_frame"] * F
-            elif tj and "dram_bytes_per_sample" in tj:
-                traffic = tj["dram_bytes_per_sample"] * step_samples
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "mean_launch_ms": ms / cnt,
-                "share_of_step": ms / prof_ms,
-                "whole_step": {"algorithmic_bytes": algo_step, "achieved": algo_step * args.steps / (dev_ms / 1e3) / 1e9,
-                               "frac": algo_step * args.steps / (dev_ms / 1e3) / 1e9 / hbm_peak},
-                "profiled_steps": prof_steps, "profiled_ms_per_step": prof_ms / prof_steps,
-                "kernels_ms_per_step": {k: v[0] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "payload_mb_per_s": tot["payloadBytes"] / (total_ms / 1e3) / 1e6,
-            "config": config_dict(args), "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * step_samples, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
-            "gpu_launches": tot["launches"], "roofline": roof, "pcm16": pcm16,
-            "walker": slots, "check": {"frames_per_step_found": frames_found // args.steps, "crc_valid_frames": tot["crcValidFrames"], "crc_errors": crc_bad}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, pmb, cores, sample, _ = cpu_leg(steps=1000, warmup=1, frames_per_thread=64, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "payload_mb_per_s": pmb}
-    if rank == 0:
-        print(json.dumps(line))
+
+# ------------------------------------------------------------------------------------------------ c5
+def build_c5_streams(m, ns, dev, rank, chunk):
+    import torch
+
+    meta_len = m.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len("s.bin") + 4, True)
+    flen = m.chunk_frame_samples(chunk + 11, False)
+    push = C5_PUSH_BLOCKS * 4096
+    period = (meta_len + C5_K * flen + 8192 + push - 1) // push
+    n = period * push
+    x = torch.zeros((ns, n), dtype=torch.float32, device=dev)
+    clean = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+    m.synchronize()
+    sigma = float((clean[0, 2205:flen - 882].double().pow(2).mean() / 10 ** (SNR_DB / 10)).sqrt())
+    s0 = rank * ns                                    # global stream index of this rank's first stream (seed = 5000 + s)
+    for s in range(ns):
+        m.build_metadata_frame(C5_K, C5_K * chunk, chunk, "s.bin", noise_sigma=sigma, noise_seed=5000 + s0 + s, noise_g0=0, out=x[s, :meta_len])
+        m.build_data_chunk_frames(n=C5_K, data_len=chunk, seq0=0, synth_seed=9000 + s0 + s, noise_sigma=sigma, noise_seed=5000 + s0 + s, noise_g0=meta_len,
+                                  out=x[s, meta_len:meta_len + C5_K * flen].view(C5_K, flen))
+    m.synchronize()
+    return x, push, period, meta_len + C5_K * flen
+
+
+def run_c5(ctx, clocks, ns=None, light=False):
+    """light: only the device-resident figure (the N = 1 point of the scaling curve inside the default c2 run)"""
+    import numpy as np
+    import torch
+
+    import audio_modem_b200 as amb
+
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
+    cfg, mod, rep, chunk = MODES["16-QAM"]
+    ns = ns or args.streams
+    m = amb.Modem(cfg, mod, rep, device=ctx.local_rank)
+    x, push, period, content = build_c5_streams(m, ns, dev, rank, chunk)
+    frames_per_period = ns * (C5_K + 1)
+    cap = ns * 3 + 64                                  # frames one push can complete (at most two per stream)
+    m.stream_open(ns, 4096, push, max_results=cap)
+    d_res = torch.empty(cap * 88, dtype=torch.uint8, device=dev)
+    d_bytes = torch.empty((cap, m.bytes_stride), dtype=torch.uint8, device=dev)
+    dres = (d_res, d_bytes)
+
+    def step(k):
+        p = k % period
+        return m.stream_push(x[:, p * push:(p + 1) * push], device_results=dres)
+
+    clocks.mark_begin()
+    got = sum(step(k) for k in range(period))          # prologue: one whole period (every stream receives its metadata frame)
+    m.synchronize()
+    c0 = m.stream_counters()
+    assert c0["metaReceived"] == ns and got >= ns * C5_K, (c0, got)
+    k0 = period
+    dev_ms, frames_found, launches = timed_steps(ctx, m, step, args.steps, args.warmup, k0)
+    c1 = m.stream_counters()
+    n_done = args.steps + args.warmup
+    decoded = c1["framesDecoded"] - c0["framesDecoded"]
+    # the signal is periodic: any `period` consecutive pushes complete 9 frames per stream
+    expect = n_done * frames_per_period / period
+    assert c1["frameErrors"] == c0["frameErrors"] and abs(decoded - expect) <= frames_per_period, (decoded, expect, c0, c1)
+    step_samples = ns * push
+    payload_bytes = frames_found * chunk * C5_K // (C5_K + 1)
+    total_ms = ctx.max_ranks(dev_ms)
+    tot = ctx.sum_ranks({"frames": frames_found, "payloadBytes": payload_bytes, "samples": args.steps * step_samples, "launches": launches})
+    value = tot["samples"] / (total_ms / 1e3) / 1e6
+    if light:
+        clocks.mark_end()
+        m.stream_close()
+        m.close()
+        return {"workload": WORKLOAD_TEXT["c5"], "streams_per_gpu": ns, "samples_per_step": step_samples, "value": value, "unit": UNIT,
+                "ms_per_step": total_ms / args.steps, "steps": args.steps, "warmup": args.warmup, "frames_found": frames_found,
+                "payload_mb_per_s": tot["payloadBytes"] / (total_ms / 1e3) / 1e6}
+    prof_steps = min(args.steps, period)
+    prof, prof_ms = profile_pass(ctx, m, step, prof_steps, k0 + n_done)
+    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
+    # end-to-end: the whole period in page-locked host memory, pushed section by section
+    e2e_steps = period
+    host = amb.modem.pinned_empty((ns, period * push), np.float32)
+    hx = host.array
+    rows = 512
+    for r0 in range(0, ns, rows):
+        hx[r0:r0 + rows] = x[r0:r0 + rows].cpu().numpy()
+    k1 = k0 + n_done + prof_steps
+    k1 += (-k1) % period                               # continue at a period boundary
+    for k in range(k1 - (k0 + n_done + prof_steps)):
+        step(k0 + n_done + prof_steps + k)
+    m.synchronize()
+    t0 = time.perf_counter()
+    e2e_frames = 0
+    for p in range(e2e_steps):
+        e2e_frames += _push_host_rows(m, host, ns, period * push, p * push, push)
+    m.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert abs(e2e_frames - frames_per_period) <= ns, (e2e_frames, frames_per_period)
+    clocks.mark_end()
+    d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
+    m.stream_close()
+    del hx
+    host.free()
     m.close()
-    if dist:
-        dist.destroy_process_group()
+    e2e_s_max = ctx.max_ranks(e2e_s)
+    frames_step = frames_per_period / period
+    algo_step = 4 * step_samples + frames_step * (chunk * C5_K / (C5_K + 1) + 64)
+    per = {"k_demod_fast": frames_step * (4 * 44 * 576 + chunk + 64), "k_parse": frames_step * (4202 + chunk + 64)}
+    roof = roofline(ctx, "c5", prof, prof_ms, prof_steps, lambda name: per.get(name, 4 * step_samples), algo_step, dev_ms, args.steps,
+                    {"frames": frames_step, "samples": step_samples})
+    config = {"workload": WORKLOAD_TEXT["c5"], "ofdm_config": cfg, "constellation": mod, "repetition": rep, "chunk_bytes": chunk,
+              "streams_per_gpu": ns, "streams_total": ns * world, "frames_per_stream": C5_K + 1, "samples_per_stream_period": period * push,
+              "push_samples_per_stream": push, "samples_per_step": step_samples, "block_len": 4096, "snr_db": SNR_DB,
+              "l2_policy": "inputs larger than L2 (step input %.0f MB per GPU, %d distinct sections cycled)" % (step_samples * 4 / 1e6, period),
+              "parallelism": "streams sharded by rank (contiguous ranges), no collective on the hot path; counters summed by one all_reduce after the timed region"}
+    line = base_line(ctx, "c5", value, total_ms, args.steps, args.warmup, tot["payloadBytes"], config, None,
+                     e2e_obj(world * e2e_steps * step_samples / e2e_s_max / 1e6, 4 * step_samples, d2h, e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["walker"] = iters
+    line["check"] = {"frames_found": tot["frames"], "frames_expected_per_period_per_gpu": frames_per_period, "frame_errors": c1["frameErrors"] - c0["frameErrors"],
+                     "crc_errors": c1["crcErrors"] - c0["crcErrors"]}
+    return line
+
+
+def _push_host_rows(m, host, ns, row_len, off, n_new):
+    """amb_stream_push from page-locked host rows [ns][row_len] starting at sample `off` (strided rows: the wrapper's
+    ascontiguousarray would copy), results to the wrapper's page-locked buffers"""
+    n = C.c_int(0)
+    ptr = C.c_void_p(host.ptr + 4 * off)
+    rc = m._L.amb_stream_push(m._h, ptr, row_len, n_new, 0, C.cast(m._res, C.c_void_p), m.max_results, C.byref(n),
+                              C.c_void_p(m._dec.ctypes.data), m.bytes_stride, 0)
+    m._ck(rc, allow_overflow=True)
+    return n.value
+
+
+# ------------------------------------------------------------------------------------------------ c4
+def build_c4_capture(m, dev, seconds, rank, chunk):
+    import torch
+
+    N = (seconds * 44100 + 4095) // 4096 * 4096
+    g = torch.Generator(device=dev)
+    g.manual_seed(4 + 1000 * rank)
+    x = torch.randn((1, N), dtype=torch.float32, device=dev, generator=g) * (10 ** (-30 / 20))
+    meta_len = m.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len("cap.bin") + 4, True)
+    flen = m.chunk_frame_samples(chunk + 11, False)
+    pos = 5 * 44100
+    buf = torch.zeros(meta_len, dtype=torch.float32, device=dev)
+    fb = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    m.build_metadata_frame(12, 12 * chunk, chunk, "cap.bin", out=buf)
+    m.synchronize()
+    x[0, pos:pos + meta_len] += buf
+    pos += meta_len
+    n_frames = 0
+    for i in range(12):
+        gap = (10 + (17 * i if seconds >= 3600 else 0)) * 44100
+        if pos + gap + flen >= N:
+            break
+        pos += gap
+        torch.cuda.synchronize()
+        m.build_data_chunk_frames(n=1, data_len=chunk, seq0=i, synth_seed=40 + i, out=fb)
+        m.synchronize()
+        x[0, pos:pos + flen] += fb[0]
+        pos += flen
+        n_frames += 1
+    torch.cuda.synchronize()
+    return x, N, n_frames
+
+
+def run_c4(ctx, clocks):
+    import numpy as np
+    import torch
+
+    import audio_modem_b200 as amb
+
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
+    cfg, mod, rep, chunk = MODES["BPSK-NARROW"]
+    m = amb.Modem(cfg, mod, rep, device=ctx.local_rank)
+    x, N, n_frames = build_c4_capture(m, dev, args.c4_seconds, rank, chunk)
+    cap = 256
+    m.stream_open(1, 4096, N, max_results=cap)
+    d_res = torch.empty(cap * 88, dtype=torch.uint8, device=dev)
+    d_bytes = torch.empty((cap, m.bytes_stride), dtype=torch.uint8, device=dev)
+    dres = (d_res, d_bytes)
+    steps, warmup = min(args.steps, 10), args.warmup
+
+    def step(k):
+        return m.stream_push(x, device_results=dres)     # the receiver sees the capture again and again (635 MB per pass: larger than L2)
+
+    clocks.mark_begin()
+    first = step(0)
+    m.synchronize()
+    c0 = m.stream_counters()
+    assert c0["metaReceived"] == 1 and c0["receivedCount"] >= n_frames - 2, (first, c0)
+    dev_ms, frames_found, launches = timed_steps(ctx, m, step, steps, warmup, 1)
+    c1 = m.stream_counters()
+    n_done = steps + warmup
+    assert c1["framesDecoded"] - c0["framesDecoded"] >= n_done * (n_frames - 1), (c0, c1)
+    prof_steps = min(steps, 2)
+    prof, prof_ms = profile_pass(ctx, m, step, prof_steps, 1 + n_done)
+    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
+    host = amb.modem.pinned_empty((1, N), np.float32)
+    hx = host.array
+    hx[...] = x.cpu().numpy()
+    m.stream_push(hx, collect=False)
+    m.synchronize()
+    e2e_steps = 3
+    t0 = time.perf_counter()
+    e2e_frames = 0
+    for k in range(e2e_steps):
+        e2e_frames += m.stream_push(hx, collect=False)
+    m.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks.mark_end()
+    d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
+    m.stream_close()
+    del hx
+    host.free()
+    m.close()
+    total_ms = ctx.max_ranks(dev_ms)
+    e2e_s_max = ctx.max_ranks(e2e_s)
+    payload = steps * n_frames * chunk
+    tot = ctx.sum_ranks({"frames": frames_found, "payloadBytes": payload, "samples": steps * N, "launches": launches})
+    value = tot["samples"] / (total_ms / 1e3) / 1e6
+    algo_step = 4 * N + (n_frames + 1) * (chunk + 64)
+    roof = roofline(ctx, "c4", prof, prof_ms, prof_steps, lambda name: 4 * N, algo_step, dev_ms, steps, {"frames": n_frames + 1, "samples": N})
+    config = {"workload": WORKLOAD_TEXT["c4"], "ofdm_config": cfg, "constellation": mod, "repetition": rep, "chunk_bytes": chunk,
+              "capture_seconds": args.c4_seconds, "samples_per_step": N, "frames_in_capture": n_frames + 1, "noise_floor_dbfs": -30, "block_len": 4096,
+              "streams_per_gpu": 1, "l2_policy": "the capture (%.0f MB) is larger than L2" % (N * 4 / 1e6),
+              "parallelism": "one capture per rank (replicas), no collective on the hot path",
+              "note": "per-kernel roofline uses 4 B per scanned sample for every kernel (the scan dominates by construction)"}
+    line = base_line(ctx, "c4", value, total_ms, steps, warmup, tot["payloadBytes"], config, None,
+                     e2e_obj(world * e2e_steps * N / e2e_s_max / 1e6, 4 * N, d2h, e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["walker"] = iters
+    line["check"] = {"frames_found_per_step": frames_found / steps, "counters_after": c1}
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ c3 / c1 (batch decode)
+def _decode_device(m, x, lens, res, dec):
+    import audio_modem_b200 as amb
+
+    rc = m._L.amb_decode_received_signals(m._h, C.c_void_p(x.data_ptr()), x.stride(0), C.c_void_p(lens.data_ptr()) if lens is not None else None, x.shape[0],
+                                          C.c_void_p(res.data_ptr()), C.c_void_p(dec.data_ptr()), dec.stride(0), amb._lib.MEM_DEVICE)
+    m._ck(rc)
+    return x.shape[0]
+
+
+def _channel_gpu(clean, n_rec, seed, dev, with_channel):
+    """n_rec recordings from the unique clean signals [U][n]: multipath FIR (1.0@0, 0.5@23, 0.25@57), CFO by an analytic-signal
+    shift (90 % within +-0.05 Hz, 10 % at +-1 Hz), AWGN 20 dB below the frame power; all on the device (torch), float32 out"""
+    import math
+
+    import torch
+
+    U, n = clean.shape
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((n_rec, (n + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    out[:, n:] = 0
+    if not with_channel:
+        for i in range(n_rec):
+            out[i, :n] = clean[i % U]
+        return out
+    t = torch.arange(n, device=dev, dtype=torch.float64) / 44100.0
+    batch = 64
+    for i0 in range(0, n_rec, batch):
+        idx = torch.arange(i0, min(n_rec, i0 + batch), device=dev)
+        y = clean[idx % U].double()
+        y = y + 0.5 * torch.nn.functional.pad(y, (23, 0))[:, :n] + 0.25 * torch.nn.functional.pad(y, (57, 0))[:, :n]
+        u = torch.rand(len(idx), generator=g, device=dev, dtype=torch.float64)
+        df = torch.where(idx % 10 == 3, torch.where(u < 0.5, -1.0, 1.0), (u - 0.5) * 0.1)
+        Y = torch.fft.fft(y, dim=1)
+        h = torch.zeros(n, device=dev, dtype=torch.float64)
+        h[0] = 1
+        h[1:(n + 1) // 2] = 2
+        if n % 2 == 0:
+            h[n // 2] = 1
+        ana = torch.fft.ifft(Y * h, dim=1)
+        ph = 2 * math.pi * df[:, None] * t[None, :]
+        y = ana.real * torch.cos(ph) - ana.imag * torch.sin(ph)
+        p = clean[idx % U][:, 22050:22050 + 20000].double().pow(2).mean(dim=1)
+        sigma = (p / 100.0).sqrt()
+        y = y + torch.randn(y.shape, generator=g, device=dev, dtype=torch.float64) * sigma[:, None]
+        out[i0:i0 + len(idx), :n] = y.float()
+    return out
+
+
+def run_batch(ctx, clocks, workload):
+    import numpy as np
+    import torch
+
+    import audio_modem_b200 as amb
+
+    args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
+    if workload == "c3":
+        plan = [("BPSK-ACOUSTIC", args.recordings // 2), ("BPSK-REPEAT", args.recordings - args.recordings // 2)]
+        payload, with_channel, uniq = 512, True, 32
+    else:
+        plan = [("QPSK", args.c1_batch)]
+        payload, with_channel, uniq = 32768, False, 4
+    parts = []
+    tx_ms = 0.0
+    for mode, n_rec in plan:
+        cfg, mod, rep, _ = MODES[mode]
+        m = amb.Modem(cfg, mod, rep, device=ctx.local_rank)
+        rng = np.random.default_rng(1000 + rank)
+        datas = [rng.integers(0, 256, payload, dtype=np.uint8) for _ in range(uniq)]
+        t0 = time.perf_counter()
+        clean = m.build_transmit_signals(datas, "rec" if workload == "c3" else "file")       # library transmit path (modem.js:498-555), host buffers
+        tx_ms += (time.perf_counter() - t0) * 1e3
+        n = clean.shape[1]
+        x = _channel_gpu(torch.from_numpy(clean).to(dev), n_rec, 77 + rank, dev, with_channel)
+        lens = torch.full((n_rec,), n, dtype=torch.int64, device=dev)
+        bs = m.decoded_capacity(x.shape[1])
+        res = torch.zeros(n_rec * 88, dtype=torch.uint8, device=dev)
+        dec = torch.zeros((n_rec, bs), dtype=torch.uint8, device=dev)
+        parts.append({"mode": mode, "m": m, "x": x, "lens": lens, "res": res, "dec": dec, "n": n, "n_rec": n_rec, "datas": datas, "bs": bs})
+    def step(k):
+        got = 0
+        for p in parts[::-1]:
+            got += _decode_device(p["m"], p["x"], p["lens"], p["res"], p["dec"])        # (amb_decode_* returns after its results are complete)
+        return got
+
+    steps, warmup = min(args.steps, 10), args.warmup
+    clocks.mark_begin()
+    step(0)
+    samples_step = sum(p["n"] * p["n_rec"] for p in parts)
+    # checks: every recording decodes to the bytes that were sent unless the channel broke it (the +-1 Hz cases)
+    ok_total = 0
+    for p in parts:
+        fr = frame_results(p["res"], p["n_rec"])
+        dec = p["dec"].cpu().numpy()
+        ok = 0
+        for i in range(p["n_rec"]):
+            r = fr[i]
+            if r.status == 0 and r.crc_valid:
+                assert bytes(dec[i, r.data_off:r.data_off + r.data_len]) == bytes(p["datas"][i % len(p["datas"])]), (p["mode"], i)
+                ok += 1
+        p["ok"] = ok
+        ok_total += ok
+        assert ok >= (0.5 if with_channel else 1.0) * p["n_rec"], (p["mode"], ok, p["n_rec"])
+    # device time: events on every handle's stream, the step time is the sum over the handles (the calls are synchronous)
+    for w in range(warmup):
+        step(w)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    evs = []
+    l0 = sum(p["m"].kernel_launches for p in parts)
+    for k in range(steps):
+        for p in parts[::-1]:
+            ext = torch.cuda.ExternalStream(p["m"].cuda_stream(), device=dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ext)
+            _decode_device(p["m"], p["x"], p["lens"], p["res"], p["dec"])
+            b.record(ext)
+            evs.append((a, b))
+    torch.cuda.synchronize()
+    ctx.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = sum(p["m"].kernel_launches for p in parts) - l0
+    prof, prof_ms = {}, 0.0
+    prof_steps = min(steps, 2)
+    for p in parts:
+        pr, ms = profile_pass(ctx, p["m"], lambda k, p=p: _decode_device(p["m"], p["x"], p["lens"], p["res"], p["dec"]), prof_steps, 0)
+        prof_ms += ms
+        for k, v in pr.items():
+            a = prof.get(k, (0.0, 0))
+            prof[k] = (a[0] + v[0], a[1] + v[1])
+    # end-to-end: recordings in page-locked host rows, results and decoded bytes back to page-locked host memory
+    e2e_steps = 3
+    hosts = []
+    for p in parts:
+        hx = amb.modem.pinned_empty(tuple(p["x"].shape), np.float32)
+        hx.array[...] = p["x"].cpu().numpy()
+        hl = np.full(p["n_rec"], p["n"], np.int64)
+        hr = amb.modem.pinned_empty((p["n_rec"] * 88,), np.uint8)
+        hd = amb.modem.pinned_empty((p["n_rec"], p["bs"]), np.uint8)
+        hosts.append((p, hx, hl, hr, hd))
+
+    def host_step():
+        for p, hx, hl, hr, hd in hosts:
+            rc = p["m"]._L.amb_decode_received_signals(p["m"]._h, C.c_void_p(hx.ptr), p["x"].shape[1], C.c_void_p(hl.ctypes.data), p["n_rec"],
+                                                       C.c_void_p(hr.ptr), C.c_void_p(hd.ptr), p["bs"], 0)
+            p["m"]._ck(rc)
+
+    host_step()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        host_step()
+    e2e_s = time.perf_counter() - t0
+    clocks.mark_end()
+    d2h = sum(p["n_rec"] * (p["bs"] + 88) for p in parts)
+    h2d = sum(p["x"].shape[0] * p["x"].shape[1] * 4 for p in parts)
+    for p, hx, hl, hr, hd in hosts:
+        hx.free(); hr.free(); hd.free()
+    for p in parts:
+        p["m"].close()
+    total_ms = ctx.max_ranks(dev_ms)
+    e2e_s_max = ctx.max_ranks(e2e_s)
+    n_rec_all = sum(p["n_rec"] for p in parts)
+    tot = ctx.sum_ranks({"frames": steps * n_rec_all, "payloadBytes": steps * ok_total * payload, "samples": steps * samples_step, "launches": launches})
+    value = tot["samples"] / (total_ms / 1e3) / 1e6
+    algo_step = 4 * samples_step + n_rec_all * (payload + 64)
+    roof = roofline(ctx, workload, prof, prof_ms, prof_steps, lambda name: 4 * samples_step, algo_step, dev_ms, steps, {"frames": n_rec_all, "samples": samples_step})
+    config = {"workload": WORKLOAD_TEXT[workload], "modes": [p["mode"] for p in parts], "recordings_per_step": n_rec_all, "payload_bytes": payload,
+              "samples_per_recording": [p["n"] for p in parts], "samples_per_step": samples_step, "unique_payloads_per_mode": uniq,
+              "channel": "multipath 1.0@0 0.5@23 0.25@57, CFO 90 % within +-0.05 Hz and 10 % at +-1 Hz, AWGN 20 dB" if with_channel else "none (loopback)",
+              "l2_policy": "inputs larger than L2 (step input %.0f MB)" % (samples_step * 4 / 1e6) if samples_step * 4 > 126e6 else "step input %.0f MB fits L2; every step re-reads the same recordings" % (samples_step * 4 / 1e6),
+              "parallelism": "recordings sharded by rank, no collective on the hot path",
+              "note": "per-kernel roofline uses 4 B per input sample for every kernel; transmit (host buffers) took %.0f ms for the unique signals" % tx_ms}
+    line = base_line(ctx, workload, value, total_ms, steps, warmup, tot["payloadBytes"], config, None,
+                     e2e_obj(world * e2e_steps * samples_step / e2e_s_max / 1e6, h2d, d2h, e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["check"] = {"crc_valid_recordings": {p["mode"]: p["ok"] for p in parts}, "recordings": {p["mode"]: p["n_rec"] for p in parts},
+                     "decoded_bytes_equal_sent_for_every_crc_valid_recording": True}
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ driver
+def run_b200(args, rank, world, local_rank, workloads):
+    ctx = Ctx(args, rank, world, local_rank)
+    for wl in workloads:
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        if wl == "c2":
+            line = run_c2(ctx, clocks)
+        elif wl == "c5":
+            line = run_c5(ctx, clocks)
+        elif wl == "c4":
+            line = run_c4(ctx, clocks)
+        else:
+            line = run_batch(ctx, clocks, wl)
+        clk = clocks.stop()
+        clk["window"] = "warm-up + timed steps + profiling pass + end-to-end legs (the same workload throughout)"
+        line["clocks"] = clk
+        if wl == "c2" and world == 1 and args.workload is None and not args.no_shard_probe:
+            # the N = 1 point of the c5 scaling curve (the N > 1 default workload), measured here so that it sits in the N = 1 record
+            sc = ClockSampler(local_rank)
+            sc.start()
+            try:
+                line["c5_shard_at_one_gpu"] = run_c5(ctx, sc, light=True)
+            except Exception as e:      # the headline must not depend on the extra probe
+                line["c5_shard_at_one_gpu"] = {"error": repr(e)[:200]}
+            sc.stop()
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            r = cpu_leg(wl, steps=1000, warmup=1, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "payload_mb_per_s": r["payload_mb_per_s"]}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    if ctx.dist:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -406,10 +1020,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload or ("c2" if world == 1 and args.gpus == 1 else "c5")
+    workloads = ["c1", "c3", "c4", "c5", "c2"] if wl == "all" else [wl]
     if args.impl == "reference":
-        run_reference(args, rank)
+        for w in workloads:
+            run_reference(args, rank, w)
     else:
-        run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank, workloads)
 
 
 if __name__ == "__main__":

@@ -98,7 +98,9 @@ def test_c5_many_streams(O, amb):
         n = (meta_len + K * flen + 8192 + push - 1) // push * push
         x = torch.zeros((ns, n), dtype=torch.float32, device=dev)
         clean = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()          # the library writes on its own stream: torch's fills must be done first
         m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+        m.synchronize()
         sigma = float((clean[0, 2205:flen - 882].double().pow(2).mean() / 10 ** 2.5).sqrt())       # 25 dB below the frame core
         for s in range(ns):
             m.build_metadata_frame(K, K * chunk, chunk, "s.bin", noise_sigma=sigma, noise_seed=5000 + s, noise_g0=0, out=x[s, :meta_len])

@@ -23,7 +23,9 @@ meta_len = m.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len("cap.bin") + 4, True)
 flen = m.chunk_frame_samples(chunk + 11, False)
 pos = 5 * 44100
 buf = torch.zeros(meta_len, dtype=torch.float32, device=dev)
+torch.cuda.synchronize()
 m.build_metadata_frame(12, 12 * chunk, chunk, "cap.bin", out=buf)
+m.synchronize()
 REPS = int(os.environ.get("C4_REPS", "3"))
 x[0, pos:pos + meta_len] += buf
 pos += meta_len
@@ -32,7 +34,9 @@ starts = []
 NF = int(os.environ.get("C4_FRAMES", "12"))
 for i in range(NF):
     pos += (10 + (17 * i if SECONDS >= 3600 else 0)) * 44100
+    torch.cuda.synchronize()
     m.build_data_chunk_frames(n=1, data_len=chunk, seq0=i, synth_seed=40 + i, out=fb)
+    m.synchronize()
     x[0, pos:pos + flen] += fb[0]
     starts.append(pos)
     pos += flen

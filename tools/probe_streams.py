@@ -31,7 +31,9 @@ push = args.push_blocks * 4096
 n = (total + 8192 + push - 1) // push * push
 x = torch.zeros((ns, n), dtype=torch.float32, device=dev)
 clean = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+torch.cuda.synchronize()
 m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+m.synchronize()
 core = m.chunk_frame_samples(chunk + 11, False) - 2205 - 882
 sigma = float((clean[0, 2205:2205 + core].double().pow(2).mean() / 10 ** 2.5).sqrt())
 t0 = time.perf_counter()
