@@ -1464,53 +1464,61 @@ __global__ void __launch_bounds__(256) k_argmax(const float* __restrict__ y, int
 }
 
 // Sequential float64 replay of detectPreamble (modem.js:292-318) for recordings whose maximum is tied between separate
-// offsets: one thread per recording, same operation order as the reference.  The sliding sums must be carried from offset 0
-// (their rounding depends on the whole history), but the metric only matters at the tied offsets [lo, hi]: every other offset
-// is below the maximum by more than the two evaluations can differ, and the first maximum among the tied ones is the answer.
-// Eight samples of each of the three taps are loaded ahead of the dependent additions.
-__global__ void k_replay(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int n,
-                         double min_energy, const int* __restrict__ ambiguous, const int64_t* __restrict__ tie_range,
-                         int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// offsets, same operation order as the reference.  The sliding sums must be carried from offset 0 (their rounding depends
+// on the whole history), but the metric only matters at the tied offsets [lo, hi]: every other offset is below the maximum
+// by more than the two evaluations can differ, and the first maximum among the tied ones is the answer.
+// One WARP per recording: the per-offset update terms (mid*bIn - aOut*mid, ...) do not depend on the sums, so the lanes
+// compute 32 of them at a time and lane 0 only carries the three chains of additions.
+__global__ void __launch_bounds__(128) k_replay(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int n,
+                                                 double min_energy, const int* __restrict__ ambiguous, const int64_t* __restrict__ tie_range,
+                                                 int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
+    __shared__ double sdp[4][32], sda[4][32], sdb[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 4 + warp;
     if (r >= n || !ambiguous[r]) return;
     const int64_t len = lens ? lens[r] : n_default;
     const float* s = y + (int64_t)r * stride;
     double p = 0, ra = 0, rb = 0;
-    for (int m = 0; m < AMB_HALF; m++) {
-        const double a = s[m], b = s[m + AMB_HALF];
-        p = amb_add(p, amb_mul(a, b)); ra = amb_add(ra, amb_mul(a, a)); rb = amb_add(rb, amb_mul(b, b));
+    if (lane == 0) {
+        for (int m = 0; m < AMB_HALF; m++) {
+            const double a = s[m], b = s[m + AMB_HALF];
+            p = amb_add(p, amb_mul(a, b)); ra = amb_add(ra, amb_mul(a, a)); rb = amb_add(rb, amb_mul(b, b));
+        }
     }
     double best = 0; int64_t best_idx = -1;
     const int64_t end = len - 2 * AMB_HALF;
     const int64_t lo = tie_range[2 * r], hi = tie_range[2 * r + 1] < end ? tie_range[2 * r + 1] : end;
-    int64_t d = 0;
-    // offsets before the tied range: slide only
-    for (; d + 8 <= lo; d += 8) {
-        float ao[8], mid[8], bi[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { ao[k] = s[d + k]; mid[k] = s[d + k + AMB_HALF]; bi[k] = s[d + k + 2 * AMB_HALF]; }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const double a0 = ao[k], m0 = mid[k], b0 = bi[k];
-            p = amb_add(p, amb_sub(amb_mul(m0, b0), amb_mul(a0, m0)));
-            ra = amb_add(ra, amb_sub(amb_mul(m0, m0), amb_mul(a0, a0)));
-            rb = amb_add(rb, amb_sub(amb_mul(b0, b0), amb_mul(m0, m0)));
-        }
-    }
-    for (; d <= hi; d++) {
-        if (d >= lo && ra > min_energy && rb > min_energy) {
-            const double m = amb_div(amb_mul(p, p), amb_mul(ra, rb));
-            if (m > best) { best = m; best_idx = d; }
-        }
+    for (int64_t d0 = 0; d0 <= hi; d0 += 32) {
+        const int64_t d = d0 + lane;
         if (d < end) {
             const double ao = s[d], mid = s[d + AMB_HALF], bi = s[d + 2 * AMB_HALF];
-            p = amb_add(p, amb_sub(amb_mul(mid, bi), amb_mul(ao, mid)));
-            ra = amb_add(ra, amb_sub(amb_mul(mid, mid), amb_mul(ao, ao)));
-            rb = amb_add(rb, amb_sub(amb_mul(bi, bi), amb_mul(mid, mid)));
+            sdp[warp][lane] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
+            sda[warp][lane] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
+            sdb[warp][lane] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
         }
+        __syncwarp();
+        if (lane == 0) {
+            const int cnt = (int)(hi - d0 + 1 < 32 ? hi - d0 + 1 : 32);
+            if (d0 + 31 < lo) {
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) { p = amb_add(p, sdp[warp][k]); ra = amb_add(ra, sda[warp][k]); rb = amb_add(rb, sdb[warp][k]); }
+            } else {
+                for (int k = 0; k < cnt; k++) {
+                    const int64_t dd = d0 + k;
+                    if (dd >= lo && ra > min_energy && rb > min_energy) {
+                        const double m = amb_div(amb_mul(p, p), amb_mul(ra, rb));
+                        if (m > best) { best = m; best_idx = dd; }
+                    }
+                    if (dd < end) { p = amb_add(p, sdp[warp][k]); ra = amb_add(ra, sda[warp][k]); rb = amb_add(rb, sdb[warp][k]); }
+                }
+            }
+        }
+        __syncwarp();
     }
-    best_out[r] = best;
-    idx_out[r] = best > 0.5 ? best_idx : -1;
+    if (lane == 0) {
+        best_out[r] = best;
+        idx_out[r] = best > 0.5 ? best_idx : -1;
+    }
 }
 
 // Fine cross-correlation + job setup for decodeReceivedSignal (modem.js:566-603): one warp per recording.

@@ -65,6 +65,8 @@ m.profile(False)
 npush = max(1, len(per) - 4)
 print({k: round(v[0] / npush, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]})
 print("per push (ms, launches):", per)
+print("fallback symbols (all pushes):", m.debug_counter(1), "link iterations", m.debug_counter(2), "passes", m.debug_counter(3))
+print("launch counts:", {k: v[1] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]})
 if len(per) > 4:
     tail = sorted(p[0] for p in per[3:-1])
     print(f"steady pushes (median): {ns * push / (tail[len(tail) // 2] / 1e3) / 1e6:.0f} Msamples/s")
