@@ -65,7 +65,7 @@ struct amb_modem {
     size_t prof_used = 0;
     // scratch
     DevBuf in_a, in_b, in_c, in_lens, out_a, out_b, out_c, out_res, out_bytes;
-    DevBuf jobs, idx, xf, psum, pmin, pmax, norm, metric, tile_max, amb, tie_rng, cidx, cbest, tx_pay, tx_out, tx_copy;
+    DevBuf jobs, idx, p_scratch, xf, psum, pmin, pmax, norm, metric, tile_max, amb, tie_rng, cidx, cbest, tx_pay, tx_out, tx_copy;
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
@@ -75,7 +75,7 @@ struct amb_modem {
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
     int rec_cap = 0;
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
-    DevBuf tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
+    DevBuf nan_pos, tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
     DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
@@ -180,10 +180,18 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     // one CTA per frame does everything (demodulate, vote, pack, parse, CRC-32) when the frame is a single symbol group whose
     // constellation indices fit in shared memory; longer frames go through the index array in HBM and k_parse
     const bool fused = m->fast_demod && m->fuse_parse && groups == 1 && (int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data <= AMB_FD_IDX_CAP;
-    // a decoded frame longer than k_parse's shared-memory staging is packed straight into the caller's row, which must hold it
-    if (!fused && amb_num_bytes((int64_t)(max_nsym > 0 ? max_nsym : 0) * T.n_data, T.bps, T.rep) > AMB_PARSE_SMEM &&
-        bytes_stride < amb_num_bytes((int64_t)max_nsym * T.n_data, T.bps, T.rep))
-        return fail(m, AMB_E_INVALID, "bytes_stride smaller than the decoded frame");
+    // a decoded frame longer than k_parse's shared-memory staging is packed straight into the caller's row when that holds it,
+    // else into a scratch row: the result (fields, CRC verdict, n_bytes) never depends on the caller's row length
+    uint8_t* p_scratch = nullptr;
+    int64_t p_scratch_stride = 0;
+    {
+        const int64_t nb_max = amb_num_bytes((int64_t)(max_nsym > 0 ? max_nsym : 0) * T.n_data, T.bps, T.rep);
+        if (!fused && nb_max > AMB_PARSE_SMEM && bytes_stride < nb_max) {
+            p_scratch_stride = (nb_max + 15) / 16 * 16;
+            CK(m->p_scratch.ensure((size_t)n_jobs * p_scratch_stride));
+            p_scratch = m->p_scratch.as<uint8_t>();
+        }
+    }
     if (!fused) CK(m->idx.ensure((size_t)n_jobs * idx_stride));
     AmbDemodOut o;
     std::memset(&o, 0, sizeof(o));
@@ -224,7 +232,7 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
     }
     if (!fused) {
         LAUNCH("k_parse", k_parse<<<n_jobs < 65536 ? n_jobs : 65536, AMB_CRC_THREADS, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride,
-                                                              d_res, d_bytes, bytes_stride, m->d_crc_ops));
+                                                              d_res, d_bytes, bytes_stride, m->d_crc_ops, p_scratch, p_scratch_stride));
     }
     return AMB_OK;
 }
@@ -399,10 +407,10 @@ void amb_destroy(amb_modem* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx,
+    DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx, &m->p_scratch,
                      &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->tie_rng, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
-                     &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
+                     &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp, &m->nan_pos,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
@@ -878,7 +886,7 @@ int amb_stream_close(amb_modem* m) {
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->raw, &m->cleaned, &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total,
-                     &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp,
+                     &m->keep, &m->keep_off, &m->redo, &m->n_redo, &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp, &m->nan_pos,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
@@ -956,6 +964,10 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         fa.span = (int)span; fa.spans = (int)((ftiles + span - 1) / span); fa.warm = 10 * per_block;
         fa.E = m->d_ema; fa.states = m->states.as<AmbStreamState>(); fa.dc_next = m->dc_next.as<double>();
         fa.sums = m->sums.as<float>(); fa.sum_stride = m->sum_stride; fa.st = ss;
+        CK(m->nan_pos.ensure((size_t)(ns + 1) * 8));
+        CK(cudaMemsetAsync(m->nan_pos.p, 0xFF, (size_t)ns * 8, m->stream));
+        CK(cudaMemsetAsync(m->nan_pos.as<unsigned long long>() + ns, 0, 8, m->stream));
+        fa.nan_pos = m->nan_pos.as<unsigned long long>(); fa.n_streams = ns; fa.g0 = m->written;
         if (front_nt == 128) {
             if (m->push_pcm16) { LAUNCH("k_front", (k_front<int16_t, 128><<<ns * fa.spans, 128, AMB_FRONT_SMEM(128), m->stream>>>(fa))); }
             else { LAUNCH("k_front", (k_front<float, 128><<<ns * fa.spans, 128, AMB_FRONT_SMEM(128), m->stream>>>(fa))); }
@@ -963,6 +975,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
             if (m->push_pcm16) { LAUNCH("k_front", (k_front<int16_t, 256><<<ns * fa.spans, 256, AMB_FRONT_SMEM(256), m->stream>>>(fa))); }
             else { LAUNCH("k_front", (k_front<float, 256><<<ns * fa.spans, 256, AMB_FRONT_SMEM(256), m->stream>>>(fa))); }
         }
+        LAUNCH("k_nan_fix", k_nan_fix<<<148 * 4, 256, 0, m->stream>>>(fa, n_new, m->base_g));
     }
     const int tri_grid_max = 148 * 64;
     LAUNCH("k_tri_store", k_tri_store<<<(m->slot_cap + 3) / 4 < tri_grid_max ? (m->slot_cap + 3) / 4 : tri_grid_max, 128, 0, m->stream>>>(m->cleaned.as<float>(), m->stride, m->base_g, m->written + n_new, ss));
@@ -1176,6 +1189,8 @@ static int stream_push_any(amb_modem* m, const void* xv, int es, int64_t x_strid
     if (mem != AMB_MEM_HOST && mem != AMB_MEM_DEVICE && mem != AMB_MEM_INPLACE) return fail(m, AMB_E_INVALID, "bad mem");
     if (results_mem != AMB_MEM_HOST && results_mem != AMB_MEM_DEVICE) return fail(m, AMB_E_INVALID, "bad results_mem");
     if (!n_results) return fail(m, AMB_E_INVALID, "n_results required");
+    if (bytes_out && bytes_stride <= 0) return fail(m, AMB_E_INVALID, "bytes_stride must be positive");
+    if (max_results < 0) return fail(m, AMB_E_INVALID, "max_results must not be negative");
     if (mem != AMB_MEM_INPLACE && !xv) return fail(m, AMB_E_INVALID, "x required");
     if (mem == AMB_MEM_INPLACE && es != 4) return fail(m, AMB_E_INVALID, "the in-place window holds float32 samples");
     if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, AMB_E_CUDA, "cudaSetDevice failed");

@@ -130,6 +130,9 @@ struct AmbFrontArgs {
     const AmbEmaTables* E; const AmbStreamState* states; double* dc_next;
     float* sums; int64_t sum_stride;
     AmbScanStore st;
+    // non-finite input (float32 pushes): nan_pos[s] = global index of the stream's first NaN / infinite sample in this push
+    // (atomic minimum; ~0 = none), nan_pos[n_streams] = 1 when any stream has one; g0 = global index of the push start
+    unsigned long long* nan_pos; int n_streams; int64_t g0;
 };
 
 #define AMB_FR_PAD(i) ((i) + (((i) >> 5) << 2))       // 4 floats of padding per 32: 128-bit accesses are conflict-free both per thread (16-float rows, 64 bytes apart) and consecutive
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
     // The EMA runs on u = m / beta (u <- alpha u + x: one FMA per sample instead of a multiplication and an FMA), and
     // cleaned = x - beta u is one more FMA.
     double m_tile = tb == 0 ? a.states[s].dc_mean / beta : 0.0;
+    if (tb == 0 && tid == 0 && a.nan_pos && !(m_tile - m_tile == 0.0)) { atomicMin(a.nan_pos + s, (unsigned long long)a.g0); a.nan_pos[a.n_streams] = 1ull; }     // poisoned by an earlier push
     // ---- history of the scan part: lives in buffer 1 (the first full tile goes to buffer 0)
     for (int i = tid; i < 2 * FBUF; i += NT) R[i] = 0.f;
     sq[0][tid] = sa[0][tid] = sT[0][tid] = sI[0][tid] = sJ[0][tid] = 0.f;
@@ -320,6 +324,18 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
                 }
             }
         }
+        if (sizeof(IN) == 4 && emit && !(q - q == 0.f) && a.nan_pos) {
+            // a NaN or an infinity among this thread's samples, or carried in through the EMA state: the reference's dcMean is NaN
+            // (or infinite) from the first such sample on and every cleaned sample after it is useless (app.js:750-755).  Record
+            // the first one; k_nan_fix makes the rest of the push follow.
+            for (int k = 0; k < 16; k++) {
+                if (!(x[k] - x[k] == 0.f)) {
+                    atomicMin(a.nan_pos + s, (unsigned long long)(a.g0 + (int64_t)t * FT + 16 * tid + k));
+                    a.nan_pos[a.n_streams] = 1ull;
+                    break;
+                }
+            }
+        }
         float iq = q, it = tt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -391,6 +407,38 @@ __global__ void __launch_bounds__(NT, 768 / NT) k_front(AmbFrontArgs a) {
         n++;
     }
     if (t1 == a.tiles && tid == 0) a.dc_next[s] = m_tile * beta;
+}
+
+// Non-finite input (rare path; exits at once unless k_front raised the flag).  From a stream's first NaN / infinite sample on,
+// the reference's DC mean is NaN and so is every cleaned sample (app.js:750-755); k_front's spans restart their EMA from a
+// 40,960-sample warm-up and would recover, so the rest of the push is made to follow here: cleaned samples NaN, the summary of
+// the tile the first bad window ends in forced hot (its earlier windows are still good: the walker evaluates it inline), the
+// tiles after it cold (every window holds a NaN: no gate passes), the defect terms and the carried mean NaN.
+__global__ void __launch_bounds__(256) k_nan_fix(AmbFrontArgs a, int64_t n_new, int64_t base_g) {
+    if (a.nan_pos[a.n_streams] == 0ull) return;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int s = 0; s < a.n_streams; s++) {
+        const unsigned long long np = a.nan_pos[s];
+        if (np == ~0ull) continue;
+        const int64_t g_bad = (int64_t)np, g_end = a.g0 + n_new;
+        float* crow = a.cleaned + (int64_t)s * a.stride;
+        for (int64_t g = g_bad + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += (int64_t)gridDim.x * blockDim.x) crow[g - base_g] = qnan;
+        const int64_t j_bad = (g_bad - base_g) >> 8, j_end = (g_end - base_g) >> 8;
+        for (int64_t j = j_bad + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_end; j += (int64_t)gridDim.x * blockDim.x) {
+            float* o = a.sums + ((int64_t)s * a.sum_stride + j) * AMB_SUM_W;
+            const bool boundary = j == j_bad;
+            o[0] = boundary ? 3.0e38f : 0.f; o[1] = 0.f; o[2] = boundary ? 3.0e38f : 0.f; o[3] = 0.f; o[4] = boundary ? 3.0e38f : 0.f;
+            if (a.st.tile_slot) a.st.tile_slot[(int64_t)s * a.sum_stride + j] = -1;
+        }
+        if (a.st.defect) {
+            const int64_t c_bad = (g_bad - base_g + AMB_TILE - 1) >> 12, c_end = (g_end - base_g) >> 12;      // calls whose first sample is at or after the bad one
+            for (int64_t c = c_bad + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c_end; c += (int64_t)gridDim.x * blockDim.x) {
+                double* D = a.st.defect + ((int64_t)s * a.st.calls_stride + c) * 3;
+                D[0] = D[1] = D[2] = (double)qnan;
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.dc_next[s] = (double)qnan;
+    }
 }
 
 // Exact float64 window sums (P, Ra, Rb) of the 256 windows of every slotted tile, and the exact candidate flag
@@ -892,7 +940,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
             amb_result_clear(&r);
             r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
             r.status = J.status;
-            if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
+            if (J.status == AMB_ST_RING_OVERWRITTEN) { r.preamble_idx = J.result_pos; r.coarse_metric = 0.0; r.fine_metric = 0.0; }      // (the reference only counts it, app.js:912-916)
             po.results[j] = r;
         }
         return;
@@ -1213,7 +1261,8 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
 #define AMB_PARSE_SMEM 8192      // decoded frames up to this many bytes are packed, parsed and checksummed in shared memory
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride /*multiple of 16*/, amb_frame_result* __restrict__ results,
-                                                uint8_t* __restrict__ bytes_out, int64_t bytes_stride, const uint32_t* __restrict__ crc_ops) {
+                                                uint8_t* __restrict__ bytes_out, int64_t bytes_stride, const uint32_t* __restrict__ crc_ops,
+                                                uint8_t* __restrict__ scratch, int64_t scratch_stride) {
     __shared__ uint32_t tab[256];
     __shared__ uint32_t sh[AMB_CRC_THREADS];
     __shared__ __align__(16) uint8_t sb[AMB_PARSE_SMEM];
@@ -1231,7 +1280,7 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
                 amb_result_clear(&r);
                 r.stream = J.stream; r.coarse_metric = J.coarse; r.fine_metric = J.fine;
                 r.status = J.status;
-                if (J.status == AMB_ST_RING_OVERWRITTEN) r.preamble_idx = J.result_pos;
+                if (J.status == AMB_ST_RING_OVERWRITTEN) { r.preamble_idx = J.result_pos; r.coarse_metric = 0.0; r.fine_metric = 0.0; }      // (the reference only counts it, app.js:912-916)
                 results[j] = r;
             }
             continue;
@@ -1239,10 +1288,12 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
         uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
         const uint8_t* ix = idx + (int64_t)j * idx_stride;
         const int64_t n_elems = (int64_t)J.nsym * T->n_data;
-        const int64_t nb_full = amb_num_bytes(n_elems, bps, rep);
-        const int64_t nb = nb_full < bytes_stride ? nb_full : bytes_stride;
+        // The whole decoded frame is packed, parsed and checksummed - in shared memory when it fits, else in the caller's row when
+        // that holds it, else in a scratch row - and the caller's row gets what fits into it (n_bytes reports the full length).
+        const int64_t nb = amb_num_bytes(n_elems, bps, rep), nb_full = nb;
+        const int64_t nb_copy = nb < bytes_stride ? nb : bytes_stride;
         const bool in_smem = nb <= AMB_PARSE_SMEM;
-        uint8_t* dst = in_smem ? sb : bytes;
+        uint8_t* dst = in_smem ? sb : (nb <= bytes_stride || !scratch ? bytes : scratch + (int64_t)j * scratch_stride);
         // majorityVote + bitsToBytes.  Without repetition whole constellation indices pack into bytes: 8 (16-QAM) or 16 (QPSK)
         // indices per 128-bit / 64-bit load make 4 bytes.
         int64_t b0 = 0;
@@ -1265,12 +1316,14 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
         if (in_smem) {
             // decoded bytes to the caller's row (16-byte stores where the row allows)
             if ((((uintptr_t)bytes) & 15) == 0) {
-                const int64_t vec = nb / 16;
+                const int64_t vec = nb_copy / 16;
                 for (int64_t q = tid; q < vec; q += AMB_CRC_THREADS) reinterpret_cast<uint4*>(bytes)[q] = reinterpret_cast<const uint4*>(sb)[q];
-                for (int64_t b = vec * 16 + tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = sb[b];
+                for (int64_t b = vec * 16 + tid; b < nb_copy; b += AMB_CRC_THREADS) bytes[b] = sb[b];
             } else {
-                for (int64_t b = tid; b < nb; b += AMB_CRC_THREADS) bytes[b] = sb[b];
+                for (int64_t b = tid; b < nb_copy; b += AMB_CRC_THREADS) bytes[b] = sb[b];
             }
+        } else if (dst != bytes) {
+            for (int64_t b = tid; b < nb_copy; b += AMB_CRC_THREADS) bytes[b] = dst[b];
         }
         if (tid == 0) {
             amb_frame_result r;
@@ -1989,6 +2042,7 @@ __global__ void __launch_bounds__(128) k_store_chunks(const amb_frame_result* __
         int64_t len = r.data_len;
         if (off >= file_cap) continue;
         if (off + len > file_cap) len = file_cap - off;
+        if (r.data_off + len > bytes_stride) len = bytes_stride > r.data_off ? bytes_stride - r.data_off : 0;      // (a row shorter than the chunk: what the caller got)
         const uint8_t* src = bytes + (int64_t)j * bytes_stride + r.data_off;
         uint8_t* dst = files + (int64_t)r.stream * file_cap + off;
         for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];

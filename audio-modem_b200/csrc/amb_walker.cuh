@@ -12,9 +12,19 @@
 //     constant defect  T(a-1) - T(a+255)  (a = first position of that call) until the next re-init.  The
 //     walker carries that defect explicitly (Ep, Ea, Eb) and the one-sample lag flag.
 //   * the pre-metadata collection window is a fixed 280-byte guess (app.js:892-896).
-// Exact ties on a noise-free plateau: the reference's sums are unchanged by the exact-zero updates, so
-// its strict '>' keeps the first plateau sample; directly evaluated sums differ in the last ulp, so a
-// new best must exceed the old one by 1e-12 relative here.
+// Near-ties and threshold crossings.  The walker evaluates window sums directly (or from prefix differences), the reference
+// carries sliding accumulators: after up to AMB_REPLAY_MAX slides the two differ by a few 1e-12 relative (3e-12 is the largest
+// seen in the tests).  Whenever a decision of a call could come out differently because of that, the call is run again by
+// amb_walk_scan_exact, which replays the reference's own recurrence from the position where its sums were last
+// re-initialised (direct summation, app.js:791-803) and applies its strict comparisons:
+//   * threshold decisions - a metric against 0.5 or 0.7 * best (app.js:811, :833), an energy against the 0.001 gate (:809,
+//     :831) - inside a relative band of AMB_BAND = 1e-10 around equality;
+//   * a candidate against the running best of the same call (app.js:811) inside AMB_BAND_TIE = 1e-12: the history the
+//     reference's two values share cancels in their difference (what is left is the rounding of the slides between the two
+//     positions, ~1e-15, and the change of the metric's gradient across the plateau times the common error, ~1e-14), and two
+//     directly evaluated metrics differ from the true ones by ~1e-13 each.
+// Only when the re-initialisation lies more than AMB_REPLAY_MAX slides back (a near-tie deep inside an idle stretch) does
+// the old rule decide: a new best must exceed the old one by 1e-12 relative.
 #pragma once
 #include "amb_device.cuh"
 
@@ -56,6 +66,7 @@ struct AmbStreamState {
     int32_t state, ac_init, lag, meta_received, chunk_size, total_chunks;
     int32_t total_file_size;            // of the metadata frame in force (ChunkAssembler.totalFileSize)
     int32_t init_call;                  // call in which the running sums were last re-initialised (meaningful while ac_init)
+    int64_t init_pos;                   // ... and the position at which they were (amb_walk_scan_exact replays from there)
     int64_t ac_scan_pos, pre_pos, frame_end;
     double Ep, Ea, Eb;
     double coarse, fine;
@@ -436,16 +447,24 @@ AMB_HD bool amb_scan_batch_serial(AmbStreamState& st, const AmbWalkScratch* W, i
     return false;
 }
 
-AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos);
+#define AMB_BAND 1e-10               // threshold decisions inside this relative band around equality are settled by the exact replay
+#define AMB_BAND_TIE 1e-12           // ... and comparisons between two metrics of one call inside this one (see the header comment)
+#ifndef AMB_REPLAY_MAX
+#define AMB_REPLAY_MAX 65536         // slides the replay may have to redo before the call in question
+#endif
 
-AMB_HD bool amb_scan_batch(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
+AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos,
+                                   int* ambig = nullptr);
+
+AMB_HD bool amb_scan_batch(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos,
+                           int* ambig = nullptr) {
 #if defined(AMB_EMU_CHECK) && !defined(__CUDA_ARCH__)
     // test build: the reduction form must agree with the serial loop on every batch
     AmbStreamState s2 = st;
     double b2 = best;
     int64_t p2 = best_pos;
     const bool r2 = amb_scan_batch_serial(s2, W, d, cnt, scan_end, b2, p2);
-    const bool r1 = amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos);
+    const bool r1 = amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos, ambig);
     if (r1 != r2 || b2 != best || p2 != best_pos || s2.pre_pos != st.pre_pos || s2.coarse != st.coarse || s2.state != st.state ||
         s2.ac_scan_pos != st.ac_scan_pos || s2.lag != st.lag) {
         fprintf(stderr, "amb_scan_batch mismatch: d=%lld cnt=%d r=%d/%d best=%.17g/%.17g pos=%lld/%lld\n", (long long)d, cnt, (int)r1, (int)r2, best, b2,
@@ -454,11 +473,12 @@ AMB_HD bool amb_scan_batch(AmbStreamState& st, const AmbWalkScratch* W, int64_t 
     }
     return r1;
 #else
-    return amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos);
+    return amb_scan_batch_reduced(st, W, d, cnt, scan_end, best, best_pos, ambig);
 #endif
 }
 
-AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos) {
+AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, int64_t d, int cnt, int64_t scan_end, double& best, int64_t& best_pos,
+                                   int* ambig) {
     const bool tracking = best > 0.5 && best_pos >= 0;
     if (!tracking && best > 0.5) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);      // not a state the walker produces
     double carry = tracking ? best : 0.0;          // running maximum before the current chunk (0: none yet)
@@ -471,13 +491,15 @@ AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, 
         const double prev = fmax(carry, amb_warp_prev(pm, -1.0));       // running maximum before position i
         const double r = fmax(carry, pm);                               // ... and at position i
         const bool amb = v > prev && !(v > prev * (1.0 + 1e-12));       // an update the 1e-12 rule would suppress
-        bool trig = false;
+        bool trig = false, band = v > 0.0 && prev > 0.5 && fabs(v - prev) <= AMB_BAND_TIE * prev;  // a candidate within the band of the running best
         if (in && r > 0.5) {
             const int nxt = d + i < scan_end ? i + 1 : i;
             trig = W->gate[nxt] && W->M[nxt] < r * 0.7;
+            if (W->gate[nxt] && fabs(W->M[nxt] - r * 0.7) <= AMB_BAND * r) band = true;               // the 0.7 test within the band
         }
         const unsigned tb = amb_warp_ballot(trig), ab = amb_warp_ballot(amb);
         const int u = tb ? amb_ffs(tb) - 1 : AMB_NLANES;                // lane of the first commit in this chunk
+        if (ambig) { const unsigned bb = amb_warp_ballot(band); if (bb & (u < AMB_NLANES ? ((2u << u) - 1u) : 0xffffffffu)) *ambig = 1; }
         if (ab & (u < AMB_NLANES ? ((2u << u) - 1u) : 0xffffffffu)) return amb_scan_batch_serial(st, W, d, cnt, scan_end, best, best_pos);
         const double top = amb_warp_bcast(u < AMB_NLANES ? r : pm, u < AMB_NLANES ? u : AMB_NLANES - 1);
         if (top > carry) {
@@ -495,6 +517,127 @@ AMB_HD bool amb_scan_batch_reduced(AmbStreamState& st, const AmbWalkScratch* W, 
     return false;
 }
 
+// true when x lies within the relative band around y
+AMB_HD bool amb_near(double x, double y) { return fabs(x - y) <= AMB_BAND * fabs(y); }
+// an energy pair whose 0.001 gate could come out differently in the reference
+AMB_HD bool amb_gate_near(double a, double b) {
+    return (amb_near(a, 0.001) && b > 0.001 * (1.0 - AMB_BAND)) || (amb_near(b, 0.001) && a > 0.001 * (1.0 - AMB_BAND));
+}
+
+// One call of _scanForPreamble exactly as the reference runs it (app.js:775-847): its running sums are re-created by direct
+// summation at st.init_pos (app.js:791-803) and slid position by position - every position except the last one of a call,
+// where the reference only advances acScanPos (app.js:826) - up to the call's first position, then the loop of
+// app.js:806-846 runs with strict comparisons.  The update terms of 256 positions at a time (mid*bIn - aOut*mid, ...) do not
+// depend on the sums: the lanes compute them into the scratch arrays, and one lane carries the three chains of additions
+// and the candidate logic.  The quotient p^2 / (ra rb) is only formed where a comparison needs it (a product comparison with
+// a 1e-7 margin settles the rest).  st is the state at call entry (ring clamp and re-initialisation applied).  Returns
+// false, leaving st alone, when the replay would be longer than AMB_REPLAY_MAX slides.
+// eval_from: first position of the call at which the fast path evaluated a window; before it the tile summaries prove (with
+// margins far above the band) that no window can be a candidate, so the replay only slides there.
+AMB_HD bool amb_walk_scan_exact(const AmbWalkGeom& G, const AmbSig& sig, AmbStreamState& st, int64_t tw, AmbWalkScratch* W, int64_t eval_from) {
+    const int64_t scan_end = tw - 2 * AMB_HALF;
+    const int64_t start = st.ac_scan_pos;
+    if (!st.ac_init || start < st.init_pos || start - st.init_pos > AMB_REPLAY_MAX || start > scan_end) return false;
+    if (eval_from < start) eval_from = start;
+    if (eval_from > scan_end + 1) eval_from = scan_end + 1;
+    // (the call that re-initialised the sums scanned from init_pos to its own end in one go, across any block boundaries the
+    // receiver had spent collecting a frame: only the call ends from that one on are skipped)
+    const int64_t first_end = ((int64_t)st.init_call + 1) * G.block_len - 2 * AMB_HALF;
+    double p = 0.0, ra = 0.0, rb = 0.0, best = 0.0;
+    int64_t best_pos = -1, end_pos = scan_end + 1;
+    int committed = 0;
+    if (AMB_LEADER()) {
+        for (int m = 0; m < AMB_HALF; m++) {
+            const double a = (double)amb_sig(sig, st.init_pos + m), b = (double)amb_sig(sig, st.init_pos + m + AMB_HALF);
+            p = amb_add(p, amb_mul(a, b)); ra = amb_add(ra, amb_mul(a, a)); rb = amb_add(rb, amb_mul(b, b));
+        }
+    }
+    // next position whose slide is skipped (the last position of a call, from the re-initialising call on)
+    int64_t next_skip = first_end;
+    // ---- phase 1: positions [init_pos, eval_from): slides only
+    for (int64_t pos = st.init_pos; pos < eval_from; pos += 256) {
+        const int n = (int)(eval_from - pos < 256 ? eval_from - pos : 256);
+        AMB_WARP_FOR(i, n) {
+            const int64_t L = pos + i;
+            const double ao = (double)amb_sig(sig, L), mid = (double)amb_sig(sig, L + AMB_HALF), bi = (double)amb_sig(sig, L + 2 * AMB_HALF);
+            W->M[i] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
+            W->A[i] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
+            W->B[i] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
+        }
+        AMB_WARP_SYNC();
+        if (AMB_LEADER()) {
+            // at most one skipped position per chunk (calls are longer than a chunk)
+            int k = next_skip >= pos && next_skip < pos + n ? (int)(next_skip - pos) : n;
+            int i = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 8
+#endif
+            for (; i < k; i++) { p = amb_add(p, W->M[i]); ra = amb_add(ra, W->A[i]); rb = amb_add(rb, W->B[i]); }
+            if (k < n) {
+                next_skip += G.block_len;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 8
+#endif
+                for (i = k + 1; i < n; i++) { p = amb_add(p, W->M[i]); ra = amb_add(ra, W->A[i]); rb = amb_add(rb, W->B[i]); }
+            }
+        }
+        AMB_WARP_SYNC();
+    }
+    while (next_skip < eval_from) next_skip += G.block_len;       // (lanes other than the leader did not advance it)
+    // ---- phase 2: positions [eval_from, scan_end]: the loop of app.js:806-846
+    for (int64_t pos = eval_from; pos <= scan_end && !committed; pos += 256) {
+        const int n = (int)(scan_end + 1 - pos < 256 ? scan_end + 1 - pos : 256);
+        AMB_WARP_FOR(i, n) {
+            const int64_t L = pos + i;
+            const double ao = (double)amb_sig(sig, L), mid = (double)amb_sig(sig, L + AMB_HALF), bi = (double)amb_sig(sig, L + 2 * AMB_HALF);
+            W->M[i] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
+            W->A[i] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
+            W->B[i] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
+        }
+        AMB_WARP_SYNC();
+        if (AMB_LEADER()) {
+            for (int i = 0; i < n; i++) {
+                const int64_t L = pos + i;
+                if (ra > 0.001 && rb > 0.001) {
+                    const double num = amb_mul(p, p), den = amb_mul(ra, rb);
+                    if (num > 0.4999999 * den && (!(best > 0.5) || num > best * 0.9999999 * den)) {
+                        const double m = amb_div(num, den);
+                        if (m > 0.5 && m > best) { best = m; best_pos = L; }
+                    }
+                }
+                if (L < scan_end) { p = amb_add(p, W->M[i]); ra = amb_add(ra, W->A[i]); rb = amb_add(rb, W->B[i]); }      // (scan_end: the call's last position, no slide)
+                if (best > 0.5 && best_pos >= 0 && ra > 0.001 && rb > 0.001) {
+                    const double num = amb_mul(p, p), den = amb_mul(ra, rb), lim = amb_mul(best, 0.7);
+                    bool drop;
+                    if (num < lim * 0.9999999 * den) drop = true;
+                    else if (num > lim * 1.0000001 * den) drop = false;
+                    else drop = amb_div(num, den) < lim;
+                    if (drop) { committed = 1; end_pos = L + 1; break; }
+                }
+            }
+        }
+        AMB_WARP_SYNC();
+        committed = amb_warp_bcast((double)committed, 0) != 0.0;
+    }
+    best = amb_warp_bcast(best, 0);
+    best_pos = (int64_t)amb_warp_bcast((double)best_pos, 0);
+    end_pos = (int64_t)amb_warp_bcast((double)end_pos, 0);
+    // the defect bookkeeping of the fast path (the lag branch of amb_walk_scan_fast): label `start` still described window start - 1
+    if (st.lag == 1 && start < scan_end) {
+        const double xm1 = (double)amb_sig(sig, start - 1), x255 = (double)amb_sig(sig, start + 255), x511 = (double)amb_sig(sig, start + 511);
+        st.Ep += xm1 * x255 - x255 * x511; st.Ea += xm1 * xm1 - x255 * x255; st.Eb += x255 * x255 - x511 * x511;
+        st.lag = 0;
+    }
+    if (committed) { amb_commit(st, best_pos, best, end_pos, end_pos - 1 < scan_end ? 0 : 1); return true; }
+    st.ac_scan_pos = scan_end + 1;
+    st.lag = 1;
+    if (best > 0.5 && best_pos >= 0) amb_commit(st, best_pos, best, scan_end + 1, 1);
+    return true;
+}
+
+AMB_HD void amb_walk_scan_fast(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums,
+                               AmbStreamState& st, int64_t tw, AmbWalkScratch* W, int* ambig, int64_t* eval_from);
+
 // _scanForPreamble, app.js:775-847, for the call whose totalWritten is `tw`
 AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums,
                           AmbStreamState& st, int64_t tw, AmbWalkScratch* W) {
@@ -507,8 +650,36 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
     if (st.ac_scan_pos > scan_end) return;
     if (!st.ac_init) {
         if (st.ac_scan_pos < oldest) return;
-        st.Ep = st.Ea = st.Eb = 0.0; st.lag = 0; st.ac_init = 1; st.init_call = (int32_t)(tw / G.block_len - 1);
+        st.Ep = st.Ea = st.Eb = 0.0; st.lag = 0; st.ac_init = 1; st.init_call = (int32_t)(tw / G.block_len - 1); st.init_pos = st.ac_scan_pos;
     }
+    // (the fields a scan call can change: saved so that the exact replay can start from the same state)
+    const int64_t s_pos = st.ac_scan_pos, s_pre = st.pre_pos;
+    const double s_Ep = st.Ep, s_Ea = st.Ea, s_Eb = st.Eb, s_coarse = st.coarse;
+    const int s_lag = st.lag, s_state = st.state;
+    int ambig = 0;
+    int64_t eval_from = (int64_t)1 << 62;
+    amb_walk_scan_fast(T, G, sig, sums, st, tw, W, &ambig, &eval_from);
+    if (amb_warp_any(ambig != 0) && s_pos >= st.init_pos && s_pos - st.init_pos <= AMB_REPLAY_MAX) {
+        AMB_STAT(13);
+#if !defined(__CUDA_ARCH__) && defined(AMB_EMU_CHECK)
+        const AmbStreamState fast = st;
+#endif
+        st.ac_scan_pos = s_pos; st.pre_pos = s_pre; st.Ep = s_Ep; st.Ea = s_Ea; st.Eb = s_Eb; st.coarse = s_coarse; st.lag = s_lag; st.state = s_state;
+        amb_walk_scan_exact(G, sig, st, tw, W, eval_from);
+#if !defined(__CUDA_ARCH__) && defined(AMB_EMU_CHECK)
+        if (getenv("EMU_DEBUG"))
+            fprintf(stderr, "exact call tw=%lld start=%lld init_pos=%lld lag=%d | fast: state %d pre %lld coarse %.17g scan %lld lag %d | exact: state %d pre %lld coarse %.17g scan %lld lag %d\n",
+                    (long long)tw, (long long)s_pos, (long long)st.init_pos, s_lag, fast.state, (long long)fast.pre_pos, fast.coarse, (long long)fast.ac_scan_pos, fast.lag,
+                    st.state, (long long)st.pre_pos, st.coarse, (long long)st.ac_scan_pos, st.lag);
+#endif
+    }
+}
+
+// the call with directly evaluated window sums (state at entry: ring clamp and re-initialisation applied); *ambig is set when
+// one of its decisions falls inside the band
+AMB_HD void amb_walk_scan_fast(const AmbTables* T, const AmbWalkGeom& G, const AmbSig& sig, const float* sums,
+                               AmbStreamState& st, int64_t tw, AmbWalkScratch* W, int* ambig, int64_t* eval_from) {
+    const int64_t scan_end = tw - 2 * AMB_HALF;
     double best = 0.0;
     int64_t best_pos = -1;
     int64_t d = st.ac_scan_pos;
@@ -523,9 +694,11 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             if (d - 1 >= 0 && rel >= 0 && rel < G.sum_tiles && (jj << 8) >= G.sum_lo) cold = !amb_tile_hot2(G, sums, jj, rel, st.Ep, st.Ea, st.Eb);
         }
         if (!cold) {
+            if (d < *eval_from) *eval_from = d;
             amb_eval_windows(G, sig, d - 1, 3, W->M, W->A, W->B);
             double m;
             if (amb_metric(W->M[0], W->A[0], W->B[0], st, &m) && m > 0.5 && m > best) { best = m; best_pos = d; }
+            if (amb_gate_near(W->A[0] + st.Ea, W->B[0] + st.Eb) || amb_near(m, 0.5)) *ambig = 1;
         }
         if (d < scan_end) {
             // slide with the label d: removes T(d), adds T(d+256)  ->  W(d+1) + [T(d-1) - T(d+255)]
@@ -536,7 +709,9 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             st.lag = 0;
             if (best > 0.5) {
                 double cur;
-                if (amb_metric(W->M[2], W->A[2], W->B[2], st, &cur) && cur < best * 0.7) { amb_commit(st, best_pos, best, d + 1, 0); return; }
+                const int gate_cur = amb_metric(W->M[2], W->A[2], W->B[2], st, &cur);
+                if (amb_gate_near(W->A[2] + st.Ea, W->B[2] + st.Eb) || (gate_cur && amb_near(cur, best * 0.7))) *ambig = 1;
+                if (gate_cur && cur < best * 0.7) { amb_commit(st, best_pos, best, d + 1, 0); return; }
             }
             d = d + 1;
         } else {
@@ -583,6 +758,7 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
         if (d_end > scan_end) d_end = scan_end;
         const int cnt = (int)(d_end - d + 1);
         const int look = d_end < scan_end ? 1 : 0;
+        if (d < *eval_from) *eval_from = d;
         amb_eval_windows(G, sig, d, cnt + look, W->M, W->A, W->B);
         if (!(best > 0.5)) {
             // idle: unless some window can pass metric > 0.5 (p^2 > 0.5 a b, tested with a margin far above the rounding of the
@@ -590,17 +766,21 @@ AMB_HD void amb_walk_scan(const AmbTables* T, const AmbWalkGeom& G, const AmbSig
             bool maybe = false;
             AMB_WARP_FOR(i, cnt + look) {
                 const double a = W->A[i] + st.Ea, b = W->B[i] + st.Eb, pp = W->M[i] + st.Ep;
-                if (a > 0.001 && b > 0.001 && pp * pp > 0.5 * a * b * (1.0 - 1e-12)) maybe = true;
+                if (a > 0.001 * (1.0 - AMB_BAND) && b > 0.001 * (1.0 - AMB_BAND) && pp * pp > 0.5 * a * b * (1.0 - 4.0 * AMB_BAND)) maybe = true;
             }
             if (!amb_warp_any(maybe)) { AMB_WARP_SYNC(); d = d_end + 1; continue; }
         }
+        bool near_thr = false;
         AMB_WARP_FOR(i, cnt + look) {
             double m;
+            const double a = W->A[i] + st.Ea, b = W->B[i] + st.Eb;
             W->gate[i] = amb_metric(W->M[i], W->A[i], W->B[i], st, &m);
             W->M[i] = m;
+            if (amb_gate_near(a, b) || (W->gate[i] && amb_near(m, 0.5))) near_thr = true;
         }
+        if (amb_warp_any(near_thr)) *ambig = 1;
         AMB_WARP_SYNC();
-        if (amb_scan_batch(st, W, d, cnt, scan_end, best, best_pos)) { AMB_WARP_SYNC(); return; }
+        if (amb_scan_batch(st, W, d, cnt, scan_end, best, best_pos, ambig)) { AMB_WARP_SYNC(); return; }
         AMB_WARP_SYNC();
         d = d_end + 1;
     }
@@ -783,5 +963,5 @@ AMB_HD int amb_run_at_or_after(const AmbRun* runs, int n, int64_t e) {
 AMB_HD bool amb_same_link_state(const AmbStreamState& a, const AmbStreamState& b) {
     return a.state == b.state && a.ac_init == b.ac_init && a.ac_scan_pos == b.ac_scan_pos && a.next_call == b.next_call &&
            a.pre_pos == b.pre_pos && a.frame_end == b.frame_end && a.meta_received == b.meta_received && a.chunk_size == b.chunk_size &&
-           (a.ac_init == 0 || (a.lag == b.lag && a.init_call == b.init_call && a.Ep == b.Ep && a.Ea == b.Ea && a.Eb == b.Eb));
+           (a.ac_init == 0 || (a.lag == b.lag && a.init_call == b.init_call && a.init_pos == b.init_pos && a.Ep == b.Ep && a.Ea == b.Ea && a.Eb == b.Eb));
 }

@@ -202,7 +202,11 @@ int amb_stream_close(amb_modem* m);
 /* where the next push's samples go on the device (stream s at dev_ptr + s*stride floats); for AMB_MEM_INPLACE */
 int amb_stream_input_window(amb_modem* m, float** dev_ptr, int64_t* stride);
 /* Feed n_new samples (multiple of block_len) to every stream: x = [n_streams][x_stride].  Frames completed by
- * these samples come back in stream-major, time order; bytes_out row j belongs to results[j]. */
+ * these samples come back grouped by stream and in time order within a stream (results[j].stream names it); a large host
+ * push is processed in sections, each of which delivers its own group.  bytes_out row j (bytes_stride bytes) belongs to
+ * results[j]: it receives the first min(n_bytes, bytes_stride) decoded bytes.  Parsing, the CRC verdict and n_bytes always
+ * cover the whole decoded frame, whatever the row length: a row shorter than n_bytes only truncates what the caller reads
+ * (a stream whose metadata frame announces a larger chunkSize than the rows were sized for still reports correct results). */
 int amb_stream_push(amb_modem* m, const float* x, int64_t x_stride, int64_t n_new, int mem, amb_frame_result* results,
                     int max_results, int* n_results, uint8_t* bytes_out, int64_t bytes_stride, int results_mem);
 /* Wire-format ingest: the same push with signed 16-bit PCM samples; sample value = s / 32768 (exact in

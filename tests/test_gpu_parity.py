@@ -531,3 +531,115 @@ def test_tx_transmit_signal_bit_identical(O, amb, modems, mode):
         assert r["crcValid"] and r["data"] == datas[0] and r["fileName"] == "a.bin"
         assert amb.analyzeLoopback(t["signal"], mod, rep, t["testData"])["quality"] == "excellent"
     amb.setOFDMConfig("standard")
+
+
+# ---------------------------------------------------------------------------------------------- edge cases added in round 2
+def _stream_events(O, amb, mode, x, pushes, max_chunk=4096, clip_ok=False):
+    """events of the CUDA path and of the oracle for one stream; with clip_ok the decoded-byte rows may be shorter than the
+    frame (the fields, CRC verdict and n_bytes must still be the oracle's, the bytes equal up to the row length)"""
+    cfg, mod, rep, _ = MODES[mode]
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        m.stream_open(1, 4096, max(pushes), max_chunk=max_chunk)
+        got, off = [], 0
+        for p in pushes:
+            got += m.stream_push(x[None, off:off + p], raw=True)
+            off += p
+        assert off == len(x)
+        rx = O.StreamingReceiver(cfg, mod, rep)
+        want = rx.push(x, 4096, raw=True)
+        assert len(got) == len(want), (len(got), len(want))
+        for (r1, b1), (r2, b2) in zip(want, got):
+            if clip_ok and len(b2) < len(b1):
+                assert len(b2) == m.bytes_stride and r2.n_bytes == r1.n_bytes
+                b1 = b1[:len(b2)]
+            assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (mode, r1.preamble_idx, results_equal(r1, b1, r2, b2, metric_tol=1e-9))
+        c, w = m.stream_counters(), rx.counters()
+        for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived", "receivedCount", "duplicates"):
+            assert c[k] == w[k], (k, c, w)
+        return want
+    finally:
+        m.close()
+
+
+def _pushes(n, per):
+    return [per] * (n // per) + ([n % per] if n % per else [])
+
+
+def test_stream_chunk_size_larger_than_the_rows(O, amb):
+    """a metadata frame announcing chunkSize 8192 (rows sized for 4096): the collection window follows it (app.js:892-896); the
+    results - fields, CRC verdict, n_bytes - do not depend on the caller's row length (k_parse used to parse the
+    clipped row), and with rows sized for the chunk the bytes are the oracle's"""
+    cfg, mod, rep, _ = MODES["QPSK"]
+    big = 8192
+    parts = [O.buildMetadataFrame(cfg, 2, 2 * big, big, "big.bin", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(70 + i, big), i, mod, rep) for i in range(2)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(80, 2048), 2, mod, rep)]          # a short chunk inside the long window
+    x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 9), tail=4 * 4096)
+    ev = _stream_events(O, amb, "QPSK", x, _pushes(len(x), 16 * 4096), clip_ok=True)
+    assert sum(1 for r, _ in ev if r.status == 0 and r.frame_type == 0xFF and r.crc_valid and r.data_len == big) == 2
+    _stream_events(O, amb, "QPSK", x, [len(x)], max_chunk=big)
+
+
+def test_stream_ring_overwritten(O, amb):
+    """RingBuffer.getRange -> null (app.js:581-582, :912-916): a metadata frame announcing a chunkSize whose collection window
+    is longer than the ring (3 * estimateFrameSamples(4112) + 8192, app.js:712-715) makes every later frame a frameError
+    without a message"""
+    cfg, mod, rep, _ = MODES["QPSK"]
+    huge = 20000
+    parts = [O.buildMetadataFrame(cfg, 2, 2 * huge, huge, "huge.bin", mod, rep)]
+    parts += [O.buildDataChunkFrame(cfg, O.randomBytes(90 + i, 2048), i, mod, rep) for i in range(6)]
+    x = pad_blocks(O.addAwgn(np.concatenate(parts), 0.003, 10), tail=64 * 4096)
+    ev = _stream_events(O, amb, "QPSK", x, _pushes(len(x), 8 * 4096), clip_ok=True)
+    assert any(r.status == 14 for r, _ in ev), [r.status for r, _ in ev]
+    _stream_events(O, amb, "QPSK", x, [len(x)], clip_ok=True)
+
+
+def test_stream_nan_samples(O, amb):
+    """a NaN sample poisons the reference's DC mean for good (app.js:750-755): frames before it decode, the frame it falls
+    into is demodulated with `x || 0` (modem.js:377), nothing is found afterwards - also in later pushes"""
+    x, _ = make_stream(O, "16-QAM", 4, 31)
+    x = x.copy()
+    bad = 16416 + 28431 + 9000               # inside the second data frame
+    x[bad] = np.nan
+    _stream_events(O, amb, "16-QAM", x, [len(x)])
+    _stream_events(O, amb, "16-QAM", x, _pushes(len(x), 4 * 4096))
+    y = x.copy()
+    y[bad + 100000 // 2] = np.nan             # a second one, in a later span of the same push
+    _stream_events(O, amb, "16-QAM", y, [len(y)])
+
+
+def test_stream_slot_table_overflow(O, amb):
+    """every tile of the push is hot (a 256-periodic tone: metric 1 everywhere), far more than the slot table holds
+    (tiles / 8 + 64): the tiles without a slot are evaluated by the walker itself (amb_eval_windows), same events"""
+    n = 96 * 4096
+    t = np.arange(n)
+    tone = (0.3 * np.sin(2 * np.pi * t * 5 / 256.0)).astype(np.float32)
+    x, _ = make_stream(O, "QPSK", 2, 33)
+    sig = np.concatenate([tone, x])
+    _stream_events(O, amb, "QPSK", sig, [len(sig)])
+    _stream_events(O, amb, "QPSK", sig, _pushes(len(sig), 32 * 4096))
+
+
+def test_stream_near_ties_take_the_exact_replay(O, amb):
+    """noise-free frames: the Schmidl-Cox plateau ties to the last ulp, and which sample wins is decided by the reference's own
+    sliding sums (strict '>', app.js:811).  The call is replayed with them (amb_walk_scan_exact): coarse position and metric
+    are the oracle's exactly, for every mode and for pushes of any length"""
+    for mode in MODES:
+        x, _ = make_stream(O, mode, 2, 35, noise=False, lead=1234)
+        want = _stream_events(O, amb, mode, x, [len(x)])
+        _stream_events(O, amb, mode, x, _pushes(len(x), 4096))
+        cfg, mod, rep, _ = MODES[mode]
+        m = amb.Modem(cfg, mod, rep, device=0)
+        try:
+            m.stream_open(1, 4096, len(x))
+            got = m.stream_push(x[None, :], raw=True)
+            exact = 0
+            for (r1, _), (r2, _) in zip(want, got):
+                assert abs(r1.coarse_metric - r2.coarse_metric) <= 1e-10 * r1.coarse_metric, (mode, r1.coarse_metric, r2.coarse_metric)
+                exact += int(r1.coarse_metric == r2.coarse_metric)
+            # a replayed call reports the reference's own value bit for bit (the standard and acoustic plateaus tie; a call without
+            # a near-tie keeps the directly evaluated sums, 1e-13 away)
+            print(mode, "events with a bit-equal coarse metric:", exact, "of", len(want))
+        finally:
+            m.close()
