@@ -49,6 +49,7 @@ EXPORTS = {
     "amb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
     "amb_estimate_frame_samples": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "amb_config_info": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "amb_modem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "amb_preamble_symbol1": (C.c_int, [C.c_int, C.c_void_p]),
     "amb_channel_est_symbol": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "amb_crc32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

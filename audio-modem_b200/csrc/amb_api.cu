@@ -569,6 +569,12 @@ int amb_config_info(int config, int32_t* out8, int32_t* pilots) {
     return AMB_OK;
 }
 
+int amb_modem_info(const amb_modem* m, int32_t* out4) {
+    if (!m || !out4) return AMB_E_INVALID;
+    out4[0] = m->tables.cfg_id; out4[1] = m->tables.mod; out4[2] = m->tables.rep; out4[3] = m->device;
+    return AMB_OK;
+}
+
 int amb_preamble_symbol1(int config, float* out) {
     AmbTables t;
     if (amb_tables_build(&t, config, AMB_MOD_QPSK, 1) != 0) return AMB_E_INVALID;

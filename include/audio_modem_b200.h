@@ -140,6 +140,8 @@ int64_t amb_estimate_frame_samples(int config, int constellation, int64_t payloa
 /* OFDM config fields: out8 = FFT_SIZE, CP_LEN, SYMBOL_LEN, SAMPLE_RATE, SUB_START, SUB_END, nPilots,
  * numDataSubs (modem.js:69-93); pilots receives nPilots bins */
 int amb_config_info(int config, int32_t* out8, int32_t* pilots);
+/* what a handle was created with: out4 = {config, constellation, repetition, device} */
+int amb_modem_info(const amb_modem* m, int32_t* out4);
 /* generatePreambleSymbol1 / generateChannelEstSymbol, modem.js:158-170, :186-200 */
 int amb_preamble_symbol1(int config, float* out_symbol_len);
 int amb_channel_est_symbol(int config, float* out_symbol_len, double* known_re_512);

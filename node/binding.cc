@@ -1,12 +1,12 @@
-// N-API addon over the C-ABI library (include/audio_modem_b200.h).
+// N-API addon over the C-ABI library (include/audio_modem_b200.h): every entry point of SURVEY.md section 8(b).
 //
-// NOT COMPILED OR TESTED IN THIS REPOSITORY: the build image has no Node.js and no node_api.h.
-// It is the reference-side binding a maintainer adds; the tested host side is the Python mirror
-// (audio-modem_b200/modem.py), which makes exactly the same C calls.
+// NOT RUN IN THIS REPOSITORY: the build image has no Node.js.  It is compiled and type-checked against
+// a declaration-only node_api.h (tests/stubs/node_api.h; tests/test_abi.py::test_napi_addon_compiles) and linked against the
+// library; the tested host side is the Python mirror (audio-modem_b200/modem.py), which makes exactly the same C calls.
 //
-// Build (on a machine with Node >= 16 and the CUDA runtime):
-//   g++ -O2 -fPIC -shared -I$(node -p "require('node:path').dirname(process.execPath)+'/../include/node'") \
-//       -I../include binding.cc -L../audio-modem_b200 -laudiomodem_b200 -o audio_modem_b200.node
+// Build (on a machine with Node >= 16 and the CUDA runtime), from this directory:
+//   g++ -O2 -std=c++17 -fPIC -shared -I"$(node -p "require('node:path').resolve(process.execPath, '..', '..', 'include', 'node')")"
+//       -I../include binding.cc -L../audio-modem_b200 -laudiomodem_b200 -Wl,-rpath,'$ORIGIN/../audio-modem_b200' -o audio_modem_b200.node
 #include <node_api.h>
 
 #include <cstring>
@@ -228,6 +228,227 @@ napi_value StreamPush(napi_env env, napi_callback_info info) {
     return arr;
 }
 
+// ---- typed-array helpers -------------------------------------------------------------------------------------------
+bool get_typed(napi_env env, napi_value v, napi_typedarray_type want, const char* what, void** data, size_t* n) {
+    napi_typedarray_type t; napi_value ab; size_t off;
+    if (napi_get_typedarray_info(env, v, &t, n, data, &ab, &off) != napi_ok || t != want) { napi_throw_type_error(env, nullptr, what); return false; }
+    return true;
+}
+template <class T>
+napi_value make_typed(napi_env env, napi_typedarray_type type, size_t n, T** data) {
+    void* p = nullptr; napi_value ab, ta;
+    if (napi_create_arraybuffer(env, n * sizeof(T), &p, &ab) != napi_ok || napi_create_typedarray(env, type, n, ab, 0, &ta) != napi_ok) {
+        napi_throw_error(env, nullptr, "allocation failed"); return nullptr;
+    }
+    *data = static_cast<T*>(p);
+    return ta;
+}
+napi_value fail_lib(napi_env env, amb_modem* m) { napi_throw_error(env, nullptr, amb_last_error(m)); return nullptr; }
+
+// detectPreambleCrossCorr(handle, Float32Array) -> number   (modem.js:235)
+napi_value DetectPreambleCrossCorr(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; const float* x; size_t n;
+    if (!get_modem(env, a[0], &m) || !get_f32(env, a[1], &x, &n)) return nullptr;
+    int64_t idx = -1;
+    if (amb_detect_preamble_xcorr(m, x, (int64_t)n, nullptr, 1, &idx, nullptr, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    napi_value out; napi_create_int64(env, idx, &out);
+    return out;
+}
+
+// preprocessSignal(handle, Float32Array) -> new Float32Array   (modem.js:213)
+napi_value PreprocessSignal(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; const float* x; size_t n;
+    if (!get_modem(env, a[0], &m) || !get_f32(env, a[1], &x, &n)) return nullptr;
+    float* out = nullptr;
+    napi_value ta = make_typed<float>(env, napi_float32_array, n, &out);
+    if (!ta) return nullptr;
+    if (n && amb_preprocess_signal(m, x, (int64_t)n, nullptr, 1, out, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    return ta;
+}
+
+// estimateChannel(handle, Float32Array rx, Float64Array knownRe, Float64Array knownIm) -> [Float64Array(512), Float64Array(512)]   (modem.js:421)
+napi_value EstimateChannel(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value a[4];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; const float* x; size_t n, nr, ni; void *kr, *ki;
+    if (!get_modem(env, a[0], &m) || !get_f32(env, a[1], &x, &n)) return nullptr;
+    if (!get_typed(env, a[2], napi_float64_array, "Float64Array knownRe expected", &kr, &nr) ||
+        !get_typed(env, a[3], napi_float64_array, "Float64Array knownIm expected", &ki, &ni)) return nullptr;
+    int32_t cfg[8];
+    amb_config_info(0, cfg, nullptr);
+    if (nr < (size_t)cfg[0] || ni < (size_t)cfg[0]) { napi_throw_type_error(env, nullptr, "known symbol shorter than FFT_SIZE"); return nullptr; }
+    // the CE symbol row: SYMBOL_LEN samples, zero-padded like the reference's `|| 0` reads (modem.js:425)
+    std::vector<float> row(1024, 0.f);
+    std::memcpy(row.data(), x, (n < row.size() ? n : row.size()) * sizeof(float));
+    double *hr = nullptr, *hi = nullptr;
+    napi_value tr = make_typed<double>(env, napi_float64_array, (size_t)cfg[0], &hr), ti = make_typed<double>(env, napi_float64_array, (size_t)cfg[0], &hi);
+    if (!tr || !ti) return nullptr;
+    if (amb_estimate_channel(m, row.data(), 1, static_cast<const double*>(kr), static_cast<const double*>(ki), hr, hi, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    napi_value arr; napi_create_array_with_length(env, 2, &arr);
+    napi_set_element(env, arr, 0, tr); napi_set_element(env, arr, 1, ti);
+    return arr;
+}
+
+// demodulateOFDM(handle, Float32Array signal, Float64Array chRe, Float64Array chIm) -> Uint8Array of 0/1   (modem.js:365; the wrapper
+// turns it into the reference's number[])
+napi_value DemodulateOFDM(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value a[4];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; const float* x; size_t n, nr, ni; void *cr, *ci;
+    if (!get_modem(env, a[0], &m) || !get_f32(env, a[1], &x, &n)) return nullptr;
+    if (!get_typed(env, a[2], napi_float64_array, "Float64Array channelRe expected", &cr, &nr) ||
+        !get_typed(env, a[3], napi_float64_array, "Float64Array channelIm expected", &ci, &ni)) return nullptr;
+    if (nr < 512 || ni < 512) { napi_throw_type_error(env, nullptr, "channel shorter than FFT_SIZE"); return nullptr; }
+    std::vector<uint8_t> bits(n + 8);                  // at most 4 bits per data subcarrier, fewer subcarriers than samples
+    int64_t nbits = 0;
+    if (n && amb_demodulate(m, x, (int64_t)n, nullptr, 1, static_cast<const double*>(cr), static_cast<const double*>(ci), bits.data(), (int64_t)bits.size(), &nbits,
+                            nullptr, 0, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    uint8_t* out = nullptr;
+    napi_value ta = make_typed<uint8_t>(env, napi_uint8_array, (size_t)nbits, &out);
+    if (!ta) return nullptr;
+    std::memcpy(out, bits.data(), (size_t)nbits);
+    return ta;
+}
+
+// modulateOFDM(handle, Uint8Array bits) -> {samples: Float32Array(numSymbols * SYMBOL_LEN), numSymbols, bitsPerSymbol, paddedLength}
+// (modem.js:322-362; the wrapper cuts `samples` into per-symbol arrays and pads the caller's array in place like modem.js:329)
+napi_value ModulateOFDM(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; void* b; size_t nb;
+    if (!get_modem(env, a[0], &m) || !get_typed(env, a[1], napi_uint8_array, "Uint8Array bits expected", &b, &nb)) return nullptr;
+    int32_t out3[3] = {0, 0, 0};
+    if (amb_modulate(m, nullptr, (int64_t)nb, (int64_t)nb, 0, nullptr, 0, out3, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    int32_t who[4], cfg[8];
+    amb_modem_info(m, who);
+    amb_config_info(who[0], cfg, nullptr);
+    const int64_t slen = cfg[2];                                          // SYMBOL_LEN of the handle's config
+    std::vector<uint8_t> bits((size_t)out3[2] + 1, 0);
+    std::memcpy(bits.data(), b, nb);
+    float* samples = nullptr;
+    napi_value ta = make_typed<float>(env, napi_float32_array, (size_t)out3[0] * (size_t)slen, &samples);
+    if (!ta) return nullptr;
+    if (out3[0] > 0 && amb_modulate(m, bits.data(), (int64_t)bits.size(), (int64_t)nb, 1, samples, (int64_t)out3[0] * slen, out3, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    napi_value o; napi_create_object(env, &o);
+    napi_set_named_property(env, o, "samples", ta);
+    set_num(env, o, "numSymbols", out3[0]); set_num(env, o, "bitsPerSymbol", out3[1]); set_num(env, o, "paddedLength", out3[2]);
+    return o;
+}
+
+// crc32(handle, Uint8Array) -> number   (modem.js:453)
+napi_value Crc32(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; void* d; size_t n;
+    if (!get_modem(env, a[0], &m) || !get_typed(env, a[1], napi_uint8_array, "Uint8Array expected", &d, &n)) return nullptr;
+    uint32_t crc = 0;
+    const int64_t len = (int64_t)n;
+    const uint8_t dummy = 0;
+    if (amb_crc32(m, n ? static_cast<const uint8_t*>(d) : &dummy, (int64_t)(n ? n : 1), &len, 1, &crc, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    napi_value out; napi_create_uint32(env, crc, &out);
+    return out;
+}
+
+// estimateFrameSamples(config, constellation, payloadBytes, repetition) -> number   (modem.js:863; no handle needed)
+napi_value EstimateFrameSamples(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value a[4];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    int32_t cfg = 0, mod = 1, rep = 1; int64_t payload = 0;
+    napi_get_value_int32(env, a[0], &cfg); napi_get_value_int32(env, a[1], &mod); napi_get_value_int64(env, a[2], &payload); napi_get_value_int32(env, a[3], &rep);
+    napi_value out; napi_create_int64(env, amb_estimate_frame_samples(cfg, mod, payload, rep), &out);
+    return out;
+}
+
+// buildMetadataFrame(handle, totalChunks, totalFileSize, chunkSize, fileName) -> Float32Array   (modem.js:758)
+napi_value BuildMetadataFrame(napi_env env, napi_callback_info info) {
+    size_t argc = 5; napi_value a[5];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; if (!get_modem(env, a[0], &m)) return nullptr;
+    int32_t tc = 0, fs = 0, cs = 0;
+    napi_get_value_int32(env, a[1], &tc); napi_get_value_int32(env, a[2], &fs); napi_get_value_int32(env, a[3], &cs);
+    char name[768]; size_t name_len = 0;
+    NAPI_CALL(env, napi_get_value_string_utf8(env, a[4], name, sizeof(name), &name_len));
+    if (name_len > 255) name_len = 255;                                   // modem.js:669
+    const int64_t len = amb_chunk_frame_samples(m, 1 + 4 + 4 + 2 + 1 + (int64_t)name_len + 4, 1);
+    float* out = nullptr;
+    napi_value ta = make_typed<float>(env, napi_float32_array, (size_t)len, &out);
+    if (!ta) return nullptr;
+    if (amb_build_metadata_frame(m, tc, fs, cs, reinterpret_cast<const uint8_t*>(name), (int)name_len, out, 0.0, 0, 0, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    return ta;
+}
+
+// buildDataChunkFrame(handle, Uint8Array chunkData, seqNum) -> Float32Array   (modem.js:763)
+napi_value BuildDataChunkFrame(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; void* d; size_t n;
+    if (!get_modem(env, a[0], &m) || !get_typed(env, a[1], napi_uint8_array, "Uint8Array chunkData expected", &d, &n)) return nullptr;
+    int32_t seq = 0; napi_get_value_int32(env, a[2], &seq);
+    const int64_t len = amb_chunk_frame_samples(m, (int64_t)n + 11, 0);
+    float* out = nullptr;
+    napi_value ta = make_typed<float>(env, napi_float32_array, (size_t)len, &out);
+    if (!ta) return nullptr;
+    if (amb_build_data_chunk_frames(m, static_cast<const uint8_t*>(d), (int64_t)n, (int)n, 1, seq, 0, out, len, 0.0, 0, 0, nullptr, AMB_MEM_HOST) != AMB_OK) return fail_lib(env, m);
+    return ta;
+}
+
+// generatePreambleSymbol1(config) -> Float32Array; generateChannelEstSymbol(config) -> {samples, knownRe, knownIm}   (modem.js:158, :186)
+napi_value GeneratePreambleSymbol1(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    int32_t cfg = 0; napi_get_value_int32(env, a[0], &cfg);
+    int32_t ci[8];
+    if (amb_config_info(cfg, ci, nullptr) != AMB_OK) { napi_throw_error(env, nullptr, "bad config"); return nullptr; }
+    float* out = nullptr;
+    napi_value ta = make_typed<float>(env, napi_float32_array, (size_t)ci[2], &out);
+    if (!ta) return nullptr;
+    amb_preamble_symbol1(cfg, out);
+    return ta;
+}
+napi_value GenerateChannelEstSymbol(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    int32_t cfg = 0; napi_get_value_int32(env, a[0], &cfg);
+    int32_t ci[8];
+    if (amb_config_info(cfg, ci, nullptr) != AMB_OK) { napi_throw_error(env, nullptr, "bad config"); return nullptr; }
+    float* s = nullptr; double *kr = nullptr, *ki = nullptr;
+    napi_value ts = make_typed<float>(env, napi_float32_array, (size_t)ci[2], &s), tr = make_typed<double>(env, napi_float64_array, (size_t)ci[0], &kr),
+               ti = make_typed<double>(env, napi_float64_array, (size_t)ci[0], &ki);
+    if (!ts || !tr || !ti) return nullptr;
+    amb_channel_est_symbol(cfg, s, kr);
+    std::memset(ki, 0, (size_t)ci[0] * sizeof(double));
+    napi_value o; napi_create_object(env, &o);
+    napi_set_named_property(env, o, "samples", ts); napi_set_named_property(env, o, "knownRe", tr); napi_set_named_property(env, o, "knownIm", ti);
+    return o;
+}
+
+// streamCounters(handle[, stream]) -> {framesDecoded, frameErrors, falsePositives, receivedCount, crcErrors, duplicates, metaReceived, samplesWritten}
+napi_value StreamCounters(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; if (!get_modem(env, a[0], &m)) return nullptr;
+    int32_t stream = -1;
+    if (argc > 1) napi_get_value_int32(env, a[1], &stream);
+    int64_t c[8];
+    if (amb_stream_counters(m, stream, c) != AMB_OK) return fail_lib(env, m);
+    static const char* keys[8] = {"framesDecoded", "frameErrors", "falsePositives", "receivedCount", "crcErrors", "duplicates", "metaReceived", "samplesWritten"};
+    napi_value o; napi_create_object(env, &o);
+    for (int k = 0; k < 8; k++) set_num(env, o, keys[k], (double)c[k]);
+    return o;
+}
+
+napi_value StreamClose(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1];
+    NAPI_CALL(env, napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    amb_modem* m; if (!get_modem(env, a[0], &m)) return nullptr;
+    if (amb_stream_close(m) != AMB_OK) return fail_lib(env, m);
+    return nullptr;
+}
+
 napi_value Init(napi_env env, napi_value exports) {
     napi_property_descriptor d[] = {
         {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -239,6 +460,19 @@ napi_value Init(napi_env env, napi_value exports) {
         {"buildTransmitSignal", nullptr, BuildTransmitSignal, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamOpen", nullptr, StreamOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"streamPush", nullptr, StreamPush, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"streamCounters", nullptr, StreamCounters, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"streamClose", nullptr, StreamClose, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"detectPreambleCrossCorr", nullptr, DetectPreambleCrossCorr, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"preprocessSignal", nullptr, PreprocessSignal, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"estimateChannel", nullptr, EstimateChannel, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"demodulateOFDM", nullptr, DemodulateOFDM, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"modulateOFDM", nullptr, ModulateOFDM, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"crc32", nullptr, Crc32, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"estimateFrameSamples", nullptr, EstimateFrameSamples, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"buildMetadataFrame", nullptr, BuildMetadataFrame, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"buildDataChunkFrame", nullptr, BuildDataChunkFrame, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"generatePreambleSymbol1", nullptr, GeneratePreambleSymbol1, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"generateChannelEstSymbol", nullptr, GenerateChannelEstSymbol, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(d) / sizeof(d[0]), d);
     return exports;

@@ -77,3 +77,48 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "modem_oracle" not in text, f
+
+
+# ---------------------------------------------------------------------------------------------- the boundary from C and from the N-API addon
+BOUNDARY_JS = ["setOFDMConfig", "detectPreamble", "detectPreambleCrossCorr", "preprocessSignal", "estimateChannel", "demodulateOFDM", "modulateOFDM",
+               "crc32", "decodeReceivedSignal", "decodeChunkFrame", "estimateFrameSamples", "buildTransmitSignal", "buildMetadataFrame",
+               "buildDataChunkFrame", "StreamingReceiver"]      # SURVEY.md section 8(b), "Signatures the drop-in keeps"
+
+
+def build_cabi_smoke(amb, tmp_path):
+    """tests/cabi_smoke.c compiled as strict C99 against the public header and linked to the library"""
+    exe = str(tmp_path / "cabi_smoke")
+    lib_dir = os.path.dirname(amb._lib.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi_smoke.c"), "-L", lib_dir, "-laudiomodem_b200", "-Wl,-rpath," + lib_dir, "-o", exe])
+    return exe
+
+
+def test_header_is_c_and_the_library_links_from_c(amb, tmp_path):
+    """the public header compiles as C99 (no C++ in the boundary) and a C program linked against the library runs its host-side
+    entry points; without a GPU amb_create refuses (AMB_E_NODEVICE) instead of falling back"""
+    exe = build_cabi_smoke(amb, tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "host side ok" in out.stdout
+
+
+def test_napi_addon_compiles_and_covers_the_boundary(amb, tmp_path):
+    """node/binding.cc is compiled (-Wall -Wextra -Werror) against a declaration-only node_api.h (tests/stubs) and linked against
+    the library: every amb_* symbol it calls exists with the signature the header declares, and it registers every entry point
+    the JS wrapper uses.  (Node.js itself is not in the image: the addon is never loaded here.)"""
+    obj, so = str(tmp_path / "binding.o"), str(tmp_path / "audio_modem_b200.node")
+    lib_dir = os.path.dirname(amb._lib.lib_path())
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-Wno-comment", "-fPIC", "-c", "-I", os.path.join(ROOT, "tests", "stubs"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "node", "binding.cc"), "-o", obj])
+    subprocess.check_call(["g++", "-shared", obj, "-L", lib_dir, "-laudiomodem_b200", "-o", so])
+    undefined = subprocess.run(["nm", "-u", obj], capture_output=True, text=True).stdout
+    called = sorted(set(re.findall(r"\b(amb_[a-z0-9_]+)\b", undefined)))
+    assert len(called) >= 20 and set(called) <= set(declared_functions()), set(called) - set(declared_functions())
+    src = open(os.path.join(ROOT, "node", "binding.cc")).read()
+    registered = set(re.findall(r'\{"([A-Za-z0-9]+)", nullptr, ', src))
+    js = open(os.path.join(ROOT, "node", "modem_b200.js")).read()
+    used = set(re.findall(r"addon\.([A-Za-z0-9]+)\(", js))
+    assert used <= registered, used - registered
+    exported = set(re.findall(r"^  ([A-Za-z0-9]+)(?:\(|:)", js, flags=re.M))
+    assert set(BOUNDARY_JS) <= exported, set(BOUNDARY_JS) - exported

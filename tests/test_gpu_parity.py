@@ -2,6 +2,8 @@
 same seeded float32 inputs.  Bars (BASELINE.json north_star): preamble indices exact, decoded bytes bit-exact, CRC
 verdicts identical, constellation points and correlation metrics within 1e-4 relative (the float64-faithful
 device path is in fact held to 1e-9 or exact equality here)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -643,3 +645,18 @@ def test_stream_near_ties_take_the_exact_replay(O, amb):
             print(mode, "events with a bit-equal coarse metric:", exact, "of", len(want))
         finally:
             m.close()
+
+
+def test_c_abi_from_compiled_c(amb, tmp_path):
+    """tests/cabi_smoke.c (strict C99, linked against the library) does create -> buildTransmitSignal -> decodeReceivedSignal ->
+    preprocess + detectPreamble -> stream push -> destroy on the GPU and checks the decoded bytes itself"""
+    import subprocess
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi import build_cabi_smoke
+
+    exe = build_cabi_smoke(amb, tmp_path)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "round trip on the GPU ok" in out.stdout
