@@ -214,3 +214,129 @@ def test_pcm16_push_equals_float_push(O, amb, mode):
             assert m.stream_counters()["samplesWritten"] == 3 * n
         finally:
             m.close()
+
+
+# ---------------------------------------------------------------------------------------------- SURVEY.md section 8(d) sizes
+def _pool_map(fn, items, threads=8):
+    """the oracle's C++ runs under ctypes with the GIL released: a thread pool keeps its replays to seconds"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(fn, items))
+
+
+def test_c2_chunk_stream_2000_frames(O, amb):
+    """config 2 at the parity size of SURVEY 8(d): the first 2,000 frames of the 16-QAM stream (57 M samples, AWGN 25 dB), one
+    push of 1,000 frames and pushes of 128 blocks - every event, every decoded byte and every counter equal to the oracle's"""
+    cfg, mod, rep, chunk = MODES["16-QAM"]
+    n_frames = 2000
+    parts = [O.buildMetadataFrame(cfg, n_frames, n_frames * chunk, chunk, "c2.bin", mod, rep)]
+    frames = _pool_map(lambda i: O.buildDataChunkFrame(cfg, O.synthBytes(2, i, chunk), i, mod, rep), range(n_frames))
+    x = np.concatenate(parts + frames)
+    p = O.power(frames[0][2205:2205 + 25344])
+    x = pad_blocks(O.addAwgnCtr(x, (p / 10 ** 2.5) ** 0.5, 3))
+    n = len(x)
+    half = (n // 2) // 4096 * 4096
+    pushes = [half] + [128 * 4096] * ((n - half) // (128 * 4096)) + ([(n - half) % (128 * 4096)] if (n - half) % (128 * 4096) else [])
+    ev = _events_equal(O, amb, "16-QAM", x, pushes)
+    ok = [r for r, _ in ev if r.status == 0 and r.frame_type == 0xFF and r.crc_valid]
+    assert len(ev) == n_frames + 1 and len(ok) >= n_frames - 8
+    assert sorted(r.seq_num for r in ok) == sorted(set(r.seq_num for r in ok))
+
+
+@pytest.mark.parametrize("mode", ["BPSK-ACOUSTIC", "BPSK-REPEAT"])
+def test_c3_recordings_batch_1000(O, amb, mode):
+    """config 3 at a tenth of its size: 500 recordings per mode through multipath, CFO (10 % at +-1 Hz) and AWGN 20 dB, one batch;
+    preambleIdx, verdict, every result field and the decoded bytes of every recording equal to the oracle's"""
+    cfg, mod, rep, _ = MODES[mode]
+    rng = np.random.default_rng(12)
+    dfs = [float(rng.choice([-1.0, 1.0])) if i % 10 == 3 else float(rng.uniform(-0.05, 0.05)) for i in range(500)]
+
+    def make(i):
+        tx = O.buildTransmitSignal(cfg, O.randomBytes(3000 + i, 512), mod, "rec", rep)
+        y = O.cfo(O.multipath(tx, [0, 23, 57], [1.0, 0.5, 0.25]), dfs[i])
+        return O.addAwgn(y, float(np.sqrt(O.power(tx[22050:][:20000]) / 100.0)), 3000 + i)
+
+    recs = _pool_map(make, range(500))
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        got = m.decode_received_signals(recs, raw=True)
+    finally:
+        m.close()
+    want = _pool_map(lambda r: O.decodeReceivedSignal(cfg, r, mod, rep, raw=True), recs)
+    ok = 0
+    for i, ((r1, b1), (r2, b2)) in enumerate(zip(want, got)):
+        assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (mode, i, results_equal(r1, b1, r2, b2, metric_tol=1e-9))
+        ok += int(r1.status == 0 and r1.crc_valid)
+    assert ok >= 300
+
+
+def test_c4_long_capture_20m_samples(O, amb):
+    """config 4 at an eighth of its length: a 21 M-sample narrowband capture (8 minutes) over a -30 dBFS noise floor with a
+    metadata frame and four data frames far apart, as one push and as pushes of 1,024 blocks: the long idle stretches make the
+    app.js:826 defect random-walk (false positives, frame errors) - every event and counter, falsePositives and frameErrors
+    included, equal to the oracle's"""
+    cfg, mod, rep, chunk = MODES["BPSK-NARROW"]
+    n = 5120 * 4096
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal(n) * 10 ** (-30 / 20)).astype(np.float32)
+    pos = 3 * 44100
+    meta = O.buildMetadataFrame(cfg, 4, 4 * chunk, chunk, "cap.bin", mod, rep)
+    x[pos:pos + len(meta)] += meta
+    pos += len(meta)
+    for i, gap_s in enumerate((12, 47, 95, 140)):
+        pos += gap_s * 44100
+        f = O.buildDataChunkFrame(cfg, O.randomBytes(700 + i, chunk), i, mod, rep)
+        x[pos:pos + len(f)] += f
+        pos += len(f)
+    assert pos < n - 8 * 4096
+    ev = _events_equal(O, amb, "BPSK-NARROW", x, [n])
+    assert sum(1 for r, _ in ev if r.status == 0 and r.crc_valid) >= 4
+    _events_equal(O, amb, "BPSK-NARROW", x, [1024 * 4096] * 5)
+
+
+def test_c5_many_streams_1024(O, amb):
+    """config 5 at 1/64 of its stream count: 1,024 independent 16-QAM streams (metadata + 8 chunks each, own payload and noise)
+    built on the device and pushed as [n_streams][8 x 4096] sections; 64 of them replayed by the oracle event for event, all of
+    them checked through the counters"""
+    import torch
+
+    cfg, mod, rep, chunk = MODES["16-QAM"]
+    ns, K = 1024, 8
+    dev = torch.device("cuda", 0)
+    m = amb.Modem(cfg, mod, rep, device=0)
+    try:
+        meta_len = m.chunk_frame_samples(1 + 4 + 4 + 2 + 1 + len("s.bin") + 4, True)
+        flen = m.chunk_frame_samples(chunk + 11, False)
+        push = 8 * 4096
+        n = (meta_len + K * flen + 8192 + push - 1) // push * push
+        x = torch.zeros((ns, n), dtype=torch.float32, device=dev)
+        clean = torch.zeros((1, flen), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        m.build_data_chunk_frames(n=1, data_len=chunk, seq0=0, synth_seed=2, out=clean)
+        m.synchronize()
+        sigma = float((clean[0, 2205:flen - 882].double().pow(2).mean() / 10 ** 2.5).sqrt())
+        for s in range(ns):
+            m.build_metadata_frame(K, K * chunk, chunk, "s.bin", noise_sigma=sigma, noise_seed=5000 + s, noise_g0=0, out=x[s, :meta_len])
+            m.build_data_chunk_frames(n=K, data_len=chunk, seq0=0, synth_seed=9000 + s, noise_sigma=sigma, noise_seed=5000 + s, noise_g0=meta_len,
+                                      out=x[s, meta_len:meta_len + K * flen].view(K, flen))
+        m.synchronize()
+        m.stream_open(ns, 4096, push)
+        got = [[] for _ in range(ns)]
+        for p0 in range(0, n, push):
+            for r, b in m.stream_push(x[:, p0:p0 + push], raw=True):
+                got[r.stream].append((r, b))
+        c = m.stream_counters()
+        assert c["metaReceived"] == ns and c["framesDecoded"] == ns * (K + 1) and c["frameErrors"] == 0
+        assert c["receivedCount"] + c["crcErrors"] == ns * K
+        pick = list(range(0, ns, 16))
+        host = x[pick].cpu().numpy()
+        wants = _pool_map(lambda i: O.StreamingReceiver(cfg, mod, rep).push(host[i], 4096, raw=True), range(len(pick)))
+        for i, s in enumerate(pick):
+            g = sorted(got[s], key=lambda t: t[0].preamble_idx)
+            assert len(g) == len(wants[i]) == K + 1
+            for (r1, b1), (r2, b2) in zip(wants[i], g):
+                assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (s, r1.preamble_idx)
+        m.stream_close()
+    finally:
+        m.close()
