@@ -1238,7 +1238,12 @@ static int stream_push_any(amb_modem* m, const void* xv, int es, int64_t x_strid
         int got = 0;
         const int rc = push_core(m, raw + sec_off[k] * es, m->max_push, sec_len[k], results ? results + (total < max_results ? total : max_results) : nullptr, room, &got,
                                  bytes_out ? bytes_out + (size_t)(total < max_results ? total : max_results) * bytes_stride : nullptr, bytes_stride, results_mem);
-        if (rc != AMB_OK && rc != AMB_E_OVERFLOW) return rc;
+        if (rc != AMB_OK && rc != AMB_E_OVERFLOW) {
+            // the copies of the later sections still read the caller's buffer: let them finish before handing it back
+            cudaStreamSynchronize(m->copy_stream);
+            *n_results = total;
+            return rc;
+        }
         if (rc == AMB_E_OVERFLOW) rc_all = AMB_E_OVERFLOW;
         total += got;
     }

@@ -54,3 +54,31 @@ def max_over_ranks(value, group=None, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that page-locked host buffers allocated
+    afterwards (amb_host_alloc) are node-local and the host->device copies of several ranks do not cross the socket
+    interconnect.  Linux only; returns {"node": n, "cpus": count} or None when the topology cannot be read (nothing changed)."""
+    import os
+    import subprocess
+
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+        dom, rest = out.split(":", 1)
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception:
+        return None

@@ -276,6 +276,10 @@ class Ctx:
         import torch
 
         self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        # page-locked host buffers on the GPU's own NUMA node (the end-to-end legs of several ranks share the host's memory)
+        import audio_modem_b200 as amb
+
+        self.numa = amb.shard.bind_to_gpu_numa_node(local_rank) if os.environ.get("AMB_NUMA_BIND", "1") != "0" else None
         torch.cuda.set_device(local_rank)
         self.dev = torch.device("cuda", local_rank)
         self.dist = None
@@ -1006,6 +1010,7 @@ def run_b200(args, rank, world, local_rank, workloads):
         clk = clocks.stop()
         clk["window"] = "warm-up + timed steps + profiling pass + end-to-end legs (the same workload throughout)"
         line["clocks"] = clk
+        line["host"] = {"numa_binding_rank0": ctx.numa, "cpu_count": os.cpu_count()}
         if wl == "c2" and world == 1 and args.workload is None and not args.no_shard_probe:
             # the N = 1 point of the c5 scaling curve (the N > 1 default workload), measured here so that it sits in the N = 1 record
             sc = ClockSampler(local_rank)
