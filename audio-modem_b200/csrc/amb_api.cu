@@ -65,7 +65,7 @@ struct amb_modem {
     size_t prof_used = 0;
     // scratch
     DevBuf in_a, in_b, in_c, in_lens, out_a, out_b, out_c, out_res, out_bytes;
-    DevBuf jobs, idx, p_scratch, xf, psum, pmin, pmax, norm, metric, tile_max, amb, tie_rng, cidx, cbest, tx_pay, tx_out, tx_copy;
+    DevBuf jobs, idx, p_scratch, xf, psum, pmin, pmax, norm, metric, tile_max, tile_max32, amb, tie_rng, cidx, cbest, tx_pay, tx_out, tx_copy;
     std::vector<PendingCopy> pending;
     // streaming
     bool open = false;
@@ -267,7 +267,12 @@ int run_detect(amb_modem* m, const float* d_y, int64_t stride, const int64_t* d_
     const int tiles = (int)((max_len + AMB_TILE - 1) / AMB_TILE) > 0 ? (int)((max_len + AMB_TILE - 1) / AMB_TILE) : 1;
     CK(m->tile_max.ensure((size_t)n * tiles * 8));
     CK(m->amb.ensure((size_t)n * 4)); CK(m->tie_rng.ensure((size_t)n * 16)); CK(m->cidx.ensure((size_t)n * 8)); CK(m->cbest.ensure((size_t)n * 8));
-    LAUNCH("k_metric", k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, tiles, m->tile_max.as<double>()));
+    // float32 screening first (AMB_METRIC_SCREEN=0 switches it off: comparison runs), then the exact sums on the tiles it leaves
+    static const bool screen = !(std::getenv("AMB_METRIC_SCREEN") && std::getenv("AMB_METRIC_SCREEN")[0] == '0');
+    CK(m->tile_max32.ensure((size_t)n * tiles * 4));
+    if (screen) LAUNCH("k_metric_screen", k_metric_screen<<<n * tiles, 256, 0, m->stream>>>(d_y, stride, d_lens, stride, 0.0099f, tiles, m->tile_max32.as<float>()));
+    LAUNCH("k_metric", k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, tiles, m->tile_max.as<double>(),
+                                                                                screen ? m->tile_max32.as<float>() : nullptr));
     LAUNCH("k_argmax", k_argmax<<<n, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
                                       m->cbest.as<double>(), m->amb.as<int>(), m->tie_rng.as<int64_t>()));
     LAUNCH("k_replay", k_replay<<<blocks_for(n, 4), 128, 0, m->stream>>>(d_y, stride, d_lens, stride, n, 0.01, m->amb.as<int>(), m->tie_rng.as<int64_t>(),
@@ -408,7 +413,7 @@ void amb_destroy(amb_modem* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     DevBuf* all[] = {&m->in_a, &m->in_b, &m->in_c, &m->in_lens, &m->out_a, &m->out_b, &m->out_c, &m->out_res, &m->out_bytes, &m->jobs, &m->idx, &m->p_scratch,
-                     &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->amb, &m->tie_rng, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
+                     &m->xf, &m->psum, &m->pmin, &m->pmax, &m->norm, &m->metric, &m->tile_max, &m->tile_max32, &m->amb, &m->tie_rng, &m->cidx, &m->cbest, &m->tx_pay, &m->tx_out, &m->tx_copy, &m->raw, &m->cleaned,
                      &m->sums, &m->dc_next, &m->states, &m->recs, &m->nrec, &m->job_off, &m->total, &m->keep, &m->keep_off, &m->redo, &m->n_redo,
                      &m->s_res, &m->s_bytes, &m->s_sel, &m->g_res, &m->g_bytes, &m->ctmp, &m->nan_pos,
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,

@@ -1438,8 +1438,80 @@ __device__ __forceinline__ bool amb_tile_metric(const AmbTileScratch& w, int dl,
     return true;
 }
 
+// float32 screening pass of the batch detector: an approximate per-tile maximum of the metric (gate slightly relaxed), from
+// which k_metric picks the tiles that can hold the maximum - the float64 prefix machinery then runs on a few tiles per
+// recording instead of all of them.  One warp per 256 windows (768 samples), everything in registers: lane l owns the 8
+// windows 8 l .. 8 l + 7, the warp scans give the prefixes of x^2 and x[i] x[i+256] at its first window (the scheme of
+// amb_window_sums_blocks in float32).  |value - exact| is ~1e-5 relative for the windows that matter (metric > 0.5, no
+// cancellation in P); the selection margin is 2e-3.
+__global__ void __launch_bounds__(256) k_metric_screen(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
+                                                        int64_t n_default, float min_energy, int tiles, float* __restrict__ tile_max32) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    AMB_SPLIT_BID(tiles, r, tile)
+    const int64_t n = lens ? lens[r] : n_default;
+    const int64_t q0 = (int64_t)tile * AMB_TILE;
+    __shared__ float red[8];
+    float best = -1.f;
+    const float* src = y + (int64_t)r * stride;
+    if (q0 - AMB_HALO + 1 + 2 * AMB_HALF <= n) {
+        for (int sub = warp; sub < AMB_TILE / 256; sub += 8) {
+            const int64_t d0 = q0 - 511 + 256 * sub;                 // first window of the sub-tile (= 1 mod 4: one float past a 16-byte boundary)
+            if (d0 + 2 * AMB_HALF > n) break;
+            float x[3][8];
+            const int64_t g0 = d0 + 8 * lane;
+            if (d0 >= 1 && d0 + 768 + 8 <= n && ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                const float* pa = src + (g0 - 1);
+#pragma unroll
+                for (int seg = 0; seg < 3; seg++) {
+                    const float4 u = *reinterpret_cast<const float4*>(pa + 256 * seg), v = *reinterpret_cast<const float4*>(pa + 256 * seg + 4);
+                    x[seg][0] = u.y; x[seg][1] = u.z; x[seg][2] = u.w; x[seg][3] = v.x; x[seg][4] = v.y; x[seg][5] = v.z; x[seg][6] = v.w;
+                    x[seg][7] = pa[256 * seg + 8];
+                }
+            } else {
+#pragma unroll
+                for (int seg = 0; seg < 3; seg++)
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { const int64_t a = g0 + 256 * seg + k; x[seg][k] = (a >= 0 && a < n) ? src[a] : 0.f; }
+            }
+            float q0s = 0.f, q1s = 0.f, q2s = 0.f, t0s = 0.f, t1s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                q0s = fmaf(x[0][k], x[0][k], q0s); q1s = fmaf(x[1][k], x[1][k], q1s); q2s = fmaf(x[2][k], x[2][k], q2s);
+                t0s = fmaf(x[0][k], x[1][k], t0s); t1s = fmaf(x[1][k], x[2][k], t1s);
+            }
+            float e0 = q0s, e1 = q1s, e2 = q2s, f0 = t0s, f1 = t1s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float u0 = __shfl_up_sync(0xffffffffu, e0, o), u1 = __shfl_up_sync(0xffffffffu, e1, o), u2 = __shfl_up_sync(0xffffffffu, e2, o);
+                const float v0 = __shfl_up_sync(0xffffffffu, f0, o), v1 = __shfl_up_sync(0xffffffffu, f1, o);
+                if (lane >= o) { e0 += u0; e1 += u1; e2 += u2; f0 += v0; f1 += v1; }
+            }
+            const float Q0 = __shfl_sync(0xffffffffu, e0, 31), Q1 = __shfl_sync(0xffffffffu, e1, 31), T0 = __shfl_sync(0xffffffffu, f0, 31);
+            // window sums at the lane's first window as (suffix of the first segment) + (prefix of the next): no large prefix is
+            // ever subtracted from another
+            float A = (Q0 - (e0 - q0s)) + (e1 - q1s), B = (Q1 - (e1 - q1s)) + (e2 - q2s), P = (T0 - (f0 - t0s)) + (f1 - t1s);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int64_t d = g0 + k;
+                if (d >= 0 && d + 2 * AMB_HALF <= n && A > min_energy && B > min_energy) best = fmaxf(best, __fdividef(P * P, A * B));
+                A += x[1][k] * x[1][k] - x[0][k] * x[0][k];
+                B += x[2][k] * x[2][k] - x[1][k] * x[1][k];
+                P += x[1][k] * x[2][k] - x[0][k] * x[1][k];
+            }
+        }
+    }
+    best = warp_maxf(best);
+    if (lane == 0) red[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int wv = 1; wv < 8; wv++) best = fmaxf(best, red[wv]);
+        tile_max32[(int64_t)r * tiles + tile] = best;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
-                                                 int64_t n_default, double min_energy, int tiles, double* __restrict__ tile_max) {
+                                                 int64_t n_default, double min_energy, int tiles, double* __restrict__ tile_max,
+                                                 const float* __restrict__ tile_max32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AmbTileScratch w = amb_tile_scratch(smem_raw);
     const int tid = threadIdx.x;
@@ -1447,6 +1519,19 @@ __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int
     const int64_t n = lens ? lens[r] : n_default;
     const int64_t q0 = (int64_t)tile * AMB_TILE;
     if (q0 - AMB_HALO + 1 + 2 * AMB_HALF > n) { if (tid == 0) tile_max[(int64_t)r * tiles + tile] = -1.0; return; }      // no window of this tile lies inside the recording
+    if (tile_max32) {
+        // only the tiles whose screening maximum is within the margin of the recording's can hold the maximum (or a tie with it)
+        __shared__ float sred[8];
+        float b32 = -1.f;
+        for (int t = tid; t < tiles; t += 256) b32 = fmaxf(b32, tile_max32[(int64_t)r * tiles + t]);
+        b32 = warp_maxf(b32);
+        if ((tid & 31) == 0) sred[tid >> 5] = b32;
+        __syncthreads();
+        for (int wv = 0; wv < 8; wv++) b32 = fmaxf(b32, sred[wv]);
+        const float mine = tile_max32[(int64_t)r * tiles + tile];
+        if (!(mine >= b32 * (1.f - 2e-3f) - 1e-6f)) { if (tid == 0) tile_max[(int64_t)r * tiles + tile] = -1.0; return; }
+        __syncthreads();
+    }
     amb_tile_prefix(w, y + (int64_t)r * stride, n, q0);
     double best = -1.0;
     for (int jj = 0; jj < AMB_TILE / 256; jj++) {

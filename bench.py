@@ -7,7 +7,7 @@ on its five configs.
       (EMA DC removal, Schmidl-Cox scan, refine, collect, demodulate, CRC-32; app.js:749-981).  One step = one push of
       `--frames-per-step` whole frames of one stream.
   --workload c5 (default at --gpus N > 1): many concurrent 16-QAM streams, each metadata + 8 data frames as in c2,
-      pushed as [n_streams][8 x 4096] sections.  8,192 streams per GPU (65,536 over the 8 GPUs of a box): weak scaling,
+      pushed as [n_streams][14 x 4096] sections.  8,192 streams per GPU (65,536 over the 8 GPUs of a box): weak scaling,
       streams sharded by rank (audio_modem_b200.shard), no collective on the hot path.  One step = one push of all the
       rank's streams; the resident signal is periodic (the streams repeat their 9 frames).
   --workload c4: narrowband long-capture search — one 1-hour 44.1 kHz capture (158.76 M samples) with a metadata frame
@@ -53,7 +53,7 @@ UNIT = "Msamples/s"
 DTYPE = "f32+f64-guard"  # float32 symbol pipeline with a float64 margin guard and float64-faithful fallback; float64 window sums
 C5_STREAMS_PER_GPU = 8192
 C5_K = 8
-C5_PUSH_BLOCKS = 8
+C5_PUSH_BLOCKS = int(os.environ.get("AMB_C5_PUSH_BLOCKS", "14"))   # 14 x 4096 = 57,344 samples per stream and push: the 8 frames of a stream (227,448 samples) are 4 pushes
 MODES = {"16-QAM": ("standard", "QAM16", 1, 4096), "QPSK": ("standard", "QPSK", 1, 2048), "BPSK-ACOUSTIC": ("acoustic", "BPSK", 1, 512),
          "BPSK-REPEAT": ("acoustic", "BPSK", 3, 512), "BPSK-NARROW": ("narrowband", "BPSK", 3, 512)}
 WORKLOAD_TEXT = {
@@ -61,7 +61,7 @@ WORKLOAD_TEXT = {
     "c2": "C2: 16-QAM chunked stream, 4 KB chunks as 28,431-sample OFDM frames, AWGN 25 dB, streaming preamble scan + CRC-32",
     "c3": "C3: BPSK and BPSK-repeat acoustic recordings over multipath + CFO + AWGN 20 dB, batched decodeReceivedSignal",
     "c4": "C4: narrowband long-capture search, 1-hour 44.1 kHz capture with sparse frames over a -30 dBFS noise floor, one push",
-    "c5": "C5: concurrent 16-QAM streams (metadata + 8 chunk frames each, AWGN 25 dB), pushed as [n_streams][8 x 4096] sections",
+    "c5": "C5: concurrent 16-QAM streams (metadata + 8 chunk frames each, AWGN 25 dB), pushed as [n_streams][14 x 4096] sections",
 }
 
 
