@@ -70,6 +70,7 @@ struct amb_modem {
     // streaming
     bool open = false;
     int walk_ctas = 148 * 16;         // grid of k_link_walk (set from the occupancy at create)
+    int front_ctas_per_sm = 6;        // resident CTAs of k_front<.., 128> per SM (occupancy at create): its spans are sized for one wave
     bool push_pcm16 = false;          // input format of the push in progress
     int n_streams = 0;
     int64_t block_len = 0, max_push = 0, hist = 0, stride = 0, base_g = 0, written = 0, sum_stride = 0, ring_cap = 0;
@@ -393,6 +394,11 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk, 128, 0) == cudaSuccess && occ > 0 &&
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
             m->walk_ctas = 4 * occ * sms;          // a few waves: the walks differ in length (measured flat from 4 to 16 waves, 7 % slower at one)
+    }
+    cudaFuncSetAttribute(k_front<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(128));
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front<float, 128>, 128, AMB_FRONT_SMEM(128)) == cudaSuccess && occ > 0) m->front_ctas_per_sm = occ;
     }
     cudaFuncSetAttribute(k_front<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(256));
     cudaFuncSetAttribute(k_front<int16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_FRONT_SMEM(256));
@@ -966,7 +972,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // (three per SM) and the same as 64 (twelve per SM); AMB_FRONT_NT=256 selects the larger step for comparison.
         static const int front_nt = (std::getenv("AMB_FRONT_NT") && std::atoi(std::getenv("AMB_FRONT_NT")) == 256) ? 256 : 128;
         const int per_block = AMB_TILE / (16 * front_nt);                    // tile steps per 4096-sample block: 1 or 2
-        const int ftiles = tiles * per_block, ctas_per_sm = 768 / front_nt;
+        const int ftiles = tiles * per_block, ctas_per_sm = front_nt == 128 ? m->front_ctas_per_sm : 768 / front_nt;
         fa.tiles = ftiles;
         // spans: enough CTAs to fill the GPU, long enough that the 40,960-sample warm-up of the EMA state stays a small part
         int64_t span = ((int64_t)ns * ftiles + 148 * ctas_per_sm - 1) / (148 * ctas_per_sm);      // one wave
@@ -1004,7 +1010,9 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     g.sum_lo = m->written - m->hist > 0 ? m->written - m->hist : 0;       // summaries and slots are kept for the last `hist` samples
     g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
-    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = m->xc.as<float>(); g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
+    // AMB_XC_STORE=0 (comparison runs): no screening store, the walkers screen their refines themselves (amb_xcorr_screen)
+    static const bool xc_store_on = !(std::getenv("AMB_XC_STORE") && std::getenv("AMB_XC_STORE")[0] == '0');
+    g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = xc_store_on ? m->xc.as<float>() : nullptr; g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
     // idle-call screening (k_cold_calls) pays when pushes are long; AMB_COLD_CALLS=0 switches it off (comparison runs)
     static const bool cold_on = !(std::getenv("AMB_COLD_CALLS") && std::getenv("AMB_COLD_CALLS")[0] == '0');
@@ -1025,7 +1033,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // next slot while it works on the current one
         // (measured per 33 k candidate slots: 148 x 8 CTAs 0.49 ms, x 16 0.45, x 32 0.43, x 64 0.42, x 128 0.41)
         const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
-        LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
+        if (xc_store_on) LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
                                                                                      m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
     }
     int n_out = 0;
