@@ -638,7 +638,7 @@ struct AmbJob {
     int32_t nsym;            // data symbols to demodulate
     int32_t status;          // preset status (non-zero: skip demod)
     int32_t stream;
-    int32_t mode;            // 0: decodeChunkFrame tail, 1: decodeReceivedSignal tail
+    int32_t mode;            // 0: decodeChunkFrame tail, 1: decodeReceivedSignal tail, 2: the same for analyzeLoopback (every symbol exact)
     AmbXform xf;
     double coarse, fine;
     int64_t result_pos;      // preamble_idx to report (-1: none)
@@ -837,6 +837,7 @@ __device__ __forceinline__ void fft16f(float2* v) {
 #define AMB_FD_HWBUF (16 * AMB_FD_TSTRIDE)              // float2 per half-warp
 #define AMB_FD_ITERS (AMB_FD_MAXBINS / 16)              // 14
 #define AMB_FD_FB_WARPS 2                               // warps that run the float64-faithful fallback
+#define AMB_FD_HDR_SYMS 12                              // header symbols the fallback demodulates first to find the frame's extent
 #define AMB_FD_CPV 4                                    // cyclic-prefix samples per lane loaded ahead of the transform
 // shared memory: the fast layout (one transpose buffer per half-warp, twiddles, equaliser tables) and the fallback layout
 // share one region; the fused kernel keeps the frame's constellation indices behind it (one byte per data subcarrier)
@@ -1156,11 +1157,56 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
             amb_channel_from_spectrum(re, im, T->known_re, nullptr, T->sub_start, T->sub_end, h_re, h_im);
         }
         __syncthreads();
+        // ---- which symbols can the parser reach?  The collection window usually runs past the frame (the trailing silence of a
+        //      recording, a short frame inside a full-length window): those symbols carry noise, fail the margin guard and
+        //      would all be redone in float64, although no result field, CRC or payload byte depends on them.  The header
+        //      symbols are demodulated faithfully first, the frame's extent follows from the header (the parsers of
+        //      amb_device.cuh), and only flagged symbols inside it are redone.  Decoded bytes beyond the extent are the
+        //      float32 pipeline's decisions (include/audio_modem_b200.h: amb_frame_result).
+        __shared__ int s_need;
+        uint8_t* hdr_idx = reinterpret_cast<uint8_t*>(qs + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS);     // [AMB_FD_HDR_SYMS][n_data]
+        const int bits_per_sym = n_data * T->bps, rep_v = T->rep;
+        const int64_t n_total = amb_num_bytes((int64_t)J.nsym * n_data, T->bps, rep_v);
+        const int hdr_syms = n_total >= 12 ? (int)(((int64_t)12 * 8 * rep_v - 1) / bits_per_sym) + 1 : 0;
+        const bool use_extent = !FUSED && J.mode != 2 && hdr_syms > 0 && hdr_syms <= AMB_FD_HDR_SYMS && hdr_syms <= J.nsym &&
+                                (size_t)AMB_FD_SMEM_FB + (size_t)AMB_FD_HDR_SYMS * AMB_FD_MAXBINS <= (size_t)AMB_FD_UNION(NT);
+        if (tid == 0) s_need = J.nsym;
+        if (use_extent) {
+            if (warp < AMB_FD_FB_WARPS) {
+                for (int hs = warp; hs < hdr_syms; hs += AMB_FD_FB_WARPS) {
+                    amb_fft512_load(sig, J.data_pos + (int64_t)hs * sym + cp, re, im);
+                    amb_fft512_faithful(re, im, tw_re, tw_im, T->sub_start, T->sub_end);
+                    amb_symbol_demap(T, re, im, h_re, h_im, qs + warp * 2 * AMB_MAX_PILOTS, hdr_idx + hs * n_data, nullptr, nullptr);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint8_t hb[12];
+                for (int b = 0; b < 12; b++) hb[b] = amb_pack_byte(hdr_idx, T->bps, rep_v, b);
+                int64_t need = -1;                                    // bytes the parser consumes; -1: no frame (only the header matters)
+                const int first = hb[0];
+                if (first == AMB_FRAME_META && (J.mode == 1 || n_total >= 6)) { if (n_total >= 16 && 12 + (int64_t)hb[11] + 4 <= n_total) need = 12 + (int64_t)hb[11] + 4; }
+                else if (first == AMB_FRAME_DATA && (J.mode == 1 || n_total >= 6)) { const int64_t dl = (hb[5] << 8) | hb[6]; if (n_total >= 11 && 7 + dl + 4 <= n_total) need = 7 + dl + 4; }
+                else if (J.mode == 1 && n_total >= 10) {
+                    const int64_t nl = first;
+                    if (nl <= 7) {                                    // dataLen sits inside the 12 header bytes
+                        const int64_t dl = (int32_t)(((uint32_t)hb[1 + nl] << 24) | ((uint32_t)hb[2 + nl] << 16) | ((uint32_t)hb[3 + nl] << 8) | (uint32_t)hb[4 + nl]);
+                        if (dl > 0 && 1 + nl + 4 + dl + 4 <= n_total) need = 1 + nl + 4 + dl + 4;
+                    } else need = n_total;                            // a long file name: the header runs past what was demodulated here
+                }
+                int need_syms = hdr_syms;
+                if (need > 0) { const int64_t q = (need * 8 * rep_v - 1) / bits_per_sym + 1; need_syms = q > J.nsym ? J.nsym : (int)q; if (need_syms < hdr_syms) need_syms = hdr_syms; }
+                s_need = need_syms;
+            }
+            __syncthreads();
+        }
+        const int need_syms = s_need;
         if (warp < AMB_FD_FB_WARPS) {
             unsigned long long my_fallbacks = 0;
             int ord = 0;
             for (int t = 0; t < n_here; t++) {
                 if (!(((t < 32 ? m0 : m1) >> (t & 31)) & 1u)) continue;
+                if (g0 + t >= need_syms) continue;                  // beyond the frame's extent
                 if ((ord++ % AMB_FD_FB_WARPS) != warp) continue;
                 const int sidx = g0 + t;
                 uint8_t* io = FUSED ? s_idx + sidx * n_data : out.idx + (int64_t)j * out.idx_stride + (int64_t)sidx * n_data;
@@ -1681,7 +1727,9 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
     AmbJob J;
     J.p = y + (int64_t)r * stride; J.base = 0; J.lo = 0; J.hi = len;
     J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
-    J.stream = r; J.mode = 1; J.status = 0; J.nsym = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
+    // mode 2: analyzeLoopback reads the fixture bytes at a fixed place whatever the header says (modem.js:1056-1066): parsed
+    // like mode 1, but the demodulator keeps every symbol exact
+    J.stream = r; J.mode = analyze ? 2 : 1; J.status = 0; J.nsym = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
     J.coarse = coarse_best[r]; J.fine = 0.0; J.result_pos = -1;
     // analyzeLoopback falls back to the cross-correlation detector (modem.js:983-987), keeps a weak refinement (no 0.1
     // test, :1016) and still reports the channel when no data follows the CE symbol (:1052)

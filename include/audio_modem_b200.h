@@ -85,6 +85,13 @@ extern "C" {
  * (modem.js:644-653), metadata (:822-827), data chunk (:843-848).  `n_bytes`
  * decoded bytes (bitsToBytes output, modem.js:605/:791) are written to the
  * caller's byte buffer; name/data are slices of it at name_off / data_off.
+ * Exactness: every byte the reference's parsers consume - header, file name,
+ * payload, CRC - is the reference's bit for bit.  Bytes after that extent
+ * come from symbols behind the frame (the rest of the collection window or
+ * recording, i.e. noise); nothing the reference returns depends on them and
+ * they are the float32 pipeline's decisions, which may differ from a
+ * float64 demodulation of the same noise.  amb_demodulate (demodulateOFDM
+ * itself) is exact for every symbol.
  */
 typedef struct amb_frame_result {
     int32_t status;          /* AMB_ST_* */
