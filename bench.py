@@ -1022,8 +1022,9 @@ def run_b200(args, rank, world, local_rank, workloads):
             sc.stop()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             r = cpu_leg(wl, steps=1000, warmup=1, budget_s=args.cpu_seconds)
+            r1 = cpu_leg(wl, steps=1000, warmup=0, budget_s=min(3.0, args.cpu_seconds), threads=1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-                                    "payload_mb_per_s": r["payload_mb_per_s"]}
+                                    "payload_mb_per_s": r["payload_mb_per_s"], "single_thread_value": r1["value"]}
         if rank == 0:
             print(json.dumps(line), flush=True)
     if ctx.dist:
