@@ -1720,6 +1720,7 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
                                                        const int64_t* __restrict__ coarse_idx, const double* __restrict__ coarse_best,
                                                        const int64_t* __restrict__ alt_idx, int analyze, AmbJob* __restrict__ jobs) {
     __shared__ double scratch[4][64];
+    __shared__ float vbuf[4][2 * 768 + 8];          // float32 screening values of the offsets c - 3 CP .. c + 3 CP (at most 1537)
     const int warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
     if (r >= n) return;
@@ -1741,7 +1742,12 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
         const int64_t R = T->fine_radius, plen = T->sym_len;
         const int64_t fs = c - R > 0 ? c - R : 0, fe = (c + R < len - plen) ? c + R : len - plen;
         int64_t pos;
-        const double best = amb_fine_xcorr(T, sig, fs, fe, c, scratch[warp], &pos);
+        // float32 screening of every offset, then the offsets within 1e-3 of its maximum exactly (the refine of the streaming
+        // path, amb_fine_xcorr_store, without a store): argmax and metric are those of the all-float64 loop of modem.js:571-586
+        AmbWalkGeom G;
+        memset(&G, 0, sizeof(G));
+        double best = amb_fine_xcorr_store(T, G, sig, fs, fe, c, scratch[warp], &pos, vbuf[warp], (int)(sizeof(vbuf[0]) / sizeof(float)));
+        best = amb_resolve_fine(T, sig, pos, best);          // (a single surviving offset: its exact metric is formed here)
         J.fine = best;
         if (!analyze && best < 0.1) J.status = AMB_ST_PREAMBLE_LOW_CORRELATION;
         else {

@@ -655,11 +655,14 @@ def run_c5(ctx, clocks, ns=None, light=False):
     iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
     # end-to-end: the whole period in page-locked host memory, one contiguous [n_streams][push] block per push (the layout a
     # caller feeding concurrent streams hands over)
+    # (several ranks share the host: with N > 1 only two pushes of the period are kept in page-locked memory and alternated - 3.8
+    # instead of 7.5 GB per rank - which cuts the streams' signal every other push but moves and processes the same bytes)
     e2e_steps = period
-    host = amb.modem.pinned_empty((period, ns, push), np.float32)
+    host_secs = period if world == 1 else min(period, 2)
+    host = amb.modem.pinned_empty((host_secs, ns, push), np.float32)
     hx = host.array
     rows = 512
-    for p in range(period):
+    for p in range(host_secs):
         for r0 in range(0, ns, rows):
             hx[p, r0:r0 + rows] = x[r0:r0 + rows, p * push:(p + 1) * push].cpu().numpy()
     k1 = k0 + n_done + prof_steps
@@ -669,10 +672,10 @@ def run_c5(ctx, clocks, ns=None, light=False):
     t0 = time.perf_counter()
     e2e_frames = 0
     for p in range(e2e_steps):
-        e2e_frames += _push_host_rows(m, host, ns, push, p * ns * push, push)
+        e2e_frames += _push_host_rows(m, host, ns, push, (p % host_secs) * ns * push, push)
     m.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert abs(e2e_frames - frames_per_period) <= ns, (e2e_frames, frames_per_period)
+    assert (abs(e2e_frames - frames_per_period) <= ns) if host_secs == period else e2e_frames > 0, (e2e_frames, frames_per_period)
     clocks.mark_end()
     d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
     m.stream_close()
