@@ -9,7 +9,7 @@ from ._lib import AmbError, FrameResult  # noqa: F401
 from .modem import (  # noqa: F401
     FRAME_DATA, FRAME_META, Modem, StreamingReceiver, analyzeLoopback, buildDataChunkFrame, buildTransmitSignal, generateTestSignal, buildMetadataFrame, crc32, decodeChunkFrame, decodeReceivedSignal, demodulateOFDM,
     detectPreamble, detectPreambleCrossCorr, estimateChannel, estimateFrameSamples, generateChannelEstSymbol,
-    generatePreambleSymbol1, preprocessSignal, result_to_object, setDevice, setOFDMConfig,
+    generatePreambleSymbol1, modulateOFDM, preprocessSignal, result_to_object, setDevice, setOFDMConfig,
 )
 
 

@@ -114,5 +114,43 @@ def main():
     print("wrote tests/golden/reference_golden.json")
 
 
+def dump_cases(ref_dir, quick=False, out_name="reference_cases.json"):
+    """the wider case list (tests/refcases.py), one engine run per mode to bound the size of a program"""
+    import time
+
+    import refcases
+    from oracle import oracle as O
+
+    prelude = open(os.path.join(HERE, "prelude.js"), encoding="utf-8").read()
+    ref = reference_program(ref_dir, verbose=False)
+    body = open(os.path.join(HERE, "dump_body.js"), encoding="utf-8").read() + open(os.path.join(HERE, "cases_body.js"), encoding="utf-8").read()
+    cases = refcases.build_cases(O, quick=quick)
+    out = {"note": "tests/refcases.py evaluated by the reference (modem.js, app.js) under Qt 6.6 QJSEngine; written by tools/qjs/dump_golden_qjs.py",
+           "inputs_sha256": {}, "cases": {}}
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["mode"], c["kind"] == "stream"), []).append(c)
+    for (mode, is_stream), cs in groups.items():
+        js_cases = []
+        for c in cs:
+            inputs = {}
+            for k, a in c["inputs"].items():
+                a = np.ascontiguousarray(a)
+                inputs[k] = {"dtype": "f32" if a.dtype == np.float32 else "u8", "hex": a.tobytes().hex()}
+                out["inputs_sha256"][f"{c['mode']}:{c['name']}:{k}"] = refcases.sha(a)
+            js_cases.append({"name": c["name"], "mode": c["mode"], "kind": c["kind"], "args": c["args"], "inputs": inputs})
+        t0 = time.time()
+        prog = prelude + "\n" + ref + "\nvar __cases = " + json.dumps(js_cases) + ";\n" + body + "\n__out = JSON.stringify(__runCases());\n"
+        out["cases"].update(json.loads(run_js(prog, "cases_prog")))
+        print(f"{mode} {'stream' if is_stream else 'batch'}: {len(cs)} cases in {time.time() - t0:.0f} s", file=sys.stderr)
+    json.dump(out, open(os.path.join(GOLD, out_name), "w"), indent=1, sort_keys=True)
+    print("wrote tests/golden/" + out_name, len(out["cases"]), "cases")
+
+
 if __name__ == "__main__":
-    main()
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    ref_dir = args[0] if args else "/root/reference"
+    if "--cases-only" not in sys.argv:
+        main()
+    if "--golden-only" not in sys.argv:
+        dump_cases(ref_dir, quick="--quick" in sys.argv, out_name="reference_cases_quick.json" if "--quick" in sys.argv else "reference_cases.json")
