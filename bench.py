@@ -27,7 +27,8 @@ float64-faithful transmit path (bit-identical to the reference's frames).
   roofline : the kernel with the largest share of the timed region, algorithmic bytes / its mean launch duration
           (per-kernel CUDA events recorded by the library in a separate pass over the same steps) against
           MEASURED_PEAKS.json; `whole_step` is the same for the whole step.
-  cpu_baseline : the oracle (C++ float64 restatement of modem.js/app.js; Node is not available) on the host cores.
+  cpu_baseline : the oracle (C++ float64 restatement of modem.js/app.js, pinned bit for bit against the reference's own
+                 outputs; Node is not available, and /root/reference does not exist on the GPU box) on the host cores.
 
 `--impl reference` times that CPU path alone (all host cores) on the same workload, metric and unit.
 """

@@ -2,9 +2,10 @@
 // Pins the oracle against the REAL reference: evaluates playok/audio-modem's own modem.js and the DOM-free part of app.js
 // (RingBuffer, StreamingReceiver) under Node.js and writes tests/golden/reference_golden.json in the schema of
 // tests/golden/golden.json (which the oracle wrote).  tests/test_golden.py::test_reference_golden_matches_the_oracle then
-// compares the two; until that file exists the test skips and parity stays "unpinned" (DESIGN.md section 2).
+// compares the two (DESIGN.md section 2).
 //
-// NOT RUN IN THIS REPOSITORY: the build image has no JavaScript engine.  One command for whoever has Node >= 16:
+// NOT RUN IN THIS REPOSITORY (no Node in the build image).  The committed reference_golden.json was written by the same dump
+// under Qt's QJSEngine (tools/qjs/dump_golden_qjs.py); this script is the second opinion under V8.  One command, Node >= 16:
 //
 //     python tests/golden/make_golden.py --inputs        # writes tests/golden/_inputs/*.f32 (the noisy stream inputs)
 //     node node/dump_golden.js /path/to/audio-modem      # the reference checkout (modem.js, app.js)

@@ -9,13 +9,15 @@
 // removal, incremental Schmidl-Cox scan, refine, collect, decode).
 // Every function cites the reference file:line it follows.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures,
-// and no JavaScript engine exists in the build container or on the GPU box,
-// so this restatement cannot be diffed against `modem.js` itself.  It is
-// pinned instead by known-answer self-checks (tests/test_oracle_kat.py):
-// IEEE CRC-32 vs zlib, the float64-rounded LCG states derived in SURVEY.md
-// §8(c), the Gray 16-QAM table, structural preamble properties, and
-// build→decode round trips in every mode.
+// PINNED against the reference's own outputs: the reference ships no tests,
+// golden vectors or fixtures, so modem.js and the receiver classes of app.js
+// are evaluated as they are by Qt's QJSEngine (the ECMAScript engine inside
+// Nsight Compute's host directory; tools/qjs/), and what they return on the
+// golden schema and on the 141 cases of tests/refcases.py is committed under
+// tests/golden/reference_golden.json / reference_cases.json (1,919 values).
+// This restatement reproduces every one of them bit for bit, floats included
+// (tests/test_golden.py).  The known-answer checks of tests/test_oracle_kat.py
+// (CRC-32 vs zlib, the float64-rounded LCG, Gray 16-QAM, round trips) remain.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may load this library.  Build with

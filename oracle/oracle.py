@@ -3,8 +3,8 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  The product package never
 imports this module.  Function names follow modem.js so that the parity tests
-read like calls into the reference.  PARITY UNPINNED (no JS engine available;
-see the header of modem_oracle.cpp).
+read like calls into the reference.  Pinned bit for bit against the outputs of
+the real modem.js / app.js (tests/golden/reference_*.json; header of modem_oracle.cpp).
 """
 import ctypes as C
 import os

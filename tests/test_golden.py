@@ -1,6 +1,7 @@
-"""Committed golden fixtures (tests/golden, generated by tests/golden/make_golden.py from the oracle): the oracle must
-still reproduce them (drift pin), and the CUDA path must reproduce them through the C-ABI (GPU).  They do not pin the
-oracle against modem.js itself - the reference ships no vectors."""
+"""Committed golden fixtures.  tests/golden/golden.json (tests/golden/make_golden.py, from the oracle): the oracle must still
+reproduce it (drift pin), and the CUDA path must reproduce it through the C-ABI (GPU).  tests/golden/reference_golden.json
+and reference_cases.json (tools/qjs/dump_golden_qjs.py, from the REAL modem.js / app.js): the oracle must equal them - the
+pin against the reference itself."""
 import hashlib
 import importlib.util
 import json

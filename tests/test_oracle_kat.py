@@ -1,6 +1,6 @@
-"""Known-answer checks that pin the oracle.  The reference ships no tests or golden vectors and
-no JS engine exists here (PARITY UNPINNED against modem.js itself); these are the facts that can be derived from
-the reference's source alone, plus round trips through its own TX."""
+"""Known-answer checks of the oracle: the facts that can be derived from the reference's source alone, plus
+round trips through its own TX.  The pin against the reference's own OUTPUTS is tests/test_golden.py (reference_golden.json,
+reference_cases.json: modem.js / app.js evaluated by Qt's QJSEngine, tools/qjs/)."""
 import zlib
 
 import numpy as np
