@@ -1061,6 +1061,9 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     L.bm_out = m->l_bmout.as<AmbStreamState>(); L.bm_rec = m->l_bmrec.as<AmbFrameRec>(); L.bm_has = m->l_bmhas.as<int>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
     const int walk_grid = (int)(blocks_for(max_links, 4) < m->walk_ctas ? blocks_for(max_links, 4) : m->walk_ctas);
+    // phase B: a CTA per flat link index where that many CTAs fit the grid - then the four warps of a CTA walk one link as a team
+    // (k_link_walk decides from total <= gridDim.x); otherwise a warp per link as in phase A
+    const int walk_grid_b = max_links <= m->walk_ctas ? (int)(max_links > 0 ? max_links : 1) : walk_grid;
     const int flat_grid = (int)(blocks_for(max_links, 128) < 148 * 8 ? blocks_for(max_links, 128) : 148 * 8);
     int* h = m->h_counts;           // pinned: [0] n_active, [1] total jobs, [2] max nsym, [3] kept, [4] n_redo
     for (int pass = 0; pass < 4096 && n_todo > 0; pass++) {
@@ -1105,7 +1108,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
                                                                                   m->cold_tag.as<int32_t>(), call_lo, call_hi));
             }
             L.trace_iter = (int)(m->link_iterations * 2 + 1);
-            LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+            LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi, g.k_end,

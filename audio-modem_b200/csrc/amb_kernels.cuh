@@ -135,6 +135,7 @@ struct AmbFrontArgs {
     unsigned long long* nan_pos; int n_streams; int64_t g0;
 };
 
+#define AMB_TEAM_VCAP 1664          // floats of the team's shared screening row (k_link_walk): 2 x fine radius + 1 = 1,537 offsets in the narrowband config
 #define AMB_FR_PAD(i) ((i) + (((i) >> 5) << 2))       // 4 floats of padding per 32: 128-bit accesses are conflict-free both per thread (16-float rows, 64 bytes apart) and consecutive
 #define AMB_FR_BUF AMB_FR_PAD(AMB_TILE)               // floats per padded tile buffer (5120)
 #ifndef AMB_FRONT_STAGES
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
         G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
     G.memo_out = nullptr; G.memo_in = nullptr;
+    G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
     sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
@@ -2614,10 +2616,16 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo, int n_streams,
                                                     int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
     __shared__ AmbWalkScratch scratch[4];
+    __shared__ float team_vbuf[AMB_TEAM_VCAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_runs = L.n_active[1];
     const int total = mode == 0 ? total_runs + n_todo : total_runs + n_streams;
-    for (int f = blockIdx.x * 4 + warp; f < total; f += gridDim.x * 4) {
+    // Few links (a long capture with sparse frames: every link of phase B gets a CTA of its own): the four warps of the CTA walk
+    // the same link as a team (AmbWalkGeom::team_n) instead of idling - the screening of a direct refine, the one long
+    // data-parallel step of such a walk (1,537 offsets x 768 taps in the narrowband config), is shared between them.
+    const bool team = mode == 1 && total <= (int)gridDim.x;
+    const bool writer = !team || warp == 0;
+    for (int f = team ? blockIdx.x : blockIdx.x * 4 + warp; f < total; f += team ? gridDim.x : gridDim.x * 4) {
         const bool first = mode == 0 && f >= total_runs;
         int s, i = 0;
         if (first) s = todo ? todo[f - total_runs] : f - total_runs;
@@ -2637,6 +2645,7 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
         G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
         G.memo_out = nullptr; G.memo_in = nullptr;
+        G.team_n = team ? 4 : 1; G.team_rank = team ? warp : 0; G.team_vbuf = team_vbuf; G.team_vcap = AMB_TEAM_VCAP;
         if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) { L.memo[f].valid = 0; L.bm_has[f] = 0; } __syncwarp(); }
         int bm = -1;                                     // phase B, link after run p: flat index of p
         if (mode == 1 && i > 0) {
@@ -2644,7 +2653,7 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
             const int have = L.bm_has[bm];
             if (have != 0) {
                 // walked in an earlier iteration of this pass: same outcome
-                if (lane == 0) {
+                if (lane == 0 && writer) {
                     const AmbStreamState so = L.bm_out[bm];
                     L.outB[f] = so; L.hasB[f] = have - 1;
                     if (have == 2) L.recB[f] = L.bm_rec[bm];
@@ -2685,7 +2694,8 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
             for (int q = 0; q < 16; q++) acc[q] = 0ull;
         }
 #endif
-        if (lane == 0) {
+        if (team) __syncthreads();                       // every warp of the team has read what the block below overwrites (bm_has)
+        if (lane == 0 && writer) {
             if (first) {
                 st.dc_mean = dc_next[s]; st.written = g.avail_hi;
                 L.first_out[s] = st; L.first_flag[s] = 1;
@@ -2755,6 +2765,7 @@ __global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
         G.tile_slot = g.tile_slot + (int64_t)s * g.sum_stride; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
         G.F = nullptr; G.F_call0 = 0; G.F_calls = 0; G.cold_tag = nullptr; G.memo_out = nullptr; G.memo_in = nullptr;
+        G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0;
         const float* srow = sums + (int64_t)s * g.sum_stride * AMB_SUM_W;
         const int64_t j0 = (k * g.block_len) >> 8, nt = g.block_len >> 8;          // 16 tiles
         int hot = 0, unknown = 0;

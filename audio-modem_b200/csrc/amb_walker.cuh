@@ -108,6 +108,12 @@ struct AmbWalkGeom {
     // Optional (k_cold_calls): cold_tag[call - F_call0] = c when the call was evaluated exactly, in parallel, under the defect a
     // receiver carries there after re-initialising its sums in call c, and holds no candidate window; -1 otherwise
     const int32_t* cold_tag;
+    // Optional (device, k_link_walk with few links): team_n warps of one CTA walk the SAME link redundantly (identical inputs,
+    // identical control flow, so every warp reaches the same CTA barriers) and share the one expensive data-parallel step, the
+    // float32 screening of a direct refine: warp team_rank computes every team_n-th group of offsets into team_vbuf (shared
+    // memory, team_vcap floats).  team_n <= 1: a warp works alone.
+    int team_n, team_rank, team_vcap;
+    float* team_vbuf;
 };
 
 // screening values in the xc store: a metric in [-1, 1]; AMB_XC_FAIL where the denominator fails its 0.001 test;
@@ -257,6 +263,32 @@ AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums,
     if (f0 < 0) return 0;
     const double b0 = G.F[f0 * 3], b1 = G.F[f0 * 3 + 1], b2 = G.F[f0 * 3 + 2];
     int64_t skipped = 0;
+    if (G.cold_tag) {
+        // runs of calls tagged cold for this trajectory (k_cold_calls): eight tags per lane and round, all loads in flight at once
+        // (an idle stretch of a long capture is thousands of such calls, and a lone warp pays a full memory latency per round)
+        const unsigned all = AMB_NLANES == 32 ? 0xffffffffu : 1u;
+        for (;;) {
+            const int64_t kk0 = k + 8 * (int64_t)AMB_LANE();
+            int32_t tag[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < 8; q++) {
+                const int64_t kk = kk0 + q, fi = kk - G.F_call0;
+                tag[q] = (kk < k_end && fi >= 0 && fi < G.F_calls) ? G.cold_tag[fi] : -1;
+            }
+            int lead = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < 8; q++) if (lead == q && tag[q] == st.init_call && st.init_call >= 0) lead++;
+            const unsigned notfull = ~amb_warp_ballot(lead == 8) & all;
+            const int fl = notfull ? amb_ffs(notfull) - 1 : -1;
+            const int adv = fl < 0 ? 8 * AMB_NLANES : 8 * fl + (int)amb_warp_bcast((double)lead, fl);
+            k += adv; skipped += adv;
+            if (fl >= 0) break;
+        }
+    }
     while (k < k_end) {
         unsigned hot;
         int valid;
@@ -309,19 +341,23 @@ AMB_HD double amb_resolve_fine(const AmbTables* T, const AmbSig& sig, int64_t po
 // encoding as the scan kernel's store: the metric, AMB_XC_FAIL where the denominator clearly fails its 0.001 test,
 // AMB_XC_UNSURE where float32 cannot tell.  |value - exact| < 1e-4 (768 taps, sequential float32 sums: n u sum|s t| <=
 // 768 * 6e-8 of the denominator, by Cauchy-Schwarz), inside the 5e-4 the consumers allow.
-AMB_HD void amb_xcorr_screen(const AmbTables* T, const AmbSig& s, int64_t lo, int n, float* v) {
+AMB_HD void amb_xcorr_screen(const AmbTables* T, const AmbSig& s, int64_t lo, int n, float* v, int team_n = 1, int team_rank = 0) {
     const int plen = T->sym_len;
     const float tE = (float)T->pre1_energy;
     const float* t = T->pre1;
-    AMB_WARP_FOR(gq, (n + 3) / 4) {
+    for (int gq = team_rank * AMB_NLANES + AMB_LANE(); gq < (n + 3) / 4; gq += team_n * AMB_NLANES) {
         const int64_t d = lo + 4 * (int64_t)gq;
         float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
         if (s.xf.kind == AMB_XF_NONE && d >= s.lo && d + plen + 3 <= s.hi) {
             const float* p = s.p + (d - s.base);
             float a0 = p[0], a1 = p[1], a2 = p[2];
+            // (software-pipelined: the loads of the next four taps are in flight while the 20 multiply-adds of these run - a
+            // lone warp has nothing else to hide their latency with)
+            float n3 = p[3], n4 = p[4], n5 = p[5], n6 = p[6], u0 = t[0], u1 = t[1], u2 = t[2], u3 = t[3];
             for (int i = 0; i < plen; i += 4) {                         // (sym_len is a multiple of 4 in every config)
-                const float a3 = p[i + 3], a4 = p[i + 4], a5 = p[i + 5], a6 = p[i + 6];
-                const float t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3];
+                const float a3 = n3, a4 = n4, a5 = n5, a6 = n6;
+                const float t0 = u0, t1 = u1, t2 = u2, t3 = u3;
+                if (i + 4 < plen) { n3 = p[i + 7]; n4 = p[i + 8]; n5 = p[i + 9]; n6 = p[i + 10]; u0 = t[i + 4]; u1 = t[i + 5]; u2 = t[i + 6]; u3 = t[i + 7]; }
                 c[0] = fmaf(a0, t0, c[0]); c[1] = fmaf(a1, t0, c[1]); c[2] = fmaf(a2, t0, c[2]); c[3] = fmaf(a3, t0, c[3]);
                 c[0] = fmaf(a1, t1, c[0]); c[1] = fmaf(a2, t1, c[1]); c[2] = fmaf(a3, t1, c[2]); c[3] = fmaf(a4, t1, c[3]);
                 c[0] = fmaf(a2, t2, c[0]); c[1] = fmaf(a3, t2, c[1]); c[2] = fmaf(a4, t2, c[2]); c[3] = fmaf(a5, t2, c[3]);
@@ -369,8 +405,18 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND)) {
         AMB_STAT(3);
         if (!vbuf || hi < lo || n > vcap) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
-        amb_xcorr_screen(T, sig, lo, n, vbuf);
-        v = vbuf;
+#if defined(__CUDA_ARCH__)
+        if (G.team_n > 1 && n <= G.team_vcap) {
+            __syncthreads();                                            // (the team's readers of the previous screening row are done)
+            amb_xcorr_screen(T, sig, lo, n, G.team_vbuf, G.team_n, G.team_rank);
+            __syncthreads();
+            v = G.team_vbuf;
+        } else
+#endif
+        {
+            amb_xcorr_screen(T, sig, lo, n, vbuf);
+            v = vbuf;
+        }
     } else {
         AMB_STAT(2);
         v = G.xc + (int64_t)slot * G.xc_w + (lo - base);
