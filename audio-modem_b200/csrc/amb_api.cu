@@ -391,7 +391,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     }
     {
         int occ = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk, 128, 0) == cudaSuccess && occ > 0 &&
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_link_walk<false>, 128, 0) == cudaSuccess && occ > 0 &&
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
             m->walk_ctas = 4 * occ * sms;          // a few waves: the walks differ in length (measured flat from 4 to 16 waves, 7 % slower at one)
     }
@@ -1011,6 +1011,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     g.block_len = m->block_len; g.ring_cap = m->ring_cap;
     g.k_end = (m->written + n_new) / m->block_len; g.rec_cap = m->rec_cap;
     // AMB_XC_STORE=0 (comparison runs): no screening store, the walkers screen their refines themselves (amb_xcorr_screen)
+    // AMB_XC_SKIP=0 (comparison runs): a screening row for every candidate tile, also those next to a higher peak
+    static const bool xc_skip_on = !(std::getenv("AMB_XC_SKIP") && std::getenv("AMB_XC_SKIP")[0] == '0');
     static const bool xc_store_on = !(std::getenv("AMB_XC_STORE") && std::getenv("AMB_XC_STORE")[0] == '0');
     g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = xc_store_on ? m->xc.as<float>() : nullptr; g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
@@ -1034,7 +1036,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // (measured per 33 k candidate slots: 148 x 8 CTAs 0.49 ms, x 16 0.45, x 32 0.43, x 64 0.42, x 128 0.41)
         const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
         if (xc_store_on) LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
-                                                                                     m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w));
+                                                                                     m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w,
+                                                                                     xc_skip_on ? m->tile_slot.as<int32_t>() : nullptr, off0 / 256, (off0 + n_new) / 256));
     }
     int n_out = 0;
     int n_todo = ns;
@@ -1091,7 +1094,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         LAUNCH("k_prefix_counts", k_prefix_counts<<<1, 1024, 0, m->stream>>>(L.n_runs, ns, L.run_off, L.n_active + 1));
         // phase A over every run, and next to it the first link of every stream
         L.trace_iter = (int)(m->link_iterations * 2);
-        LAUNCH("k_link_walk_A", k_link_walk<<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+        LAUNCH("k_link_walk_A", k_link_walk<false><<<walk_grid, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                             m->dc_next.as<double>(), todo, n_todo, ns, 0, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
         LAUNCH("k_chain_next", k_chain_next<<<flat_grid, 128, 0, m->stream>>>(ns, L));
         m->link_passes++;
@@ -1108,7 +1111,9 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
                                                                                   m->cold_tag.as<int32_t>(), call_lo, call_hi));
             }
             L.trace_iter = (int)(m->link_iterations * 2 + 1);
-            LAUNCH("k_link_walk_B", k_link_walk<<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+            LAUNCH("k_link_walk_B", k_link_walk<false><<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+                                                                                m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
+            LAUNCH("k_link_walk_B_team", k_link_walk<true><<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi, g.k_end,

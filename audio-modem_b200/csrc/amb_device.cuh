@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define AMB_HD __host__ __device__ __forceinline__
+#define AMB_HD_COLD __host__ __device__ __noinline__        // rarely taken, register-hungry paths: kept out of the callers' allocation
 #else
 #define AMB_HD inline
+#define AMB_HD_COLD inline
 #endif
 
 #if defined(__CUDA_ARCH__)

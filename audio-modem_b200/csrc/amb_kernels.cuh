@@ -2365,9 +2365,42 @@ __device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bo
 }
 __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                       const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count,
-                                                      const int32_t* __restrict__ cand_list, int slot_cap, float* __restrict__ xc, int xc_w) {
+                                                      const int32_t* __restrict__ cand_list, int slot_cap, float* __restrict__ xc, int xc_w,
+                                                      int32_t* __restrict__ tile_slot_rw, int64_t tile_lo, int64_t tile_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_cand = min(slot_count[1], slot_cap);
+    // A preamble's candidate windows (metric > 0.5) usually spread over two adjacent tiles, but the coarse position the walker
+    // refines around is the maximum of the metric, which lies in the tile with the higher peak: a candidate tile whose exact
+    // maximum (tsum[0], k_tri_store) is clearly below that of a candidate neighbour of this push gets no row (AMB_TS_NOXC; should a
+    // walker want it after all - a carried defect reshaping the peak - it screens the refine itself, amb_xcorr_screen).
+    auto skip_row = [&](int sl) -> bool {
+        if (!tile_slot_rw || !g.tsum) return false;
+        const int s = slot_info[sl * 4];
+        const int64_t t = slot_info[sl * 4 + 1];
+        const float mine = g.tsum[(int64_t)sl * 4] * 1.02f;
+        bool skip = false;
+#pragma unroll
+        const int64_t per_call = g.block_len >> 8, gt = t + (g.base_g >> 8);      // (global tile index: tile gt holds the window-end samples [256 gt, 256 gt + 256))
+        for (int dn = -1; dn <= 1; dn += 2) {
+            const int64_t nb = t + dn;
+            if (nb < tile_lo || nb >= tile_hi) continue;
+            // the running best is per call (app.js:806): where a call ends between the two tiles, the scan commits the best of the
+            // earlier one at the end of its data (app.js:842-846) whatever follows - both rows are needed
+            if (per_call > 0 && ((dn < 0 ? gt : gt + 1) % per_call) == 0) continue;
+            const int raw = tile_slot_rw[(int64_t)s * g.sum_stride + nb];
+            if (raw >= 0 && (raw & AMB_TS_CAND) && g.tsum[(int64_t)(raw & AMB_TS_MASK) * 4] > mine) skip = true;
+        }
+        if (skip && threadIdx.x == 0) atomicOr(tile_slot_rw + (int64_t)s * g.sum_stride + t, AMB_TS_NOXC);
+        return skip;
+    };
+    auto next_cand = [&](int& ci) -> int {
+        while (ci < n_cand) {
+            const int sl = cand_list[ci];
+            if (!skip_row(sl)) return sl;
+            ci += gridDim.x;
+        }
+        return -1;
+    };
     const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
     const int L = xc_w + plen;                                         // samples needed (multiple of 16 for every config)
     const int LP = AMB_XC_PADI(L) + 4;
@@ -2388,7 +2421,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
     const float t_last_u = split > 0 ? T->pre1[cp + split - 1] : 0.f, t_last = T->pre1[cp + 255];
     const int64_t lo = g.base_g > 0 ? g.base_g : 0;
     int ci = blockIdx.x;
-    int slot = ci < n_cand ? cand_list[ci] : -1;
+    int slot = next_cand(ci);
     if (slot >= 0) {
         const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
         const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
@@ -2422,7 +2455,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
         __syncthreads();                                               // u, u2, SQ complete; sg is free
         const int cur = slot;
         ci += gridDim.x;
-        slot = ci < n_cand ? cand_list[ci] : -1;
+        slot = next_cand(ci);
         if (slot >= 0) {
             const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
             const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
@@ -2611,19 +2644,23 @@ __device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n
 //   (k_chain_links applies it), so that phase A keeps reading an unchanging states[].
 // mode 1 (phase B): flat link index, start state = the stream's current state (link 0) or the phase-A end state of the
 //   previous chain run; the warp also decides whether its link reproduced the speculation (first_stop).
+template <bool TEAM>
 __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                     const float* __restrict__ sums, const AmbStreamState* __restrict__ states,
                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo, int n_streams,
                                                     int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
     __shared__ AmbWalkScratch scratch[4];
-    __shared__ float team_vbuf[AMB_TEAM_VCAP];
+    __shared__ float team_vbuf[TEAM ? AMB_TEAM_VCAP : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_runs = L.n_active[1];
     const int total = mode == 0 ? total_runs + n_todo : total_runs + n_streams;
+    // (phase B is launched in both instantiations, the link count decides on the device which one runs: the team code costs the
+    // warp-per-link walk of a dense stream registers it cannot spare)
+    if (TEAM != (mode == 1 && total <= (int)gridDim.x)) return;
     // Few links (a long capture with sparse frames: every link of phase B gets a CTA of its own): the four warps of the CTA walk
     // the same link as a team (AmbWalkGeom::team_n) instead of idling - the screening of a direct refine, the one long
     // data-parallel step of such a walk (1,537 offsets x 768 taps in the narrowband config), is shared between them.
-    const bool team = mode == 1 && total <= (int)gridDim.x;
+    constexpr bool team = TEAM;
     const bool writer = !team || warp == 0;
     for (int f = team ? blockIdx.x : blockIdx.x * 4 + warp; f < total; f += team ? gridDim.x : gridDim.x * 4) {
         const bool first = mode == 0 && f >= total_runs;

@@ -129,7 +129,8 @@ struct AmbWalkGeom {
 // (the same flags as slot_info[2], here so that the walker learns them with the slot number in one load)
 #define AMB_TS_ROWS (1 << 30)
 #define AMB_TS_CAND (1 << 29)
-#define AMB_TS_MASK ((1 << 29) - 1)
+#define AMB_TS_NOXC (1 << 28)         // set by k_xcorr_store: a candidate tile whose screening row was left out (a neighbour holds the peak)
+#define AMB_TS_MASK ((1 << 28) - 1)
 AMB_HD int amb_tile_slot_raw(const AmbWalkGeom& G, int64_t j) {
     if (!G.tile_slot) return -1;
     const int64_t rel = j - (G.sum_base >> 8);
@@ -254,6 +255,35 @@ AMB_HD int amb_call_cold(const AmbWalkGeom& G, const float* sums, int64_t k, dou
 // skipped (< k_end) and advances the state over them.
 struct AmbColdCache { int64_t base; unsigned hot; int32_t init_call; };     // hot flags of calls base .. base + 31 on the trajectory of init_call
 
+// Length of the run of calls from k on that k_cold_calls tagged cold for the trajectory of init_call: eight tags per lane and
+// round, all loads in flight at once (an idle stretch of a long capture is thousands of such calls, and a lone warp pays a full
+// memory latency per round).  Called once a whole round of 32 calls was cold.
+AMB_HD_COLD int64_t amb_skip_tagged_calls(const int32_t* cold_tag, int64_t F_call0, int64_t F_calls, int32_t init_call, int64_t k, int64_t k_end) {
+    const unsigned all = AMB_NLANES == 32 ? 0xffffffffu : 1u;
+    int64_t total = 0;
+    if (init_call < 0) return 0;
+    for (;;) {
+        const int64_t kk0 = k + total + 8 * (int64_t)AMB_LANE();
+        int32_t tag[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 8; q++) {
+            const int64_t kk = kk0 + q, fi = kk - F_call0;
+            tag[q] = (kk < k_end && fi >= 0 && fi < F_calls) ? cold_tag[fi] : -1;
+        }
+        int lead = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 8; q++) if (lead == q && tag[q] == init_call) lead++;
+        const unsigned notfull = ~amb_warp_ballot(lead == 8) & all;
+        const int fl = notfull ? amb_ffs(notfull) - 1 : -1;
+        total += fl < 0 ? 8 * AMB_NLANES : 8 * fl + (int)amb_warp_bcast((double)lead, fl);
+        if (fl >= 0) return total;
+    }
+}
+
 AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums, AmbStreamState& st, int64_t k_end, AmbWalkScratch* W, AmbColdCache& cc) {
     if (!G.F || st.state != AMB_RX_IDLE || !st.ac_init || st.lag != 1) return 0;
     int64_t k = st.next_call;
@@ -263,32 +293,6 @@ AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums,
     if (f0 < 0) return 0;
     const double b0 = G.F[f0 * 3], b1 = G.F[f0 * 3 + 1], b2 = G.F[f0 * 3 + 2];
     int64_t skipped = 0;
-    if (G.cold_tag) {
-        // runs of calls tagged cold for this trajectory (k_cold_calls): eight tags per lane and round, all loads in flight at once
-        // (an idle stretch of a long capture is thousands of such calls, and a lone warp pays a full memory latency per round)
-        const unsigned all = AMB_NLANES == 32 ? 0xffffffffu : 1u;
-        for (;;) {
-            const int64_t kk0 = k + 8 * (int64_t)AMB_LANE();
-            int32_t tag[8];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int q = 0; q < 8; q++) {
-                const int64_t kk = kk0 + q, fi = kk - G.F_call0;
-                tag[q] = (kk < k_end && fi >= 0 && fi < G.F_calls) ? G.cold_tag[fi] : -1;
-            }
-            int lead = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int q = 0; q < 8; q++) if (lead == q && tag[q] == st.init_call && st.init_call >= 0) lead++;
-            const unsigned notfull = ~amb_warp_ballot(lead == 8) & all;
-            const int fl = notfull ? amb_ffs(notfull) - 1 : -1;
-            const int adv = fl < 0 ? 8 * AMB_NLANES : 8 * fl + (int)amb_warp_bcast((double)lead, fl);
-            k += adv; skipped += adv;
-            if (fl >= 0) break;
-        }
-    }
     while (k < k_end) {
         unsigned hot;
         int valid;
@@ -318,6 +322,7 @@ AMB_HD int64_t amb_walk_skip_cold_calls(const AmbWalkGeom& G, const float* sums,
         if (first > valid) first = valid;
         k += first; skipped += first;
         if (first < valid) break;
+        if (first == 32 && G.cold_tag) { const int64_t adv = amb_skip_tagged_calls(G.cold_tag, G.F_call0, G.F_calls, st.init_call, k, k_end); k += adv; skipped += adv; }
     }
     if (skipped > 0) {
         const int64_t fi = k - 1 - G.F_call0;
@@ -341,7 +346,7 @@ AMB_HD double amb_resolve_fine(const AmbTables* T, const AmbSig& sig, int64_t po
 // encoding as the scan kernel's store: the metric, AMB_XC_FAIL where the denominator clearly fails its 0.001 test,
 // AMB_XC_UNSURE where float32 cannot tell.  |value - exact| < 1e-4 (768 taps, sequential float32 sums: n u sum|s t| <=
 // 768 * 6e-8 of the denominator, by Cauchy-Schwarz), inside the 5e-4 the consumers allow.
-AMB_HD void amb_xcorr_screen(const AmbTables* T, const AmbSig& s, int64_t lo, int n, float* v, int team_n = 1, int team_rank = 0) {
+AMB_HD_COLD void amb_xcorr_screen(const AmbTables* T, const AmbSig s, int64_t lo, int n, float* v, int team_n = 1, int team_rank = 0) {
     const int plen = T->sym_len;
     const float tE = (float)T->pre1_energy;
     const float* t = T->pre1;
@@ -402,7 +407,7 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
     const int64_t base = (j << 8) - 511 - T->fine_radius;
     const int n = (int)(hi - lo + 1);
     const float* v;
-    if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND)) {
+    if (raw < 0 || lo < base || hi >= base + G.xc_w || hi < lo || !(raw & AMB_TS_CAND) || (raw & AMB_TS_NOXC)) {
         AMB_STAT(3);
         if (!vbuf || hi < lo || n > vcap) return amb_fine_xcorr(T, sig, lo, hi, p, scratch, pos_out);
 #if defined(__CUDA_ARCH__)

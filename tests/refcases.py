@@ -49,6 +49,23 @@ def build_cases(O, quick=False):
         add("decode/noise_only", mode, "decode", x=(np.random.default_rng(5).standard_normal(40000) * 0.05).astype(np.float32))
         add("decode/silence", mode, "decode", x=np.zeros(9000, np.float32))
         add("decode/dc_offset", mode, "decode", x=(O.addAwgn(sig, 0.002, 3) + np.float32(0.21)).astype(np.float32))
+        # ---- analyzeLoopback (modem.js:975-1081) on generateTestSignal's fixture through channels, its early returns and its
+        # detector fallback (the cases of tests/test_gpu_parity.py::_loopback_cases)
+        t = O.generateTestSignal(cfg, mod, rep)["signal"]
+        lead_t = 13230 if cfg == "standard" else 22050
+        pw = O.power(t[lead_t:][:5000])
+        lb = {"clean": t, "awgn_20db": O.addAwgn(t, np.sqrt(pw / 10 ** 2.0), 3),
+              "multipath_12db": O.addAwgn(O.multipath(t, [0, 23, 57], [1.0, 0.5, 0.25]), np.sqrt(pw / 10 ** 1.2), 4),
+              "awgn_3db": O.addAwgn(t, np.sqrt(pw / 10 ** 0.3), 5), "ce_does_not_fit": t[: lead_t + 2 * sl + 10],
+              "no_data_symbols": t[: lead_t + 3 * sl], "packet_cut_short": t[: lead_t + 3 * sl + 5 * sl // 2],
+              "silence": np.zeros(30000, np.float32)}
+        spike = t.copy()
+        spike[5] = 60.0                      # the energy gate of detectPreamble fails -> detectPreambleCrossCorr fallback (modem.js:983-987)
+        lb["spike_fallback"] = spike
+        for k, v in lb.items():
+            if narrow and k in ("multipath_12db", "awgn_3db", "spike_fallback"):
+                continue
+            add("loopback/" + k, mode, "loopback", x=np.ascontiguousarray(v, np.float32))
         # ---- decodeChunkFrame (modem.js:770-849): the edge frames of tests/test_gpu_parity.py::test_decode_chunk_frames
         lead = 2205 - 4
         frames = {
@@ -119,6 +136,8 @@ def build_cases(O, quick=False):
     f = O.buildDataChunkFrame(cfg, O.randomBytes(5, 512), 0, mod, rep)
     add("stream/c4_noise_floor_then_frame", "BPSK-NARROW", "stream",
         x=pad_blocks(np.concatenate([quiet, O.addAwgn(f, 10 ** (-30 / 20), 8)])))
+    # ---- BASELINE config 1 at full size: buildTransmitSignal(32 KB, QPSK) -> decodeReceivedSignal (392,418 samples, noise-free)
+    add("decode/c1_32kb_loopback", "QPSK", "decode", x=O.buildTransmitSignal("standard", O.randomBytes(1, 32768), "QPSK", "file", 1))
     # ---- integer / table functions
     add("misc/tables", "QPSK", "misc", bytes_a=O.randomBytes(3, 4107), bits_a=(O.randomBytes(4, 999) & 1).astype(np.uint8),
         fft_re=np.random.default_rng(7).standard_normal(512).astype(np.float32), fft_im=np.random.default_rng(8).standard_normal(512).astype(np.float32))
@@ -157,9 +176,18 @@ def oracle_outputs(O, case):
         sl = O.config(cfg)["SYMBOL_LEN"]
         ce = O.generateChannelEstSymbol(cfg)
         h_re, h_im = O.estimateChannel(cfg, x[2 * sl: 3 * sl], ce["knownRe"], ce["knownIm"])
-        bits = O.demodulateOFDM(cfg, x[3 * sl:], mod, h_re, h_im)
+        bits, eq = O.demodulateOFDM(cfg, x[3 * sl:], mod, h_re, h_im, with_eq=True)
+        eq = np.ascontiguousarray(eq, np.float64)
         return {"H_sha256": sha(np.concatenate([h_re, h_im])), "H_first": [float(h_re[O.config(cfg)["SUB_START"]]), float(h_im[O.config(cfg)["SUB_START"]])],
-                "bits_sha256": sha(np.asarray(bits, np.uint8)), "n_bits": int(len(bits))}
+                "bits_sha256": sha(np.asarray(bits, np.uint8)), "n_bits": int(len(bits)),
+                # the equalised, phase-corrected points handed to constellationDemap (modem.js:410-412), as (re, im) float64 pairs
+                "eq_sha256": sha(eq), "eq_n": int(len(eq)), "eq_first": [float(v) for v in eq[:3].ravel()]}
+    if kind == "loopback":
+        r = O.analyzeLoopback(cfg, inp["x"], mod, rep)
+        mags = np.asarray(r.pop("channelMagnitude"), np.float64)
+        r.pop("startIdx", None)
+        r.update(channelMagnitude_sha256=sha(mags), channelMagnitude_n=int(len(mags)))
+        return r
     if kind == "modulate":
         bits = inp["bits"]
         sym = O.modulateOFDM(cfg, bits, mod)

@@ -69,10 +69,25 @@ def test_batch_operators_equal_the_reference(amb, cases, mode):
                 h_re, h_im = m.estimate_channel([x[2 * sl: 3 * sl]])
                 hh = np.concatenate([np.asarray(h_re[0], np.float64), np.asarray(h_im[0], np.float64)])
                 assert hashlib.sha256(hh.tobytes()).hexdigest() == want["H_sha256"], (mode, "H is not bit-identical to the reference's")
-                bits = m.demodulate([x[3 * sl:]], h_re, h_im)[0]
-                bits = np.asarray(bits, np.uint8)[: want["n_bits"]]
+                bits, eq = m.demodulate([x[3 * sl:]], h_re, h_im, with_eq=True)
+                bits = np.asarray(bits[0], np.uint8)[: want["n_bits"]]
                 assert hashlib.sha256(bits.tobytes()).hexdigest() == want["bits_sha256"], (mode, "demodulateOFDM bits")
-                n += 2
+                # the equalised points the reference hands to constellationDemap (north star: within 1e-4 relative; here bit-identical)
+                eq = np.ascontiguousarray(np.asarray(eq[0], np.float64)[: want["eq_n"]])
+                assert len(eq) == want["eq_n"]
+                assert np.allclose(eq[:3].ravel(), want["eq_first"], rtol=1e-4, atol=0)
+                assert hashlib.sha256(eq.tobytes()).hexdigest() == want["eq_sha256"], (mode, "equalised points are not bit-identical to the reference's")
+                n += 3
+            elif c["kind"] == "loopback":
+                want = _check_inputs(c)
+                lb = m.analyze_loopback([c["inputs"]["x"]])[0]
+                mags = np.asarray(lb.pop("channelMagnitude"), np.float64)
+                lb.pop("startIdx", None)
+                assert (hashlib.sha256(mags.tobytes()).hexdigest(), len(mags)) == (want["channelMagnitude_sha256"], want["channelMagnitude_n"]), (mode, c["name"])
+                for k, v in lb.items():
+                    w = want[k]
+                    assert (abs(v - w) <= 1e-12 * abs(w) if isinstance(w, float) else v == w), (mode, c["name"], k, v, w)
+                n += 1
             elif c["kind"] == "modulate":
                 want = _check_inputs(c)
                 amb.setOFDMConfig(cfg)

@@ -22,13 +22,25 @@ function __runCase(c) {
     } else if (c.kind === 'ops') {
         var ce = generateChannelEstSymbol();
         var h = estimateChannel(inp.x.subarray(2 * SL, 3 * SL), ce.knownRe, ce.knownIm);
+        var eqs = [], realDemap = constellationDemap;
+        constellationDemap = function (cc, cr, ci) { eqs.push(cr, ci); return realDemap(cc, cr, ci); };   // the points demodulateOFDM hands to the demapper
         var bits = demodulateOFDM(inp.x.subarray(3 * SL), mod, h[0], h[1]);
+        constellationDemap = realDemap;
+        var eqa = Float64Array.from(eqs);
+        out.eq_sha256 = __sha256(__bytes_of(eqa)); out.eq_n = eqs.length / 2; out.eq_first = eqs.slice(0, 6);
         var hh = new Float64Array(2 * OFDM.FFT_SIZE);
         hh.set(h[0], 0); hh.set(h[1], OFDM.FFT_SIZE);
         out.H_sha256 = __sha256(__bytes_of(hh));
         out.H_first = [h[0][OFDM.SUB_START], h[1][OFDM.SUB_START]];
         out.bits_sha256 = __sha256(Uint8Array.from(bits));
         out.n_bits = bits.length;
+    } else if (c.kind === 'loopback') {
+        var fx = new Uint8Array(16);
+        for (var q = 0; q < 16; q++) fx[q] = q;
+        var lb = analyzeLoopback(inp.x, mod, rep, fx);
+        var mags = Float64Array.from(lb.channelMagnitude);
+        out = { detected: lb.detected, correlation: lb.correlation, ber: lb.ber, snrEstimate: lb.snrEstimate, quality: lb.quality,
+            channelMagnitude_sha256: __sha256(__bytes_of(mags)), channelMagnitude_n: mags.length };
     } else if (c.kind === 'modulate') {
         var b = Array.from(inp.bits);
         var r = modulateOFDM(b, mod);
@@ -86,6 +98,6 @@ function __runCase(c) {
 }
 function __runCases() {
     var res = {};
-    __cases.forEach(function (c) { res[c.mode + ':' + c.name] = __runCase(c); });
+    __cases.forEach(function (c) { var t0 = Date.now(); var r = __runCase(c); r.__ms = Date.now() - t0; res[c.mode + ':' + c.name] = r; });
     return res;
 }

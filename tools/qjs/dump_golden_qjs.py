@@ -141,7 +141,12 @@ def dump_cases(ref_dir, quick=False, out_name="reference_cases.json"):
             js_cases.append({"name": c["name"], "mode": c["mode"], "kind": c["kind"], "args": c["args"], "inputs": inputs})
         t0 = time.time()
         prog = prelude + "\n" + ref + "\nvar __cases = " + json.dumps(js_cases) + ";\n" + body + "\n__out = JSON.stringify(__runCases());\n"
-        out["cases"].update(json.loads(run_js(prog, "cases_prog")))
+        got = json.loads(run_js(prog, "cases_prog"))
+        for c in cs:                                   # engine wall time per case goes to a side table (not a parity value)
+            key = c["mode"] + ":" + c["name"]
+            n_samples = int(sum(len(a) for k, a in c["inputs"].items() if k == "x"))
+            out.setdefault("engine_ms", {})[key] = {"ms": got[key].pop("__ms"), "samples": n_samples}
+        out["cases"].update(got)
         print(f"{mode} {'stream' if is_stream else 'batch'}: {len(cs)} cases in {time.time() - t0:.0f} s", file=sys.stderr)
     json.dump(out, open(os.path.join(GOLD, out_name), "w"), indent=1, sort_keys=True)
     print("wrote tests/golden/" + out_name, len(out["cases"]), "cases")
