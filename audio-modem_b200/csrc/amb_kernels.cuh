@@ -1456,8 +1456,24 @@ __global__ void k_apply_xform(const float* __restrict__ x, int64_t stride, const
     AMB_SPLIT_BID(per, r, blk)
     const int64_t n = lens ? lens[r] : n_default;
     const AmbXform f = xf[r];
-    for (int64_t i = (int64_t)blk * blockDim.x + threadIdx.x; i < n; i += (int64_t)per * blockDim.x)
-        out[(int64_t)r * stride + i] = amb_xform(f, x[(int64_t)r * stride + i]);
+    const float* xr = x + (int64_t)r * stride;
+    float* orow = out + (int64_t)r * stride;
+    if (((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(orow)) & 15) == 0) {
+        // 128-bit path: a CTA takes spans of 2048 consecutive samples, a thread two float4 of each (both loads issued before the
+        // arithmetic: float64 subtraction and an IEEE float32 division per sample, modem.js:221-229)
+        const int64_t n4 = n >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        float4* o4 = reinterpret_cast<float4*>(orow);
+        for (int64_t q = (int64_t)blk * 512 + threadIdx.x; q < n4; q += (int64_t)per * 512) {
+            const bool two = q + 256 < n4;
+            const float4 a = x4[q], b = two ? x4[q + 256] : make_float4(0.f, 0.f, 0.f, 0.f);
+            o4[q] = make_float4(amb_xform(f, a.x), amb_xform(f, a.y), amb_xform(f, a.z), amb_xform(f, a.w));
+            if (two) o4[q + 256] = make_float4(amb_xform(f, b.x), amb_xform(f, b.y), amb_xform(f, b.z), amb_xform(f, b.w));
+        }
+        if (blk == 0) for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) orow[i] = amb_xform(f, xr[i]);
+        return;
+    }
+    for (int64_t i = (int64_t)blk * blockDim.x + threadIdx.x; i < n; i += (int64_t)per * blockDim.x) orow[i] = amb_xform(f, xr[i]);
 }
 
 // Schmidl-Cox metric of a recording (modem.js:304-309), float64, gate = min_energy.
