@@ -78,7 +78,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf nan_pos, tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, l_startA, xc_peak, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
     int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
@@ -360,8 +360,8 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
             }
             for (int di = 0; di < T.n_data; di++) ft.role[T.data_k[di] - T.sub_start] = di;
         }
-        if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 8) != cudaSuccess) return bail(AMB_E_NOMEM);
-        if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 8) != cudaSuccess) return bail(AMB_E_CUDA);
+        if (cudaMalloc(&m->d_fast, sizeof(ft)) != cudaSuccess || cudaMalloc(&m->d_fallbacks, 32) != cudaSuccess) return bail(AMB_E_NOMEM);
+        if (cudaMemcpy(m->d_fast, &ft, sizeof(ft), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(m->d_fallbacks, 0, 32) != cudaSuccess) return bail(AMB_E_CUDA);
         std::vector<uint32_t> ops((size_t)AMB_CRC_MAXL * AMB_CRC_OPS, 0u);
         for (int L = 0; L < AMB_CRC_MAXL; L++) {
             for (int k = 0; k < 32; k++) ops[(size_t)L * AMB_CRC_OPS + k] = amb_gf_xpow8((uint32_t)(L * k));
@@ -425,7 +425,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -462,6 +462,13 @@ int64_t amb_debug_counter(amb_modem* m, int which) {
         return (int64_t)v[which - 16];
     }
 #endif
+    if (which == 6 || which == 7) {
+        // phase-B links answered by phase A's own walk (6) and walked again (7), cumulative
+        unsigned long long v = 0;
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpy(&v, m->d_fallbacks + (which - 5), 8, cudaMemcpyDeviceToHost);
+        return (int64_t)v;
+    }
     if (which == 2) return m->link_iterations;
     if (which == 3) return m->link_passes;
     if ((which == 4 || which == 5) && m->open) {
@@ -862,7 +869,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(m->tile_slot.ensure(ns * m->sum_stride * 4)); CK(m->tri.ensure((size_t)m->slot_cap * 256 * 3 * 8));
     CK(m->slot_info.ensure((size_t)m->slot_cap * 16)); CK(m->slot_count.ensure(16)); CK(m->tsum.ensure((size_t)m->slot_cap * 16)); CK(m->cand_list.ensure((size_t)m->slot_cap * 4));
     CK(m->defect.ensure(ns * m->calls_stride * 3 * 8)); CK(m->fpre.ensure(ns * m->calls_stride * 3 * 8)); CK(m->cold_tag.ensure(ns * m->calls_stride * 4));
-    CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4));
+    CK(m->xc.ensure((size_t)m->slot_cap * m->xc_w * 4)); CK(m->xc_peak.ensure((size_t)m->slot_cap * 8));
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMB_XC_SMEM(AMB_XC_MAXW + 768));
@@ -876,6 +883,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
         CK(m->l_next.ensure(nr * 4)); CK(m->l_vis.ensure(nr)); CK(m->l_ja.ensure(nr * 4)); CK(m->l_jb.ensure(nr * 4));
         CK(m->l_linkrun.ensure(nl * 4)); CK(m->l_outB.ensure(nl * sizeof(AmbStreamState))); CK(m->l_recB.ensure(nl * sizeof(AmbFrameRec)));
         CK(m->l_hasB.ensure(nl * 4)); CK(m->l_memo.ensure(nr * sizeof(AmbRefineMemo)));
+        CK(m->l_startA.ensure(nr * sizeof(AmbStartA)));
         CK(m->l_bmout.ensure(nr * sizeof(AmbStreamState))); CK(m->l_bmrec.ensure(nr * sizeof(AmbFrameRec))); CK(m->l_bmhas.ensure(nr * 4));
         CK(m->l_first.ensure(ns * sizeof(AmbStreamState))); CK(m->l_firstflag.ensure(ns * 4)); CK(m->l_firststop.ensure(ns * 4)); CK(m->l_fpsum.ensure(ns * 8));
     }
@@ -907,7 +915,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     m->open = false;
     m->file_cap = 0;
@@ -960,7 +968,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     AmbScanStore ss;
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.sum_stride = m->sum_stride; ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
-    ss.tsum = m->tsum.as<float>(); ss.cand_list = m->cand_list.as<int32_t>();
+    ss.tsum = m->tsum.as<float>(); ss.cand_list = m->cand_list.as<int32_t>(); ss.xc_peak = m->xc_peak.as<unsigned long long>();
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
     CK(cudaMemsetAsync(m->slot_count.p, 0, 8, m->stream));          // [0] slots, [1] slots holding a candidate
@@ -1016,6 +1024,9 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     static const bool xc_store_on = !(std::getenv("AMB_XC_STORE") && std::getenv("AMB_XC_STORE")[0] == '0');
     g.tile_slot = m->tile_slot.as<int32_t>(); g.tri = m->tri.as<double>(); g.xc = xc_store_on ? m->xc.as<float>() : nullptr; g.xc_w = m->xc_w; g.slot_info = m->slot_info.as<int32_t>(); g.tsum = m->tsum.as<float>();
     g.F = m->fpre.as<double>(); g.calls_stride = m->calls_stride;
+    // AMB_PREDICT=0 (comparison runs): phase A starts every run from the synthetic state, phase B walks every link
+    static const bool predict_on = !(std::getenv("AMB_PREDICT") && std::getenv("AMB_PREDICT")[0] == '0');
+    g.xc_peak = (xc_store_on && predict_on) ? m->xc_peak.as<unsigned long long>() : nullptr;
     // idle-call screening (k_cold_calls) pays when pushes are long; AMB_COLD_CALLS=0 switches it off (comparison runs)
     static const bool cold_on = !(std::getenv("AMB_COLD_CALLS") && std::getenv("AMB_COLD_CALLS")[0] == '0');
     const bool use_cold = cold_on && n_new / m->block_len >= 64;
@@ -1037,7 +1048,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
         if (xc_store_on) LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
                                                                                      m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w,
-                                                                                     xc_skip_on ? m->tile_slot.as<int32_t>() : nullptr, off0 / 256, (off0 + n_new) / 256));
+                                                                                     xc_skip_on ? m->tile_slot.as<int32_t>() : nullptr, off0 / 256, (off0 + n_new) / 256,
+                                                                                     m->xc_peak.as<unsigned long long>()));
     }
     int n_out = 0;
     int n_todo = ns;
@@ -1061,6 +1073,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     L.link_run = m->l_linkrun.as<int>(); L.outB = m->l_outB.as<AmbStreamState>(); L.recB = m->l_recB.as<AmbFrameRec>(); L.hasB = m->l_hasB.as<int>();
     L.first_out = m->l_first.as<AmbStreamState>(); L.first_flag = m->l_firstflag.as<int>(); L.first_stop = m->l_firststop.as<int>();
     L.fp_sum = m->l_fpsum.as<unsigned long long>(); L.memo = m->l_memo.as<AmbRefineMemo>();
+    L.startA = g.xc_peak ? m->l_startA.as<AmbStartA>() : nullptr; L.stats = m->d_fallbacks + 1;
     L.bm_out = m->l_bmout.as<AmbStreamState>(); L.bm_rec = m->l_bmrec.as<AmbFrameRec>(); L.bm_has = m->l_bmhas.as<int>();
     const int64_t max_links = (int64_t)ns * m->run_cap + ns;
     const int walk_grid = (int)(blocks_for(max_links, 4) < m->walk_ctas ? blocks_for(max_links, 4) : m->walk_ctas);

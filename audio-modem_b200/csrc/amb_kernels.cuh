@@ -100,6 +100,7 @@ struct AmbScanStore {
     int slot_cap;
     float* tsum;             // [slot_cap][4] exact extremes of the slot's windows (amb_slot_cold)
     int32_t* cand_list;      // [slot_cap] slots holding a candidate, in no particular order; their number is slot_count[1]
+    unsigned long long* xc_peak;   // [slot_cap] maximum of the slot's screening row (k_xcorr_store; amb_xc_peak_key), 0 = none
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
             st.tile_slot[(int64_t)s * st.sum_stride + tile] = slot | (any ? AMB_TS_CAND : 0) | (rows ? AMB_TS_ROWS : 0);
             st.slot_info[slot * 4 + 3] = c_lo | (c_hi << 16);               // candidate windows span [c_lo, c_hi]
             if (any && st.cand_list) st.cand_list[atomicAdd(st.slot_count + 1, 1)] = slot;
+            if (st.xc_peak) st.xc_peak[slot] = 0ull;
         }
     }
 }
@@ -542,6 +544,7 @@ struct AmbStreamGeom {
     // stores of the scan kernels (see AmbWalkGeom)
     const int32_t* tile_slot; const double* tri; const float* xc; int xc_w;
     const int32_t* slot_info; const float* tsum;
+    const unsigned long long* xc_peak;   // [slot] maximum of the screening row (amb_xc_peak_key), 0 = none; or NULL
     const double* F; int64_t calls_stride;
     const int32_t* cold_tag;   // [n_streams][calls_stride] (k_cold_calls), or NULL
 };
@@ -2376,13 +2379,25 @@ __global__ void __launch_bounds__(256) k_defect_scan(const double* __restrict__ 
 #define AMB_XC_PADI(i) ((i) + (((i) >> 4) << 2))
 #define AMB_XC_SQI(i) ((i) + ((i) >> 4))                 // prefix of squares: one double of padding per 16 (the epilogue reads it 16 apart)
 #define AMB_XC_SMEM(L) ((size_t)((L) + 2 * (AMB_XC_PADI(L) + 4) + 512) * 4 + (size_t)(AMB_XC_SQI(L) + 2) * 8 + 64)
+// (screening value, offset) of a row's maximum as one ordered 64-bit key: larger value first, then the smaller offset
+__device__ __forceinline__ unsigned long long amb_xc_peak_key(float v, int o) {
+    const unsigned u = __float_as_uint(v);
+    const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned)(0x7fffffff - o);
+}
+__device__ __forceinline__ float amb_xc_peak_value(unsigned long long key) {
+    const unsigned ord = (unsigned)(key >> 32);
+    return __uint_as_float((ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord);
+}
+__device__ __forceinline__ int amb_xc_peak_offset(unsigned long long key) { return 0x7fffffff - (int)(unsigned)(key & 0xffffffffu); }
 __device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
 __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                       const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count,
                                                       const int32_t* __restrict__ cand_list, int slot_cap, float* __restrict__ xc, int xc_w,
-                                                      int32_t* __restrict__ tile_slot_rw, int64_t tile_lo, int64_t tile_hi) {
+                                                      int32_t* __restrict__ tile_slot_rw, int64_t tile_lo, int64_t tile_hi,
+                                                      unsigned long long* __restrict__ xc_peak) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_cand = min(slot_count[1], slot_cap);
     // A preamble's candidate windows (metric > 0.5) usually spread over two adjacent tiles, but the coarse position the walker
@@ -2486,6 +2501,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
         for (int i = tid; i < xc_w; i += nt) if (i < o_lo || i >= o_hi) out[i] = AMB_XC_UNSURE;
         const int par = (lane >> 4) & 1;
         const float* tpar = tp + 256 * par;
+        unsigned long long peak = 0ull;                                  // this thread's best (value, first offset) of the row
         for (int blk = (o_lo >> 4) + warp * 16 + (lane & 15); 16 * blk < o_hi; blk += nwarps * 16) {
             float2 acc2[AMB_XC_PER];
 #pragma unroll
@@ -2534,7 +2550,14 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
                 else if (d2 < 1e-6f * (1.f - 2e-4f)) v = AMB_XC_FAIL;
                 else v = AMB_XC_UNSURE;
                 out[o] = v;
+                if (v > -1.5f && v < 1.5f) { const unsigned long long key = amb_xc_peak_key(v, o); if (key > peak) peak = key; }
             }
+        }
+        if (xc_peak) {
+            // the row's maximum: where phase A expects the frame of the run BEFORE its own to start (k_link_walk)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, peak, o); if (u > peak) peak = u; }
+            if (lane == 0 && peak) atomicMax(xc_peak + cur, peak);
         }
     }
 }
@@ -2544,6 +2567,7 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
 // metadata frame take this path; the others are walked one frame per pass by k_walk (their pre-metadata behaviour
 // re-scans inside frames and does not speculate well, and it ends with the first metadata frame).
 // ================================================================================================
+struct AmbStartA { int64_t pos, call, false_pos; };
 struct AmbLinkBufs {
     AmbRun* runs;            // [n_streams][run_cap]
     int* n_runs;             // [n_streams]
@@ -2567,6 +2591,10 @@ struct AmbLinkBufs {
     // the successor next[p] are fixed), and a chain rebuilt after a failed speculation mostly consists of the same links: the
     // outcome is kept per flat run index p and reused by later iterations.  bm_has: 0 = not walked yet, 1 + has otherwise.
     AmbStreamState* bm_out; AmbFrameRec* bm_rec; int* bm_has;
+    // Start state phase A gave run p (per flat run index): where the scan was re-initialised, in which call, and the refine
+    // failures counted so far.  A phase-B link whose exact start state is that very state has been walked already - by phase A.
+    struct AmbStartA* startA;
+    unsigned long long* stats;   // [0] phase-B links answered by phase A's walk, [1] walked again
     int trace_iter;          // development (-DAMB_WALK_STATS): launch sequence number recorded in the walk trace
 };
 
@@ -2654,6 +2682,32 @@ __device__ __forceinline__ int stream_of_flat(const int* __restrict__ off, int n
     return lo;
 }
 
+// Where phase A lets run r's walk begin.  The receiver reaches a run from the end of the frame before it (app.js:974-981: the
+// scan restarts at the frame end), and in a dense stream that frame is the one whose preamble made the run before: its start is
+// where that run's screening rows peak (k_xcorr_store), its length follows from the metadata in force.  Starting phase A in
+// exactly the state the receiver will be in makes the walk the real one, not a speculation: phase B then only compares states.
+// Returns the predicted frame end, or -1 (no earlier run in reach, no clear peak: the synthetic start of amb_run_start_state).
+__device__ __forceinline__ int64_t amb_predict_scan_start(const AmbTables* __restrict__ T, const AmbStreamGeom& g, int s, const AmbStreamState& flags,
+                                                          const AmbRun& prev, const AmbRun& run) {
+    if (!g.xc_peak || !g.tile_slot || !flags.meta_received) return -1;
+    const int64_t t_first = (prev.first_pos + 511 - g.base_g) >> 8, t_last = (prev.last_pos + 256 - g.base_g) >> 8;
+    if (t_first < 0 || t_last >= g.sum_stride || t_last - t_first > 8) return -1;
+    unsigned long long best = 0ull;
+    int64_t best_t = -1;
+    for (int64_t t = t_first; t <= t_last; t++) {
+        const int raw = g.tile_slot[(int64_t)s * g.sum_stride + t];
+        if (raw < 0 || !(raw & AMB_TS_CAND) || (raw & AMB_TS_NOXC)) continue;
+        const unsigned long long key = g.xc_peak[raw & AMB_TS_MASK];
+        if ((key >> 32) > (best >> 32)) { best = key; best_t = t; }
+    }
+    if (best_t < 0 || !(amb_xc_peak_value(best) > 0.3f)) return -1;
+    const int64_t start = g.base_g + (best_t << 8) - 511 - T->fine_radius + amb_xc_peak_offset(best);
+    const int64_t end = start + amb_frame_samples(T, (int64_t)(flags.chunk_size ? flags.chunk_size : 4096) + 11);
+    // the frame must end before the run does (else the chain skips the run), and not more than 32 calls ahead of it
+    if (end > run.last_pos || end < run.first_pos - 32 * g.block_len) return -1;
+    return end;
+}
+
 // One warp per link (grid-stride; the totals live on the device so no host round trip sizes the launch).
 // mode 0 (phase A): flat run index f < total_runs: synthetic start before the run.  f - total_runs < n_todo: the FIRST
 //   link of the pass for one stream, from its carried state (which may be mid-frame); its end state goes to first_out
@@ -2720,9 +2774,51 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         }
         if (mode == 1 && L.link_run[f] >= 0) G.memo_in = L.memo + L.run_off[s] + L.link_run[f];
         if (first) {}
-        else if (mode == 0) st = amb_run_start_state(states[s], L.runs[(int64_t)s * L.run_cap + i], G);
+        else if (mode == 0) {
+            const AmbRun* rr = L.runs + (int64_t)s * L.run_cap;
+            st = amb_run_start_state(states[s], rr[i], G);
+            if (L.startA) {
+                int64_t e = -1, call_min = 0;
+                if (i > 0) e = amb_predict_scan_start(T, g, s, st, rr[i - 1], rr[i]);
+                else {
+                    // the first run of the push: the frame before it is the one the stream is collecting (or has just finished)
+                    const AmbStreamState& cs = states[s];
+                    if (cs.state == AMB_RX_COLLECT) { e = cs.frame_end; call_min = cs.next_call + 1; }
+                    else if (cs.state == AMB_RX_IDLE && !cs.ac_init) { e = cs.ac_scan_pos; call_min = cs.next_call; }
+                    if (e > rr[i].last_pos || e < rr[i].first_pos - 32 * g.block_len) e = -1;
+                }
+                if (e >= 0) {
+                    st.ac_scan_pos = e; st.next_call = (e + g.block_len - 1) / g.block_len;
+                    if (st.next_call < call_min) st.next_call = call_min;
+                    if (i == 0 && states[s].state == AMB_RX_IDLE) st.next_call = states[s].next_call;
+                }
+                if (lane == 0 && writer) { AmbStartA sa; sa.pos = st.ac_scan_pos; sa.call = st.next_call; sa.false_pos = st.false_pos; L.startA[f] = sa; }
+            }
+        }
         else if (i == 0) st = states[s];
         else st = L.endA[L.run_off[s] + L.link_run[f - 1]];
+        if (mode == 1 && L.startA && L.link_run[f] >= 0) {
+            // phase A walked this run from the very state the link starts in, found a frame and counted no refine failure on the
+            // way: its record and end state are the link's (the fields a walk never touches are carried over from the start state)
+            const int fa = L.run_off[s] + L.link_run[f];
+            const AmbStartA sa = L.startA[fa];
+            if (L.hasA[fa] == 1 && st.state == AMB_RX_IDLE && !st.ac_init && st.pre_pos == -1 && st.frame_end == -1 && st.ac_scan_pos == sa.pos &&
+                st.next_call == sa.call) {
+                const AmbStreamState ea = L.endA[fa];
+                if (ea.false_pos == sa.false_pos && ea.meta_received == st.meta_received && ea.chunk_size == st.chunk_size) {
+                    if (lane == 0 && writer) {
+                        AmbStreamState so = ea;
+                        amb_carry_unwalked(so, st);
+                        AmbFrameRec rb = L.recA[fa];
+                        rb.snap = so;
+                        L.outB[f] = so; L.hasB[f] = 1; L.recB[f] = rb;
+                        if (L.stats) atomicAdd(L.stats, 1ull);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
+        }
         AmbSig sig;
         sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
         sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
@@ -2748,6 +2844,7 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         }
 #endif
         if (team) __syncthreads();                       // every warp of the team has read what the block below overwrites (bm_has)
+        if (lane == 0 && writer && mode == 1 && L.stats) atomicAdd(L.stats + 1, 1ull);
         if (lane == 0 && writer) {
             if (first) {
                 st.dc_mean = dc_next[s]; st.written = g.avail_hi;
@@ -2802,16 +2899,31 @@ __global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float
         const int off = L.run_off[s], lo_f = off + s;
         // governing link: the last one whose re-initialisation call is before k (binary search; link 0 starts from the current
         // state, link i from the phase-A end state of the run before it)
-        int a = 0, b = n_links - 1;
-        while (a < b) {
-            const int mid = (a + b + 1) >> 1;
-            const int64_t c = amb_link_init_call(L.endA[off + L.link_run[lo_f + mid - 1]], g.block_len);
-            if (c >= 0 && c < k) a = mid; else b = mid - 1;
+        int a = 0;
+        int64_t c;
+        if (n_links <= 33) {
+            // lane l looks at link l + 1: one round of loads instead of a dependent chain
+            const int l1 = lane + 1;
+            int64_t cl = -1;
+            if (l1 < n_links) cl = amb_link_init_call(L.endA[off + L.link_run[lo_f + l1 - 1]], g.block_len);
+            const unsigned bal = __ballot_sync(0xffffffffu, cl >= 0 && cl < k);
+            a = bal ? 32 - __clz((int)bal) : 0;
+            c = __shfl_sync(0xffffffffu, cl, a > 0 ? a - 1 : 0);
+            if (a == 0) c = amb_link_init_call(cur, g.block_len);
+        } else {
+            int b = n_links - 1;
+            while (a < b) {
+                const int mid = (a + b + 1) >> 1;
+                const int64_t cm = amb_link_init_call(L.endA[off + L.link_run[lo_f + mid - 1]], g.block_len);
+                if (cm >= 0 && cm < k) a = mid; else b = mid - 1;
+            }
+            c = amb_link_init_call(a == 0 ? cur : L.endA[off + L.link_run[lo_f + a - 1]], g.block_len);
         }
-        const int64_t c = amb_link_init_call(a == 0 ? cur : L.endA[off + L.link_run[lo_f + a - 1]], g.block_len);
         const int64_t F0 = g.base_g / g.block_len;
         const int64_t fc = c - F0, fk = k - F0;
         if (c < 0 || c >= k || fc < 0 || fk >= g.calls_stride) continue;
+        // tagged cold under this very hypothesis by an earlier iteration of the pass (the chain behind the first link rarely changes)
+        if (cold_tag[(int64_t)s * g.calls_stride + fk] == (int32_t)c) continue;
         const double* F = g.F + (int64_t)s * g.calls_stride * 3;
         const double Ep = F[fk * 3] - F[fc * 3], Ea = F[fk * 3 + 1] - F[fc * 3 + 1], Eb = F[fk * 3 + 2] - F[fc * 3 + 2];
         AmbWalkGeom G;

@@ -9,7 +9,8 @@
 extern "C" {
 #endif
 /* development counters: 0 kernel launches, 1 data symbols redone by the float64-faithful fallback of the fast
- * demodulator, 2 link-resolution iterations, 3 link-resolution passes, 4 slotted tiles and 5 candidate tiles of the last push */
+ * demodulator, 2 link-resolution iterations, 3 link-resolution passes, 4 slotted tiles and 5 candidate tiles of the last push,
+ * 6 phase-B links answered by phase A's own walk (its start state was the exact one), 7 phase-B links walked again */
 int64_t amb_debug_counter(amb_modem* m, int which);
 /* copies the last push's per-slot records to host memory (which = 0: {stream, arena tile, flags, candidate span} int32 x 4;
  * which = 1: {max metric, min Ra, min Rb, excluded} float x 4); returns the slot count */

@@ -1003,6 +1003,14 @@ AMB_HD AmbStreamState amb_run_start_state(const AmbStreamState& flags_from, cons
     return s;
 }
 
+// the fields of a stream state that a walk never writes (flags, frame counters, the carried mean) plus the running count of
+// refine failures, taken over from `from`: what a walk started in `from` would hand on
+AMB_HD void amb_carry_unwalked(AmbStreamState& dst, const AmbStreamState& from) {
+    dst.meta_received = from.meta_received; dst.chunk_size = from.chunk_size; dst.total_chunks = from.total_chunks; dst.total_file_size = from.total_file_size;
+    dst.frames_decoded = from.frames_decoded; dst.frame_errors = from.frame_errors; dst.false_pos = from.false_pos; dst.received = from.received;
+    dst.crc_errors = from.crc_errors; dst.dups = from.dups; dst.dc_mean = from.dc_mean; dst.written = from.written;
+}
+
 // first run with windows at or after position e (runs are sorted by position); n if none
 AMB_HD int amb_run_at_or_after(const AmbRun* runs, int n, int64_t e) {
     int lo = 0, hi = n;

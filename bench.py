@@ -493,7 +493,8 @@ def run_c2(ctx, clocks):
     prof_steps = min(args.steps, 4)
     prof, prof_ms = profile_pass(ctx, m, step, prof_steps, n_done + 2)
     slots = {"slotted_tiles_per_frame": m.debug_counter(4) / F, "candidate_tiles_per_frame": m.debug_counter(5) / F,
-             "link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
+             "link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3)),
+             "phase_b_links_taken_from_phase_a": m.debug_counter(6), "phase_b_links_walked": m.debug_counter(7)}
 
     # end-to-end: host buffers (page-locked), H2D of the samples + D2H of results and decoded bytes inside the timed region
     host = amb.modem.pinned_empty((1, step_samples), np.float32)
@@ -653,7 +654,8 @@ def run_c5(ctx, clocks, ns=None, light=False):
                 "payload_mb_per_s": tot["payloadBytes"] / (total_ms / 1e3) / 1e6}
     prof_steps = period
     prof, prof_ms = profile_pass(ctx, m, step, prof_steps, k0 + n_done)
-    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
+    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3)),
+             "phase_b_links_taken_from_phase_a": m.debug_counter(6), "phase_b_links_walked": m.debug_counter(7)}
     # end-to-end: the whole period in page-locked host memory, one contiguous [n_streams][push] block per push (the layout a
     # caller feeding concurrent streams hands over)
     # (several ranks share the host: with N > 1 only two pushes of the period are kept in page-locked memory and alternated - 3.8
@@ -779,7 +781,8 @@ def run_c4(ctx, clocks):
     assert c1["framesDecoded"] - c0["framesDecoded"] >= n_done * (n_frames - 1), (c0, c1)
     prof_steps = min(steps, 2)
     prof, prof_ms = profile_pass(ctx, m, step, prof_steps, 1 + n_done)
-    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3))}
+    iters = {"link_iterations_per_push": m.debug_counter(2) / max(1, m.debug_counter(3)),
+             "phase_b_links_taken_from_phase_a": m.debug_counter(6), "phase_b_links_walked": m.debug_counter(7)}
     host = amb.modem.pinned_empty((1, N), np.float32)
     hx = host.array
     hx[...] = x.cpu().numpy()
