@@ -78,7 +78,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf nan_pos, tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, l_startA, xc_peak, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, l_startA, xc_peak, cold_list, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
     int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
@@ -425,7 +425,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -915,7 +915,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     m->open = false;
     m->file_cap = 0;
@@ -969,6 +969,9 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     ss.tile_slot = m->tile_slot.as<int32_t>(); ss.sum_stride = m->sum_stride; ss.tri = m->tri.as<double>(); ss.slot_info = m->slot_info.as<int32_t>();
     ss.slot_count = m->slot_count.as<int>(); ss.slot_cap = m->slot_cap; ss.defect = m->defect.as<double>(); ss.calls_stride = m->calls_stride;
     ss.tsum = m->tsum.as<float>(); ss.cand_list = m->cand_list.as<int32_t>(); ss.xc_peak = m->xc_peak.as<unsigned long long>();
+    // AMB_TRI_JUNK32=0 (comparison runs): every slotted tile gets its float64 window sums
+    static const bool junk32_on = !(std::getenv("AMB_TRI_JUNK32") && std::getenv("AMB_TRI_JUNK32")[0] == '0');
+    ss.junk32 = junk32_on ? 1 : 0;
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
     CK(cudaMemsetAsync(m->slot_count.p, 0, 8, m->stream));          // [0] slots, [1] slots holding a candidate
@@ -1118,10 +1121,16 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
             LAUNCH("k_chain_links", k_chain_links<<<ns, ns < 64 ? 1024 : 256, ns < 64 ? AMB_CHAIN_SMEM : 0, m->stream>>>(ns, m->states.as<AmbStreamState>(), L, ns < 64 ? AMB_CHAIN_SMEM_RUNS : 0));
             if (use_cold) {
                 const int64_t call_lo = m->written / m->block_len, call_hi = (m->written + n_new) / m->block_len;
-                const int64_t warps = (int64_t)ns * (call_hi - call_lo);
-                const int cgrid = (int)(blocks_for(warps, 4) < 148 * 32 ? blocks_for(warps, 4) : 148 * 32);
+                const int64_t calls = (int64_t)ns * (call_hi - call_lo);
+                CK(m->cold_list.ensure((size_t)calls * 16 + 16));
+                int* list_count = m->cold_list.as<int>();                   // [0] count (16 bytes), then the int4 entries
+                int4* list = reinterpret_cast<int4*>(m->cold_list.as<int>() + 4);
+                CK(cudaMemsetAsync(list_count, 0, 4, m->stream));
+                const int lgrid = (int)(blocks_for(calls, 256) < 148 * 8 ? blocks_for(calls, 256) : 148 * 8);
+                LAUNCH("k_cold_list", k_cold_list<<<lgrid, 256, 0, m->stream>>>(g, m->states.as<AmbStreamState>(), ns, L, m->cold_tag.as<int32_t>(), call_lo, call_hi, list_count, list));
+                const int cgrid = (int)(blocks_for(calls, 4) < 148 * 12 ? blocks_for(calls, 4) : 148 * 12);
                 LAUNCH("k_cold_calls", k_cold_calls<<<cgrid, 128, 0, m->stream>>>(g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(), ns, L,
-                                                                                  m->cold_tag.as<int32_t>(), call_lo, call_hi));
+                                                                                  m->cold_tag.as<int32_t>(), call_lo, call_hi, list_count, list));
             }
             L.trace_iter = (int)(m->link_iterations * 2 + 1);
             LAUNCH("k_link_walk_B", k_link_walk<false><<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),

@@ -101,6 +101,7 @@ struct AmbScanStore {
     float* tsum;             // [slot_cap][4] exact extremes of the slot's windows (amb_slot_cold)
     int32_t* cand_list;      // [slot_cap] slots holding a candidate, in no particular order; their number is slot_count[1]
     unsigned long long* xc_peak;   // [slot_cap] maximum of the slot's screening row (k_xcorr_store; amb_xc_peak_key), 0 = none
+    int junk32;              // k_tri_store settles the slots float32 can prove empty without the float64 sums (amb_tile_junk32)
     double* defect;          // [n_streams][calls_stride][3]  D_k of arena call k
     int64_t calls_stride;
 };
@@ -458,6 +459,73 @@ __global__ void __launch_bounds__(256) k_nan_fix(AmbFrontArgs a, int64_t n_new, 
 // The rest (most of them: the zero-padded last symbol of a chunk and the silence after it, flagged by the conservative
 // tile summary) are settled by their extremes alone (amb_slot_cold); should a large carried defect make the walker want
 // such a tile after all, it evaluates the windows itself (amb_eval_windows).
+// Float32 pre-test of a slotted tile (same register layout and scan scheme as amb_tile_sums_regs).  Most slots are not
+// preambles: the conservative summary of k_front flags every tile in which the signal level changes (the end of a frame, the
+// start of the next), and their windows have metrics around 1 / 256.  Where float32 can PROVE, for every window of the tile,
+// that both energies clear half the gate and the metric stays below 0.2, the slot is settled here: no candidate, no rows, and
+// the extremes the walker's amb_slot_cold needs as bounds (metric rounded up, energies rounded down by the error bound).
+// Error bound: a prefix goes through at most 15 float32 additions of non-negative terms (8 in the lane, 5 scan levels, segment
+// base, final difference) - relative error below 1e-6 of the prefix, i.e. below 1e-6 Q of the span's total energy Q for the
+// squares and, as |x y| <= (x^2 + y^2) / 2, for the products too; a window sum is a difference of two prefixes: 2e-6 Q.  The
+// test uses 4e-6 Q.  Returns true (warp-uniform) when the slot is settled.
+__device__ __forceinline__ float amb_warp_excl_scanf(float v, int lane, float* total) {
+    float inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ bool amb_tile_junk32(const float (&x)[3][8], int lane, int64_t g_first, const AmbScanStore& st, int slot, int s, int tile) {
+    if (!st.tsum || !st.junk32) return false;
+    float q[3][8], t[2][8], qb[3], tb[2];
+    float run_q = 0.f, run_t = 0.f;
+#pragma unroll
+    for (int seg = 0; seg < 3; seg++) {
+        float lq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { q[seg][k] = lq; lq = fmaf(x[seg][k], x[seg][k], lq); }
+        float tot;
+        const float off = amb_warp_excl_scanf(lq, lane, &tot);
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[seg][k] += off;
+        qb[seg] = run_q; run_q += tot;
+        if (seg < 2) {
+            float lt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { t[seg][k] = lt; lt = fmaf(x[seg][k], x[seg + 1][k], lt); }
+            const float offt = amb_warp_excl_scanf(lt, lane, &tot);
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[seg][k] += offt;
+            tb[seg] = run_t; run_t += tot;
+        }
+    }
+    const float delta = 4e-6f * run_q + 1e-30f;
+    float mup = 0.f, mnA = 3.0e38f, mnB = 3.0e38f;
+    bool ok = run_q - run_q == 0.f;                                    // (a NaN or an infinity among the samples: not here)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (g_first + 8 * lane + k < 0) continue;                       // (windows before the stream start do not exist)
+        const float P = fabsf((tb[1] + t[1][k]) - (tb[0] + t[0][k])) + delta;
+        const float A = (qb[1] + q[1][k]) - (qb[0] + q[0][k]) - delta, B = (qb[2] + q[2][k]) - (qb[1] + q[1][k]) - delta;
+        if (!(A > 0.00051f && B > 0.00051f)) ok = false;
+        mnA = fminf(mnA, A); mnB = fminf(mnB, B);
+        mup = fmaxf(mup, __fdividef(P * P, A * B));
+    }
+    mup = mup * (1.f + 1e-5f);                                          // the products and the approximate division above
+    if (!(mup < 0.2f)) ok = false;
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    mup = warp_maxf(mup); mnA = warp_minf(mnA); mnB = warp_minf(mnB);
+    if (lane == 0) {
+        float* ts = st.tsum + (int64_t)slot * 4;
+        ts[0] = mup + 1e-30f; ts[1] = mnA * (1.f - 1e-6f); ts[2] = mnB * (1.f - 1e-6f); ts[3] = 0.f;
+        st.slot_info[slot * 4 + 2] = 0;
+        st.tile_slot[(int64_t)s * st.sum_stride + tile] = slot;
+        st.slot_info[slot * 4 + 3] = 255;                              // (empty candidate span: c_lo = 255, c_hi = 0)
+        if (st.xc_peak) st.xc_peak[slot] = 0ull;
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ cleaned, int64_t stride, int64_t base_g, int64_t avail_hi, AmbScanStore st) {
     const int lane = threadIdx.x & 31;
     const int n_slots = min(*st.slot_count, st.slot_cap);
@@ -482,6 +550,7 @@ __global__ void __launch_bounds__(128, 4) k_tri_store(const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < 8; k++) { const int64_t a = a_first + 256 * seg + 8 * lane + k; x[seg][k] = (a >= 0 && a < a_hi) ? row[a] : 0.f; }
         }
+        if (amb_tile_junk32(x, lane, base_g + a_first, st, slot, s, tile)) continue;
         double oP[8], oA[8], oB[8];
         amb_tile_sums_regs(x, lane, oP, oA, oB);
         int cand = 0, c_lo = 255, c_hi = 0, excluded = 0;
@@ -2714,8 +2783,11 @@ __device__ __forceinline__ int64_t amb_predict_scan_start(const AmbTables* __res
 //   (k_chain_links applies it), so that phase A keeps reading an unchanging states[].
 // mode 1 (phase B): flat link index, start state = the stream's current state (link 0) or the phase-A end state of the
 //   previous chain run; the warp also decides whether its link reproduced the speculation (first_stop).
+#ifndef AMB_WALK_CTAS
+#define AMB_WALK_CTAS 4          // resident CTAs per SM of the warp-per-link walker (development: -DAMB_WALK_CTAS=5 to compare)
+#endif
 template <bool TEAM>
-__global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+__global__ void __launch_bounds__(128, TEAM ? 4 : AMB_WALK_CTAS) k_link_walk(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
                                                     const float* __restrict__ sums, const AmbStreamState* __restrict__ states,
                                                     const double* __restrict__ dc_next, const int* __restrict__ todo, int n_todo, int n_streams,
                                                     int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
@@ -2798,20 +2870,29 @@ __global__ void __launch_bounds__(128, 4) k_link_walk(const AmbTables* __restric
         else if (i == 0) st = states[s];
         else st = L.endA[L.run_off[s] + L.link_run[f - 1]];
         if (mode == 1 && L.startA && L.link_run[f] >= 0) {
-            // phase A walked this run from the very state the link starts in, found a frame and counted no refine failure on the
-            // way: its record and end state are the link's (the fields a walk never touches are carried over from the start state)
+            // phase A walked this run from the very state the link starts in (and counted no refine failure on the way): its
+            // record and end state are the link's.  The fields a walk never writes are carried over from the start state, and so
+            // are the ones this walk did not reach (no scan initialised: the defect terms; no commit / refine: the metrics).
             const int fa = L.run_off[s] + L.link_run[f];
             const AmbStartA sa = L.startA[fa];
-            if (L.hasA[fa] == 1 && st.state == AMB_RX_IDLE && !st.ac_init && st.pre_pos == -1 && st.frame_end == -1 && st.ac_scan_pos == sa.pos &&
-                st.next_call == sa.call) {
+            if (st.state == AMB_RX_IDLE && !st.ac_init && st.pre_pos == -1 && st.frame_end == -1 && st.ac_scan_pos == sa.pos && st.next_call == sa.call) {
                 const AmbStreamState ea = L.endA[fa];
-                if (ea.false_pos == sa.false_pos && ea.meta_received == st.meta_received && ea.chunk_size == st.chunk_size) {
+                const int ha = L.hasA[fa];
+                if ((ha == 0 || ha == 1) && ea.false_pos == sa.false_pos && ea.meta_received == st.meta_received && ea.chunk_size == st.chunk_size) {
                     if (lane == 0 && writer) {
                         AmbStreamState so = ea;
                         amb_carry_unwalked(so, st);
-                        AmbFrameRec rb = L.recA[fa];
-                        rb.snap = so;
-                        L.outB[f] = so; L.hasB[f] = 1; L.recB[f] = rb;
+                        if (ha == 0) {
+                            if (!so.ac_init) { so.Ep = st.Ep; so.Ea = st.Ea; so.Eb = st.Eb; so.lag = st.lag; so.init_call = st.init_call; so.init_pos = st.init_pos; }
+                            if (so.state == AMB_RX_IDLE) so.coarse = st.coarse;
+                            if (so.state != AMB_RX_COLLECT) so.fine = st.fine;
+                            atomicMin(&L.first_stop[s], i);                  // no frame: the chain ends here (as after a walk)
+                        } else {
+                            AmbFrameRec rb = L.recA[fa];
+                            rb.snap = so;
+                            L.recB[f] = rb;
+                        }
+                        L.outB[f] = so; L.hasB[f] = ha;
                         if (L.stats) atomicAdd(L.stats, 1ull);
                     }
                     __syncwarp();
@@ -2881,49 +2962,67 @@ __device__ __forceinline__ int64_t amb_link_init_call(const AmbStreamState& st, 
     return c > st.next_call ? c : st.next_call;
 }
 
-__global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float* __restrict__ cleaned, const float* __restrict__ sums,
-                                                    const AmbStreamState* __restrict__ states, int n_streams, AmbLinkBufs L,
-                                                    int32_t* __restrict__ cold_tag, int64_t call_lo, int64_t call_hi) {
+// k_cold_list (one THREAD per call) finds the governing link of every idle call and lists the calls that still need the
+// screening; k_cold_calls (one WARP per listed call) does the screening.  After the first iteration of a pass almost every
+// call is already tagged under its hypothesis (the chain behind the first link rarely changes), and a warp per call only to
+// find that out cost 0.09 ms per iteration on a one-hour capture.
+__global__ void __launch_bounds__(256) k_cold_list(AmbStreamGeom g, const AmbStreamState* __restrict__ states, int n_streams, AmbLinkBufs L,
+                                                   const int32_t* __restrict__ cold_tag, int64_t call_lo, int64_t call_hi,
+                                                   int* __restrict__ list_count, int4* __restrict__ list) {
     const int lane = threadIdx.x & 31;
     const int64_t per = call_hi - call_lo;
     const int64_t total = (int64_t)n_streams * per;
-    for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * 4) {
-        const int s = (int)(w / per);
-        const int64_t k = call_lo + w % per;
-        if (!L.active[s]) continue;
-        const int n_links = L.n_links[s];
-        // (dense streams - a link every few calls - have nothing to skip)
-        if (n_links <= 0 || (int64_t)n_links * 64 > per) continue;
-        const AmbStreamState cur = states[s];
-        if (k < cur.next_call) continue;
-        const int off = L.run_off[s], lo_f = off + s;
-        // governing link: the last one whose re-initialisation call is before k (binary search; link 0 starts from the current
-        // state, link i from the phase-A end state of the run before it)
-        int a = 0;
-        int64_t c;
-        if (n_links <= 33) {
-            // lane l looks at link l + 1: one round of loads instead of a dependent chain
-            const int l1 = lane + 1;
-            int64_t cl = -1;
-            if (l1 < n_links) cl = amb_link_init_call(L.endA[off + L.link_run[lo_f + l1 - 1]], g.block_len);
-            const unsigned bal = __ballot_sync(0xffffffffu, cl >= 0 && cl < k);
-            a = bal ? 32 - __clz((int)bal) : 0;
-            c = __shfl_sync(0xffffffffu, cl, a > 0 ? a - 1 : 0);
-            if (a == 0) c = amb_link_init_call(cur, g.block_len);
-        } else {
-            int b = n_links - 1;
-            while (a < b) {
-                const int mid = (a + b + 1) >> 1;
-                const int64_t cm = amb_link_init_call(L.endA[off + L.link_run[lo_f + mid - 1]], g.block_len);
-                if (cm >= 0 && cm < k) a = mid; else b = mid - 1;
+    const int64_t span = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x; w0 < total; w0 += span) {
+        const int64_t w = w0 + threadIdx.x;
+        int4 e = make_int4(0, 0, 0, 0);
+        bool need = false;
+        if (w < total) {
+            const int s = (int)(w / per);
+            const int64_t k = call_lo + w % per;
+            const int n_links = L.active[s] ? L.n_links[s] : 0;
+            // (dense streams - a link every few calls - have nothing to skip)
+            if (n_links > 0 && (int64_t)n_links * 64 <= per && k >= states[s].next_call) {
+                const int off = L.run_off[s], lo_f = off + s;
+                // governing link: the last one whose re-initialisation call is before k (link 0 starts from the current state,
+                // link i from the phase-A end state of the run before it)
+                int a = 0, b = n_links - 1;
+                while (a < b) {
+                    const int mid = (a + b + 1) >> 1;
+                    const int64_t cm = amb_link_init_call(L.endA[off + L.link_run[lo_f + mid - 1]], g.block_len);
+                    if (cm >= 0 && cm < k) a = mid; else b = mid - 1;
+                }
+                const int64_t c = amb_link_init_call(a == 0 ? states[s] : L.endA[off + L.link_run[lo_f + a - 1]], g.block_len);
+                const int64_t F0 = g.base_g / g.block_len;
+                const int64_t fc = c - F0, fk = k - F0;
+                if (!(c < 0 || c >= k || fc < 0 || fk >= g.calls_stride) && cold_tag[(int64_t)s * g.calls_stride + fk] != (int32_t)c) {
+                    need = true;
+                    e = make_int4(s, (int)(k - call_lo), (int)c, 0);
+                }
             }
-            c = amb_link_init_call(a == 0 ? cur : L.endA[off + L.link_run[lo_f + a - 1]], g.block_len);
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(list_count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) list[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float* __restrict__ cleaned, const float* __restrict__ sums,
+                                                    const AmbStreamState* __restrict__ states, int n_streams, AmbLinkBufs L,
+                                                    int32_t* __restrict__ cold_tag, int64_t call_lo, int64_t call_hi,
+                                                    const int* __restrict__ list_count, const int4* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const int n_list = *list_count;
+    for (int idx = blockIdx.x * 4 + (threadIdx.x >> 5); idx < n_list; idx += gridDim.x * 4) {
+        const int4 e = list[idx];
+        const int s = e.x;
+        const int64_t k = call_lo + e.y, c = e.z;
         const int64_t F0 = g.base_g / g.block_len;
         const int64_t fc = c - F0, fk = k - F0;
-        if (c < 0 || c >= k || fc < 0 || fk >= g.calls_stride) continue;
-        // tagged cold under this very hypothesis by an earlier iteration of the pass (the chain behind the first link rarely changes)
-        if (cold_tag[(int64_t)s * g.calls_stride + fk] == (int32_t)c) continue;
         const double* F = g.F + (int64_t)s * g.calls_stride * 3;
         const double Ep = F[fk * 3] - F[fc * 3], Ea = F[fk * 3 + 1] - F[fc * 3 + 1], Eb = F[fk * 3 + 2] - F[fc * 3 + 2];
         AmbWalkGeom G;
