@@ -78,7 +78,7 @@ struct amb_modem {
     DevBuf raw, cleaned, sums, dc_next, states, recs, nrec, job_off, total, keep, keep_off, redo, n_redo, s_res, s_bytes, s_sel, g_res, g_bytes, ctmp;
     DevBuf nan_pos, tile_slot, tri, slot_info, slot_count, defect, fpre, xc, dpart, tsum, cand_list;
     DevBuf l_chunks, l_runs, l_nruns, l_runoff, l_recA, l_endA, l_hasA, l_next, l_linkrun, l_nlinks, l_outB, l_recB, l_hasB, l_vis, l_ja, l_jb, l_active, l_nactive;
-    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, l_startA, xc_peak, cold_list, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
+    DevBuf l_first, l_firstflag, l_firststop, l_fpsum, l_memo, l_bmout, l_bmrec, l_bmhas, l_startA, xc_peak, xc_rows, cold_list, cold_tag, post_acc, bitmaps, files, file_reset, store_off;
     int64_t file_cap = 0;          // bytes per stream of the chunk store (0: assembly not enabled)
     int64_t bitmap_bits = 0;       // per-stream capacity of the chunk bitmap (ChunkAssembler.receivedBitmap)
     int* h_counts = nullptr;       // pinned host words for the per-push device->host counters
@@ -425,7 +425,7 @@ void amb_destroy(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->xc_rows, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
     if (m->d_tables) cudaFree(m->d_tables);
@@ -873,6 +873,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     CK(cudaMemsetAsync(m->defect.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     CK(cudaMemsetAsync(m->fpre.p, 0, ns * m->calls_stride * 3 * 8, m->stream));
     cudaFuncSetAttribute(k_xcorr_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AMB_XC_SMEM(AMB_XC_MAXW + 768));
+    cudaFuncSetAttribute(k_link_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AMB_TEAM_STAGE_FLOATS * 4));
     m->run_cap = (int)(max_push / 512) + 2;
     CK(m->l_runs.ensure(ns * m->run_cap * sizeof(AmbRun))); CK(m->l_nruns.ensure(ns * 4)); CK(m->l_runoff.ensure(ns * 4));
     CK(m->l_nlinks.ensure(ns * 4)); CK(m->l_active.ensure(ns * 4)); CK(m->l_nactive.ensure(16));
@@ -915,7 +916,7 @@ int amb_stream_close(amb_modem* m) {
                      &m->tile_slot, &m->tri, &m->slot_info, &m->slot_count, &m->defect, &m->fpre, &m->xc, &m->dpart, &m->tsum, &m->cand_list,
                      &m->l_chunks, &m->l_runs, &m->l_nruns, &m->l_runoff, &m->l_recA, &m->l_endA, &m->l_hasA, &m->l_next, &m->l_linkrun, &m->l_nlinks, &m->l_outB,
                      &m->l_recB, &m->l_hasB, &m->l_vis, &m->l_ja, &m->l_jb, &m->l_active, &m->l_nactive,
-                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
+                     &m->l_first, &m->l_firstflag, &m->l_firststop, &m->l_fpsum, &m->l_memo, &m->l_bmout, &m->l_bmrec, &m->l_bmhas, &m->l_startA, &m->xc_peak, &m->xc_rows, &m->cold_list, &m->cold_tag, &m->post_acc, &m->bitmaps, &m->files, &m->file_reset, &m->store_off};
     for (DevBuf* b : all) b->release();
     m->open = false;
     m->file_cap = 0;
@@ -974,7 +975,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
     ss.junk32 = junk32_on ? 1 : 0;
     // tiles the walker can look at (the history and the new samples): no slot (-1) until this push assigns one
     CK(cudaMemset2DAsync(m->tile_slot.as<int32_t>() + (off0 - m->hist) / 256, (size_t)m->sum_stride * 4, 0xFF, (size_t)((m->hist + n_new) / 256) * 4, ns, m->stream));
-    CK(cudaMemsetAsync(m->slot_count.p, 0, 8, m->stream));          // [0] slots, [1] slots holding a candidate
+    CK(cudaMemsetAsync(m->slot_count.p, 0, 12, m->stream));         // [0] slots, [1] slots holding a candidate, [2] screening rows (k_xcorr_rows)
     {
         // 1+2. DC removal and the window-sum summaries of the new window-end samples, one pass (k_front)
         AmbFrontArgs fa;
@@ -1049,10 +1050,16 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // next slot while it works on the current one
         // (measured per 33 k candidate slots: 148 x 8 CTAs 0.49 ms, x 16 0.45, x 32 0.43, x 64 0.42, x 128 0.41)
         const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
-        if (xc_store_on) LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_info.as<int32_t>(),
-                                                                                     m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap, m->xc.as<float>(), m->xc_w,
-                                                                                     xc_skip_on ? m->tile_slot.as<int32_t>() : nullptr, off0 / 256, (off0 + n_new) / 256,
+        if (xc_store_on) {
+            CK(m->xc_rows.ensure((size_t)m->slot_cap * 16));
+            const int rgrid = (int)(blocks_for(m->slot_cap, 256) < 148 * 4 ? blocks_for(m->slot_cap, 256) : 148 * 4);
+            LAUNCH("k_xcorr_rows", k_xcorr_rows<<<rgrid, 256, 0, m->stream>>>(g, m->slot_info.as<int32_t>(), m->slot_count.as<int>(), m->cand_list.as<int32_t>(), m->slot_cap,
+                                                                               xc_skip_on ? m->tile_slot.as<int32_t>() : nullptr, off0 / 256, (off0 + n_new) / 256,
+                                                                               reinterpret_cast<int4*>(m->xc_rows.p)));
+            LAUNCH("k_xcorr_store", k_xcorr_store<<<grid, threads, smem, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->slot_count.as<int>(),
+                                                                                     reinterpret_cast<const int4*>(m->xc_rows.p), m->slot_cap, m->xc.as<float>(), m->xc_w,
                                                                                      m->xc_peak.as<unsigned long long>()));
+        }
     }
     int n_out = 0;
     int n_todo = ns;
@@ -1135,7 +1142,7 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
             L.trace_iter = (int)(m->link_iterations * 2 + 1);
             LAUNCH("k_link_walk_B", k_link_walk<false><<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
-            LAUNCH("k_link_walk_B_team", k_link_walk<true><<<walk_grid_b, 128, 0, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
+            LAUNCH("k_link_walk_B_team", k_link_walk<true><<<walk_grid_b, 128, AMB_TEAM_STAGE_FLOATS * 4, m->stream>>>(m->d_tables, g, m->cleaned.as<float>(), m->sums.as<float>(), m->states.as<AmbStreamState>(),
                                                                                 m->dc_next.as<double>(), todo, n_todo, ns, 1, m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_copy", k_verify_copy<<<flat_grid, 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->recs.as<AmbFrameRec>(), m->nrec.as<int>(), L));
             LAUNCH("k_verify_final", k_verify_final<<<blocks_for(ns, 128), 128, 0, m->stream>>>(ns, m->rec_cap, m->states.as<AmbStreamState>(), m->dc_next.as<double>(), g.avail_hi, g.k_end,

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(128) k_walk(const AmbTables* __restrict__ T, A
     G.F = g.F ? g.F + (int64_t)s * g.calls_stride * 3 : nullptr; G.F_call0 = g.base_g / g.block_len; G.F_calls = g.calls_stride;
         G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
     G.memo_out = nullptr; G.memo_in = nullptr;
-    G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0;
+    G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0; G.team_stage = nullptr;
     AmbSig sig;
     sig.p = cleaned + (int64_t)s * g.stride; sig.base = g.base_g; sig.lo = g.base_g > 0 ? g.base_g : 0; sig.hi = g.avail_hi;
     sig.xf.kind = AMB_XF_NONE; sig.xf.mx = 0.f; sig.xf.mean = 0.0;
@@ -2462,45 +2462,59 @@ __device__ __forceinline__ int amb_xc_peak_offset(unsigned long long key) { retu
 __device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
-__global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
-                                                      const int32_t* __restrict__ slot_info, const int* __restrict__ slot_count,
-                                                      const int32_t* __restrict__ cand_list, int slot_cap, float* __restrict__ xc, int xc_w,
-                                                      int32_t* __restrict__ tile_slot_rw, int64_t tile_lo, int64_t tile_hi,
-                                                      unsigned long long* __restrict__ xc_peak) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// k_xcorr_rows (one thread per candidate slot) decides which candidate tiles get a screening row and lists them;
+// k_xcorr_store strides over that list.  (The decision is a chain of five dependent loads: taken inside k_xcorr_store, by every
+// CTA for each of its candidates, it sat between the barriers of the row loop - a third of the kernel's time.)
+// A preamble's candidate windows (metric > 0.5) usually spread over two adjacent tiles, but the coarse position the walker
+// refines around is the maximum of the metric, which lies in the tile with the higher peak: a candidate tile whose exact
+// maximum (tsum[0], k_tri_store) is clearly below that of a candidate neighbour of this push gets no row (AMB_TS_NOXC; should a
+// walker want it after all - a carried defect reshaping the peak - it screens the refine itself, amb_xcorr_screen).
+__global__ void __launch_bounds__(256) k_xcorr_rows(AmbStreamGeom g, const int32_t* __restrict__ slot_info, int* __restrict__ slot_count,
+                                                    const int32_t* __restrict__ cand_list, int slot_cap, int32_t* __restrict__ tile_slot_rw,
+                                                    int64_t tile_lo, int64_t tile_hi, int4* __restrict__ row_list) {
     const int n_cand = min(slot_count[1], slot_cap);
-    // A preamble's candidate windows (metric > 0.5) usually spread over two adjacent tiles, but the coarse position the walker
-    // refines around is the maximum of the metric, which lies in the tile with the higher peak: a candidate tile whose exact
-    // maximum (tsum[0], k_tri_store) is clearly below that of a candidate neighbour of this push gets no row (AMB_TS_NOXC; should a
-    // walker want it after all - a carried defect reshaping the peak - it screens the refine itself, amb_xcorr_screen).
-    auto skip_row = [&](int sl) -> bool {
-        if (!tile_slot_rw || !g.tsum) return false;
-        const int s = slot_info[sl * 4];
-        const int64_t t = slot_info[sl * 4 + 1];
-        const float mine = g.tsum[(int64_t)sl * 4] * 1.02f;
-        bool skip = false;
-#pragma unroll
-        const int64_t per_call = g.block_len >> 8, gt = t + (g.base_g >> 8);      // (global tile index: tile gt holds the window-end samples [256 gt, 256 gt + 256))
-        for (int dn = -1; dn <= 1; dn += 2) {
-            const int64_t nb = t + dn;
-            if (nb < tile_lo || nb >= tile_hi) continue;
-            // the running best is per call (app.js:806): where a call ends between the two tiles, the scan commits the best of the
-            // earlier one at the end of its data (app.js:842-846) whatever follows - both rows are needed
-            if (per_call > 0 && ((dn < 0 ? gt : gt + 1) % per_call) == 0) continue;
-            const int raw = tile_slot_rw[(int64_t)s * g.sum_stride + nb];
-            if (raw >= 0 && (raw & AMB_TS_CAND) && g.tsum[(int64_t)(raw & AMB_TS_MASK) * 4] > mine) skip = true;
-        }
-        if (skip && threadIdx.x == 0) atomicOr(tile_slot_rw + (int64_t)s * g.sum_stride + t, AMB_TS_NOXC);
-        return skip;
-    };
-    auto next_cand = [&](int& ci) -> int {
-        while (ci < n_cand) {
+    const int lane = threadIdx.x & 31;
+    for (int c0 = blockIdx.x * blockDim.x; c0 < n_cand; c0 += gridDim.x * blockDim.x) {
+        const int ci = c0 + threadIdx.x;
+        bool keep = false;
+        int4 e = make_int4(0, 0, 0, 0);
+        if (ci < n_cand) {
             const int sl = cand_list[ci];
-            if (!skip_row(sl)) return sl;
-            ci += gridDim.x;
+            const int s = slot_info[sl * 4];
+            const int64_t t = slot_info[sl * 4 + 1];
+            bool skip = false;
+            if (tile_slot_rw && g.tsum) {
+                const float mine = g.tsum[(int64_t)sl * 4] * 1.02f;
+                const int64_t per_call = g.block_len >> 8, gt = t + (g.base_g >> 8);      // (global tile index: tile gt holds the window-end samples [256 gt, 256 gt + 256))
+                for (int dn = -1; dn <= 1; dn += 2) {
+                    const int64_t nb = t + dn;
+                    if (nb < tile_lo || nb >= tile_hi) continue;
+                    // the running best is per call (app.js:806): where a call ends between the two tiles, the scan commits the best of the
+                    // earlier one at the end of its data (app.js:842-846) whatever follows - both rows are needed
+                    if (per_call > 0 && ((dn < 0 ? gt : gt + 1) % per_call) == 0) continue;
+                    const int raw = tile_slot_rw[(int64_t)s * g.sum_stride + nb];
+                    if (raw >= 0 && (raw & AMB_TS_CAND) && g.tsum[(int64_t)(raw & AMB_TS_MASK) * 4] > mine) skip = true;
+                }
+                if (skip) atomicOr(tile_slot_rw + (int64_t)s * g.sum_stride + t, AMB_TS_NOXC);
+            }
+            keep = !skip;
+            e = make_int4(sl, s, (int)t, slot_info[sl * 4 + 3]);
         }
-        return -1;
-    };
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(slot_count + 2, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) row_list[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restrict__ T, AmbStreamGeom g, const float* __restrict__ cleaned,
+                                                      const int* __restrict__ slot_count, const int4* __restrict__ row_list, int slot_cap,
+                                                      float* __restrict__ xc, int xc_w, unsigned long long* __restrict__ xc_peak) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_rows = min(slot_count[2], slot_cap);
     const int plen = T->sym_len, cp = T->cp_len, R = T->fine_radius;
     const int L = xc_w + plen;                                         // samples needed (multiple of 16 for every config)
     const int LP = AMB_XC_PADI(L) + 4;
@@ -2521,10 +2535,11 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
     const float t_last_u = split > 0 ? T->pre1[cp + split - 1] : 0.f, t_last = T->pre1[cp + 255];
     const int64_t lo = g.base_g > 0 ? g.base_g : 0;
     int ci = blockIdx.x;
-    int slot = next_cand(ci);
+    int4 row = ci < n_rows ? row_list[ci] : make_int4(-1, 0, 0, 0);
+    int slot = row.x;
     if (slot >= 0) {
-        const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
-        const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
+        const float* src = cleaned + (int64_t)row.y * g.stride;
+        const int64_t base = g.base_g + ((int64_t)row.z << 8) - 511 - R;
         for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -2553,19 +2568,20 @@ __global__ void __launch_bounds__(256, 3) k_xcorr_store(const AmbTables* __restr
             if (tid == nt - 1) SQ[AMB_XC_SQI(L)] = off;
         }
         __syncthreads();                                               // u, u2, SQ complete; sg is free
-        const int cur = slot;
+        const int cur = slot, cur_span = row.w;
         ci += gridDim.x;
-        slot = next_cand(ci);
+        row = ci < n_rows ? row_list[ci] : make_int4(-1, 0, 0, 0);
+        slot = row.x;
         if (slot >= 0) {
-            const float* src = cleaned + (int64_t)slot_info[slot * 4] * g.stride;
-            const int64_t base = g.base_g + ((int64_t)slot_info[slot * 4 + 1] << 8) - 511 - R;
+            const float* src = cleaned + (int64_t)row.y * g.stride;
+            const int64_t base = g.base_g + ((int64_t)row.z << 8) - 511 - R;
             for (int i = tid; i < L; i += nt) { const int64_t p = base + i; const bool ok = p >= lo && p < g.avail_hi; cp_async4_zfill(sg + i, ok ? src + (p - g.base_g) : cleaned, ok); }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         float* out = xc + (int64_t)cur * xc_w;
         // a refine around candidate window w reads offsets w .. w + 2R: only the span of the tile's candidate windows (plus a
         // margin for candidates that exist only under the walker's defect) is computed, the rest is marked UNSURE
-        const int c_lo = slot_info[cur * 4 + 3] & 0xffff, c_hi = (slot_info[cur * 4 + 3] >> 16) & 0xffff;
+        const int c_lo = cur_span & 0xffff, c_hi = (cur_span >> 16) & 0xffff;
         const int o_lo = max(0, (c_lo - 16) & ~15), o_hi = min(xc_w, (c_hi + 2 * R + 1 + 16 + 15) & ~15);
         for (int i = tid; i < xc_w; i += nt) if (i < o_lo || i >= o_hi) out[i] = AMB_XC_UNSURE;
         const int par = (lane >> 4) & 1;
@@ -2793,6 +2809,7 @@ __global__ void __launch_bounds__(128, TEAM ? 4 : AMB_WALK_CTAS) k_link_walk(con
                                                     int mode, AmbFrameRec* __restrict__ recs, int* __restrict__ nrec, AmbLinkBufs L) {
     __shared__ AmbWalkScratch scratch[4];
     __shared__ float team_vbuf[TEAM ? AMB_TEAM_VCAP : 1];
+    extern __shared__ __align__(16) unsigned char walk_dyn[];          // TEAM: AMB_TEAM_STAGE_FLOATS floats (amb_xcorr_screen_team)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_runs = L.n_active[1];
     const int total = mode == 0 ? total_runs + n_todo : total_runs + n_streams;
@@ -2825,6 +2842,7 @@ __global__ void __launch_bounds__(128, TEAM ? 4 : AMB_WALK_CTAS) k_link_walk(con
         G.cold_tag = g.cold_tag ? g.cold_tag + (int64_t)s * g.calls_stride : nullptr;
         G.memo_out = nullptr; G.memo_in = nullptr;
         G.team_n = team ? 4 : 1; G.team_rank = team ? warp : 0; G.team_vbuf = team_vbuf; G.team_vcap = AMB_TEAM_VCAP;
+        G.team_stage = team ? reinterpret_cast<float*>(walk_dyn) : nullptr;
         if (!first && mode == 0) { G.memo_out = L.memo + f; if (lane == 0) { L.memo[f].valid = 0; L.bm_has[f] = 0; } __syncwarp(); }
         int bm = -1;                                     // phase B, link after run p: flat index of p
         if (mode == 1 && i > 0) {
@@ -3029,7 +3047,7 @@ __global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float
         G.block_len = g.block_len; G.ring_cap = g.ring_cap; G.sum_base = g.base_g; G.sum_tiles = g.sum_stride; G.sum_lo = g.sum_lo;
         G.tile_slot = g.tile_slot + (int64_t)s * g.sum_stride; G.tri = g.tri; G.xc = g.xc; G.xc_w = g.xc_w; G.slot_info = g.slot_info; G.tsum = g.tsum;
         G.F = nullptr; G.F_call0 = 0; G.F_calls = 0; G.cold_tag = nullptr; G.memo_out = nullptr; G.memo_in = nullptr;
-        G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0;
+        G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0; G.team_stage = nullptr;
         const float* srow = sums + (int64_t)s * g.sum_stride * AMB_SUM_W;
         const int64_t j0 = (k * g.block_len) >> 8, nt = g.block_len >> 8;          // 16 tiles
         int hot = 0, unknown = 0;
@@ -3108,6 +3126,23 @@ __global__ void __launch_bounds__(1024) k_chain_links(int n_streams, AmbStreamSt
     int first = n;
     if (st.state == AMB_RX_IDLE && !st.ac_init) first = amb_run_at_or_after(runs, n, st.ac_scan_pos);
     extern __shared__ __align__(16) unsigned char chain_smem[];
+    // A dense stream: every run from `first` on hands over to the next one (a frame per run).  Then the chain is first, first + 1,
+    // ... and neither the pointer doubling nor the compaction is needed.
+    bool sequential = true;
+    for (int r = first + tid; r < n; r += blockDim.x) if (L.next[off + r] != r + 1) sequential = false;
+    if (__syncthreads_and(sequential)) {
+        for (int r = first + tid; r < n; r += blockDim.x) link_run[r - first] = r;
+        __syncthreads();
+        if (tid == 0) {
+            int m = n - first;
+            const bool tail = m == 0 || L.hasA[off + link_run[m - 1]];
+            if (tail) link_run[m++] = -1;
+            L.n_links[s] = m;
+            L.first_stop[s] = m - 1;
+            L.fp_sum[s] = 0ull;
+        }
+        return;
+    }
     if (n <= smem_runs && n < 65535) {
         // the whole pointer-doubling runs in shared memory (16-bit run indices)
         unsigned short* sa = reinterpret_cast<unsigned short*>(chain_smem);

@@ -114,6 +114,7 @@ struct AmbWalkGeom {
     // memory, team_vcap floats).  team_n <= 1: a warp works alone.
     int team_n, team_rank, team_vcap;
     float* team_vbuf;
+    float* team_stage;          // device, team_n > 1: shared-memory staging area of amb_xcorr_screen_team (AMB_TEAM_STAGE_FLOATS floats), or NULL
 };
 
 // screening values in the xc store: a metric in [-1, 1]; AMB_XC_FAIL where the denominator fails its 0.001 test;
@@ -395,6 +396,77 @@ AMB_HD_COLD void amb_xcorr_screen(const AmbTables* T, const AmbSig s, int64_t lo
     AMB_WARP_SYNC();
 }
 
+#define AMB_TS_PADI(i) ((i) + (((i) >> 4) << 2))
+#define AMB_TEAM_STAGE_FLOATS (AMB_TS_PADI(1664 + 768 + 32) + 768 + 16)
+#if defined(__CUDA_ARCH__)
+// The same screening by the warps of a team (one CTA, team_n x 32 threads; called by all of them): samples and taps staged in
+// shared memory, a thread takes 16 consecutive offsets and steps through the taps 16 at a time with a 32-sample register
+// window (256 multiply-adds per 8 128-bit shared loads).  A one-hour capture's refine - 1,537 offsets x 768 taps, alone on its
+// SM - took ~150,000 cycles with amb_xcorr_screen (global loads, four offsets per lane, three rounds); this takes one round.
+// Samples are padded by 4 floats per 16 in shared memory: the 128-bit loads of the 8 threads of a quarter-warp (80 bytes apart)
+// then hit distinct bank groups.  Values: a sequential float32 sum per offset, as in amb_xcorr_screen (same error bound).
+__device__ __noinline__ void amb_xcorr_screen_team(const AmbTables* T, const AmbSig s, int64_t lo, int n, float* v, float* stage, int team_n, int team_rank) {
+    const int plen = T->sym_len;                                     // a multiple of 16 in every config (576, 640, 768)
+    const int nthreads = team_n * 32, tid = team_rank * 32 + (int)(threadIdx.x & 31);
+    const int ngroups = (n + 15) >> 4;
+    const int ns = 16 * ngroups + plen + 16;
+    float* sm = stage;
+    float* tp = stage + AMB_TS_PADI(1664 + 768 + 32);
+    const float tE = (float)T->pre1_energy;
+    for (int i = tid; i < ns; i += nthreads) sm[AMB_TS_PADI(i)] = amb_sig(s, lo + i);
+    for (int i = tid; i < plen; i += nthreads) tp[i] = T->pre1[i];
+    __syncthreads();
+    for (int gq = tid; gq < ngroups; gq += nthreads) {
+        float c[16], w[32];
+#pragma unroll
+        for (int q = 0; q < 16; q++) c[q] = 0.f;
+        {
+            const float4* p4 = reinterpret_cast<const float4*>(sm + AMB_TS_PADI(16 * gq));
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float4 u = p4[j]; w[4 * j] = u.x; w[4 * j + 1] = u.y; w[4 * j + 2] = u.z; w[4 * j + 3] = u.w; }
+        }
+        float e4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < plen; t += 16) {
+            const float4* p4 = reinterpret_cast<const float4*>(sm + AMB_TS_PADI(16 * gq + t + 16));
+            const float4* t4 = reinterpret_cast<const float4*>(tp + t);
+            float tap[16];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 u = p4[j]; w[16 + 4 * j] = u.x; w[17 + 4 * j] = u.y; w[18 + 4 * j] = u.z; w[19 + 4 * j] = u.w;
+                const float4 a = t4[j]; tap[4 * j] = a.x; tap[4 * j + 1] = a.y; tap[4 * j + 2] = a.z; tap[4 * j + 3] = a.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) c[q] = fmaf(w[q + j], tap[j], c[q]);
+            }
+            // energy of the first offset's window (four chains); the other fifteen slide from it below
+#pragma unroll
+            for (int j = 0; j < 16; j++) e4[j & 3] = fmaf(w[j], w[j], e4[j & 3]);
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j] = w[16 + j];
+        }
+        float e = (e4[0] + e4[1]) + (e4[2] + e4[3]);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            if (q > 0) {
+                const float out = sm[AMB_TS_PADI(16 * gq + q - 1)], in = sm[AMB_TS_PADI(16 * gq + q - 1 + plen)];
+                e = e - out * out + in * in;
+            }
+            if (16 * gq + q < n) {
+                const float d2 = e * tE;
+                float r;
+                if (d2 > 1e-6f * (1.f + 1e-3f)) r = c[q] / sqrtf(d2);
+                else if (d2 < 1e-6f * (1.f - 1e-3f)) r = AMB_XC_FAIL;
+                else r = AMB_XC_UNSURE;
+                if (!(r == r)) r = AMB_XC_UNSURE;                           // NaN samples: let the exact evaluation decide
+                v[16 * gq + q] = r;
+            }
+        }
+    }
+}
+#endif
+
 // Refine with float32 screening values - the scan kernel's store where it covers [lo, hi], otherwise computed here into vbuf
 // (capacity vcap floats) - : offsets whose screening metric is within 1e-3 of the maximum are re-evaluated exactly
 // (amb_xcorr_at), so the argmax and the reported metric are the reference's.  Falls back to the exact evaluation of every
@@ -413,7 +485,8 @@ AMB_HD double amb_fine_xcorr_store(const AmbTables* T, const AmbWalkGeom& G, con
 #if defined(__CUDA_ARCH__)
         if (G.team_n > 1 && n <= G.team_vcap) {
             __syncthreads();                                            // (the team's readers of the previous screening row are done)
-            amb_xcorr_screen(T, sig, lo, n, G.team_vbuf, G.team_n, G.team_rank);
+            if (G.team_stage && sig.xf.kind == AMB_XF_NONE) amb_xcorr_screen_team(T, sig, lo, n, G.team_vbuf, G.team_stage, G.team_n, G.team_rank);
+            else amb_xcorr_screen(T, sig, lo, n, G.team_vbuf, G.team_n, G.team_rank);
             __syncthreads();
             v = G.team_vbuf;
         } else

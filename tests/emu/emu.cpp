@@ -226,7 +226,7 @@ int emu_stream(int cfg, int mod, int rep, const float* x, int64_t n, int64_t blo
     AmbWalkGeom G;
     G.block_len = block_len; G.ring_cap = amb_tables_estimate_frame_samples(cfg, mod, 4096 + 16, rep) * 3 + 8192;
     G.sum_base = 0; G.sum_tiles = n_tiles; G.sum_lo = 0;
-    G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0;
+    G.team_n = 1; G.team_rank = 0; G.team_vbuf = nullptr; G.team_vcap = 0; G.team_stage = nullptr;
     // stores as the scan kernels write them (k_scan_sums, k_defect_prefix, k_xcorr_store): slots only for the tiles of the
     // current push, float64 triples, float32 screening correlation, per-call defect prefix
     std::vector<int32_t> tile_slot((size_t)n_tiles, -1);
