@@ -1049,7 +1049,8 @@ static int push_core(amb_modem* m, const void* src, int64_t src_stride, int64_t 
         // the CTAs stride over the compact list of candidate slots (k_tri_store): even shares, and each CTA prefetches its
         // next slot while it works on the current one
         // (measured per 33 k candidate slots: 148 x 8 CTAs 0.49 ms, x 16 0.45, x 32 0.43, x 64 0.42, x 128 0.41)
-        const int grid = m->slot_cap < 148 * 128 ? m->slot_cap : 148 * 128;
+        static const int xc_mult = std::getenv("AMB_XC_GRID") ? std::atoi(std::getenv("AMB_XC_GRID")) : 128;      // (development: CTAs per SM of the launch)
+        const int grid = m->slot_cap < 148 * xc_mult ? m->slot_cap : 148 * xc_mult;
         if (xc_store_on) {
             CK(m->xc_rows.ensure((size_t)m->slot_cap * 16));
             const int rgrid = (int)(blocks_for(m->slot_cap, 256) < 148 * 4 ? blocks_for(m->slot_cap, 256) : 148 * 4);

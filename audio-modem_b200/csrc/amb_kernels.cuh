@@ -3029,7 +3029,10 @@ __global__ void __launch_bounds__(256) k_cold_list(AmbStreamGeom g, const AmbStr
     }
 }
 
-__global__ void __launch_bounds__(128) k_cold_calls(AmbStreamGeom g, const float* __restrict__ cleaned, const float* __restrict__ sums,
+#ifndef AMB_COLD_CTAS
+#define AMB_COLD_CTAS 3
+#endif
+__global__ void __launch_bounds__(128, AMB_COLD_CTAS) k_cold_calls(AmbStreamGeom g, const float* __restrict__ cleaned, const float* __restrict__ sums,
                                                     const AmbStreamState* __restrict__ states, int n_streams, AmbLinkBufs L,
                                                     int32_t* __restrict__ cold_tag, int64_t call_lo, int64_t call_hi,
                                                     const int* __restrict__ list_count, const int4* __restrict__ list) {

@@ -162,7 +162,8 @@ class Modem:
         return int(self._L.amb_kernel_launches(self._h))
 
     def debug_counter(self, which):
-        """0 launches, 1 fast-demod fallback symbols, 2 link iterations, 3 link passes"""
+        """0 launches, 1 fast-demod fallback symbols, 2 link iterations, 3 link passes, 4 / 5 slotted / candidate tiles of the last push,
+        6 phase-B links answered by phase A's own walk, 7 phase-B links walked again"""
         return int(self._L.amb_debug_counter(self._h, which))
 
     def debug_slots(self):

@@ -382,6 +382,47 @@ def roofline(ctx, workload, prof, prof_ms, prof_steps, per_launch_bytes, algo_st
             "kernels_ms_per_step": {k: v[0] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 
 
+def h2d_copy_ceiling(ctx, host_ptr, nbytes, reps=3):
+    """GB/s per rank of a plain cudaMemcpyAsync of the end-to-end leg's own page-locked buffer into device memory, all ranks
+    copying at once (barrier first), nothing else running: the ceiling the host gives the end-to-end figure.  None when the
+    runtime library cannot be reached."""
+    import ctypes
+
+    import torch
+
+    try:
+        rt = None
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                rt = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if rt is None:
+            return None
+        rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        rt.cudaMemcpyAsync.restype = ctypes.c_int
+        nbytes = int(min(nbytes, 2 << 30))
+        dst = torch.empty(nbytes, dtype=torch.uint8, device=ctx.dev)
+        stream = torch.cuda.current_stream(ctx.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if rt.cudaMemcpyAsync(dst.data_ptr(), host_ptr, nbytes, 1, stream.cuda_stream) != 0:
+            return None
+        torch.cuda.synchronize(ctx.dev)
+        ctx.barrier()
+        e0.record(stream)
+        for _ in range(reps):
+            if rt.cudaMemcpyAsync(dst.data_ptr(), host_ptr, nbytes, 1, stream.cuda_stream) != 0:
+                return None
+        e1.record(stream)
+        torch.cuda.synchronize(ctx.dev)
+        ms = ctx.max_ranks(e0.elapsed_time(e1))
+        del dst
+        return nbytes * reps / (ms / 1e3) / 1e9
+    except Exception:          # noqa: BLE001  (a diagnostic: the bench line does not depend on it)
+        return None
+
+
 def e2e_obj(value, h2d, d2h, steps, seconds, world):
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
             "h2d_gb_per_s_per_rank": h2d * steps / seconds / 1e9 / max(world, 1) if seconds > 0 else None}
@@ -509,6 +550,7 @@ def run_c2(ctx, clocks):
     m.synchronize()
     e2e_s = time.perf_counter() - t0
     assert e2e_frames == args.e2e_steps * F, e2e_frames
+    h2d_ceiling = h2d_copy_ceiling(ctx, host.ptr, 4 * step_samples)
     # wire-format ingest (reported apart: 2 B per sample changes the byte count): the same samples as signed
     # 16-bit PCM through amb_stream_push_pcm16, device-resident and end to end
     pcm_dev = (segs[0] * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
@@ -564,6 +606,7 @@ def run_c2(ctx, clocks):
               "parallelism": "streams sharded by rank, no collective on the hot path"}
     line = base_line(ctx, "c2", value, total_ms, args.steps, args.warmup, tot["payloadBytes"], config, None,
                      e2e_obj(world * args.e2e_steps * step_samples / e2e_s_max / 1e6, 4 * step_samples, d2h, args.e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["e2e"]["h2d_copy_ceiling_gb_per_s_per_rank"] = h2d_ceiling      # plain cudaMemcpyAsync of the same page-locked buffer, all ranks at once
     line["pcm16"] = pcm16
     line["walker"] = slots
     line["check"] = {"frames_per_step_found": frames_found // args.steps, "frames_decoded_warmup_and_timed": decoded, "crc_errors_warmup_and_timed": crc_bad,
@@ -681,6 +724,7 @@ def run_c5(ctx, clocks, ns=None, light=False):
     assert (abs(e2e_frames - frames_per_period) <= ns) if host_secs == period else e2e_frames > 0, (e2e_frames, frames_per_period)
     clocks.mark_end()
     d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
+    h2d_ceiling = h2d_copy_ceiling(ctx, host.ptr, 4 * ns * push)
     m.stream_close()
     del hx
     host.free()
@@ -699,6 +743,7 @@ def run_c5(ctx, clocks, ns=None, light=False):
               "note": "every stream receives its metadata frame in the prologue; the timed steps cycle over its 8 data frames (steady state)"}
     line = base_line(ctx, "c5", value, total_ms, args.steps, args.warmup, tot["payloadBytes"], config, None,
                      e2e_obj(world * e2e_steps * step_samples / e2e_s_max / 1e6, 4 * step_samples, d2h, e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["e2e"]["h2d_copy_ceiling_gb_per_s_per_rank"] = h2d_ceiling      # plain cudaMemcpyAsync of the same page-locked buffer, all ranks at once
     line["walker"] = iters
     line["check"] = {"frames_found": tot["frames"], "frames_expected_per_period_per_gpu": frames_per_period, "frame_errors": c1["frameErrors"] - c0["frameErrors"],
                      "crc_errors": c1["crcErrors"] - c0["crcErrors"], "fallback_symbols_per_step": fallbacks / n_done}
@@ -797,6 +842,7 @@ def run_c4(ctx, clocks):
     e2e_s = time.perf_counter() - t0
     clocks.mark_end()
     d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
+    h2d_ceiling = h2d_copy_ceiling(ctx, host.ptr, 4 * ns * push)
     m.stream_close()
     del hx
     host.free()

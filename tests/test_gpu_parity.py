@@ -334,6 +334,41 @@ def test_stream_single_block_pushes(O, amb):
     assert [bytes(b[r.data_off:r.data_off + r.data_len]) for r, b in got[0] if r.frame_type == 0xFF] == pay
 
 
+@pytest.mark.parametrize("snr_db,gaps", [(25.0, None), (25.0, [0, 2500, 40, 9000]), (7.0, [0, 333])])
+def test_stream_phase_a_walks_stand_for_phase_b(O, amb, snr_db, gaps):
+    """Dense streams after their metadata frame: phase A starts every run where it expects the receiver to be (the frame end
+    predicted from the screening peak of the run before, or from the carried state) and phase B takes its walk over where the
+    exact start state is that very state; everything else is walked again.  Events and counters equal the oracle's either way."""
+    mode = "16-QAM"
+    cfg, mod, rep, _ = MODES[mode]
+    x, _ = make_stream(O, mode, 12, 31, snr_db=snr_db, gaps=gaps)
+    n = len(x)
+    first = 6 * 4096                                   # the metadata frame (16,416 samples) arrives in a push of its own
+    pushes = [first, (n - first) // 4096 // 2 * 4096]
+    pushes.append(n - sum(pushes))
+    m = amb.Modem(cfg, mod, rep, device=0)
+    m.stream_open(1, 4096, max(pushes))
+    got, off = [], 0
+    for p in pushes:
+        got += list(m.stream_push(x[None, off:off + p], raw=True))
+        off += p
+    taken, walked = m.debug_counter(6), m.debug_counter(7)
+    rx = O.StreamingReceiver(cfg, mod, rep)
+    want = rx.push(x, 4096, raw=True)
+    assert len(got) == len(want) >= 10, (len(got), len(want))
+    for (r1, b1), (r2, b2) in zip(want, got):
+        assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], r1.preamble_idx
+    c, cc = rx.counters(), m.stream_counters(0)
+    for k in ("framesDecoded", "frameErrors", "falsePositives", "crcErrors", "metaReceived", "receivedCount", "duplicates"):
+        assert c[k] == cc[k], (k, c[k], cc[k])
+    if snr_db >= 20:
+        assert taken >= 6, (taken, walked)              # most links of the two dense pushes
+        assert walked >= 1, (taken, walked)             # (the last link of a push at least: no frame completes in it)
+    # (at 7 dB the metadata frame fails its CRC: the stream stays on the sequential pre-metadata path, results as the oracle's)
+    m.stream_close()
+    m.close()
+
+
 @pytest.mark.parametrize("lead", [0, 777, 3000, 4000])
 def test_stream_block_alignment(O, amb, lead):
     x, _ = make_stream(O, "16-QAM", 5, 11, lead=lead, gaps=[0, 100, 5000, 333])
