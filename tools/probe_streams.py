@@ -70,6 +70,11 @@ print("launch counts:", {k: v[1] for k, v in sorted(prof.items(), key=lambda kv:
 if len(per) > 4:
     tail = sorted(p[0] for p in per[3:-1])
     print(f"steady pushes (median): {ns * push / (tail[len(tail) // 2] / 1e3) / 1e6:.0f} Msamples/s")
+if os.environ.get("AMB_LIB", "").endswith("stats.so"):
+    names = ["rows", "direct", "refine_store", "refine_direct", "refine_memo", "skip_rounds", "scan_calls", "refine_fail", "exact_offsets",
+             "cyc_eval", "cyc_refine", "cyc_skip", "cyc_scan", "exact_replays"]
+    print("walk stats (all pushes, phase A + phase B):", dict(zip(names, [m.debug_counter(16 + i) for i in range(len(names))])),
+          "taken", m.debug_counter(6), "walked", m.debug_counter(7))
 c = m.stream_counters()
 print(f"{ns} streams: {frames} frames in {dt * 1e3:.1f} ms -> {ns * n / dt / 1e6:.0f} Msamples/s, {n // push} pushes, counters {c}")
 assert c["metaReceived"] == ns, c
