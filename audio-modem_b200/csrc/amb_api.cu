@@ -173,7 +173,7 @@ int check_common(amb_modem* m, int n, int64_t stride, int mem) {
 inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
 
 // demod + parse over m->jobs (n_jobs), results/bytes already device pointers
-int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_frame_result* d_res, uint8_t* d_bytes, int64_t bytes_stride) {
+int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_frame_result* d_res, uint8_t* d_bytes, int64_t bytes_stride, bool two_pass = false) {
     if (n_jobs == 0) return AMB_OK;
     const AmbTables& T = m->tables;
     const int64_t idx_stride = ((int64_t)(max_nsym > 0 ? max_nsym : 1) * T.n_data + 15) / 16 * 16;      // rows 16-byte aligned for k_parse's vector loads
@@ -207,26 +207,40 @@ int run_demod_parse(amb_modem* m, int n_jobs, int max_nsym, bool frame_max, amb_
             LAUNCH("k_frame_max", k_frame_max<<<n_jobs * parts, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs, parts));
         }
         // warps per CTA (two symbols each per round): the count that leaves the fewest symbol slots empty for the longest frame
-        int nw = 8;
-        {
-            const int ns_grp = max_nsym < AMB_SYM_GROUP ? (max_nsym > 0 ? max_nsym : 1) : AMB_SYM_GROUP;
+        auto warps_for = [](int nsym_max) {
+            int nw = 8;
+            const int ns_grp = nsym_max < AMB_SYM_GROUP ? (nsym_max > 0 ? nsym_max : 1) : AMB_SYM_GROUP;
             int best_cost = 1 << 30;
             // (+1: the CE symbol takes one half-warp slot of the first round)
             for (int w = 8; w >= 5; w--) { const int cost = ((ns_grp + 1 + 2 * w - 1) / (2 * w)) * w; if (cost < best_cost) { best_cost = cost; nw = w; } }
-        }
+            return nw;
+        };
         // instantiated per constellation and per CTA size class (7 warps or fewer leave registers for a fourth resident CTA)
 #define AMB_DEMOD_LAUNCH(MODV, NTV, FUSEDV) \
-    LAUNCH("k_demod_fast", (k_demod_fast<MODV, NTV, FUSEDV><<<dim3(n_jobs, groups), 32 * nw, AMB_DEMOD_FAST_SMEM(NTV, FUSEDV), m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks, po)))
+    LAUNCH("k_demod_fast", (k_demod_fast<MODV, NTV, FUSEDV><<<dim3(n_jobs, l_groups), 32 * l_nw, AMB_DEMOD_FAST_SMEM(NTV, FUSEDV), m->stream>>>(m->d_tables, m->d_fast, m->jobs.as<AmbJob>(), n_jobs, o, m->d_fallbacks, po)))
 #define AMB_DEMOD_LAUNCH_MOD(NTV, FUSEDV) \
     do { \
         if (T.mod == AMB_MOD_QAM16) { AMB_DEMOD_LAUNCH(AMB_MOD_QAM16, NTV, FUSEDV); } \
         else if (T.mod == AMB_MOD_QPSK) { AMB_DEMOD_LAUNCH(AMB_MOD_QPSK, NTV, FUSEDV); } \
         else { AMB_DEMOD_LAUNCH(AMB_MOD_BPSK, NTV, FUSEDV); } \
     } while (0)
-        if (nw <= 7) { if (fused) AMB_DEMOD_LAUNCH_MOD(224, true); else AMB_DEMOD_LAUNCH_MOD(224, false); }
-        else { if (fused) AMB_DEMOD_LAUNCH_MOD(256, true); else AMB_DEMOD_LAUNCH_MOD(256, false); }
+        auto launch_demod = [&](int l_groups, int l_nw) -> int {
+            if (l_nw <= 7) { if (fused) AMB_DEMOD_LAUNCH_MOD(224, true); else AMB_DEMOD_LAUNCH_MOD(224, false); }
+            else { if (fused) AMB_DEMOD_LAUNCH_MOD(256, true); else AMB_DEMOD_LAUNCH_MOD(256, false); }
+            return AMB_OK;
+        };
 #undef AMB_DEMOD_LAUNCH_MOD
 #undef AMB_DEMOD_LAUNCH
+        // recordings (decodeReceivedSignal): header symbols first, then only the symbols inside the frame's extent (k_extent)
+        const int bits_per_sym = T.n_data * T.bps;
+        const int hdr_syms = (int)(((int64_t)12 * 8 * T.rep - 1) / bits_per_sym) + 1;
+        static const bool two_pass_on = !(std::getenv("AMB_TWO_PASS") && std::getenv("AMB_TWO_PASS")[0] == '0');
+        if (two_pass && two_pass_on && !fused && hdr_syms <= AMB_FD_HDR_SYMS && max_nsym >= 3 * hdr_syms) {
+            LAUNCH("k_demod_limit", k_demod_limit<<<blocks_for(n_jobs, 128), 128, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs, hdr_syms));
+            int rc = launch_demod(1, warps_for(hdr_syms)); if (rc) return rc;
+            LAUNCH("k_extent", k_extent<<<blocks_for(n_jobs, 128), 128, 0, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, m->idx.as<uint8_t>(), idx_stride, hdr_syms));
+        }
+        { int rc = launch_demod(groups, warps_for(max_nsym)); if (rc) return rc; }
     } else {
         if (frame_max) { LAUNCH("k_frame_max", k_frame_max<<<n_jobs, 256, 0, m->stream>>>(m->jobs.as<AmbJob>(), n_jobs, 1)); }
         LAUNCH("k_demod", k_demod<<<dim3(n_jobs, groups), 256, AMB_DEMOD_SMEM, m->stream>>>(m->d_tables, m->jobs.as<AmbJob>(), n_jobs, o));
@@ -758,7 +772,7 @@ int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, co
     LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
                                                              m->cbest.as<double>(), nullptr, 0, m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(max_len / T.sym_len);
-    if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride))) return rc;
+    if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride, true))) return rc;
     return flush(m);
 }
 

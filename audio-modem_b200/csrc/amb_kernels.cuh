@@ -716,6 +716,9 @@ struct AmbJob {
     AmbXform xf;
     double coarse, fine;
     int64_t result_pos;      // preamble_idx to report (-1: none)
+    // two-pass demodulation of recordings (k_demod_limit / k_extent): > 0 = data symbols of the whole collection window (what the
+    // reference demodulates; sets the decoded length) while nsym is cut to the frame's extent; bytes behind it decode to 0
+    int32_t nsym_full, pad_;
 };
 
 // per-frame peak (app.js:918-925) of frames too long for one demodulator CTA: `parts` CTAs per frame, combined by an atomic
@@ -989,6 +992,26 @@ __device__ __forceinline__ float2 fd_split(const float2* buf, const float2 w /* 
     return make_float2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
 }
 
+// Data symbols the parsers can reach, from the first 12 decoded bytes (the frame's extent): what the header announces -
+// metadata frame 12 + nameLen + 4, data chunk 7 + dataLen + 4, whole-file frame 1 + nameLen + 4 + dataLen + 4 (modem.js:805-849,
+// :607-653) - or only the header symbols when no frame fits the decoded length (the result then depends on the header alone).
+__device__ __forceinline__ int amb_extent_syms(const uint8_t* hb, int64_t n_total, int mode, int nsym, int bits_per_sym, int rep_v, int hdr_syms) {
+    int64_t need = -1;                                    // bytes the parser consumes; -1: no frame (only the header matters)
+    const int first = hb[0];
+    if (first == AMB_FRAME_META && (mode == 1 || n_total >= 6)) { if (n_total >= 16 && 12 + (int64_t)hb[11] + 4 <= n_total) need = 12 + (int64_t)hb[11] + 4; }
+    else if (first == AMB_FRAME_DATA && (mode == 1 || n_total >= 6)) { const int64_t dl = (hb[5] << 8) | hb[6]; if (n_total >= 11 && 7 + dl + 4 <= n_total) need = 7 + dl + 4; }
+    else if (mode == 1 && n_total >= 10) {
+        const int64_t nl = first;
+        if (nl <= 7) {                                    // dataLen sits inside the 12 header bytes
+            const int64_t dl = (int32_t)(((uint32_t)hb[1 + nl] << 24) | ((uint32_t)hb[2 + nl] << 16) | ((uint32_t)hb[3 + nl] << 8) | (uint32_t)hb[4 + nl]);
+            if (dl > 0 && 1 + nl + 4 + dl + 4 <= n_total) need = 1 + nl + 4 + dl + 4;
+        } else need = n_total;                            // a long file name: the header runs past what was demodulated here
+    }
+    int need_syms = hdr_syms;
+    if (need > 0) { const int64_t q = (need * 8 * rep_v - 1) / bits_per_sym + 1; need_syms = q > nsym ? nsym : (int)q; if (need_syms < hdr_syms) need_syms = hdr_syms; }
+    return need_syms;
+}
+
 // FUSED (frames of one symbol group whose indices fit AMB_FD_IDX_CAP: every chunk frame of the standard config): the CTA
 // also does what k_parse does - majority vote, byte packing, header parse, CRC-32 - from the constellation indices it
 // keeps in shared memory, and writes the decoded bytes and the result itself; the index array never goes to HBM.
@@ -1240,7 +1263,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
         __shared__ int s_need;
         uint8_t* hdr_idx = reinterpret_cast<uint8_t*>(qs + AMB_FD_FB_WARPS * 2 * AMB_MAX_PILOTS);     // [AMB_FD_HDR_SYMS][n_data]
         const int bits_per_sym = n_data * T->bps, rep_v = T->rep;
-        const int64_t n_total = amb_num_bytes((int64_t)J.nsym * n_data, T->bps, rep_v);
+        const int64_t n_total = amb_num_bytes((int64_t)(J.nsym_full > 0 ? J.nsym_full : J.nsym) * n_data, T->bps, rep_v);
         const int hdr_syms = n_total >= 12 ? (int)(((int64_t)12 * 8 * rep_v - 1) / bits_per_sym) + 1 : 0;
         const bool use_extent = !FUSED && J.mode != 2 && hdr_syms > 0 && hdr_syms <= AMB_FD_HDR_SYMS && hdr_syms <= J.nsym &&
                                 (size_t)AMB_FD_SMEM_FB + (size_t)AMB_FD_HDR_SYMS * AMB_FD_MAXBINS <= (size_t)AMB_FD_UNION(NT);
@@ -1257,19 +1280,7 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
             if (tid == 0) {
                 uint8_t hb[12];
                 for (int b = 0; b < 12; b++) hb[b] = amb_pack_byte(hdr_idx, T->bps, rep_v, b);
-                int64_t need = -1;                                    // bytes the parser consumes; -1: no frame (only the header matters)
-                const int first = hb[0];
-                if (first == AMB_FRAME_META && (J.mode == 1 || n_total >= 6)) { if (n_total >= 16 && 12 + (int64_t)hb[11] + 4 <= n_total) need = 12 + (int64_t)hb[11] + 4; }
-                else if (first == AMB_FRAME_DATA && (J.mode == 1 || n_total >= 6)) { const int64_t dl = (hb[5] << 8) | hb[6]; if (n_total >= 11 && 7 + dl + 4 <= n_total) need = 7 + dl + 4; }
-                else if (J.mode == 1 && n_total >= 10) {
-                    const int64_t nl = first;
-                    if (nl <= 7) {                                    // dataLen sits inside the 12 header bytes
-                        const int64_t dl = (int32_t)(((uint32_t)hb[1 + nl] << 24) | ((uint32_t)hb[2 + nl] << 16) | ((uint32_t)hb[3 + nl] << 8) | (uint32_t)hb[4 + nl]);
-                        if (dl > 0 && 1 + nl + 4 + dl + 4 <= n_total) need = 1 + nl + 4 + dl + 4;
-                    } else need = n_total;                            // a long file name: the header runs past what was demodulated here
-                }
-                int need_syms = hdr_syms;
-                if (need > 0) { const int64_t q = (need * 8 * rep_v - 1) / bits_per_sym + 1; need_syms = q > J.nsym ? J.nsym : (int)q; if (need_syms < hdr_syms) need_syms = hdr_syms; }
+                const int need_syms = amb_extent_syms(hb, n_total, J.mode, J.nsym, bits_per_sym, rep_v, hdr_syms);
                 s_need = need_syms;
             }
             __syncthreads();
@@ -1386,6 +1397,31 @@ __global__ void __launch_bounds__(NT, NT <= 224 ? 4 : 3) k_demod_fast(const AmbT
     if (tid == 0) po.results[j] = p_res;
 }
 
+// Two-pass demodulation of recordings (amb_decode_received_signals): a recording is much longer than the frame it holds (C3:
+// 88,260 samples for a frame of ~30,000), and the reference demodulates every symbol of it although its result only holds what
+// the parsers consume.  Pass 1 demodulates the header symbols (k_demod_limit cuts nsym and keeps the whole count in nsym_full), k_extent reads the frame's extent
+// from the 12 header bytes exactly as the in-kernel fallback does, pass 2 demodulates the symbols inside it.  Decoded bytes
+// behind the extent are 0 (include/audio_modem_b200.h: amb_frame_result).
+__global__ void k_demod_limit(AmbJob* __restrict__ jobs, int n, int hdr_syms) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    AmbJob& J = jobs[j];
+    J.nsym_full = 0;
+    if (J.status == 0 && J.mode == 1 && J.nsym > hdr_syms) { J.nsym_full = J.nsym; J.nsym = hdr_syms; }
+}
+__global__ void k_extent(const AmbTables* __restrict__ T, AmbJob* __restrict__ jobs, int n, const uint8_t* __restrict__ idx, int64_t idx_stride, int hdr_syms) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    AmbJob& J = jobs[j];
+    if (J.nsym_full <= 0) return;                        // (not limited by k_demod_limit: every symbol)
+    const int bps = T->bps, rep = T->rep;
+    const int64_t n_total = amb_num_bytes((int64_t)J.nsym_full * T->n_data, bps, rep);
+    const uint8_t* ix = idx + (int64_t)j * idx_stride;
+    uint8_t hb[12];
+    for (int b = 0; b < 12; b++) hb[b] = amb_pack_byte(ix, bps, rep, b);
+    J.nsym = amb_extent_syms(hb, n_total, J.mode, J.nsym_full, T->n_data * bps, rep, hdr_syms);
+}
+
 #define AMB_PARSE_SMEM 8192      // decoded frames up to this many bytes are packed, parsed and checksummed in shared memory
 __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __restrict__ T, const AmbJob* __restrict__ jobs, int n_jobs,
                                                 const uint8_t* __restrict__ idx, int64_t idx_stride /*multiple of 16*/, amb_frame_result* __restrict__ results,
@@ -1415,18 +1451,20 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
         }
         uint8_t* bytes = bytes_out + (int64_t)j * bytes_stride;
         const uint8_t* ix = idx + (int64_t)j * idx_stride;
-        const int64_t n_elems = (int64_t)J.nsym * T->n_data;
+        const int64_t n_elems = (int64_t)(J.nsym_full > 0 ? J.nsym_full : J.nsym) * T->n_data;
         // The whole decoded frame is packed, parsed and checksummed - in shared memory when it fits, else in the caller's row when
         // that holds it, else in a scratch row - and the caller's row gets what fits into it (n_bytes reports the full length).
         const int64_t nb = amb_num_bytes(n_elems, bps, rep), nb_full = nb;
         const int64_t nb_copy = nb < bytes_stride ? nb : bytes_stride;
         const bool in_smem = nb <= AMB_PARSE_SMEM;
         uint8_t* dst = in_smem ? sb : (nb <= bytes_stride || !scratch ? bytes : scratch + (int64_t)j * scratch_stride);
+        // (two-pass demodulation: symbols behind the frame's extent were not demodulated, their bytes decode to 0)
+        const int64_t nbv = (J.nsym_full > 0 && J.nsym < J.nsym_full) ? amb_num_bytes((int64_t)J.nsym * T->n_data, bps, rep) : nb;
         // majorityVote + bitsToBytes.  Without repetition whole constellation indices pack into bytes: 8 (16-QAM) or 16 (QPSK)
         // indices per 128-bit / 64-bit load make 4 bytes.
         int64_t b0 = 0;
         if (rep == 1 && bps == 4) {
-            const int64_t quads = nb / 4;
+            const int64_t quads = nbv / 4;
             for (int64_t q = tid; q < quads; q += AMB_CRC_THREADS) {
                 const uint2 v = *reinterpret_cast<const uint2*>(ix + 8 * q);
                 // index bytes i0..i7 (little endian in v.x, v.y) -> output bytes (i0<<4|i1), (i2<<4|i3), ...
@@ -1439,7 +1477,7 @@ __global__ void __launch_bounds__(AMB_CRC_THREADS) k_parse(const AmbTables* __re
             }
             b0 = quads * 4;
         }
-        for (int64_t b = b0 + tid; b < nb; b += AMB_CRC_THREADS) dst[b] = amb_pack_byte(ix, bps, rep, b);
+        for (int64_t b = b0 + tid; b < nb; b += AMB_CRC_THREADS) dst[b] = b < nbv ? amb_pack_byte(ix, bps, rep, b) : (uint8_t)0;
         __syncthreads();
         if (in_smem) {
             // decoded bytes to the caller's row (16-byte stores where the row allows)
@@ -1820,7 +1858,7 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
     J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
     // mode 2: analyzeLoopback reads the fixture bytes at a fixed place whatever the header says (modem.js:1056-1066): parsed
     // like mode 1, but the demodulator keeps every symbol exact
-    J.stream = r; J.mode = analyze ? 2 : 1; J.status = 0; J.nsym = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
+    J.stream = r; J.mode = analyze ? 2 : 1; J.status = 0; J.nsym = 0; J.nsym_full = 0; J.pad_ = 0; J.pos = -1; J.len = 0; J.ce_pos = 0; J.data_pos = 0;
     J.coarse = coarse_best[r]; J.fine = 0.0; J.result_pos = -1;
     // analyzeLoopback falls back to the cross-correlation detector (modem.js:983-987), keeps a weak refinement (no 0.1
     // test, :1016) and still reports the channel when no data follows the CE symbol (:1052)
@@ -2000,7 +2038,7 @@ __global__ void k_jobs_chunk(const AmbTables* __restrict__ T, const float* __res
     J.p = frames + (int64_t)r * stride; J.base = 0; J.lo = 0; J.hi = len;
     J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
     J.stream = r; J.mode = 0; J.status = 0; J.pos = 0; J.len = len; J.coarse = 0; J.fine = 0; J.result_pos = -1;
-    J.ce_pos = 2 * (int64_t)T->sym_len; J.data_pos = 3 * (int64_t)T->sym_len; J.nsym = 0;
+    J.ce_pos = 2 * (int64_t)T->sym_len; J.data_pos = 3 * (int64_t)T->sym_len; J.nsym = 0; J.nsym_full = 0; J.pad_ = 0;
     if (J.ce_pos + T->sym_len > len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
     else if (J.data_pos >= len) J.status = AMB_ST_NO_DATA_AFTER_CE;
     else J.nsym = (int32_t)((len - J.data_pos) / T->sym_len);
@@ -2018,7 +2056,7 @@ __global__ void k_jobs_rows(const AmbTables* __restrict__ T, const float* __rest
     J.xf.kind = AMB_XF_NONE; J.xf.mx = 0.f; J.xf.mean = 0.0;
     J.stream = r; J.mode = 0; J.status = 0; J.pos = 0; J.len = len; J.coarse = 0; J.fine = 0; J.result_pos = -1;
     J.ce_pos = 0; J.data_pos = 0;
-    J.nsym = ce_only ? 0 : (int32_t)(len / T->sym_len);
+    J.nsym = ce_only ? 0 : (int32_t)(len / T->sym_len); J.nsym_full = 0; J.pad_ = 0;
     jobs[r] = J;
 }
 
@@ -2038,7 +2076,7 @@ __global__ void k_jobs_stream(const AmbTables* __restrict__ T, AmbStreamGeom g, 
     J.xf.kind = AMB_XF_SCALE; J.xf.mx = 0.f; J.xf.mean = 0.0;
     J.stream = s; J.mode = 0; J.status = R.status; J.pos = R.pos; J.len = R.len; J.coarse = R.coarse; J.fine = R.fine;
     J.result_pos = R.pos;
-    J.ce_pos = R.pos + 2 * (int64_t)T->sym_len; J.data_pos = R.pos + 3 * (int64_t)T->sym_len; J.nsym = 0;
+    J.ce_pos = R.pos + 2 * (int64_t)T->sym_len; J.data_pos = R.pos + 3 * (int64_t)T->sym_len; J.nsym = 0; J.nsym_full = 0; J.pad_ = 0;
     if (R.status == 0) {
         if (2 * (int64_t)T->sym_len + T->sym_len > R.len) J.status = AMB_ST_FRAME_TOO_SHORT_FOR_CE;
         else if (3 * (int64_t)T->sym_len >= R.len) J.status = AMB_ST_NO_DATA_AFTER_CE;

@@ -90,8 +90,10 @@ extern "C" {
  * come from symbols behind the frame (the rest of the collection window or
  * recording, i.e. noise); nothing the reference returns depends on them and
  * they are the float32 pipeline's decisions, which may differ from a
- * float64 demodulation of the same noise.  amb_demodulate (demodulateOFDM
- * itself) is exact for every symbol.
+ * float64 demodulation of the same noise - or zero where those symbols were
+ * not demodulated at all (amb_decode_received_signals reads the extent from
+ * the header and stops there).  amb_demodulate (demodulateOFDM itself) is
+ * exact for every symbol.
  */
 typedef struct amb_frame_result {
     int32_t status;          /* AMB_ST_* */
