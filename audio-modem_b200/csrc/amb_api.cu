@@ -285,11 +285,18 @@ int run_detect(amb_modem* m, const float* d_y, int64_t stride, const int64_t* d_
     // float32 screening first (AMB_METRIC_SCREEN=0 switches it off: comparison runs), then the exact sums on the tiles it leaves
     static const bool screen = !(std::getenv("AMB_METRIC_SCREEN") && std::getenv("AMB_METRIC_SCREEN")[0] == '0');
     CK(m->tile_max32.ensure((size_t)n * tiles * 4));
+    // AMB_METRIC_MERGE=0 (comparison runs): k_metric with a CTA per (recording, tile), then k_argmax
+    static const bool merge = !(std::getenv("AMB_METRIC_MERGE") && std::getenv("AMB_METRIC_MERGE")[0] == '0');
     if (screen) LAUNCH("k_metric_screen", k_metric_screen<<<n * tiles, 256, 0, m->stream>>>(d_y, stride, d_lens, stride, 0.0099f, tiles, m->tile_max32.as<float>()));
-    LAUNCH("k_metric", k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, tiles, m->tile_max.as<double>(),
-                                                                                screen ? m->tile_max32.as<float>() : nullptr));
-    LAUNCH("k_argmax", k_argmax<<<n, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
-                                      m->cbest.as<double>(), m->amb.as<int>(), m->tie_rng.as<int64_t>()));
+    if (screen && merge) {
+        LAUNCH("k_metric_argmax", k_metric_argmax<<<n, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->tile_max32.as<float>(), m->tile_max.as<double>(), tiles,
+                                                                                         m->cidx.as<int64_t>(), m->cbest.as<double>(), m->amb.as<int>(), m->tie_rng.as<int64_t>()));
+    } else {
+        LAUNCH("k_metric", k_metric<<<n * tiles, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, tiles, m->tile_max.as<double>(),
+                                                                                    screen ? m->tile_max32.as<float>() : nullptr));
+        LAUNCH("k_argmax", k_argmax<<<n, 256, AMB_SCAN_SMEM, m->stream>>>(d_y, stride, d_lens, stride, 0.01, m->tile_max.as<double>(), tiles, m->cidx.as<int64_t>(),
+                                          m->cbest.as<double>(), m->amb.as<int>(), m->tie_rng.as<int64_t>()));
+    }
     LAUNCH("k_replay", k_replay<<<blocks_for(n, 4), 128, 0, m->stream>>>(d_y, stride, d_lens, stride, n, 0.01, m->amb.as<int>(), m->tie_rng.as<int64_t>(),
                                                                        m->cidx.as<int64_t>(), m->cbest.as<double>()));
     return AMB_OK;
@@ -422,6 +429,7 @@ int amb_create(amb_modem** out, int device, int config, int constellation, int r
     cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_DEMOD_SMEM);
     cudaFuncSetAttribute(k_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
+    cudaFuncSetAttribute(k_metric_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_SCAN_SMEM);
     cudaFuncSetAttribute(k_tx_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
     cudaFuncSetAttribute(k_modulate, cudaFuncAttributeMaxDynamicSharedMemorySize, AMB_TX_SMEM);
     *out = m;

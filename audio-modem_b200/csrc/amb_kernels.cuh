@@ -1636,49 +1636,73 @@ __global__ void __launch_bounds__(256) k_metric_screen(const float* __restrict__
     float best = -1.f;
     const float* src = y + (int64_t)r * stride;
     if (q0 - AMB_HALO + 1 + 2 * AMB_HALF <= n) {
-        for (int sub = warp; sub < AMB_TILE / 256; sub += 8) {
-            const int64_t d0 = q0 - 511 + 256 * sub;                 // first window of the sub-tile (= 1 mod 4: one float past a 16-byte boundary)
-            if (d0 + 2 * AMB_HALF > n) break;
+        // a warp takes two CONSECUTIVE sub-tiles of 256 windows: the second one reuses two of the first one's three sample
+        // segments, their partial sums and their scans (same values as computing them again), and loads one new segment
+        const bool fast_ok = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        for (int pair = warp; pair < AMB_TILE / 512; pair += 8) {
             float x[3][8];
-            const int64_t g0 = d0 + 8 * lane;
-            if (d0 >= 1 && d0 + 768 + 8 <= n && ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-                const float* pa = src + (g0 - 1);
-#pragma unroll
-                for (int seg = 0; seg < 3; seg++) {
-                    const float4 u = *reinterpret_cast<const float4*>(pa + 256 * seg), v = *reinterpret_cast<const float4*>(pa + 256 * seg + 4);
-                    x[seg][0] = u.y; x[seg][1] = u.z; x[seg][2] = u.w; x[seg][3] = v.x; x[seg][4] = v.y; x[seg][5] = v.z; x[seg][6] = v.w;
-                    x[seg][7] = pa[256 * seg + 8];
-                }
-            } else {
-#pragma unroll
-                for (int seg = 0; seg < 3; seg++)
-#pragma unroll
-                    for (int k = 0; k < 8; k++) { const int64_t a = g0 + 256 * seg + k; x[seg][k] = (a >= 0 && a < n) ? src[a] : 0.f; }
-            }
             float q0s = 0.f, q1s = 0.f, q2s = 0.f, t0s = 0.f, t1s = 0.f;
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f, f0 = 0.f, f1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                q0s = fmaf(x[0][k], x[0][k], q0s); q1s = fmaf(x[1][k], x[1][k], q1s); q2s = fmaf(x[2][k], x[2][k], q2s);
-                t0s = fmaf(x[0][k], x[1][k], t0s); t1s = fmaf(x[1][k], x[2][k], t1s);
-            }
-            float e0 = q0s, e1 = q1s, e2 = q2s, f0 = t0s, f1 = t1s;
+            for (int half = 0; half < 2; half++) {
+                const int sub = 2 * pair + half;
+                const int64_t d0 = q0 - 511 + 256 * sub;             // first window of the sub-tile (= 1 mod 4: one float past a 16-byte boundary)
+                if (d0 + 2 * AMB_HALF > n) break;
+                const int64_t g0 = d0 + 8 * lane;
+                const int seg_lo = half == 0 ? 0 : 2;                // segments to load: all three, or only the new one
+                if (half == 1) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float u0 = __shfl_up_sync(0xffffffffu, e0, o), u1 = __shfl_up_sync(0xffffffffu, e1, o), u2 = __shfl_up_sync(0xffffffffu, e2, o);
-                const float v0 = __shfl_up_sync(0xffffffffu, f0, o), v1 = __shfl_up_sync(0xffffffffu, f1, o);
-                if (lane >= o) { e0 += u0; e1 += u1; e2 += u2; f0 += v0; f1 += v1; }
-            }
-            const float Q0 = __shfl_sync(0xffffffffu, e0, 31), Q1 = __shfl_sync(0xffffffffu, e1, 31), T0 = __shfl_sync(0xffffffffu, f0, 31);
-            // window sums at the lane's first window as (suffix of the first segment) + (prefix of the next): no large prefix is
-            // ever subtracted from another
-            float A = (Q0 - (e0 - q0s)) + (e1 - q1s), B = (Q1 - (e1 - q1s)) + (e2 - q2s), P = (T0 - (f0 - t0s)) + (f1 - t1s);
+                    for (int k = 0; k < 8; k++) { x[0][k] = x[1][k]; x[1][k] = x[2][k]; }
+                    q0s = q1s; q1s = q2s; t0s = t1s; e0 = e1; e1 = e2; f0 = f1;
+                }
+                if (d0 >= 1 && d0 + 768 + 8 <= n && fast_ok) {
+                    const float* pa = src + (g0 - 1);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int64_t d = g0 + k;
-                if (d >= 0 && d + 2 * AMB_HALF <= n && A > min_energy && B > min_energy) best = fmaxf(best, __fdividef(P * P, A * B));
-                A += x[1][k] * x[1][k] - x[0][k] * x[0][k];
-                B += x[2][k] * x[2][k] - x[1][k] * x[1][k];
-                P += x[1][k] * x[2][k] - x[0][k] * x[1][k];
+                    for (int seg = 0; seg < 3; seg++) {
+                        if (seg < seg_lo) continue;
+                        const float4 u = *reinterpret_cast<const float4*>(pa + 256 * seg), v = *reinterpret_cast<const float4*>(pa + 256 * seg + 4);
+                        x[seg][0] = u.y; x[seg][1] = u.z; x[seg][2] = u.w; x[seg][3] = v.x; x[seg][4] = v.y; x[seg][5] = v.z; x[seg][6] = v.w;
+                        x[seg][7] = pa[256 * seg + 8];
+                    }
+                } else {
+#pragma unroll
+                    for (int seg = 0; seg < 3; seg++) {
+                        if (seg < seg_lo) continue;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { const int64_t a = g0 + 256 * seg + k; x[seg][k] = (a >= 0 && a < n) ? src[a] : 0.f; }
+                    }
+                }
+                if (half == 0) {
+                    q0s = 0.f; q1s = 0.f; t0s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { q0s = fmaf(x[0][k], x[0][k], q0s); q1s = fmaf(x[1][k], x[1][k], q1s); t0s = fmaf(x[0][k], x[1][k], t0s); }
+                }
+                q2s = 0.f; t1s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { q2s = fmaf(x[2][k], x[2][k], q2s); t1s = fmaf(x[1][k], x[2][k], t1s); }
+                if (half == 0) { e0 = q0s; e1 = q1s; f0 = t0s; }
+                e2 = q2s; f1 = t1s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float u2 = __shfl_up_sync(0xffffffffu, e2, o), v1 = __shfl_up_sync(0xffffffffu, f1, o);
+                    if (lane >= o) { e2 += u2; f1 += v1; }
+                    if (half == 0) {
+                        const float u0 = __shfl_up_sync(0xffffffffu, e0, o), u1 = __shfl_up_sync(0xffffffffu, e1, o), v0 = __shfl_up_sync(0xffffffffu, f0, o);
+                        if (lane >= o) { e0 += u0; e1 += u1; f0 += v0; }
+                    }
+                }
+                const float Q0 = __shfl_sync(0xffffffffu, e0, 31), Q1 = __shfl_sync(0xffffffffu, e1, 31), T0 = __shfl_sync(0xffffffffu, f0, 31);
+                // window sums at the lane's first window as (suffix of the first segment) + (prefix of the next): no large prefix is
+                // ever subtracted from another
+                float A = (Q0 - (e0 - q0s)) + (e1 - q1s), B = (Q1 - (e1 - q1s)) + (e2 - q2s), P = (T0 - (f0 - t0s)) + (f1 - t1s);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int64_t d = g0 + k;
+                    if (d >= 0 && d + 2 * AMB_HALF <= n && A > min_energy && B > min_energy) best = fmaxf(best, __fdividef(P * P, A * B));
+                    A += x[1][k] * x[1][k] - x[0][k] * x[0][k];
+                    B += x[2][k] * x[2][k] - x[1][k] * x[1][k];
+                    P += x[1][k] * x[2][k] - x[0][k] * x[1][k];
+                }
             }
         }
     }
@@ -1737,6 +1761,84 @@ __global__ void __launch_bounds__(256) k_metric(const float* __restrict__ y, int
 // is decided in the reference by its own rounding sequence: exactly equal values on an even-bin plateau (first
 // wins), last-ulp differences on an odd-bin plateau after DC removal.  `ambiguous` is then set, tie_range gets the
 // first and last tied offset, and k_replay settles it with the reference's own sequential recurrence.
+// k_metric and k_argmax in one launch, a CTA per recording (the screening pass has run): k_metric is launched with a CTA per
+// (recording, tile) and all but one or two of a recording's tiles leave at once - 430,000 CTAs for the 10,000 recordings of C3,
+// 1.7 ms of mostly launch traffic.  Here the CTA finds the recording's screening maximum, evaluates the tiles within the
+// margin exactly (same routine, same values as k_metric), and goes on as k_argmax does.
+__global__ void __launch_bounds__(256) k_metric_argmax(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
+                                                        int64_t n_default, double min_energy, const float* __restrict__ tile_max32,
+                                                        double* __restrict__ tile_max, int tiles,
+                                                        int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous,
+                                                        int64_t* __restrict__ tie_range /*[n][2]*/) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AmbTileScratch w = amb_tile_scratch(smem_raw);
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int64_t n = lens ? lens[r] : n_default;
+    __shared__ double sbest;
+    __shared__ long long sfirst, slast, scount;
+    __shared__ float sred[8];
+    __shared__ double red[8];
+    if (tid == 0) { sbest = -1.0; sfirst = (long long)1 << 62; slast = -1; scount = 0; }
+    __syncthreads();
+    if (n < 2 * AMB_HALF) { if (tid == 0) { idx_out[r] = -1; best_out[r] = 0.0; ambiguous[r] = 0; } return; }
+    const int used = (int)((n - 1) / AMB_TILE) + 1 < tiles ? (int)((n - 1) / AMB_TILE) + 1 : tiles;
+    const float* t32 = tile_max32 + (int64_t)r * tiles;
+    double* tmx = tile_max + (int64_t)r * tiles;
+    // the recording's screening maximum
+    float b32 = -1.f;
+    for (int t = tid; t < tiles; t += 256) b32 = fmaxf(b32, t32[t]);
+    b32 = warp_maxf(b32);
+    if ((tid & 31) == 0) sred[tid >> 5] = b32;
+    __syncthreads();
+    for (int wv = 0; wv < 8; wv++) b32 = fmaxf(b32, sred[wv]);
+    const float keep = b32 * (1.f - 2e-3f) - 1e-6f;
+    // exact per-tile maxima of the tiles that can hold the maximum (or a tie with it); -1 for the others
+    double b = -1.0;
+    for (int t = 0; t < used; t++) {
+        const int64_t q0 = (int64_t)t * AMB_TILE;
+        const bool inside = !(q0 - AMB_HALO + 1 + 2 * AMB_HALF > n);
+        if (!inside || !(t32[t] >= keep)) { if (tid == 0) tmx[t] = -1.0; continue; }       // (uniform over the CTA)
+        __syncthreads();
+        amb_tile_prefix(w, y + (int64_t)r * stride, n, q0);
+        double best = -1.0;
+        for (int jj = 0; jj < AMB_TILE / 256; jj++) {
+            int64_t d; double m;
+            if (amb_tile_metric(w, jj * 256 + 1 + tid, q0, n, min_energy, &d, &m)) best = fmax(best, m);
+        }
+        best = warp_maxd(best);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = best;
+        __syncthreads();
+        for (int wv = 0; wv < 8; wv++) best = fmax(best, red[wv]);
+        if (tid == 0) tmx[t] = best;
+        b = fmax(b, best);
+    }
+    for (int t = used + tid; t < tiles; t += 256) tmx[t] = -1.0;
+    __syncthreads();
+    const double best = b;                               // (the same value in every thread)
+    if (!(best > 0.0)) { if (tid == 0) { idx_out[r] = -1; best_out[r] = 0.0; ambiguous[r] = 0; } return; }
+    const double thr = best * (1.0 - 1e-9);
+    long long first = (long long)1 << 62, last = -1, count = 0;
+    for (int t = 0; t < used; t++) {
+        if (tmx[t] < thr) continue;                      // (uniform over the CTA: written before the barrier above)
+        const int64_t q0 = (int64_t)t * AMB_TILE;
+        __syncthreads();
+        amb_tile_prefix(w, y + (int64_t)r * stride, n, q0);
+        for (int jj = 0; jj < AMB_TILE / 256; jj++) {
+            int64_t d; double m;
+            if (amb_tile_metric(w, jj * 256 + 1 + tid, q0, n, min_energy, &d, &m) && m >= thr) { if (d < first) first = d; if (d > last) last = d; count++; }
+        }
+    }
+    atomicMin(&sfirst, first); atomicMax(&slast, last); atomicAdd((unsigned long long*)&scount, (unsigned long long)count);
+    __syncthreads();
+    if (tid == 0) {
+        best_out[r] = best;
+        ambiguous[r] = scount > 1 ? 1 : 0;
+        tie_range[2 * r] = (int64_t)sfirst; tie_range[2 * r + 1] = (int64_t)slast;
+        idx_out[r] = best > 0.5 ? (int64_t)sfirst : -1;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_argmax(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens,
                                                  int64_t n_default, double min_energy, const double* __restrict__ tile_max, int tiles,
                                                  int64_t* __restrict__ idx_out, double* __restrict__ best_out, int* __restrict__ ambiguous,
