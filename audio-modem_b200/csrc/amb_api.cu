@@ -777,7 +777,7 @@ int amb_decode_received_signals(amb_modem* m, const float* x, int64_t stride, co
     if ((rc = run_apply(m, d_x, stride, d_lens, n, max_len, m->norm.as<float>()))) return rc;
     if ((rc = run_detect(m, m->norm.as<float>(), stride, d_lens, n, max_len))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
+    LAUNCH("k_refine_batch", k_refine_batch<<<n, 128, AMB_TEAM_STAGE_FLOATS * 4, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
                                                              m->cbest.as<double>(), nullptr, 0, m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(max_len / T.sym_len);
     if ((rc = run_demod_parse(m, n, max_nsym, false, d_res, d_bytes, bytes_stride, true))) return rc;
@@ -810,7 +810,7 @@ int amb_analyze_loopback(amb_modem* m, const float* x, int64_t stride, const int
     double* d_xbest = reinterpret_cast<double*>(d_xidx + n);
     if ((rc = run_detect_xcorr(m, m->norm.as<float>(), stride, d_lens, n, d_xidx, d_xbest))) return rc;
     CK(m->jobs.ensure((size_t)n * sizeof(AmbJob)));
-    LAUNCH("k_refine_batch", k_refine_batch<<<blocks_for(n, 4), 128, 0, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
+    LAUNCH("k_refine_batch", k_refine_batch<<<n, 128, AMB_TEAM_STAGE_FLOATS * 4, m->stream>>>(m->d_tables, m->norm.as<float>(), stride, d_lens, stride, n, m->cidx.as<int64_t>(),
                                                              m->cbest.as<double>(), d_xidx, 1, m->jobs.as<AmbJob>()));
     const int max_nsym = (int)(max_len / T.sym_len);
     if ((rc = run_demod_parse(m, n, max_nsym, false, m->out_res.as<amb_frame_result>(), m->out_bytes.as<uint8_t>(), bytes_stride))) return rc;

@@ -1949,10 +1949,14 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
                                                        const int64_t* __restrict__ lens, int64_t n_default, int n,
                                                        const int64_t* __restrict__ coarse_idx, const double* __restrict__ coarse_best,
                                                        const int64_t* __restrict__ alt_idx, int analyze, AmbJob* __restrict__ jobs) {
+    // A CTA per recording: its four warps run the same code on the same recording as a team (as the long-capture walker does)
+    // and share the one long data-parallel step, the float32 screening of the 2 x 3 CP + 1 offsets (amb_xcorr_screen_team:
+    // samples and taps staged in dynamic shared memory, 16 offsets per thread); warp 0 writes the job.
     __shared__ double scratch[4][64];
-    __shared__ float vbuf[4][2 * 768 + 8];          // float32 screening values of the offsets c - 3 CP .. c + 3 CP (at most 1537)
+    __shared__ float vbuf[AMB_TEAM_VCAP];           // float32 screening values of the offsets c - 3 CP .. c + 3 CP (at most 1537)
+    extern __shared__ __align__(16) unsigned char refine_dyn[];         // AMB_TEAM_STAGE_FLOATS floats
     const int warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * 4 + warp;
+    const int r = blockIdx.x;
     if (r >= n) return;
     const int64_t len = lens ? lens[r] : n_default;
     AmbJob J;
@@ -1976,7 +1980,8 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
         // path, amb_fine_xcorr_store, without a store): argmax and metric are those of the all-float64 loop of modem.js:571-586
         AmbWalkGeom G;
         memset(&G, 0, sizeof(G));
-        double best = amb_fine_xcorr_store(T, G, sig, fs, fe, c, scratch[warp], &pos, vbuf[warp], (int)(sizeof(vbuf[0]) / sizeof(float)));
+        G.team_n = 4; G.team_rank = warp; G.team_vbuf = vbuf; G.team_vcap = AMB_TEAM_VCAP; G.team_stage = reinterpret_cast<float*>(refine_dyn);
+        double best = amb_fine_xcorr_store(T, G, sig, fs, fe, c, scratch[warp], &pos, vbuf, AMB_TEAM_VCAP);
         best = amb_resolve_fine(T, sig, pos, best);          // (a single surviving offset: its exact metric is formed here)
         J.fine = best;
         if (!analyze && best < 0.1) J.status = AMB_ST_PREAMBLE_LOW_CORRELATION;
@@ -1989,7 +1994,7 @@ __global__ void __launch_bounds__(128) k_refine_batch(const AmbTables* __restric
             else J.nsym = (int32_t)((len - J.data_pos) / plen);
         }
     }
-    if ((threadIdx.x & 31) == 0) jobs[r] = J;
+    if (threadIdx.x == 0) jobs[r] = J;
 }
 
 // analyzeLoopback's report (modem.js:1016-1081) for recordings refined by k_refine_batch(analyze) and decoded by the
