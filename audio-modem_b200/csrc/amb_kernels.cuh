@@ -1894,7 +1894,10 @@ __global__ void __launch_bounds__(256) k_argmax(const float* __restrict__ y, int
 __global__ void __launch_bounds__(128) k_replay(const float* __restrict__ y, int64_t stride, const int64_t* __restrict__ lens, int64_t n_default, int n,
                                                  double min_energy, const int* __restrict__ ambiguous, const int64_t* __restrict__ tie_range,
                                                  int64_t* __restrict__ idx_out, double* __restrict__ best_out) {
-    __shared__ double sdp[4][32], sda[4][32], sdb[4][32];
+    // (the update terms of 32 positions are formed by the lanes, one lane carries the three chains of additions in the reference's
+    // order; the samples of the NEXT 32 positions are loaded before that lane starts on the current ones, so their latency hides
+    // behind its additions - a lone warp has nothing else to hide it with)
+    __shared__ double sdp[4][2][32], sda[4][2][32], sdb[4][2][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 4 + warp;
     if (r >= n || !ambiguous[r]) return;
@@ -1910,20 +1913,29 @@ __global__ void __launch_bounds__(128) k_replay(const float* __restrict__ y, int
     double best = 0; int64_t best_idx = -1;
     const int64_t end = len - 2 * AMB_HALF;
     const int64_t lo = tie_range[2 * r], hi = tie_range[2 * r + 1] < end ? tie_range[2 * r + 1] : end;
-    for (int64_t d0 = 0; d0 <= hi; d0 += 32) {
-        const int64_t d = d0 + lane;
+    auto terms = [&](int64_t d, int buf) {
         if (d < end) {
             const double ao = s[d], mid = s[d + AMB_HALF], bi = s[d + 2 * AMB_HALF];
-            sdp[warp][lane] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
-            sda[warp][lane] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
-            sdb[warp][lane] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
+            sdp[warp][buf][lane] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
+            sda[warp][buf][lane] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
+            sdb[warp][buf][lane] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
         }
-        __syncwarp();
+    };
+    if (hi >= 0) terms(lane, 0);
+    __syncwarp();
+    int buf = 0;
+    for (int64_t d0 = 0; d0 <= hi; d0 += 32, buf ^= 1) {
+        // samples of the next round: in flight while lane 0 adds
+        const int64_t dn = d0 + 32 + lane;
+        const bool have_next = d0 + 32 <= hi && dn < end;
+        float n_ao = 0.f, n_mid = 0.f, n_bi = 0.f;
+        if (have_next) { n_ao = s[dn]; n_mid = s[dn + AMB_HALF]; n_bi = s[dn + 2 * AMB_HALF]; }
         if (lane == 0) {
+            const double* tp = sdp[warp][buf]; const double* ta = sda[warp][buf]; const double* tb = sdb[warp][buf];
             const int cnt = (int)(hi - d0 + 1 < 32 ? hi - d0 + 1 : 32);
             if (d0 + 31 < lo) {
 #pragma unroll 8
-                for (int k = 0; k < 32; k++) { p = amb_add(p, sdp[warp][k]); ra = amb_add(ra, sda[warp][k]); rb = amb_add(rb, sdb[warp][k]); }
+                for (int k = 0; k < 32; k++) { p = amb_add(p, tp[k]); ra = amb_add(ra, ta[k]); rb = amb_add(rb, tb[k]); }
             } else {
                 for (int k = 0; k < cnt; k++) {
                     const int64_t dd = d0 + k;
@@ -1931,9 +1943,15 @@ __global__ void __launch_bounds__(128) k_replay(const float* __restrict__ y, int
                         const double m = amb_div(amb_mul(p, p), amb_mul(ra, rb));
                         if (m > best) { best = m; best_idx = dd; }
                     }
-                    if (dd < end) { p = amb_add(p, sdp[warp][k]); ra = amb_add(ra, sda[warp][k]); rb = amb_add(rb, sdb[warp][k]); }
+                    if (dd < end) { p = amb_add(p, tp[k]); ra = amb_add(ra, ta[k]); rb = amb_add(rb, tb[k]); }
                 }
             }
+        }
+        if (have_next) {
+            const double ao = n_ao, mid = n_mid, bi = n_bi;
+            sdp[warp][buf ^ 1][lane] = amb_sub(amb_mul(mid, bi), amb_mul(ao, mid));
+            sda[warp][buf ^ 1][lane] = amb_sub(amb_mul(mid, mid), amb_mul(ao, ao));
+            sdb[warp][buf ^ 1][lane] = amb_sub(amb_mul(bi, bi), amb_mul(mid, mid));
         }
         __syncwarp();
     }
