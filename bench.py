@@ -842,7 +842,7 @@ def run_c4(ctx, clocks):
     e2e_s = time.perf_counter() - t0
     clocks.mark_end()
     d2h = (e2e_frames // e2e_steps) * (m.bytes_stride + 88)
-    h2d_ceiling = h2d_copy_ceiling(ctx, host.ptr, 4 * ns * push)
+    h2d_ceiling = h2d_copy_ceiling(ctx, host.ptr, 4 * N)
     m.stream_close()
     del hx
     host.free()
@@ -861,6 +861,7 @@ def run_c4(ctx, clocks):
               "note": "per-kernel roofline uses 4 B per scanned sample for every kernel (the scan dominates by construction)"}
     line = base_line(ctx, "c4", value, total_ms, steps, warmup, tot["payloadBytes"], config, None,
                      e2e_obj(world * e2e_steps * N / e2e_s_max / 1e6, 4 * N, d2h, e2e_steps, e2e_s_max, 1), tot["launches"], roof)
+    line["e2e"]["h2d_copy_ceiling_gb_per_s_per_rank"] = h2d_ceiling      # plain cudaMemcpyAsync of the same page-locked buffer, all ranks at once
     line["walker"] = iters
     line["check"] = {"frames_found_per_step": frames_found / steps, "counters_after": c1}
     return line
