@@ -854,6 +854,7 @@ int amb_stream_open(amb_modem* m, int n_streams, int block_len, int64_t max_push
     {
         size_t free_b = 0, total_b = 0;
         double budget = 48e9;
+        if (std::getenv("AMB_ARENA_GB") && std::atof(std::getenv("AMB_ARENA_GB")) > 0.0) budget = std::atof(std::getenv("AMB_ARENA_GB")) * 1e9;      // (development: arena budget)
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)free_b / 4.0 < budget) budget = (double)free_b / 4.0;
         const double per_stream = budget / ((double)n_streams * 4.0) - (double)m->hist;
         const int64_t fit = per_stream > 0 ? (int64_t)(per_stream / (double)max_push) : 0;

@@ -234,6 +234,37 @@ def test_decode_received_signals_batch(O, modems, mode):
         assert objs[i] == O.decodeReceivedSignal(cfg, r, mod, rep), (mode, i)
 
 
+@pytest.mark.parametrize("mode", ["BPSK-ACOUSTIC", "BPSK-REPEAT", "16-QAM"])
+def test_decode_received_signals_stop_at_the_frames_extent(O, modems, mode):
+    """Recordings much longer than the frame they hold (BASELINE config 3: 88,260 samples around a frame of ~30,000): the header
+    symbols are demodulated first, the extent is read from the header, and only the symbols inside it are demodulated
+    (k_demod_limit / k_extent).  Every result field and every byte the parsers consume equal the oracle's, n_bytes is the
+    length of the whole decoded recording, and the bytes behind the extent are 0."""
+    from helpers import frame_extent
+
+    cfg, mod, rep, _ = MODES[mode]
+    m = modems(mode)
+    rng = np.random.default_rng(9)
+    recs = []
+    for i in range(5):
+        tx = O.buildTransmitSignal(cfg, bytes(O.randomBytes(2000 + i, 40 + 90 * i)), mod, "r%d.bin" % i, rep)
+        p = O.power(tx[13230 if cfg == "standard" else 22050:][:5000])
+        tail = (rng.standard_normal(2 * len(tx) + 997 * i) * np.sqrt(p / 100.0)).astype(np.float32)      # noise at -20 dB behind the frame
+        recs.append(np.concatenate([O.addAwgn(tx, np.sqrt(p / 100.0), 70 + i), tail]))
+    got = m.decode_received_signals(recs, raw=True)
+    for i, r in enumerate(recs):
+        r1, b1 = O.decodeReceivedSignal(cfg, r, mod, rep, raw=True)
+        r2, b2 = got[i]
+        assert results_equal(r1, b1, r2, b2, metric_tol=1e-9) == [], (mode, i)
+        assert r1.status == 0 and r2.n_bytes == r1.n_bytes == len(b1), (mode, i, r1.status, r2.n_bytes, len(b1))
+        ext = frame_extent(r1)
+        b2 = np.asarray(b2, np.uint8)
+        assert len(b1) > 2 * ext                                           # (the recording really is much longer than its frame)
+        # behind the extent, rounded up to whole symbols, nothing was demodulated
+        sym_bytes = -(-O.config(cfg)["NUM_DATA_SUBS"] * {"BPSK": 1, "QPSK": 2, "QAM16": 4}[mod] // (8 * rep))       # bytes per OFDM symbol, rounded up
+        assert not b2[ext + 2 * sym_bytes + 16:].any(), (mode, i, ext)
+
+
 def _loopback_cases(O, cfg, mod, rep):
     """generateTestSignal (modem.js:913-975) clean and through channels, plus the early-return and fallback cases"""
     t = O.generateTestSignal(cfg, mod, rep)["signal"]

@@ -56,9 +56,27 @@ for ip, p0 in enumerate(range(0, n, push)):
         m.profile(True)
     t1 = time.perf_counter()
     l0 = m.kernel_launches
+    stats_lib = os.environ.get("AMB_LIB", "").endswith("stats.so")
+    if stats_lib:
+        import ctypes as C
+        import numpy as np
+        tr = np.zeros((16384, 24), np.uint64)
+        m._L.amb_debug_read(m._h, 2, C.c_void_p(tr.ctypes.data), tr.nbytes)          # (reading resets the trace)
     frames += m.stream_push(x[:, p0:p0 + push], device_results=(d_res, d_bytes))
     m.synchronize()
     per.append((round((time.perf_counter() - t1) * 1e3, 2), m.kernel_launches - l0))
+    if stats_lib and ip >= 2:
+        rows = int(m._L.amb_debug_read(m._h, 2, C.c_void_p(tr.ctypes.data), tr.nbytes))
+        t = tr[:max(0, min(rows, 16384))].astype(np.int64)
+        t = t[t[:, 1] != 9]
+        print(f"push {ip}: {rows} trace rows")
+        for mode in sorted(set(t[:, 1].tolist())):
+            for has in (0, 1):
+                sel = t[(t[:, 1] == mode) & (t[:, 3] == has)]
+                if len(sel):
+                    print("   mode %d (%s) has %d: %5d walks, cycles mean %7.0f max %7d | eval %6.0f refine %6.0f skip %6.0f scan %6.0f | rows %.2f direct %.2f scancalls %.2f" %
+                          (mode, {0: "A run", 1: "B link", 2: "A first"}.get(mode, "?"), has, len(sel), sel[:, 6].mean(), sel[:, 6].max(), sel[:, 17].mean(), sel[:, 18].mean(),
+                           sel[:, 19].mean(), sel[:, 20].mean(), sel[:, 8].mean(), sel[:, 9].mean(), sel[:, 14].mean()))
 dt = time.perf_counter() - t0
 prof = m.profile_read()
 m.profile(False)
