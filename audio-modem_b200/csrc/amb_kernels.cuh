@@ -2984,7 +2984,13 @@ __global__ void __launch_bounds__(128, TEAM ? 4 : AMB_WALK_CTAS) k_link_walk(con
     // data-parallel step of such a walk (1,537 offsets x 768 taps in the narrowband config), is shared between them.
     constexpr bool team = TEAM;
     const bool writer = !team || warp == 0;
-    for (int f = team ? blockIdx.x : blockIdx.x * 4 + warp; f < total; f += team ? gridDim.x : gridDim.x * 4) {
+    int round = 0;
+    for (int f0 = team ? blockIdx.x : blockIdx.x * 4 + warp; f0 < total; f0 += team ? gridDim.x : gridDim.x * 4, round++) {
+        // Neighbouring indices change places in every other round: with two runs per stream and push (many streams, short
+        // pushes) the even indices are the runs phase A does not walk at all and the odd ones full walks, and a warp whose
+        // index keeps its parity over the rounds would collect all of the one kind (measured: a third of phase A idle).
+        int f = f0;
+        if (!team && (round & 1) && (f ^ 1) < total) f ^= 1;
         const bool first = mode == 0 && f >= total_runs;
         int s, i = 0;
         if (first) s = todo ? todo[f - total_runs] : f - total_runs;
@@ -3036,6 +3042,15 @@ __global__ void __launch_bounds__(128, TEAM ? 4 : AMB_WALK_CTAS) k_link_walk(con
                 else {
                     // the first run of the push: the frame before it is the one the stream is collecting (or has just finished)
                     const AmbStreamState& cs = states[s];
+                    if (cs.state == AMB_RX_IDLE && !(g.cold_tag != nullptr)) {
+                        // ... unless the stream is scanning: then the pass's first link (walked next to phase A, from the carried
+                        // state) runs into this very run and decodes its frame, and the chain starts behind it - this walk would
+                        // be thrown away (many streams with short pushes: a third of phase A).  Should the chain want the run after
+                        // all (the first link ended at a failed refine before it), phase B walks it: hasA = 0 never verifies.
+                        if (lane == 0 && writer) { AmbStartA sa; sa.pos = -1; sa.call = -1; sa.false_pos = 0; L.startA[f] = sa; L.endA[f] = st; L.hasA[f] = 0; }
+                        __syncwarp();
+                        continue;
+                    }
                     if (cs.state == AMB_RX_COLLECT) { e = cs.frame_end; call_min = cs.next_call + 1; }
                     else if (cs.state == AMB_RX_IDLE && !cs.ac_init) { e = cs.ac_scan_pos; call_min = cs.next_call; }
                     if (e > rr[i].last_pos || e < rr[i].first_pos - 32 * g.block_len) e = -1;
