@@ -3,7 +3,7 @@
 # Logs go to gpurun_out/tests_<group>.log; a summary line per group is printed.
 mkdir -p gpurun_out
 groups=("crc32 or preprocess or extension or api_argument or selftest" "detect_preamble" "estimate_channel" "decode_chunk_frames or fast_demodulator"
-        "decode_received" "stream_matches_oracle" "stream_single_block or stream_block_alignment" "stream_edge_cases or second_metadata"
+        "decode_received" "stream_matches_oracle" "stream_single_block or stream_block_alignment" "stream_edge_cases or second_metadata or phase_a_walks"
         "many_streams or round_trip" "tx_frames" "golden")
 i=0
 for g in "${groups[@]}"; do
